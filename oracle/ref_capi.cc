@@ -1,0 +1,255 @@
+// oracle/_ref/librl_ref.so — the UNMODIFIED reference headers, compiled where they lie under
+// /root/reference, behind a flat C API.  TEST INFRASTRUCTURE ONLY: only tests/, smoke() and
+// bench.py's cpu_baseline / --impl reference legs may load this library.
+//
+// Nothing from the reference is copied: this file only #includes its headers
+// (-I/root/reference, -I/root/reference/RandBLAS) against the shim BLAS++/LAPACK++/Random123
+// headers in oracle/shim/ (ours), and forwards.  Every entry point names the reference symbol
+// it calls.  The same signatures (prefix rlo_) are exported by the independent restatement in
+// oracle/rl_oracle.c + oracle/rl_oracle.py, and (prefix rlb200_, device pointers) by the product.
+#include <RandBLAS.hh>
+#include "RandLAPACK/rl_blaspp.hh"
+#include "RandLAPACK/rl_lapackpp.hh"
+#include "RandLAPACK/rl_exceptions.hh"
+#include "RandLAPACK/misc/rl_util.hh"
+#include "RandLAPACK/comps/rl_orth.hh"
+#include "RandLAPACK/comps/rl_rs.hh"
+#include "RandLAPACK/comps/rl_rf.hh"
+#include "RandLAPACK/comps/rl_qb.hh"
+#include "RandLAPACK/drivers/rl_rsvd.hh"
+#include "RandLAPACK/drivers/rl_cqrrpt.hh"
+#include "RandLAPACK/drivers/rl_bqrrp.hh"
+#include "RandLAPACK/testing/rl_gen.hh"
+
+#include <cstring>
+#include <memory>
+#include <chrono>
+
+#include "oracle_capi.h"
+
+using RNG = r123::Philox4x32;
+using State = RandBLAS::RNGState<RNG>;
+
+static State load_state(const uint32_t s[6]) {
+    State st;
+    for (int i = 0; i < 4; ++i) st.counter.v[i] = s[i];
+    for (int i = 0; i < 2; ++i) st.key.v[i] = s[4 + i];
+    return st;
+}
+static void store_state(const State& st, uint32_t s[6]) {
+    for (int i = 0; i < 4; ++i) s[i] = st.counter.v[i];
+    for (int i = 0; i < 2; ++i) s[4 + i] = st.key.v[i];
+}
+
+template <typename T>
+static std::unique_ptr<RandLAPACK::Stabilization<T>> make_stab(int kind, bool cond_check) {
+    switch (kind) {
+        case RL_STAB_PLUL:    return std::make_unique<RandLAPACK::PLUL<T>>(cond_check, false);
+        case RL_STAB_CHOLQRQ: return std::make_unique<RandLAPACK::CholQRQ<T>>(cond_check, false);
+        case RL_STAB_HQRQ:    return std::make_unique<RandLAPACK::HQRQ<T>>(cond_check, false);
+    }
+    throw std::runtime_error("bad stabiliser kind");
+}
+
+// the canonical stack of test/drivers/test_rsvd.cc:68-93
+template <typename T>
+struct Stack {
+    std::unique_ptr<RandLAPACK::Stabilization<T>> stab, orth_rf, orth_qb;
+    RandLAPACK::RS<T, RNG> rs;
+    RandLAPACK::RF<T, RNG> rf;
+    RandLAPACK::QB<T, RNG> qb;
+    RandLAPACK::RSVD<T, RNG> rsvd;
+    explicit Stack(const rl_stack_opts& o)
+        : stab(make_stab<T>(o.stab, o.cond_check)), orth_rf(make_stab<T>(o.orth_rf, o.cond_check)),
+          orth_qb(make_stab<T>(o.orth_qb, o.cond_check)),
+          rs(*stab, o.passes_over_data, o.passes_per_stab, false, o.cond_check),
+          rf(rs, *orth_rf, false, o.cond_check), qb(rf, *orth_qb, false, o.orth_check), rsvd(qb, o.block_sz) {}
+};
+
+#define RL_TRY try {
+#define RL_CATCH } catch (const std::exception& e) { std::snprintf(g_err, sizeof g_err, "%s", e.what()); return RL_ERR_EXCEPTION; }
+static thread_local char g_err[512];
+
+template <typename T>
+static int fill_dense_impl(int64_t n_rows, int64_t n_cols, int family, int major_axis, int layout, int64_t sub_rows,
+                           int64_t sub_cols, int64_t ro, int64_t co, T* buff, uint32_t state[6]) {
+    RL_TRY
+    RandBLAS::DenseDist D(n_rows, n_cols, family == RL_FAMILY_UNIFORM ? RandBLAS::ScalarDist::Uniform : RandBLAS::ScalarDist::Gaussian,
+                          major_axis == RL_AXIS_SHORT ? RandBLAS::Axis::Short : RandBLAS::Axis::Long);
+    blas::Layout lay = layout == RL_LAYOUT_NATURAL ? D.natural_layout
+                       : (layout == RL_LAYOUT_ROWMAJOR ? blas::Layout::RowMajor : blas::Layout::ColMajor);
+    State st = load_state(state);
+    // RandBLAS/RandBLAS/dense_skops.hh:560-603 (fill_dense_unpacked); :620-623 is the full-matrix special case
+    State nxt = RandBLAS::fill_dense_unpacked(lay, D, sub_rows, sub_cols, ro, co, buff, st);
+    store_state(nxt, state);
+    return 0;
+    RL_CATCH
+}
+
+template <typename T>
+static int rs_impl(int64_t m, int64_t n, const T* A, int64_t k, T* Omega, uint32_t state[6], const rl_stack_opts* o) {
+    RL_TRY
+    Stack<T> s(*o);
+    State st = load_state(state);
+    int rc = s.rs.call(m, n, A, k, Omega, st);   // RandLAPACK/comps/rl_rs.hh:116-178
+    store_state(st, state);
+    return rc;
+    RL_CATCH
+}
+
+template <typename T>
+static int rf_impl(int64_t m, int64_t n, const T* A, int64_t k, T* Q, uint32_t state[6], const rl_stack_opts* o) {
+    RL_TRY
+    Stack<T> s(*o);
+    State st = load_state(state);
+    int rc = s.rf.call(m, n, A, k, Q, st);       // RandLAPACK/comps/rl_rf.hh:106-137
+    store_state(st, state);
+    return rc;
+    RL_CATCH
+}
+
+template <typename T>
+static int qb_impl(int64_t m, int64_t n, T* A, int64_t* k, int64_t b_sz, T tol, T* Q_out, T* BT_out, uint32_t state[6],
+                   const rl_stack_opts* o) {
+    RL_TRY
+    Stack<T> s(*o);
+    State st = load_state(state);
+    T *Q = nullptr, *BT = nullptr;
+    int64_t k_io = *k;
+    int rc = s.qb.call(m, n, A, k_io, b_sz, tol, Q, BT, st);   // RandLAPACK/comps/rl_qb.hh:133-268
+    std::memcpy(Q_out, Q, sizeof(T) * m * k_io);
+    std::memcpy(BT_out, BT, sizeof(T) * n * k_io);
+    free(Q); free(BT);
+    *k = k_io;
+    store_state(st, state);
+    return rc;
+    RL_CATCH
+}
+
+template <typename T>
+static int rsvd_impl(int64_t m, int64_t n, T* A, int64_t* k, T tol, T* U_out, T* S_out, T* V_out, uint32_t state[6],
+                     const rl_stack_opts* o) {
+    RL_TRY
+    Stack<T> s(*o);
+    State st = load_state(state);
+    T *U = nullptr, *S = nullptr, *V = nullptr;
+    int64_t k_io = *k;
+    int rc = s.rsvd.call(m, n, A, k_io, tol, U, S, V, st);     // RandLAPACK/drivers/rl_rsvd.hh:113-154
+    std::memcpy(U_out, U, sizeof(T) * m * k_io);
+    std::memcpy(S_out, S, sizeof(T) * k_io);
+    std::memcpy(V_out, V, sizeof(T) * n * k_io);
+    free(U); free(S); free(V);
+    *k = k_io;
+    store_state(st, state);
+    return rc;
+    RL_CATCH
+}
+
+template <typename T>
+static int stab_impl(int kind, int64_t m, int64_t k, T* A, int cond_check) {
+    RL_TRY
+    auto st = make_stab<T>(kind, cond_check);   // RandLAPACK/comps/rl_orth.hh:68-98,144-164,211-230
+    return st->call(m, k, A);
+    RL_CATCH
+}
+
+template <typename T>
+static int mat_gen_impl(int type, int64_t m, int64_t n, int64_t rank, T cond, T exponent, T scaling, T* A, uint32_t state[6]) {
+    RL_TRY
+    RandLAPACK::gen::mat_gen_info<T> info(m, n, (RandLAPACK::gen::mat_type)type);
+    info.rank = rank; info.cond_num = cond; info.exponent = exponent; info.scaling = scaling;
+    State st = load_state(state);
+    RandLAPACK::gen::mat_gen(info, A, st);      // RandLAPACK/testing/rl_gen.hh:712-773
+    store_state(st, state);
+    return 0;
+    RL_CATCH
+}
+
+extern "C" {
+
+const char* rlref_last_error(void) { return g_err; }
+const char* rlref_kind(void) { return "reference"; }
+
+int rlref_set_num_threads(int n) {
+    scipy_openblas_set_num_threads(n);
+#if defined(RandBLAS_HAS_OpenMP)
+    omp_set_num_threads(n);
+#endif
+    return 0;
+}
+int rlref_get_num_threads(void) { return scipy_openblas_get_num_threads(); }
+
+int rlref_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) {
+    RNG rng; RNG::ctr_type c; RNG::key_type k;
+    for (int i = 0; i < 4; ++i) c.v[i] = ctr[i];
+    for (int i = 0; i < 2; ++i) k.v[i] = key[i];
+    auto r = rng(c, k);
+    for (int i = 0; i < 4; ++i) out[i] = r.v[i];
+    return 0;
+}
+
+int rlref_ctr_incr(uint32_t ctr[4], uint64_t step) {
+    RNG::ctr_type c;
+    for (int i = 0; i < 4; ++i) c.v[i] = ctr[i];
+    c.incr(step);
+    for (int i = 0; i < 4; ++i) ctr[i] = c.v[i];
+    return 0;
+}
+
+int rlref_boxmuller(uint32_t u0, uint32_t u1, float out[2]) {
+    auto f = r123::boxmuller(u0, u1);
+    out[0] = f.x; out[1] = f.y;
+    return 0;
+}
+
+int rlref_fill_dense_f64(int64_t n_rows, int64_t n_cols, int family, int major_axis, int layout, int64_t sub_rows, int64_t sub_cols,
+                         int64_t ro, int64_t co, double* buff, uint32_t state[6]) {
+    return fill_dense_impl<double>(n_rows, n_cols, family, major_axis, layout, sub_rows, sub_cols, ro, co, buff, state);
+}
+int rlref_fill_dense_f32(int64_t n_rows, int64_t n_cols, int family, int major_axis, int layout, int64_t sub_rows, int64_t sub_cols,
+                         int64_t ro, int64_t co, float* buff, uint32_t state[6]) {
+    return fill_dense_impl<float>(n_rows, n_cols, family, major_axis, layout, sub_rows, sub_cols, ro, co, buff, state);
+}
+
+int rlref_stab_f64(int kind, int64_t m, int64_t k, double* A, int cond_check) { return stab_impl<double>(kind, m, k, A, cond_check); }
+int rlref_stab_f32(int kind, int64_t m, int64_t k, float* A, int cond_check) { return stab_impl<float>(kind, m, k, A, cond_check); }
+
+int rlref_rs_f64(int64_t m, int64_t n, const double* A, int64_t k, double* Omega, uint32_t state[6], const rl_stack_opts* o) {
+    return rs_impl<double>(m, n, A, k, Omega, state, o);
+}
+int rlref_rs_f32(int64_t m, int64_t n, const float* A, int64_t k, float* Omega, uint32_t state[6], const rl_stack_opts* o) {
+    return rs_impl<float>(m, n, A, k, Omega, state, o);
+}
+int rlref_rf_f64(int64_t m, int64_t n, const double* A, int64_t k, double* Q, uint32_t state[6], const rl_stack_opts* o) {
+    return rf_impl<double>(m, n, A, k, Q, state, o);
+}
+int rlref_rf_f32(int64_t m, int64_t n, const float* A, int64_t k, float* Q, uint32_t state[6], const rl_stack_opts* o) {
+    return rf_impl<float>(m, n, A, k, Q, state, o);
+}
+int rlref_qb_f64(int64_t m, int64_t n, double* A, int64_t* k, int64_t b_sz, double tol, double* Q, double* BT, uint32_t state[6],
+                 const rl_stack_opts* o) {
+    return qb_impl<double>(m, n, A, k, b_sz, tol, Q, BT, state, o);
+}
+int rlref_qb_f32(int64_t m, int64_t n, float* A, int64_t* k, int64_t b_sz, float tol, float* Q, float* BT, uint32_t state[6],
+                 const rl_stack_opts* o) {
+    return qb_impl<float>(m, n, A, k, b_sz, tol, Q, BT, state, o);
+}
+int rlref_rsvd_f64(int64_t m, int64_t n, double* A, int64_t* k, double tol, double* U, double* S, double* V, uint32_t state[6],
+                   const rl_stack_opts* o) {
+    return rsvd_impl<double>(m, n, A, k, tol, U, S, V, state, o);
+}
+int rlref_rsvd_f32(int64_t m, int64_t n, float* A, int64_t* k, float tol, float* U, float* S, float* V, uint32_t state[6],
+                   const rl_stack_opts* o) {
+    return rsvd_impl<float>(m, n, A, k, tol, U, S, V, state, o);
+}
+
+int rlref_mat_gen_f64(int type, int64_t m, int64_t n, int64_t rank, double cond, double exponent, double scaling, double* A,
+                      uint32_t state[6]) {
+    return mat_gen_impl<double>(type, m, n, rank, cond, exponent, scaling, A, state);
+}
+int rlref_mat_gen_f32(int type, int64_t m, int64_t n, int64_t rank, float cond, float exponent, float scaling, float* A,
+                      uint32_t state[6]) {
+    return mat_gen_impl<float>(type, m, n, rank, cond, exponent, scaling, A, state);
+}
+
+} // extern "C"

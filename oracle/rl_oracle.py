@@ -1,0 +1,403 @@
+"""CPU restatement of the RandLAPACK sketch-and-factor drivers (RS / RF / QB / RSVD and the
+CholQRQ / PLUL / HQRQ stabilisers) on numpy + the LAPACK that scipy bundles.
+
+TEST INFRASTRUCTURE ONLY.  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg may
+import this module; the product (randlapack_b200/) never does.
+
+Every function cites the reference lines it follows (paths relative to the reference root).
+The random-number layer (Philox4x32-10, Box-Muller, DenseDist counter layout) lives in
+oracle/rl_oracle.c so that it uses the same libm calls as the reference's host path; this module
+loads it through ctypes.  Parity pins: see the header of oracle/rl_oracle.c; the drivers here are
+validated bit-for-bit / to round-off against the real reference compiled in oracle/_ref
+(tests/test_oracle_drivers.py) and against the golden fixtures in tests/golden/.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from dataclasses import dataclass
+
+import numpy as np
+from scipy.linalg import get_blas_funcs, get_lapack_funcs
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+STAB_PLUL, STAB_CHOLQRQ, STAB_HQRQ = 0, 1, 2
+FAMILY_GAUSSIAN, FAMILY_UNIFORM = 0, 1
+AXIS_LONG, AXIS_SHORT = 0, 1
+LAYOUT_NATURAL, LAYOUT_COLMAJOR, LAYOUT_ROWMAJOR = 0, 1, 2
+
+_u32 = ctypes.c_uint32
+_i64 = ctypes.c_int64
+_lib = None
+
+
+def lib() -> ctypes.CDLL:
+    """Load oracle/librl_oracle.so (built by `make -C oracle oracle`)."""
+    global _lib
+    if _lib is None:
+        _lib = ctypes.CDLL(os.path.join(_HERE, "librl_oracle.so"))
+    return _lib
+
+
+# --------------------------------------------------------------------------------------------
+# RNG layer (thin ctypes veneer over rl_oracle.c)
+# --------------------------------------------------------------------------------------------
+class RNGState:
+    """RandBLAS::RNGState<Philox4x32> (RandBLAS/RandBLAS/base.hh:64-164): 128-bit counter + 64-bit key."""
+
+    def __init__(self, key: int = 0, counter=(0, 0, 0, 0)):
+        if isinstance(key, (tuple, list)):
+            k = tuple(int(x) & 0xFFFFFFFF for x in key)
+        else:  # RNGState(uint64 k): key.incr(k) on a zero key (base.hh:119)
+            k = (int(key) & 0xFFFFFFFF, (int(key) >> 32) & 0xFFFFFFFF)
+        self.counter = tuple(int(c) & 0xFFFFFFFF for c in counter)
+        self.key = k
+
+    def words(self):
+        return (_u32 * 6)(*self.counter, *self.key)
+
+    @classmethod
+    def from_words(cls, w):
+        return cls(key=(w[4], w[5]), counter=(w[0], w[1], w[2], w[3]))
+
+    def copy(self):
+        return RNGState(self.key, self.counter)
+
+    def __eq__(self, other):
+        return self.counter == other.counter and self.key == other.key
+
+    def __repr__(self):
+        return f"RNGState(counter={self.counter}, key={self.key})"
+
+
+def philox4x32_10(ctr, key):
+    out = (_u32 * 4)()
+    lib().rlo_philox4x32_10((_u32 * 4)(*ctr), (_u32 * 2)(*key), out)
+    return tuple(out)
+
+
+def ctr_incr(ctr, step: int):
+    c = (_u32 * 4)(*ctr)
+    lib().rlo_ctr_incr(c, ctypes.c_uint64(step))
+    return tuple(c)
+
+
+def fill_dense(n_rows, n_cols, state: RNGState, dtype=np.float64, family=FAMILY_GAUSSIAN, major_axis=AXIS_LONG,
+               layout=LAYOUT_NATURAL, sub=None):
+    """RandBLAS::fill_dense / fill_dense_unpacked (dense_skops.hh:560-603, 620-623).
+
+    Returns (matrix as a 2-D numpy array in the requested layout, next RNGState)."""
+    sub_rows, sub_cols, ro, co = sub if sub is not None else (n_rows, n_cols, 0, 0)
+    dt = np.dtype(dtype)
+    buf = np.empty(sub_rows * sub_cols, dtype=dt)
+    w = state.words()
+    fn = lib().rlo_fill_dense_f64 if dt == np.float64 else lib().rlo_fill_dense_f32
+    fn.argtypes = [_i64, _i64, ctypes.c_int, ctypes.c_int, ctypes.c_int, _i64, _i64, _i64, _i64, ctypes.c_void_p,
+                   ctypes.POINTER(_u32)]
+    rc = fn(n_rows, n_cols, family, major_axis, layout, sub_rows, sub_cols, ro, co, buf.ctypes.data, w)
+    if rc:
+        raise ValueError("fill_dense: invalid arguments (randblas_require failed)")
+    is_wide, fa_long = n_rows < n_cols, major_axis == AXIS_LONG
+    nat_col = (not is_wide and fa_long) or (is_wide and not fa_long)  # dense_skops.hh:184-196
+    col = nat_col if layout == LAYOUT_NATURAL else layout == LAYOUT_COLMAJOR
+    mat = buf.reshape((sub_rows, sub_cols), order="F" if col else "C")
+    return mat, RNGState.from_words(w)
+
+
+# --------------------------------------------------------------------------------------------
+# BLAS/LAPACK veneer: same routines, same argument order as the reference's calls
+# --------------------------------------------------------------------------------------------
+def _F(a):
+    return np.asfortranarray(a)
+
+
+def _gemm(a, b, ta=False, tb=False, alpha=1.0, beta=0.0, c=None):
+    (gemm,) = get_blas_funcs(("gemm",), (a, b))
+    if c is None:
+        return gemm(alpha, a, b, trans_a=int(ta), trans_b=int(tb))
+    return gemm(alpha, a, b, beta=beta, c=c, trans_a=int(ta), trans_b=int(tb), overwrite_c=1)
+
+
+# --------------------------------------------------------------------------------------------
+# Stabilisers (RandLAPACK/comps/rl_orth.hh)
+# --------------------------------------------------------------------------------------------
+class CholQRQ:
+    """rl_orth.hh:25-98 — syrk(Upper,Trans) -> potrf(Upper) -> [cond check] -> trsm(Right,Upper,NoTrans)."""
+
+    def __init__(self, cond_check=False, verbose=False):
+        self.cond_check, self.verbose, self.chol_fail = cond_check, verbose, False
+
+    def call(self, A):
+        m, k = A.shape
+        syrk, trsm = get_blas_funcs(("syrk", "trsm"), (A,))
+        (potrf,) = get_lapack_funcs(("potrf",), (A,))
+        G = syrk(1.0, A, trans=1, lower=0)                       # :78
+        R, info = potrf(G, lower=0, clean=0)                      # :81
+        if info != 0:
+            self.chol_fail = True
+            return 1, A
+        if self.cond_check:                                       # :88-93
+            if cond_num(R) > 1.0 / np.sqrt(np.finfo(A.dtype).eps):
+                return 1, A
+        Q = trsm(1.0, R, A, side=1, lower=0, trans_a=0, diag=0)   # :95
+        return 0, _F(Q)
+
+
+class HQRQ:
+    """rl_orth.hh:100-164 — geqrf + ungqr."""
+
+    def __init__(self, cond_check=False, verbose=False):
+        self.cond_check, self.verbose = cond_check, verbose
+
+    def call(self, A):
+        geqrf, orgqr = get_lapack_funcs(("geqrf", "orgqr"), (A,))
+        qr, tau, _, info = geqrf(A)
+        if info:
+            return 1, A
+        q, _, info = orgqr(qr, tau)
+        return 0, _F(q)
+
+
+class PLUL:
+    """rl_orth.hh:166-230 — getrf (singular U tolerated) -> unit-lower L (get_L) -> laswp(1..n, incx=+1)."""
+
+    def __init__(self, cond_check=False, verbose=False):
+        self.cond_check, self.verbose = cond_check, verbose
+
+    def call(self, A):
+        m, n = A.shape
+        (getrf, laswp) = get_lapack_funcs(("getrf", "laswp"), (A,))
+        lu, piv, info = getrf(A)                                  # :222
+        L = np.tril(lu, -1)                                       # util::get_L(m,n,A,1): rl_util.hh:101-114
+        idx = np.arange(min(m, n))
+        L[idx, idx] = 1.0
+        L = _F(L)
+        # lapack::laswp(n, A, m, 1, n, ipiv, 1) (:225): forward application of the interchanges
+        L = laswp(L, piv, k1=0, k2=min(m, n) - 1, off=0, inc=1)
+        return 0, _F(L)
+
+
+def make_stab(kind, cond_check=False):
+    return {STAB_PLUL: PLUL, STAB_CHOLQRQ: CholQRQ, STAB_HQRQ: HQRQ}[kind](cond_check, False)
+
+
+def cond_num(A):
+    """util::cond_num_check (rl_util.hh:402-424): gesdd(NoVec), s[0]/s[n-1] (inf if s[n-1]==0)."""
+    (gesdd,) = get_lapack_funcs(("gesdd",), (A,))
+    _, s, _, _ = gesdd(A, compute_uv=0)
+    return np.inf if s[-1] == 0 else s[0] / s[-1]
+
+
+def orthogonality_check(Q):
+    """util::orthogonality_check (rl_util.hh:467-496): ||triu(Q'Q) - I||_F / sqrt(k) > tol."""
+    k = Q.shape[1]
+    (syrk,) = get_blas_funcs(("syrk",), (Q,))
+    G = syrk(1.0, Q, trans=1, lower=0)
+    G[np.arange(k), np.arange(k)] -= 1.0
+    tol = 1e-10 if Q.dtype == np.float64 else 1e-2
+    return np.linalg.norm(G) / np.sqrt(k) > tol
+
+
+# --------------------------------------------------------------------------------------------
+# RS / RF / QB / RSVD
+# --------------------------------------------------------------------------------------------
+@dataclass
+class StackOpts:
+    """Mirror of rl_stack_opts (oracle/oracle_capi.h) = the canonical stack of test/drivers/test_rsvd.cc:68-93."""
+    passes_over_data: int = 0
+    passes_per_stab: int = 1
+    block_sz: int = 0
+    stab: int = STAB_PLUL
+    orth_rf: int = STAB_CHOLQRQ
+    orth_qb: int = STAB_CHOLQRQ
+    cond_check: bool = False
+    orth_check: bool = False
+
+
+class RS:
+    """RandLAPACK::RS (rl_rs.hh:31-178)."""
+
+    def __init__(self, stab, p, q, verbose=False, cond_check=False):
+        self.stab, self.passes_over_data, self.passes_per_stab = stab, p, q
+        self.cond_check, self.cond_nums = cond_check, []
+
+    def call(self, A, k, state: RNGState, omega_override=None):
+        """Returns (rc, Omega n-by-k, next_state). `omega_override` lets a parity test inject the very
+        operator the device generated (cf. test/drivers/test_bqrrp_gpu.cu:91-103, where the reference
+        feeds one host-built sketch to both its CPU and GPU paths)."""
+        m, n = A.shape
+        p, q, p_done = self.passes_over_data, self.passes_per_stab, 0
+        dt = A.dtype
+        if p % 2 == 0:                                             # :132-135
+            Om, state = fill_dense(n, k, state, dt)
+            Om = _F(Om)
+            if omega_override is not None:
+                Om = _F(omega_override.astype(dt))
+        else:                                                      # :136-149
+            Om1, state = fill_dense(m, k, state, dt)
+            Om1 = _F(Om1)
+            if omega_override is not None:
+                Om1 = _F(omega_override.astype(dt))
+            Om = _gemm(A, Om1, ta=True)
+            p_done += 1
+            if p_done % q == 0:
+                rc, Om = self.stab.call(Om)
+                if rc:
+                    return 1, Om, state
+        while p - p_done > 0:                                      # :151-174
+            Om1 = _gemm(A, Om)
+            p_done += 1
+            if self.cond_check:
+                self.cond_nums.append(cond_num(Om1))
+            if p_done % q == 0:
+                rc, Om1 = self.stab.call(Om1)
+                if rc:
+                    return 1, Om, state
+            Om = _gemm(A, Om1, ta=True)
+            p_done += 1
+            if self.cond_check:
+                self.cond_nums.append(cond_num(Om))
+            if p_done % q == 0:
+                rc, Om = self.stab.call(Om)
+                if rc:
+                    return 1, Om, state
+        return 0, Om, state
+
+
+class RF:
+    """RandLAPACK::RF (rl_rf.hh:31-137)."""
+
+    def __init__(self, rs, orth, verbose=False, cond_check=False):
+        self.rs, self.orth, self.cond_check, self.cond_nums = rs, orth, cond_check, []
+
+    def call(self, A, k, state, omega_override=None):
+        rc, Om, state = self.rs.call(A, k, state, omega_override)   # :118
+        if rc:
+            return 1, None, state
+        Q = _gemm(A, Om)                                             # :123
+        if self.cond_check:
+            self.cond_nums.append(cond_num(Q))
+        rc, Q = self.orth.call(Q)                                    # :129
+        if rc:
+            return 2, Q, state
+        return 0, Q, state
+
+
+class QB:
+    """RandLAPACK::QB (rl_qb.hh:36-268). Returns (rc, k, Q m-by-k, BT n-by-k, state)."""
+
+    def __init__(self, rf, orth, verbose=False, orth_check=False):
+        self.rf, self.orth, self.orth_check = rf, orth, orth_check
+
+    def call(self, A, k, b_sz, tol, state, omega_override=None):
+        m, n = A.shape
+        dt = A.dtype
+        eps = np.finfo(dt).eps
+        tol = max(tol, 100 * eps)                                    # :149
+        curr, norm_B, approx_err = 0, dt.type(0), dt.type(0)
+        (lange,) = get_lapack_funcs(("lange",), (A,))
+        norm_A = dt.type(lange("F", A))                              # :168
+        A_cpy = _F(A.copy())                                         # :171
+        Q = np.zeros((m, 0), dtype=dt, order="F")
+        BT = np.zeros((n, 0), dtype=dt, order="F")
+        while curr < k:
+            b_sz = min(b_sz, k - curr)
+            nxt = curr + b_sz
+            rc, Q_i, state = self.rf.call(A_cpy, b_sz, state, omega_override)   # :191
+            if rc:
+                return 6, curr, Q, BT, state
+            if self.orth_check and orthogonality_check(Q_i):         # :199-207
+                return 4, curr, Q, BT, state
+            if curr != 0:                                            # :210-215
+                QtQi = _gemm(Q, Q_i, ta=True)
+                Q_i = _gemm(Q, QtQi, alpha=-1.0, beta=1.0, c=_F(Q_i))
+                _, Q_i = self.orth.call(Q_i)
+            BT_i = _gemm(A_cpy, Q_i, ta=True)                        # :218
+            norm_B_i = dt.type(lange("F", BT_i))
+            norm_B = dt.type(np.hypot(norm_B, norm_B_i))             # :222
+            prev_err = approx_err
+            approx_err = dt.type(np.sqrt(np.abs(norm_A - norm_B)) * (np.sqrt(norm_A + norm_B) / norm_A))   # :225
+            Qn = _F(np.hstack([Q, Q_i]))
+            BTn = _F(np.hstack([BT, BT_i]))
+            if curr > 0 and approx_err > prev_err:                   # :228-234 (Q,BT buffers already hold block i)
+                return 2, curr, Qn, BTn, state
+            if self.orth_check and orthogonality_check(Qn):          # :236-244
+                return 5, curr, Qn, BTn, state
+            Q, BT = Qn, BTn
+            curr += b_sz
+            if approx_err < tol:                                     # :250-256
+                return 0, curr, Q, BT, state
+            A_cpy = _gemm(Q_i, BT_i, tb=True, alpha=-1.0, beta=1.0, c=A_cpy)   # :260
+        return 3, curr, Q, BT, state
+
+
+class RSVD:
+    """RandLAPACK::RSVD (rl_rsvd.hh:34-154). Returns (rc, k, U m-by-k, S k, V n-by-k, state)."""
+
+    def __init__(self, qb, block_sz):
+        self.qb, self.block_sz = qb, block_sz
+
+    def call(self, A, k, tol, state, omega_override=None):
+        m, n = A.shape
+        if k <= 0 or tol < 0:                                        # :128-132
+            raise ValueError("RandLAPACK::Error: invalid argument")
+        _, k, Q, BT, state = self.qb.call(A, k, self.block_sz, tol, state, omega_override)   # :137 (rc ignored)
+        (gesdd,) = get_lapack_funcs(("gesdd",), (BT,))
+        # gesdd(SomeVec, n, k, BT, n, S, V, n, UT_buf, k): BT = V * diag(S) * UT_buf   (:146)
+        V, S, UT, info = gesdd(_F(BT[:, :k]), compute_uv=1, full_matrices=0)
+        U = _gemm(_F(Q[:, :k]), UT, tb=True)                         # :148
+        return 0, k, _F(U), S, _F(V), state
+
+
+def make_stack(o: StackOpts):
+    stab = make_stab(o.stab, o.cond_check)
+    rs = RS(stab, o.passes_over_data, o.passes_per_stab, False, o.cond_check)
+    rf = RF(rs, make_stab(o.orth_rf, o.cond_check), False, o.cond_check)
+    qb = QB(rf, make_stab(o.orth_qb, o.cond_check), False, o.orth_check)
+    return rs, rf, qb, RSVD(qb, o.block_sz)
+
+
+# --------------------------------------------------------------------------------------------
+# Test-matrix generators the reference's tests use as inputs (RandLAPACK/testing/rl_gen.hh)
+# --------------------------------------------------------------------------------------------
+def gen_poly_singvals(k, frac_spectrum_one, cond, p, dtype=np.float64):
+    """rl_gen.hh:105-126."""
+    T = np.dtype(dtype).type
+    s = np.empty(k, dtype=dtype)
+    offset = int(np.floor(k * frac_spectrum_one))
+    first, last = T(1.0), T(1.0) / T(cond)
+    neg_invp = -T(1.0) / T(p)
+    a = np.power((np.power(last, neg_invp) - np.power(first, neg_invp)) / T(k - offset), T(p))
+    b = np.power(a * first, neg_invp) - offset
+    s[:offset] = 1.0
+    for i in range(offset, k):
+        s[i] = 1 / (a * np.power(T(i) + b, T(p)))
+    return s
+
+
+def gen_singvec(m, n, S_diag, state, dtype=np.float64):
+    """rl_gen.hh:62-92: A = Q_U diag(S) Q_V', Q_U/Q_V from Householder QR of Gaussian m-by-k / n-by-k."""
+    k = len(S_diag)
+    A = np.zeros((m, n), dtype=dtype, order="F")
+    U, state = fill_dense(m, k, state, dtype)
+    V, state = fill_dense(n, k, state, dtype)
+    U, V = _F(U), _F(V)
+    A[np.arange(k), np.arange(k)] = S_diag
+    geqrf, ormqr = get_lapack_funcs(("geqrf", "ormqr"), (A,))
+
+    def _ormqr(side, trans, qr, tau, c):
+        _, lw, _ = ormqr(side, trans, qr, tau, c, lwork=-1)
+        out, _, info = ormqr(side, trans, qr, tau, c, lwork=int(lw[0]))
+        return _F(out)
+    qr, tau, _, _ = geqrf(U)
+    A = _ormqr("L", "N", qr, tau, A)
+    qr, tau, _, _ = geqrf(V)
+    A = _ormqr("R", "T", qr, tau, A)
+    return A, state
+
+
+def gen_poly_mat(m, n, k, cond, exponent, state, frac_spectrum_one=0.1, dtype=np.float64):
+    """rl_gen.hh gen_poly_mat (mat_gen case `polynomial`, :720-723) with diag=false."""
+    s = gen_poly_singvals(k, frac_spectrum_one, cond, exponent, dtype)
+    return gen_singvec(m, n, s, state, dtype)
