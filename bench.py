@@ -1,0 +1,357 @@
+#!/usr/bin/env python
+"""bench.py — rank-k RSVD throughput (Gflop/s) on tall dense fp64 A, the metric BASELINE.json names.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--m M --n N --k K --p P]
+
+One "step" = one complete RSVD (RS -> RF -> CholQRQ -> QB -> SVD(B) -> U) of a resident synthetic A.
+N = 1: BASELINE.json configs[1] (2^24 x 1024 fp64, rank 256).  N > 1 (torchrun): the same per-GPU row block on every
+rank (weak scaling), i.e. an (N * 2^24) x 1024 row-sharded A with Gram / B^T / norm allreduces over NCCL.
+Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for every field.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "rsvd_gflops"
+UNIT = "Gflop/s"
+
+
+def rsvd_flops(m, n, k, p, q=1):
+    """Algorithmic flop count (SURVEY.md 8d / DESIGN.md): (p+2) tall GEMMs of 2mnk, CholQR of Q (2mk^2), U = Q*W (2mk^2),
+    plus one CholQR per stabilised power pass (2mk^2 on the m x k iterate, 2nk^2 on the n x k one).  The O(nk^2 + k^3) small
+    factorizations are not counted."""
+    f = (p + 2) * 2.0 * m * n * k + 4.0 * m * k * k
+    for pass_idx in range(1, p + 1):
+        if pass_idx % q == 0:
+            # with p even the passes alternate A*Omega (m x k) and A^T*Omega_1 (n x k), starting with m x k
+            # with p odd the first pass is A^T*Omega_1 (n x k)
+            tall = (pass_idx % 2 == 1) if p % 2 == 0 else (pass_idx % 2 == 0)
+            f += 2.0 * (m if tall else n) * k * k
+    return f
+
+
+def class_flops(m, n, k, p, q=1):
+    """Algorithmic flops per kernel class for one step: NN (A*Omega), TN (A^T*Y and the Gram syrk's), RIGHTMUL (Y*R^-1, Q*W)."""
+    n_even = p // 2
+    nn = (n_even + 1) * 2.0 * m * n * k
+    tn = (p - n_even + 1) * 2.0 * m * n * k
+    rm = 2.0 * m * k * k        # U = Q W
+    tn += 1.0 * m * k * k       # syrk of CholQR(Q)
+    rm += 1.0 * m * k * k       # trsm of CholQR(Q)
+    for pass_idx in range(1, p + 1):
+        if pass_idx % q == 0:
+            tall = (pass_idx % 2 == 1) if p % 2 == 0 else (pass_idx % 2 == 0)
+            d = m if tall else n
+            tn += 1.0 * d * k * k
+            rm += 1.0 * d * k * k
+    return {"gemm_nn": nn, "gemm_tn": tn, "rightmul": rm}
+
+
+class ClockSampler:
+    """nvidia-smi sampling of SM clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, pw = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def measured_fp64_peak():
+    """fp64 tensor-pipe (DMMA.8x8x4) peak of THIS device from tools/peaks (register-resident loop, ~1 s).
+    MEASURED_PEAKS.json only has HBM and bf16, so the fp64 denominator is measured here and labelled as such."""
+    exe = os.path.join(ROOT, "tools", "peaks")
+    try:
+        out = subprocess.run([exe], capture_output=True, text=True, timeout=120).stdout.strip().splitlines()[-1]
+        d = json.loads(out)
+        return max(d["dmma_tflops"], d["dfma_tflops"]), "measured in-run by tools/peaks (DMMA.8x8x4 / DFMA register loop)", d
+    except Exception as e:  # noqa: BLE001
+        return 37.0, f"nominal B200 fp64 (tools/peaks failed: {type(e).__name__})", None
+
+
+def load_peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        return {}
+
+
+# --------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the reference's own CPU RSVD (oracle/_ref when it was compiled, else the oracle port)
+# --------------------------------------------------------------------------------------------------
+def cpu_rsvd_runner(n, k, p, q):
+    import numpy as np
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import _ref
+    from oracle import rl_oracle as O
+    o = O.StackOpts(p, q, k, O.STAB_CHOLQRQ, O.STAB_CHOLQRQ, O.STAB_CHOLQRQ, False, False)
+    R = _ref.ref_lib()
+    cores = os.cpu_count() or 1
+    if R is not None:
+        R.rlref_set_num_threads(cores)
+
+        def run(A):
+            rc, kk, U, S, V, st = _ref.ref_rsvd(R, A, k, 0.0, [0] * 6, o)
+            return S
+        return run, "reference", cores
+    *_, rsvd = O.make_stack(o)
+
+    def run(A):
+        rc, kk, U, S, V, st = rsvd.call(A, k, 0.0, O.RNGState(0))
+        return S
+    return run, "port", cores
+
+
+def cpu_sample(n, k, p, q, m_cpu, steps, warmup):
+    import numpy as np
+    import torch
+    run, kind, cores = cpu_rsvd_runner(n, k, p, q)
+    torch.manual_seed(0)
+    A = np.asfortranarray(torch.randn((n, m_cpu), dtype=torch.float64).numpy().T)
+    for _ in range(warmup):
+        run(A)
+    ts = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        run(A)
+        ts.append(time.perf_counter() - t0)
+    t = sum(ts) / len(ts)
+    gf = rsvd_flops(m_cpu, n, k, p, q) / t / 1e9
+    return gf, t, kind, cores
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--m", type=int, default=1 << 24, help="rows per GPU")
+    ap.add_argument("--n", type=int, default=1024)
+    ap.add_argument("--k", type=int, default=256)
+    ap.add_argument("--p", type=int, default=2, help="RS passes_over_data")
+    ap.add_argument("--q", type=int, default=1, help="RS passes_per_stab")
+    ap.add_argument("--m-cpu", type=int, default=1 << 17, help="rows of the bounded CPU-baseline sample")
+    ap.add_argument("--m-e2e", type=int, default=1 << 20, help="rows of the host-buffer (e2e) measurement")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    n, k, p, q = args.n, args.k, args.p, args.q
+    config = {"workload": f"rank-{k} RSVD of a ({world}x{args.m}) x {n} fp64 Gaussian matrix (BASELINE.json configs[1] per GPU), "
+                          f"RS(p={p}, q={q}, CholQRQ) + RF(CholQRQ) + QB(block={k}, CholQRQ) + RSVD",
+              "m_per_gpu": args.m, "n": n, "k": k, "passes_over_data": p, "passes_per_stab": q, "stabiliser": "CholQRQ",
+              "l2": "inputs (A: m*n*8 bytes per GPU) exceed the 126 MB L2 by >1000x; no flush needed",
+              "parallelism": f"row-sharded x{world}" if world > 1 else "single GPU"}
+
+    if args.impl == "reference":
+        # the reference's own CPU implementation of the path on the host cores, bounded sample of the same workload
+        if rank != 0:
+            return 0
+        gf, t, kind, cores = cpu_sample(n, k, p, q, args.m_cpu, max(1, args.steps), max(0, min(args.warmup, 1)))
+        sample = f"{args.m_cpu} x {n} fp64 rows of the same workload (k={k}, p={p}), {cores} threads"
+        print(json.dumps({"impl": "reference", "metric": METRIC, "value": gf, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+                          "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak",
+                          "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
+                          "cpu_baseline": {"value": gf, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
+                          "e2e": {"value": gf, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                          "gpu_launches": 0}))
+        return 0
+
+    import torch
+    import randlapack_b200 as rl
+
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    else:
+        dist = None
+        torch.cuda.set_device(0)
+    dev = torch.device("cuda", torch.cuda.current_device())
+    ctx = rl.Context(dev.index)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- synthetic resident input: A = Gaussian DenseDist(m_global, n) sample, generated ON DEVICE by our own fill kernel
+    m_local = args.m
+    free_b, total_b = torch.cuda.mem_get_info()
+    need = 8 * (m_local * n + m_local * k) + (2 << 30)
+    while need > free_b and m_local > (1 << 16):
+        m_local //= 2
+        need = 8 * (m_local * n + m_local * k) + (2 << 30)
+    if m_local != args.m:
+        config["workload"] += f" [REDUCED to {m_local} rows per GPU: only {free_b / 1e9:.1f} GB free]"
+        config["m_per_gpu"] = m_local
+    m_global = m_local * world
+    A = rl.empty_f(m_local, n, torch.float64, dev)
+    buf, _ = None, None
+    st_in = rl.RNGState(0xA2)
+    fn = ctx._lib.rlb200_fill_dense_f64_dev
+    ctx.check(fn(ctx._h, m_global, n, rl.FAMILY_GAUSSIAN, rl.AXIS_LONG, rl.LAYOUT_NATURAL, m_local, n, rank * m_local, 0,
+                 A.data_ptr(), st_in.words()))
+    U = rl.empty_f(m_local, k, torch.float64, dev)
+    S = torch.empty(k, dtype=torch.float64, device=dev)
+    V = rl.empty_f(n, k, torch.float64, dev)
+    if world > 1:
+        ctx.set_shard(rank * m_local, m_global)
+    stack = rl.RSVD(rl.QB(rl.RF(rl.RS(rl.CholQRQ(), p, q), rl.CholQRQ()), rl.CholQRQ()), k)
+
+    def step():
+        rc, kk, *_ = stack.call(ctx, A, k, 0.0, rl.RNGState(0), U=U, S=S, V=V)
+        assert rc == 0 and kk == k, (rc, kk, stack.qb_code)
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    ctx.timers_enable(True)
+    for w in range(5):
+        ctx.timer_read(w, reset=True)
+    ctx.launch_count(reset=True)
+    sampler = ClockSampler(dev.index)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    ms_total = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    launches = ctx.launch_count()
+    tms = {nm: ctx.timer_read(i) for i, nm in enumerate(["gemm_nn", "gemm_tn", "rightmul", "small", "fill"])}
+    ctx.timers_enable(False)
+    if dist is not None:
+        t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = t.item()
+    ms_step = ms_total / args.steps
+    value = rsvd_flops(m_global, n, k, p, q) / (ms_step * 1e-3) / 1e9
+
+    # ---- sanity of the timed result (not timed): orthonormal U on a row sample is meaningless when sharded; check sigma > 0, finite
+    assert torch.isfinite(S).all() and (S[:-1] >= S[1:]).all() and S[-1] > 0
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return 0
+
+    # ---- roofline of the dominant kernel (per-class CUDA-event times were recorded on the launching stream)
+    cf = class_flops(m_local, n, k, p, q)
+    # the in-place right-multiplies run through the NN kernel class timer as well: split them analytically
+    nn_ms, nn_l = tms["gemm_nn"]
+    tn_ms, tn_l = tms["gemm_tn"]
+    peak, peak_src, peak_detail = measured_fp64_peak()
+    dom = "gemm_nn" if nn_ms >= tn_ms else "gemm_tn"
+    dom_ms = max(nn_ms, tn_ms) / args.steps
+    dom_flops = (cf["gemm_nn"] + cf["rightmul"]) if dom == "gemm_nn" else cf["gemm_tn"]
+    achieved = dom_flops / (dom_ms * 1e-3) / 1e12 if dom_ms > 0 else 0.0
+    roofline = {"bound": "tensor", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                "frac": achieved / peak if peak else None, "traffic": None,
+                "peak_source": peak_src + "; fp64 pipe (MEASURED_PEAKS.json has no fp64 figure)",
+                "class_ms_per_step": {kname: v[0] / args.steps for kname, v in tms.items()},
+                "class_launches_per_step": {kname: v[1] / args.steps for kname, v in tms.items()},
+                "whole_step_frac_of_fp64_peak": (value / 1e3) / peak if peak else None}
+
+    # ---- e2e: the reference-facing call with HOST buffers (pinned), copies inside the timed region
+    e2e = None
+    if not args.no_e2e and world == 1:
+        try:
+            m_e = args.m_e2e
+            avail_kb = [int(l.split()[1]) for l in open("/proc/meminfo") if l.startswith("MemAvailable")][0]
+            while 8 * m_e * n * 2.2 > avail_kb * 1024 * 0.5 and m_e > (1 << 14):
+                m_e //= 2
+            del A, U
+            torch.cuda.empty_cache()
+            Ah = torch.empty((n, m_e), dtype=torch.float64, pin_memory=True).t()
+            tmp = rl.empty_f(m_e, n, torch.float64, dev)
+            ctx.check(fn(ctx._h, m_e, n, rl.FAMILY_GAUSSIAN, rl.AXIS_LONG, rl.LAYOUT_NATURAL, m_e, n, 0, 0, tmp.data_ptr(),
+                         rl.RNGState(0xA2).words()))
+            Ah.copy_(tmp)
+            del tmp
+            torch.cuda.synchronize()
+            for _ in range(2):
+                stack.call_host(ctx, Ah, k, 0.0, rl.RNGState(0))
+            t0 = time.perf_counter()
+            reps = max(2, args.steps)
+            for _ in range(reps):
+                rc, kk, Uh, Sh, Vh = stack.call_host(ctx, Ah, k, 0.0, rl.RNGState(0))
+            te = (time.perf_counter() - t0) / reps
+            e2e = {"value": rsvd_flops(m_e, n, k, p, q) / te / 1e9, "unit": UNIT, "h2d_bytes_per_step": 8 * m_e * n,
+                   "d2h_bytes_per_step": 8 * (m_e * k + k + n * k), "ms_per_step": te * 1e3,
+                   "workload": f"{m_e} x {n} fp64 host-resident A (pinned), rlb200_rsvd_f64_host: H2D + RSVD + D2H of U,S,V"}
+        except Exception as e:  # noqa: BLE001
+            e2e = {"value": None, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0, "error": f"{type(e).__name__}: {e}"}
+
+    cpu = None
+    if not args.no_cpu and world == 1:
+        try:
+            gf, t, kind, cores = cpu_sample(n, k, p, q, args.m_cpu, 2, 1)
+            cpu = {"value": gf, "unit": UNIT, "cores": cores, "kind": kind, "ms_per_step": t * 1e3,
+                   "sample": f"{args.m_cpu} x {n} fp64 rows of the same workload (k={k}, p={p}), 1 warm-up + 2 timed runs"}
+        except Exception as e:  # noqa: BLE001
+            cpu = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "reference", "sample": f"failed: {type(e).__name__}: {e}"}
+
+    out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+           "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+           "data": "synthetic", "config": config, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
+           "gpu_launches": launches, "flops_per_step": rsvd_flops(m_global, n, k, p, q)}
+    print(json.dumps(out))
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

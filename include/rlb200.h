@@ -1,0 +1,175 @@
+/* rlb200.h — C-ABI of librlb200.so: a B200 (sm_100a) implementation of RandLAPACK's
+ * sketch-and-factor hot path (RandBLAS dense sketch operators -> RS/RF rangefinder ->
+ * CholQRQ -> QB -> RSVD).
+ *
+ * The reference (BallisticLA/RandLAPACK) has no FFI: its seam is C++ virtual dispatch on the
+ * abstract bases Stabilization / RowSketcher / RangeFinder / QBalg / RSVDalg.  Each entry point
+ * below therefore names the reference `call` (file:line, relative to the reference root) it
+ * replaces; include/RandLAPACK_B200.hh wraps them in classes with the reference's constructor
+ * arguments, public fields and `call` signatures (and, when RLB200_WITH_RANDLAPACK is defined,
+ * deriving from the reference's own bases), see INTEGRATION.md.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; no C++/torch types cross this boundary.
+ *  - `_dev` entry points take DEVICE pointers (column-major, 64-bit dims) and enqueue on the
+ *    context's stream; outputs live in caller-provided device buffers.
+ *  - `_host` entry points take HOST pointers, stage through the device and block until done;
+ *    they reproduce the reference's argument meaning for host callers.
+ *  - return value: the reference's own int code for numeric events (see each function), or a
+ *    negative RLB200_ERR_* for argument / CUDA / collective failures (never throws, never aborts).
+ *  - RNG state: 6 x uint32 = Philox4x32 counter[4] (little-endian 128-bit) + key[2], in/out, with
+ *    exactly the reference's advancement (RandBLAS/RandBLAS/base.hh:64-164).
+ *  - there is NO CPU fallback: every compute entry point fails with RLB200_ERR_CUDA if no sm_100
+ *    device is usable.
+ */
+#ifndef RLB200_H
+#define RLB200_H
+#include <stdint.h>
+#include <stddef.h>
+
+#if defined(__GNUC__)
+#define RLB200_API __attribute__((visibility("default")))
+#else
+#define RLB200_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RLB200_ABI_VERSION 1
+
+/* negative = infrastructure error; >= 0 = the reference's return code */
+enum {
+    RLB200_OK = 0,
+    RLB200_ERR_ARG = -1,       /* what randlapack_require / randblas_require would have thrown on */
+    RLB200_ERR_CUDA = -2,
+    RLB200_ERR_ALLOC = -3,
+    RLB200_ERR_COLLECTIVE = -4,
+    RLB200_ERR_UNSUPPORTED = -5
+};
+
+/* Stabilization<T> implementations (RandLAPACK/comps/rl_orth.hh) */
+enum { RLB200_STAB_PLUL = 0, RLB200_STAB_CHOLQRQ = 1, RLB200_STAB_HQRQ = 2 };
+/* RandBLAS::ScalarDist / Axis / layout selectors (RandBLAS/RandBLAS/dense_skops.hh:209-347) */
+enum { RLB200_FAMILY_GAUSSIAN = 0, RLB200_FAMILY_UNIFORM = 1 };
+enum { RLB200_AXIS_LONG = 0, RLB200_AXIS_SHORT = 1 };
+enum { RLB200_LAYOUT_NATURAL = 0, RLB200_LAYOUT_COLMAJOR = 1, RLB200_LAYOUT_ROWMAJOR = 2 };
+
+typedef struct rlb200_ctx rlb200_ctx;
+
+/* The canonical algorithm stack of test/drivers/test_rsvd.cc:68-93, flattened.
+ * Value-compatible with oracle/oracle_capi.h:rl_stack_opts. */
+typedef struct rlb200_stack_opts {
+    int64_t passes_over_data;  /* RS::passes_over_data  (rl_rs.hh:45)  */
+    int64_t passes_per_stab;   /* RS::passes_per_stab   (rl_rs.hh:46)  */
+    int64_t block_sz;          /* RSVD::block_sz        (rl_rsvd.hh:44) */
+    int32_t stab;              /* RS stabiliser,        RLB200_STAB_*  */
+    int32_t orth_rf;           /* RF orthogonaliser                    */
+    int32_t orth_qb;           /* QB re-orthogonaliser                 */
+    int32_t cond_check;        /* bool: CholQRQ cond check (rl_orth.hh:88-93); RS/RF cond logging is not offered */
+    int32_t orth_check;        /* bool: QB orthogonality_check (rl_qb.hh:199-207,236-244) */
+    int32_t reserved;
+} rlb200_stack_opts;
+
+/* Sum-allreduce hook for row-sharded operation (net-new; the reference is single-address-space).
+ * Called on `count` elements of `elem_size` bytes at DEVICE pointer `buf`, stream-ordered on
+ * `stream` (a cudaStream_t).  Return 0 on success.  NULL hook = single shard. */
+typedef int (*rlb200_allreduce_fn)(void* user, void* buf, int64_t count, int32_t elem_size, void* stream);
+
+/* ---- context ------------------------------------------------------------------------------- */
+RLB200_API int rlb200_abi_version(void);
+/* device: CUDA ordinal; stream: cudaStream_t to enqueue on (NULL = legacy default stream). */
+RLB200_API int rlb200_create(rlb200_ctx** out, int device, void* stream);
+RLB200_API int rlb200_destroy(rlb200_ctx* ctx);
+RLB200_API const char* rlb200_last_error(const rlb200_ctx* ctx);
+RLB200_API int rlb200_set_stream(rlb200_ctx* ctx, void* stream);
+RLB200_API int rlb200_synchronize(rlb200_ctx* ctx);
+/* Row-sharding: this process holds rows [row_offset, row_offset+m_local) of an m_global-row matrix. */
+RLB200_API int rlb200_set_shard(rlb200_ctx* ctx, int64_t row_offset, int64_t m_global, rlb200_allreduce_fn fn, void* user);
+/* kernels launched since creation / last reset (for bench.py's gpu_launches). */
+RLB200_API int64_t rlb200_launch_count(rlb200_ctx* ctx, int reset);
+/* CUDA-event timing of the kernels tagged `which` (see RLB200_TIMER_*), ms since last reset. */
+enum { RLB200_TIMER_GEMM_NN = 0, RLB200_TIMER_GEMM_TN = 1, RLB200_TIMER_RIGHTMUL = 2, RLB200_TIMER_SMALL = 3, RLB200_TIMER_FILL = 4, RLB200_TIMER_COUNT = 5 };
+RLB200_API int rlb200_timers_enable(rlb200_ctx* ctx, int on);
+RLB200_API int rlb200_timer_read(rlb200_ctx* ctx, int which, double* ms, int64_t* launches, int reset);
+
+/* ---- a1: Philox4x32-10 stream (r123::Philox4x32 via RandBLAS/RandBLAS/base.hh:53) -----------
+ * out_dev[4*i .. 4*i+3] = Philox(counter = state.counter + i, key = state.key), i in [0,n). */
+RLB200_API int rlb200_philox_stream_dev(rlb200_ctx* ctx, const uint32_t state[6], int64_t n, uint32_t* out_dev);
+
+/* ---- a2-a4: RandBLAS::fill_dense / fill_dense_unpacked (dense_skops.hh:560-603, 620-655) ----
+ * Writes the sub_rows x sub_cols block at (ro, co) of the sample of
+ * DenseDist(n_rows, n_cols, family, major_axis) defined by `state`, in `layout`
+ * (NATURAL = D.natural_layout), to buff_dev with leading dimension = the block's own extent.
+ * state <- the reference's returned next state. */
+RLB200_API int rlb200_fill_dense_f64_dev(rlb200_ctx* ctx, int64_t n_rows, int64_t n_cols, int family, int major_axis, int layout,
+                              int64_t sub_rows, int64_t sub_cols, int64_t ro, int64_t co, double* buff_dev, uint32_t state[6]);
+RLB200_API int rlb200_fill_dense_f32_dev(rlb200_ctx* ctx, int64_t n_rows, int64_t n_cols, int family, int major_axis, int layout,
+                              int64_t sub_rows, int64_t sub_cols, int64_t ro, int64_t co, float* buff_dev, uint32_t state[6]);
+
+/* ---- blas::gemm as used on the path (ColMajor; rl_rs.hh:142,153,165; rl_rf.hh:123; rl_qb.hh:218;
+ *      rl_rsvd.hh:148).  transa/transb: 0 = NoTrans, 1 = Trans.  Shapes the tall-skinny kernels cover:
+ *      NN with the long dimension on m; TN with the long dimension on k (split-K, deterministic). */
+RLB200_API int rlb200_gemm_f64_dev(rlb200_ctx* ctx, int transa, int transb, int64_t m, int64_t n, int64_t k, double alpha,
+                        const double* A_dev, int64_t lda, const double* B_dev, int64_t ldb, double beta, double* C_dev, int64_t ldc);
+RLB200_API int rlb200_gemm_f32_dev(rlb200_ctx* ctx, int transa, int transb, int64_t m, int64_t n, int64_t k, float alpha,
+                        const float* A_dev, int64_t lda, const float* B_dev, int64_t ldb, float beta, float* C_dev, int64_t ldc);
+
+/* ---- a8/a9: Stabilization<T>::call(m, k, A) (rl_orth.hh:13-23): CholQRQ :68-98, HQRQ :144-164,
+ *      PLUL :211-230.  In place on the m x k column-major A_dev (lda = m).
+ *      Returns 0, or 1 exactly where the reference does (potrf failure -> chol_fail; cond check). */
+RLB200_API int rlb200_stab_f64_dev(rlb200_ctx* ctx, int kind, int64_t m, int64_t k, double* A_dev, int cond_check, int* chol_fail);
+RLB200_API int rlb200_stab_f32_dev(rlb200_ctx* ctx, int kind, int64_t m, int64_t k, float* A_dev, int cond_check, int* chol_fail);
+
+/* ---- a10: RS<T,RNG>::call(m, n, A, k, Omega, state) (rl_rs.hh:116-178) ----------------------
+ * Omega_dev: n x k.  work_dev: m x k scratch (the reference's Omega_1), may be NULL when p == 0.
+ * Returns 0 / 1 (stabiliser failure). */
+RLB200_API int rlb200_rs_f64_dev(rlb200_ctx* ctx, int64_t m, int64_t n, const double* A_dev, int64_t k, double* Omega_dev,
+                      double* work_dev, uint32_t state[6], const rlb200_stack_opts* opts);
+RLB200_API int rlb200_rs_f32_dev(rlb200_ctx* ctx, int64_t m, int64_t n, const float* A_dev, int64_t k, float* Omega_dev,
+                      float* work_dev, uint32_t state[6], const rlb200_stack_opts* opts);
+
+/* ---- a11: RF<T,RNG>::call(m, n, A, k, Q, state) (rl_rf.hh:106-137) --------------------------
+ * Q_dev: m x k (also used as RS scratch before being overwritten).  Returns 0 / 1 / 2. */
+RLB200_API int rlb200_rf_f64_dev(rlb200_ctx* ctx, int64_t m, int64_t n, const double* A_dev, int64_t k, double* Q_dev,
+                      uint32_t state[6], const rlb200_stack_opts* opts);
+RLB200_API int rlb200_rf_f32_dev(rlb200_ctx* ctx, int64_t m, int64_t n, const float* A_dev, int64_t k, float* Q_dev,
+                      uint32_t state[6], const rlb200_stack_opts* opts);
+
+/* ---- a12: QB<T,RNG>::call(m, n, A, k, block_sz, tol, Q, BT, state) (rl_qb.hh:133-268) -------
+ * Q_dev: m x k, BT_dev: n x k caller-allocated for the requested k; *k is in/out as in the reference.
+ * With block_sz == k (single block) A_dev is only read; with block_sz < k the reference deflates a
+ * COPY of A (rl_qb.hh:162,171,260): pass Acpy_dev (m x n scratch) or NULL to deflate A_dev in place.
+ * Returns the reference's codes 0/2/3/4/5/6. */
+RLB200_API int rlb200_qb_f64_dev(rlb200_ctx* ctx, int64_t m, int64_t n, double* A_dev, int64_t* k, int64_t block_sz, double tol,
+                      double* Q_dev, double* BT_dev, double* Acpy_dev, uint32_t state[6], const rlb200_stack_opts* opts);
+RLB200_API int rlb200_qb_f32_dev(rlb200_ctx* ctx, int64_t m, int64_t n, float* A_dev, int64_t* k, int64_t block_sz, float tol,
+                      float* Q_dev, float* BT_dev, float* Acpy_dev, uint32_t state[6], const rlb200_stack_opts* opts);
+
+/* ---- a13: RSVD<T,RNG>::call(m, n, A, k, tol, U, S, V, state) (rl_rsvd.hh:113-154) -----------
+ * U_dev: m x k, S_dev: k, V_dev: n x k for the requested k; *k in/out.  U is formed in the Q buffer
+ * (U_dev doubles as Q), so no second m x k allocation exists.  Returns 0 (the reference ignores QB's code);
+ * qb_code (optional) receives QB's code. */
+RLB200_API int rlb200_rsvd_f64_dev(rlb200_ctx* ctx, int64_t m, int64_t n, double* A_dev, int64_t* k, double tol, double* U_dev,
+                        double* S_dev, double* V_dev, double* Acpy_dev, uint32_t state[6], const rlb200_stack_opts* opts, int* qb_code);
+RLB200_API int rlb200_rsvd_f32_dev(rlb200_ctx* ctx, int64_t m, int64_t n, float* A_dev, int64_t* k, float tol, float* U_dev,
+                        float* S_dev, float* V_dev, float* Acpy_dev, uint32_t state[6], const rlb200_stack_opts* opts, int* qb_code);
+
+/* Host-pointer form of the same call: A, U, S, V are HOST buffers (U: m x k, S: k, V: n x k for the
+ * requested k, caller-allocated); copies A to the device, runs rlb200_rsvd_*_dev, copies results back. */
+RLB200_API int rlb200_rsvd_f64_host(rlb200_ctx* ctx, int64_t m, int64_t n, const double* A, int64_t* k, double tol, double* U,
+                         double* S, double* V, uint32_t state[6], const rlb200_stack_opts* opts, int* qb_code);
+RLB200_API int rlb200_rsvd_f32_host(rlb200_ctx* ctx, int64_t m, int64_t n, const float* A, int64_t* k, float tol, float* U,
+                         float* S, float* V, uint32_t state[6], const rlb200_stack_opts* opts, int* qb_code);
+
+/* ---- lapack::gesdd(SomeVec) of a tall n x k matrix as used at rl_rsvd.hh:146 ----------------
+ * B_dev (n x k, ld n) is overwritten by its left singular vectors (n x k), S_dev by the singular
+ * values (descending), W_dev (k x k, ld k) by the RIGHT singular vectors as columns (so B_in = B_out diag(S) W^T). */
+RLB200_API int rlb200_svd_tall_f64_dev(rlb200_ctx* ctx, int64_t n, int64_t k, double* B_dev, double* S_dev, double* W_dev);
+RLB200_API int rlb200_svd_tall_f32_dev(rlb200_ctx* ctx, int64_t n, int64_t k, float* B_dev, float* S_dev, float* W_dev);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RLB200_H */

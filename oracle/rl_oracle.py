@@ -231,12 +231,13 @@ class RS:
         dt = A.dtype
         if p % 2 == 0:                                             # :132-135
             Om, state = fill_dense(n, k, state, dt)
-            Om = _F(Om)
+            # the natural-layout buffer is handed to BLAS as a column-major n x k matrix (:153), whatever D.natural_layout is
+            Om = _F(np.ravel(Om, order="K").reshape((n, k), order="F"))
             if omega_override is not None:
                 Om = _F(omega_override.astype(dt))
         else:                                                      # :136-149
             Om1, state = fill_dense(m, k, state, dt)
-            Om1 = _F(Om1)
+            Om1 = _F(np.ravel(Om1, order="K").reshape((m, k), order="F"))
             if omega_override is not None:
                 Om1 = _F(omega_override.astype(dt))
             Om = _gemm(A, Om1, ta=True)

@@ -1,0 +1,427 @@
+"""randlapack_b200 — host-side mirror of RandLAPACK's algorithm objects over librlb200.so.
+
+The product is the sm_100a shared library behind the C-ABI of include/rlb200.h (C++ host code +
+hand-written CUDA kernels).  This package is the thin Python veneer the tests and bench.py drive it
+through: it mirrors the reference's objects for this path — RNGState, DenseDist/fill_dense, CholQRQ,
+RS, RF, QB, RSVD (same constructor arguments, public fields, return codes) — and uses torch only for
+device memory, streams and torch.distributed plumbing.
+
+Matrices are torch CUDA tensors in COLUMN-MAJOR storage (shape (m, n), strides (1, m)); `empty_f`,
+`to_f` build them.  Nothing here computes on the CPU and nothing imports oracle/.
+"""
+from __future__ import annotations
+
+import ctypes
+from dataclasses import dataclass
+
+from . import _capi
+from ._capi import (STAB_PLUL, STAB_CHOLQRQ, STAB_HQRQ, FAMILY_GAUSSIAN, FAMILY_UNIFORM, AXIS_LONG, AXIS_SHORT,  # noqa: F401
+                    LAYOUT_NATURAL, LAYOUT_COLMAJOR, LAYOUT_ROWMAJOR, StackOpts)
+
+__all__ = ["Context", "RNGState", "DenseDist", "fill_dense", "CholQRQ", "PLUL", "HQRQ", "RS", "RF", "QB", "RSVD", "empty_f",
+           "to_f", "Error", "shard_rows"]
+
+
+class Error(RuntimeError):
+    """Raised for negative RLB200_ERR_* codes (what RandLAPACK::Error / RandBLAS::Error / a CUDA abort are in the reference)."""
+
+    def __init__(self, code, msg):
+        super().__init__(f"rlb200 error {code}: {msg}")
+        self.code = code
+
+
+def _torch():
+    import torch
+    return torch
+
+
+def empty_f(m, n, dtype, device):
+    """Uninitialised m x n column-major matrix."""
+    torch = _torch()
+    return torch.empty((n, m), dtype=dtype, device=device).t()
+
+
+def to_f(x):
+    """Column-major copy of a 2-D tensor (no-op if it already is)."""
+    if x.dim() == 2 and x.stride(0) == 1 and (x.stride(1) == x.shape[0] or x.shape[1] <= 1):
+        return x
+    return x.t().contiguous().t()
+
+
+def _is_f(x):
+    return x.dim() == 2 and x.stride(0) == 1 and (x.stride(1) == x.shape[0] or x.shape[1] <= 1) or x.dim() == 1 and x.is_contiguous()
+
+
+def _suffix(dtype):
+    torch = _torch()
+    if dtype == torch.float64:
+        return "f64"
+    if dtype == torch.float32:
+        return "f32"
+    raise TypeError("T must be float or double, as in the reference")
+
+
+class RNGState:
+    """RandBLAS::RNGState<r123::Philox4x32> (RandBLAS/RandBLAS/base.hh:64-164)."""
+
+    def __init__(self, key=0, counter=(0, 0, 0, 0)):
+        if isinstance(key, (tuple, list)):
+            self.key = tuple(int(x) & 0xFFFFFFFF for x in key)
+        else:   # RNGState(uint64 k): zero key incremented by k (base.hh:119)
+            self.key = (int(key) & 0xFFFFFFFF, (int(key) >> 32) & 0xFFFFFFFF)
+        self.counter = tuple(int(c) & 0xFFFFFFFF for c in counter)
+
+    def words(self):
+        return (ctypes.c_uint32 * 6)(*self.counter, *self.key)
+
+    def assign(self, w):
+        self.counter, self.key = (w[0], w[1], w[2], w[3]), (w[4], w[5])
+
+    def copy(self):
+        return RNGState(self.key, self.counter)
+
+    def __eq__(self, o):
+        return self.counter == o.counter and self.key == o.key
+
+    def __repr__(self):
+        return f"RNGState(counter={self.counter}, key={self.key})"
+
+
+class Context:
+    """Opaque rlb200_ctx: device, stream, workspaces, optional row-shard description."""
+
+    def __init__(self, device=None, stream=None):
+        torch = _torch()
+        self._lib = _capi.load()
+        if not torch.cuda.is_available():
+            raise Error(_capi.ERR_CUDA, "no CUDA device: librlb200 has no CPU fallback")
+        if device is None:
+            device = torch.cuda.current_device()
+        self.device = torch.device("cuda", device if isinstance(device, int) else device.index)
+        with torch.cuda.device(self.device):
+            s = stream if stream is not None else torch.cuda.current_stream().cuda_stream
+        h = ctypes.c_void_p()
+        rc = self._lib.rlb200_create(ctypes.byref(h), self.device.index, ctypes.c_void_p(s))
+        if rc:
+            raise Error(rc, "rlb200_create failed (needs an sm_100 device)")
+        self._h = h
+        self._hook = None
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.rlb200_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def check(self, rc):
+        if rc < 0:
+            raise Error(rc, self._lib.rlb200_last_error(self._h).decode())
+        return rc
+
+    def synchronize(self):
+        self.check(self._lib.rlb200_synchronize(self._h))
+
+    def launch_count(self, reset=False):
+        return self._lib.rlb200_launch_count(self._h, int(reset))
+
+    def timers_enable(self, on=True):
+        self.check(self._lib.rlb200_timers_enable(self._h, int(on)))
+
+    def timer_read(self, which, reset=False):
+        ms, n = ctypes.c_double(), ctypes.c_int64()
+        self.check(self._lib.rlb200_timer_read(self._h, which, ctypes.byref(ms), ctypes.byref(n), int(reset)))
+        return ms.value, n.value
+
+    # ---- row sharding over torch.distributed -------------------------------------------------
+    def set_shard(self, row_offset, m_global, group=None):
+        """This rank holds rows [row_offset, row_offset + m_local) of an m_global-row A.  Gram / B^T / norm
+        partials are sum-allreduced over `group` (torch.distributed; NCCL on GPUs)."""
+        self._hook = _capi.ALLREDUCE_FN(make_allreduce_hook(group))
+        self.check(self._lib.rlb200_set_shard(self._h, row_offset, m_global, self._hook, None))
+
+    def clear_shard(self):
+        self._hook = None
+        self.check(self._lib.rlb200_set_shard(self._h, 0, -1, ctypes.cast(None, _capi.ALLREDUCE_FN), None))
+
+
+def shard_rows(m_global, world_size, rank, align=128):
+    """Row block [r0, r1) of rank `rank`: contiguous, aligned to `align` rows (a multiple of 4 keeps every
+    shard's first row on a Philox counter boundary of the odd-p operator, RandBLAS dense_skops.hh:109-123)."""
+    per = -(-m_global // world_size)
+    per = -(-per // align) * align
+    r0 = min(m_global, rank * per)
+    r1 = min(m_global, r0 + per)
+    return r0, r1
+
+
+class _CudaBuf:
+    def __init__(self, ptr, nbytes):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 3}
+
+
+def make_allreduce_hook(group=None):
+    """Build the rlb200_allreduce_fn callback: sum-allreduce `count` elements at `buf` over `group`.
+    Device buffers (NCCL) are wrapped zero-copy; host buffers (gloo, used by the CPU tests of this plumbing)
+    are wrapped through ctypes."""
+    torch = _torch()
+    import torch.distributed as dist
+
+    def hook(user, buf, count, elem_size, stream):
+        try:
+            dt = {8: torch.float64, 4: torch.float32}[elem_size]
+            backend = dist.get_backend(group)
+            if backend == "nccl":
+                t = torch.as_tensor(_CudaBuf(buf, count * elem_size), device="cuda").view(dt)
+                ext = torch.cuda.ExternalStream(stream) if stream else torch.cuda.default_stream()
+                with torch.cuda.stream(ext):
+                    dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+            else:
+                import numpy as np
+                arr = np.ctypeslib.as_array(ctypes.cast(buf, ctypes.POINTER(ctypes.c_uint8)), shape=(count * elem_size,))
+                t = torch.from_numpy(arr).view(dt)
+                dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+            return 0
+        except Exception as e:  # never let an exception unwind through the C frames
+            import sys
+            print(f"[rlb200 allreduce hook] {type(e).__name__}: {e}", file=sys.stderr)
+            return 1
+    return hook
+
+
+# --------------------------------------------------------------------------------------------------
+# RandBLAS dense operators
+# --------------------------------------------------------------------------------------------------
+@dataclass
+class DenseDist:
+    """RandBLAS::DenseDist (RandBLAS/RandBLAS/dense_skops.hh:228-347)."""
+    n_rows: int
+    n_cols: int
+    family: int = FAMILY_GAUSSIAN
+    major_axis: int = AXIS_LONG
+
+    def __post_init__(self):
+        if self.n_rows <= 0 or self.n_cols <= 0:
+            raise Error(_capi.ERR_ARG, "randblas_require(n_rows > 0 && n_cols > 0)")
+        mx, mn = max(self.n_rows, self.n_cols), min(self.n_rows, self.n_cols)
+        self.dim_major = mx if self.major_axis == AXIS_LONG else mn
+        self.dim_minor = self.n_rows + self.n_cols - self.dim_major
+        self.isometry_scale = float(self.dim_minor) ** -0.5
+        is_wide, fa_long = self.n_rows < self.n_cols, self.major_axis == AXIS_LONG
+        self.natural_layout = LAYOUT_ROWMAJOR if (is_wide and fa_long) or (not is_wide and not fa_long) else LAYOUT_COLMAJOR
+
+
+def fill_dense(ctx: Context, D: DenseDist, state: RNGState, dtype=None, layout=LAYOUT_NATURAL, sub=None):
+    """RandBLAS::fill_dense(D, buff, seed) -> next state (dense_skops.hh:620-623) and fill_dense_unpacked (:560-603).
+    Returns (buffer as a 1-D device tensor in the requested layout, next RNGState)."""
+    torch = _torch()
+    dtype = dtype or torch.float64
+    sub_rows, sub_cols, ro, co = sub if sub is not None else (D.n_rows, D.n_cols, 0, 0)
+    buf = torch.empty(max(sub_rows * sub_cols, 1), dtype=dtype, device=ctx.device)
+    w = state.words()
+    fn = getattr(ctx._lib, f"rlb200_fill_dense_{_suffix(dtype)}_dev")
+    ctx.check(fn(ctx._h, D.n_rows, D.n_cols, D.family, D.major_axis, layout, sub_rows, sub_cols, ro, co, buf.data_ptr(), w))
+    nxt = RNGState()
+    nxt.assign(w)
+    return buf[: sub_rows * sub_cols], nxt
+
+
+def philox_stream(ctx: Context, state: RNGState, n: int):
+    torch = _torch()
+    out = torch.empty((max(n, 1), 4), dtype=torch.int32, device=ctx.device)
+    ctx.check(ctx._lib.rlb200_philox_stream_dev(ctx._h, state.words(), n, out.data_ptr()))
+    return out[:n]
+
+
+def gemm(ctx: Context, transa, transb, alpha, A, B, beta=0.0, C=None):
+    """blas::gemm(ColMajor, ...) on column-major device tensors, shapes as BLAS defines them."""
+    m = A.shape[1] if transa else A.shape[0]
+    k = A.shape[0] if transa else A.shape[1]
+    n = B.shape[0] if transb else B.shape[1]
+    assert _is_f(A) and _is_f(B)
+    if C is None:
+        C = empty_f(m, n, A.dtype, A.device)
+        beta = 0.0
+    fn = getattr(ctx._lib, f"rlb200_gemm_{_suffix(A.dtype)}_dev")
+    ctx.check(fn(ctx._h, int(transa), int(transb), m, n, k, alpha, A.data_ptr(), max(A.stride(1), A.shape[0]) if A.shape[1] > 1 else A.shape[0],
+                 B.data_ptr(), max(B.stride(1), B.shape[0]) if B.shape[1] > 1 else B.shape[0], beta, C.data_ptr(),
+                 max(C.stride(1), C.shape[0]) if C.shape[1] > 1 else C.shape[0]))
+    return C
+
+
+# --------------------------------------------------------------------------------------------------
+# Algorithm objects (RandLAPACK/comps, RandLAPACK/drivers)
+# --------------------------------------------------------------------------------------------------
+class _Stab:
+    kind = None
+
+    def __init__(self, cond_check=False, verbose=False):
+        self.cond_check, self.verbose = cond_check, verbose
+        self.chol_fail = False
+
+    def call(self, ctx: Context, A):
+        """Stabilization<T>::call(m, k, A) (rl_orth.hh:13-23): in place; returns the reference's int code."""
+        assert _is_f(A)
+        m, k = A.shape
+        cf = ctypes.c_int(0)
+        fn = getattr(ctx._lib, f"rlb200_stab_{_suffix(A.dtype)}_dev")
+        rc = ctx.check(fn(ctx._h, self.kind, m, k, A.data_ptr(), int(self.cond_check), ctypes.byref(cf)))
+        self.chol_fail = bool(cf.value)
+        return rc
+
+
+class CholQRQ(_Stab):
+    """RandLAPACK::CholQRQ (rl_orth.hh:25-98)."""
+    kind = STAB_CHOLQRQ
+
+
+class PLUL(_Stab):
+    """RandLAPACK::PLUL (rl_orth.hh:166-230)."""
+    kind = STAB_PLUL
+
+
+class HQRQ(_Stab):
+    """RandLAPACK::HQRQ (rl_orth.hh:100-164)."""
+    kind = STAB_HQRQ
+
+
+class RS:
+    """RandLAPACK::RS(stab, p, q, verbose, cond_check) (rl_rs.hh:31-178)."""
+
+    def __init__(self, stab_obj, p, q, verbose=False, cond_check=False):
+        self.Stab_Obj, self.passes_over_data, self.passes_per_stab = stab_obj, p, q
+        self.verbose, self.cond_check = verbose, cond_check
+
+    def _opts(self, o: StackOpts):
+        o.passes_over_data, o.passes_per_stab, o.stab = self.passes_over_data, self.passes_per_stab, self.Stab_Obj.kind
+        o.cond_check = int(self.cond_check or self.Stab_Obj.cond_check)
+
+    def call(self, ctx: Context, A, k, state: RNGState):
+        """-> (rc, Omega n x k).  `state` is advanced in place like the reference's in/out reference."""
+        torch = _torch()
+        m, n = A.shape
+        o = StackOpts()
+        self._opts(o)
+        Omega = empty_f(n, k, A.dtype, A.device)
+        work = empty_f(m, k, A.dtype, A.device) if self.passes_over_data > 0 else None
+        w = state.words()
+        fn = getattr(ctx._lib, f"rlb200_rs_{_suffix(A.dtype)}_dev")
+        rc = ctx.check(fn(ctx._h, m, n, A.data_ptr(), k, Omega.data_ptr(), work.data_ptr() if work is not None else None, w,
+                          ctypes.byref(o)))
+        state.assign(w)
+        return rc, Omega
+
+
+class RF:
+    """RandLAPACK::RF(rs, orth, verbose, cond_check) (rl_rf.hh:31-137)."""
+
+    def __init__(self, rs_obj, orth_obj, verbose=False, cond_check=False):
+        self.rs, self.orth, self.verbose, self.cond_check = rs_obj, orth_obj, verbose, cond_check
+
+    def _opts(self, o: StackOpts):
+        self.rs._opts(o)
+        o.orth_rf = self.orth.kind
+
+    def call(self, ctx: Context, A, k, state: RNGState, Q=None):
+        m, n = A.shape
+        o = StackOpts()
+        self._opts(o)
+        if Q is None:
+            Q = empty_f(m, k, A.dtype, A.device)
+        w = state.words()
+        fn = getattr(ctx._lib, f"rlb200_rf_{_suffix(A.dtype)}_dev")
+        rc = ctx.check(fn(ctx._h, m, n, A.data_ptr(), k, Q.data_ptr(), w, ctypes.byref(o)))
+        state.assign(w)
+        return rc, Q
+
+
+class QB:
+    """RandLAPACK::QB(rf, orth, verbose, orth_check) (rl_qb.hh:36-268)."""
+
+    def __init__(self, rf_obj, orth_obj, verbose=False, orth_check=False):
+        self.rf, self.orth, self.verbose, self.orth_check = rf_obj, orth_obj, verbose, orth_check
+
+    def _opts(self, o: StackOpts):
+        self.rf._opts(o)
+        o.orth_qb, o.orth_check = self.orth.kind, int(self.orth_check)
+
+    def call(self, ctx: Context, A, k, block_sz, tol, state: RNGState, Q=None, BT=None):
+        """-> (rc, k_out, Q m x k, BT n x k); columns beyond k_out are unspecified."""
+        m, n = A.shape
+        o = StackOpts()
+        self._opts(o)
+        o.block_sz = block_sz
+        if Q is None:
+            Q = empty_f(m, k, A.dtype, A.device)
+        if BT is None:
+            BT = empty_f(n, k, A.dtype, A.device)
+        kk = ctypes.c_int64(k)
+        w = state.words()
+        fn = getattr(ctx._lib, f"rlb200_qb_{_suffix(A.dtype)}_dev")
+        rc = ctx.check(fn(ctx._h, m, n, A.data_ptr(), ctypes.byref(kk), block_sz, tol, Q.data_ptr(), BT.data_ptr(), None, w,
+                          ctypes.byref(o)))
+        state.assign(w)
+        return rc, kk.value, Q, BT
+
+
+class RSVD:
+    """RandLAPACK::RSVD(qb, block_sz) (rl_rsvd.hh:34-154)."""
+
+    def __init__(self, qb_obj, block_sz):
+        self.QB_Obj, self.block_sz = qb_obj, block_sz
+        self.qb_code = None
+
+    def _opts(self):
+        o = StackOpts()
+        self.QB_Obj._opts(o)
+        o.block_sz = self.block_sz
+        return o
+
+    def call(self, ctx: Context, A, k, tol, state: RNGState, U=None, S=None, V=None):
+        """Device-resident call -> (rc, k_out, U m x k, S k, V n x k).  A is only read when block_sz == k."""
+        torch = _torch()
+        m, n = A.shape
+        o = self._opts()
+        if U is None:
+            U = empty_f(m, k, A.dtype, A.device)
+        if S is None:
+            S = torch.empty(k, dtype=A.dtype, device=A.device)
+        if V is None:
+            V = empty_f(n, k, A.dtype, A.device)
+        kk, qc = ctypes.c_int64(k), ctypes.c_int(0)
+        w = state.words()
+        fn = getattr(ctx._lib, f"rlb200_rsvd_{_suffix(A.dtype)}_dev")
+        rc = ctx.check(fn(ctx._h, m, n, A.data_ptr(), ctypes.byref(kk), tol, U.data_ptr(), S.data_ptr(), V.data_ptr(), None, w,
+                          ctypes.byref(o), ctypes.byref(qc)))
+        state.assign(w)
+        self.qb_code = qc.value
+        return rc, kk.value, U, S, V
+
+    def call_host(self, ctx: Context, A_host, k, tol, state: RNGState):
+        """The reference-facing form: HOST column-major A in, host U, S, V out (copies inside)."""
+        torch = _torch()
+        m, n = A_host.shape
+        assert _is_f(A_host) and not A_host.is_cuda
+        o = self._opts()
+        U = empty_f(m, k, A_host.dtype, "cpu")
+        S = torch.empty(k, dtype=A_host.dtype)
+        V = empty_f(n, k, A_host.dtype, "cpu")
+        kk, qc = ctypes.c_int64(k), ctypes.c_int(0)
+        w = state.words()
+        fn = getattr(ctx._lib, f"rlb200_rsvd_{_suffix(A_host.dtype)}_host")
+        rc = ctx.check(fn(ctx._h, m, n, A_host.data_ptr(), ctypes.byref(kk), tol, U.data_ptr(), S.data_ptr(), V.data_ptr(), w,
+                          ctypes.byref(o), ctypes.byref(qc)))
+        state.assign(w)
+        self.qb_code = qc.value
+        return rc, kk.value, U, S, V
+
+
+def svd_tall(ctx: Context, B):
+    """lapack::gesdd(SomeVec) of a tall n x k device matrix: returns (left vectors n x k [in place], S, right vectors k x k)."""
+    torch = _torch()
+    n, k = B.shape
+    S = torch.empty(k, dtype=B.dtype, device=B.device)
+    W = empty_f(k, k, B.dtype, B.device)
+    fn = getattr(ctx._lib, f"rlb200_svd_tall_{_suffix(B.dtype)}_dev")
+    ctx.check(fn(ctx._h, n, k, B.data_ptr(), S.data_ptr(), W.data_ptr()))
+    return B, S, W

@@ -1,0 +1,79 @@
+"""ctypes binding of librlb200.so (the C-ABI declared in include/rlb200.h).
+
+The library is the product; this module only loads it and declares argument types.  There is no
+Python/CPU fallback: if the shared library is missing the import raises, and every compute call
+returns RLB200_ERR_CUDA (raised as RuntimeError) when no sm_100 device is usable.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "librlb200.so")
+
+OK, ERR_ARG, ERR_CUDA, ERR_ALLOC, ERR_COLLECTIVE, ERR_UNSUPPORTED = 0, -1, -2, -3, -4, -5
+STAB_PLUL, STAB_CHOLQRQ, STAB_HQRQ = 0, 1, 2
+FAMILY_GAUSSIAN, FAMILY_UNIFORM = 0, 1
+AXIS_LONG, AXIS_SHORT = 0, 1
+LAYOUT_NATURAL, LAYOUT_COLMAJOR, LAYOUT_ROWMAJOR = 0, 1, 2
+TIMER_GEMM_NN, TIMER_GEMM_TN, TIMER_RIGHTMUL, TIMER_SMALL, TIMER_FILL = 0, 1, 2, 3, 4
+
+c_i64, c_i32, c_u32, c_int, c_vp = ctypes.c_int64, ctypes.c_int32, ctypes.c_uint32, ctypes.c_int, ctypes.c_void_p
+P_u32, P_i64, P_int = ctypes.POINTER(c_u32), ctypes.POINTER(c_i64), ctypes.POINTER(c_int)
+
+
+class StackOpts(ctypes.Structure):
+    """rlb200_stack_opts (include/rlb200.h) — the canonical stack of test/drivers/test_rsvd.cc:68-93."""
+    _fields_ = [("passes_over_data", c_i64), ("passes_per_stab", c_i64), ("block_sz", c_i64), ("stab", c_i32),
+                ("orth_rf", c_i32), ("orth_qb", c_i32), ("cond_check", c_i32), ("orth_check", c_i32), ("reserved", c_i32)]
+
+
+ALLREDUCE_FN = ctypes.CFUNCTYPE(c_int, c_vp, c_vp, c_i64, c_i32, c_vp)
+
+# name -> (restype, argtypes); mirrors include/rlb200.h one to one (tests/test_abi.py checks the header against this table)
+_F = lambda ft: {  # noqa: E731  typed entry points, ft = ctypes float type
+    "fill_dense": (c_int, [c_vp, c_i64, c_i64, c_int, c_int, c_int, c_i64, c_i64, c_i64, c_i64, c_vp, P_u32]),
+    "gemm": (c_int, [c_vp, c_int, c_int, c_i64, c_i64, c_i64, ft, c_vp, c_i64, c_vp, c_i64, ft, c_vp, c_i64]),
+    "stab": (c_int, [c_vp, c_int, c_i64, c_i64, c_vp, c_int, P_int]),
+    "rs": (c_int, [c_vp, c_i64, c_i64, c_vp, c_i64, c_vp, c_vp, P_u32, ctypes.POINTER(StackOpts)]),
+    "rf": (c_int, [c_vp, c_i64, c_i64, c_vp, c_i64, c_vp, P_u32, ctypes.POINTER(StackOpts)]),
+    "qb": (c_int, [c_vp, c_i64, c_i64, c_vp, P_i64, c_i64, ft, c_vp, c_vp, c_vp, P_u32, ctypes.POINTER(StackOpts)]),
+    "rsvd": (c_int, [c_vp, c_i64, c_i64, c_vp, P_i64, ft, c_vp, c_vp, c_vp, c_vp, P_u32, ctypes.POINTER(StackOpts), P_int]),
+    "svd_tall": (c_int, [c_vp, c_i64, c_i64, c_vp, c_vp, c_vp]),
+}
+SIGNATURES = {
+    "rlb200_abi_version": (c_int, []),
+    "rlb200_create": (c_int, [ctypes.POINTER(c_vp), c_int, c_vp]),
+    "rlb200_destroy": (c_int, [c_vp]),
+    "rlb200_last_error": (ctypes.c_char_p, [c_vp]),
+    "rlb200_set_stream": (c_int, [c_vp, c_vp]),
+    "rlb200_synchronize": (c_int, [c_vp]),
+    "rlb200_set_shard": (c_int, [c_vp, c_i64, c_i64, ALLREDUCE_FN, c_vp]),
+    "rlb200_launch_count": (c_i64, [c_vp, c_int]),
+    "rlb200_timers_enable": (c_int, [c_vp, c_int]),
+    "rlb200_timer_read": (c_int, [c_vp, c_int, ctypes.POINTER(ctypes.c_double), P_i64, c_int]),
+    "rlb200_philox_stream_dev": (c_int, [c_vp, P_u32, c_i64, c_vp]),
+}
+for _suf, _ft in (("f64", ctypes.c_double), ("f32", ctypes.c_float)):
+    for _name, _sig in _F(_ft).items():
+        SIGNATURES[f"rlb200_{_name}_{_suf}_dev"] = _sig
+    SIGNATURES[f"rlb200_rsvd_{_suf}_host"] = (c_int, [c_vp, c_i64, c_i64, c_vp, P_i64, _ft, c_vp, c_vp, c_vp, P_u32,
+                                                      ctypes.POINTER(StackOpts), P_int])
+
+_lib = None
+
+
+def load() -> ctypes.CDLL:
+    """Load librlb200.so and declare every signature.  Raises if the library was not built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                              "(make -C randlapack_b200/csrc). There is no fallback implementation.")
+        lib = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)   # AttributeError if the .so does not export a declared symbol
+            fn.restype, fn.argtypes = res, args
+        _lib = lib
+    return _lib

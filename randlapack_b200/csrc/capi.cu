@@ -1,0 +1,171 @@
+// extern "C" surface of librlb200.so (see include/rlb200.h for the contract of every entry point).
+#include "drivers.cuh"
+#include <new>
+
+using namespace rlb;
+
+struct rlb200_ctx : public rlb::Ctx {};
+
+#define CTX_OK(ctx)                              \
+    do { if (!(ctx)) return RLB200_ERR_ARG; } while (0)
+
+// every compute entry point binds the context's device first
+static int bind(rlb200_ctx* ctx) {
+    RLB_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+    return 0;
+}
+
+extern "C" {
+
+int rlb200_abi_version(void) { return RLB200_ABI_VERSION; }
+
+int rlb200_create(rlb200_ctx** out, int device, void* stream) {
+    if (!out) return RLB200_ERR_ARG;
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) { cudaGetLastError(); return RLB200_ERR_CUDA; }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return RLB200_ERR_CUDA;
+    if (prop.major != 10) return RLB200_ERR_UNSUPPORTED;   // sm_100a cubins only; no fallback path exists
+    rlb200_ctx* ctx = new (std::nothrow) rlb200_ctx();
+    if (!ctx) return RLB200_ERR_ALLOC;
+    ctx->device = device;
+    ctx->stream = static_cast<cudaStream_t>(stream);
+    ctx->num_sms = prop.multiProcessorCount;
+    if (cudaSetDevice(device) != cudaSuccess || cudaMallocHost(&ctx->hbox, 4096) != cudaSuccess) { delete ctx; return RLB200_ERR_CUDA; }
+    ctx->hbox_bytes = 4096;
+    *out = ctx;
+    return 0;
+}
+
+int rlb200_destroy(rlb200_ctx* ctx) {
+    if (!ctx) return 0;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    arena_destroy(ctx);
+    if (ctx->ws) cudaFree(ctx->ws);
+    if (ctx->hbox) cudaFreeHost(ctx->hbox);
+    for (auto& t : ctx->timers) { if (t.e0) cudaEventDestroy(t.e0); if (t.e1) cudaEventDestroy(t.e1); }
+    delete ctx;
+    return 0;
+}
+
+const char* rlb200_last_error(const rlb200_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int rlb200_set_stream(rlb200_ctx* ctx, void* stream) { CTX_OK(ctx); ctx->stream = static_cast<cudaStream_t>(stream); return 0; }
+
+int rlb200_synchronize(rlb200_ctx* ctx) {
+    CTX_OK(ctx);
+    RLB_CHECK(bind(ctx));
+    RLB_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int rlb200_set_shard(rlb200_ctx* ctx, int64_t row_offset, int64_t m_global, rlb200_allreduce_fn fn, void* user) {
+    CTX_OK(ctx);
+    if (m_global < 0) { ctx->row_offset = 0; ctx->m_global = -1; ctx->allreduce = nullptr; ctx->allreduce_user = nullptr; return 0; }
+    RLB_REQUIRE(ctx, row_offset >= 0 && row_offset <= m_global);
+    ctx->row_offset = row_offset; ctx->m_global = m_global; ctx->allreduce = fn; ctx->allreduce_user = user;
+    return 0;
+}
+
+int64_t rlb200_launch_count(rlb200_ctx* ctx, int reset) {
+    if (!ctx) return -1;
+    int64_t v = ctx->launches;
+    if (reset) ctx->launches = 0;
+    return v;
+}
+
+int rlb200_timers_enable(rlb200_ctx* ctx, int on) { CTX_OK(ctx); ctx->timers_on = on != 0; return 0; }
+
+int rlb200_timer_read(rlb200_ctx* ctx, int which, double* ms, int64_t* launches, int reset) {
+    CTX_OK(ctx);
+    RLB_REQUIRE(ctx, which >= 0 && which < RLB200_TIMER_COUNT);
+    Timer& t = ctx->timers[which];
+    if (t.pending) {
+        RLB_CUDA_OK(ctx, cudaEventSynchronize(t.e1));
+        float f = 0;
+        RLB_CUDA_OK(ctx, cudaEventElapsedTime(&f, t.e0, t.e1));
+        t.ms += f; t.pending = false;
+    }
+    if (ms) *ms = t.ms;
+    if (launches) *launches = t.launches;
+    if (reset) { t.ms = 0; t.launches = 0; }
+    return 0;
+}
+
+int rlb200_philox_stream_dev(rlb200_ctx* ctx, const uint32_t state[6], int64_t n, uint32_t* out_dev) {
+    CTX_OK(ctx); RLB_CHECK(bind(ctx));
+    return philox_stream(ctx, state, n, out_dev);
+}
+
+#define DEFINE_TYPED(T, SUF)                                                                                                        \
+    int rlb200_fill_dense_##SUF##_dev(rlb200_ctx* ctx, int64_t n_rows, int64_t n_cols, int family, int major_axis, int layout,      \
+                                      int64_t sub_rows, int64_t sub_cols, int64_t ro, int64_t co, T* buff_dev, uint32_t state[6]) { \
+        CTX_OK(ctx); RLB_CHECK(bind(ctx));                                                                                          \
+        return fill_dense_unpacked<T>(ctx, n_rows, n_cols, family, major_axis, layout, sub_rows, sub_cols, ro, co, buff_dev, state); \
+    }                                                                                                                               \
+    int rlb200_gemm_##SUF##_dev(rlb200_ctx* ctx, int transa, int transb, int64_t m, int64_t n, int64_t k, T alpha, const T* A,      \
+                                int64_t lda, const T* B, int64_t ldb, T beta, T* C, int64_t ldc) {                                  \
+        CTX_OK(ctx); RLB_CHECK(bind(ctx));                                                                                          \
+        if (!transa && !transb) return gemm_nn<T>(ctx, m, n, k, (double)alpha, A, lda, B, ldb, (double)beta, C, ldc);               \
+        if (!transa && transb)  return gemm_nt<T>(ctx, m, n, k, (double)alpha, A, lda, B, ldb, (double)beta, C, ldc);               \
+        if (transa && !transb)  return gemm_tn<T>(ctx, k, m, n, (double)alpha, A, lda, B, ldb, (double)beta, C, ldc, 0);            \
+        ctx->err = "gemm(Trans,Trans) is not on the sketch-and-factor path";                                                        \
+        return RLB200_ERR_UNSUPPORTED;                                                                                              \
+    }                                                                                                                               \
+    int rlb200_stab_##SUF##_dev(rlb200_ctx* ctx, int kind, int64_t m, int64_t k, T* A_dev, int cond_check, int* chol_fail) {        \
+        CTX_OK(ctx); RLB_CHECK(bind(ctx));                                                                                          \
+        if (chol_fail) *chol_fail = 0;                                                                                              \
+        return stab_call<T>(ctx, kind, m, k, A_dev, cond_check != 0, ctx->m_global >= 0, chol_fail);                                \
+    }                                                                                                                               \
+    int rlb200_rs_##SUF##_dev(rlb200_ctx* ctx, int64_t m, int64_t n, const T* A_dev, int64_t k, T* Omega_dev, T* work_dev,          \
+                              uint32_t state[6], const rlb200_stack_opts* opts) {                                                   \
+        CTX_OK(ctx); RLB_CHECK(bind(ctx)); RLB_REQUIRE(ctx, opts && state);                                                         \
+        return rs_call<T>(ctx, m, n, A_dev, k, Omega_dev, work_dev, state, *opts);                                                  \
+    }                                                                                                                               \
+    int rlb200_rf_##SUF##_dev(rlb200_ctx* ctx, int64_t m, int64_t n, const T* A_dev, int64_t k, T* Q_dev, uint32_t state[6],        \
+                              const rlb200_stack_opts* opts) {                                                                      \
+        CTX_OK(ctx); RLB_CHECK(bind(ctx)); RLB_REQUIRE(ctx, opts && state);                                                         \
+        return rf_call<T>(ctx, m, n, A_dev, k, Q_dev, state, *opts);                                                                \
+    }                                                                                                                               \
+    int rlb200_qb_##SUF##_dev(rlb200_ctx* ctx, int64_t m, int64_t n, T* A_dev, int64_t* k, int64_t block_sz, T tol, T* Q_dev,       \
+                              T* BT_dev, T* Acpy_dev, uint32_t state[6], const rlb200_stack_opts* opts) {                           \
+        CTX_OK(ctx); RLB_CHECK(bind(ctx)); RLB_REQUIRE(ctx, opts && state);                                                         \
+        return qb_call<T>(ctx, m, n, A_dev, k, block_sz, tol, Q_dev, BT_dev, Acpy_dev, state, *opts);                               \
+    }                                                                                                                               \
+    int rlb200_rsvd_##SUF##_dev(rlb200_ctx* ctx, int64_t m, int64_t n, T* A_dev, int64_t* k, T tol, T* U_dev, T* S_dev, T* V_dev,   \
+                                T* Acpy_dev, uint32_t state[6], const rlb200_stack_opts* opts, int* qb_code) {                      \
+        CTX_OK(ctx); RLB_CHECK(bind(ctx)); RLB_REQUIRE(ctx, opts && state);                                                         \
+        return rsvd_call<T>(ctx, m, n, A_dev, k, tol, U_dev, S_dev, V_dev, Acpy_dev, state, *opts, qb_code);                        \
+    }                                                                                                                               \
+    int rlb200_svd_tall_##SUF##_dev(rlb200_ctx* ctx, int64_t n, int64_t k, T* B_dev, T* S_dev, T* W_dev) {                          \
+        CTX_OK(ctx); RLB_CHECK(bind(ctx));                                                                                          \
+        ArenaScope as(ctx);                                                                                                         \
+        void* ws = arena_push(ctx, svd_ws_bytes(n, k, sizeof(T)));                                                                  \
+        if (!ws) return RLB200_ERR_ALLOC;                                                                                           \
+        return svd_tall<T>(ctx, n, k, B_dev, n, S_dev, W_dev, ws, nullptr);                                                         \
+    }                                                                                                                               \
+    int rlb200_rsvd_##SUF##_host(rlb200_ctx* ctx, int64_t m, int64_t n, const T* A, int64_t* k, T tol, T* U, T* S, T* V,            \
+                                 uint32_t state[6], const rlb200_stack_opts* opts, int* qb_code) {                                  \
+        CTX_OK(ctx); RLB_CHECK(bind(ctx)); RLB_REQUIRE(ctx, opts && state && k && *k > 0 && m > 0 && n > 0 && A && U && S && V);    \
+        ArenaScope as(ctx);                                                                                                         \
+        const int64_t k_in = *k;                                                                                                    \
+        T* dA = as.take<T>((size_t)m * n); if (!dA) return RLB200_ERR_ALLOC;                                                        \
+        T* dU = as.take<T>((size_t)m * k_in); if (!dU) return RLB200_ERR_ALLOC;                                                     \
+        T* dS = as.take<T>((size_t)k_in); if (!dS) return RLB200_ERR_ALLOC;                                                         \
+        T* dV = as.take<T>((size_t)n * k_in); if (!dV) return RLB200_ERR_ALLOC;                                                     \
+        RLB_CUDA_OK(ctx, cudaMemcpyAsync(dA, A, sizeof(T) * m * n, cudaMemcpyHostToDevice, ctx->stream));                           \
+        int rc = rsvd_call<T>(ctx, m, n, dA, k, tol, dU, dS, dV, (T*)nullptr, state, *opts, qb_code);                               \
+        if (rc < 0) return rc;                                                                                                      \
+        RLB_CUDA_OK(ctx, cudaMemcpyAsync(U, dU, sizeof(T) * m * (*k), cudaMemcpyDeviceToHost, ctx->stream));                        \
+        RLB_CUDA_OK(ctx, cudaMemcpyAsync(S, dS, sizeof(T) * (*k), cudaMemcpyDeviceToHost, ctx->stream));                            \
+        RLB_CUDA_OK(ctx, cudaMemcpyAsync(V, dV, sizeof(T) * n * (*k), cudaMemcpyDeviceToHost, ctx->stream));                        \
+        RLB_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));                                                                       \
+        return rc;                                                                                                                  \
+    }
+
+DEFINE_TYPED(double, f64)
+DEFINE_TYPED(float, f32)
+
+}  // extern "C"

@@ -1,0 +1,159 @@
+// Shared device/host helpers for librlb200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/rlb200.h"
+
+namespace rlb {
+
+constexpr int kNumSMsB200 = 148;
+
+// ------------------------------------------------------------------------------------------
+// context
+// ------------------------------------------------------------------------------------------
+struct Timer {
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    double ms = 0.0;
+    int64_t launches = 0;
+    bool pending = false;
+};
+
+struct ArenaChunk { char* p; size_t cap; size_t used; };
+
+struct Ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    int num_sms = kNumSMsB200;
+    // workspace arena (device), grown on demand, reused across calls
+    void* ws = nullptr;
+    size_t ws_bytes = 0;
+    // stack allocator for driver-level device buffers (drivers.cu)
+    std::vector<ArenaChunk> arena;
+    // small pinned host mailbox for return codes / scalars
+    void* hbox = nullptr;
+    size_t hbox_bytes = 0;
+    // row sharding
+    int64_t row_offset = 0;
+    int64_t m_global = -1;
+    rlb200_allreduce_fn allreduce = nullptr;
+    void* allreduce_user = nullptr;
+    // stats
+    int64_t launches = 0;
+    bool timers_on = false;
+    Timer timers[RLB200_TIMER_COUNT];
+    std::string err;
+};
+
+#define RLB_CUDA_OK(ctx, expr)                                                                      \
+    do {                                                                                            \
+        cudaError_t _e = (expr);                                                                    \
+        if (_e != cudaSuccess) {                                                                    \
+            (ctx)->err = std::string(#expr) + ": " + cudaGetErrorString(_e) + " @" + __FILE__ + ":" + \
+                         std::to_string(__LINE__);                                                  \
+            return RLB200_ERR_CUDA;                                                                 \
+        }                                                                                           \
+    } while (0)
+
+#define RLB_REQUIRE(ctx, cond)                                                                      \
+    do {                                                                                            \
+        if (!(cond)) {                                                                              \
+            (ctx)->err = std::string("(" #cond ") was required, but did not hold @") + __FILE__ + ":" + \
+                         std::to_string(__LINE__);                                                  \
+            return RLB200_ERR_ARG;                                                                  \
+        }                                                                                           \
+    } while (0)
+
+#define RLB_CHECK(expr)                                                                             \
+    do {                                                                                            \
+        int _rc = (expr);                                                                           \
+        if (_rc < 0) return _rc;                                                                    \
+    } while (0)
+
+// Reserve `bytes` of device workspace (256-B aligned sub-allocations are carved by the caller).
+int ws_reserve(Ctx* ctx, size_t bytes);
+
+struct WsCarver {
+    char* base;
+    size_t off = 0;
+    explicit WsCarver(void* b) : base(static_cast<char*>(b)) {}
+    template <typename T>
+    T* take(size_t count) {
+        T* p = reinterpret_cast<T*>(base + off);
+        off += ((count * sizeof(T) + 255) / 256) * 256;
+        return p;
+    }
+};
+inline size_t ws_round(size_t bytes) { return ((bytes + 255) / 256) * 256; }
+
+// launch bookkeeping: counts kernels and (optionally) brackets them with CUDA events on ctx->stream.
+struct LaunchScope {
+    Ctx* ctx;
+    int which;
+    LaunchScope(Ctx* c, int w, int n_kernels = 1) : ctx(c), which(w) {
+        ctx->launches += n_kernels;
+        Timer& t = ctx->timers[which];
+        t.launches += n_kernels;
+        if (ctx->timers_on) {
+            if (!t.e0) { cudaEventCreate(&t.e0); cudaEventCreate(&t.e1); }
+            if (t.pending) { cudaEventSynchronize(t.e1); float ms = 0; cudaEventElapsedTime(&ms, t.e0, t.e1); t.ms += ms; t.pending = false; }
+            cudaEventRecord(t.e0, ctx->stream);
+        }
+    }
+    ~LaunchScope() {
+        Timer& t = ctx->timers[which];
+        if (ctx->timers_on) { cudaEventRecord(t.e1, ctx->stream); t.pending = true; }
+    }
+};
+
+// ------------------------------------------------------------------------------------------
+// device helpers
+// ------------------------------------------------------------------------------------------
+#ifdef __CUDACC__
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+// cp.async (LDGSTS): 16-byte and 8-byte forms with zero-fill when `valid` is false.
+__device__ __forceinline__ void cp_async_16(void* smem_dst, const void* gmem_src, bool valid) {
+    uint32_t d = smem_u32(smem_dst);
+    int sz = valid ? 16 : 0;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(d), "l"(gmem_src), "r"(sz));
+}
+__device__ __forceinline__ void cp_async_8(void* smem_dst, const void* gmem_src, bool valid) {
+    uint32_t d = smem_u32(smem_dst);
+    int sz = valid ? 8 : 0;
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(d), "l"(gmem_src), "r"(sz));
+}
+__device__ __forceinline__ void cp_async_4(void* smem_dst, const void* gmem_src, bool valid) {
+    uint32_t d = smem_u32(smem_dst);
+    int sz = valid ? 4 : 0;
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;\n" ::"r"(d), "l"(gmem_src), "r"(sz));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+// fp64 tensor-core MMA: D(8x8) += A(8x4, row) * B(4x8, col).  Lane l holds
+//   a = A[l/4][l%4], b = B[l%4][l/4], c0/c1 = C[l/4][2*(l%4) + {0,1}].   SASS: DMMA.8x8x4
+__device__ __forceinline__ void dmma_884(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
+template <typename T>
+__device__ __forceinline__ T warp_sum(T v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+#endif  // __CUDACC__
+
+}  // namespace rlb

@@ -1,0 +1,402 @@
+// Host-side control flow: Stabilization / RS / RF / QB / RSVD on device-resident, optionally row-sharded data.
+// Reference `call`s reproduced (paths relative to the reference root):
+//   CholQRQ::call  RandLAPACK/comps/rl_orth.hh:68-98      RS::call   RandLAPACK/comps/rl_rs.hh:116-178
+//   RF::call       RandLAPACK/comps/rl_rf.hh:106-137      QB::call   RandLAPACK/comps/rl_qb.hh:133-268
+//   RSVD::call     RandLAPACK/drivers/rl_rsvd.hh:113-154
+#include "drivers.cuh"
+#include "philox.cuh"
+#include <algorithm>
+#include <cmath>
+#include <limits>
+
+namespace rlb {
+
+// ------------------------------------------------------------------------------------------------
+// memory
+// ------------------------------------------------------------------------------------------------
+int ws_reserve(Ctx* ctx, size_t bytes) {
+    if (bytes <= ctx->ws_bytes) return 0;
+    if (ctx->ws) {
+        RLB_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+        RLB_CUDA_OK(ctx, cudaFree(ctx->ws));
+        ctx->ws = nullptr; ctx->ws_bytes = 0;
+    }
+    size_t want = std::max(bytes, (size_t)64 << 20);
+    if (cudaMalloc(&ctx->ws, want) != cudaSuccess) {
+        cudaGetLastError();
+        ctx->err = "workspace allocation of " + std::to_string(want) + " bytes failed";
+        return RLB200_ERR_ALLOC;
+    }
+    ctx->ws_bytes = want;
+    return 0;
+}
+
+static std::vector<ArenaChunk>& chunks_of(Ctx* ctx) { return ctx->arena; }
+size_t arena_mark(Ctx* ctx) {
+    size_t t = 0;
+    for (auto& c : chunks_of(ctx)) t += c.used;
+    return t;
+}
+void* arena_push(Ctx* ctx, size_t bytes) {
+    bytes = ws_round(std::max<size_t>(bytes, 1));
+    auto& ch = chunks_of(ctx);
+    // first chunk (in order) with room whose successors are all empty keeps stack discipline
+    for (size_t i = 0; i < ch.size(); ++i) {
+        bool later_empty = true;
+        for (size_t j = i + 1; j < ch.size(); ++j) later_empty &= (ch[j].used == 0);
+        if (later_empty && ch[i].cap - ch[i].used >= bytes) {
+            void* p = ch[i].p + ch[i].used;
+            ch[i].used += bytes;
+            return p;
+        }
+    }
+    size_t cap = std::max(bytes, (size_t)32 << 20);
+    void* p = nullptr;
+    if (cudaMalloc(&p, cap) != cudaSuccess) {
+        cudaGetLastError();
+        ctx->err = "device allocation of " + std::to_string(cap) + " bytes failed";
+        return nullptr;
+    }
+    ch.push_back({static_cast<char*>(p), cap, bytes});
+    return p;
+}
+void arena_release(Ctx* ctx, size_t mark_total) {
+    auto& ch = chunks_of(ctx);
+    size_t t = 0;
+    for (auto& c : ch) {
+        if (t >= mark_total) c.used = 0;
+        else if (t + c.used > mark_total) c.used = mark_total - t;
+        t += c.used;
+    }
+}
+void arena_destroy(Ctx* ctx) {
+    for (auto& c : ctx->arena) cudaFree(c.p);
+    ctx->arena.clear();
+}
+
+#define RLB_ALLOC(ctx, ptr)                                   \
+    do { if (!(ptr)) return RLB200_ERR_ALLOC; } while (0)
+
+template <typename T>
+static int allreduce_sum(Ctx* ctx, T* buf, int64_t count) {
+    if (!ctx->allreduce) return 0;
+    int rc = ctx->allreduce(ctx->allreduce_user, buf, count, (int32_t)sizeof(T), ctx->stream);
+    if (rc != 0) { ctx->err = "allreduce hook failed with code " + std::to_string(rc); return RLB200_ERR_COLLECTIVE; }
+    return 0;
+}
+
+template <typename T>
+static int read_scalar(Ctx* ctx, const T* dev, T* host) {
+    RLB_CUDA_OK(ctx, cudaMemcpyAsync(ctx->hbox, dev, sizeof(T), cudaMemcpyDeviceToHost, ctx->stream));
+    RLB_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+    std::memcpy(host, ctx->hbox, sizeof(T));
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Stabilization
+// ------------------------------------------------------------------------------------------------
+// cond(R) via the singular values of the k x k factor (util::cond_num_check, rl_util.hh:402-424)
+template <typename T>
+static int cond_of_square(Ctx* ctx, int64_t k, const T* R, double* cond) {
+    ArenaScope as(ctx);
+    T* Rc = as.take<T>(k * k); RLB_ALLOC(ctx, Rc);
+    T* S = as.take<T>(k); RLB_ALLOC(ctx, S);
+    T* W = as.take<T>(k * k); RLB_ALLOC(ctx, W);
+    void* ws = arena_push(ctx, svd_ws_bytes(k, k, sizeof(T))); RLB_ALLOC(ctx, ws);
+    RLB_CUDA_OK(ctx, cudaMemcpyAsync(Rc, R, sizeof(T) * k * k, cudaMemcpyDeviceToDevice, ctx->stream));
+    RLB_CHECK(svd_tall<T>(ctx, k, k, Rc, k, S, W, ws, nullptr));
+    std::vector<T> s(k);
+    RLB_CUDA_OK(ctx, cudaMemcpyAsync(s.data(), S, sizeof(T) * k, cudaMemcpyDeviceToHost, ctx->stream));
+    RLB_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+    *cond = (s[k - 1] == 0) ? std::numeric_limits<double>::infinity() : (double)s[0] / (double)s[k - 1];
+    return 0;
+}
+
+template <typename T>
+static int cholqrq(Ctx* ctx, int64_t m, int64_t k, T* A, bool cond_check, bool rows_sharded, int* chol_fail) {
+    RLB_REQUIRE(ctx, k <= 16384);
+    if (k == 0) return 0;
+    ArenaScope as(ctx);
+    T* G = as.take<T>(k * k); RLB_ALLOC(ctx, G);
+    T* Rinv = as.take<T>(k * k); RLB_ALLOC(ctx, Rinv);
+    int* info_dev = as.take<int>(1); RLB_ALLOC(ctx, info_dev);
+    RLB_CUDA_OK(ctx, cudaMemsetAsync(G, 0, sizeof(T) * k * k, ctx->stream));
+    // G = A^T A, upper triangle (rl_orth.hh:78)
+    RLB_CHECK(gemm_tn<T>(ctx, m, k, k, 1.0, A, m, A, m, 0.0, G, k, /*upper_only=*/1));
+    if (rows_sharded) RLB_CHECK(allreduce_sum<T>(ctx, G, k * k));
+    // R = chol(G) (rl_orth.hh:81); failure => chol_fail, return 1
+    RLB_CHECK(potrf_upper<T>(ctx, (int)k, G, (int)k, info_dev));
+    int info = 0;
+    RLB_CHECK(read_scalar<int>(ctx, info_dev, &info));
+    if (info != 0) {
+        if (chol_fail) *chol_fail = 1;
+        return 1;
+    }
+    if (cond_check) {   // rl_orth.hh:88-93 — the whole k x k buffer (upper R, zero strictly-lower part) is examined
+        double cond = 0;
+        RLB_CHECK(cond_of_square<T>(ctx, k, G, &cond));
+        if (cond > 1.0 / std::sqrt((double)std::numeric_limits<T>::epsilon())) return 1;
+    }
+    // A <- A R^{-1} (rl_orth.hh:95), as a tall product with the explicit triangular inverse
+    RLB_CHECK(trtri_upper<T>(ctx, (int)k, G, (int)k, Rinv));
+    if (k <= 256) {
+        RLB_CHECK(gemm_nn_inplace<T>(ctx, m, k, k, 1.0, A, m, Rinv, k));
+    } else {
+        T* tmp = as.take<T>((size_t)m * k); RLB_ALLOC(ctx, tmp);
+        RLB_CUDA_OK(ctx, cudaMemcpyAsync(tmp, A, sizeof(T) * m * k, cudaMemcpyDeviceToDevice, ctx->stream));
+        RLB_CHECK(gemm_nn<T>(ctx, m, k, k, 1.0, tmp, m, Rinv, k, 0.0, A, m));
+    }
+    return 0;
+}
+
+template <typename T>
+int stab_call(Ctx* ctx, int kind, int64_t m, int64_t k, T* A, bool cond_check, bool rows_sharded, int* chol_fail) {
+    RLB_REQUIRE(ctx, m >= 0 && k >= 0);
+    switch (kind) {
+        case RLB200_STAB_CHOLQRQ: return cholqrq<T>(ctx, m, k, A, cond_check, rows_sharded, chol_fail);
+        case RLB200_STAB_PLUL:
+        case RLB200_STAB_HQRQ:
+            ctx->err = "PLUL / HQRQ stabilisers are not implemented on the device yet (see DESIGN.md, scope table)";
+            return RLB200_ERR_UNSUPPORTED;
+    }
+    RLB_REQUIRE(ctx, !"unknown stabiliser kind");
+    return RLB200_ERR_ARG;
+}
+
+// ------------------------------------------------------------------------------------------------
+// RS  (rl_rs.hh:116-178)
+// ------------------------------------------------------------------------------------------------
+// full-matrix next state of a DenseDist sample (dense_skops.hh:169-182)
+static void dense_next_state(int64_t n_rows, int64_t n_cols, uint32_t state[6]) {
+    int64_t major = std::max(n_rows, n_cols), minor = std::min(n_rows, n_cols);
+    Ctr128 c;
+    for (int i = 0; i < 4; ++i) c.v[i] = state[i];
+    c = ctr_add(c, (uint64_t)(((major + 3) / 4) * minor));
+    for (int i = 0; i < 4; ++i) state[i] = c.v[i];
+}
+
+template <typename T>
+int rs_call(Ctx* ctx, int64_t m, int64_t n, const T* A, int64_t k, T* Omega, T* work, uint32_t state[6], const rlb200_stack_opts& o) {
+    RLB_REQUIRE(ctx, m > 0 && n > 0 && k > 0);
+    const int64_t p = o.passes_over_data, q = o.passes_per_stab;
+    RLB_REQUIRE(ctx, p >= 0 && (p == 0 || q >= 1));
+    RLB_REQUIRE(ctx, p == 0 || work != nullptr);
+    const bool sharded = ctx->m_global >= 0;
+    const int64_t mg = sharded ? ctx->m_global : m;
+    int64_t p_done = 0;
+    T* Omega_1 = work;
+    if (p % 2 == 0) {
+        // Omega = fill_dense(DenseDist(n, k))  (:132-135); replicated on every shard
+        RLB_CHECK(fill_dense_unpacked<T>(ctx, n, k, RLB200_FAMILY_GAUSSIAN, RLB200_AXIS_LONG, RLB200_LAYOUT_NATURAL, n, k, 0, 0, Omega, state));
+    } else {
+        // Omega_1 = fill_dense(DenseDist(m, k)) (:136-139); each shard generates only its row block of the
+        // m_global x k operator through the sub-matrix counter rule, then the state advances as for the whole matrix.
+        uint32_t st_full[6];
+        std::memcpy(st_full, state, sizeof st_full);
+        if (mg > k) {   // tall: natural layout is column-major, rows can be sliced
+            uint32_t st_sub[6];
+            std::memcpy(st_sub, state, sizeof st_sub);
+            RLB_CHECK(fill_dense_unpacked<T>(ctx, mg, k, RLB200_FAMILY_GAUSSIAN, RLB200_AXIS_LONG, RLB200_LAYOUT_NATURAL, m, k,
+                                             sharded ? ctx->row_offset : 0, 0, Omega_1, st_sub));
+        } else {
+            RLB_REQUIRE(ctx, !sharded);   // wide/square operator buffers are reinterpreted, cannot be row-sliced
+            uint32_t st_sub[6];
+            std::memcpy(st_sub, state, sizeof st_sub);
+            RLB_CHECK(fill_dense_unpacked<T>(ctx, mg, k, RLB200_FAMILY_GAUSSIAN, RLB200_AXIS_LONG, RLB200_LAYOUT_NATURAL, mg, k, 0, 0, Omega_1, st_sub));
+        }
+        dense_next_state(mg, k, st_full);
+        std::memcpy(state, st_full, sizeof st_full);
+        // Omega = A^T Omega_1 (:142)
+        RLB_CHECK(gemm_tn<T>(ctx, m, n, k, 1.0, A, m, Omega_1, m, 0.0, Omega, n, 0));
+        if (sharded) RLB_CHECK(allreduce_sum<T>(ctx, Omega, n * k));
+        ++p_done;
+        if (p_done % q == 0) {
+            int rc = stab_call<T>(ctx, o.stab, n, k, Omega, o.cond_check, false, nullptr);
+            if (rc) return rc < 0 ? rc : 1;
+        }
+    }
+    while (p - p_done > 0) {
+        // Omega_1 = A Omega (:153)
+        RLB_CHECK(gemm_nn<T>(ctx, m, k, n, 1.0, A, m, Omega, n, 0.0, Omega_1, m));
+        ++p_done;
+        if (p_done % q == 0) {
+            int rc = stab_call<T>(ctx, o.stab, m, k, Omega_1, o.cond_check, sharded, nullptr);
+            if (rc) return rc < 0 ? rc : 1;
+        }
+        // Omega = A^T Omega_1 (:165)
+        RLB_CHECK(gemm_tn<T>(ctx, m, n, k, 1.0, A, m, Omega_1, m, 0.0, Omega, n, 0));
+        if (sharded) RLB_CHECK(allreduce_sum<T>(ctx, Omega, n * k));
+        ++p_done;
+        if (p_done % q == 0) {
+            int rc = stab_call<T>(ctx, o.stab, n, k, Omega, o.cond_check, false, nullptr);
+            if (rc) return rc < 0 ? rc : 1;
+        }
+    }
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// RF  (rl_rf.hh:106-137)
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+int rf_call(Ctx* ctx, int64_t m, int64_t n, const T* A, int64_t k, T* Q, uint32_t state[6], const rlb200_stack_opts& o) {
+    RLB_REQUIRE(ctx, m > 0 && n > 0 && k > 0);
+    ArenaScope as(ctx);
+    T* Omega = as.take<T>(n * k); RLB_ALLOC(ctx, Omega);
+    // RS's m x k scratch (Omega_1) lives in Q, which is overwritten afterwards anyway
+    int rc = rs_call<T>(ctx, m, n, A, k, Omega, Q, state, o);
+    if (rc) return rc < 0 ? rc : 1;                                           // :118-120
+    RLB_CHECK(gemm_nn<T>(ctx, m, k, n, 1.0, A, m, Omega, n, 0.0, Q, m));      // :123
+    rc = stab_call<T>(ctx, o.orth_rf, m, k, Q, o.cond_check, ctx->m_global >= 0, nullptr);   // :129
+    if (rc) return rc < 0 ? rc : 2;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// QB  (rl_qb.hh:133-268)
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+static int fro_norm(Ctx* ctx, const T* A, int64_t m, int64_t n, int64_t lda, bool rows_sharded, double* out) {
+    ArenaScope as(ctx);
+    double* part = as.take<double>(sumsq_ws_doubles(ctx) + 1); RLB_ALLOC(ctx, part);
+    double* res = part + sumsq_ws_doubles(ctx);
+    RLB_CHECK(sumsq<T>(ctx, A, m, n, lda, part, res));
+    if (rows_sharded) RLB_CHECK(allreduce_sum<double>(ctx, res, 1));
+    double ss = 0;
+    RLB_CHECK(read_scalar<double>(ctx, res, &ss));
+    *out = std::sqrt(ss);
+    return 0;
+}
+
+// util::orthogonality_check (rl_util.hh:467-496)
+template <typename T>
+static int orth_check(Ctx* ctx, int64_t m, int64_t k, const T* Q, bool rows_sharded, bool* lost) {
+    ArenaScope as(ctx);
+    T* G = as.take<T>(k * k); RLB_ALLOC(ctx, G);
+    RLB_CUDA_OK(ctx, cudaMemsetAsync(G, 0, sizeof(T) * k * k, ctx->stream));
+    RLB_CHECK(gemm_tn<T>(ctx, m, k, k, 1.0, Q, m, Q, m, 0.0, G, k, 1));
+    if (rows_sharded) RLB_CHECK(allreduce_sum<T>(ctx, G, k * k));
+    std::vector<T> g(k * k);
+    RLB_CUDA_OK(ctx, cudaMemcpyAsync(g.data(), G, sizeof(T) * k * k, cudaMemcpyDeviceToHost, ctx->stream));
+    RLB_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+    double ss = 0;
+    for (int64_t j = 0; j < k; ++j)
+        for (int64_t i = 0; i <= j; ++i) { double v = (double)g[i + j * k] - (i == j ? 1.0 : 0.0); ss += v * v; }
+    const double tol = sizeof(T) == 8 ? 1.0e-10 : 1.0e-2;
+    *lost = std::sqrt(ss) / std::sqrt((double)k) > tol;
+    return 0;
+}
+
+template <typename T>
+int qb_call(Ctx* ctx, int64_t m, int64_t n, T* A, int64_t* k_io, int64_t b_sz, T tol_in, T* Q, T* BT, T* Acpy, uint32_t state[6],
+            const rlb200_stack_opts& o) {
+    RLB_REQUIRE(ctx, m > 0 && n > 0 && k_io && *k_io > 0 && b_sz > 0);
+    const bool sharded = ctx->m_global >= 0;
+    const int64_t k = *k_io;
+    int64_t curr_sz = 0, next_sz = 0;
+    const T tol = std::max(tol_in, (T)100 * std::numeric_limits<T>::epsilon());   // :149
+    T norm_B = 0, prev_err = 0, approx_err = 0;
+    ArenaScope as(ctx);
+    double nA = 0;
+    RLB_CHECK(fro_norm<T>(ctx, A, m, n, m, sharded, &nA));                       // :168
+    const T norm_A = (T)nA;
+    const bool multi_block = b_sz < k;
+    T* A_work = A;
+    T* QtQi = nullptr;
+    if (multi_block) {
+        // the reference deflates a copy of A (:162,171,260)
+        if (!Acpy) { Acpy = as.take<T>((size_t)m * n); RLB_ALLOC(ctx, Acpy); }
+        RLB_CUDA_OK(ctx, cudaMemcpyAsync(Acpy, A, sizeof(T) * m * n, cudaMemcpyDeviceToDevice, ctx->stream));
+        A_work = Acpy;
+        QtQi = as.take<T>((size_t)k * b_sz); RLB_ALLOC(ctx, QtQi);
+    }
+    while (curr_sz < k) {
+        b_sz = std::min(b_sz, k - curr_sz);
+        next_sz = curr_sz + b_sz;
+        T* Q_i = Q + m * curr_sz;
+        T* BT_i = BT + n * curr_sz;
+        int rc = rf_call<T>(ctx, m, n, A_work, b_sz, Q_i, state, o);             // :191
+        if (rc < 0) return rc;
+        if (rc) { *k_io = curr_sz; return 6; }
+        if (o.orth_check) {                                                       // :199-207
+            bool lost = false;
+            RLB_CHECK(orth_check<T>(ctx, m, b_sz, Q_i, sharded, &lost));
+            if (lost) { *k_io = curr_sz; return 4; }
+        }
+        if (curr_sz != 0) {                                                       // :210-215
+            // (the reference stores QtQi with ld = next_sz; a compact ld = curr_sz keeps the allreduce contiguous)
+            RLB_CHECK(gemm_tn<T>(ctx, m, curr_sz, b_sz, 1.0, Q, m, Q_i, m, 0.0, QtQi, curr_sz, 0));
+            if (sharded) RLB_CHECK(allreduce_sum<T>(ctx, QtQi, curr_sz * b_sz));
+            RLB_CHECK(gemm_nn<T>(ctx, m, b_sz, curr_sz, -1.0, Q, m, QtQi, curr_sz, 1.0, Q_i, m));
+            int rc2 = stab_call<T>(ctx, o.orth_qb, m, b_sz, Q_i, o.cond_check, sharded, nullptr);
+            if (rc2 < 0) return rc2;   // (the reference ignores a numeric failure here, :214)
+        }
+        RLB_CHECK(gemm_tn<T>(ctx, m, n, b_sz, 1.0, A_work, m, Q_i, m, 0.0, BT_i, n, 0));   // :218
+        if (sharded) RLB_CHECK(allreduce_sum<T>(ctx, BT_i, n * b_sz));
+        double nBi = 0;
+        RLB_CHECK(fro_norm<T>(ctx, BT_i, n, b_sz, n, false, &nBi));               // :221
+        norm_B = (T)std::hypot((T)norm_B, (T)nBi);                                // :222
+        prev_err = approx_err;
+        approx_err = std::sqrt(std::abs(norm_A - norm_B)) * (std::sqrt(norm_A + norm_B) / norm_A);   // :225
+        if (curr_sz > 0 && approx_err > prev_err) { *k_io = curr_sz; return 2; }  // :228-234
+        if (o.orth_check) {                                                       // :236-244
+            bool lost = false;
+            RLB_CHECK(orth_check<T>(ctx, m, next_sz, Q, sharded, &lost));
+            if (lost) { *k_io = curr_sz; return 5; }
+        }
+        curr_sz += b_sz;
+        if (approx_err < tol) { *k_io = curr_sz; return 0; }                      // :250-256
+        // A_work -= Q_i BT_i^T (:260) — only needed when another block follows (the reference also runs it after
+        // the last block, where its result is never read)
+        if (curr_sz < k)
+            RLB_CHECK(gemm_nt<T>(ctx, m, n, b_sz, -1.0, Q_i, m, BT_i, n, 1.0, A_work, m));
+    }
+    return 3;
+}
+
+// ------------------------------------------------------------------------------------------------
+// RSVD  (rl_rsvd.hh:113-154)
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+int rsvd_call(Ctx* ctx, int64_t m, int64_t n, T* A, int64_t* k_io, T tol, T* U, T* S, T* V, T* Acpy, uint32_t state[6],
+              const rlb200_stack_opts& o, int* qb_code) {
+    // :128-132
+    RLB_REQUIRE(ctx, m >= 0);
+    RLB_REQUIRE(ctx, n >= 0);
+    RLB_REQUIRE(ctx, k_io && *k_io > 0);
+    RLB_REQUIRE(ctx, tol >= (T)0);
+    RLB_REQUIRE(ctx, !(A == nullptr && m > 0 && n > 0));
+    RLB_REQUIRE(ctx, m > 0 && n > 0 && *k_io <= n && o.block_sz > 0);
+    // Q lives in U, BT in V; the SVD of BT (n x k) overwrites V with its left singular vectors, which is exactly
+    // what the reference returns in V (gesdd's U argument, :146)
+    int rc = qb_call<T>(ctx, m, n, A, k_io, o.block_sz, tol, U, V, Acpy, state, o);   // :137 (code ignored by the reference)
+    if (rc < 0) return rc;
+    if (qb_code) *qb_code = rc;
+    const int64_t k = *k_io;
+    if (k == 0) return 0;
+    ArenaScope as(ctx);
+    T* W = as.take<T>(k * k); RLB_ALLOC(ctx, W);
+    void* ws = arena_push(ctx, svd_ws_bytes(n, k, sizeof(T))); RLB_ALLOC(ctx, ws);
+    RLB_CHECK(svd_tall<T>(ctx, n, k, V, n, S, W, ws, nullptr));                   // :146
+    // U = Q * UT_buf^T = Q * W (:148), in place
+    if (k <= 256) {
+        RLB_CHECK(gemm_nn_inplace<T>(ctx, m, k, k, 1.0, U, m, W, k));
+    } else {
+        T* tmp = as.take<T>((size_t)m * k); RLB_ALLOC(ctx, tmp);
+        RLB_CUDA_OK(ctx, cudaMemcpyAsync(tmp, U, sizeof(T) * m * k, cudaMemcpyDeviceToDevice, ctx->stream));
+        RLB_CHECK(gemm_nn<T>(ctx, m, k, k, 1.0, tmp, m, W, k, 0.0, U, m));
+    }
+    return 0;
+}
+
+#define INST(T)                                                                                                             \
+    template int stab_call<T>(Ctx*, int, int64_t, int64_t, T*, bool, bool, int*);                                           \
+    template int rs_call<T>(Ctx*, int64_t, int64_t, const T*, int64_t, T*, T*, uint32_t*, const rlb200_stack_opts&);         \
+    template int rf_call<T>(Ctx*, int64_t, int64_t, const T*, int64_t, T*, uint32_t*, const rlb200_stack_opts&);             \
+    template int qb_call<T>(Ctx*, int64_t, int64_t, T*, int64_t*, int64_t, T, T*, T*, T*, uint32_t*, const rlb200_stack_opts&); \
+    template int rsvd_call<T>(Ctx*, int64_t, int64_t, T*, int64_t*, T, T*, T*, T*, T*, uint32_t*, const rlb200_stack_opts&, int*);
+INST(double)
+INST(float)
+
+}  // namespace rlb

@@ -1,0 +1,65 @@
+// Host-side control flow of the sketch-and-factor stack on top of the sm_100a kernels:
+// Stabilization (CholQRQ/...), RS, RF, QB, RSVD — same order of operations, same return codes and the
+// same RNG-state advancement as the reference's `call`s, but device-resident and row-shardable.
+#pragma once
+#include "common.cuh"
+
+namespace rlb {
+
+// ---- kernel-level entry points (defined in the .cu files) -----------------------------------------
+template <typename T>
+int fill_dense_unpacked(Ctx* ctx, int64_t n_rows, int64_t n_cols, int family, int major_axis, int layout, int64_t sub_rows,
+                        int64_t sub_cols, int64_t ro, int64_t co, T* buff, uint32_t state[6]);
+int philox_stream(Ctx* ctx, const uint32_t state[6], int64_t n, uint32_t* out);
+template <typename T>
+int gemm_nn(Ctx* ctx, int64_t m, int64_t N, int64_t K, double alpha, const T* A, int64_t lda, const T* B, int64_t ldb, double beta,
+            T* C, int64_t ldc);
+template <typename T>
+int gemm_nt(Ctx* ctx, int64_t m, int64_t N, int64_t K, double alpha, const T* A, int64_t lda, const T* B, int64_t ldb, double beta,
+            T* C, int64_t ldc);
+template <typename T>
+int gemm_nn_inplace(Ctx* ctx, int64_t m, int64_t N, int64_t K, double alpha, T* X, int64_t ldx, const T* B, int64_t ldb);
+template <typename T>
+int gemm_tn(Ctx* ctx, int64_t m, int64_t N1, int64_t N2, double alpha, const T* A, int64_t lda, const T* B, int64_t ldb, double beta,
+            T* C, int64_t ldc, int upper_only);
+template <typename T>
+int sumsq(Ctx* ctx, const T* A, int64_t m, int64_t n, int64_t lda, double* partial_ws, double* out_dev);
+int sumsq_ws_doubles(Ctx* ctx);
+template <typename T>
+int potrf_upper(Ctx* ctx, int k, T* A, int lda, int* info_dev);
+template <typename T>
+int trtri_upper(Ctx* ctx, int k, const T* R, int ldr, T* Rinv);
+size_t svd_ws_bytes(int64_t n, int64_t k, size_t elem);
+template <typename T>
+int svd_tall(Ctx* ctx, int64_t n, int64_t k, T* B, int64_t ldb, T* S, T* W, void* ws, int* sweeps_out);
+
+// ---- arena: stack allocator for driver-level device buffers ---------------------------------------
+void* arena_push(Ctx* ctx, size_t bytes);          // nullptr on failure (ctx->err set)
+void arena_release(Ctx* ctx, size_t mark_total);   // pop back to a previous mark
+size_t arena_mark(Ctx* ctx);
+void arena_destroy(Ctx* ctx);
+
+struct ArenaScope {
+    Ctx* ctx; size_t mk;
+    explicit ArenaScope(Ctx* c) : ctx(c), mk(arena_mark(c)) {}
+    ~ArenaScope() { arena_release(ctx, mk); }
+    template <typename T> T* take(size_t count) { return static_cast<T*>(arena_push(ctx, count * sizeof(T))); }
+};
+
+// ---- drivers ---------------------------------------------------------------------------------------
+// rows_sharded: the m rows of A are this rank's block of a row-sharded matrix (Gram needs an allreduce);
+// false for replicated operands (the n x k Omega).
+template <typename T>
+int stab_call(Ctx* ctx, int kind, int64_t m, int64_t k, T* A, bool cond_check, bool rows_sharded, int* chol_fail);
+template <typename T>
+int rs_call(Ctx* ctx, int64_t m, int64_t n, const T* A, int64_t k, T* Omega, T* work, uint32_t state[6], const rlb200_stack_opts& o);
+template <typename T>
+int rf_call(Ctx* ctx, int64_t m, int64_t n, const T* A, int64_t k, T* Q, uint32_t state[6], const rlb200_stack_opts& o);
+template <typename T>
+int qb_call(Ctx* ctx, int64_t m, int64_t n, T* A, int64_t* k, int64_t block_sz, T tol, T* Q, T* BT, T* Acpy, uint32_t state[6],
+            const rlb200_stack_opts& o);
+template <typename T>
+int rsvd_call(Ctx* ctx, int64_t m, int64_t n, T* A, int64_t* k, T tol, T* U, T* S, T* V, T* Acpy, uint32_t state[6],
+              const rlb200_stack_opts& o, int* qb_code);
+
+}  // namespace rlb
