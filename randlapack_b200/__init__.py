@@ -49,7 +49,13 @@ def to_f(x):
 
 
 def _is_f(x):
-    return x.dim() == 2 and x.stride(0) == 1 and (x.stride(1) == x.shape[0] or x.shape[1] <= 1) or x.dim() == 1 and x.is_contiguous()
+    """column-major with leading dimension >= rows (or a contiguous vector)"""
+    return x.dim() == 2 and (x.stride(0) == 1 or x.shape[0] <= 1) and (x.stride(1) >= x.shape[0] or x.shape[1] <= 1) \
+        or x.dim() == 1 and x.is_contiguous()
+
+
+def _ld(x):
+    return x.stride(1) if x.shape[1] > 1 else max(x.shape[0], 1)
 
 
 def _suffix(dtype):
@@ -243,9 +249,7 @@ def gemm(ctx: Context, transa, transb, alpha, A, B, beta=0.0, C=None):
         C = empty_f(m, n, A.dtype, A.device)
         beta = 0.0
     fn = getattr(ctx._lib, f"rlb200_gemm_{_suffix(A.dtype)}_dev")
-    ctx.check(fn(ctx._h, int(transa), int(transb), m, n, k, alpha, A.data_ptr(), max(A.stride(1), A.shape[0]) if A.shape[1] > 1 else A.shape[0],
-                 B.data_ptr(), max(B.stride(1), B.shape[0]) if B.shape[1] > 1 else B.shape[0], beta, C.data_ptr(),
-                 max(C.stride(1), C.shape[0]) if C.shape[1] > 1 else C.shape[0]))
+    ctx.check(fn(ctx._h, int(transa), int(transb), m, n, k, alpha, A.data_ptr(), _ld(A), B.data_ptr(), _ld(B), beta, C.data_ptr(), _ld(C)))
     return C
 
 

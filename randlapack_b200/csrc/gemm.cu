@@ -62,8 +62,10 @@ gemm_nn_kernel(int64_t m, int N, int K, double alpha, const T* __restrict__ A, i
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int wm = warp % WGM, wn = warp / WGM;
-    const int64_t m0 = (int64_t)blockIdx.x * TM;
-    const int n0 = blockIdx.y * TN;
+    // 1-D grid, N-tile index fastest: the CTAs that share a row block of A are launched back to back (L2 reuse)
+    const int ntiles = (N + TN - 1) / TN;
+    const int64_t m0 = (int64_t)(blockIdx.x / ntiles) * TM;
+    const int n0 = (int)(blockIdx.x % ntiles) * TN;
     const int nk = (K + KS - 1) / KS;
 
     auto load_stage = [&](int stage, int kt) {
@@ -168,12 +170,14 @@ static bool al16(const T* p, int64_t ld) {
 }
 
 template <typename T, int TM, int TN, int WGM, int WGN, int KS, int STAGES, int MINB, bool TB = false>
-static int launch_nn(Ctx* ctx, int64_t m, int N, int K, double alpha, const T* A, int64_t lda, const T* B, int64_t ldb, double beta,
+int launch_nn(Ctx* ctx, int64_t m, int N, int K, double alpha, const T* A, int64_t lda, const T* B, int64_t ldb, double beta,
                      T* C, int64_t ldc) {
     using Cfg = NNCfg<T, TM, TN, WGM, WGN, KS, STAGES>;
     auto kern = gemm_nn_kernel<T, TM, TN, WGM, WGN, KS, STAGES, MINB, TB>;
     RLB_CUDA_OK(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
-    dim3 grid((unsigned)((m + TM - 1) / TM), (unsigned)((N + TN - 1) / TN));
+    const int64_t nblk = ((m + TM - 1) / TM) * ((N + TN - 1) / TN);
+    RLB_REQUIRE(ctx, nblk < (1ll << 31));
+    dim3 grid((unsigned)nblk);
     LaunchScope ls(ctx, RLB200_TIMER_GEMM_NN);
     kern<<<grid, Cfg::THREADS, Cfg::SMEM, ctx->stream>>>(m, N, K, alpha, A, lda, B, ldb, beta, C, ldc, al16(A, lda), TB ? 0 : al16(B, ldb));
     RLB_CUDA_OK(ctx, cudaGetLastError());
@@ -187,9 +191,10 @@ int gemm_nn(Ctx* ctx, int64_t m, int64_t N, int64_t K, double alpha, const T* A,
     RLB_REQUIRE(ctx, m >= 0 && N >= 0 && K >= 0 && N < (1ll << 30) && K < (1ll << 30));
     RLB_REQUIRE(ctx, (m + 63) / 64 < (1ll << 31));
     if (m == 0 || N == 0) return 0;
+    // tile shapes from the sweep in tools/gemm_tune.cu (profiles/gemm_tune_r1.json): two CTAs per SM hide each other's
+    // barriers, prologue and epilogue; 128x64x32 reaches 89% of the measured DMMA peak on the C2 shape
     if (N <= 32)  return launch_nn<T, 128, 32, 4, 1, 16, 4, 2>(ctx, m, (int)N, (int)K, alpha, A, lda, B, ldb, beta, C, ldc);
-    if (N <= 64)  return launch_nn<T, 128, 64, 4, 2, 16, 4, 1>(ctx, m, (int)N, (int)K, alpha, A, lda, B, ldb, beta, C, ldc);
-    return launch_nn<T, 128, 128, 2, 4, 16, 3, 1>(ctx, m, (int)N, (int)K, alpha, A, lda, B, ldb, beta, C, ldc);
+    return launch_nn<T, 128, 64, 4, 2, 32, 2, 2>(ctx, m, (int)N, (int)K, alpha, A, lda, B, ldb, beta, C, ldc);
 }
 
 // C = alpha*A*B^T + beta*C with B stored N x K (the deflation update of rl_qb.hh:260)
@@ -198,7 +203,7 @@ int gemm_nt(Ctx* ctx, int64_t m, int64_t N, int64_t K, double alpha, const T* A,
             T* C, int64_t ldc) {
     RLB_REQUIRE(ctx, m >= 0 && N >= 0 && K >= 0 && N < (1ll << 30) && K < (1ll << 30));
     if (m == 0 || N == 0) return 0;
-    return launch_nn<T, 128, 128, 2, 4, 16, 3, 1, true>(ctx, m, (int)N, (int)K, alpha, A, lda, B, ldb, beta, C, ldc);
+    return launch_nn<T, 128, 64, 4, 2, 32, 2, 2, true>(ctx, m, (int)N, (int)K, alpha, A, lda, B, ldb, beta, C, ldc);
 }
 
 // X <- alpha * X * B  in place (X: m x K, B: K x N with N <= K so the result fits in X's columns 0..N-1).
@@ -207,9 +212,9 @@ template <typename T>
 int gemm_nn_inplace(Ctx* ctx, int64_t m, int64_t N, int64_t K, double alpha, T* X, int64_t ldx, const T* B, int64_t ldb) {
     RLB_REQUIRE(ctx, N <= 256 && N <= K);
     if (m == 0 || N == 0) return 0;
-    if (N <= 64)  return launch_nn<T, 128, 64, 4, 2, 16, 4, 1>(ctx, m, (int)N, (int)K, alpha, X, ldx, B, ldb, 0.0, X, ldx);
-    if (N <= 128) return launch_nn<T, 128, 128, 2, 4, 16, 3, 1>(ctx, m, (int)N, (int)K, alpha, X, ldx, B, ldb, 0.0, X, ldx);
-    return launch_nn<T, 64, 256, 2, 4, 16, 3, 1>(ctx, m, (int)N, (int)K, alpha, X, ldx, B, ldb, 0.0, X, ldx);
+    if (N <= 64)  return launch_nn<T, 128, 64, 4, 2, 32, 2, 2>(ctx, m, (int)N, (int)K, alpha, X, ldx, B, ldb, 0.0, X, ldx);
+    if (N <= 128) return launch_nn<T, 128, 128, 2, 4, 32, 3, 1>(ctx, m, (int)N, (int)K, alpha, X, ldx, B, ldb, 0.0, X, ldx);
+    return launch_nn<T, 64, 256, 2, 4, 32, 2, 1>(ctx, m, (int)N, (int)K, alpha, X, ldx, B, ldb, 0.0, X, ldx);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -226,8 +231,8 @@ struct TNCfg {
 };
 
 // partial[split][j][i] (column-major N1 x N2 per split, ld = N1) = A[rows of split]^T B[rows of split]
-template <typename T, int T1, int T2, int WG1, int WG2, int KS, int STAGES>
-__global__ void __launch_bounds__(WG1* WG2 * 32, 1)
+template <typename T, int T1, int T2, int WG1, int WG2, int KS, int STAGES, int MINB>
+__global__ void __launch_bounds__(WG1* WG2 * 32, MINB)
 gemm_tn_kernel(int64_t m, int N1, int N2, const T* __restrict__ A, int64_t lda, const T* __restrict__ B, int64_t ldb,
                double* __restrict__ partial, int64_t rows_per_split, int tiles1, int upper_only, int a_al16, int b_al16) {
     using Cfg = TNCfg<T, T1, T2, WG1, WG2, KS, STAGES>;
@@ -333,21 +338,31 @@ __global__ void splitk_reduce_kernel(const double* __restrict__ partial, int spl
     }
 }
 
-template <typename T, int T1, int T2, int WG1, int WG2, int KS, int STAGES>
-static int launch_tn(Ctx* ctx, int64_t m, int N1, int N2, double alpha, const T* A, int64_t lda, const T* B, int64_t ldb, double beta,
+template <typename T, int T1, int T2, int WG1, int WG2, int KS, int STAGES, int MINB = 1>
+int launch_tn(Ctx* ctx, int64_t m, int N1, int N2, double alpha, const T* A, int64_t lda, const T* B, int64_t ldb, double beta,
                      T* C, int64_t ldc, int upper_only) {
     using Cfg = TNCfg<T, T1, T2, WG1, WG2, KS, STAGES>;
     const int tiles1 = (N1 + T1 - 1) / T1, tiles2 = (N2 + T2 - 1) / T2;
     const int tiles = tiles1 * tiles2;
-    // enough splits for ~2 waves of CTAs, each split a multiple of KS rows and at least 8*KS rows
-    int64_t want = std::max<int64_t>(1, (2ll * ctx->num_sms + tiles - 1) / tiles);
+    // tiles that actually run (syrk skips the ones strictly below the diagonal)
+    int active = 0;
+    for (int t2 = 0; t2 < tiles2; ++t2)
+        for (int t1 = 0; t1 < tiles1; ++t1) active += !(upper_only && t1 * T1 >= t2 * T2 + T2);
+    // split-K factor: every CTA does the same amount of work, so pick the smallest number of splits that makes the number of
+    // working CTAs a whole number of waves (a multiple of the SM count; 1 CTA per SM), then cap by the matrix height.
+    auto gcd = [](int64_t a, int64_t b) { while (b) { int64_t t = a % b; a = b; b = t; } return a; };
+    const int64_t slots = (int64_t)ctx->num_sms * MINB;   // CTAs resident at once
+    int64_t want = slots / gcd(active, slots);
+    while (want * active < 2 * slots) want *= 2;
+    const int64_t max_splits = std::max<int64_t>(1, m / (8 * KS));
+    want = std::min(want, max_splits);
     int64_t rows_per_split = (m + want - 1) / want;
-    rows_per_split = std::max<int64_t>(((rows_per_split + KS - 1) / KS) * KS, 8 * KS);
+    rows_per_split = std::max<int64_t>(((rows_per_split + KS - 1) / KS) * KS, KS);
     const int splits = (int)std::max<int64_t>(1, (m + rows_per_split - 1) / rows_per_split);
     const size_t pbytes = (size_t)splits * N1 * N2 * sizeof(double);
     RLB_CHECK(ws_reserve(ctx, pbytes));
     double* partial = static_cast<double*>(ctx->ws);
-    auto kern = gemm_tn_kernel<T, T1, T2, WG1, WG2, KS, STAGES>;
+    auto kern = gemm_tn_kernel<T, T1, T2, WG1, WG2, KS, STAGES, MINB>;
     RLB_CUDA_OK(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
     LaunchScope ls(ctx, RLB200_TIMER_GEMM_TN, 2);
     dim3 grid((unsigned)tiles, (unsigned)splits);
@@ -367,9 +382,11 @@ int gemm_tn(Ctx* ctx, int64_t m, int64_t N1, int64_t N2, double alpha, const T* 
             T* C, int64_t ldc, int upper_only) {
     RLB_REQUIRE(ctx, m >= 0 && N1 >= 0 && N2 >= 0 && N1 < (1 << 20) && N2 < (1 << 20));
     if (N1 == 0 || N2 == 0) return 0;
-    if (N1 <= 64 && N2 <= 64)
-        return launch_tn<T, 64, 64, 2, 4, 16, 4>(ctx, m, (int)N1, (int)N2, alpha, A, lda, B, ldb, beta, C, ldc, upper_only);
-    return launch_tn<T, 128, 128, 2, 4, 16, 4>(ctx, m, (int)N1, (int)N2, alpha, A, lda, B, ldb, beta, C, ldc, upper_only);
+    // tile shapes from tools/gemm_tune.cu: 64x128x32 with 2 CTAs/SM reaches 90% of the DMMA peak on A^T*Y (C2 shape);
+    // the Gram (syrk) case prefers 64x64 tiles (finer triangle, 4 CTAs/SM)
+    if (upper_only || (N1 <= 64 && N2 <= 64))
+        return launch_tn<T, 64, 64, 2, 2, 16, 3, 4>(ctx, m, (int)N1, (int)N2, alpha, A, lda, B, ldb, beta, C, ldc, upper_only);
+    return launch_tn<T, 64, 128, 2, 4, 32, 2, 2>(ctx, m, (int)N1, (int)N2, alpha, A, lda, B, ldb, beta, C, ldc, upper_only);
 }
 
 #define INST(T)                                                                                                                  \

