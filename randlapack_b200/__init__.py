@@ -401,15 +401,16 @@ class RSVD:
         self.qb_code = qc.value
         return rc, kk.value, U, S, V
 
-    def call_host(self, ctx: Context, A_host, k, tol, state: RNGState):
-        """The reference-facing form: HOST column-major A in, host U, S, V out (copies inside)."""
+    def call_host(self, ctx: Context, A_host, k, tol, state: RNGState, U=None, S=None, V=None):
+        """The reference-facing form: HOST column-major A in, host U, S, V out (copies inside).
+        U, S, V may be preallocated (e.g. pinned) host buffers of the requested k."""
         torch = _torch()
         m, n = A_host.shape
         assert _is_f(A_host) and not A_host.is_cuda
         o = self._opts()
-        U = empty_f(m, k, A_host.dtype, "cpu")
-        S = torch.empty(k, dtype=A_host.dtype)
-        V = empty_f(n, k, A_host.dtype, "cpu")
+        U = empty_f(m, k, A_host.dtype, "cpu") if U is None else U
+        S = torch.empty(k, dtype=A_host.dtype) if S is None else S
+        V = empty_f(n, k, A_host.dtype, "cpu") if V is None else V
         kk, qc = ctypes.c_int64(k), ctypes.c_int(0)
         w = state.words()
         fn = getattr(ctx._lib, f"rlb200_rsvd_{_suffix(A_host.dtype)}_host")

@@ -155,9 +155,17 @@ int stab_call(Ctx* ctx, int kind, int64_t m, int64_t k, T* A, bool cond_check, b
     RLB_REQUIRE(ctx, m >= 0 && k >= 0);
     switch (kind) {
         case RLB200_STAB_CHOLQRQ: return cholqrq<T>(ctx, m, k, A, cond_check, rows_sharded, chol_fail);
-        case RLB200_STAB_PLUL:
+        case RLB200_STAB_PLUL: {
+            if (rows_sharded && ctx->allreduce) {
+                ctx->err = "PLUL on a row-sharded iterate needs a cross-rank pivot search (max-allreduce); not offered yet";
+                return RLB200_ERR_UNSUPPORTED;
+            }
+            ArenaScope as(ctx);
+            void* ws = arena_push(ctx, plul_ws_bytes(ctx, k)); RLB_ALLOC(ctx, ws);
+            return plul<T>(ctx, m, k, A, m, ws);   // rl_orth.hh:211-230: always returns 0
+        }
         case RLB200_STAB_HQRQ:
-            ctx->err = "PLUL / HQRQ stabilisers are not implemented on the device yet (see DESIGN.md, scope table)";
+            ctx->err = "HQRQ stabiliser is not implemented on the device yet (see DESIGN.md, scope table)";
             return RLB200_ERR_UNSUPPORTED;
     }
     RLB_REQUIRE(ctx, !"unknown stabiliser kind");

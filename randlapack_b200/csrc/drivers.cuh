@@ -30,6 +30,9 @@ int potrf_upper(Ctx* ctx, int k, T* A, int lda, int* info_dev);
 template <typename T>
 int trtri_upper(Ctx* ctx, int k, const T* R, int ldr, T* Rinv);
 size_t svd_ws_bytes(int64_t n, int64_t k, size_t elem);
+size_t plul_ws_bytes(Ctx* ctx, int64_t n);
+template <typename T>
+int plul(Ctx* ctx, int64_t m, int64_t n, T* A, int64_t lda, void* ws);
 template <typename T>
 int svd_tall(Ctx* ctx, int64_t n, int64_t k, T* B, int64_t ldb, T* S, T* W, void* ws, int* sweeps_out);
 

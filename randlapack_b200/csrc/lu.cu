@@ -1,0 +1,155 @@
+// PLUL stabiliser (RandLAPACK/comps/rl_orth.hh:211-230): getrf with partial pivoting on the m x n iterate,
+// keep the unit-lower-trapezoidal L (util::get_L, rl_util.hh:101-114) and apply lapack::laswp(n, A, m, 1, n, ipiv, +1).
+//
+// Pivot rule = LAPACK's: at step j the pivot is the FIRST row of maximal |a_ij| (idamax) among rows i >= j of the
+// updated column; the sub-diagonal is scaled by the reciprocal of the pivot; a zero pivot column is skipped.
+// This first version is the unblocked right-looking form (BLAS-2, HBM-bound: 8*m*n^2 bytes for an m x n iterate);
+// everything stays on the device, no host round trips (pivot indices live in device memory).
+#include "common.cuh"
+
+namespace rlb {
+
+struct PivCand {
+    double v;
+    long long i;
+};
+
+__device__ __forceinline__ PivCand better(PivCand a, PivCand b) {
+    // larger |value| wins; ties go to the smaller row index (idamax returns the first maximum)
+    if (b.v > a.v || (b.v == a.v && b.i < a.i)) return b;
+    return a;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) lu_argmax_partial(const T* __restrict__ A, int64_t m, int64_t lda, int j, PivCand* __restrict__ part) {
+    PivCand best{-1.0, (long long)m};
+    const T* col = A + (int64_t)j * lda;
+    for (int64_t i = j + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += (int64_t)gridDim.x * blockDim.x) {
+        PivCand c{fabs((double)col[i]), (long long)i};
+        best = better(best, c);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        PivCand c{__shfl_xor_sync(0xffffffffu, best.v, o), __shfl_xor_sync(0xffffffffu, best.i, o)};
+        best = better(best, c);
+    }
+    __shared__ PivCand sh[8];
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = best;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; ++w) best = better(best, sh[w]);
+        part[blockIdx.x] = best;
+    }
+}
+
+// final reduction + row interchange j <-> p over all n columns; records ipiv[j] = p (0-based) and pivot validity
+template <typename T>
+__global__ void __launch_bounds__(256) lu_pivot_swap(T* __restrict__ A, int64_t lda, int n, int j, const PivCand* __restrict__ part, int nparts,
+                                                     long long* __restrict__ ipiv, int* __restrict__ nonzero) {
+    __shared__ PivCand sbest;
+    if (threadIdx.x < 32) {
+        PivCand best{-1.0, (long long)1 << 62};
+        for (int q = threadIdx.x; q < nparts; q += 32) best = better(best, part[q]);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            PivCand c{__shfl_xor_sync(0xffffffffu, best.v, o), __shfl_xor_sync(0xffffffffu, best.i, o)};
+            best = better(best, c);
+        }
+        if (threadIdx.x == 0) { sbest = best; ipiv[j] = best.i; nonzero[j] = best.v != 0.0; }
+    }
+    __syncthreads();
+    const long long p = sbest.i;
+    if (sbest.v != 0.0 && p != j) {
+        for (int c = threadIdx.x; c < n; c += blockDim.x) {
+            T* col = A + (int64_t)c * lda;
+            T t = col[j]; col[j] = col[p]; col[p] = t;
+        }
+    }
+}
+
+// l_i = a_ij * (1 / a_jj) for i > j, then a_ic -= l_i * a_jc for c > j   (dscal by the reciprocal + dger)
+template <typename T>
+__global__ void __launch_bounds__(256) lu_scale_update(T* __restrict__ A, int64_t m, int64_t lda, int n, int j, const int* __restrict__ nonzero) {
+    __shared__ double urow[1024];
+    const int ncols = n - j - 1;
+    T* colj = A + (int64_t)j * lda;
+    const bool nz = nonzero[j] != 0;
+    const T rinv = nz ? (T)1 / colj[j] : (T)1;
+    for (int c0 = 0; c0 < max(ncols, 1); c0 += 1024) {
+        const int nc = min(1024, ncols - c0);
+        __syncthreads();
+        for (int c = threadIdx.x; c < nc; c += blockDim.x) urow[c] = (double)A[j + (int64_t)(j + 1 + c0 + c) * lda];
+        __syncthreads();
+        for (int64_t i = j + 1 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += (int64_t)gridDim.x * blockDim.x) {
+            T l = colj[i];
+            if (c0 == 0 && nz) { l = l * rinv; colj[i] = l; }
+            else if (nz) { /* already scaled in the first chunk */ }
+            for (int c = 0; c < nc; ++c) {
+                T* a = A + i + (int64_t)(j + 1 + c0 + c) * lda;
+                *a = (T)((double)*a - (double)l * urow[c]);
+            }
+        }
+        if (ncols <= 0) break;
+    }
+}
+
+// get_L (zero strictly-upper part, unit diagonal) followed by laswp(n, A, lda, 1, n, ipiv, +1):
+// for i = 0..kmin-1 in order: swap rows i and ipiv[i]
+template <typename T>
+__global__ void __launch_bounds__(256) lu_make_L(T* __restrict__ A, int64_t m, int64_t lda, int n) {
+    const int64_t total = (int64_t)n * min((int64_t)n, m);   // only the top min(m,n) rows hold upper-triangle entries
+    const int64_t rows = min((int64_t)n, m);
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t i = e % rows, c = e / rows;
+        if (i < c) A[i + c * lda] = (T)0;
+        else if (i == c) A[i + c * lda] = (T)1;
+    }
+}
+template <typename T>
+__global__ void __launch_bounds__(1024) lu_laswp_forward(T* __restrict__ A, int64_t lda, int n, int kmin, const long long* __restrict__ ipiv) {
+    for (int i = 0; i < kmin; ++i) {
+        const long long p = ipiv[i];
+        if (p != i) {
+            for (int c = threadIdx.x; c < n; c += blockDim.x) {
+                T* col = A + (int64_t)c * lda;
+                T t = col[i]; col[i] = col[p]; col[p] = t;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+size_t plul_ws_bytes(Ctx* ctx, int64_t n) {
+    return ws_round(sizeof(PivCand) * (size_t)ctx->num_sms * 8) + ws_round(sizeof(long long) * n) + ws_round(sizeof(int) * n);
+}
+
+template <typename T>
+int plul(Ctx* ctx, int64_t m, int64_t n, T* A, int64_t lda, void* ws) {
+    RLB_REQUIRE(ctx, m >= 0 && n >= 0 && n < (1 << 30));
+    if (m == 0 || n == 0) return 0;
+    WsCarver cv(ws);
+    PivCand* part = cv.take<PivCand>((size_t)ctx->num_sms * 8);
+    long long* ipiv = cv.take<long long>(n);
+    int* nonzero = cv.take<int>(n);
+    const int kmin = (int)std::min<int64_t>(m, n);
+    LaunchScope ls(ctx, RLB200_TIMER_SMALL, 3 * kmin + 2);
+    for (int j = 0; j < kmin; ++j) {
+        const int64_t rows = m - j;
+        const int nb = (int)std::max<int64_t>(1, std::min<int64_t>((rows + 255) / 256, (int64_t)ctx->num_sms * 8));
+        lu_argmax_partial<T><<<nb, 256, 0, ctx->stream>>>(A, m, lda, j, part);
+        lu_pivot_swap<T><<<1, 256, 0, ctx->stream>>>(A, lda, (int)n, j, part, nb, ipiv, nonzero);
+        if (rows > 1) {
+            const int ub = (int)std::max<int64_t>(1, std::min<int64_t>((rows - 1 + 255) / 256, (int64_t)ctx->num_sms * 8));
+            lu_scale_update<T><<<ub, 256, 0, ctx->stream>>>(A, m, lda, (int)n, j, nonzero);
+        }
+    }
+    lu_make_L<T><<<(unsigned)std::min<int64_t>((n * std::min<int64_t>(n, m) + 255) / 256, 4096), 256, 0, ctx->stream>>>(A, m, lda, (int)n);
+    lu_laswp_forward<T><<<1, 1024, 0, ctx->stream>>>(A, lda, (int)n, kmin, ipiv);
+    RLB_CUDA_OK(ctx, cudaGetLastError());
+    return 0;
+}
+
+template int plul<double>(Ctx*, int64_t, int64_t, double*, int64_t, void*);
+template int plul<float>(Ctx*, int64_t, int64_t, float*, int64_t, void*);
+
+}  // namespace rlb

@@ -154,11 +154,9 @@ def test_rs_rf_vs_oracle(ctx, m, n, k, p, q):
 def test_rsvd_golden_configs(ctx, i):
     """The reference's outputs (golden, generated from the compiled reference) on its own inputs, incl. BASELINE configs[0]."""
     m, n, k, p, q, b, stab = [int(x) for x in GOLD[f"rsvd{i}_args"]]
-    if stab != rl.STAB_CHOLQRQ and p > 0:
-        pytest.skip("PLUL stabiliser not implemented on device yet")
     cond, expo = GOLD[f"rsvd{i}_cond_expo"]
     A, st0 = poly(m, n, n if m > 10 else k, cond, expo)
-    *_, RSVD = _stack(p, q, b)
+    *_, RSVD = _stack(p, q, b, stab=stab)
     st = rl.RNGState(st0.key, st0.counter)
     rc, kk, U, S, V = RSVD.call(ctx, dev(A), k, 0.0, st)
     assert [rc, kk] == [int(x) for x in GOLD[f"rsvd{i}_rc_k"]]
@@ -247,12 +245,60 @@ def test_rsvd_argument_errors(ctx):
         RSVD.call(ctx, A, 2, -1.0, rl.RNGState())
 
 
-def test_plul_hqrq_report_unsupported(ctx):
+@pytest.mark.parametrize("m,k", [(50, 5), (1000, 37), (300, 300), (20000, 64), (7, 7), (1, 1)])
+def test_plul_vs_oracle(ctx, m, k):
+    """PLUL::call (rl_orth.hh:211-230): same pivots => L agrees with the oracle's getrf/get_L/laswp to round-off."""
+    rng = np.random.default_rng(m * 7 + k)
+    Y = np.asfortranarray(rng.standard_normal((m, k)))
+    rc_o, L_o = O.PLUL().call(Y.copy(order="F"))
+    Yd = dev(Y).clone()
+    rc = rl.PLUL().call(ctx, Yd)
+    assert rc == rc_o == 0
+    L = host(Yd)
+    assert np.abs(L).max() <= 1.0 + 1e-12          # partial pivoting: |l_ij| <= 1
+    assert np.abs(L - L_o).max() <= 1e-10
+
+
+def test_plul_zero_column_and_ties(ctx):
+    # a zero pivot column is tolerated (rl_orth.hh:218-222); ties resolve to the first row, as idamax does
+    Y = np.asfortranarray(np.array([[2.0, 0.0, 1.0], [-2.0, 0.0, 3.0], [1.0, 0.0, -3.0], [2.0, 0.0, 0.5]]))
+    rc_o, L_o = O.PLUL().call(Y.copy(order="F"))
+    Yd = dev(Y).clone()
+    assert rl.PLUL().call(ctx, Yd) == rc_o == 0
+    assert np.allclose(host(Yd), L_o, atol=1e-14)
+
+
+def test_plul_f32(ctx):
+    rng = np.random.default_rng(5)
+    Y = np.asfortranarray(rng.standard_normal((500, 20)).astype(np.float32))
+    rc_o, L_o = O.PLUL().call(Y.copy(order="F"))
+    Yd = dev(Y).clone()
+    assert rl.PLUL().call(ctx, Yd) == 0
+    assert np.abs(host(Yd) - L_o).max() <= 1e-4
+
+
+def test_canonical_stack_with_plul(ctx):
+    """The reference's canonical RSVD stack (test/drivers/test_rsvd.cc:68-93): PLUL stabiliser, CholQRQ orthogonalisers."""
+    m, n, k, p = 1500, 200, 24, 2
+    A, st0 = poly(m, n, n)
+    _, _, QB, RSVD = _stack(p, 1, k, stab=rl.STAB_PLUL)
+    o = O.StackOpts(p, 1, k, O.STAB_PLUL, O.STAB_CHOLQRQ, O.STAB_CHOLQRQ)
+    *_, rsvd_o = O.make_stack(o)
+    st_d = rl.RNGState(st0.key, st0.counter)
+    Om_dev = _device_operator(ctx, m, n, k, p, st_d)
+    s = st_d.copy()
+    rc, kk, U, S, V = RSVD.call(ctx, dev(A), k, 0.0, s)
+    rc_o, kk_o, U_o, S_o, V_o, s_o = rsvd_o.call(A, k, 0.0, st0.copy(), omega_override=Om_dev)
+    assert (rc, kk) == (rc_o, kk_o) and s.counter == s_o.counter
+    assert np.abs(S.cpu().numpy() - S_o).max() <= 1e-10 * S_o[0]
+    assert _ref.subspace_sin(U_o, host(U)) <= 1e-9
+
+
+def test_hqrq_reports_unsupported(ctx):
     A = dev(np.asfortranarray(np.random.default_rng(0).standard_normal((50, 5)))).clone()
-    for cls in (rl.PLUL, rl.HQRQ):
-        with pytest.raises(rl.Error) as e:
-            cls().call(ctx, A)
-        assert e.value.code == -5
+    with pytest.raises(rl.Error) as e:
+        rl.HQRQ().call(ctx, A)
+    assert e.value.code == -5
 
 
 def test_rsvd_large_properties(ctx):
