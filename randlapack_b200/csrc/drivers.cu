@@ -141,7 +141,7 @@ static int cholqrq(Ctx* ctx, int64_t m, int64_t k, T* A, bool cond_check, bool r
     // A <- A R^{-1} (rl_orth.hh:95), as a tall product with the explicit triangular inverse
     RLB_CHECK(trtri_upper<T>(ctx, (int)k, G, (int)k, Rinv));
     if (k <= 256) {
-        RLB_CHECK(gemm_nn_inplace<T>(ctx, m, k, k, 1.0, A, m, Rinv, k));
+        RLB_CHECK(gemm_nn_inplace<T>(ctx, m, k, k, 1.0, A, m, Rinv, k, /*b_upper_tri=*/true));
     } else {
         T* tmp = as.take<T>((size_t)m * k); RLB_ALLOC(ctx, tmp);
         RLB_CUDA_OK(ctx, cudaMemcpyAsync(tmp, A, sizeof(T) * m * k, cudaMemcpyDeviceToDevice, ctx->stream));
@@ -306,9 +306,10 @@ int qb_call(Ctx* ctx, int64_t m, int64_t n, T* A, int64_t* k_io, int64_t b_sz, T
     const T tol = std::max(tol_in, (T)100 * std::numeric_limits<T>::epsilon());   // :149
     T norm_B = 0, prev_err = 0, approx_err = 0;
     ArenaScope as(ctx);
-    double nA = 0;
-    RLB_CHECK(fro_norm<T>(ctx, A, m, n, m, sharded, &nA));                       // :168
-    const T norm_A = (T)nA;
+    // ||A||_F (:168) is accumulated inside the first block's A^T*Q_i pass (the A tiles are on chip there anyway), which
+    // saves one full sweep over A; it is only consumed after that product (:225).
+    T norm_A = 0;
+    double* nA_dev = as.take<double>(1); RLB_ALLOC(ctx, nA_dev);
     const bool multi_block = b_sz < k;
     T* A_work = A;
     T* QtQi = nullptr;
@@ -340,8 +341,14 @@ int qb_call(Ctx* ctx, int64_t m, int64_t n, T* A, int64_t* k_io, int64_t b_sz, T
             int rc2 = stab_call<T>(ctx, o.orth_qb, m, b_sz, Q_i, o.cond_check, sharded, nullptr);
             if (rc2 < 0) return rc2;   // (the reference ignores a numeric failure here, :214)
         }
-        RLB_CHECK(gemm_tn<T>(ctx, m, n, b_sz, 1.0, A_work, m, Q_i, m, 0.0, BT_i, n, 0));   // :218
+        RLB_CHECK(gemm_tn<T>(ctx, m, n, b_sz, 1.0, A_work, m, Q_i, m, 0.0, BT_i, n, 0, curr_sz == 0 ? nA_dev : nullptr));   // :218
         if (sharded) RLB_CHECK(allreduce_sum<T>(ctx, BT_i, n * b_sz));
+        if (curr_sz == 0) {
+            if (sharded) RLB_CHECK(allreduce_sum<double>(ctx, nA_dev, 1));
+            double ss = 0;
+            RLB_CHECK(read_scalar<double>(ctx, nA_dev, &ss));
+            norm_A = (T)std::sqrt(ss);
+        }
         double nBi = 0;
         RLB_CHECK(fro_norm<T>(ctx, BT_i, n, b_sz, n, false, &nBi));               // :221
         norm_B = (T)std::hypot((T)norm_B, (T)nBi);                                // :222

@@ -18,10 +18,11 @@ template <typename T>
 int gemm_nt(Ctx* ctx, int64_t m, int64_t N, int64_t K, double alpha, const T* A, int64_t lda, const T* B, int64_t ldb, double beta,
             T* C, int64_t ldc);
 template <typename T>
-int gemm_nn_inplace(Ctx* ctx, int64_t m, int64_t N, int64_t K, double alpha, T* X, int64_t ldx, const T* B, int64_t ldb);
+int gemm_nn_inplace(Ctx* ctx, int64_t m, int64_t N, int64_t K, double alpha, T* X, int64_t ldx, const T* B, int64_t ldb,
+                    bool b_upper_tri = false);
 template <typename T>
 int gemm_tn(Ctx* ctx, int64_t m, int64_t N1, int64_t N2, double alpha, const T* A, int64_t lda, const T* B, int64_t ldb, double beta,
-            T* C, int64_t ldc, int upper_only);
+            T* C, int64_t ldc, int upper_only, double* a_sumsq_out = nullptr);
 template <typename T>
 int sumsq(Ctx* ctx, const T* A, int64_t m, int64_t n, int64_t lda, double* partial_ws, double* out_dev);
 int sumsq_ws_doubles(Ctx* ctx);

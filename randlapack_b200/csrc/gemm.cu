@@ -50,7 +50,9 @@ struct NNCfg {
     static constexpr size_t SMEM = (size_t)STAGES * (A_ELEMS + B_ELEMS) * sizeof(T);
 };
 
-template <typename T, int TM, int TN, int WGM, int WGN, int KS, int STAGES, int MINB, bool TB>
+// TB : B is given transposed (N x K).   TRI: B is upper triangular (B[k][n] = 0 for k > n): MMA column tiles are dealt to the
+// warps round-robin and every 8-column tile skips the k-range below its diagonal (~half the work, evenly spread).
+template <typename T, int TM, int TN, int WGM, int WGN, int KS, int STAGES, int MINB, bool TB, bool TRI>
 __global__ void __launch_bounds__(WGM* WGN * 32, MINB)
 gemm_nn_kernel(int64_t m, int N, int K, double alpha, const T* __restrict__ A, int64_t lda, const T* __restrict__ B, int64_t ldb,
                double beta, T* C, int64_t ldc, int a_al16, int b_al16) {
@@ -113,7 +115,9 @@ gemm_nn_kernel(int64_t m, int N, int K, double alpha, const T* __restrict__ A, i
     }
 
     const int arow = wm * Cfg::WM + (lane >> 2), ak = lane & 3;
-    const int bcol = wn * Cfg::WN + (lane >> 2), bk = lane & 3;
+    const int bk = lane & 3;
+    // first column (within the CTA tile) of this warp's j-th 8-column MMA tile
+    auto tile_col = [&](int j) { return TRI ? (j * WGN + wn) * 8 : wn * Cfg::WN + j * 8; };
 
     for (int kt = 0; kt < nk; ++kt) {
         cp_async_wait<STAGES - 2>();
@@ -131,18 +135,21 @@ gemm_nn_kernel(int64_t m, int N, int K, double alpha, const T* __restrict__ A, i
 #pragma unroll
             for (int i = 0; i < Cfg::MI; ++i) af[i] = (double)a[(kk + ak) * Cfg::SA + arow + i * 8];
 #pragma unroll
-            for (int j = 0; j < Cfg::NI; ++j) bf[j] = (double)b[(bcol + j * 8) * Cfg::SB + kk + bk];
+            for (int j = 0; j < Cfg::NI; ++j) bf[j] = (double)b[(tile_col(j) + (lane >> 2)) * Cfg::SB + kk + bk];
 #pragma unroll
-            for (int i = 0; i < Cfg::MI; ++i)
+            for (int j = 0; j < Cfg::NI; ++j) {
+                // rows k >= (last column of the tile) + 1 of an upper-triangular B are zero (warp-uniform test)
+                if (TRI && kt * KS + kk >= n0 + tile_col(j) + 8) continue;
 #pragma unroll
-                for (int j = 0; j < Cfg::NI; ++j) dmma_884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+                for (int i = 0; i < Cfg::MI; ++i) dmma_884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+            }
         }
     }
     cp_async_wait<0>();
     __syncthreads();   // every warp is past its last smem read (and, for in-place use, every read of A is done)
 
     // epilogue
-    const int crow = wm * Cfg::WM + (lane >> 2), ccol = wn * Cfg::WN + 2 * (lane & 3);
+    const int crow = wm * Cfg::WM + (lane >> 2);
 #pragma unroll
     for (int i = 0; i < Cfg::MI; ++i) {
         const int64_t gr = m0 + crow + i * 8;
@@ -151,7 +158,7 @@ gemm_nn_kernel(int64_t m, int N, int K, double alpha, const T* __restrict__ A, i
         for (int j = 0; j < Cfg::NI; ++j) {
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
-                const int gc = n0 + ccol + j * 8 + h;
+                const int gc = n0 + tile_col(j) + 2 * (lane & 3) + h;
                 if (gc < N) {
                     T* p = C + gr + (int64_t)gc * ldc;
                     double v = alpha * acc[i][j][h];
@@ -169,11 +176,11 @@ static bool al16(const T* p, int64_t ld) {
     return (reinterpret_cast<uintptr_t>(p) % 16 == 0) && (ld % E == 0);
 }
 
-template <typename T, int TM, int TN, int WGM, int WGN, int KS, int STAGES, int MINB, bool TB = false>
+template <typename T, int TM, int TN, int WGM, int WGN, int KS, int STAGES, int MINB, bool TB = false, bool TRI = false>
 int launch_nn(Ctx* ctx, int64_t m, int N, int K, double alpha, const T* A, int64_t lda, const T* B, int64_t ldb, double beta,
                      T* C, int64_t ldc) {
     using Cfg = NNCfg<T, TM, TN, WGM, WGN, KS, STAGES>;
-    auto kern = gemm_nn_kernel<T, TM, TN, WGM, WGN, KS, STAGES, MINB, TB>;
+    auto kern = gemm_nn_kernel<T, TM, TN, WGM, WGN, KS, STAGES, MINB, TB, TRI>;
     RLB_CUDA_OK(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
     const int64_t nblk = ((m + TM - 1) / TM) * ((N + TN - 1) / TN);
     RLB_REQUIRE(ctx, nblk < (1ll << 31));
@@ -209,9 +216,14 @@ int gemm_nt(Ctx* ctx, int64_t m, int64_t N, int64_t K, double alpha, const T* A,
 // X <- alpha * X * B  in place (X: m x K, B: K x N with N <= K so the result fits in X's columns 0..N-1).
 // One CTA owns every column of its 64 rows, so all of X's tile is consumed before anything is stored.
 template <typename T>
-int gemm_nn_inplace(Ctx* ctx, int64_t m, int64_t N, int64_t K, double alpha, T* X, int64_t ldx, const T* B, int64_t ldb) {
+int gemm_nn_inplace(Ctx* ctx, int64_t m, int64_t N, int64_t K, double alpha, T* X, int64_t ldx, const T* B, int64_t ldb, bool b_upper_tri) {
     RLB_REQUIRE(ctx, N <= 256 && N <= K);
     if (m == 0 || N == 0) return 0;
+    if (b_upper_tri) {
+        if (N <= 64)  return launch_nn<T, 128, 64, 4, 2, 32, 2, 2, false, true>(ctx, m, (int)N, (int)K, alpha, X, ldx, B, ldb, 0.0, X, ldx);
+        if (N <= 128) return launch_nn<T, 128, 128, 2, 4, 32, 3, 1, false, true>(ctx, m, (int)N, (int)K, alpha, X, ldx, B, ldb, 0.0, X, ldx);
+        return launch_nn<T, 64, 256, 2, 4, 32, 2, 1, false, true>(ctx, m, (int)N, (int)K, alpha, X, ldx, B, ldb, 0.0, X, ldx);
+    }
     if (N <= 64)  return launch_nn<T, 128, 64, 4, 2, 32, 2, 2>(ctx, m, (int)N, (int)K, alpha, X, ldx, B, ldb, 0.0, X, ldx);
     if (N <= 128) return launch_nn<T, 128, 128, 2, 4, 32, 3, 1>(ctx, m, (int)N, (int)K, alpha, X, ldx, B, ldb, 0.0, X, ldx);
     return launch_nn<T, 64, 256, 2, 4, 32, 2, 1>(ctx, m, (int)N, (int)K, alpha, X, ldx, B, ldb, 0.0, X, ldx);
@@ -234,7 +246,8 @@ struct TNCfg {
 template <typename T, int T1, int T2, int WG1, int WG2, int KS, int STAGES, int MINB>
 __global__ void __launch_bounds__(WG1* WG2 * 32, MINB)
 gemm_tn_kernel(int64_t m, int N1, int N2, const T* __restrict__ A, int64_t lda, const T* __restrict__ B, int64_t ldb,
-               double* __restrict__ partial, int64_t rows_per_split, int tiles1, int upper_only, int a_al16, int b_al16) {
+               double* __restrict__ partial, int64_t rows_per_split, int tiles1, int upper_only, int a_al16, int b_al16,
+               double* __restrict__ sq_part) {
     using Cfg = TNCfg<T, T1, T2, WG1, WG2, KS, STAGES>;
     constexpr int E = 16 / sizeof(T);
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -280,6 +293,8 @@ gemm_tn_kernel(int64_t m, int N1, int N2, const T* __restrict__ A, int64_t lda, 
         cp_async_commit();
     }
     const int arow = w1 * Cfg::W1 + (lane >> 2), bcol = w2 * Cfg::W2 + (lane >> 2), kq = lane & 3;
+    const bool do_sq = (sq_part != nullptr) && (t2 == 0);
+    double sq = 0.0;
     for (int kt = 0; kt < nk; ++kt) {
         cp_async_wait<STAGES - 2>();
         __syncthreads();
@@ -290,6 +305,12 @@ gemm_tn_kernel(int64_t m, int N1, int N2, const T* __restrict__ A, int64_t lda, 
         }
         const T* a = sA + (size_t)(kt % STAGES) * Cfg::A_ELEMS;
         const T* b = sB + (size_t)(kt % STAGES) * Cfg::B_ELEMS;
+        if (do_sq) {   // fused lange(Fro, A) (rl_qb.hh:168): the A tile is already on chip, zero-filled outside the matrix
+            for (int e = tid; e < T1 * KS; e += Cfg::THREADS) {
+                const double v = (double)a[(e / KS) * Cfg::SK + (e % KS)];
+                sq = fma(v, v, sq);
+            }
+        }
 #pragma unroll
         for (int kk = 0; kk < KS; kk += 4) {
             double af[Cfg::MI], bf[Cfg::NI];
@@ -304,6 +325,17 @@ gemm_tn_kernel(int64_t m, int N1, int N2, const T* __restrict__ A, int64_t lda, 
         }
     }
     cp_async_wait<0>();
+    if (do_sq) {
+        __shared__ double sq_sh[32];
+        sq = warp_sum(sq);
+        if (lane == 0) sq_sh[warp] = sq;
+        __syncthreads();
+        if (tid == 0) {
+            double t = 0.0;
+            for (int w = 0; w < Cfg::THREADS / 32; ++w) t += sq_sh[w];
+            sq_part[(int64_t)split * tiles1 + t1] = t;
+        }
+    }
 
     double* P = partial + (int64_t)split * N1 * N2;
     const int crow = w1 * Cfg::W1 + (lane >> 2), ccol = w2 * Cfg::W2 + 2 * (lane & 3);
@@ -319,6 +351,14 @@ gemm_tn_kernel(int64_t m, int N1, int N2, const T* __restrict__ A, int64_t lda, 
                 if (gj < N2) P[gi + (int64_t)gj * N1] = acc[i][j][h];
             }
     }
+}
+
+// out = sum(part[0..n)) in a fixed order (single warp)
+__global__ void sum_fixed_order_kernel(const double* __restrict__ part, int n, double* __restrict__ out) {
+    double s = 0.0;
+    for (int i = threadIdx.x; i < n; i += 32) s += part[i];
+    s = warp_sum(s);
+    if (threadIdx.x == 0) *out = s;
 }
 
 // C = alpha * sum_s partial[s] + beta * C ; fixed summation order => run-to-run deterministic
@@ -340,7 +380,7 @@ __global__ void splitk_reduce_kernel(const double* __restrict__ partial, int spl
 
 template <typename T, int T1, int T2, int WG1, int WG2, int KS, int STAGES, int MINB = 1>
 int launch_tn(Ctx* ctx, int64_t m, int N1, int N2, double alpha, const T* A, int64_t lda, const T* B, int64_t ldb, double beta,
-                     T* C, int64_t ldc, int upper_only) {
+                     T* C, int64_t ldc, int upper_only, double* a_sumsq_out = nullptr) {
     using Cfg = TNCfg<T, T1, T2, WG1, WG2, KS, STAGES>;
     const int tiles1 = (N1 + T1 - 1) / T1, tiles2 = (N2 + T2 - 1) / T2;
     const int tiles = tiles1 * tiles2;
@@ -360,15 +400,17 @@ int launch_tn(Ctx* ctx, int64_t m, int N1, int N2, double alpha, const T* A, int
     rows_per_split = std::max<int64_t>(((rows_per_split + KS - 1) / KS) * KS, KS);
     const int splits = (int)std::max<int64_t>(1, (m + rows_per_split - 1) / rows_per_split);
     const size_t pbytes = (size_t)splits * N1 * N2 * sizeof(double);
-    RLB_CHECK(ws_reserve(ctx, pbytes));
+    RLB_CHECK(ws_reserve(ctx, pbytes + (size_t)splits * tiles1 * sizeof(double)));
     double* partial = static_cast<double*>(ctx->ws);
+    double* sq_part = a_sumsq_out ? partial + (size_t)splits * N1 * N2 : nullptr;
     auto kern = gemm_tn_kernel<T, T1, T2, WG1, WG2, KS, STAGES, MINB>;
     RLB_CUDA_OK(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
-    LaunchScope ls(ctx, RLB200_TIMER_GEMM_TN, 2);
+    LaunchScope ls(ctx, RLB200_TIMER_GEMM_TN, a_sumsq_out ? 3 : 2);
     dim3 grid((unsigned)tiles, (unsigned)splits);
     kern<<<grid, Cfg::THREADS, Cfg::SMEM, ctx->stream>>>(m, N1, N2, A, lda, B, ldb, partial, rows_per_split, tiles1, upper_only,
-                                                         al16(A, lda), al16(B, ldb));
+                                                         al16(A, lda), al16(B, ldb), sq_part);
     RLB_CUDA_OK(ctx, cudaGetLastError());
+    if (a_sumsq_out) sum_fixed_order_kernel<<<1, 32, 0, ctx->stream>>>(sq_part, splits * tiles1, a_sumsq_out);
     const int64_t total = (int64_t)N1 * N2;
     int rb = (int)std::min<int64_t>((total + 255) / 256, (int64_t)ctx->num_sms * 8);
     splitk_reduce_kernel<T><<<rb, 256, 0, ctx->stream>>>(partial, splits, N1, N2, alpha, beta, C, ldc, upper_only, T1, T2);
@@ -379,21 +421,21 @@ int launch_tn(Ctx* ctx, int64_t m, int N1, int N2, double alpha, const T* A, int
 // NOTE: uses ctx->ws for the split-K partials; callers must not hold live data at the start of ctx->ws.
 template <typename T>
 int gemm_tn(Ctx* ctx, int64_t m, int64_t N1, int64_t N2, double alpha, const T* A, int64_t lda, const T* B, int64_t ldb, double beta,
-            T* C, int64_t ldc, int upper_only) {
+            T* C, int64_t ldc, int upper_only, double* a_sumsq_out) {
     RLB_REQUIRE(ctx, m >= 0 && N1 >= 0 && N2 >= 0 && N1 < (1 << 20) && N2 < (1 << 20));
     if (N1 == 0 || N2 == 0) return 0;
     // tile shapes from tools/gemm_tune.cu: 64x128x32 with 2 CTAs/SM reaches 90% of the DMMA peak on A^T*Y (C2 shape);
     // the Gram (syrk) case prefers 64x64 tiles (finer triangle, 4 CTAs/SM)
     if (upper_only || (N1 <= 64 && N2 <= 64))
-        return launch_tn<T, 64, 64, 2, 2, 16, 3, 4>(ctx, m, (int)N1, (int)N2, alpha, A, lda, B, ldb, beta, C, ldc, upper_only);
-    return launch_tn<T, 64, 128, 2, 4, 32, 2, 2>(ctx, m, (int)N1, (int)N2, alpha, A, lda, B, ldb, beta, C, ldc, upper_only);
+        return launch_tn<T, 64, 64, 2, 2, 16, 3, 4>(ctx, m, (int)N1, (int)N2, alpha, A, lda, B, ldb, beta, C, ldc, upper_only, a_sumsq_out);
+    return launch_tn<T, 64, 128, 2, 4, 32, 2, 2>(ctx, m, (int)N1, (int)N2, alpha, A, lda, B, ldb, beta, C, ldc, upper_only, a_sumsq_out);
 }
 
 #define INST(T)                                                                                                                  \
     template int gemm_nn<T>(Ctx*, int64_t, int64_t, int64_t, double, const T*, int64_t, const T*, int64_t, double, T*, int64_t);  \
     template int gemm_nt<T>(Ctx*, int64_t, int64_t, int64_t, double, const T*, int64_t, const T*, int64_t, double, T*, int64_t);  \
-    template int gemm_nn_inplace<T>(Ctx*, int64_t, int64_t, int64_t, double, T*, int64_t, const T*, int64_t);                     \
-    template int gemm_tn<T>(Ctx*, int64_t, int64_t, int64_t, double, const T*, int64_t, const T*, int64_t, double, T*, int64_t, int);
+    template int gemm_nn_inplace<T>(Ctx*, int64_t, int64_t, int64_t, double, T*, int64_t, const T*, int64_t, bool);                     \
+    template int gemm_tn<T>(Ctx*, int64_t, int64_t, int64_t, double, const T*, int64_t, const T*, int64_t, double, T*, int64_t, int, double*);
 INST(double)
 INST(float)
 
