@@ -1,0 +1,51 @@
+"""Worker for tests/test_gpu_multi.py (launched under torchrun, one rank per GPU): row-sharded RSVD over NCCL must
+reproduce the single-GPU result on the same matrix and the same RNG state."""
+import json
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import randlapack_b200 as rl  # noqa: E402
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    ctx = rl.Context(local)
+    out = {}
+    for (m, n, k, p) in [(40000, 256, 32, 2), (70001, 128, 16, 3), (12800, 64, 64, 0)]:
+        # global matrix: planted decaying spectrum so that the factors are well defined; identical on every rank
+        g = torch.Generator(device="cuda").manual_seed(1234)
+        G1 = torch.randn((m, n), dtype=torch.float64, device="cuda", generator=g)
+        sig = torch.logspace(0, -3, n, dtype=torch.float64, device="cuda")
+        G2 = torch.linalg.qr(torch.randn((n, n), dtype=torch.float64, device="cuda", generator=g))[0]
+        A_full = rl.to_f((torch.linalg.qr(G1)[0] * sig) @ G2.t())
+        dist.broadcast(A_full.t(), src=0)
+        r0, r1 = rl.shard_rows(m, world, rank)
+        A_loc = rl.to_f(A_full[r0:r1].clone())
+        stack = rl.RSVD(rl.QB(rl.RF(rl.RS(rl.CholQRQ(), p, 1), rl.CholQRQ()), rl.CholQRQ(), orth_check=True), k)
+        ctx.set_shard(r0, m)
+        st = rl.RNGState(3)
+        rc, kk, U, S, V = stack.call(ctx, A_loc, k, 0.0, st)
+        ctx.clear_shard()
+        st1 = rl.RNGState(3)
+        rc1, kk1, U1, S1, V1 = stack.call(ctx, A_full, k, 0.0, st1)
+        res = {"rc": [rc, rc1], "k": [kk, kk1], "state_equal": st == st1,
+               "S_rel": ((S[:kk] - S1[:kk]).abs().max() / S1[0]).item() if kk else 0.0,
+               "V_abs": (V[:, :kk].abs() - V1[:, :kk].abs()).abs().max().item() if kk else 0.0,
+               "U_abs": (U[:, :kk].abs() - U1[r0:r1, :kk].abs()).abs().max().item() if kk else 0.0}
+        out[f"{m}x{n}_k{k}_p{p}"] = res
+    gathered = [None] * world
+    dist.all_gather_object(gathered, out)
+    if rank == 0:
+        print("MULTI_RESULT " + json.dumps(gathered))
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

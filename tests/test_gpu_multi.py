@@ -1,0 +1,27 @@
+"""Row-sharded RSVD over NCCL (2 GPUs) == single-GPU RSVD on the same matrix and RNG state.
+Tolerances: the sharded path reduces Gram / A^T Y partials in a different order (fp64 round-off only): sigma to 1e-12
+relative, factors to 1e-9 (up to sign)."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_sharded_rsvd_matches_single_gpu():
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29533", os.path.join(ROOT, "tests", "_multi_worker.py")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    line = [ln for ln in r.stdout.splitlines() if ln.startswith("MULTI_RESULT ")]
+    assert line, r.stdout[-2000:] + r.stderr[-4000:]
+    for per_rank in json.loads(line[0][len("MULTI_RESULT "):]):
+        for name, res in per_rank.items():
+            assert res["rc"][0] == res["rc"][1] and res["k"][0] == res["k"][1], (name, res)
+            assert res["state_equal"], (name, res)
+            assert res["S_rel"] <= 1e-12 and res["V_abs"] <= 1e-9 and res["U_abs"] <= 1e-9, (name, res)
