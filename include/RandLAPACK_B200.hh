@@ -1,0 +1,306 @@
+// RandLAPACK_B200.hh — algorithm objects for RandLAPACK's sketch-and-factor path, backed by librlb200.so (sm_100a).
+//
+// Same shape as the reference's objects (constructor arguments, public fields, `call` signatures with HOST pointers,
+// malloc-family ownership of QB/RSVD outputs, int return codes), so existing RandLAPACK compositions keep compiling:
+//
+//   reference (paths relative to the reference root)                       this header
+//   RandLAPACK::Stabilization<T>      comps/rl_orth.hh:13-23               rlb200::Stabilization<T>
+//   RandLAPACK::CholQRQ/PLUL/HQRQ<T>  comps/rl_orth.hh:25-230              rlb200::CholQRQ / PLUL / HQRQ<T>
+//   RandLAPACK::RowSketcher / RS      comps/rl_rs.hh:15-178                rlb200::RS<T>
+//   RandLAPACK::RangeFinder / RF      comps/rl_rf.hh:16-137                rlb200::RF<T>
+//   RandLAPACK::QBalg / QB            comps/rl_qb.hh:17-268                rlb200::QB<T>
+//   RandLAPACK::RSVDalg / RSVD        drivers/rl_rsvd.hh:15-154            rlb200::RSVD<T>
+//
+// Two modes:
+//  * default: self-contained (no reference headers needed); `rlb200::RNGState` stands in for RandBLAS::RNGState.
+//  * #define RLB200_WITH_RANDLAPACK (after including <RandLAPACK.hh>): every class derives from the reference's own
+//    abstract base and takes RandBLAS::RNGState<r123::Philox4x32>&, so e.g. a reference RandLAPACK::RSVD can be
+//    constructed on top of an rlb200::QB, or a reference QB on top of an rlb200::RF.
+//
+// The B200 objects compose with each other on the device in one flattened call (no host round trips between RS, RF,
+// QB and RSVD).  A B200 RS/RF/QB needs B200 stabilisers (it asks them for their kind); mixing in a CPU stabiliser is
+// rejected with std::invalid_argument rather than silently falling back to the CPU.
+#pragma once
+#include <cstdint>
+#include <cstdlib>
+#include <cstring>
+#include <limits>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "rlb200.h"
+
+namespace rlb200 {
+
+// thrown for negative RLB200_ERR_* codes (argument errors are RandLAPACK::Error / RandBLAS::Error in the reference,
+// CUDA failures abort there: RandLAPACK/rl_exceptions.hh:37-52, RandLAPACK/gpu_functions/rl_cuda_macros.hh:34-42)
+class Error : public std::runtime_error {
+public:
+    Error(int code, const std::string& what) : std::runtime_error("rlb200 error " + std::to_string(code) + ": " + what), code(code) {}
+    int code;
+};
+
+// RAII owner of an rlb200_ctx (device + stream + workspaces)
+class Context {
+public:
+    explicit Context(int device = 0, void* stream = nullptr) {
+        int rc = rlb200_create(&h_, device, stream);
+        if (rc) throw Error(rc, "rlb200_create failed (an sm_100 device is required; there is no CPU fallback)");
+    }
+    ~Context() { rlb200_destroy(h_); }
+    Context(const Context&) = delete;
+    Context& operator=(const Context&) = delete;
+    rlb200_ctx* get() const { return h_; }
+    int check(int rc) const {
+        if (rc < 0) throw Error(rc, rlb200_last_error(h_));
+        return rc;
+    }
+private:
+    rlb200_ctx* h_ = nullptr;
+};
+
+// process-wide context on device 0 for objects built with the reference's own constructor arguments
+inline Context& default_context() {
+    static Context ctx(0, nullptr);
+    return ctx;
+}
+
+#ifndef RLB200_WITH_RANDLAPACK
+// stand-in for RandBLAS::RNGState<r123::Philox4x32> (RandBLAS/RandBLAS/base.hh:64-164)
+struct RNGState {
+    uint32_t counter[4] = {0, 0, 0, 0};
+    uint32_t key[2] = {0, 0};
+    RNGState() = default;
+    explicit RNGState(uint64_t k) { key[0] = (uint32_t)k; key[1] = (uint32_t)(k >> 32); }
+};
+inline void state_to_words(const RNGState& s, uint32_t w[6]) { std::memcpy(w, s.counter, 16); std::memcpy(w + 4, s.key, 8); }
+inline void words_to_state(const uint32_t w[6], RNGState& s) { std::memcpy(s.counter, w, 16); std::memcpy(s.key, w + 4, 8); }
+using state_t = RNGState;
+#define RLB200_OVERRIDE
+#else
+using state_t = RandBLAS::RNGState<r123::Philox4x32>;
+inline void state_to_words(const state_t& s, uint32_t w[6]) { for (int i = 0; i < 4; ++i) w[i] = s.counter.v[i]; w[4] = s.key.v[0]; w[5] = s.key.v[1]; }
+inline void words_to_state(const uint32_t w[6], state_t& s) { for (int i = 0; i < 4; ++i) s.counter.v[i] = w[i]; s.key.v[0] = w[4]; s.key.v[1] = w[5]; }
+#define RLB200_OVERRIDE override
+#endif
+
+namespace detail {
+template <typename T> struct abi;
+template <> struct abi<double> {
+    static constexpr auto stab = rlb200_stab_f64_dev; static constexpr auto rs = rlb200_rs_f64_dev; static constexpr auto rf = rlb200_rf_f64_dev;
+    static constexpr auto qb = rlb200_qb_f64_dev; static constexpr auto rsvd_host = rlb200_rsvd_f64_host;
+};
+template <> struct abi<float> {
+    static constexpr auto stab = rlb200_stab_f32_dev; static constexpr auto rs = rlb200_rs_f32_dev; static constexpr auto rf = rlb200_rf_f32_dev;
+    static constexpr auto qb = rlb200_qb_f32_dev; static constexpr auto rsvd_host = rlb200_rsvd_f32_host;
+};
+
+// device buffer staged from / to a host pointer
+template <typename T>
+class DevBuf {
+public:
+    DevBuf(Context& c, int64_t count, const T* init = nullptr) : c_(c), n_(count) {
+        c_.check(rlb200_dev_alloc(c_.get(), sizeof(T) * (size_t)count, &p_));
+        if (init) c_.check(rlb200_copy_h2d(c_.get(), p_, init, sizeof(T) * (size_t)count));
+    }
+    ~DevBuf() { rlb200_dev_free(c_.get(), p_); }
+    T* ptr() { return static_cast<T*>(p_); }
+    void to_host(T* dst, int64_t count) { c_.check(rlb200_copy_d2h(c_.get(), dst, p_, sizeof(T) * (size_t)count)); }
+private:
+    Context& c_; void* p_ = nullptr; int64_t n_;
+};
+}  // namespace detail
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Stabilization (rl_orth.hh)
+// ---------------------------------------------------------------------------------------------------------------------
+#ifndef RLB200_WITH_RANDLAPACK
+template <typename T>
+class Stabilization {
+public:
+    virtual ~Stabilization() {}
+    virtual int call(int64_t m, int64_t k, T* A) = 0;
+};
+template <typename T> using StabBase = Stabilization<T>;
+#else
+template <typename T> using StabBase = RandLAPACK::Stabilization<T>;
+#endif
+
+// common part of the three B200 stabilisers: in place on a HOST m x k column-major matrix, like the reference
+template <typename T>
+class DeviceStab : public StabBase<T> {
+public:
+    DeviceStab(Context& ctx, int kind, bool c_check, bool verb) : cond_check(c_check), verbose(verb), chol_fail(false), ctx_(ctx), kind_(kind) {}
+    int call(int64_t m, int64_t k, T* A) override {
+        detail::DevBuf<T> d(ctx_, m * k, A);
+        int cf = 0;
+        int rc = ctx_.check(detail::abi<T>::stab(ctx_.get(), kind_, m, k, d.ptr(), cond_check, &cf));
+        chol_fail = cf != 0;
+        d.to_host(A, m * k);
+        return rc;
+    }
+    int kind() const { return kind_; }
+    Context& context() const { return ctx_; }
+    bool cond_check, verbose, chol_fail;
+private:
+    Context& ctx_;
+    int kind_;
+};
+// constructors: the reference's (c_check, verb) — using default_context() — or with an explicit Context first
+template <typename T> struct CholQRQ : DeviceStab<T> {
+    CholQRQ(bool c_check, bool verb) : DeviceStab<T>(default_context(), RLB200_STAB_CHOLQRQ, c_check, verb) {}
+    CholQRQ(Context& c, bool c_check, bool verb) : DeviceStab<T>(c, RLB200_STAB_CHOLQRQ, c_check, verb) {}
+};
+template <typename T> struct PLUL : DeviceStab<T> {
+    PLUL(bool c_check, bool verb) : DeviceStab<T>(default_context(), RLB200_STAB_PLUL, c_check, verb) {}
+    PLUL(Context& c, bool c_check, bool verb) : DeviceStab<T>(c, RLB200_STAB_PLUL, c_check, verb) {}
+};
+template <typename T> struct HQRQ : DeviceStab<T> {
+    HQRQ(bool c_check, bool verb) : DeviceStab<T>(default_context(), RLB200_STAB_HQRQ, c_check, verb) {}
+    HQRQ(Context& c, bool c_check, bool verb) : DeviceStab<T>(c, RLB200_STAB_HQRQ, c_check, verb) {}
+};
+
+template <typename T>
+inline DeviceStab<T>& require_device_stab(StabBase<T>& s, const char* who) {
+    auto* d = dynamic_cast<DeviceStab<T>*>(&s);
+    if (!d) throw std::invalid_argument(std::string(who) + ": composes only with rlb200 stabilisers (CholQRQ/PLUL/HQRQ); no CPU fallback");
+    return *d;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// RS (rl_rs.hh:31-178)
+// ---------------------------------------------------------------------------------------------------------------------
+template <typename T>
+class RS
+#ifdef RLB200_WITH_RANDLAPACK
+    : public RandLAPACK::RowSketcher<T, r123::Philox4x32>
+#endif
+{
+public:
+    RS(StabBase<T>& stab_obj, int64_t p, int64_t q, bool verb, bool cond)
+        : Stab_Obj(stab_obj), passes_over_data(p), passes_per_stab(q), verbose(verb), cond_check(cond) {}
+    virtual ~RS() {}
+    void fill(rlb200_stack_opts& o) const {
+        auto& s = require_device_stab<T>(Stab_Obj, "rlb200::RS");
+        o.passes_over_data = passes_over_data; o.passes_per_stab = passes_per_stab; o.stab = s.kind();
+        o.cond_check = s.cond_check;
+    }
+    Context& context() const { return require_device_stab<T>(Stab_Obj, "rlb200::RS").context(); }
+    // A: m x n (host, column-major); Omega: n x k (host, caller-allocated, as in RF::call rl_rf.hh:116)
+    int call(int64_t m, int64_t n, const T*& A, int64_t k, T*& Omega, state_t& state) RLB200_OVERRIDE {
+        Context& c = context();
+        rlb200_stack_opts o{}; fill(o);
+        detail::DevBuf<T> dA(c, m * n, A), dOm(c, n * k), dW(c, passes_over_data > 0 ? m * k : 1);
+        uint32_t w[6]; state_to_words(state, w);
+        int rc = c.check(detail::abi<T>::rs(c.get(), m, n, dA.ptr(), k, dOm.ptr(), dW.ptr(), w, &o));
+        words_to_state(w, state);
+        dOm.to_host(Omega, n * k);
+        return rc;
+    }
+    StabBase<T>& Stab_Obj;
+    int64_t passes_over_data, passes_per_stab;
+    bool verbose, cond_check;
+    std::vector<T> cond_nums;   // kept for source compatibility; condition-number logging is not offered on the device
+};
+
+// ---------------------------------------------------------------------------------------------------------------------
+// RF (rl_rf.hh:31-137)
+// ---------------------------------------------------------------------------------------------------------------------
+template <typename T>
+class RF
+#ifdef RLB200_WITH_RANDLAPACK
+    : public RandLAPACK::RangeFinder<T, r123::Philox4x32>
+#endif
+{
+public:
+    RF(RS<T>& rs_obj, StabBase<T>& orth_obj, bool verb, bool cond) : rs(rs_obj), orth(orth_obj), verbose(verb), cond_check(cond) {}
+    virtual ~RF() {}
+    void fill(rlb200_stack_opts& o) const { rs.fill(o); o.orth_rf = require_device_stab<T>(orth, "rlb200::RF").kind(); }
+    Context& context() const { return rs.context(); }
+    int call(int64_t m, int64_t n, const T* A, int64_t k, T* Q, state_t& state) RLB200_OVERRIDE {
+        Context& c = context();
+        rlb200_stack_opts o{}; fill(o);
+        detail::DevBuf<T> dA(c, m * n, A), dQ(c, m * k);
+        uint32_t w[6]; state_to_words(state, w);
+        int rc = c.check(detail::abi<T>::rf(c.get(), m, n, dA.ptr(), k, dQ.ptr(), w, &o));
+        words_to_state(w, state);
+        dQ.to_host(Q, m * k);
+        return rc;
+    }
+    RS<T>& rs;
+    StabBase<T>& orth;
+    bool verbose, cond_check;
+    std::vector<T> cond_nums;
+};
+
+// ---------------------------------------------------------------------------------------------------------------------
+// QB (rl_qb.hh:36-268)
+// ---------------------------------------------------------------------------------------------------------------------
+template <typename T>
+class QB
+#ifdef RLB200_WITH_RANDLAPACK
+    : public RandLAPACK::QBalg<T, r123::Philox4x32>
+#endif
+{
+public:
+    QB(RF<T>& rf_obj, StabBase<T>& orth_obj, bool verb, bool orth) : rf(rf_obj), orth(orth_obj), verbose(verb), orth_check(orth) {}
+    virtual ~QB() {}
+    void fill(rlb200_stack_opts& o) const {
+        rf.fill(o); o.orth_qb = require_device_stab<T>(orth, "rlb200::QB").kind(); o.orth_check = orth_check;
+    }
+    Context& context() const { return rf.context(); }
+    // Q, BT: nullptr or malloc-family on entry; (re)allocated here with calloc and owned by the caller (rl_qb.hh:154-159)
+    int call(int64_t m, int64_t n, T* A, int64_t& k, int64_t block_sz, T tol, T*& Q, T*& BT, state_t& state) RLB200_OVERRIDE {
+        Context& c = context();
+        rlb200_stack_opts o{}; fill(o); o.block_sz = block_sz;
+        if (Q) free(Q);
+        if (BT) free(BT);
+        const int64_t k_in = k;
+        Q = (T*)calloc((size_t)(m * k_in), sizeof(T));
+        BT = (T*)calloc((size_t)(n * k_in), sizeof(T));
+        detail::DevBuf<T> dA(c, m * n, A), dQ(c, m * k_in), dBT(c, n * k_in);
+        uint32_t w[6]; state_to_words(state, w);
+        int rc = c.check(detail::abi<T>::qb(c.get(), m, n, dA.ptr(), &k, block_sz, tol, dQ.ptr(), dBT.ptr(), nullptr, w, &o));
+        words_to_state(w, state);
+        if (k > 0) { dQ.to_host(Q, m * k); dBT.to_host(BT, n * k); }
+        return rc;
+    }
+    RF<T>& rf;
+    StabBase<T>& orth;
+    bool verbose, orth_check;
+};
+
+// ---------------------------------------------------------------------------------------------------------------------
+// RSVD (rl_rsvd.hh:34-154)
+// ---------------------------------------------------------------------------------------------------------------------
+template <typename T>
+class RSVD
+#ifdef RLB200_WITH_RANDLAPACK
+    : public RandLAPACK::RSVDalg<T, r123::Philox4x32>
+#endif
+{
+public:
+    RSVD(QB<T>& qb_obj, int64_t b_sz) : QB_Obj(qb_obj), block_sz(b_sz) {}
+    virtual ~RSVD() {}
+    // U (m x k), S (k), V (n x k) are calloc'd here and free()d by the caller (rl_rsvd.hh:141-143, test_rsvd.cc:162-164)
+    int call(int64_t m, int64_t n, T* A, int64_t& k, T tol, T*& U, T*& S, T*& V, state_t& state) RLB200_OVERRIDE {
+        Context& c = QB_Obj.context();
+        rlb200_stack_opts o{}; QB_Obj.fill(o); o.block_sz = block_sz;
+        const int64_t k_in = k;
+        if (k_in <= 0) throw Error(RLB200_ERR_ARG, "target rank k must be > 0");          // rl_rsvd.hh:130
+        U = (T*)calloc((size_t)(m * k_in), sizeof(T));
+        S = (T*)calloc((size_t)k_in, sizeof(T));
+        V = (T*)calloc((size_t)(n * k_in), sizeof(T));
+        uint32_t w[6]; state_to_words(state, w);
+        int rc = c.check(detail::abi<T>::rsvd_host(c.get(), m, n, A, &k, tol, U, S, V, w, &o, &qb_code));
+        words_to_state(w, state);
+        return rc;
+    }
+    QB<T>& QB_Obj;
+    int64_t block_sz;
+    int qb_code = 0;   // the code QB returned (the reference discards it, rl_rsvd.hh:137)
+};
+
+}  // namespace rlb200

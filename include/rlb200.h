@@ -94,6 +94,13 @@ enum { RLB200_TIMER_GEMM_NN = 0, RLB200_TIMER_GEMM_TN = 1, RLB200_TIMER_RIGHTMUL
 RLB200_API int rlb200_timers_enable(rlb200_ctx* ctx, int on);
 RLB200_API int rlb200_timer_read(rlb200_ctx* ctx, int which, double* ms, int64_t* launches, int reset);
 
+/* ---- device memory helpers for host-pointer callers (the C++ adapters in RandLAPACK_B200.hh stage through these so that
+ *      they need no CUDA headers).  Copies are stream-ordered on the context's stream; d2h blocks until complete. */
+RLB200_API int rlb200_dev_alloc(rlb200_ctx* ctx, size_t bytes, void** out_dev);
+RLB200_API int rlb200_dev_free(rlb200_ctx* ctx, void* dev);
+RLB200_API int rlb200_copy_h2d(rlb200_ctx* ctx, void* dst_dev, const void* src_host, size_t bytes);
+RLB200_API int rlb200_copy_d2h(rlb200_ctx* ctx, void* dst_host, const void* src_dev, size_t bytes);
+
 /* ---- a1: Philox4x32-10 stream (r123::Philox4x32 via RandBLAS/RandBLAS/base.hh:53) -----------
  * out_dev[4*i .. 4*i+3] = Philox(counter = state.counter + i, key = state.key), i in [0,n). */
 RLB200_API int rlb200_philox_stream_dev(rlb200_ctx* ctx, const uint32_t state[6], int64_t n, uint32_t* out_dev);

@@ -54,6 +54,10 @@ SIGNATURES = {
     "rlb200_timers_enable": (c_int, [c_vp, c_int]),
     "rlb200_timer_read": (c_int, [c_vp, c_int, ctypes.POINTER(ctypes.c_double), P_i64, c_int]),
     "rlb200_philox_stream_dev": (c_int, [c_vp, P_u32, c_i64, c_vp]),
+    "rlb200_dev_alloc": (c_int, [c_vp, ctypes.c_size_t, ctypes.POINTER(c_vp)]),
+    "rlb200_dev_free": (c_int, [c_vp, c_vp]),
+    "rlb200_copy_h2d": (c_int, [c_vp, c_vp, c_vp, ctypes.c_size_t]),
+    "rlb200_copy_d2h": (c_int, [c_vp, c_vp, c_vp, ctypes.c_size_t]),
 }
 for _suf, _ft in (("f64", ctypes.c_double), ("f32", ctypes.c_float)):
     for _name, _sig in _F(_ft).items():

@@ -94,6 +94,34 @@ int rlb200_timer_read(rlb200_ctx* ctx, int which, double* ms, int64_t* launches,
     return 0;
 }
 
+int rlb200_dev_alloc(rlb200_ctx* ctx, size_t bytes, void** out_dev) {
+    CTX_OK(ctx); RLB_CHECK(bind(ctx)); RLB_REQUIRE(ctx, out_dev != nullptr);
+    *out_dev = nullptr;
+    if (cudaMalloc(out_dev, bytes ? bytes : 1) != cudaSuccess) {
+        cudaGetLastError();
+        ctx->err = "device allocation of " + std::to_string(bytes) + " bytes failed";
+        return RLB200_ERR_ALLOC;
+    }
+    return 0;
+}
+int rlb200_dev_free(rlb200_ctx* ctx, void* dev) {
+    CTX_OK(ctx); RLB_CHECK(bind(ctx));
+    RLB_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+    RLB_CUDA_OK(ctx, cudaFree(dev));
+    return 0;
+}
+int rlb200_copy_h2d(rlb200_ctx* ctx, void* dst_dev, const void* src_host, size_t bytes) {
+    CTX_OK(ctx); RLB_CHECK(bind(ctx));
+    RLB_CUDA_OK(ctx, cudaMemcpyAsync(dst_dev, src_host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    return 0;
+}
+int rlb200_copy_d2h(rlb200_ctx* ctx, void* dst_host, const void* src_dev, size_t bytes) {
+    CTX_OK(ctx); RLB_CHECK(bind(ctx));
+    RLB_CUDA_OK(ctx, cudaMemcpyAsync(dst_host, src_dev, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    RLB_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
 int rlb200_philox_stream_dev(rlb200_ctx* ctx, const uint32_t state[6], int64_t n, uint32_t* out_dev) {
     CTX_OK(ctx); RLB_CHECK(bind(ctx));
     return philox_stream(ctx, state, n, out_dev);

@@ -1,0 +1,142 @@
+// Drop-in test of include/RandLAPACK_B200.hh (needs a B200 at run time).
+//   default build  : self-contained objects, checks the factorisation invariants the reference's tests assert
+//                    (test/comps/test_qb.cc:162-174 exponents).
+//   -DWITH_REF     : compiled against the UNMODIFIED reference headers; the reference's own RandLAPACK::RSVD driver runs on top
+//                    of rlb200::QB (which derives from RandLAPACK::QBalg), and a reference QB on top of rlb200::RF, and both
+//                    are compared with the all-reference CPU stack on the same input and RNG state.
+#ifdef WITH_REF
+#include <RandBLAS.hh>
+#include "RandLAPACK/rl_blaspp.hh"
+#include "RandLAPACK/rl_lapackpp.hh"
+#include "RandLAPACK/rl_exceptions.hh"
+#include "RandLAPACK/misc/rl_util.hh"
+#include "RandLAPACK/comps/rl_orth.hh"
+#include "RandLAPACK/comps/rl_rs.hh"
+#include "RandLAPACK/comps/rl_rf.hh"
+#include "RandLAPACK/comps/rl_qb.hh"
+#include "RandLAPACK/drivers/rl_rsvd.hh"
+#include "RandLAPACK/testing/rl_gen.hh"
+#define RLB200_WITH_RANDLAPACK
+#endif
+#include "RandLAPACK_B200.hh"
+
+#include <cmath>
+#include <cstdio>
+#include <random>
+#include <vector>
+
+static double fro(const std::vector<double>& a) { double s = 0; for (double v : a) s += v * v; return std::sqrt(s); }
+
+// ||Q^T Q - I||_F for an m x k column-major Q
+static double orth_err(int64_t m, int64_t k, const double* Q) {
+    double s = 0;
+    for (int64_t i = 0; i < k; ++i)
+        for (int64_t j = 0; j < k; ++j) {
+            double d = 0;
+            for (int64_t r = 0; r < m; ++r) d += Q[r + i * m] * Q[r + j * m];
+            d -= (i == j);
+            s += d * d;
+        }
+    return std::sqrt(s);
+}
+// ||A - U diag(S) V^T||_F
+static double resid(int64_t m, int64_t n, int64_t k, const double* A, const double* U, const double* S, const double* V) {
+    double s = 0;
+    for (int64_t j = 0; j < n; ++j)
+        for (int64_t i = 0; i < m; ++i) {
+            double d = A[i + j * m];
+            for (int64_t l = 0; l < k; ++l) d -= U[i + l * m] * S[l] * V[j + l * n];
+            s += d * d;
+        }
+    return std::sqrt(s);
+}
+
+int main() {
+    const int64_t m = 600, n = 80, k = 20, p = 2, q = 1;
+    int fails = 0;
+#ifndef WITH_REF
+    // planted rank-k matrix + small noise
+    std::mt19937_64 gen(7);
+    std::normal_distribution<double> nd;
+    std::vector<double> L(m * k), R(n * k), A(m * n, 0.0);
+    for (auto& v : L) v = nd(gen);
+    for (auto& v : R) v = nd(gen);
+    for (int64_t j = 0; j < n; ++j)
+        for (int64_t i = 0; i < m; ++i) {
+            double s = 1e-9 * nd(gen);
+            for (int64_t l = 0; l < k; ++l) s += L[i + l * m] * R[j + l * n] / (1.0 + l);
+            A[i + j * m] = s;
+        }
+    rlb200::CholQRQ<double> stab(false, false), orth_rf(false, false), orth_qb(false, false);   // the reference's ctor arguments
+    rlb200::RS<double> rs(stab, p, q, false, false);
+    rlb200::RF<double> rf(rs, orth_rf, false, false);
+    rlb200::QB<double> qb(rf, orth_qb, false, true);
+    rlb200::RSVD<double> rsvd(qb, k);
+    rlb200::RNGState state(0);
+    double *U = nullptr, *S = nullptr, *V = nullptr;
+    int64_t kk = k;
+    int rc = rsvd.call(m, n, A.data(), kk, 0.0, U, S, V, state);
+    const double eps625 = std::pow(std::numeric_limits<double>::epsilon(), 0.625);
+    double eu = orth_err(m, kk, U), ev = orth_err(n, kk, V), r = resid(m, n, kk, A.data(), U, S, V) / fro(A);
+    std::printf("standalone: rc=%d k=%lld qb_code=%d  ||U'U-I||=%.2e ||V'V-I||=%.2e  resid=%.2e  state.ctr0=%u\n", rc, (long long)kk,
+                rsvd.qb_code, eu, ev, r, state.counter[0]);
+    fails += !(rc == 0 && kk == k && eu <= eps625 && ev <= eps625 && r <= 1e-7 && state.counter[0] == (uint32_t)(k * ((n + 3) / 4)));
+    free(U); free(S); free(V);
+    // a CPU stabiliser cannot be mixed into a device stack: rejected, never a silent fallback
+    struct HostStab : rlb200::Stabilization<double> { int call(int64_t, int64_t, double*) override { return 0; } } hs;
+    rlb200::RS<double> bad(hs, 0, 1, false, false);
+    try { rlb200_stack_opts o{}; bad.fill(o); fails += 1; } catch (const std::invalid_argument&) {}
+#else
+    using RNG = r123::Philox4x32;
+    auto run = [&](int which, std::vector<double>& Sout, double& res, double& eu) {
+        auto state = RandBLAS::RNGState<RNG>();
+        std::vector<double> A(m * n);
+        RandLAPACK::gen::mat_gen_info<double> info((int64_t&)m, (int64_t&)n, RandLAPACK::gen::polynomial);
+        info.cond_num = 2025; info.rank = n; info.exponent = 2.0;
+        RandLAPACK::gen::mat_gen(info, A.data(), state);
+        std::vector<double> A0 = A;
+        double *U = nullptr, *S = nullptr, *V = nullptr;
+        int64_t kk = k;
+        int rc = 0;
+        if (which == 0) {          // all reference (CPU)
+            RandLAPACK::CholQRQ<double> stab(false, false), o1(false, false), o2(false, false);
+            RandLAPACK::RS<double, RNG> rs(stab, p, q, false, false);
+            RandLAPACK::RF<double, RNG> rf(rs, o1, false, false);
+            RandLAPACK::QB<double, RNG> qb(rf, o2, false, false);
+            RandLAPACK::RSVD<double, RNG> rsvd(qb, k);
+            rc = rsvd.call(m, n, A.data(), kk, 0.0, U, S, V, state);
+        } else if (which == 1) {   // reference RSVD driver on top of the B200 QB (derives from RandLAPACK::QBalg)
+            rlb200::CholQRQ<double> stab(false, false), o1(false, false), o2(false, false);
+            rlb200::RS<double> rs(stab, p, q, false, false);
+            rlb200::RF<double> rf(rs, o1, false, false);
+            rlb200::QB<double> qb(rf, o2, false, false);
+            RandLAPACK::RSVD<double, RNG> rsvd(qb, k);
+            rc = rsvd.call(m, n, A.data(), kk, 0.0, U, S, V, state);
+        } else {                   // reference QB + RSVD on top of the B200 RF (derives from RandLAPACK::RangeFinder)
+            rlb200::CholQRQ<double> stab(false, false), o1(false, false);
+            RandLAPACK::CholQRQ<double> o2(false, false);
+            rlb200::RS<double> rs(stab, p, q, false, false);
+            rlb200::RF<double> rf(rs, o1, false, false);
+            RandLAPACK::QB<double, RNG> qb(rf, o2, false, false);
+            RandLAPACK::RSVD<double, RNG> rsvd(qb, k);
+            rc = rsvd.call(m, n, A.data(), kk, 0.0, U, S, V, state);
+        }
+        Sout.assign(S, S + kk);
+        res = resid(m, n, kk, A0.data(), U, S, V) / fro(A0);
+        eu = orth_err(m, kk, U);
+        std::printf("with-ref[%d]: rc=%d k=%lld resid=%.12e ||U'U-I||=%.2e state.ctr0=%u\n", which, rc, (long long)kk, res, eu, state.counter.v[0]);
+        free(U); free(S); free(V);
+        return (int)state.counter.v[0];
+    };
+    std::vector<double> S0, S1, S2;
+    double r0, r1, r2, e0, e1, e2;
+    int c0 = run(0, S0, r0, e0), c1 = run(1, S1, r1, e1), c2 = run(2, S2, r2, e2);
+    double d1 = 0, d2 = 0;
+    for (int64_t i = 0; i < k; ++i) { d1 = std::max(d1, std::abs(S1[i] - S0[i]) / S0[0]); d2 = std::max(d2, std::abs(S2[i] - S0[i]) / S0[0]); }
+    std::printf("with-ref: max rel sigma diff  B200-QB under ref RSVD: %.2e   B200-RF under ref QB: %.2e\n", d1, d2);
+    // device Gaussian entries differ from the host libm path by a few float ulps => 2e-6 (see tests/test_gpu_fill.py)
+    fails += !(c0 == c1 && c1 == c2 && d1 <= 2e-6 && d2 <= 2e-6 && std::abs(r1 - r0) <= 2e-6 && std::abs(r2 - r0) <= 2e-6 && e1 <= 1e-9 && e2 <= 1e-9);
+#endif
+    std::printf(fails ? "DROPIN_FAIL\n" : "DROPIN_OK\n");
+    return fails;
+}
