@@ -90,7 +90,8 @@ RLB200_API int rlb200_set_shard(rlb200_ctx* ctx, int64_t row_offset, int64_t m_g
 /* kernels launched since creation / last reset (for bench.py's gpu_launches). */
 RLB200_API int64_t rlb200_launch_count(rlb200_ctx* ctx, int reset);
 /* CUDA-event timing of the kernels tagged `which` (see RLB200_TIMER_*), ms since last reset. */
-enum { RLB200_TIMER_GEMM_NN = 0, RLB200_TIMER_GEMM_TN = 1, RLB200_TIMER_RIGHTMUL = 2, RLB200_TIMER_SMALL = 3, RLB200_TIMER_FILL = 4, RLB200_TIMER_COUNT = 5 };
+enum { RLB200_TIMER_GEMM_NN = 0, RLB200_TIMER_GEMM_TN = 1, RLB200_TIMER_RIGHTMUL = 2, RLB200_TIMER_SMALL = 3, RLB200_TIMER_FILL = 4, RLB200_TIMER_SKETCH = 5,
+       RLB200_TIMER_FACTOR = 6, RLB200_TIMER_COUNT = 7 };
 RLB200_API int rlb200_timers_enable(rlb200_ctx* ctx, int on);
 RLB200_API int rlb200_timer_read(rlb200_ctx* ctx, int which, double* ms, int64_t* launches, int reset);
 
@@ -114,6 +115,50 @@ RLB200_API int rlb200_fill_dense_f64_dev(rlb200_ctx* ctx, int64_t n_rows, int64_
                               int64_t sub_rows, int64_t sub_cols, int64_t ro, int64_t co, double* buff_dev, uint32_t state[6]);
 RLB200_API int rlb200_fill_dense_f32_dev(rlb200_ctx* ctx, int64_t n_rows, int64_t n_cols, int family, int major_axis, int layout,
                               int64_t sub_rows, int64_t sub_cols, int64_t ro, int64_t co, float* buff_dev, uint32_t state[6]);
+
+/* ---- a6: RandBLAS::fill_sparse / fill_sparse_unpacked (RandBLAS/RandBLAS/sparse_skops.hh:568-704, 746) ---------------------
+ * COO triplets (vals, rows, cols; 0-based, relative to the block) of the sub_rows x sub_cols block at (ro, co) of the sample of
+ * SparseDist(n_rows, n_cols, vec_nnz, major_axis) defined by `state`, in the reference's order (one long-axis vector after the
+ * other, short-axis indices ascending within a vector).  *nnz_out (HOST) receives the number of triplets; with NULL output
+ * arrays only the size bound vec_nnz * (#long-axis vectors) is returned and `state` is untouched (the reference's size query).
+ * state <- the reference's returned state (counter after the last sampled vector).  Axis::Short only (SASO; the default). */
+RLB200_API int rlb200_fill_sparse_f64_dev(rlb200_ctx* ctx, int64_t n_rows, int64_t n_cols, int64_t vec_nnz, int major_axis,
+                               int64_t sub_rows, int64_t sub_cols, int64_t ro, int64_t co, int64_t* nnz_out, double* vals_dev,
+                               int64_t* rows_dev, int64_t* cols_dev, uint32_t state[6]);
+RLB200_API int rlb200_fill_sparse_f32_dev(rlb200_ctx* ctx, int64_t n_rows, int64_t n_cols, int64_t vec_nnz, int major_axis,
+                               int64_t sub_rows, int64_t sub_cols, int64_t ro, int64_t co, int64_t* nnz_out, float* vals_dev,
+                               int64_t* rows_dev, int64_t* cols_dev, uint32_t state[6]);
+
+/* ---- a7: sketch_general(ColMajor, NoTrans, NoTrans, d, n, m, alpha, S, ro_s, co_s, A, lda, beta, B, ldb) with a SparseSkOp
+ *      (RandBLAS/RandBLAS/skge.hh:538-571 lskges; call site RandLAPACK/drivers/rl_cqrrpt.hh:214-221).
+ * S = SparseSkOp(SparseDist(S_rows, S_cols, vec_nnz, Axis::Short), state), wide (S_rows <= S_cols), regenerated on device from
+ * the Philox state (never passed in).  B(d x n) = alpha * S[ro_s:ro_s+d, co_s:co_s+m] * A(m x n) + beta * B.
+ * state <- S.next_state (sparse_skops.hh:302-312).  Row-sharded contexts use the shard's columns of S and allreduce B. */
+RLB200_API int rlb200_sketch_sparse_left_f64_dev(rlb200_ctx* ctx, int64_t S_rows, int64_t S_cols, int64_t vec_nnz, int64_t d, int64_t n,
+                                      int64_t m, double alpha, int64_t ro_s, int64_t co_s, const double* A_dev, int64_t lda, double beta,
+                                      double* B_dev, int64_t ldb, uint32_t state[6]);
+RLB200_API int rlb200_sketch_sparse_left_f32_dev(rlb200_ctx* ctx, int64_t S_rows, int64_t S_cols, int64_t vec_nnz, int64_t d, int64_t n,
+                                      int64_t m, float alpha, int64_t ro_s, int64_t co_s, const float* A_dev, int64_t lda, float beta,
+                                      float* B_dev, int64_t ldb, uint32_t state[6]);
+
+/* ---- a5: sketch_general with a DenseSkOp, left (lskge3, skge.hh:155-203) and right (rskge3, skge.hh:308-356), ColMajor, NoTrans.
+ * S = DenseSkOp(DenseDist(S_rows, S_cols, family, major_axis), state); it is never materialised as a whole: panels are regenerated
+ * from the Philox state into an L2-resident ring buffer and consumed by the tensor-pipe GEMM.
+ *   left :  B(d x n) = alpha * S[ro_s:ro_s+d, co_s:co_s+m] * A(m x n) + beta * B
+ *   right:  B(m x d) = alpha * A(m x n) * S[ro_s:ro_s+n, co_s:co_s+d] + beta * B
+ * state <- S.next_state. */
+RLB200_API int rlb200_sketch_dense_left_f64_dev(rlb200_ctx* ctx, int64_t S_rows, int64_t S_cols, int family, int major_axis, int64_t d,
+                                     int64_t n, int64_t m, double alpha, int64_t ro_s, int64_t co_s, const double* A_dev, int64_t lda,
+                                     double beta, double* B_dev, int64_t ldb, uint32_t state[6]);
+RLB200_API int rlb200_sketch_dense_left_f32_dev(rlb200_ctx* ctx, int64_t S_rows, int64_t S_cols, int family, int major_axis, int64_t d,
+                                     int64_t n, int64_t m, float alpha, int64_t ro_s, int64_t co_s, const float* A_dev, int64_t lda,
+                                     float beta, float* B_dev, int64_t ldb, uint32_t state[6]);
+RLB200_API int rlb200_sketch_dense_right_f64_dev(rlb200_ctx* ctx, int64_t S_rows, int64_t S_cols, int family, int major_axis, int64_t m,
+                                      int64_t d, int64_t n, double alpha, const double* A_dev, int64_t lda, int64_t ro_s, int64_t co_s,
+                                      double beta, double* B_dev, int64_t ldb, uint32_t state[6]);
+RLB200_API int rlb200_sketch_dense_right_f32_dev(rlb200_ctx* ctx, int64_t S_rows, int64_t S_cols, int family, int major_axis, int64_t m,
+                                      int64_t d, int64_t n, float alpha, const float* A_dev, int64_t lda, int64_t ro_s, int64_t co_s,
+                                      float beta, float* B_dev, int64_t ldb, uint32_t state[6]);
 
 /* ---- blas::gemm as used on the path (ColMajor; rl_rs.hh:142,153,165; rl_rf.hh:123; rl_qb.hh:218;
  *      rl_rsvd.hh:148).  transa/transb: 0 = NoTrans, 1 = Trans.  Shapes the tall-skinny kernels cover:

@@ -165,6 +165,83 @@ static int mat_gen_impl(int type, int64_t m, int64_t n, int64_t rank, T cond, T 
     RL_CATCH
 }
 
+template <typename T>
+static int fill_sparse_impl(int64_t n_rows, int64_t n_cols, int64_t vec_nnz, int major_axis, int64_t sub_rows, int64_t sub_cols,
+                            int64_t ro, int64_t co, int64_t* nnz, T* vals, int64_t* rows, int64_t* cols, uint32_t state[6]) {
+    RL_TRY
+    RandBLAS::SparseDist D(n_rows, n_cols, vec_nnz, major_axis == RL_AXIS_SHORT ? RandBLAS::Axis::Short : RandBLAS::Axis::Long);
+    State st = load_state(state);
+    // RandBLAS/RandBLAS/sparse_skops.hh:568-704
+    State nxt = RandBLAS::fill_sparse_unpacked(D, sub_rows, sub_cols, ro, co, *nnz, vals, rows, cols, st);
+    store_state(nxt, state);
+    return 0;
+    RL_CATCH
+}
+
+template <typename T>
+static int sketch_sparse_left_impl(int64_t S_rows, int64_t S_cols, int64_t vec_nnz, int64_t d, int64_t n, int64_t m, T alpha, int64_t ro,
+                                   int64_t co, const T* A, int64_t lda, T beta, T* B, int64_t ldb, uint32_t state[6]) {
+    RL_TRY
+    RandBLAS::SparseDist DS(S_rows, S_cols, vec_nnz);
+    State st = load_state(state);
+    RandBLAS::SparseSkOp<T, RNG> S(DS, st);      // as at RandLAPACK/drivers/rl_cqrrpt.hh:214-216
+    store_state(S.next_state, state);
+    RandBLAS::sketch_general(blas::Layout::ColMajor, blas::Op::NoTrans, blas::Op::NoTrans, d, n, m, alpha, S, ro, co, A, lda, beta, B, ldb);
+    return 0;
+    RL_CATCH
+}
+
+template <typename T>
+static int sketch_dense_impl(bool left, int64_t S_rows, int64_t S_cols, int family, int major_axis, int64_t d, int64_t n, int64_t m,
+                             T alpha, int64_t ro, int64_t co, const T* A, int64_t lda, T beta, T* B, int64_t ldb, uint32_t state[6]) {
+    RL_TRY
+    RandBLAS::DenseDist D(S_rows, S_cols, family == RL_FAMILY_UNIFORM ? RandBLAS::ScalarDist::Uniform : RandBLAS::ScalarDist::Gaussian,
+                          major_axis == RL_AXIS_SHORT ? RandBLAS::Axis::Short : RandBLAS::Axis::Long);
+    State st = load_state(state);
+    RandBLAS::DenseSkOp<T, RNG> S(D, st);
+    store_state(S.next_state, state);
+    if (left)   // RandBLAS/RandBLAS/skge.hh:883-905 -> lskge3 :155-203
+        RandBLAS::sketch_general(blas::Layout::ColMajor, blas::Op::NoTrans, blas::Op::NoTrans, d, n, m, alpha, S, ro, co, A, lda, beta, B, ldb);
+    else        // skge.hh:1031-1052 -> rskge3 :308-356   (here m x d = (m x n)(n x d))
+        RandBLAS::sketch_general(blas::Layout::ColMajor, blas::Op::NoTrans, blas::Op::NoTrans, m, d, n, alpha, A, lda, S, ro, co, beta, B, ldb);
+    return 0;
+    RL_CATCH
+}
+
+// CQRRPT (RandLAPACK/drivers/rl_cqrrpt.hh:146-391) with the default subroutines (geqp3) unless qrcp says otherwise
+template <typename T>
+static int cqrrpt_impl(int64_t m, int64_t n, T* A, int64_t lda, T* R, int64_t ldr, int64_t* J, T d_factor, T eps, int64_t nnz, int qrcp,
+                       int64_t* rank, uint32_t state[6]) {
+    RL_TRY
+    RandLAPACK::CQRRPT<T, RNG> alg(false, eps);
+    alg.nnz = nnz;
+    alg.qrcp = qrcp == 1 ? RandLAPACK::CQRRPTSubroutines::QRCP::bqrrp
+             : qrcp == 2 ? RandLAPACK::CQRRPTSubroutines::QRCP::hqrrp : RandLAPACK::CQRRPTSubroutines::QRCP::geqp3;
+    State st = load_state(state);
+    int rc = alg.call(m, n, A, lda, R, ldr, J, d_factor, st);
+    store_state(st, state);
+    *rank = alg.rank;
+    return rc;
+    RL_CATCH
+}
+
+// BQRRP (RandLAPACK/drivers/rl_bqrrp.hh:154-665). qrcp_wide: 0 luqr (default), 1 geqp3; qr_tall: 0 geqrf (default), 1 cholqr, 2 geqrt
+template <typename T>
+static int bqrrp_impl(int64_t m, int64_t n, T* A, int64_t lda, T d_factor, int64_t b_sz, int qrcp_wide, int qr_tall, T* tau, int64_t* J,
+                      int64_t* rank, uint32_t state[6]) {
+    RL_TRY
+    RandLAPACK::BQRRP<T, RNG> alg(false, b_sz);
+    alg.qrcp_wide = qrcp_wide == 1 ? RandLAPACK::BQRRPSubroutines::QRCPWide::geqp3 : RandLAPACK::BQRRPSubroutines::QRCPWide::luqr;
+    alg.qr_tall = qr_tall == 1 ? RandLAPACK::BQRRPSubroutines::QRTall::cholqr
+                : qr_tall == 2 ? RandLAPACK::BQRRPSubroutines::QRTall::geqrt : RandLAPACK::BQRRPSubroutines::QRTall::geqrf;
+    State st = load_state(state);
+    int rc = alg.call(m, n, A, lda, d_factor, tau, J, st);
+    store_state(st, state);
+    *rank = alg.rank;
+    return rc;
+    RL_CATCH
+}
+
 extern "C" {
 
 const char* rlref_last_error(void) { return g_err; }
@@ -251,5 +328,34 @@ int rlref_mat_gen_f32(int type, int64_t m, int64_t n, int64_t rank, float cond, 
                       uint32_t state[6]) {
     return mat_gen_impl<float>(type, m, n, rank, cond, exponent, scaling, A, state);
 }
+
+#define RLREF_TYPED(T, SUF)                                                                                                               \
+    int rlref_fill_sparse_##SUF(int64_t n_rows, int64_t n_cols, int64_t vec_nnz, int major_axis, int64_t sub_rows, int64_t sub_cols,       \
+                                int64_t ro, int64_t co, int64_t* nnz, T* vals, int64_t* rows, int64_t* cols, uint32_t state[6]) {          \
+        return fill_sparse_impl<T>(n_rows, n_cols, vec_nnz, major_axis, sub_rows, sub_cols, ro, co, nnz, vals, rows, cols, state);         \
+    }                                                                                                                                     \
+    int rlref_sketch_sparse_left_##SUF(int64_t S_rows, int64_t S_cols, int64_t vec_nnz, int64_t d, int64_t n, int64_t m, T alpha,          \
+                                       int64_t ro, int64_t co, const T* A, int64_t lda, T beta, T* B, int64_t ldb, uint32_t state[6]) {    \
+        return sketch_sparse_left_impl<T>(S_rows, S_cols, vec_nnz, d, n, m, alpha, ro, co, A, lda, beta, B, ldb, state);                   \
+    }                                                                                                                                     \
+    int rlref_sketch_dense_left_##SUF(int64_t S_rows, int64_t S_cols, int family, int major_axis, int64_t d, int64_t n, int64_t m, T alpha, \
+                                      int64_t ro, int64_t co, const T* A, int64_t lda, T beta, T* B, int64_t ldb, uint32_t state[6]) {     \
+        return sketch_dense_impl<T>(true, S_rows, S_cols, family, major_axis, d, n, m, alpha, ro, co, A, lda, beta, B, ldb, state);        \
+    }                                                                                                                                     \
+    int rlref_sketch_dense_right_##SUF(int64_t S_rows, int64_t S_cols, int family, int major_axis, int64_t m, int64_t d, int64_t n,        \
+                                       T alpha, const T* A, int64_t lda, int64_t ro, int64_t co, T beta, T* B, int64_t ldb,                \
+                                       uint32_t state[6]) {                                                                                \
+        return sketch_dense_impl<T>(false, S_rows, S_cols, family, major_axis, d, n, m, alpha, ro, co, A, lda, beta, B, ldb, state);       \
+    }                                                                                                                                     \
+    int rlref_cqrrpt_##SUF(int64_t m, int64_t n, T* A, int64_t lda, T* R, int64_t ldr, int64_t* J, T d_factor, T eps, int64_t nnz,         \
+                           int qrcp, int64_t* rank, uint32_t state[6]) {                                                                   \
+        return cqrrpt_impl<T>(m, n, A, lda, R, ldr, J, d_factor, eps, nnz, qrcp, rank, state);                                             \
+    }                                                                                                                                     \
+    int rlref_bqrrp_##SUF(int64_t m, int64_t n, T* A, int64_t lda, T d_factor, int64_t b_sz, int qrcp_wide, int qr_tall, T* tau,           \
+                          int64_t* J, int64_t* rank, uint32_t state[6]) {                                                                  \
+        return bqrrp_impl<T>(m, n, A, lda, d_factor, b_sz, qrcp_wide, qr_tall, tau, J, rank, state);                                       \
+    }
+RLREF_TYPED(double, f64)
+RLREF_TYPED(float, f32)
 
 } // extern "C"

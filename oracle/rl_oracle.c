@@ -178,3 +178,66 @@ int rlo_dense_next_state(int64_t n_rows, int64_t n_cols, int major_axis, uint32_
     ctr_incr(state, (uint64_t)(((major + 3) / 4) * minor));
     return 0;
 }
+
+/* ---- SASO sampling (Axis::Short SparseDist) --------------------------------------------------------
+ * Follows RandBLAS/RandBLAS/sparse_skops.hh:55-142 (_considerate_fisher_yates / repeated_fisher_yates: one Philox
+ * call per draw, p = t + s % (dim_major - t), swap on an index array that is restored after every vector; vec_nnz == 1
+ * delegates to sample_indices_iid_uniform, util.hh:520-542, which is the same arithmetic), :568-704
+ * (fill_sparse_unpacked: per-vector insertion sort by the short-axis index, then the sub-block filter) and
+ * :302-312 (next state).  Written with a real index array + undo pass, i.e. differently from the device kernel's
+ * assignment log, so that the two implementations check each other.
+ * major[i], minor[i], sign[i] for i < *nnz_out are relative to the sub-block; state <- counter after the last vector. */
+int rlo_saso_coo(int64_t n_rows, int64_t n_cols, int64_t vec_nnz, int64_t sub_rows, int64_t sub_cols, int64_t ro, int64_t co,
+                 int64_t* nnz_out, int64_t* rows, int64_t* cols, double* vals, uint32_t state[6]) {
+    if (n_rows <= 0 || n_cols <= 0 || vec_nnz <= 0) return -1;
+    const int short_is_rows = n_rows <= n_cols;
+    const int64_t dim_major = short_is_rows ? n_rows : n_cols;
+    if (vec_nnz > dim_major || n_rows < sub_rows + ro || n_cols < sub_cols + co) return -1;
+    const int64_t short_off = short_is_rows ? ro : co, short_sub = short_is_rows ? sub_rows : sub_cols;
+    const int64_t long_off = short_is_rows ? co : ro, long_sub = short_is_rows ? sub_cols : sub_rows;
+    int64_t* idx = (int64_t*)malloc(sizeof(int64_t) * (size_t)dim_major);
+    int64_t* piv = (int64_t*)malloc(sizeof(int64_t) * (size_t)vec_nnz);
+    int64_t* smp = (int64_t*)malloc(sizeof(int64_t) * (size_t)vec_nnz);
+    double* sg = (double*)malloc(sizeof(double) * (size_t)vec_nnz);
+    for (int64_t i = 0; i < dim_major; ++i) idx[i] = i;
+    uint32_t ctr[4]; memcpy(ctr, state, 16);
+    ctr_incr(ctr, (uint64_t)(long_off * vec_nnz));
+    int64_t out = 0;
+    for (int64_t v = 0; v < long_sub; ++v) {
+        for (int64_t t = 0; t < vec_nnz; ++t) {
+            uint32_t rv[4];
+            philox4x32_10(ctr, state + 4, rv);
+            ctr_incr(ctr, 1);
+            uint64_t s = (uint64_t)rv[0] + ((uint64_t)rv[1] << 32);
+            int64_t p = t + (int64_t)(s % (uint64_t)(dim_major - t));
+            piv[t] = p;
+            int64_t tmp = idx[p]; idx[p] = idx[t]; idx[t] = tmp;
+            smp[t] = idx[t];
+            sg[t] = (rv[2] % 2 == 0) ? 1.0 : -1.0;
+        }
+        for (int64_t t = vec_nnz - 1; t >= 0; --t) { int64_t s = smp[t], p = piv[t]; idx[t] = idx[p]; idx[p] = s; }
+        for (int64_t a = 1; a < vec_nnz; ++a) {            /* insertion sort by short-axis index */
+            int64_t key = smp[a]; double kv = sg[a]; int64_t c = a - 1;
+            for (; c >= 0 && smp[c] > key; --c) { smp[c + 1] = smp[c]; sg[c + 1] = sg[c]; }
+            smp[c + 1] = key; sg[c + 1] = kv;
+        }
+        for (int64_t t = 0; t < vec_nnz; ++t) {
+            int64_t mc = smp[t] - short_off;
+            if (mc >= 0 && mc < short_sub) {
+                if (short_is_rows) { rows[out] = mc; cols[out] = v; } else { cols[out] = mc; rows[out] = v; }
+                vals[out] = sg[t];
+                ++out;
+            }
+        }
+    }
+    free(idx); free(piv); free(smp); free(sg);
+    *nnz_out = out;
+    memcpy(state, ctr, 16);
+    return 0;
+}
+
+/* SparseSkOp::next_state = compute_next_state (sparse_skops.hh:302-312), Axis::Short */
+int rlo_saso_next_state(int64_t n_rows, int64_t n_cols, int64_t vec_nnz, uint32_t state[6]) {
+    ctr_incr(state, (uint64_t)((n_rows > n_cols ? n_rows : n_cols) * vec_nnz));
+    return 0;
+}

@@ -402,3 +402,72 @@ def gen_poly_mat(m, n, k, cond, exponent, state, frac_spectrum_one=0.1, dtype=np
     """rl_gen.hh gen_poly_mat (mat_gen case `polynomial`, :720-723) with diag=false."""
     s = gen_poly_singvals(k, frac_spectrum_one, cond, exponent, dtype)
     return gen_singvec(m, n, s, state, dtype)
+
+
+# --------------------------------------------------------------------------------------------
+# RandBLAS sketching operators applied (sparse_skops.hh, skge.hh)
+# --------------------------------------------------------------------------------------------
+def fill_sparse(n_rows, n_cols, vec_nnz, state: RNGState, dtype=np.float64, sub=None):
+    """RandBLAS::fill_sparse_unpacked for SparseDist(n_rows, n_cols, vec_nnz, Axis::Short) (sparse_skops.hh:568-704).
+    -> (nnz, vals, rows, cols, returned RNGState)."""
+    sr, sc, ro, co = sub if sub is not None else (n_rows, n_cols, 0, 0)
+    cap = max(1, vec_nnz * max(sr, sc))
+    rows, cols = np.empty(cap, dtype=np.int64), np.empty(cap, dtype=np.int64)
+    vals = np.empty(cap, dtype=np.float64)
+    nnz = _i64(0)
+    w = state.words()
+    fn = lib().rlo_saso_coo
+    fn.argtypes = [_i64] * 7 + [ctypes.POINTER(_i64), ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.POINTER(_u32)]
+    rc = fn(n_rows, n_cols, vec_nnz, sr, sc, ro, co, ctypes.byref(nnz), rows.ctypes.data, cols.ctypes.data, vals.ctypes.data, w)
+    if rc:
+        raise ValueError("fill_sparse: invalid arguments (randblas_require failed)")
+    k = nnz.value
+    return k, vals[:k].astype(dtype), rows[:k].copy(), cols[:k].copy(), RNGState.from_words(w)
+
+
+def saso_next_state(n_rows, n_cols, vec_nnz, state: RNGState):
+    """SparseSkOp::next_state (sparse_skops.hh:302-312)."""
+    w = state.words()
+    lib().rlo_saso_next_state(_i64(n_rows), _i64(n_cols), _i64(vec_nnz), w)
+    return RNGState.from_words(w)
+
+
+def sketch_sparse_left(S_rows, S_cols, vec_nnz, d, A, state: RNGState, alpha=1.0, beta=0.0, B=None, ro=0, co=0):
+    """sketch_general(ColMajor, NoTrans, NoTrans, d, n, m, alpha, S, ro, co, A, lda, beta, B, ldb), S a wide SASO
+    (skge.hh:538-571; the +-1 entries are NOT scaled by isometry_scale).  -> (B, S.next_state)."""
+    from scipy.sparse import coo_matrix
+    m, n = A.shape
+    k, vals, rows, cols, _ = fill_sparse(S_rows, S_cols, vec_nnz, state, A.dtype, sub=(d, m, ro, co))
+    S = coo_matrix((vals, (rows, cols)), shape=(d, m)).tocsr()
+    out = alpha * (S @ A)
+    if B is not None and beta != 0:
+        out = out + beta * B
+    return _F(out.astype(A.dtype)), saso_next_state(S_rows, S_cols, vec_nnz, state)
+
+
+def dense_next_state(n_rows, n_cols, major_axis, state: RNGState):
+    w = state.words()
+    lib().rlo_dense_next_state(_i64(n_rows), _i64(n_cols), ctypes.c_int(major_axis), w)
+    return RNGState.from_words(w)
+
+
+def sketch_dense_left(S_rows, S_cols, d, A, state: RNGState, family=FAMILY_GAUSSIAN, major_axis=AXIS_LONG, alpha=1.0, beta=0.0,
+                      B=None, ro=0, co=0):
+    """lskge3 (skge.hh:155-203): B = alpha * S[ro:ro+d, co:co+m] A + beta B.  -> (B, S.next_state)."""
+    m, n = A.shape
+    S, _ = fill_dense(S_rows, S_cols, state, A.dtype, family, major_axis, LAYOUT_COLMAJOR, sub=(d, m, ro, co))
+    out = alpha * (S @ A)
+    if B is not None and beta != 0:
+        out = out + beta * B
+    return _F(out), dense_next_state(S_rows, S_cols, major_axis, state)
+
+
+def sketch_dense_right(A, S_rows, S_cols, d, state: RNGState, family=FAMILY_GAUSSIAN, major_axis=AXIS_LONG, alpha=1.0, beta=0.0,
+                       B=None, ro=0, co=0):
+    """rskge3 (skge.hh:308-356): B = alpha * A S[ro:ro+n, co:co+d] + beta B."""
+    m, n = A.shape
+    S, _ = fill_dense(S_rows, S_cols, state, A.dtype, family, major_axis, LAYOUT_COLMAJOR, sub=(n, d, ro, co))
+    out = alpha * (A @ S)
+    if B is not None and beta != 0:
+        out = out + beta * B
+    return _F(out), dense_next_state(S_rows, S_cols, major_axis, state)

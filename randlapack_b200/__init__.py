@@ -18,7 +18,7 @@ from . import _capi
 from ._capi import (STAB_PLUL, STAB_CHOLQRQ, STAB_HQRQ, FAMILY_GAUSSIAN, FAMILY_UNIFORM, AXIS_LONG, AXIS_SHORT,  # noqa: F401
                     LAYOUT_NATURAL, LAYOUT_COLMAJOR, LAYOUT_ROWMAJOR, StackOpts)
 
-__all__ = ["Context", "RNGState", "DenseDist", "fill_dense", "CholQRQ", "PLUL", "HQRQ", "RS", "RF", "QB", "RSVD", "empty_f",
+__all__ = ["Context", "RNGState", "DenseDist", "fill_dense", "SparseDist", "fill_sparse", "sketch_general_left", "sketch_general_right", "CholQRQ", "PLUL", "HQRQ", "RS", "RF", "QB", "RSVD", "empty_f",
            "to_f", "Error", "shard_rows"]
 
 
@@ -230,6 +230,86 @@ def fill_dense(ctx: Context, D: DenseDist, state: RNGState, dtype=None, layout=L
     nxt = RNGState()
     nxt.assign(w)
     return buf[: sub_rows * sub_cols], nxt
+
+
+@dataclass
+class SparseDist:
+    """RandBLAS::SparseDist (RandBLAS/RandBLAS/sparse_skops.hh:167-282); Axis::Short (SASO) is the default and the only axis on device."""
+    n_rows: int
+    n_cols: int
+    vec_nnz: int = 4
+    major_axis: int = AXIS_SHORT
+
+    def __post_init__(self):
+        if self.n_rows <= 0 or self.n_cols <= 0 or self.vec_nnz <= 0:
+            raise Error(_capi.ERR_ARG, "randblas_require(n_rows > 0 && n_cols > 0 && vec_nnz > 0)")
+        mx, mn = max(self.n_rows, self.n_cols), min(self.n_rows, self.n_cols)
+        self.dim_major = mn if self.major_axis == AXIS_SHORT else mx
+        self.dim_minor = self.n_rows + self.n_cols - self.dim_major
+        if self.vec_nnz > self.dim_major:
+            raise Error(_capi.ERR_ARG, "randblas_require(vec_nnz <= dim_major)")
+        self.full_nnz = self.vec_nnz * self.dim_minor
+        self.isometry_scale = self.vec_nnz ** -0.5 if self.major_axis == AXIS_SHORT else \
+            (self.dim_major / (self.vec_nnz * float(self.dim_minor))) ** 0.5
+
+
+def fill_sparse(ctx: Context, D: SparseDist, state: RNGState, dtype=None, sub=None):
+    """RandBLAS::fill_sparse_unpacked (sparse_skops.hh:568-704): -> (nnz, vals, rows, cols [device], returned RNGState)."""
+    torch = _torch()
+    dtype = dtype or torch.float64
+    sub_rows, sub_cols, ro, co = sub if sub is not None else (D.n_rows, D.n_cols, 0, 0)
+    fn = getattr(ctx._lib, f"rlb200_fill_sparse_{_suffix(dtype)}_dev")
+    cap = ctypes.c_int64(0)
+    w = state.words()
+    ctx.check(fn(ctx._h, D.n_rows, D.n_cols, D.vec_nnz, D.major_axis, sub_rows, sub_cols, ro, co, ctypes.byref(cap), None, None, None, w))
+    vals = torch.empty(max(cap.value, 1), dtype=dtype, device=ctx.device)
+    rows = torch.empty(max(cap.value, 1), dtype=torch.int64, device=ctx.device)
+    cols = torch.empty(max(cap.value, 1), dtype=torch.int64, device=ctx.device)
+    nnz = ctypes.c_int64(0)
+    ctx.check(fn(ctx._h, D.n_rows, D.n_cols, D.vec_nnz, D.major_axis, sub_rows, sub_cols, ro, co, ctypes.byref(nnz), vals.data_ptr(),
+                 rows.data_ptr(), cols.data_ptr(), w))
+    nxt = RNGState()
+    nxt.assign(w)
+    return nnz.value, vals[: nnz.value], rows[: nnz.value], cols[: nnz.value], nxt
+
+
+def sketch_general_left(ctx: Context, D, state: RNGState, A, d=None, alpha=1.0, beta=0.0, B=None, ro_s=0, co_s=0):
+    """RandBLAS::sketch_general(ColMajor, NoTrans, NoTrans, d, n, m, alpha, S, ro_s, co_s, A, lda, beta, B, ldb) with
+    S = D.sample(state) regenerated on device (skge.hh:840-1052).  D is a DenseDist or a SparseDist.  `state` <- S.next_state."""
+    m, n = A.shape
+    assert _is_f(A)
+    d = D.n_rows - ro_s if d is None else d
+    if B is None:
+        B = empty_f(d, n, A.dtype, A.device)
+        beta = 0.0
+    w = state.words()
+    if isinstance(D, SparseDist):
+        if D.major_axis != AXIS_SHORT:
+            raise Error(_capi.ERR_UNSUPPORTED, "Axis::Long sparse operators are not offered on the device")
+        fn = getattr(ctx._lib, f"rlb200_sketch_sparse_left_{_suffix(A.dtype)}_dev")
+        ctx.check(fn(ctx._h, D.n_rows, D.n_cols, D.vec_nnz, d, n, m, alpha, ro_s, co_s, A.data_ptr(), _ld(A), beta, B.data_ptr(), _ld(B), w))
+    else:
+        fn = getattr(ctx._lib, f"rlb200_sketch_dense_left_{_suffix(A.dtype)}_dev")
+        ctx.check(fn(ctx._h, D.n_rows, D.n_cols, D.family, D.major_axis, d, n, m, alpha, ro_s, co_s, A.data_ptr(), _ld(A), beta,
+                     B.data_ptr(), _ld(B), w))
+    state.assign(w)
+    return B
+
+
+def sketch_general_right(ctx: Context, A, D: DenseDist, state: RNGState, d=None, alpha=1.0, beta=0.0, B=None, ro_s=0, co_s=0):
+    """sketch_general(ColMajor, NoTrans, NoTrans, m, d, n, alpha, A, lda, S, ro_s, co_s, beta, B, ldb), dense S (rskge3, skge.hh:308-356)."""
+    m, n = A.shape
+    assert _is_f(A)
+    d = D.n_cols - co_s if d is None else d
+    if B is None:
+        B = empty_f(m, d, A.dtype, A.device)
+        beta = 0.0
+    w = state.words()
+    fn = getattr(ctx._lib, f"rlb200_sketch_dense_right_{_suffix(A.dtype)}_dev")
+    ctx.check(fn(ctx._h, D.n_rows, D.n_cols, D.family, D.major_axis, m, d, n, alpha, A.data_ptr(), _ld(A), ro_s, co_s, beta,
+                 B.data_ptr(), _ld(B), w))
+    state.assign(w)
+    return B
 
 
 def philox_stream(ctx: Context, state: RNGState, n: int):

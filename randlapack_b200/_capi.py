@@ -17,7 +17,7 @@ STAB_PLUL, STAB_CHOLQRQ, STAB_HQRQ = 0, 1, 2
 FAMILY_GAUSSIAN, FAMILY_UNIFORM = 0, 1
 AXIS_LONG, AXIS_SHORT = 0, 1
 LAYOUT_NATURAL, LAYOUT_COLMAJOR, LAYOUT_ROWMAJOR = 0, 1, 2
-TIMER_GEMM_NN, TIMER_GEMM_TN, TIMER_RIGHTMUL, TIMER_SMALL, TIMER_FILL = 0, 1, 2, 3, 4
+TIMER_GEMM_NN, TIMER_GEMM_TN, TIMER_RIGHTMUL, TIMER_SMALL, TIMER_FILL, TIMER_SKETCH, TIMER_FACTOR = 0, 1, 2, 3, 4, 5, 6
 
 c_i64, c_i32, c_u32, c_int, c_vp = ctypes.c_int64, ctypes.c_int32, ctypes.c_uint32, ctypes.c_int, ctypes.c_void_p
 P_u32, P_i64, P_int = ctypes.POINTER(c_u32), ctypes.POINTER(c_i64), ctypes.POINTER(c_int)
@@ -41,6 +41,12 @@ _F = lambda ft: {  # noqa: E731  typed entry points, ft = ctypes float type
     "qb": (c_int, [c_vp, c_i64, c_i64, c_vp, P_i64, c_i64, ft, c_vp, c_vp, c_vp, P_u32, ctypes.POINTER(StackOpts)]),
     "rsvd": (c_int, [c_vp, c_i64, c_i64, c_vp, P_i64, ft, c_vp, c_vp, c_vp, c_vp, P_u32, ctypes.POINTER(StackOpts), P_int]),
     "svd_tall": (c_int, [c_vp, c_i64, c_i64, c_vp, c_vp, c_vp]),
+    "fill_sparse": (c_int, [c_vp, c_i64, c_i64, c_i64, c_int, c_i64, c_i64, c_i64, c_i64, P_i64, c_vp, c_vp, c_vp, P_u32]),
+    "sketch_sparse_left": (c_int, [c_vp, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, ft, c_i64, c_i64, c_vp, c_i64, ft, c_vp, c_i64, P_u32]),
+    "sketch_dense_left": (c_int, [c_vp, c_i64, c_i64, c_int, c_int, c_i64, c_i64, c_i64, ft, c_i64, c_i64, c_vp, c_i64, ft, c_vp, c_i64,
+                                  P_u32]),
+    "sketch_dense_right": (c_int, [c_vp, c_i64, c_i64, c_int, c_int, c_i64, c_i64, c_i64, ft, c_vp, c_i64, c_i64, c_i64, ft, c_vp, c_i64,
+                                   P_u32]),
 }
 SIGNATURES = {
     "rlb200_abi_version": (c_int, []),

@@ -133,6 +133,33 @@ int rlb200_philox_stream_dev(rlb200_ctx* ctx, const uint32_t state[6], int64_t n
         CTX_OK(ctx); RLB_CHECK(bind(ctx));                                                                                          \
         return fill_dense_unpacked<T>(ctx, n_rows, n_cols, family, major_axis, layout, sub_rows, sub_cols, ro, co, buff_dev, state); \
     }                                                                                                                               \
+    int rlb200_fill_sparse_##SUF##_dev(rlb200_ctx* ctx, int64_t n_rows, int64_t n_cols, int64_t vec_nnz, int major_axis,            \
+                                       int64_t sub_rows, int64_t sub_cols, int64_t ro, int64_t co, int64_t* nnz_out, T* vals_dev,   \
+                                       int64_t* rows_dev, int64_t* cols_dev, uint32_t state[6]) {                                   \
+        CTX_OK(ctx); RLB_CHECK(bind(ctx)); RLB_REQUIRE(ctx, state);                                                                 \
+        return fill_sparse_unpacked<T>(ctx, n_rows, n_cols, vec_nnz, major_axis, sub_rows, sub_cols, ro, co, nnz_out, vals_dev,     \
+                                       rows_dev, cols_dev, state);                                                                  \
+    }                                                                                                                               \
+    int rlb200_sketch_sparse_left_##SUF##_dev(rlb200_ctx* ctx, int64_t S_rows, int64_t S_cols, int64_t vec_nnz, int64_t d, int64_t n, \
+                                              int64_t m, T alpha, int64_t ro_s, int64_t co_s, const T* A_dev, int64_t lda, T beta,  \
+                                              T* B_dev, int64_t ldb, uint32_t state[6]) {                                           \
+        CTX_OK(ctx); RLB_CHECK(bind(ctx)); RLB_REQUIRE(ctx, state);                                                                 \
+        return sketch_sparse_left<T>(ctx, S_rows, S_cols, vec_nnz, d, n, m, alpha, ro_s, co_s, A_dev, lda, beta, B_dev, ldb, state); \
+    }                                                                                                                               \
+    int rlb200_sketch_dense_left_##SUF##_dev(rlb200_ctx* ctx, int64_t S_rows, int64_t S_cols, int family, int major_axis, int64_t d, \
+                                             int64_t n, int64_t m, T alpha, int64_t ro_s, int64_t co_s, const T* A_dev, int64_t lda, \
+                                             T beta, T* B_dev, int64_t ldb, uint32_t state[6]) {                                    \
+        CTX_OK(ctx); RLB_CHECK(bind(ctx)); RLB_REQUIRE(ctx, state);                                                                 \
+        return sketch_dense_left<T>(ctx, S_rows, S_cols, family, major_axis, d, n, m, alpha, ro_s, co_s, A_dev, lda, beta, B_dev,   \
+                                    ldb, state);                                                                                    \
+    }                                                                                                                               \
+    int rlb200_sketch_dense_right_##SUF##_dev(rlb200_ctx* ctx, int64_t S_rows, int64_t S_cols, int family, int major_axis, int64_t m, \
+                                              int64_t d, int64_t n, T alpha, const T* A_dev, int64_t lda, int64_t ro_s, int64_t co_s, \
+                                              T beta, T* B_dev, int64_t ldb, uint32_t state[6]) {                                   \
+        CTX_OK(ctx); RLB_CHECK(bind(ctx)); RLB_REQUIRE(ctx, state);                                                                 \
+        return sketch_dense_right<T>(ctx, S_rows, S_cols, family, major_axis, m, d, n, alpha, A_dev, lda, ro_s, co_s, beta, B_dev,  \
+                                     ldb, state);                                                                                   \
+    }                                                                                                                               \
     int rlb200_gemm_##SUF##_dev(rlb200_ctx* ctx, int transa, int transb, int64_t m, int64_t n, int64_t k, T alpha, const T* A,      \
                                 int64_t lda, const T* B, int64_t ldb, T beta, T* C, int64_t ldc) {                                  \
         CTX_OK(ctx); RLB_CHECK(bind(ctx));                                                                                          \

@@ -139,6 +139,22 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
 
+// copy a run of `len` (<= E) valid elements (rest zero) of one 16-byte chunk
+template <typename T>
+__device__ __forceinline__ void load_chunk(T* sdst, const T* gsrc, int valid_elems, bool aligned16) {
+    constexpr int E = 16 / sizeof(T);
+    if (aligned16 && (valid_elems >= E || valid_elems <= 0)) {
+        cp_async_16(sdst, gsrc, valid_elems > 0);
+    } else {
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+            bool v = e < valid_elems;
+            if (sizeof(T) == 8) cp_async_8(sdst + e, v ? gsrc + e : gsrc, v);
+            else                cp_async_4(sdst + e, v ? gsrc + e : gsrc, v);
+        }
+    }
+}
+
 // fp64 tensor-core MMA: D(8x8) += A(8x4, row) * B(4x8, col).  Lane l holds
 //   a = A[l/4][l%4], b = B[l%4][l/4], c0/c1 = C[l/4][2*(l%4) + {0,1}].   SASS: DMMA.8x8x4
 __device__ __forceinline__ void dmma_884(double& c0, double& c1, double a, double b) {

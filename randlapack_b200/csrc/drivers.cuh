@@ -37,6 +37,20 @@ int plul(Ctx* ctx, int64_t m, int64_t n, T* A, int64_t lda, void* ws);
 template <typename T>
 int svd_tall(Ctx* ctx, int64_t n, int64_t k, T* B, int64_t ldb, T* S, T* W, void* ws, int* sweeps_out);
 
+// ---- sketch-apply (sketch.cu) -----------------------------------------------------------------------
+template <typename T>
+int fill_sparse_unpacked(Ctx* ctx, int64_t n_rows, int64_t n_cols, int64_t vec_nnz, int major_axis, int64_t sub_rows, int64_t sub_cols,
+                         int64_t ro, int64_t co, int64_t* nnz_out, T* vals, int64_t* rows, int64_t* cols, uint32_t state[6]);
+template <typename T>
+int sketch_sparse_left(Ctx* ctx, int64_t S_rows, int64_t S_cols, int64_t vec_nnz, int64_t d, int64_t n, int64_t m, T alpha, int64_t ro,
+                       int64_t co, const T* A, int64_t lda, T beta, T* B, int64_t ldb, uint32_t state[6]);
+template <typename T>
+int sketch_dense_left(Ctx* ctx, int64_t S_rows, int64_t S_cols, int family, int major_axis, int64_t d, int64_t n, int64_t m, T alpha,
+                      int64_t ro, int64_t co, const T* A, int64_t lda, T beta, T* B, int64_t ldb, uint32_t state[6]);
+template <typename T>
+int sketch_dense_right(Ctx* ctx, int64_t S_rows, int64_t S_cols, int family, int major_axis, int64_t m, int64_t d, int64_t n, T alpha,
+                       const T* A, int64_t lda, int64_t ro, int64_t co, T beta, T* B, int64_t ldb, uint32_t state[6]);
+
 // ---- arena: stack allocator for driver-level device buffers ---------------------------------------
 void* arena_push(Ctx* ctx, size_t bytes);          // nullptr on failure (ctx->err set)
 void arena_release(Ctx* ctx, size_t mark_total);   // pop back to a previous mark

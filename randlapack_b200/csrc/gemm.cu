@@ -20,22 +20,6 @@ template <typename T> struct Pad;
 template <> struct Pad<double> { static constexpr int A = 4, B = 4; };   // strides = 4 (mod 16) 8-byte words
 template <> struct Pad<float>  { static constexpr int A = 8, B = 4; };   // strides = 8 / 4 (mod 32) 4-byte words
 
-// copy a run of `len` (<= E) valid elements (rest zero) of one 16-byte chunk
-template <typename T>
-__device__ __forceinline__ void load_chunk(T* sdst, const T* gsrc, int valid_elems, bool aligned16) {
-    constexpr int E = 16 / sizeof(T);
-    if (aligned16 && (valid_elems >= E || valid_elems <= 0)) {
-        cp_async_16(sdst, gsrc, valid_elems > 0);
-    } else {
-#pragma unroll
-        for (int e = 0; e < E; ++e) {
-            bool v = e < valid_elems;
-            if (sizeof(T) == 8) cp_async_8(sdst + e, v ? gsrc + e : gsrc, v);
-            else                cp_async_4(sdst + e, v ? gsrc + e : gsrc, v);
-        }
-    }
-}
-
 // ------------------------------------------------------------------------------------------------
 // NN
 // ------------------------------------------------------------------------------------------------

@@ -1,0 +1,490 @@
+// RandBLAS sketch-apply on device.
+//
+//   sparse (SASO / count-sketch)   SparseDist + SparseSkOp + fill_sparse(_unpacked)  RandBLAS/RandBLAS/sparse_skops.hh:55-142, 167-312, 568-704
+//                                  sample_indices_iid_uniform                        RandBLAS/RandBLAS/util.hh:520-542
+//                                  lskges -> left_spmm -> apply_csr_jik_p11          RandBLAS/RandBLAS/skge.hh:538-571, sparse_data/csr_spmm_impl.hh:115-153
+//   dense (Gaussian / uniform)     lskge3 / rskge3                                   RandBLAS/RandBLAS/skge.hh:155-203, 308-356
+//
+// Sparse left sketch  B(d x n) = alpha * S(d x m) * A(m x n) + beta * B,  S wide, Axis::Short, vec_nnz non-zeros (+-1) per column.
+// HBM-bound: A is streamed exactly once (sizeof(T)*m*n bytes), the operator costs 2 bytes per non-zero.  No atomics
+// (shared-memory float atomics are CAS loops on sm_100a and L2 reductions run at ~1.3 cycles/lane): instead
+//   1. saso_plan_kernel regenerates the operator from the Philox state, one CTA per chunk of R consecutive columns of S (= rows of A),
+//      and sorts the chunk's non-zeros by (sketch row, source row): a per-chunk CSR (offsets per sketch row + packed local row/sign).
+//   2. saso_apply_kernel: a CTA owns CW columns of A and all d sketch rows; every thread owns RPT sketch rows and keeps its
+//      RPT x CW accumulators in REGISTERS for its whole row range; chunks of A are staged through shared memory with a cp.async
+//      double buffer; a thread walks the CSR lists of its rows and adds the staged values.  Summation order is fixed
+//      (source rows ascending), so the result is run-to-run deterministic.
+//   3. partial sums of the row splits are combined in a fixed order.
+#include "drivers.cuh"
+#include "philox.cuh"
+#include <algorithm>
+
+namespace rlb {
+
+constexpr int kSasoMaxNnz = 64;
+constexpr int kSasoThreads = 512;
+
+// ---- one column of a wide Axis::Short SparseSkOp: the draws of repeated_fisher_yates (sparse_skops.hh:55-142) ----------------------
+// rows[t], neg[t] in draw order, then insertion-sorted by row (sparse_skops.hh:641-668; rows are distinct).
+__device__ void saso_column(const Ctr128& seed, uint32_t k0, uint32_t k1, int64_t j, int nnz, int64_t d, uint32_t* rows, uint8_t* neg) {
+    uint32_t lp[2 * kSasoMaxNnz], lv[2 * kSasoMaxNnz];   // log of assignments to the (virtually identity) index array
+    int nlog = 0;
+    auto get = [&](uint32_t x) {
+        for (int i = nlog - 1; i >= 0; --i) if (lp[i] == x) return lv[i];
+        return x;
+    };
+    for (int t = 0; t < nnz; ++t) {
+        uint32_t rv[4];
+        philox4x32_10(ctr_add(seed, (uint64_t)j * (uint64_t)nnz + (uint64_t)t), k0, k1, rv);
+        const uint64_t s = (uint64_t)rv[0] + ((uint64_t)rv[1] << 32);          // promote_uint_pair (util.hh:516-518)
+        const uint32_t p = (uint32_t)t + (uint32_t)(s % (uint64_t)(d - t));    // sample from {t, ..., d-1}
+        const uint32_t a = get(p), b = get((uint32_t)t);
+        if (nnz > 1) { lp[nlog] = p; lv[nlog] = b; ++nlog; lp[nlog] = (uint32_t)t; lv[nlog] = a; ++nlog; }
+        rows[t] = a;
+        neg[t] = (rv[2] & 1u) ? 1 : 0;                                         // (rv[2] % 2 == 0) ? +1 : -1
+    }
+    for (int a = 1; a < nnz; ++a) {
+        uint32_t key = rows[a]; uint8_t v = neg[a];
+        int c = a - 1;
+        for (; c >= 0 && rows[c] > key; --c) { rows[c + 1] = rows[c]; neg[c + 1] = neg[c]; }
+        rows[c + 1] = key; neg[c + 1] = v;
+    }
+}
+
+// ---- COO export (fill_sparse_unpacked) for parity tests and host callers ---------------------------------------------------------
+// vector i (absolute long-axis index long_off + i) keeps the entries whose short-axis index lies in [short_off, short_off + short_sub)
+__global__ void __launch_bounds__(256) saso_count_kernel(Ctr128 seed, uint32_t k0, uint32_t k1, int64_t long_off, int64_t long_sub, int nnz,
+                                                         int64_t dim_major, int64_t short_off, int64_t short_sub, int* __restrict__ cnt) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < long_sub; i += (int64_t)gridDim.x * blockDim.x) {
+        uint32_t rows[kSasoMaxNnz]; uint8_t neg[kSasoMaxNnz];
+        saso_column(seed, k0, k1, long_off + i, nnz, dim_major, rows, neg);
+        int c = 0;
+        for (int t = 0; t < nnz; ++t) c += ((int64_t)rows[t] >= short_off && (int64_t)rows[t] < short_off + short_sub);
+        cnt[i] = c;
+    }
+}
+// exclusive scan of cnt[0..n) -> pos[0..n], single CTA
+__global__ void __launch_bounds__(1024) scan_int_kernel(const int* __restrict__ cnt, int64_t n, int64_t* __restrict__ pos) {
+    __shared__ int64_t wsum[32];
+    __shared__ int64_t carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (int64_t base = 0; base < n; base += 1024) {
+        const int64_t i = base + threadIdx.x;
+        int64_t v = i < n ? cnt[i] : 0, x = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { int64_t y = __shfl_up_sync(0xffffffffu, x, o); if ((threadIdx.x & 31) >= o) x += y; }
+        if ((threadIdx.x & 31) == 31) wsum[threadIdx.x >> 5] = x;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            int64_t w = wsum[threadIdx.x], xs = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { int64_t y = __shfl_up_sync(0xffffffffu, xs, o); if (threadIdx.x >= o) xs += y; }
+            wsum[threadIdx.x] = xs - w;
+        }
+        __syncthreads();
+        const int64_t excl = carry + wsum[threadIdx.x >> 5] + x - v;
+        if (i < n) pos[i] = excl;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry = excl + v;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) pos[n] = carry;
+}
+template <typename T>
+__global__ void __launch_bounds__(256) saso_coo_kernel(Ctr128 seed, uint32_t k0, uint32_t k1, int64_t long_off, int64_t long_sub, int nnz,
+                                                       int64_t dim_major, int64_t short_off, int64_t short_sub, const int64_t* __restrict__ pos,
+                                                       T* __restrict__ vals, int64_t* __restrict__ idx_major, int64_t* __restrict__ idx_minor) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < long_sub; i += (int64_t)gridDim.x * blockDim.x) {
+        uint32_t rows[kSasoMaxNnz]; uint8_t neg[kSasoMaxNnz];
+        saso_column(seed, k0, k1, long_off + i, nnz, dim_major, rows, neg);
+        int64_t o = pos[i];
+        for (int t = 0; t < nnz; ++t) {
+            const int64_t r = (int64_t)rows[t] - short_off;
+            if (r >= 0 && r < short_sub) { idx_major[o] = r; idx_minor[o] = i; vals[o] = neg[t] ? (T)-1 : (T)1; ++o; }
+        }
+    }
+}
+
+static int saso_check(Ctx* ctx, int64_t n_rows, int64_t n_cols, int64_t vec_nnz, int major_axis) {
+    RLB_REQUIRE(ctx, n_rows > 0);          // sparse_skops.hh:222-225
+    RLB_REQUIRE(ctx, n_cols > 0);
+    RLB_REQUIRE(ctx, vec_nnz > 0);
+    if (major_axis != RLB200_AXIS_SHORT) { ctx->err = "SparseDist with Axis::Long (LASO) is not offered on the device"; return RLB200_ERR_UNSUPPORTED; }
+    RLB_REQUIRE(ctx, vec_nnz <= std::min(n_rows, n_cols));
+    if (vec_nnz > kSasoMaxNnz) { ctx->err = "vec_nnz > 64 is not offered on the device"; return RLB200_ERR_UNSUPPORTED; }
+    RLB_REQUIRE(ctx, std::min(n_rows, n_cols) < (1ll << 31));
+    return 0;
+}
+
+static void saso_next_state(int64_t n_rows, int64_t n_cols, int64_t vec_nnz, uint32_t state[6]) {   // compute_next_state, sparse_skops.hh:302-312
+    Ctr128 c;
+    for (int i = 0; i < 4; ++i) c.v[i] = state[i];
+    c = ctr_add(c, (uint64_t)(std::max(n_rows, n_cols) * vec_nnz));
+    for (int i = 0; i < 4; ++i) state[i] = c.v[i];
+}
+
+template <typename T>
+int fill_sparse_unpacked(Ctx* ctx, int64_t n_rows, int64_t n_cols, int64_t vec_nnz, int major_axis, int64_t sub_rows, int64_t sub_cols,
+                         int64_t ro, int64_t co, int64_t* nnz_out, T* vals, int64_t* rows, int64_t* cols, uint32_t state[6]) {
+    RLB_CHECK(saso_check(ctx, n_rows, n_cols, vec_nnz, major_axis));
+    RLB_REQUIRE(ctx, sub_rows >= 0 && sub_cols >= 0 && ro >= 0 && co >= 0);
+    RLB_REQUIRE(ctx, n_rows >= sub_rows + ro);      // sparse_skops.hh:575-576
+    RLB_REQUIRE(ctx, n_cols >= sub_cols + co);
+    RLB_REQUIRE(ctx, nnz_out != nullptr);
+    const bool short_is_rows = n_rows <= n_cols;
+    const int64_t dim_major = std::min(n_rows, n_cols);
+    const int64_t short_off = short_is_rows ? ro : co, short_sub = short_is_rows ? sub_rows : sub_cols;
+    const int64_t long_off = short_is_rows ? co : ro, long_sub = short_is_rows ? sub_cols : sub_rows;
+    if (!vals || !rows || !cols) { *nnz_out = vec_nnz * long_sub; return 0; }   // size query (:603-606); state untouched
+    Ctr128 seed;
+    for (int i = 0; i < 4; ++i) seed.v[i] = state[i];
+    *nnz_out = 0;
+    if (long_sub > 0) {
+        ArenaScope as(ctx);
+        int* cnt = as.take<int>(long_sub); if (!cnt) return RLB200_ERR_ALLOC;
+        int64_t* pos = as.take<int64_t>(long_sub + 1); if (!pos) return RLB200_ERR_ALLOC;
+        const int nb = (int)std::min<int64_t>((long_sub + 255) / 256, (int64_t)ctx->num_sms * 16);
+        LaunchScope ls(ctx, RLB200_TIMER_FILL, 3);
+        saso_count_kernel<<<nb, 256, 0, ctx->stream>>>(seed, state[4], state[5], long_off, long_sub, (int)vec_nnz, dim_major, short_off, short_sub, cnt);
+        scan_int_kernel<<<1, 1024, 0, ctx->stream>>>(cnt, long_sub, pos);
+        saso_coo_kernel<T><<<nb, 256, 0, ctx->stream>>>(seed, state[4], state[5], long_off, long_sub, (int)vec_nnz, dim_major, short_off, short_sub, pos,
+                                                        vals, short_is_rows ? rows : cols, short_is_rows ? cols : rows);
+        RLB_CUDA_OK(ctx, cudaGetLastError());
+        RLB_CUDA_OK(ctx, cudaMemcpyAsync(ctx->hbox, pos + long_sub, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+        RLB_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+        *nnz_out = *static_cast<int64_t*>(ctx->hbox);
+    }
+    // returned state = counter after the last sampled vector (sparse_skops.hh:613-614, 139)
+    Ctr128 nx = ctr_add(seed, (uint64_t)((long_off + long_sub) * vec_nnz));
+    for (int i = 0; i < 4; ++i) state[i] = nx.v[i];
+    return 0;
+}
+template int fill_sparse_unpacked<double>(Ctx*, int64_t, int64_t, int64_t, int, int64_t, int64_t, int64_t, int64_t, int64_t*, double*, int64_t*, int64_t*, uint32_t*);
+template int fill_sparse_unpacked<float>(Ctx*, int64_t, int64_t, int64_t, int, int64_t, int64_t, int64_t, int64_t, int64_t*, float*, int64_t*, int64_t*, uint32_t*);
+
+// ---- plan: per-chunk CSR of the operator ----------------------------------------------------------------------------------------------
+// chunk q covers columns [q*R, (q+1)*R) of the sub-operator (absolute column col0 + q*R + jl).
+// key = (sketch row - ro) << 12 | jl << 1 | neg ; invalid = 0xFFFFFFFF.  ent[q*E + i] = key & 0xFFF, off[q*(d_pad+1) + r] = #keys < r<<12.
+__global__ void __launch_bounds__(256) saso_plan_kernel(Ctr128 seed, uint32_t k0, uint32_t k1, int64_t col0, int64_t m_sub, int64_t d_full,
+                                                        int64_t ro, int d_sub, int nnz, int R, int E2, int d_pad,
+                                                        uint16_t* __restrict__ ent, uint16_t* __restrict__ off) {
+    extern __shared__ uint32_t keys[];
+    const int q = blockIdx.x;
+    const int E = R * nnz;
+    for (int i = E + threadIdx.x; i < E2; i += blockDim.x) keys[i] = 0xFFFFFFFFu;
+    for (int jl = threadIdx.x; jl < R; jl += blockDim.x) {
+        const int64_t j = (int64_t)q * R + jl;
+        uint32_t rows[kSasoMaxNnz]; uint8_t neg[kSasoMaxNnz];
+        if (j < m_sub) saso_column(seed, k0, k1, col0 + j, nnz, d_full, rows, neg);
+        for (int t = 0; t < nnz; ++t) {
+            uint32_t key = 0xFFFFFFFFu;
+            if (j < m_sub) {
+                const int64_t r = (int64_t)rows[t] - ro;
+                if (r >= 0 && r < d_sub) key = ((uint32_t)r << 12) | ((uint32_t)jl << 1) | neg[t];
+            }
+            keys[jl * nnz + t] = key;
+        }
+    }
+    __syncthreads();
+    // bitonic sort of E2 (power of two) keys
+    for (int k = 2; k <= E2; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = threadIdx.x; i < E2; i += blockDim.x) {
+                const int l = i ^ j;
+                if (l > i) {
+                    const uint32_t a = keys[i], b = keys[l];
+                    const bool up = (i & k) == 0;
+                    if ((a > b) == up) { keys[i] = b; keys[l] = a; }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    for (int i = threadIdx.x; i < E; i += blockDim.x) ent[(int64_t)q * E + i] = (uint16_t)(keys[i] & 0xFFFu);
+    for (int r = threadIdx.x; r <= d_pad; r += blockDim.x) {
+        const uint32_t bound = (r >= d_sub) ? 0xFFFFFFFFu : ((uint32_t)r << 12);
+        int lo = 0, hi = E2;   // first index with key >= bound
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if (keys[mid] < bound) lo = mid + 1; else hi = mid; }
+        off[(int64_t)q * (d_pad + 1) + r] = (uint16_t)lo;
+    }
+}
+
+// ---- apply ------------------------------------------------------------------------------------------------------------------------------
+template <typename T, int RPT, int CW>
+__global__ void __launch_bounds__(kSasoThreads, 1)
+saso_apply_kernel(const T* __restrict__ A, int64_t lda, int64_t m, int n, int d_sub, int R, int E, int nchunks, int chunks_per_split,
+                  const uint16_t* __restrict__ ent, const uint16_t* __restrict__ off, T* __restrict__ partial, int a_al16) {
+    constexpr int EV = 16 / sizeof(T);
+    constexpr int d_pad = kSasoThreads * RPT;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T* tile = reinterpret_cast<T*>(smem_raw);
+    const int RP = R + EV;                       // row pitch of one staged column (keeps 16-byte alignment, shifts banks)
+    const int tid = threadIdx.x;
+    const int c0 = blockIdx.x * CW;
+    const int split = blockIdx.y;
+    const int q0 = split * chunks_per_split, q1 = min(nchunks, q0 + chunks_per_split);
+
+    auto stage = [&](int buf, int q) {
+        T* t = tile + (size_t)buf * CW * RP;
+        const int64_t J0 = (int64_t)q * R;
+        const int per_col = R / EV;
+        for (int i = tid; i < CW * per_col; i += kSasoThreads) {
+            const int c = i / per_col, jl = (i - c * per_col) * EV;
+            int valid = (c0 + c < n) ? (int)max((int64_t)0, min((int64_t)EV, m - (J0 + jl))) : 0;
+            const T* src = A + (J0 + jl) + (int64_t)(c0 + c) * lda;
+            load_chunk<T>(t + c * RP + jl, valid > 0 ? src : A, valid, a_al16);
+        }
+    };
+
+    T acc[RPT][CW];
+#pragma unroll
+    for (int i = 0; i < RPT; ++i)
+#pragma unroll
+        for (int c = 0; c < CW; ++c) acc[i][c] = (T)0;
+
+    if (q0 < q1) stage(0, q0);
+    cp_async_commit();
+    for (int q = q0; q < q1; ++q) {
+        const int buf = (q - q0) & 1;
+        if (q + 1 < q1) stage(buf ^ 1, q + 1);
+        cp_async_commit();
+        // this thread's CSR offsets (global/L2; contiguous across the CTA)
+        const uint16_t* op = off + (int64_t)q * (d_pad + 1) + tid * RPT;
+        int o[RPT + 1];
+#pragma unroll
+        for (int i = 0; i <= RPT; ++i) o[i] = op[i];
+        cp_async_wait<1>();
+        __syncthreads();
+        const T* t = tile + (size_t)buf * CW * RP;
+        const uint16_t* ep = ent + (int64_t)q * E;
+#pragma unroll
+        for (int i = 0; i < RPT; ++i) {
+            for (int e = o[i]; e < o[i + 1]; ++e) {
+                const uint32_t w = ep[e];
+                const int jl = w >> 1;
+                const bool ng = w & 1u;
+#pragma unroll
+                for (int c = 0; c < CW; ++c) {
+                    const T v = t[c * RP + jl];
+                    acc[i][c] += ng ? -v : v;
+                }
+            }
+        }
+        __syncthreads();   // everyone is done with `buf` before it is refilled two iterations later
+    }
+    cp_async_wait<0>();
+    T* P = partial + (int64_t)split * d_sub * n;
+#pragma unroll
+    for (int c = 0; c < CW; ++c) {
+        if (c0 + c >= n) continue;
+#pragma unroll
+        for (int i = 0; i < RPT; ++i) {
+            const int r = tid * RPT + i;
+            if (r < d_sub) P[r + (int64_t)(c0 + c) * d_sub] = acc[i][c];
+        }
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) saso_reduce_kernel(const T* __restrict__ partial, int splits, int d, int n, T alpha, T beta, T* __restrict__ B, int64_t ldb) {
+    const int64_t total = (int64_t)d * n;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        T s = (T)0;
+        for (int p = 0; p < splits; ++p) s += partial[(int64_t)p * total + e];
+        T* b = B + (e % d) + (e / d) * ldb;
+        T v = alpha * s;
+        if (beta != (T)0) v += beta * (*b);
+        *b = v;
+    }
+}
+
+template <typename T, int RPT, int CW>
+static int saso_apply_launch(Ctx* ctx, const T* A, int64_t lda, int64_t m, int n, int d_sub, int R, int E, int nchunks, const uint16_t* ent,
+                             const uint16_t* off, T alpha, T beta, T* B, int64_t ldb) {
+    constexpr int EV = 16 / sizeof(T);
+    const int tiles = (n + CW - 1) / CW;
+    int splits = (int)std::max<int64_t>(1, std::min<int64_t>(nchunks, (4ll * ctx->num_sms + tiles - 1) / tiles));
+    const int cps = (nchunks + splits - 1) / splits;
+    splits = (nchunks + cps - 1) / cps;
+    ArenaScope as(ctx);
+    T* partial = as.take<T>((size_t)splits * d_sub * n); if (!partial) return RLB200_ERR_ALLOC;
+    const size_t smem = (size_t)2 * CW * (R + EV) * sizeof(T);
+    auto kern = saso_apply_kernel<T, RPT, CW>;
+    RLB_CUDA_OK(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int al = (reinterpret_cast<uintptr_t>(A) % 16 == 0) && (lda % EV == 0);
+    LaunchScope ls(ctx, RLB200_TIMER_SKETCH, 2);
+    kern<<<dim3(tiles, splits), kSasoThreads, smem, ctx->stream>>>(A, lda, m, n, d_sub, R, E, nchunks, cps, ent, off, partial, al);
+    const int64_t total = (int64_t)d_sub * n;
+    saso_reduce_kernel<T><<<(unsigned)std::min<int64_t>((total + 255) / 256, (int64_t)ctx->num_sms * 8), 256, 0, ctx->stream>>>(partial, splits, d_sub, n, alpha, beta, B, ldb);
+    RLB_CUDA_OK(ctx, cudaGetLastError());
+    return 0;
+}
+
+// B(d x n) = alpha * S[ro:ro+d, co:co+m] * A(m x n) + beta * B ; S ~ SparseDist(S_rows, S_cols, vec_nnz, Axis::Short) sampled at `state`.
+// With a row shard set on the context, A holds rows [row_offset, row_offset + m) of the global matrix: the matching columns of S
+// are used and B is sum-allreduced (beta is applied by the shard that owns row 0).  state <- S.next_state.
+template <typename T>
+int sketch_sparse_left(Ctx* ctx, int64_t S_rows, int64_t S_cols, int64_t vec_nnz, int64_t d, int64_t n, int64_t m, T alpha, int64_t ro,
+                       int64_t co, const T* A, int64_t lda, T beta, T* B, int64_t ldb, uint32_t state[6]) {
+    RLB_CHECK(saso_check(ctx, S_rows, S_cols, vec_nnz, RLB200_AXIS_SHORT));
+    RLB_REQUIRE(ctx, d >= 0 && n >= 0 && m >= 0 && ro >= 0 && co >= 0);
+    const bool sharded = ctx->m_global >= 0;
+    const int64_t shard_off = sharded ? ctx->row_offset : 0;
+    RLB_REQUIRE(ctx, S_rows >= d + ro);                                   // submatrix bounds (skge.hh / sparse_skops.hh:575-576)
+    RLB_REQUIRE(ctx, S_cols >= (sharded ? ctx->m_global : m) + co);
+    RLB_REQUIRE(ctx, lda >= m && ldb >= d);
+    if (S_rows > S_cols) { ctx->err = "left sparse sketch with a tall operator is not offered on the device"; return RLB200_ERR_UNSUPPORTED; }
+    if (d > kSasoThreads * 32) { ctx->err = "sketch dimension d > 16384 is not offered by the sparse sketch kernel"; return RLB200_ERR_UNSUPPORTED; }
+    RLB_REQUIRE(ctx, n < (1ll << 31));
+    Ctr128 seed;
+    for (int i = 0; i < 4; ++i) seed.v[i] = state[i];
+    if (d > 0 && n > 0) {
+        if (m == 0) {
+            // B <- beta * B
+            const T bz = (sharded && shard_off != 0) ? (T)0 : beta;
+            LaunchScope ls(ctx, RLB200_TIMER_SKETCH);
+            saso_reduce_kernel<T><<<(unsigned)std::min<int64_t>((d * n + 255) / 256, 1184), 256, 0, ctx->stream>>>(B, 0, (int)d, (int)n, (T)0, bz, B, ldb);
+            RLB_CUDA_OK(ctx, cudaGetLastError());
+        } else {
+            int R = 2048;
+            while (R > 256 && (int64_t)R * vec_nnz > 16384) R >>= 1;
+            const int E = R * (int)vec_nnz;
+            int E2 = 1; while (E2 < E) E2 <<= 1;
+            const int nchunks = (int)((m + R - 1) / R);
+            const int rpt = d <= 512 ? 1 : d <= 1024 ? 2 : d <= 4096 ? 8 : 32;
+            const int d_pad = kSasoThreads * rpt;
+            ArenaScope as(ctx);
+            uint16_t* ent = as.take<uint16_t>((size_t)nchunks * E); if (!ent) return RLB200_ERR_ALLOC;
+            uint16_t* off = as.take<uint16_t>((size_t)nchunks * (d_pad + 1)); if (!off) return RLB200_ERR_ALLOC;
+            {
+                RLB_CUDA_OK(ctx, cudaFuncSetAttribute(saso_plan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, E2 * 4));
+                LaunchScope ls(ctx, RLB200_TIMER_SKETCH);
+                saso_plan_kernel<<<nchunks, 256, E2 * 4, ctx->stream>>>(seed, state[4], state[5], co + shard_off, m, S_rows, ro, (int)d, (int)vec_nnz, R,
+                                                                        E2, d_pad, ent, off);
+                RLB_CUDA_OK(ctx, cudaGetLastError());
+            }
+            const T beta_eff = (sharded && shard_off != 0) ? (T)0 : beta;
+            int rc;
+            if (sizeof(T) == 4) {
+                if (rpt == 1)      rc = saso_apply_launch<T, 1, 8>(ctx, A, lda, m, (int)n, (int)d, R, E, nchunks, ent, off, alpha, beta_eff, B, ldb);
+                else if (rpt == 2) rc = saso_apply_launch<T, 2, 8>(ctx, A, lda, m, (int)n, (int)d, R, E, nchunks, ent, off, alpha, beta_eff, B, ldb);
+                else if (rpt == 8) rc = saso_apply_launch<T, 8, 8>(ctx, A, lda, m, (int)n, (int)d, R, E, nchunks, ent, off, alpha, beta_eff, B, ldb);
+                else               rc = saso_apply_launch<T, 32, 2>(ctx, A, lda, m, (int)n, (int)d, R, E, nchunks, ent, off, alpha, beta_eff, B, ldb);
+            } else {
+                if (rpt == 1)      rc = saso_apply_launch<T, 1, 4>(ctx, A, lda, m, (int)n, (int)d, R, E, nchunks, ent, off, alpha, beta_eff, B, ldb);
+                else if (rpt == 2) rc = saso_apply_launch<T, 2, 4>(ctx, A, lda, m, (int)n, (int)d, R, E, nchunks, ent, off, alpha, beta_eff, B, ldb);
+                else if (rpt == 8) rc = saso_apply_launch<T, 8, 4>(ctx, A, lda, m, (int)n, (int)d, R, E, nchunks, ent, off, alpha, beta_eff, B, ldb);
+                else               rc = saso_apply_launch<T, 32, 1>(ctx, A, lda, m, (int)n, (int)d, R, E, nchunks, ent, off, alpha, beta_eff, B, ldb);
+            }
+            RLB_CHECK(rc);
+        }
+        if (sharded && ctx->allreduce) {
+            if (ldb == d) {
+                int rc = ctx->allreduce(ctx->allreduce_user, B, d * n, (int32_t)sizeof(T), ctx->stream);
+                if (rc != 0) { ctx->err = "allreduce hook failed with code " + std::to_string(rc); return RLB200_ERR_COLLECTIVE; }
+            } else {
+                for (int64_t c = 0; c < n; ++c) {
+                    int rc = ctx->allreduce(ctx->allreduce_user, B + c * ldb, d, (int32_t)sizeof(T), ctx->stream);
+                    if (rc != 0) { ctx->err = "allreduce hook failed with code " + std::to_string(rc); return RLB200_ERR_COLLECTIVE; }
+                }
+            }
+        }
+    }
+    saso_next_state(S_rows, S_cols, vec_nnz, state);
+    return 0;
+}
+template int sketch_sparse_left<double>(Ctx*, int64_t, int64_t, int64_t, int64_t, int64_t, int64_t, double, int64_t, int64_t, const double*, int64_t, double, double*, int64_t, uint32_t*);
+template int sketch_sparse_left<float>(Ctx*, int64_t, int64_t, int64_t, int64_t, int64_t, int64_t, float, int64_t, int64_t, const float*, int64_t, float, float*, int64_t, uint32_t*);
+
+// ---- dense sketches -----------------------------------------------------------------------------------------------------------------------
+// The operator is never materialised in HBM as a whole: column panels of S (left) / row panels (right) of at most `panel_bytes` are
+// regenerated from the Philox state into a small ring buffer that stays L2-resident and are consumed at once by the tensor-pipe GEMM.
+//
+// left  (lskge3, skge.hh:155-203):  B(d x n) = alpha * S[ro:ro+d, co:co+m] * A(m x n) + beta * B
+// right (rskge3, skge.hh:308-356):  B(m x d) = alpha * A(m x n) * S[ro:ro+n, co:co+d] + beta * B
+// S ~ DenseDist(S_rows, S_cols, family, major_axis) sampled at `state`; state <- the full operator's next_state
+// (DenseSkOp's constructor, dense_skops.hh:405-417).
+static void dense_next_state_axis(int64_t n_rows, int64_t n_cols, int major_axis, uint32_t state[6]) {   // dense_skops.hh:169-182
+    const int64_t mx = std::max(n_rows, n_cols), mn = std::min(n_rows, n_cols);
+    const int64_t major = major_axis == RLB200_AXIS_LONG ? mx : mn, minor = major_axis == RLB200_AXIS_LONG ? mn : mx;
+    Ctr128 c;
+    for (int i = 0; i < 4; ++i) c.v[i] = state[i];
+    c = ctr_add(c, (uint64_t)(((major + 3) / 4) * minor));
+    for (int i = 0; i < 4; ++i) state[i] = c.v[i];
+}
+
+constexpr size_t kDensePanelBytes = (size_t)32 << 20;
+
+template <typename T>
+int sketch_dense_left(Ctx* ctx, int64_t S_rows, int64_t S_cols, int family, int major_axis, int64_t d, int64_t n, int64_t m, T alpha,
+                      int64_t ro, int64_t co, const T* A, int64_t lda, T beta, T* B, int64_t ldb, uint32_t state[6]) {
+    RLB_REQUIRE(ctx, S_rows > 0 && S_cols > 0 && d >= 0 && n >= 0 && m >= 0 && ro >= 0 && co >= 0);
+    const bool sharded = ctx->m_global >= 0;
+    const int64_t shard_off = sharded ? ctx->row_offset : 0;
+    RLB_REQUIRE(ctx, S_rows >= d + ro);
+    RLB_REQUIRE(ctx, S_cols >= (sharded ? ctx->m_global : m) + co);
+    RLB_REQUIRE(ctx, lda >= m && ldb >= d);
+    if (d > 0 && n > 0) {
+        const T beta0 = (sharded && shard_off != 0) ? (T)0 : beta;
+        int64_t pc = std::max<int64_t>(64, (int64_t)(kDensePanelBytes / sizeof(T)) / std::max<int64_t>(d, 1));
+        pc = std::min<int64_t>((pc / 64) * 64, std::max<int64_t>(m, 1));
+        ArenaScope as(ctx);
+        T* panel = as.take<T>((size_t)2 * d * pc); if (!panel) return RLB200_ERR_ALLOC;
+        if (m == 0) RLB_CHECK(gemm_nn<T>(ctx, d, n, 0, 0.0, panel, d, A, lda, (double)beta0, B, ldb));
+        int buf = 0;
+        for (int64_t j0 = 0; j0 < m; j0 += pc, buf ^= 1) {
+            const int64_t w = std::min(pc, m - j0);
+            T* P = panel + (size_t)buf * d * pc;
+            uint32_t st[6];
+            std::memcpy(st, state, sizeof st);
+            // the d x w block of S at (ro, co + shard_off + j0), column-major with ld = d
+            RLB_CHECK(fill_dense_unpacked<T>(ctx, S_rows, S_cols, family, major_axis, RLB200_LAYOUT_COLMAJOR, d, w, ro, co + shard_off + j0, P, st));
+            RLB_CHECK(gemm_nn<T>(ctx, d, n, w, (double)alpha, P, d, A + j0, lda, j0 == 0 ? (double)beta0 : 1.0, B, ldb));
+        }
+        if (sharded && ctx->allreduce) {
+            for (int64_t c = 0; c < (ldb == d ? 1 : n); ++c) {
+                int rc = ctx->allreduce(ctx->allreduce_user, B + c * ldb, ldb == d ? d * n : d, (int32_t)sizeof(T), ctx->stream);
+                if (rc != 0) { ctx->err = "allreduce hook failed with code " + std::to_string(rc); return RLB200_ERR_COLLECTIVE; }
+            }
+        }
+    }
+    dense_next_state_axis(S_rows, S_cols, major_axis, state);
+    return 0;
+}
+
+template <typename T>
+int sketch_dense_right(Ctx* ctx, int64_t S_rows, int64_t S_cols, int family, int major_axis, int64_t m, int64_t d, int64_t n, T alpha,
+                       const T* A, int64_t lda, int64_t ro, int64_t co, T beta, T* B, int64_t ldb, uint32_t state[6]) {
+    RLB_REQUIRE(ctx, S_rows > 0 && S_cols > 0 && d >= 0 && n >= 0 && m >= 0 && ro >= 0 && co >= 0);
+    RLB_REQUIRE(ctx, S_rows >= n + ro);
+    RLB_REQUIRE(ctx, S_cols >= d + co);
+    RLB_REQUIRE(ctx, lda >= m && ldb >= m);
+    if (m > 0 && d > 0) {
+        int64_t pr = std::max<int64_t>(64, (int64_t)(kDensePanelBytes / sizeof(T)) / std::max<int64_t>(d, 1));
+        pr = std::min<int64_t>((pr / 64) * 64, std::max<int64_t>(n, 1));
+        ArenaScope as(ctx);
+        T* panel = as.take<T>((size_t)2 * d * pr); if (!panel) return RLB200_ERR_ALLOC;
+        if (n == 0) RLB_CHECK(gemm_nn<T>(ctx, m, d, 0, 0.0, A, lda, panel, 1, (double)beta, B, ldb));
+        int buf = 0;
+        for (int64_t i0 = 0; i0 < n; i0 += pr, buf ^= 1) {
+            const int64_t h = std::min(pr, n - i0);
+            T* P = panel + (size_t)buf * d * pr;
+            uint32_t st[6];
+            std::memcpy(st, state, sizeof st);
+            // the h x d block of S at (ro + i0, co), column-major with ld = h
+            RLB_CHECK(fill_dense_unpacked<T>(ctx, S_rows, S_cols, family, major_axis, RLB200_LAYOUT_COLMAJOR, h, d, ro + i0, co, P, st));
+            RLB_CHECK(gemm_nn<T>(ctx, m, d, h, (double)alpha, A + i0 * lda, lda, P, h, i0 == 0 ? (double)beta : 1.0, B, ldb));
+        }
+    }
+    dense_next_state_axis(S_rows, S_cols, major_axis, state);
+    return 0;
+}
+
+#define INST(T)                                                                                                                                  \
+    template int sketch_dense_left<T>(Ctx*, int64_t, int64_t, int, int, int64_t, int64_t, int64_t, T, int64_t, int64_t, const T*, int64_t, T, T*, int64_t, uint32_t*); \
+    template int sketch_dense_right<T>(Ctx*, int64_t, int64_t, int, int, int64_t, int64_t, int64_t, T, const T*, int64_t, int64_t, int64_t, T, T*, int64_t, uint32_t*);
+INST(double)
+INST(float)
+
+}  // namespace rlb

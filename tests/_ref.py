@@ -74,3 +74,97 @@ def subspace_sin(Q1, Q2):
     """sin of the largest principal angle between range(Q1) and range(Q2) (orthonormal columns)."""
     M = Q2 - Q1 @ (Q1.T @ Q2)
     return np.linalg.norm(M, 2)
+
+
+def _ft(dt):
+    return ctypes.c_double if dt == np.float64 else ctypes.c_float
+
+
+def _suf(dt):
+    return "f64" if dt == np.float64 else "f32"
+
+
+def ref_fill_sparse(lib, n_rows, n_cols, vec_nnz, seed6, dtype=np.float64, axis=1, sub=None, prefix="rlref"):
+    """RandBLAS::fill_sparse_unpacked via the compiled reference -> (rc, nnz, vals, rows, cols, returned state)."""
+    sr, sc, ro, co = sub if sub else (n_rows, n_cols, 0, 0)
+    cap = vec_nnz * max(n_rows, n_cols)
+    vals = np.zeros(cap, dtype=dtype)
+    rows = np.full(cap, -1, dtype=np.int64)
+    cols = np.full(cap, -1, dtype=np.int64)
+    nnz = i64(0)
+    st = (u32 * 6)(*seed6)
+    f = getattr(lib, f"{prefix}_fill_sparse_{_suf(dtype)}")
+    f.argtypes = [i64, i64, i64, ctypes.c_int, i64, i64, i64, i64, ctypes.POINTER(i64), ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                  ctypes.POINTER(u32)]
+    rc = f(n_rows, n_cols, vec_nnz, axis, sr, sc, ro, co, ctypes.byref(nnz), vals.ctypes.data, rows.ctypes.data, cols.ctypes.data, st)
+    k = nnz.value
+    return rc, k, vals[:k], rows[:k], cols[:k], list(st)
+
+
+def ref_sketch_sparse_left(lib, S_rows, S_cols, vec_nnz, d, A, seed6, alpha=1.0, beta=0.0, B=None, ro=0, co=0):
+    m, n = A.shape
+    dt = A.dtype
+    A = np.asfortranarray(A)
+    B = np.zeros((d, n), dtype=dt, order="F") if B is None else np.asfortranarray(B.copy())
+    st = (u32 * 6)(*seed6)
+    f = getattr(lib, f"rlref_sketch_sparse_left_{_suf(dt)}")
+    ft = _ft(dt)
+    f.argtypes = [i64, i64, i64, i64, i64, i64, ft, i64, i64, ctypes.c_void_p, i64, ft, ctypes.c_void_p, i64, ctypes.POINTER(u32)]
+    rc = f(S_rows, S_cols, vec_nnz, d, n, m, alpha, ro, co, A.ctypes.data, m, beta, B.ctypes.data, d, st)
+    return rc, B, list(st)
+
+
+def ref_sketch_dense(lib, left, S_rows, S_cols, d, A, seed6, family=0, axis=0, alpha=1.0, beta=0.0, B=None, ro=0, co=0):
+    """left: B(d x n) = alpha S A + beta B with A m x n; right: B(m x d) = alpha A S + beta B."""
+    m, n = A.shape
+    dt = A.dtype
+    A = np.asfortranarray(A)
+    shape = (d, n) if left else (m, d)
+    B = np.zeros(shape, dtype=dt, order="F") if B is None else np.asfortranarray(B.copy())
+    st = (u32 * 6)(*seed6)
+    ft = _ft(dt)
+    if left:
+        f = getattr(lib, f"rlref_sketch_dense_left_{_suf(dt)}")
+        f.argtypes = [i64, i64, ctypes.c_int, ctypes.c_int, i64, i64, i64, ft, i64, i64, ctypes.c_void_p, i64, ft, ctypes.c_void_p, i64,
+                      ctypes.POINTER(u32)]
+        rc = f(S_rows, S_cols, family, axis, d, n, m, alpha, ro, co, A.ctypes.data, m, beta, B.ctypes.data, d, st)
+    else:
+        f = getattr(lib, f"rlref_sketch_dense_right_{_suf(dt)}")
+        f.argtypes = [i64, i64, ctypes.c_int, ctypes.c_int, i64, i64, i64, ft, ctypes.c_void_p, i64, i64, i64, ft, ctypes.c_void_p, i64,
+                      ctypes.POINTER(u32)]
+        rc = f(S_rows, S_cols, family, axis, m, d, n, alpha, A.ctypes.data, m, ro, co, beta, B.ctypes.data, m, st)
+    return rc, B, list(st)
+
+
+def ref_cqrrpt(lib, A, d_factor, seed6, eps=None, nnz=2, qrcp=0):
+    """RandLAPACK::CQRRPT::call via the compiled reference -> (rc, rank, Q m x n [first rank cols valid], R n x n, J, state)."""
+    m, n = A.shape
+    dt = A.dtype
+    Q = np.asfortranarray(A.copy())
+    R = np.zeros((n, n), dtype=dt, order="F")
+    J = np.zeros(n, dtype=np.int64)
+    rank = i64(0)
+    st = (u32 * 6)(*seed6)
+    ft = _ft(dt)
+    eps = float(np.finfo(dt).eps) ** 0.85 if eps is None else eps
+    f = getattr(lib, f"rlref_cqrrpt_{_suf(dt)}")
+    f.argtypes = [i64, i64, ctypes.c_void_p, i64, ctypes.c_void_p, i64, ctypes.c_void_p, ft, ft, i64, ctypes.c_int, ctypes.POINTER(i64),
+                  ctypes.POINTER(u32)]
+    rc = f(m, n, Q.ctypes.data, m, R.ctypes.data, n, J.ctypes.data, d_factor, eps, nnz, qrcp, ctypes.byref(rank), st)
+    return rc, rank.value, Q, R, J, list(st)
+
+
+def ref_bqrrp(lib, A, d_factor, b_sz, seed6, qrcp_wide=0, qr_tall=0):
+    """RandLAPACK::BQRRP::call via the compiled reference -> (rc, rank, A_out [GEQP3 format], tau, J, state)."""
+    m, n = A.shape
+    dt = A.dtype
+    F = np.asfortranarray(A.copy())
+    tau = np.zeros(n, dtype=dt)
+    J = np.zeros(n, dtype=np.int64)
+    rank = i64(0)
+    st = (u32 * 6)(*seed6)
+    f = getattr(lib, f"rlref_bqrrp_{_suf(dt)}")
+    f.argtypes = [i64, i64, ctypes.c_void_p, i64, _ft(dt), i64, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p,
+                  ctypes.POINTER(i64), ctypes.POINTER(u32)]
+    rc = f(m, n, F.ctypes.data, m, d_factor, b_sz, qrcp_wide, qr_tall, tau.ctypes.data, J.ctypes.data, ctypes.byref(rank), st)
+    return rc, rank.value, F, tau, J, list(st)

@@ -1,0 +1,168 @@
+"""GPU parity, RandBLAS sketch-apply through the C-ABI.
+
+Tolerances (stated):
+ * SparseSkOp triplets (rows, cols, +-1 values) and RNG-state advancement are integer work: bit-exact against the oracle and
+   against the reference-generated golden vectors.
+ * Applied sparse sketch: sums of +-A entries; the device adds in ascending source-row order, the reference in a reassociated
+   (OpenMP simd) order, so B is compared to 50 eps * (largest magnitude a sum of its length can reach).
+ * Dense sketch: the device's Gaussian entries are within a few float ulps of the host libm's (tests/test_gpu_fill.py), so against
+   the oracle/golden B is compared to 2e-6 relative (Frobenius); against a product with the DEVICE-generated operator to 1e-12."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import randlapack_b200 as rl
+from oracle import rl_oracle as O
+
+pytestmark = pytest.mark.gpu
+G = np.load(os.path.join(os.path.dirname(__file__), "golden", "sketch_vectors.npz"))
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a.T)).cuda().t()
+
+
+def host(t):
+    return np.asfortranarray(t.cpu().numpy())
+
+
+def _st(seed):
+    return rl.RNGState(key=(int(seed[4]), int(seed[5])), counter=[int(x) for x in seed[:4]])
+
+
+def _ost(seed):
+    return O.RNGState((int(seed[4]), int(seed[5])), [int(x) for x in seed[:4]])
+
+
+@pytest.mark.parametrize("i", range(int(G["sp_count"])))
+def test_fill_sparse_golden(ctx, i):
+    nr, nc, nnz, sr, sc, ro, co = [int(x) for x in G[f"sp{i}_args"]]
+    k, vals, rows, cols, nxt = rl.fill_sparse(ctx, rl.SparseDist(nr, nc, nnz), _st(G[f"sp{i}_seed"]), torch.float64, (sr, sc, ro, co))
+    assert k == len(G[f"sp{i}_rows"])
+    assert np.array_equal(rows.cpu().numpy(), G[f"sp{i}_rows"]) and np.array_equal(cols.cpu().numpy(), G[f"sp{i}_cols"])
+    assert np.array_equal(vals.cpu().numpy(), G[f"sp{i}_vals"])
+    assert list(nxt.words()) == list(G[f"sp{i}_next"])
+
+
+def test_fill_sparse_vs_oracle_random(ctx):
+    rng = np.random.default_rng(17)
+    for trial in range(30):
+        nr, nc = int(rng.integers(1, 70)), int(rng.integers(1, 3000))
+        if rng.random() < 0.3:
+            nr, nc = nc, nr
+        nnz = int(rng.integers(1, min(nr, nc, 12) + 1))
+        sr, sc = int(rng.integers(1, nr + 1)), int(rng.integers(1, nc + 1))
+        sub = (sr, sc, int(rng.integers(0, nr - sr + 1)), int(rng.integers(0, nc - sc + 1)))
+        seed = [int(x) for x in rng.integers(0, 2 ** 32, 6)]
+        if trial % 3 == 0:
+            seed[0], seed[1] = 0xFFFFFFF0, 0xFFFFFFFF
+        dt = torch.float32 if trial % 2 else torch.float64
+        k, vals, rows, cols, nxt = rl.fill_sparse(ctx, rl.SparseDist(nr, nc, nnz), _st(seed), dt, sub)
+        k2, v2, r2, c2, st2 = O.fill_sparse(nr, nc, nnz, _ost(seed), sub=sub)
+        assert k == k2, (nr, nc, nnz, sub)
+        assert np.array_equal(rows.cpu().numpy(), r2) and np.array_equal(cols.cpu().numpy(), c2)
+        assert np.array_equal(vals.cpu().numpy().astype(np.float64), v2)
+        assert list(nxt.words()) == list(st2.words())
+
+
+@pytest.mark.parametrize("i", range(int(G["ap_count"])))
+def test_sparse_apply_golden(ctx, i):
+    sr, sc, nnz, d, m, n, ro, co = [int(x) for x in G[f"ap{i}_args"]]
+    alpha, beta = [float(x) for x in G[f"ap{i}_ab"]]
+    A, B0, Bref = G[f"ap{i}_A"], G[f"ap{i}_B0"], G[f"ap{i}_B"]
+    st = rl.RNGState(0)
+    B = rl.sketch_general_left(ctx, rl.SparseDist(sr, sc, nnz), st, dev(A), d, alpha, beta, dev(B0), ro, co)
+    tol = 50 * np.finfo(A.dtype).eps * (np.abs(A).max() * nnz * m / d + np.abs(B0).max() * abs(beta)) * max(1.0, abs(alpha))
+    assert np.abs(host(B) - Bref).max() <= tol
+    assert list(st.words()) == list(G[f"ap{i}_next"])
+
+
+# (d, m, n, nnz): covers every rows-per-thread variant of the kernel (d <= 512, 1024, 4096, 16384), ragged m (not a multiple of
+# the 2048-row chunk), n not a multiple of the column tile, single-row / single-column inputs
+APPLY = [(1, 1, 1, 1), (16, 16, 3, 16), (16, 333, 5, 3), (600, 5000, 17, 2), (2000, 9000, 9, 1), (4096, 20000, 24, 1), (5000, 12000, 6, 4),
+         (64, 70000, 33, 8), (300, 4097, 8, 16)]
+
+
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+@pytest.mark.parametrize("case", APPLY)
+def test_sparse_apply_vs_oracle(ctx, dtype, case):
+    d, m, n, nnz = case
+    npdt = np.float64 if dtype == torch.float64 else np.float32
+    rng = np.random.default_rng(d + m)
+    A = np.asfortranarray(rng.standard_normal((m, n)).astype(npdt))
+    st, ost = rl.RNGState(3), O.RNGState(3)
+    B = rl.sketch_general_left(ctx, rl.SparseDist(d, m, nnz), st, dev(A))
+    Bo, onxt = O.sketch_sparse_left(d, m, nnz, d, A, ost)
+    tol = 50 * np.finfo(npdt).eps * np.abs(A).max() * max(4.0, 8.0 * nnz * m / d)
+    assert np.abs(host(B) - Bo).max() <= tol, np.abs(host(B) - Bo).max()
+    assert list(st.words()) == list(onxt.words())
+    # run-to-run determinism (fixed summation order)
+    B2 = rl.sketch_general_left(ctx, rl.SparseDist(d, m, nnz), rl.RNGState(3), dev(A))
+    assert torch.equal(B, B2)
+
+
+def test_sparse_apply_properties_large(ctx):
+    """Size-independent properties at a size the oracle does not run at: linearity, and the checksum
+    1^T (S A) = (1^T S) A with 1^T S taken from the device's own (bit-exact-tested) triplets."""
+    d, m, n, nnz = 4096, 1 << 20, 64, 2
+    g = torch.Generator(device="cuda").manual_seed(1)
+    A1 = rl.to_f(torch.randn((m, n), dtype=torch.float32, device="cuda", generator=g))
+    A2 = rl.to_f(torch.randn((m, n), dtype=torch.float32, device="cuda", generator=g))
+    D = rl.SparseDist(d, m, nnz)
+    B1 = rl.sketch_general_left(ctx, D, rl.RNGState(9), A1)
+    B2 = rl.sketch_general_left(ctx, D, rl.RNGState(9), A2)
+    B12 = rl.sketch_general_left(ctx, D, rl.RNGState(9), rl.to_f(A1 + A2))
+    scale = float(nnz * m / d) ** 0.5
+    assert (B12 - (B1 + B2)).abs().max().item() <= 1e-5 * scale * 8
+    k, vals, rows, cols, _ = rl.fill_sparse(ctx, D, rl.RNGState(9), torch.float32)
+    colsum = torch.zeros(m, dtype=torch.float64, device="cuda").index_add_(0, cols, vals.double())
+    lhs = B1.double().sum(dim=0)
+    rhs = colsum @ A1.double()
+    assert (lhs - rhs).abs().max().item() <= 1e-3 * (nnz * m) ** 0.5
+
+
+@pytest.mark.parametrize("i", range(int(G["dn_count"])))
+def test_dense_apply_golden(ctx, i):
+    left, sr, sc, d, m, n, ro, co, fam, ax = [int(x) for x in G[f"dn{i}_args"]]
+    A, Bref = G[f"dn{i}_A"], G[f"dn{i}_B"]
+    st = rl.RNGState(key=(9, 0), counter=(3, 0, 0, 0))
+    D = rl.DenseDist(sr, sc, fam, ax)
+    if left:
+        B = rl.sketch_general_left(ctx, D, st, dev(A), d, ro_s=ro, co_s=co)
+    else:
+        B = rl.sketch_general_right(ctx, dev(A), D, st, d, ro_s=ro, co_s=co)
+    tol = 2e-6 if A.dtype == np.float64 else 2e-5
+    assert np.linalg.norm(host(B) - Bref) <= tol * np.linalg.norm(Bref)
+    assert list(st.words()) == list(G[f"dn{i}_next"])
+
+
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+def test_dense_left_never_materialised_matches_materialised(ctx, dtype):
+    """S (d x m) would be 2.1 GB here in fp64; the kernel regenerates it in 32 MB panels.  Compare against the product with
+    explicitly materialised row-blocks of the same operator, and check alpha/beta handling."""
+    d, m, n = 128, 1 << 21, 32
+    if dtype == torch.float32:
+        d, m = 256, 1 << 19
+    g = torch.Generator(device="cuda").manual_seed(4)
+    A = rl.to_f(torch.randn((m, n), dtype=dtype, device="cuda", generator=g))
+    B0 = rl.to_f(torch.randn((d, n), dtype=dtype, device="cuda", generator=g))
+    D = rl.DenseDist(d, m)
+    st = rl.RNGState(21)
+    B = rl.sketch_general_left(ctx, D, st, A, d, alpha=0.5, beta=-1.0, B=B0.clone())
+    exp = -1.0 * B0.double()
+    step = 1 << 17
+    for j0 in range(0, m, step):
+        buf, _ = rl.fill_dense(ctx, D, rl.RNGState(21), dtype, rl.LAYOUT_COLMAJOR, (d, step, 0, j0))
+        S = buf.view(step, d).t()
+        exp += 0.5 * (S.double() @ A[j0:j0 + step].double())
+    rel = ((B.double() - exp).norm() / exp.norm()).item()
+    assert rel <= (1e-12 if dtype == torch.float64 else 1e-5), rel
+    _, nxt = rl.fill_dense(ctx, D, rl.RNGState(21), dtype, rl.LAYOUT_NATURAL, (1, 1, 0, 0))
+    assert st == O_next(d, m, 21)
+
+
+def O_next(nr, nc, key):
+    s = O.dense_next_state(nr, nc, O.AXIS_LONG, O.RNGState(key))
+    return rl.RNGState(s.key, s.counter)
