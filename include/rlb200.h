@@ -215,6 +215,33 @@ RLB200_API int rlb200_rsvd_f64_host(rlb200_ctx* ctx, int64_t m, int64_t n, const
 RLB200_API int rlb200_rsvd_f32_host(rlb200_ctx* ctx, int64_t m, int64_t n, const float* A, int64_t* k, float tol, float* U,
                          float* S, float* V, uint32_t state[6], const rlb200_stack_opts* opts, int* qb_code);
 
+/* ---- a14: CQRRPT<T,RNG>::call(m, n, A, lda, R, ldr, J, d_factor, state) (RandLAPACK/drivers/rl_cqrrpt.hh:146-391) with the
+ *      default QRCP (geqp3, :56-66,247).  `eps` and `nnz` are the object's public fields (ctor argument `ep`; SASO nnz, default 2).
+ * A_dev (m x n, lda >= m) is overwritten by Q (its first *rank columns); R_dev (ldr >= n, n columns) receives the rank x n
+ * upper-trapezoidal factor (only the entries the reference writes are written); J_dev: n 1-based GEQP3-style pivots;
+ * *rank <- this->rank.  A[:, J] = Q R.  Returns 0, or 1 exactly where the reference does (:300-305).
+ * Row-sharded contexts: A_dev holds this rank's row block; the sketch and the Gram matrix are allreduced, R/J/rank are replicated. */
+RLB200_API int rlb200_cqrrpt_f64_dev(rlb200_ctx* ctx, int64_t m, int64_t n, double* A_dev, int64_t lda, double* R_dev, int64_t ldr,
+                          int64_t* J_dev, double d_factor, double eps, int64_t nnz, int64_t* rank, uint32_t state[6]);
+RLB200_API int rlb200_cqrrpt_f32_dev(rlb200_ctx* ctx, int64_t m, int64_t n, float* A_dev, int64_t lda, float* R_dev, int64_t ldr,
+                          int64_t* J_dev, float d_factor, float eps, int64_t nnz, int64_t* rank, uint32_t state[6]);
+/* Host-pointer form (the reference's own calling convention): A, R, J are HOST buffers. */
+RLB200_API int rlb200_cqrrpt_f64_host(rlb200_ctx* ctx, int64_t m, int64_t n, double* A, int64_t lda, double* R, int64_t ldr, int64_t* J,
+                           double d_factor, double eps, int64_t nnz, int64_t* rank, uint32_t state[6]);
+RLB200_API int rlb200_cqrrpt_f32_host(rlb200_ctx* ctx, int64_t m, int64_t n, float* A, int64_t lda, float* R, int64_t ldr, int64_t* J,
+                           float d_factor, float eps, int64_t nnz, int64_t* rank, uint32_t state[6]);
+
+/* ---- lapack::geqp3 / geqrf of a small (L2-resident) d x n matrix, as used on the sketch (rl_cqrrpt.hh:247, rl_bqrrp.hh:336,356).
+ * pivot != 0: J_dev receives n 1-based pivots (all columns free on entry, i.e. LAPACK's jpvt = 0 convention of the call sites). */
+RLB200_API int rlb200_qr_small_f64_dev(rlb200_ctx* ctx, int pivot, int64_t d, int64_t n, double* A_dev, int64_t lda, int64_t* J_dev,
+                            double* tau_dev);
+RLB200_API int rlb200_qr_small_f32_dev(rlb200_ctx* ctx, int pivot, int64_t d, int64_t n, float* A_dev, int64_t lda, int64_t* J_dev,
+                            float* tau_dev);
+/* ---- util::col_swap(m, n, k, A, lda, idx) = lapack::lapmt(forward) (RandLAPACK/misc/rl_util.hh:151-165): column i of A <- old
+ *      column idx[i]-1; idx_host: n 1-based entries on the HOST (left unchanged). */
+RLB200_API int rlb200_col_swap_f64_dev(rlb200_ctx* ctx, int64_t m, int64_t n, double* A_dev, int64_t lda, const int64_t* idx_host);
+RLB200_API int rlb200_col_swap_f32_dev(rlb200_ctx* ctx, int64_t m, int64_t n, float* A_dev, int64_t lda, const int64_t* idx_host);
+
 /* ---- lapack::gesdd(SomeVec) of a tall n x k matrix as used at rl_rsvd.hh:146 ----------------
  * B_dev (n x k, ld n) is overwritten by its left singular vectors (n x k), S_dev by the singular
  * values (descending), W_dev (k x k, ld k) by the RIGHT singular vectors as columns (so B_in = B_out diag(S) W^T). */

@@ -404,6 +404,26 @@ def gen_poly_mat(m, n, k, cond, exponent, state, frac_spectrum_one=0.1, dtype=np
     return gen_singvec(m, n, s, state, dtype)
 
 
+def gen_adversarial_mat(m, n, sigma, state, dtype=np.float64):
+    """rl_gen.hh:311-359 (mat_gen case `adverserial`): A = orth(G_U with 10 rows scaled by sigma) * triu(orth(G_V)) with the
+    diagonal of the triangular factor scaled by 1e-2 from column 11 on."""
+    U, state = fill_dense(m, n, state, dtype)
+    V, state = fill_dense(n, n, state, dtype)
+    U, V = _F(U.copy()), _F(V.copy())
+    U[:10, :] *= np.dtype(dtype).type(sigma)
+    geqrf, orgqr = get_lapack_funcs(("geqrf", "orgqr"), (U,))
+
+    def _q(M):
+        qr, tau, _, _ = geqrf(M)
+        _, lw, _ = orgqr(qr, tau, lwork=-1)
+        q, _, info = orgqr(qr, tau, lwork=int(lw[0]))
+        return _F(q)
+    U, V = _q(U), np.triu(_q(V))
+    for i in range(11, n):
+        V[i, i] *= np.dtype(dtype).type(10e-3)
+    return _gemm(U, _F(V)), state
+
+
 # --------------------------------------------------------------------------------------------
 # RandBLAS sketching operators applied (sparse_skops.hh, skge.hh)
 # --------------------------------------------------------------------------------------------
@@ -471,3 +491,65 @@ def sketch_dense_right(A, S_rows, S_cols, d, state: RNGState, family=FAMILY_GAUS
     if B is not None and beta != 0:
         out = out + beta * B
     return _F(out), dense_next_state(S_rows, S_cols, major_axis, state)
+
+
+# --------------------------------------------------------------------------------------------
+# CQRRPT (RandLAPACK/drivers/rl_cqrrpt.hh:146-391), default subroutines (SASO sketch, geqp3)
+# --------------------------------------------------------------------------------------------
+def col_swap(A, idx):
+    """util::col_swap = lapack::lapmt(forward) (rl_util.hh:151-165): new column i = old column idx[i]-1."""
+    return _F(A[:, np.asarray(idx, dtype=np.int64) - 1])
+
+
+class CQRRPT:
+    """RandLAPACK::CQRRPT(timing, eps); fields nnz (=2), rank.  qrcp = geqp3."""
+
+    def __init__(self, eps, nnz=2):
+        self.eps, self.nnz, self.rank = eps, nnz, None
+
+    def call(self, A, d_factor, state: RNGState, R=None):
+        """-> (rc, Q (m x n, first rank columns meaningful), R (n x n), J (1-based), next state)."""
+        A = _F(np.array(A, copy=True))
+        m, n = A.shape
+        dt = A.dtype
+        eps_m = np.finfo(dt).eps
+        R = np.zeros((n, n), dtype=dt, order="F") if R is None else _F(np.array(R, copy=True))
+        J = np.zeros(n, dtype=np.int64)
+        k = n
+        d = int(dt.type(d_factor) * dt.type(n))                                     # :197
+        eps_initial = dt.type(2) * dt.type(np.power(np.float64(eps_m), 0.95))       # :199
+        A_hat, state = sketch_sparse_left(d, m, self.nnz, d, A, state)              # :214-221
+        geqp3, trsm_, potrf = get_lapack_funcs(("geqp3",), (A_hat,))[0], get_blas_funcs(("trsm",), (A,))[0], \
+            get_lapack_funcs(("potrf",), (A,))[0]
+        A_hat, jpvt, tau, _, info = geqp3(A_hat)                                    # :247
+        J[:] = jpvt
+        if not A_hat[0, 0]:                                                         # :256
+            return 0, A, R, J, state
+        dg = np.abs(np.diag(A_hat)[:n])
+        for i in range(n):                                                          # :267-272
+            if dg[i] / dg[0] < eps_initial:
+                k = i
+                break
+        self.rank = k
+        new_rank = k
+        R[:k, :k] = np.triu(A_hat[:k, :k]) + np.tril(R[:k, :k], -1)                 # lacpy(Upper) :284
+        A = col_swap(A, J)                                                          # :291-292
+        if np.any(np.diag(R)[:k] == 0):                                             # :300-305
+            return 1, A, R, J, state
+        A[:, :k] = trsm_(1.0, _F(R[:k, :k]), _F(A[:, :k]), side=1, lower=0)          # :306
+        G = np.triu(_gemm(_F(A[:, :k]), _F(A[:, :k]), ta=True))                     # syrk(Upper) :309
+        c, info = potrf(_F(G + np.tril(R[:k, :k], -1)), lower=0, clean=0)           # :311
+        R[:k, :k] = c
+        if info:                                                                    # :311-336
+            running_max = running_min = R[0, 0]
+            cond_threshold = np.sqrt(dt.type(self.eps) / eps_m)
+            for i in range(k):
+                curr = abs(R[i, i])
+                running_max, running_min = max(running_max, curr), min(running_min, curr)
+                if running_min * cond_threshold < running_max and i > 1:
+                    new_rank = i - 1
+                    break
+        self.rank = new_rank                                                        # :339
+        A[:, :new_rank] = trsm_(1.0, _F(R[:new_rank, :new_rank]), _F(A[:, :new_rank]), side=1, lower=0)   # :342
+        R[:new_rank, :] = R[:new_rank, :] @ np.triu(A_hat[:n, :n])                  # trmm :349
+        return 0, A, R, J, state

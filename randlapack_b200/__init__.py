@@ -18,7 +18,7 @@ from . import _capi
 from ._capi import (STAB_PLUL, STAB_CHOLQRQ, STAB_HQRQ, FAMILY_GAUSSIAN, FAMILY_UNIFORM, AXIS_LONG, AXIS_SHORT,  # noqa: F401
                     LAYOUT_NATURAL, LAYOUT_COLMAJOR, LAYOUT_ROWMAJOR, StackOpts)
 
-__all__ = ["Context", "RNGState", "DenseDist", "fill_dense", "SparseDist", "fill_sparse", "sketch_general_left", "sketch_general_right", "CholQRQ", "PLUL", "HQRQ", "RS", "RF", "QB", "RSVD", "empty_f",
+__all__ = ["Context", "RNGState", "DenseDist", "fill_dense", "SparseDist", "fill_sparse", "sketch_general_left", "sketch_general_right", "CQRRPT", "qr_small", "col_swap", "CholQRQ", "PLUL", "HQRQ", "RS", "RF", "QB", "RSVD", "empty_f",
            "to_f", "Error", "shard_rows"]
 
 
@@ -499,6 +499,72 @@ class RSVD:
         state.assign(w)
         self.qb_code = qc.value
         return rc, kk.value, U, S, V
+
+
+class CQRRPT:
+    """RandLAPACK::CQRRPT(time_subroutines, eps) (rl_cqrrpt.hh:45-146); public fields nnz (SASO non-zeros per column, default 2), rank.
+    qrcp is fixed to the reference's default (geqp3)."""
+
+    def __init__(self, time_subroutines=False, eps=None):
+        self.timing, self.eps, self.nnz, self.rank = time_subroutines, eps, 2, None
+
+    def _eps(self, dtype):
+        torch = _torch()
+        return float(torch.finfo(dtype).eps) ** 0.85 if self.eps is None else self.eps
+
+    def call(self, ctx: Context, A, d_factor, state: RNGState, R=None, J=None):
+        """A (m x n device, column-major) is overwritten by Q; -> (rc, R n x n [first rank rows valid], J int64 1-based)."""
+        torch = _torch()
+        assert _is_f(A)
+        m, n = A.shape
+        if R is None:
+            R = torch.zeros((n, n), dtype=A.dtype, device=A.device).t()
+        if J is None:
+            J = torch.zeros(n, dtype=torch.int64, device=A.device)
+        rank = ctypes.c_int64(0)
+        w = state.words()
+        fn = getattr(ctx._lib, f"rlb200_cqrrpt_{_suffix(A.dtype)}_dev")
+        rc = ctx.check(fn(ctx._h, m, n, A.data_ptr(), _ld(A), R.data_ptr(), _ld(R), J.data_ptr(), d_factor, self._eps(A.dtype), self.nnz,
+                          ctypes.byref(rank), w))
+        state.assign(w)
+        self.rank = rank.value
+        return rc, R, J
+
+    def call_host(self, ctx: Context, A_host, d_factor, state: RNGState, R=None, J=None):
+        """The reference-facing form: HOST column-major A (overwritten by Q), host R / J out; copies inside."""
+        torch = _torch()
+        assert _is_f(A_host) and not A_host.is_cuda
+        m, n = A_host.shape
+        R = torch.zeros((n, n), dtype=A_host.dtype).t() if R is None else R
+        J = torch.zeros(n, dtype=torch.int64) if J is None else J
+        rank = ctypes.c_int64(0)
+        w = state.words()
+        fn = getattr(ctx._lib, f"rlb200_cqrrpt_{_suffix(A_host.dtype)}_host")
+        rc = ctx.check(fn(ctx._h, m, n, A_host.data_ptr(), _ld(A_host), R.data_ptr(), _ld(R), J.data_ptr(), d_factor,
+                          self._eps(A_host.dtype), self.nnz, ctypes.byref(rank), w))
+        state.assign(w)
+        self.rank = rank.value
+        return rc, R, J
+
+
+def qr_small(ctx: Context, A, pivot=True):
+    """lapack::geqp3 (pivot) / geqrf of a small device matrix, in place -> (J int64 1-based or None, tau)."""
+    torch = _torch()
+    d, n = A.shape
+    J = torch.zeros(n, dtype=torch.int64, device=A.device)
+    tau = torch.zeros(max(min(d, n), 1), dtype=A.dtype, device=A.device)
+    fn = getattr(ctx._lib, f"rlb200_qr_small_{_suffix(A.dtype)}_dev")
+    ctx.check(fn(ctx._h, int(pivot), d, n, A.data_ptr(), _ld(A), J.data_ptr(), tau.data_ptr()))
+    return (J if pivot else None), tau[: min(d, n)]
+
+
+def col_swap(ctx: Context, A, idx):
+    """util::col_swap / lapack::lapmt(forward): column i of A <- old column idx[i]-1 (idx: 1-based, host sequence)."""
+    m, n = A.shape
+    arr = (ctypes.c_int64 * n)(*[int(x) for x in idx])
+    fn = getattr(ctx._lib, f"rlb200_col_swap_{_suffix(A.dtype)}_dev")
+    ctx.check(fn(ctx._h, m, n, A.data_ptr(), _ld(A), arr))
+    return A
 
 
 def svd_tall(ctx: Context, B):

@@ -41,6 +41,9 @@ _F = lambda ft: {  # noqa: E731  typed entry points, ft = ctypes float type
     "qb": (c_int, [c_vp, c_i64, c_i64, c_vp, P_i64, c_i64, ft, c_vp, c_vp, c_vp, P_u32, ctypes.POINTER(StackOpts)]),
     "rsvd": (c_int, [c_vp, c_i64, c_i64, c_vp, P_i64, ft, c_vp, c_vp, c_vp, c_vp, P_u32, ctypes.POINTER(StackOpts), P_int]),
     "svd_tall": (c_int, [c_vp, c_i64, c_i64, c_vp, c_vp, c_vp]),
+    "cqrrpt": (c_int, [c_vp, c_i64, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, ft, ft, c_i64, P_i64, P_u32]),
+    "qr_small": (c_int, [c_vp, c_int, c_i64, c_i64, c_vp, c_i64, c_vp, c_vp]),
+    "col_swap": (c_int, [c_vp, c_i64, c_i64, c_vp, c_i64, c_vp]),
     "fill_sparse": (c_int, [c_vp, c_i64, c_i64, c_i64, c_int, c_i64, c_i64, c_i64, c_i64, P_i64, c_vp, c_vp, c_vp, P_u32]),
     "sketch_sparse_left": (c_int, [c_vp, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, ft, c_i64, c_i64, c_vp, c_i64, ft, c_vp, c_i64, P_u32]),
     "sketch_dense_left": (c_int, [c_vp, c_i64, c_i64, c_int, c_int, c_i64, c_i64, c_i64, ft, c_i64, c_i64, c_vp, c_i64, ft, c_vp, c_i64,
@@ -68,6 +71,7 @@ SIGNATURES = {
 for _suf, _ft in (("f64", ctypes.c_double), ("f32", ctypes.c_float)):
     for _name, _sig in _F(_ft).items():
         SIGNATURES[f"rlb200_{_name}_{_suf}_dev"] = _sig
+    SIGNATURES[f"rlb200_cqrrpt_{_suf}_host"] = (c_int, [c_vp, c_i64, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, _ft, _ft, c_i64, P_i64, P_u32])
     SIGNATURES[f"rlb200_rsvd_{_suf}_host"] = (c_int, [c_vp, c_i64, c_i64, c_vp, P_i64, _ft, c_vp, c_vp, c_vp, P_u32,
                                                       ctypes.POINTER(StackOpts), P_int])
 

@@ -194,6 +194,48 @@ int rlb200_philox_stream_dev(rlb200_ctx* ctx, const uint32_t state[6], int64_t n
         CTX_OK(ctx); RLB_CHECK(bind(ctx)); RLB_REQUIRE(ctx, opts && state);                                                         \
         return rsvd_call<T>(ctx, m, n, A_dev, k, tol, U_dev, S_dev, V_dev, Acpy_dev, state, *opts, qb_code);                        \
     }                                                                                                                               \
+    int rlb200_cqrrpt_##SUF##_dev(rlb200_ctx* ctx, int64_t m, int64_t n, T* A_dev, int64_t lda, T* R_dev, int64_t ldr, int64_t* J_dev, \
+                                  T d_factor, T eps, int64_t nnz, int64_t* rank, uint32_t state[6]) {                               \
+        CTX_OK(ctx); RLB_CHECK(bind(ctx)); RLB_REQUIRE(ctx, state && rank);                                                         \
+        return cqrrpt_call<T>(ctx, m, n, A_dev, lda, R_dev, ldr, J_dev, d_factor, eps, nnz, rank, state);                           \
+    }                                                                                                                               \
+    int rlb200_cqrrpt_##SUF##_host(rlb200_ctx* ctx, int64_t m, int64_t n, T* A, int64_t lda, T* R, int64_t ldr, int64_t* J,         \
+                                   T d_factor, T eps, int64_t nnz, int64_t* rank, uint32_t state[6]) {                              \
+        CTX_OK(ctx); RLB_CHECK(bind(ctx)); RLB_REQUIRE(ctx, state && rank);                                                         \
+        RLB_REQUIRE(ctx, m >= 0 && n >= 0 && lda >= m && ldr >= n);                                                                 \
+        *rank = 0;                                                                                                                  \
+        if (m == 0 || n == 0) return cqrrpt_call<T>(ctx, m, n, A, lda, R, ldr, J, d_factor, eps, nnz, rank, state);                 \
+        RLB_REQUIRE(ctx, A && R && J);                                                                                              \
+        ArenaScope as(ctx);                                                                                                         \
+        T* dA = as.take<T>((size_t)m * n); if (!dA) return RLB200_ERR_ALLOC;                                                        \
+        T* dR = as.take<T>((size_t)n * n); if (!dR) return RLB200_ERR_ALLOC;                                                        \
+        int64_t* dJ = as.take<int64_t>((size_t)n); if (!dJ) return RLB200_ERR_ALLOC;                                                \
+        RLB_CUDA_OK(ctx, cudaMemcpy2DAsync(dA, m * sizeof(T), A, lda * sizeof(T), m * sizeof(T), n, cudaMemcpyHostToDevice, ctx->stream)); \
+        RLB_CUDA_OK(ctx, cudaMemcpy2DAsync(dR, n * sizeof(T), R, ldr * sizeof(T), n * sizeof(T), n, cudaMemcpyHostToDevice, ctx->stream)); \
+        int rc = cqrrpt_call<T>(ctx, m, n, dA, m, dR, n, dJ, d_factor, eps, nnz, rank, state);                                      \
+        if (rc < 0) return rc;                                                                                                      \
+        RLB_CUDA_OK(ctx, cudaMemcpy2DAsync(A, lda * sizeof(T), dA, m * sizeof(T), m * sizeof(T), n, cudaMemcpyDeviceToHost, ctx->stream)); \
+        RLB_CUDA_OK(ctx, cudaMemcpy2DAsync(R, ldr * sizeof(T), dR, n * sizeof(T), n * sizeof(T), n, cudaMemcpyDeviceToHost, ctx->stream)); \
+        RLB_CUDA_OK(ctx, cudaMemcpyAsync(J, dJ, sizeof(int64_t) * n, cudaMemcpyDeviceToHost, ctx->stream));                         \
+        RLB_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));                                                                       \
+        return rc;                                                                                                                  \
+    }                                                                                                                               \
+    int rlb200_qr_small_##SUF##_dev(rlb200_ctx* ctx, int pivot, int64_t d, int64_t n, T* A_dev, int64_t lda, int64_t* J_dev,        \
+                                    T* tau_dev) {                                                                                   \
+        CTX_OK(ctx); RLB_CHECK(bind(ctx));                                                                                          \
+        ArenaScope as(ctx);                                                                                                         \
+        void* ws = arena_push(ctx, qrcp_ws_bytes(n)); if (!ws) return RLB200_ERR_ALLOC;                                             \
+        int rc = qr_small<T>(ctx, pivot != 0, d, n, A_dev, lda, J_dev, tau_dev, ws);                                                \
+        if (rc < 0) return rc;                                                                                                      \
+        RLB_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));                                                                       \
+        return rc;                                                                                                                  \
+    }                                                                                                                               \
+    int rlb200_col_swap_##SUF##_dev(rlb200_ctx* ctx, int64_t m, int64_t n, T* A_dev, int64_t lda, const int64_t* idx_host) {        \
+        CTX_OK(ctx); RLB_CHECK(bind(ctx)); RLB_REQUIRE(ctx, m >= 0 && n >= 0 && lda >= m && (idx_host || n == 0));                  \
+        std::vector<int64_t> p((size_t)n);                                                                                          \
+        for (int64_t i = 0; i < n; ++i) { p[i] = idx_host[i] - 1; RLB_REQUIRE(ctx, p[i] >= 0 && p[i] < n); }                        \
+        return col_permute<T>(ctx, m, n, A_dev, lda, p.data());                                                                     \
+    }                                                                                                                               \
     int rlb200_svd_tall_##SUF##_dev(rlb200_ctx* ctx, int64_t n, int64_t k, T* B_dev, T* S_dev, T* W_dev) {                          \
         CTX_OK(ctx); RLB_CHECK(bind(ctx));                                                                                          \
         ArenaScope as(ctx);                                                                                                         \

@@ -119,34 +119,25 @@ static int cholqrq(Ctx* ctx, int64_t m, int64_t k, T* A, bool cond_check, bool r
     if (k == 0) return 0;
     ArenaScope as(ctx);
     T* G = as.take<T>(k * k); RLB_ALLOC(ctx, G);
-    T* Rinv = as.take<T>(k * k); RLB_ALLOC(ctx, Rinv);
-    int* info_dev = as.take<int>(1); RLB_ALLOC(ctx, info_dev);
     RLB_CUDA_OK(ctx, cudaMemsetAsync(G, 0, sizeof(T) * k * k, ctx->stream));
     // G = A^T A, upper triangle (rl_orth.hh:78)
     RLB_CHECK(gemm_tn<T>(ctx, m, k, k, 1.0, A, m, A, m, 0.0, G, k, /*upper_only=*/1));
     if (rows_sharded) RLB_CHECK(allreduce_sum<T>(ctx, G, k * k));
     // R = chol(G) (rl_orth.hh:81); failure => chol_fail, return 1
-    RLB_CHECK(potrf_upper<T>(ctx, (int)k, G, (int)k, info_dev));
     int info = 0;
-    RLB_CHECK(read_scalar<int>(ctx, info_dev, &info));
+    RLB_CHECK(potrf_blocked<T>(ctx, k, G, k, &info));
     if (info != 0) {
         if (chol_fail) *chol_fail = 1;
         return 1;
     }
     if (cond_check) {   // rl_orth.hh:88-93 — the whole k x k buffer (upper R, zero strictly-lower part) is examined
+        if (k > 256) RLB_CHECK(tri_op<T>(ctx, 1, k, k, G, k, G, k));   // the blocked factorisation scribbles below the diagonal
         double cond = 0;
         RLB_CHECK(cond_of_square<T>(ctx, k, G, &cond));
         if (cond > 1.0 / std::sqrt((double)std::numeric_limits<T>::epsilon())) return 1;
     }
-    // A <- A R^{-1} (rl_orth.hh:95), as a tall product with the explicit triangular inverse
-    RLB_CHECK(trtri_upper<T>(ctx, (int)k, G, (int)k, Rinv));
-    if (k <= 256) {
-        RLB_CHECK(gemm_nn_inplace<T>(ctx, m, k, k, 1.0, A, m, Rinv, k, /*b_upper_tri=*/true));
-    } else {
-        T* tmp = as.take<T>((size_t)m * k); RLB_ALLOC(ctx, tmp);
-        RLB_CUDA_OK(ctx, cudaMemcpyAsync(tmp, A, sizeof(T) * m * k, cudaMemcpyDeviceToDevice, ctx->stream));
-        RLB_CHECK(gemm_nn<T>(ctx, m, k, k, 1.0, tmp, m, Rinv, k, 0.0, A, m));
-    }
+    // A <- A R^{-1} (rl_orth.hh:95): blocked right-solve whose blocks are tall tensor-pipe GEMMs
+    RLB_CHECK(trsm_right_upper<T>(ctx, m, k, G, k, A, m));
     return 0;
 }
 
@@ -405,12 +396,111 @@ int rsvd_call(Ctx* ctx, int64_t m, int64_t n, T* A, int64_t* k_io, T tol, T* U, 
     return 0;
 }
 
+// ------------------------------------------------------------------------------------------------
+// CQRRPT  (rl_cqrrpt.hh:146-391)
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+static int read_diag(Ctx* ctx, const T* M, int64_t ld, int64_t k, std::vector<T>& out) {
+    out.resize((size_t)k);
+    if (k == 0) return 0;
+    RLB_CUDA_OK(ctx, cudaMemcpy2DAsync(out.data(), sizeof(T), M, (ld + 1) * sizeof(T), sizeof(T), k, cudaMemcpyDeviceToHost, ctx->stream));
+    RLB_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+template <typename T>
+int cqrrpt_call(Ctx* ctx, int64_t m, int64_t n, T* A, int64_t lda, T* R, int64_t ldr, int64_t* J_dev, T d_factor, T eps_user, int64_t nnz,
+                int64_t* rank_out, uint32_t state[6]) {
+    // :161-168
+    RLB_REQUIRE(ctx, m >= 0);
+    RLB_REQUIRE(ctx, n >= 0);
+    RLB_REQUIRE(ctx, lda >= m);
+    RLB_REQUIRE(ctx, ldr >= n);
+    RLB_REQUIRE(ctx, d_factor >= (T)1.0);
+    RLB_REQUIRE(ctx, !(A == nullptr && m > 0 && n > 0));
+    RLB_REQUIRE(ctx, !(R == nullptr && n > 0));
+    RLB_REQUIRE(ctx, !(J_dev == nullptr && n > 0));
+    RLB_REQUIRE(ctx, rank_out != nullptr);
+    const bool sharded = ctx->m_global >= 0;
+    const int64_t mg = sharded ? ctx->m_global : m;
+    *rank_out = 0;
+    if (n == 0) return 0;
+    RLB_REQUIRE(ctx, mg > 0);
+    int64_t k = n;
+    const int64_t d = (int64_t)(d_factor * (T)n);                                             // :197
+    RLB_REQUIRE(ctx, d <= mg);                                                                // SparseDist(d, m): the operator must be wide
+    const T eps_initial = (T)2 * (T)std::pow((double)std::numeric_limits<T>::epsilon(), 0.95);   // :199
+    ArenaScope as(ctx);
+    T* A_hat = as.take<T>((size_t)d * n); RLB_ALLOC(ctx, A_hat);
+    T* tau = as.take<T>((size_t)n); RLB_ALLOC(ctx, tau);
+    // SASO (:214-221); state <- S.next_state
+    RLB_CHECK(sketch_sparse_left<T>(ctx, d, mg, nnz, d, n, m, (T)1, 0, 0, A, lda, (T)0, A_hat, d, state));
+    // QRCP of the sketch (:247)
+    {
+        ArenaScope as2(ctx);
+        void* ws = arena_push(ctx, qrcp_ws_bytes(n)); RLB_ALLOC(ctx, ws);
+        RLB_CHECK(qr_small<T>(ctx, true, d, n, A_hat, d, J_dev, tau, ws));
+    }
+    std::vector<T> dg;
+    RLB_CHECK(read_diag<T>(ctx, A_hat, d, n, dg));
+    if (!dg[0]) return 0;                                                                     // :256-261 all-zero input
+    for (int64_t i = 0; i < n; ++i) {                                                         // :267-272
+        if (std::abs(dg[i]) / std::abs(dg[0]) < eps_initial) { k = i; break; }
+    }
+    *rank_out = k;
+    int64_t new_rank = k;
+    RLB_CHECK(tri_op<T>(ctx, 0, k, k, A_hat, d, R, ldr));                                     // lacpy(Upper) :284
+    // col_swap (:291-292)
+    {
+        std::vector<int64_t> J((size_t)n);
+        RLB_CUDA_OK(ctx, cudaMemcpyAsync(J.data(), J_dev, sizeof(int64_t) * n, cudaMemcpyDeviceToHost, ctx->stream));
+        RLB_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+        for (auto& v : J) v -= 1;
+        RLB_CHECK(col_permute<T>(ctx, m, n, A, lda, J.data()));
+    }
+    for (int64_t i = 0; i < k; ++i) if (dg[i] == (T)0) return 1;                              // diag_is_nonzero :300-305
+    RLB_CHECK(trsm_right_upper<T>(ctx, m, k, R, ldr, A, lda));                                // :306
+    // CholQR (:314-339): the Gram / Cholesky factor is built in scratch so that only the upper triangle of R is written
+    T* G = as.take<T>((size_t)k * k); RLB_ALLOC(ctx, G);
+    RLB_CUDA_OK(ctx, cudaMemsetAsync(G, 0, sizeof(T) * k * k, ctx->stream));
+    RLB_CHECK(gemm_tn<T>(ctx, m, k, k, 1.0, A, lda, A, lda, 0.0, G, k, 1));
+    if (sharded) RLB_CHECK(allreduce_sum<T>(ctx, G, k * k));
+    int info = 0;
+    RLB_CHECK(potrf_blocked<T>(ctx, k, G, k, &info));
+    RLB_CHECK(tri_op<T>(ctx, 0, k, k, G, k, R, ldr));
+    if (info != 0) {                                                                          // :311-336 a-posteriori rank estimate
+        std::vector<T> rd;
+        RLB_CHECK(read_diag<T>(ctx, G, k, k, rd));
+        T running_max = rd[0], running_min = rd[0];
+        const T cond_threshold = std::sqrt(eps_user / std::numeric_limits<T>::epsilon());
+        for (int64_t i = 0; i < k; ++i) {
+            const T curr = std::abs(rd[i]);
+            running_max = std::max(running_max, curr);
+            running_min = std::min(running_min, curr);
+            if ((running_min * cond_threshold < running_max) && i > 1) { new_rank = i - 1; break; }
+        }
+    }
+    *rank_out = new_rank;                                                                     // :339
+    RLB_CHECK(trsm_right_upper<T>(ctx, m, new_rank, R, ldr, A, lda));                         // :342
+    // R <- R[0:new_rank, 0:n] * triu(A_hat[0:n, 0:n])  (trmm :349)
+    if (new_rank > 0) {
+        T* U = as.take<T>((size_t)n * n); RLB_ALLOC(ctx, U);
+        T* Rin = as.take<T>((size_t)new_rank * n); RLB_ALLOC(ctx, Rin);
+        RLB_CHECK(tri_op<T>(ctx, 2, n, n, A_hat, d, U, n));
+        RLB_CUDA_OK(ctx, cudaMemcpy2DAsync(Rin, new_rank * sizeof(T), R, ldr * sizeof(T), new_rank * sizeof(T), n, cudaMemcpyDeviceToDevice, ctx->stream));
+        RLB_CHECK(gemm_nn<T>(ctx, new_rank, n, n, 1.0, Rin, new_rank, U, n, 0.0, R, ldr));
+    }
+    RLB_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));   // scratch is released on return
+    return 0;
+}
+
 #define INST(T)                                                                                                             \
     template int stab_call<T>(Ctx*, int, int64_t, int64_t, T*, bool, bool, int*);                                           \
     template int rs_call<T>(Ctx*, int64_t, int64_t, const T*, int64_t, T*, T*, uint32_t*, const rlb200_stack_opts&);         \
     template int rf_call<T>(Ctx*, int64_t, int64_t, const T*, int64_t, T*, uint32_t*, const rlb200_stack_opts&);             \
     template int qb_call<T>(Ctx*, int64_t, int64_t, T*, int64_t*, int64_t, T, T*, T*, T*, uint32_t*, const rlb200_stack_opts&); \
-    template int rsvd_call<T>(Ctx*, int64_t, int64_t, T*, int64_t*, T, T*, T*, T*, T*, uint32_t*, const rlb200_stack_opts&, int*);
+    template int rsvd_call<T>(Ctx*, int64_t, int64_t, T*, int64_t*, T, T*, T*, T*, T*, uint32_t*, const rlb200_stack_opts&, int*); \
+    template int cqrrpt_call<T>(Ctx*, int64_t, int64_t, T*, int64_t, T*, int64_t, int64_t*, T, T, int64_t, int64_t*, uint32_t*);
 INST(double)
 INST(float)
 

@@ -51,6 +51,19 @@ template <typename T>
 int sketch_dense_right(Ctx* ctx, int64_t S_rows, int64_t S_cols, int family, int major_axis, int64_t m, int64_t d, int64_t n, T alpha,
                        const T* A, int64_t lda, int64_t ro, int64_t co, T beta, T* B, int64_t ldb, uint32_t state[6]);
 
+// ---- factorisation building blocks (factor.cu) -----------------------------------------------------
+template <typename T>
+int col_permute(Ctx* ctx, int64_t m, int64_t n, T* A, int64_t lda, const int64_t* perm_host);
+template <typename T>
+int tri_op(Ctx* ctx, int mode, int64_t rows, int64_t cols, const T* src, int64_t lds, T* dst, int64_t ldd);
+template <typename T>
+int potrf_blocked(Ctx* ctx, int64_t k, T* A, int64_t lda, int* info_host);
+template <typename T>
+int trsm_right_upper(Ctx* ctx, int64_t m, int64_t k, const T* R, int64_t ldr, T* X, int64_t ldx);
+size_t qrcp_ws_bytes(int64_t n);
+template <typename T>
+int qr_small(Ctx* ctx, bool pivot, int64_t d, int64_t n, T* A, int64_t lda, int64_t* jpvt_dev, T* tau_dev, void* ws);
+
 // ---- arena: stack allocator for driver-level device buffers ---------------------------------------
 void* arena_push(Ctx* ctx, size_t bytes);          // nullptr on failure (ctx->err set)
 void arena_release(Ctx* ctx, size_t mark_total);   // pop back to a previous mark
@@ -79,5 +92,10 @@ int qb_call(Ctx* ctx, int64_t m, int64_t n, T* A, int64_t* k, int64_t block_sz, 
 template <typename T>
 int rsvd_call(Ctx* ctx, int64_t m, int64_t n, T* A, int64_t* k, T tol, T* U, T* S, T* V, T* Acpy, uint32_t state[6],
               const rlb200_stack_opts& o, int* qb_code);
+
+// CQRRPT::call (rl_cqrrpt.hh:146-391), geqp3 flavour.  R_dev: n x n region (ldr >= n), J_dev: n pivots (1-based), *rank_out <- this->rank.
+template <typename T>
+int cqrrpt_call(Ctx* ctx, int64_t m, int64_t n, T* A, int64_t lda, T* R, int64_t ldr, int64_t* J_dev, T d_factor, T eps, int64_t nnz,
+                int64_t* rank_out, uint32_t state[6]);
 
 }  // namespace rlb

@@ -1,0 +1,152 @@
+"""GPU parity, CQRRPT and its building blocks through the C-ABI.
+
+Tolerances (stated): return code, rank, RNG state and the pivot vector J are exact (bit-exact integers) against the golden vectors
+of the real reference and against the oracle on matrices whose pivot gaps dominate round-off (for rank-deficient inputs only the
+first `rank` pivots are meaningful — the rest order round-off noise, also between the reference and its own restatement).
+R and Q: fp64 1e-9 relative / fp32 2e-3 (CholQR of a sketch-preconditioned matrix; the sketch is summed in another order), and
+the reference's own acceptance test (test/drivers/test_cqrrpt.cc:98-104): all three error measures <= eps^0.75."""
+import numpy as np
+import pytest
+import torch
+
+import randlapack_b200 as rl
+from _qrcases import G, cq_input, qr_invariants
+from oracle import rl_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a.T)).cuda().t()
+
+
+def host(t):
+    return np.asfortranarray(t.cpu().numpy())
+
+
+@pytest.mark.parametrize("i", range(int(G["cq_count"])))
+def test_cqrrpt_golden(ctx, i):
+    A, st, c = cq_input(i)
+    alg = rl.CQRRPT(False, c["eps"])
+    alg.nnz = c["nnz"]
+    Ad = dev(A)
+    s = rl.RNGState(st.key, st.counter)
+    rc, R, J = alg.call(ctx, Ad, c["d_factor"], s)
+    rc_ref, rank_ref = [int(x) for x in G[f"cq{i}_rc_rank"]]
+    assert (rc, alg.rank) == (rc_ref, rank_ref)
+    assert list(s.words()) == list(G[f"cq{i}_state_out"])
+    Q, R, J = host(Ad), host(R), J.cpu().numpy()
+    r = rank_ref
+    assert sorted(J.tolist()) == list(range(1, c["n"] + 1))
+    assert np.array_equal(J[:r], G[f"cq{i}_J"][:r]), "pivot vector differs from the reference's"
+    if np.array_equal(J, G[f"cq{i}_J"]):
+        tol = 1e-9 if c["dtype"] == np.float64 else 2e-3
+        assert np.abs(np.diag(R)[:r] - G[f"cq{i}_Rdiag"][:r]).max() <= tol * np.abs(G[f"cq{i}_Rdiag"]).max()
+        h = min(r, 32)
+        assert np.abs(R[:h] - G[f"cq{i}_Rhead"]).max() <= tol * np.abs(G[f"cq{i}_Rhead"]).max()
+        assert np.abs(Q[:32, :r] - G[f"cq{i}_Qhead"]).max() <= tol * 10
+    e = qr_invariants(A, Q, R, J, r)
+    assert max(e) <= np.finfo(c["dtype"]).eps ** 0.75, e
+
+
+def test_cqrrpt_host_call_and_zero_matrix(ctx):
+    A, st, c = cq_input(2)
+    alg = rl.CQRRPT(False, c["eps"])
+    Ah = torch.from_numpy(np.array(A.T, order="C", copy=True)).t()   # (A.T of an F-ordered array is already C-contiguous: force a copy)
+    s = rl.RNGState(st.key, st.counter)
+    rc, R, J = alg.call_host(ctx, Ah, c["d_factor"], s)
+    assert rc == 0 and alg.rank == int(G["cq2_rc_rank"][1]) and np.array_equal(J.numpy(), G["cq2_J"])
+    e = qr_invariants(A, Ah.numpy(), R.numpy(), J.numpy(), alg.rank)
+    assert max(e) <= np.finfo(np.float64).eps ** 0.75
+    # all-zero input: the reference returns 0 right after the QRCP (rl_cqrrpt.hh:256-261), A untouched
+    Z = rl.to_f(torch.zeros((500, 20), dtype=torch.float64, device="cuda"))
+    rc, R, J = alg.call(ctx, Z, 2.0, rl.RNGState(0))
+    assert rc == 0 and float(Z.abs().max()) == 0.0
+    # argument validation = randlapack_require (rl_cqrrpt.hh:161-168)
+    with pytest.raises(rl.Error):
+        alg.call(ctx, Z, 0.5, rl.RNGState(0))
+
+
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+@pytest.mark.parametrize("shape", [(64, 40), (300, 300), (40, 64), (1500, 700), (1, 1), (5, 1)])
+def test_qrcp_small_vs_lapack(ctx, dtype, shape):
+    """geqp3 of the sketch: pivots bit-exact against LAPACK's on columns with graded norms; R equal to round-off; and geqrf."""
+    from scipy.linalg import lapack
+    d, n = shape
+    npdt = np.float64 if dtype == torch.float64 else np.float32
+    rng = np.random.default_rng(d * 7 + n)
+    A = rng.standard_normal((d, n)) * (1.0 + 0.37 * rng.permutation(n))[None, :] ** -1.0
+    A = np.asfortranarray(A.astype(npdt))
+    Ad = dev(A)
+    J, tau = rl.qr_small(ctx, Ad, pivot=True)
+    f = lapack.dgeqp3 if npdt == np.float64 else lapack.sgeqp3
+    qr, jpvt, tau_ref, _, info = f(A)
+    assert np.array_equal(J.cpu().numpy(), jpvt)
+    tol = 1e-11 if npdt == np.float64 else 1e-3
+    Rd, Rr = np.triu(host(Ad))[:min(d, n)], np.triu(qr)[:min(d, n)]
+    assert np.abs(Rd - Rr).max() <= tol * np.abs(Rr).max()
+    assert np.abs(tau.cpu().numpy() - tau_ref).max() <= tol * 10
+    assert np.abs(np.tril(host(Ad), -1) - np.tril(qr, -1)).max() <= tol * 100
+    # unpivoted
+    Ad = dev(A)
+    _, tau = rl.qr_small(ctx, Ad, pivot=False)
+    g = lapack.dgeqrf if npdt == np.float64 else lapack.sgeqrf
+    qr, tau_ref, _, info = g(A)
+    assert np.abs(host(Ad) - qr).max() <= tol * 100 * np.abs(qr).max()
+    assert np.abs(tau.cpu().numpy() - tau_ref).max() <= tol * 10
+
+
+def test_qrcp_ties_and_zero_columns(ctx):
+    """iamax semantics: first maximum wins; zero columns stay at the end with tau = 0."""
+    from scipy.linalg import lapack
+    A = np.zeros((8, 6), order="F")
+    A[:, 1] = 1.0
+    A[:, 3] = 1.0           # exact tie with column 1
+    A[0, 4] = 0.5
+    Ad = dev(A)
+    J, tau = rl.qr_small(ctx, Ad, pivot=True)
+    qr, jpvt, tau_ref, _, info = lapack.dgeqp3(A)
+    assert np.array_equal(J.cpu().numpy(), jpvt)
+    assert np.allclose(tau.cpu().numpy(), tau_ref, atol=1e-14)
+
+
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+def test_col_swap(ctx, dtype):
+    rng = np.random.default_rng(3)
+    for (m, n) in [(1, 1), (7, 5), (1000, 33), (4096, 64), (1001, 17)]:
+        A = rl.to_f(torch.randn((m, n), dtype=dtype, device="cuda"))
+        ref = A.clone()
+        idx = rng.permutation(n) + 1
+        rl.col_swap(ctx, A, idx)
+        assert torch.equal(A, ref[:, torch.from_numpy(idx - 1).cuda()])
+    # property at scale: a permutation followed by its inverse is the identity (bit-exact), on a matrix larger than L2
+    m, n = 1 << 20, 64
+    A = rl.to_f(torch.randn((m, n), dtype=dtype, device="cuda"))
+    ref = A.clone()
+    idx = rng.permutation(n) + 1
+    inv = np.argsort(idx - 1) + 1
+    rl.col_swap(ctx, A, idx)
+    assert not torch.equal(A, ref)
+    rl.col_swap(ctx, A, inv)
+    assert torch.equal(A, ref)
+
+
+def test_cqrrpt_large_property(ctx):
+    """A size the oracle does not run at (2^20 x 512 fp32, n > 256 exercises the blocked Cholesky / right-solve):
+    ||Q'Q - I||, ||A[:,J] - QR|| on a row sample, J a permutation, R upper triangular."""
+    m, n = 1 << 20, 512
+    g = torch.Generator(device="cuda").manual_seed(5)
+    A = rl.to_f(torch.randn((m, n), dtype=torch.float32, device="cuda", generator=g))
+    A *= (1.0 + torch.arange(n, device="cuda", dtype=torch.float32))[None, :] ** -0.5
+    A0 = A.clone()
+    alg = rl.CQRRPT(False, None)
+    alg.nnz = 1
+    rc, R, J = alg.call(ctx, A, 2.0, rl.RNGState(1))
+    assert rc == 0 and alg.rank == n
+    assert sorted(J.cpu().tolist()) == list(range(1, n + 1))
+    assert float(torch.tril(R, -1).abs().max()) == 0.0
+    QtQ = rl.gemm(ctx, True, False, 1.0, A, A)
+    assert float((QtQ - torch.eye(n, device="cuda")).norm()) / n ** 0.5 <= 1e-4
+    rows = torch.randint(0, m, (4096,), device="cuda")
+    E = A0[rows][:, J - 1].double() - A[rows].double() @ R.double()
+    assert float(E.norm() / A0[rows].double().norm()) <= 1e-4

@@ -1,0 +1,43 @@
+"""CPU: the oracle's CQRRPT restatement against the golden vectors from the real reference (tests/golden/qr_vectors.npz) and,
+when oracle/_ref exists, against the compiled reference directly.  Pivots, rank, return code and RNG state are exact;
+R and Q to round-off (the sketch is summed in a different order than the reference's OpenMP-simd loop)."""
+import numpy as np
+import pytest
+
+import _ref
+from _qrcases import G, cq_input, qr_invariants
+from oracle import rl_oracle as O
+
+
+@pytest.mark.parametrize("i", range(int(G["cq_count"])))
+def test_cqrrpt_golden(i):
+    A, st, c = cq_input(i)
+    alg = O.CQRRPT(c["eps"], c["nnz"])
+    rc, Q, R, J, st2 = alg.call(A, c["d_factor"], st)
+    rc_ref, rank_ref = [int(x) for x in G[f"cq{i}_rc_rank"]]
+    assert (rc, alg.rank) == (rc_ref, rank_ref)
+    assert list(st2.words()) == list(G[f"cq{i}_state_out"])
+    r = rank_ref
+    full = r == c["n"]
+    assert np.array_equal(J[:r], G[f"cq{i}_J"][:r]) or not full     # beyond the numerical rank the pivots are round-off noise
+    if full or np.array_equal(J, G[f"cq{i}_J"]):
+        tol = 1e-9 if c["dtype"] == np.float64 else 2e-3
+        assert np.abs(np.diag(R)[:r] - G[f"cq{i}_Rdiag"][:r]).max() <= tol * np.abs(G[f"cq{i}_Rdiag"]).max()
+        assert np.abs(Q[:32, :r] - G[f"cq{i}_Qhead"]).max() <= tol * 10
+    e = qr_invariants(A, Q, R, J, r)
+    atol = np.finfo(c["dtype"]).eps ** 0.75
+    assert max(e) <= atol, e
+
+
+@pytest.mark.skipif(_ref.ref_lib() is None, reason="compiled reference not present")
+def test_cqrrpt_vs_compiled_reference():
+    L = _ref.ref_lib()
+    for (m, n, k, cond, dt, nnz, df) in [(10, 5, 5, 2, np.float64, 2, 2.0), (1500, 80, 80, 1e3, np.float64, 3, 1.5), (900, 64, 64, 50, np.float32, 4, 1.25)]:
+        A, st = _ref.ref_mat_gen(L, 0, m, n, k, cond, 2.0, [0] * 6, dt)
+        eps = float(np.finfo(dt).eps) ** 0.85
+        rc, rank, Q, R, J, st2 = _ref.ref_cqrrpt(L, A, df, st, eps, nnz)
+        o = O.CQRRPT(eps, nnz)
+        rc2, Q2, R2, J2, st3 = o.call(A, df, O.RNGState((st[4], st[5]), st[:4]))
+        assert (rc, rank) == (rc2, o.rank) and np.array_equal(J, J2) and st2 == list(st3.words())
+        tol = 1e-11 if dt == np.float64 else 1e-4
+        assert np.abs(R - R2).max() <= tol * np.abs(R).max() and np.abs(Q[:, :rank] - Q2[:, :rank]).max() <= tol * 10
