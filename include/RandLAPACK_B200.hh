@@ -10,6 +10,8 @@
 //   RandLAPACK::RangeFinder / RF      comps/rl_rf.hh:16-137                rlb200::RF<T>
 //   RandLAPACK::QBalg / QB            comps/rl_qb.hh:17-268                rlb200::QB<T>
 //   RandLAPACK::RSVDalg / RSVD        drivers/rl_rsvd.hh:15-154            rlb200::RSVD<T>
+//   RandLAPACK::CQRRPTalg / CQRRPT    drivers/rl_cqrrpt.hh:20-391          rlb200::CQRRPT<T>
+//   RandLAPACK::BQRRPalg / BQRRP      drivers/rl_bqrrp.hh:19-665           rlb200::BQRRP<T>
 //
 // Two modes:
 //  * default: self-contained (no reference headers needed); `rlb200::RNGState` stands in for RandBLAS::RNGState.
@@ -91,10 +93,12 @@ template <typename T> struct abi;
 template <> struct abi<double> {
     static constexpr auto stab = rlb200_stab_f64_dev; static constexpr auto rs = rlb200_rs_f64_dev; static constexpr auto rf = rlb200_rf_f64_dev;
     static constexpr auto qb = rlb200_qb_f64_dev; static constexpr auto rsvd_host = rlb200_rsvd_f64_host;
+    static constexpr auto cqrrpt_host = rlb200_cqrrpt_f64_host; static constexpr auto bqrrp_host = rlb200_bqrrp_f64_host;
 };
 template <> struct abi<float> {
     static constexpr auto stab = rlb200_stab_f32_dev; static constexpr auto rs = rlb200_rs_f32_dev; static constexpr auto rf = rlb200_rf_f32_dev;
     static constexpr auto qb = rlb200_qb_f32_dev; static constexpr auto rsvd_host = rlb200_rsvd_f32_host;
+    static constexpr auto cqrrpt_host = rlb200_cqrrpt_f32_host; static constexpr auto bqrrp_host = rlb200_bqrrp_f32_host;
 };
 
 // device buffer staged from / to a host pointer
@@ -301,6 +305,77 @@ public:
     QB<T>& QB_Obj;
     int64_t block_sz;
     int qb_code = 0;   // the code QB returned (the reference discards it, rl_rsvd.hh:137)
+};
+
+// ---------------------------------------------------------------------------------------------------------------------
+// CQRRPT (rl_cqrrpt.hh:20-391): same constructor (time_subroutines, eps), public fields and call signature (HOST pointers).
+// ---------------------------------------------------------------------------------------------------------------------
+template <typename T>
+class CQRRPT
+#ifdef RLB200_WITH_RANDLAPACK
+    : public RandLAPACK::CQRRPTalg<T, r123::Philox4x32>
+#endif
+{
+public:
+    CQRRPT(bool time_subroutines, T ep) : timing(time_subroutines), eps(ep), rank(0), nnz(2), ctx_(&default_context()) {}
+    CQRRPT(Context& c, bool time_subroutines, T ep) : timing(time_subroutines), eps(ep), rank(0), nnz(2), ctx_(&c) {}
+    virtual ~CQRRPT() {}
+    // A (m x n, lda) <- Q; R (ldr >= n): rank x n; J: n 1-based pivots (rl_cqrrpt.hh:146-156)
+    int call(int64_t m, int64_t n, T* A, int64_t lda, T* R, int64_t ldr, int64_t* J, T d_factor, state_t& state) RLB200_OVERRIDE {
+        uint32_t w[6]; state_to_words(state, w);
+        int64_t r = 0;
+        int rc = ctx_->check(detail::abi<T>::cqrrpt_host(ctx_->get(), m, n, A, lda, R, ldr, J, d_factor, eps, nnz, &r, w));
+        words_to_state(w, state);
+        rank = r;
+        return rc;
+    }
+    bool timing;
+    T eps;
+    int64_t rank;
+    std::vector<long> times;   // kept for source compatibility; per-phase host timing is not offered (see rlb200_timer_read)
+    int64_t nnz;
+private:
+    Context* ctx_;
+};
+
+// ---------------------------------------------------------------------------------------------------------------------
+// BQRRP (rl_bqrrp.hh:19-665): same constructor (time_subroutines, b_sz), public fields and call signature (HOST pointers).
+// ---------------------------------------------------------------------------------------------------------------------
+struct BQRRPSubroutines {
+    enum QRCPWide { luqr = RLB200_QRCP_LUQR, geqp3 = RLB200_QRCP_GEQP3 };
+    enum QRTall { geqrf = RLB200_QRTALL_GEQRF, cholqr = RLB200_QRTALL_CHOLQR, geqrt = RLB200_QRTALL_GEQRT };
+};
+template <typename T>
+class BQRRP
+#ifdef RLB200_WITH_RANDLAPACK
+    : public RandLAPACK::BQRRPalg<T, r123::Philox4x32>
+#endif
+{
+public:
+    using Subroutines = BQRRPSubroutines;
+    BQRRP(bool time_subroutines, int64_t b_sz) : BQRRP(default_context(), time_subroutines, b_sz) {}
+    BQRRP(Context& c, bool time_subroutines, int64_t b_sz)
+        : timing(time_subroutines), rank(0), block_size(b_sz), internal_nb(b_sz), tol(std::numeric_limits<T>::epsilon()),
+          qrcp_wide(Subroutines::luqr), qr_tall(Subroutines::geqrf), ctx_(&c) {
+        if (b_sz <= 0) throw Error(RLB200_ERR_ARG, "BQRRP block size b_sz must be > 0");      // rl_bqrrp.hh:66
+    }
+    virtual ~BQRRP() {}
+    int call(int64_t m, int64_t n, T* A, int64_t lda, T d_factor, T* tau, int64_t* J, state_t& state) RLB200_OVERRIDE {
+        uint32_t w[6]; state_to_words(state, w);
+        int64_t r = 0;
+        int rc = ctx_->check(detail::abi<T>::bqrrp_host(ctx_->get(), m, n, A, lda, d_factor, block_size, (int)qrcp_wide, (int)qr_tall, tau, J, &r, w));
+        words_to_state(w, state);
+        rank = r;
+        return rc;
+    }
+    bool timing;
+    int64_t rank, block_size, internal_nb;
+    T tol;
+    std::vector<long> times;
+    Subroutines::QRCPWide qrcp_wide;
+    Subroutines::QRTall qr_tall;
+private:
+    Context* ctx_;
 };
 
 }  // namespace rlb200

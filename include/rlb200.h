@@ -231,6 +231,26 @@ RLB200_API int rlb200_cqrrpt_f64_host(rlb200_ctx* ctx, int64_t m, int64_t n, dou
 RLB200_API int rlb200_cqrrpt_f32_host(rlb200_ctx* ctx, int64_t m, int64_t n, float* A, int64_t lda, float* R, int64_t ldr, int64_t* J,
                            float d_factor, float eps, int64_t nnz, int64_t* rank, uint32_t state[6]);
 
+/* ---- a15: BQRRP<T,RNG>::call(m, n, A, lda, d_factor, tau, J, state) (RandLAPACK/drivers/rl_bqrrp.hh:154-665), and the
+ *      device-pointer convention of BQRRP_GPU::call (rl_bqrrp_gpu.hh:152-942).  block_size, qrcp_wide, qr_tall are the object's
+ *      fields: block_size = ctor's b_sz; qrcp_wide: 0 = luqr (default), 1 = geqp3; qr_tall: 0 = geqrf (default), 1 = cholqr
+ *      (CholQR + Householder reconstruction; the choice BQRRP_GPU makes), 2 = geqrt.  tol = eps (ctor default).
+ * On exit A_dev is GEQP3-formatted (R in the upper triangle, Householder vectors below), tau_dev (n; entries written as the
+ * reference writes them), J_dev (n 1-based pivots), *rank <- this->rank.  The d x n Gaussian sketch is formed internally from `state`
+ * exactly as the CPU reference does (:309-312) with S regenerated on chip; state <- the reference's advanced state.
+ * Not row-shardable (RLB200_ERR_UNSUPPORTED on a sharded context): replicas only. */
+enum { RLB200_QRCP_LUQR = 0, RLB200_QRCP_GEQP3 = 1 };
+enum { RLB200_QRTALL_GEQRF = 0, RLB200_QRTALL_CHOLQR = 1, RLB200_QRTALL_GEQRT = 2 };
+RLB200_API int rlb200_bqrrp_f64_dev(rlb200_ctx* ctx, int64_t m, int64_t n, double* A_dev, int64_t lda, double d_factor, int64_t block_size,
+                         int qrcp_wide, int qr_tall, double* tau_dev, int64_t* J_dev, int64_t* rank, uint32_t state[6]);
+RLB200_API int rlb200_bqrrp_f32_dev(rlb200_ctx* ctx, int64_t m, int64_t n, float* A_dev, int64_t lda, float d_factor, int64_t block_size,
+                         int qrcp_wide, int qr_tall, float* tau_dev, int64_t* J_dev, int64_t* rank, uint32_t state[6]);
+/* Host-pointer form (the CPU reference's calling convention): A, tau, J are HOST buffers. */
+RLB200_API int rlb200_bqrrp_f64_host(rlb200_ctx* ctx, int64_t m, int64_t n, double* A, int64_t lda, double d_factor, int64_t block_size,
+                          int qrcp_wide, int qr_tall, double* tau, int64_t* J, int64_t* rank, uint32_t state[6]);
+RLB200_API int rlb200_bqrrp_f32_host(rlb200_ctx* ctx, int64_t m, int64_t n, float* A, int64_t lda, float d_factor, int64_t block_size,
+                          int qrcp_wide, int qr_tall, float* tau, int64_t* J, int64_t* rank, uint32_t state[6]);
+
 /* ---- lapack::geqp3 / geqrf of a small (L2-resident) d x n matrix, as used on the sketch (rl_cqrrpt.hh:247, rl_bqrrp.hh:336,356).
  * pivot != 0: J_dev receives n 1-based pivots (all columns free on entry, i.e. LAPACK's jpvt = 0 convention of the call sites). */
 RLB200_API int rlb200_qr_small_f64_dev(rlb200_ctx* ctx, int pivot, int64_t d, int64_t n, double* A_dev, int64_t lda, int64_t* J_dev,

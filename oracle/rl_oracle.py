@@ -553,3 +553,140 @@ class CQRRPT:
         A[:, :new_rank] = trsm_(1.0, _F(R[:new_rank, :new_rank]), _F(A[:, :new_rank]), side=1, lower=0)   # :342
         R[:new_rank, :] = R[:new_rank, :] @ np.triu(A_hat[:n, :n])                  # trmm :349
         return 0, A, R, J, state
+
+
+# --------------------------------------------------------------------------------------------
+# BQRRP (RandLAPACK/drivers/rl_bqrrp.hh:154-665)
+# --------------------------------------------------------------------------------------------
+def orhr_col(Q):
+    """LAPACK dorhr_col with a single T block (NB >= n), restated: Householder reconstruction of an m x n matrix with
+    orthonormal columns.  -> (V unit-lower-trapezoidal m x n, T n x n upper, D (+-1)).
+    Steps (LAPACK 3.9 dorhr_col.f / dlaorhr_col_getrfnp.f): modified LU without pivoting Q1 - S = L1 U1 with
+    S = diag(D), D_i = -sign of the i-th pivot; V2 = Q2 U1^-1; T = (-U1 S) V1^-T.  Used at rl_bqrrp.hh:466."""
+    from scipy.linalg import solve_triangular
+    Q = np.array(Q, dtype=Q.dtype, order="F", copy=True)
+    m, n = Q.shape
+    D = np.zeros(n, dtype=Q.dtype)
+    for i in range(n):
+        D[i] = -np.copysign(1.0, Q[i, i])
+        Q[i, i] -= D[i]
+        Q[i + 1:n, i] *= Q.dtype.type(1.0) / Q[i, i]
+        Q[i + 1:n, i + 1:n] -= np.outer(Q[i + 1:n, i], Q[i, i + 1:n])
+    U1 = np.triu(Q[:n, :n])
+    V1 = np.tril(Q[:n, :n], -1) + np.eye(n, dtype=Q.dtype)
+    if m > n:
+        Q[n:, :] = solve_triangular(U1, Q[n:, :].T, trans="T", lower=False).T
+    V = Q.copy()
+    V[:n, :n] = V1
+    Tm = U1 * np.where(D == 1.0, -1.0, 1.0)[None, :]            # column j scaled by -D_j
+    Tm = solve_triangular(V1, Tm.T, lower=True, unit_diagonal=True).T     # X V1^T = Tm
+    return _F(V), _F(np.triu(Tm)), D
+
+
+class BQRRP:
+    """RandLAPACK::BQRRP(timing, b_sz): fields block_size, tol (= eps), qrcp_wide ('luqr' | 'geqp3'), qr_tall ('geqrf' | 'cholqr'), rank.
+    apply_trans_q = ormqr (applied here through the compact-WY form, which is what ormqr computes)."""
+
+    def __init__(self, b_sz, qrcp_wide="luqr", qr_tall="geqrf"):
+        self.block_size, self.qrcp_wide, self.qr_tall, self.rank = b_sz, qrcp_wide, qr_tall, None
+
+    def call(self, A, d_factor, state: RNGState):
+        """-> (rc, A_out [GEQP3 format], tau, J (1-based), next state)."""
+        A = _F(np.array(A, copy=True))
+        m, n = A.shape
+        dt = A.dtype
+        eps = np.finfo(dt).eps
+        tol = eps
+        tau = np.zeros(n, dtype=dt)
+        J = np.zeros(n, dtype=np.int64)
+        rows, cols, curr, b_sz = m, n, 0, self.block_size
+        maxiter = int(np.ceil(dt.type(min(m, n)) / dt.type(b_sz)))
+        b_const = b_sz
+        d = int(dt.type(d_factor) * dt.type(b_sz))
+        sd = d
+        geqp3, geqrf, getrf, potrf, ormqr = get_lapack_funcs(("geqp3", "geqrf", "getrf", "potrf", "ormqr"), (A,))
+        (trsm_,) = get_blas_funcs(("trsm",), (A,))
+        # sketch (:309-312): the row-major d x m fill_dense buffer is READ as ColMajor with ld = d
+        S, state = fill_dense(d, m, state, dt)                   # natural layout of a wide Long-axis operator = row-major
+        S_used = np.ascontiguousarray(S).reshape(-1).reshape((d, m), order="F")
+        A_sk = _F(S_used @ A)
+        sk0 = 0                                                  # column offset of the live sketch inside A_sk
+
+        def ormqr_apply(V, tau_, C):
+            _, lw, _ = ormqr("L", "T", V, tau_, C, lwork=-1)
+            out, _, info = ormqr("L", "T", V, tau_, C, lwork=int(lw[0]))
+            return out
+
+        for it in range(maxiter):
+            b_sz = min(b_sz, min(m, n) - curr)
+            block_rank = b_sz
+            Ask = A_sk[:sd, sk0:sk0 + cols]
+            if self.qrcp_wide == "geqp3":                        # :335-336
+                qr, jp, tw, _, _ = geqp3(_F(Ask))
+                A_sk[:sd, sk0:sk0 + cols] = qr
+                Jb = np.asarray(jp, dtype=np.int64)
+            else:                                                # :337-357
+                lu, piv, _ = getrf(_F(Ask.T))
+                Jb = np.arange(1, cols + 1, dtype=np.int64)
+                for i in range(min(sd, cols)):
+                    Jb[piv[i]], Jb[i] = Jb[i], Jb[piv[i]]
+                qr, tw, _, _ = geqrf(_F(Ask[:, Jb - 1]))
+                A_sk[:sd, sk0:sk0 + cols] = qr
+            A[:, curr:] = A[:, curr:][:, Jb - 1]                  # :365
+            block_zero = not np.any(np.abs(A[curr:, curr]) > eps)   # :372-379
+            if it == 0:
+                J[:cols] = Jb
+            else:
+                J[curr:curr + cols] = J[curr:curr + cols][Jb - 1]
+            if block_zero:
+                self.rank = curr
+                return 0, A, tau, J, state
+            R_sk = A_sk[:, sk0:]
+            for i in range(b_sz):                                # :421-427
+                if abs(R_sk[i, i]) / abs(R_sk[0, 0]) < tol:
+                    block_rank = i
+                    break
+            P = A[curr:, curr:curr + b_sz]                       # the panel (view)
+            W1 = A[curr:, curr + b_sz:]
+            if self.qr_tall == "cholqr":                         # :441-497
+                br = block_rank
+                X = trsm_(1.0, _F(np.triu(R_sk[:br, :br])), _F(P[:, :br]), side=1, lower=0)
+                G = np.triu(_gemm(X, X, ta=True))
+                c, info = potrf(_F(G), lower=0, clean=1)
+                X = trsm_(1.0, _F(c), X, side=1, lower=0)
+                V, Tm, D = orhr_col(X)
+                Rfull = np.triu(c) * D[:, None]
+                tau[curr:curr + br] = np.diag(Tm)
+                Rpad = np.zeros((br, b_sz), dtype=dt)
+                Rpad[:, :br] = Rfull
+                R11 = Rpad @ np.triu(R_sk[:b_sz, :b_sz])         # trmm :486
+                k_refl, Vk, tk = br, V, np.diag(Tm).copy()
+                P[:, :br] = np.tril(V, -1)
+                P[:br, :b_sz] = np.triu(R11) + np.tril(P[:br, :b_sz], -1)
+            else:                                                # geqrf :498-510
+                qr, tq, _, _ = geqrf(_F(P))
+                P[:, :] = qr
+                tau[curr:curr + len(tq)] = tq
+                k_refl, Vk, tk = block_rank, qr, tq
+            if k_refl > 0 and cols - b_sz > 0:                   # :541-562
+                m_apply = block_rank if block_rank != b_const else rows
+                Vq = _F(np.tril(Vk[:m_apply, :k_refl], -1) + np.eye(m_apply, k_refl, dtype=dt))
+                W1[:m_apply, :] = ormqr_apply(Vq, np.asarray(tk[:k_refl], dtype=dt), _F(W1[:m_apply, :]))
+            curr += b_sz
+            if curr >= min(m, n) or block_rank != b_const:       # :583-598
+                self.rank = curr
+                return 0, A, tau, J, state
+            R11 = np.triu(A[curr - b_sz:curr, curr - b_sz:curr])
+            R12 = A[curr - b_sz:curr, curr:]
+            R_sk[:b_sz, :b_sz] = np.triu(R_sk[:b_sz, :b_sz])     # get_U :605
+            R_sk[:b_sz, :b_sz] = trsm_(1.0, _F(R11), _F(R_sk[:b_sz, :b_sz]), side=1, lower=0)   # :606
+            R_sk[:b_sz, b_sz:cols] -= R_sk[:b_sz, :b_sz] @ R12   # :610
+            sd = min(sd, cols)
+            if sd - b_sz > 0:                                    # :617-618
+                blk = R_sk[b_sz:sd, b_sz:sd]
+                blk[:, :] = np.triu(blk)
+            sk0 += b_sz
+            rows -= b_sz
+            cols -= b_sz
+        self.rank = curr
+        return 0, A, tau, J, state

@@ -16,9 +16,10 @@ from dataclasses import dataclass
 
 from . import _capi
 from ._capi import (STAB_PLUL, STAB_CHOLQRQ, STAB_HQRQ, FAMILY_GAUSSIAN, FAMILY_UNIFORM, AXIS_LONG, AXIS_SHORT,  # noqa: F401
-                    LAYOUT_NATURAL, LAYOUT_COLMAJOR, LAYOUT_ROWMAJOR, StackOpts)
+                    LAYOUT_NATURAL, LAYOUT_COLMAJOR, LAYOUT_ROWMAJOR, StackOpts, QRCP_LUQR, QRCP_GEQP3, QRTALL_GEQRF,
+                    QRTALL_CHOLQR, QRTALL_GEQRT)
 
-__all__ = ["Context", "RNGState", "DenseDist", "fill_dense", "SparseDist", "fill_sparse", "sketch_general_left", "sketch_general_right", "CQRRPT", "qr_small", "col_swap", "CholQRQ", "PLUL", "HQRQ", "RS", "RF", "QB", "RSVD", "empty_f",
+__all__ = ["Context", "RNGState", "DenseDist", "fill_dense", "SparseDist", "fill_sparse", "sketch_general_left", "sketch_general_right", "CQRRPT", "BQRRP", "qr_small", "col_swap", "CholQRQ", "PLUL", "HQRQ", "RS", "RF", "QB", "RSVD", "empty_f",
            "to_f", "Error", "shard_rows"]
 
 
@@ -545,6 +546,48 @@ class CQRRPT:
         state.assign(w)
         self.rank = rank.value
         return rc, R, J
+
+
+class BQRRP:
+    """RandLAPACK::BQRRP(time_subroutines, b_sz) (rl_bqrrp.hh:43-152); public fields block_size, qrcp_wide, qr_tall, rank.
+    Defaults are the reference's (luqr + geqrf); BQRRP_GPU's configuration is qr_tall = QRTALL_CHOLQR."""
+
+    def __init__(self, time_subroutines=False, b_sz=256):
+        if b_sz <= 0:
+            raise Error(_capi.ERR_ARG, "randlapack_require(b_sz > 0)")
+        self.timing, self.block_size, self.rank = time_subroutines, b_sz, None
+        self.qrcp_wide, self.qr_tall = _capi.QRCP_LUQR, _capi.QRTALL_GEQRF
+
+    def call(self, ctx: Context, A, d_factor, state: RNGState, tau=None, J=None):
+        """A (m x n device, column-major) is overwritten GEQP3-style -> (rc, tau (n), J int64 1-based)."""
+        torch = _torch()
+        assert _is_f(A)
+        m, n = A.shape
+        tau = torch.zeros(n, dtype=A.dtype, device=A.device) if tau is None else tau
+        J = torch.zeros(n, dtype=torch.int64, device=A.device) if J is None else J
+        rank = ctypes.c_int64(0)
+        w = state.words()
+        fn = getattr(ctx._lib, f"rlb200_bqrrp_{_suffix(A.dtype)}_dev")
+        rc = ctx.check(fn(ctx._h, m, n, A.data_ptr(), _ld(A), d_factor, self.block_size, self.qrcp_wide, self.qr_tall, tau.data_ptr(),
+                          J.data_ptr(), ctypes.byref(rank), w))
+        state.assign(w)
+        self.rank = rank.value
+        return rc, tau, J
+
+    def call_host(self, ctx: Context, A_host, d_factor, state: RNGState, tau=None, J=None):
+        torch = _torch()
+        assert _is_f(A_host) and not A_host.is_cuda
+        m, n = A_host.shape
+        tau = torch.zeros(n, dtype=A_host.dtype) if tau is None else tau
+        J = torch.zeros(n, dtype=torch.int64) if J is None else J
+        rank = ctypes.c_int64(0)
+        w = state.words()
+        fn = getattr(ctx._lib, f"rlb200_bqrrp_{_suffix(A_host.dtype)}_host")
+        rc = ctx.check(fn(ctx._h, m, n, A_host.data_ptr(), _ld(A_host), d_factor, self.block_size, self.qrcp_wide, self.qr_tall,
+                          tau.data_ptr(), J.data_ptr(), ctypes.byref(rank), w))
+        state.assign(w)
+        self.rank = rank.value
+        return rc, tau, J
 
 
 def qr_small(ctx: Context, A, pivot=True):

@@ -17,6 +17,8 @@ STAB_PLUL, STAB_CHOLQRQ, STAB_HQRQ = 0, 1, 2
 FAMILY_GAUSSIAN, FAMILY_UNIFORM = 0, 1
 AXIS_LONG, AXIS_SHORT = 0, 1
 LAYOUT_NATURAL, LAYOUT_COLMAJOR, LAYOUT_ROWMAJOR = 0, 1, 2
+QRCP_LUQR, QRCP_GEQP3 = 0, 1
+QRTALL_GEQRF, QRTALL_CHOLQR, QRTALL_GEQRT = 0, 1, 2
 TIMER_GEMM_NN, TIMER_GEMM_TN, TIMER_RIGHTMUL, TIMER_SMALL, TIMER_FILL, TIMER_SKETCH, TIMER_FACTOR = 0, 1, 2, 3, 4, 5, 6
 
 c_i64, c_i32, c_u32, c_int, c_vp = ctypes.c_int64, ctypes.c_int32, ctypes.c_uint32, ctypes.c_int, ctypes.c_void_p
@@ -42,6 +44,7 @@ _F = lambda ft: {  # noqa: E731  typed entry points, ft = ctypes float type
     "rsvd": (c_int, [c_vp, c_i64, c_i64, c_vp, P_i64, ft, c_vp, c_vp, c_vp, c_vp, P_u32, ctypes.POINTER(StackOpts), P_int]),
     "svd_tall": (c_int, [c_vp, c_i64, c_i64, c_vp, c_vp, c_vp]),
     "cqrrpt": (c_int, [c_vp, c_i64, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, ft, ft, c_i64, P_i64, P_u32]),
+    "bqrrp": (c_int, [c_vp, c_i64, c_i64, c_vp, c_i64, ft, c_i64, c_int, c_int, c_vp, c_vp, P_i64, P_u32]),
     "qr_small": (c_int, [c_vp, c_int, c_i64, c_i64, c_vp, c_i64, c_vp, c_vp]),
     "col_swap": (c_int, [c_vp, c_i64, c_i64, c_vp, c_i64, c_vp]),
     "fill_sparse": (c_int, [c_vp, c_i64, c_i64, c_i64, c_int, c_i64, c_i64, c_i64, c_i64, P_i64, c_vp, c_vp, c_vp, P_u32]),
@@ -72,6 +75,7 @@ for _suf, _ft in (("f64", ctypes.c_double), ("f32", ctypes.c_float)):
     for _name, _sig in _F(_ft).items():
         SIGNATURES[f"rlb200_{_name}_{_suf}_dev"] = _sig
     SIGNATURES[f"rlb200_cqrrpt_{_suf}_host"] = (c_int, [c_vp, c_i64, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, _ft, _ft, c_i64, P_i64, P_u32])
+    SIGNATURES[f"rlb200_bqrrp_{_suf}_host"] = (c_int, [c_vp, c_i64, c_i64, c_vp, c_i64, _ft, c_i64, c_int, c_int, c_vp, c_vp, P_i64, P_u32])
     SIGNATURES[f"rlb200_rsvd_{_suf}_host"] = (c_int, [c_vp, c_i64, c_i64, c_vp, P_i64, _ft, c_vp, c_vp, c_vp, P_u32,
                                                       ctypes.POINTER(StackOpts), P_int])
 

@@ -1,0 +1,476 @@
+// BQRRP on device: BQRRP::call (RandLAPACK/drivers/rl_bqrrp.hh:154-665) — blocked QR with randomised column pivoting.
+// Output format is GEQP3's: A holds R (upper) and the Householder vectors, tau, J (1-based), rank.
+//
+// Per panel (block size b) the reference does: QRCP of the d x cols sketch (LU-based `luqr` or geqp3), column swap of the trailing
+// matrix, rank estimate, panel QR (geqrf | CholQR + Householder reconstruction orhr_col | geqrt), Q^T applied to the trailing
+// matrix (ormqr | gemqrt), sketch update.  Here:
+//   * the Gaussian sketch S A is formed with S regenerated panel-by-panel from the Philox state (never materialised as a whole);
+//   * every O(rows * cols * b) operation — preconditioning solves, Gram matrices, Householder reconstruction's V2 = Q2 U^-1,
+//     and above all the trailing update C <- (I - V T V^T)^T C — runs as tall DMMA GEMMs (compact WY form);
+//   * the b x b pieces (modified LU of orhr_col, T factor, larft) are one-CTA kernels;
+//   * pivot decisions are made on the device; only pivot vectors / rank scalars (O(n) integers per panel) travel to the host.
+#include "drivers.cuh"
+#include "philox.cuh"
+#include <algorithm>
+#include <cmath>
+#include <limits>
+#include <numeric>
+
+namespace rlb {
+
+#define RLB_ALLOC_(p) do { if (!(p)) return RLB200_ERR_ALLOC; } while (0)
+
+// ---- small kernels -----------------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) transpose_kernel(int64_t rows, int64_t cols, const T* __restrict__ A, int64_t lda, T* __restrict__ B, int64_t ldb) {
+    __shared__ T tile[32][33];
+    const int64_t bi = (int64_t)blockIdx.x * 32, bj = (int64_t)blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (int r = ty; r < 32; r += 8) {
+        const int64_t i = bi + tx, j = bj + r;
+        tile[r][tx] = (i < rows && j < cols) ? A[i + j * lda] : (T)0;
+    }
+    __syncthreads();
+    for (int r = ty; r < 32; r += 8) {
+        const int64_t j = bj + tx, i = bi + r;
+        if (i < rows && j < cols) B[j + i * ldb] = tile[tx][r];
+    }
+}
+// B (cols x rows, ldb) = A^T, A rows x cols (lda)   (util::transposition, rl_util.hh:314-334)
+template <typename T>
+int transpose(Ctx* ctx, int64_t rows, int64_t cols, const T* A, int64_t lda, T* B, int64_t ldb) {
+    if (rows == 0 || cols == 0) return 0;
+    LaunchScope ls(ctx, RLB200_TIMER_SMALL);
+    dim3 grid((unsigned)((rows + 31) / 32), (unsigned)((cols + 31) / 32));
+    RLB_REQUIRE(ctx, grid.y < 65536);
+    transpose_kernel<T><<<grid, 256, 0, ctx->stream>>>(rows, cols, A, lda, B, ldb);
+    RLB_CUDA_OK(ctx, cudaGetLastError());
+    return 0;
+}
+
+// flag <- any(|x[i]| > thr), i < n   (rl_bqrrp.hh:373-379)
+template <typename T>
+__global__ void __launch_bounds__(256) any_above_kernel(const T* __restrict__ x, int64_t n, double thr, int* __restrict__ flag) {
+    bool f = false;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) f |= fabs((double)x[i]) > thr;
+    if (__syncthreads_or(f) && threadIdx.x == 0) atomicOr(flag, 1);
+}
+
+// unit-lower-triangular clean copy of the leading n x n block: dst[i][j] = (i > j) ? src[i][j] : (i == j)
+template <typename T>
+__global__ void __launch_bounds__(256) unit_lower_kernel(int n, const T* __restrict__ src, int64_t lds, T* __restrict__ dst, int ldd) {
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n * n; e += gridDim.x * blockDim.x) {
+        const int i = e % n, j = e / n;
+        dst[i + (size_t)j * ldd] = i > j ? src[i + (int64_t)j * lds] : (i == j ? (T)1 : (T)0);
+    }
+}
+
+// LAPACK dlaorhr_col_getrfnp: modified LU without pivoting of the n x n block: A - S = L U, S = diag(D), D(i) = -sign(A(i,i)).
+template <typename T>
+__global__ void __launch_bounds__(1024) orhr_getrfnp_kernel(int n, T* __restrict__ A, int64_t lda, T* __restrict__ D) {
+    __shared__ double s_piv;
+    for (int i = 0; i < n; ++i) {
+        if (threadIdx.x == 0) {
+            const double aii = (double)A[i + (int64_t)i * lda];
+            const double dsgn = -copysign(1.0, aii);
+            D[i] = (T)dsgn;
+            const double p = aii - dsgn;
+            A[i + (int64_t)i * lda] = (T)p;
+            s_piv = (double)(T)p;
+        }
+        __syncthreads();
+        const double rp = 1.0 / s_piv;
+        for (int r = i + 1 + threadIdx.x; r < n; r += blockDim.x) A[r + (int64_t)i * lda] = (T)((double)A[r + (int64_t)i * lda] * rp);
+        __syncthreads();
+        const int w = n - i - 1;
+        for (int e = threadIdx.x; e < w * w; e += blockDim.x) {
+            const int r = i + 1 + e % w, c = i + 1 + e / w;
+            A[r + (int64_t)c * lda] = (T)((double)A[r + (int64_t)c * lda] - (double)A[r + (int64_t)i * lda] * (double)A[i + (int64_t)c * lda]);
+        }
+        __syncthreads();
+    }
+}
+
+// T (n x n upper, ldt; strictly-lower part zeroed) = (-U S) V1^{-T}  (dorhr_col steps 2-1 .. 2-4 with one block);
+// U = upper triangle of A (incl. diagonal), V1 = unit lower triangle of A.  Row i of T only depends on row i: one thread per row.
+template <typename T>
+__global__ void __launch_bounds__(256) orhr_tfactor_kernel(int n, const T* __restrict__ A, int64_t lda, const T* __restrict__ D, T* __restrict__ Tm, int ldt,
+                                                           T* __restrict__ tau) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    for (int j = 0; j < i; ++j) Tm[i + (size_t)j * ldt] = (T)0;
+    for (int j = i; j < n; ++j) {
+        const double u = (double)A[i + (int64_t)j * lda];
+        double acc = ((double)D[j] == 1.0) ? -u : u;
+        for (int l = i; l < j; ++l) acc -= (double)Tm[i + (size_t)l * ldt] * (double)A[j + (int64_t)l * lda];
+        Tm[i + (size_t)j * ldt] = (T)acc;
+        if (j == i && tau) tau[i] = (T)acc;
+    }
+}
+
+// rows of the upper triangle scaled by D: R[j][i] *= D[j] for j <= i   (rl_bqrrp.hh:471-473)
+template <typename T>
+__global__ void __launch_bounds__(256) scale_rows_upper_kernel(int n, T* __restrict__ R, int ldr, const T* __restrict__ D) {
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n * n; e += gridDim.x * blockDim.x) {
+        const int j = e % n, i = e / n;
+        if (j <= i) R[j + (size_t)i * ldr] *= D[j];
+    }
+}
+
+// LAPACK larft (Forward, Columnwise) from the Gram matrix G = V^T V (upper part used) and tau; one thread per row of T is not
+// possible (column i needs all of T[0:i,0:i]), so: sequential over columns, threads over rows.
+template <typename T>
+__global__ void __launch_bounds__(1024) larft_gram_kernel(int k, const T* __restrict__ G, int ldg, const T* __restrict__ tau, T* __restrict__ Tm, int ldt) {
+    extern __shared__ double sh[];   // w[k]
+    for (int i = 0; i < k; ++i) {
+        const double ti = (double)tau[i];
+        // w = -tau_i * G[0:i, i]
+        for (int r = threadIdx.x; r < i; r += blockDim.x) sh[r] = -ti * (double)G[r + (size_t)i * ldg];
+        __syncthreads();
+        // T[0:i, i] = T[0:i,0:i] * w   (upper triangular)
+        for (int r = threadIdx.x; r < k; r += blockDim.x) {
+            if (r < i) {
+                double acc = 0.0;
+                for (int l = r; l < i; ++l) acc += (double)Tm[r + (size_t)l * ldt] * sh[l];
+                Tm[r + (size_t)i * ldt] = (T)acc;
+            } else {
+                Tm[r + (size_t)i * ldt] = (r == i) ? (T)ti : (T)0;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+template <typename T>
+int make_unit_lower(Ctx* ctx, int64_t n, const T* src, int64_t lds, T* dst, int64_t ldd) {
+    if (n == 0) return 0;
+    LaunchScope ls(ctx, RLB200_TIMER_SMALL);
+    unit_lower_kernel<T><<<(unsigned)std::min<int64_t>((n * n + 255) / 256, 1024), 256, 0, ctx->stream>>>((int)n, src, lds, dst, (int)ldd);
+    RLB_CUDA_OK(ctx, cudaGetLastError());
+    return 0;
+}
+// Tm (k x k upper, ldt; strictly-lower part zeroed) = larft(Forward, Columnwise) given G = V^T V and tau
+template <typename T>
+int larft_from_gram(Ctx* ctx, int64_t k, const T* G, int64_t ldg, const T* tau, T* Tm, int64_t ldt) {
+    if (k == 0) return 0;
+    LaunchScope ls(ctx, RLB200_TIMER_SMALL);
+    larft_gram_kernel<T><<<1, 1024, sizeof(double) * k, ctx->stream>>>((int)k, G, (int)ldg, tau, Tm, (int)ldt);
+    RLB_CUDA_OK(ctx, cudaGetLastError());
+    return 0;
+}
+// in place on the top n x n block: strictly-upper part <- 0, diagonal <- dval
+template <typename T>
+__global__ void __launch_bounds__(256) set_upper_diag_kernel(int n, T* __restrict__ A, int64_t lda, T dval, int add_to_diag) {
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n * n; e += gridDim.x * blockDim.x) {
+        const int i = e % n, j = e / n;
+        if (add_to_diag) { if (i == j) A[i + (int64_t)j * lda] += dval; }
+        else if (i < j) A[i + (int64_t)j * lda] = (T)0;
+        else if (i == j) A[i + (int64_t)j * lda] = dval;
+    }
+}
+template <typename T>
+int set_upper_diag(Ctx* ctx, int64_t n, T* A, int64_t lda, T dval, bool add_to_diag) {
+    if (n == 0) return 0;
+    LaunchScope ls(ctx, RLB200_TIMER_SMALL);
+    set_upper_diag_kernel<T><<<(unsigned)std::min<int64_t>((n * n + 255) / 256, 1024), 256, 0, ctx->stream>>>((int)n, A, lda, dval, add_to_diag ? 1 : 0);
+    RLB_CUDA_OK(ctx, cudaGetLastError());
+    return 0;
+}
+
+// ---- the sketch: A_sk (d x n, ld d) = S_used * A with S = fill_dense(DenseDist(d, m)) read as ColMajor d x m, ld d (rl_bqrrp.hh:309-312)
+template <typename T>
+int fill_dense_launch(Ctx* ctx, int family, int64_t n_cols_parent, T* out, int64_t nr, int64_t nc, int64_t ptr, int64_t rs, int64_t cs,
+                      const uint32_t state[6], uint32_t next_ctr[4]);
+
+// P[0 .. f1-f0) = parent-order entries f0 .. f1-1 of the d x m row-major operator buffer
+template <typename T>
+static int fill_flat_range(Ctx* ctx, int64_t m, int64_t f0, int64_t f1, T* P, const uint32_t state[6]) {
+    uint32_t nx[4];
+    int64_t f = f0;
+    while (f < f1) {
+        const int64_t c0 = f % m;
+        if (c0 != 0 || f1 - f < m) {           // partial row
+            const int64_t len = std::min(f1 - f, m - c0);
+            RLB_CHECK(fill_dense_launch<T>(ctx, RLB200_FAMILY_GAUSSIAN, m, P + (f - f0), 1, len, f, len, 1, state, nx));
+            f += len;
+        } else {                               // a run of full rows
+            const int64_t nrows = (f1 - f) / m;
+            RLB_CHECK(fill_dense_launch<T>(ctx, RLB200_FAMILY_GAUSSIAN, m, P + (f - f0), nrows, m, f, m, 1, state, nx));
+            f += nrows * m;
+        }
+    }
+    return 0;
+}
+
+template <typename T>
+static int bqrrp_sketch(Ctx* ctx, int64_t d, int64_t m, int64_t n, const T* A, int64_t lda, T* A_sk, uint32_t state[6]) {
+    int64_t pc = std::max<int64_t>(64, (int64_t)(((size_t)32 << 20) / sizeof(T)) / std::max<int64_t>(d, 1));
+    pc = std::min<int64_t>((pc / 64) * 64, m);
+    ArenaScope as(ctx);
+    T* panel = as.take<T>((size_t)2 * d * pc); if (!panel) return RLB200_ERR_ALLOC;
+    int buf = 0;
+    for (int64_t j0 = 0; j0 < m; j0 += pc, buf ^= 1) {
+        const int64_t w = std::min(pc, m - j0);
+        T* P = panel + (size_t)buf * d * pc;
+        RLB_CHECK(fill_flat_range<T>(ctx, m, j0 * d, (j0 + w) * d, P, state));
+        RLB_CHECK(gemm_nn<T>(ctx, d, n, w, 1.0, P, d, A + j0, lda, j0 == 0 ? 0.0 : 1.0, A_sk, d));
+    }
+    // state = fill_dense(D, S, state): next state of the full d x m operator (dense_skops.hh:169-182)
+    Ctr128 c;
+    for (int i = 0; i < 4; ++i) c.v[i] = state[i];
+    const int64_t major = std::max(d, m), minor = std::min(d, m);
+    c = ctr_add(c, (uint64_t)(((major + 3) / 4) * minor));
+    for (int i = 0; i < 4; ++i) state[i] = c.v[i];
+    return 0;
+}
+
+// ---- geqrf of the wide sketch (sd x cols, sd <= cols typically): Householder QR of the leading square block with the identity
+// appended so that Q^T comes out explicitly, then R12 = Q^T A12 as one GEMM (instead of cols rank-1 updates per column).
+template <typename T>
+static int geqrf_wide(Ctx* ctx, int64_t sd, int64_t cols, T* A, int64_t lda, T* tau, void* qr_ws) {
+    const int64_t kq = std::min(sd, cols);
+    if (cols <= 2 * sd || sd < 16) return qr_small<T>(ctx, false, sd, cols, A, lda, nullptr, tau, qr_ws);
+    ArenaScope as(ctx);
+    T* W = as.take<T>((size_t)sd * 2 * sd); if (!W) return RLB200_ERR_ALLOC;       // [A11 | I]
+    RLB_CUDA_OK(ctx, cudaMemcpy2DAsync(W, sd * sizeof(T), A, lda * sizeof(T), sd * sizeof(T), sd, cudaMemcpyDeviceToDevice, ctx->stream));
+    RLB_CUDA_OK(ctx, cudaMemsetAsync(W + sd * sd, 0, sizeof(T) * sd * sd, ctx->stream));
+    {
+        LaunchScope ls(ctx, RLB200_TIMER_SMALL);
+        unit_lower_kernel<T><<<(unsigned)std::min<int64_t>((sd * sd + 255) / 256, 1024), 256, 0, ctx->stream>>>((int)sd, W + sd * sd, sd, W + sd * sd, (int)sd);
+    }
+    RLB_CHECK(qr_small<T>(ctx, false, sd, 2 * sd, W, sd, nullptr, tau, qr_ws));      // W = [R11 \ V | Q^T]
+    RLB_CUDA_OK(ctx, cudaMemcpy2DAsync(A, lda * sizeof(T), W, sd * sizeof(T), sd * sizeof(T), sd, cudaMemcpyDeviceToDevice, ctx->stream));
+    const int64_t rest = cols - sd;
+    T* tmp = as.take<T>((size_t)sd * rest); if (!tmp) return RLB200_ERR_ALLOC;
+    RLB_CHECK(gemm_nn<T>(ctx, sd, rest, sd, 1.0, W + sd * sd, sd, A + sd * lda, lda, 0.0, tmp, sd));
+    RLB_CUDA_OK(ctx, cudaMemcpy2DAsync(A + sd * lda, lda * sizeof(T), tmp, sd * sizeof(T), sd * sizeof(T), rest, cudaMemcpyDeviceToDevice, ctx->stream));
+    (void)kq;
+    return 0;
+}
+
+// C (rows x nc, ldc) <- (I - V Tm V^T)^T C, V = [V1 (k x k unit lower, clean, ld k); V2 ((rows - k) x k, ldv)], Tm k x k upper (ldt).
+// W, W2: k x nc scratch.
+template <typename T>
+static int apply_qt_wy(Ctx* ctx, int64_t rows, int64_t k, int64_t nc, const T* V1c, const T* V2, int64_t ldv, const T* Tm, int64_t ldt, T* C,
+                       int64_t ldc, T* W, T* W2) {
+    if (nc == 0 || k == 0) return 0;
+    RLB_CHECK(gemm_tn<T>(ctx, k, k, nc, 1.0, V1c, k, C, ldc, 0.0, W, k, 0));                                  // W = V1^T C1
+    if (rows > k) RLB_CHECK(gemm_tn<T>(ctx, rows - k, k, nc, 1.0, V2, ldv, C + k, ldc, 1.0, W, k, 0));        //   + V2^T C2
+    RLB_CHECK(gemm_tn<T>(ctx, k, k, nc, 1.0, Tm, ldt, W, k, 0.0, W2, k, 0));                                  // W2 = T^T W
+    RLB_CHECK(gemm_nn<T>(ctx, k, nc, k, -1.0, V1c, k, W2, k, 1.0, C, ldc));                                   // C1 -= V1 W2
+    if (rows > k) RLB_CHECK(gemm_nn<T>(ctx, rows - k, nc, k, -1.0, V2, ldv, W2, k, 1.0, C + k, ldc));         // C2 -= V2 W2
+    return 0;
+}
+
+template <typename T>
+static int read_diag_host(Ctx* ctx, const T* M, int64_t ld, int64_t k, std::vector<T>& out) {
+    out.resize((size_t)k);
+    if (k == 0) return 0;
+    RLB_CUDA_OK(ctx, cudaMemcpy2DAsync(out.data(), sizeof(T), M, (ld + 1) * sizeof(T), sizeof(T), k, cudaMemcpyDeviceToHost, ctx->stream));
+    RLB_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+template <typename T>
+int getrf_pivots(Ctx* ctx, int64_t m, int64_t n, T* A, int64_t lda, void* ws, std::vector<int64_t>& ipiv_host);
+
+// ---- the driver --------------------------------------------------------------------------------------------------------------
+template <typename T>
+int bqrrp_call(Ctx* ctx, int64_t m, int64_t n, T* A, int64_t lda, T d_factor, int64_t block_size, int qrcp_wide, int qr_tall, T* tau,
+               int64_t* J_dev, int64_t* rank_out, uint32_t state[6]) {
+    // rl_bqrrp.hh:172-178 and the constructor's requirement :66
+    RLB_REQUIRE(ctx, block_size > 0);
+    RLB_REQUIRE(ctx, m >= 0);
+    RLB_REQUIRE(ctx, n >= 0);
+    RLB_REQUIRE(ctx, lda >= m);
+    RLB_REQUIRE(ctx, d_factor >= (T)1.0);
+    RLB_REQUIRE(ctx, !(A == nullptr && m > 0 && n > 0));
+    RLB_REQUIRE(ctx, !(tau == nullptr && n > 0));
+    RLB_REQUIRE(ctx, !(J_dev == nullptr && n > 0));
+    RLB_REQUIRE(ctx, rank_out != nullptr);
+    if (ctx->m_global >= 0) { ctx->err = "BQRRP is not row-shardable (column pivoting couples all rows): replicas only"; return RLB200_ERR_UNSUPPORTED; }
+    *rank_out = 0;
+    if (m == 0 || n == 0) return 0;
+    const T eps = std::numeric_limits<T>::epsilon();
+    const T tol = eps;                                                                  // ctor default :69
+    int64_t rows = m, cols = n, curr_sz = 0, b_sz = block_size;
+    const int64_t maxiter = (int64_t)std::ceil((T)std::min(m, n) / (T)b_sz);            // :201
+    const int64_t b_const = b_sz;
+    const int64_t d = (int64_t)(d_factor * (T)b_sz);                                    // :205
+    int64_t sd = d;
+    RLB_REQUIRE(ctx, d <= m);   // DenseDist(d, m) is read as a wide operator (rl_bqrrp.hh:309-312)
+
+    ArenaScope as(ctx);
+    T* A_sk0 = as.take<T>((size_t)d * n); RLB_ALLOC_(A_sk0);
+    T* A_sk_trans = qrcp_wide == 0 ? as.take<T>((size_t)n * d) : nullptr; if (qrcp_wide == 0) RLB_ALLOC_(A_sk_trans);
+    T* R_tall = as.take<T>((size_t)b_const * b_const); RLB_ALLOC_(R_tall);
+    T* T_dat = as.take<T>((size_t)b_const * b_const); RLB_ALLOC_(T_dat);
+    T* V1c = as.take<T>((size_t)b_const * b_const); RLB_ALLOC_(V1c);
+    T* Gs = as.take<T>((size_t)b_const * b_const); RLB_ALLOC_(Gs);
+    T* Dv = as.take<T>((size_t)b_const); RLB_ALLOC_(Dv);
+    T* Work2 = as.take<T>((size_t)std::max<int64_t>(n, 2 * d)); RLB_ALLOC_(Work2);
+    T* Wa = as.take<T>((size_t)b_const * n); RLB_ALLOC_(Wa);
+    T* Wb = as.take<T>((size_t)b_const * n); RLB_ALLOC_(Wb);
+    int64_t* Jbuf_dev = as.take<int64_t>((size_t)n); RLB_ALLOC_(Jbuf_dev);
+    int* flag_dev = as.take<int>(1); RLB_ALLOC_(flag_dev);
+    void* qr_ws = arena_push(ctx, qrcp_ws_bytes(std::max<int64_t>(n, 2 * d))); RLB_ALLOC_(qr_ws);
+    void* lu_ws = arena_push(ctx, plul_ws_bytes(ctx, d)); RLB_ALLOC_(lu_ws);
+    RLB_CUDA_OK(ctx, cudaMemsetAsync(R_tall, 0, sizeof(T) * b_const * b_const, ctx->stream));
+    RLB_CUDA_OK(ctx, cudaMemsetAsync(T_dat, 0, sizeof(T) * b_const * b_const, ctx->stream));
+
+    std::vector<int64_t> J((size_t)n, 0), J_buffer((size_t)n, 0), ipiv;
+    auto finish = [&](int64_t rank) -> int {
+        *rank_out = rank;
+        RLB_CUDA_OK(ctx, cudaMemcpyAsync(J_dev, J.data(), sizeof(int64_t) * n, cudaMemcpyHostToDevice, ctx->stream));
+        RLB_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+        return 0;
+    };
+
+    // Gaussian sketch (:309-312)
+    RLB_CHECK(bqrrp_sketch<T>(ctx, d, m, n, A, lda, A_sk0, state));
+    T* A_sk = A_sk0;
+    T* A_work = A;
+
+    for (int64_t iter = 0; iter < maxiter; ++iter) {
+        b_sz = std::min(b_sz, std::min(m, n) - curr_sz);                                // :320
+        int64_t block_rank = b_sz;
+        // ---- qrcp_wide (:335-357)
+        if (qrcp_wide == 1) {
+            RLB_CHECK(qr_small<T>(ctx, true, sd, cols, A_sk, d, Jbuf_dev, Work2, qr_ws));
+            RLB_CUDA_OK(ctx, cudaMemcpyAsync(J_buffer.data(), Jbuf_dev, sizeof(int64_t) * cols, cudaMemcpyDeviceToHost, ctx->stream));
+            RLB_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+        } else {
+            RLB_CHECK(transpose<T>(ctx, sd, cols, A_sk, d, A_sk_trans, n));
+            RLB_CHECK(getrf_pivots<T>(ctx, cols, sd, A_sk_trans, n, lu_ws, ipiv));
+            std::iota(J_buffer.begin(), J_buffer.begin() + cols, (int64_t)1);
+            for (int64_t i = 0; i < std::min(sd, cols); ++i) std::swap(J_buffer[ipiv[i]], J_buffer[i]);
+            std::vector<int64_t> p0((size_t)cols);
+            for (int64_t i = 0; i < cols; ++i) p0[i] = J_buffer[i] - 1;
+            RLB_CHECK(col_permute<T>(ctx, sd, cols, A_sk, d, p0.data()));
+            RLB_CHECK(geqrf_wide<T>(ctx, sd, cols, A_sk, d, Work2, qr_ws));
+        }
+        // ---- pivot the trailing columns of A over all m rows (:365)
+        {
+            std::vector<int64_t> p0((size_t)cols);
+            for (int64_t i = 0; i < cols; ++i) p0[i] = J_buffer[i] - 1;
+            RLB_CHECK(col_permute<T>(ctx, m, cols, A + lda * curr_sz, lda, p0.data()));
+        }
+        // ---- zero-block test on the first pivoted column (:372-379)
+        RLB_CUDA_OK(ctx, cudaMemsetAsync(flag_dev, 0, sizeof(int), ctx->stream));
+        {
+            LaunchScope ls(ctx, RLB200_TIMER_SMALL);
+            any_above_kernel<T><<<(unsigned)std::min<int64_t>((rows + 255) / 256, 1024), 256, 0, ctx->stream>>>(A_work, rows, (double)eps, flag_dev);
+        }
+        int nonzero = 0;
+        RLB_CUDA_OK(ctx, cudaMemcpyAsync(ctx->hbox, flag_dev, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        RLB_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+        nonzero = *static_cast<int*>(ctx->hbox);
+        // ---- update the global pivot vector (:382-387, 407-411)
+        if (iter == 0) std::copy(J_buffer.begin(), J_buffer.begin() + cols, J.begin());
+        else {
+            std::vector<int64_t> old(J.begin() + curr_sz, J.begin() + curr_sz + cols);
+            for (int64_t i = 0; i < cols; ++i) J[curr_sz + i] = old[J_buffer[i] - 1];
+        }
+        if (!nonzero) return finish(curr_sz);                                           // :381-402
+        T* Work1 = A_work + lda * b_sz;
+        T* R_sk = A_sk;
+        // ---- naive rank estimate on the sketch's R (:421-427)
+        {
+            std::vector<T> dg;
+            RLB_CHECK(read_diag_host<T>(ctx, R_sk, d, b_sz, dg));
+            for (int64_t i = 0; i < b_sz; ++i)
+                if (std::abs(dg[i]) / std::abs(dg[0]) < tol) { block_rank = i; break; }
+        }
+        T* tau_sub = tau + curr_sz;
+        const int64_t nc = cols - b_sz;
+        const int64_t m_apply = (block_rank != b_const) ? block_rank : rows;          // :549-561
+        int64_t k_refl = block_rank;
+        if (qr_tall == 1 && block_rank > 0) {
+            // ---- CholQR + Householder reconstruction (:441-497)
+            const int64_t br = block_rank;
+            RLB_CHECK(trsm_right_upper<T>(ctx, rows, br, R_sk, d, A_work, lda));
+            RLB_CUDA_OK(ctx, cudaMemsetAsync(Gs, 0, sizeof(T) * br * br, ctx->stream));
+            RLB_CHECK(gemm_tn<T>(ctx, rows, br, br, 1.0, A_work, lda, A_work, lda, 0.0, Gs, br, 1));
+            int info = 0;
+            RLB_CHECK(potrf_blocked<T>(ctx, br, Gs, br, &info));                       // failure is not checked by the reference (:447-448)
+            RLB_CUDA_OK(ctx, cudaMemsetAsync(R_tall, 0, sizeof(T) * b_const * b_const, ctx->stream));
+            RLB_CHECK(tri_op<T>(ctx, 0, br, br, Gs, br, R_tall, b_const));
+            RLB_CHECK(trsm_right_upper<T>(ctx, rows, br, R_tall, b_const, A_work, lda));
+            // orhr_col(rows, br, nb, A_work, lda, T_dat, b_const, D) (:466)
+            {
+                LaunchScope ls(ctx, RLB200_TIMER_SMALL, 4);
+                orhr_getrfnp_kernel<T><<<1, 1024, 0, ctx->stream>>>((int)br, A_work, lda, Dv);
+                if (rows > br) { /* V2 = Q2 U1^{-1} below */ }
+                RLB_CUDA_OK(ctx, cudaGetLastError());
+            }
+            if (rows > br) RLB_CHECK(trsm_right_upper<T>(ctx, rows - br, br, A_work, lda, A_work + br, lda));
+            {
+                LaunchScope ls(ctx, RLB200_TIMER_SMALL, 3);
+                orhr_tfactor_kernel<T><<<(unsigned)((br + 255) / 256), 256, 0, ctx->stream>>>((int)br, A_work, lda, Dv, T_dat, (int)b_const, tau_sub);
+                scale_rows_upper_kernel<T><<<(unsigned)std::min<int64_t>((br * br + 255) / 256, 1024), 256, 0, ctx->stream>>>((int)br, R_tall, (int)b_const, Dv);
+                unit_lower_kernel<T><<<(unsigned)std::min<int64_t>((br * br + 255) / 256, 1024), 256, 0, ctx->stream>>>((int)br, A_work, lda, V1c, (int)br);
+                RLB_CUDA_OK(ctx, cudaGetLastError());
+            }
+            // R11 = R11_full(0:br, :) * R_sk(0:b, 0:b)  (trmm :486) — computed now, stored into A after the trailing update because the
+            // update still needs the reflectors' unit-lower block and reads nothing of R11
+            RLB_CHECK(tri_op<T>(ctx, 2, b_sz, b_sz, R_sk, d, Gs, b_sz));               // clean upper copy of R_sk
+        } else if (block_rank > 0 || qr_tall != 1) {
+            // ---- Householder panel QR (geqrf / geqrt flavours, :429-440, 498-510): b_sz reflectors
+            RLB_CHECK(qr_small<T>(ctx, false, rows, b_sz, A_work, lda, nullptr, tau_sub, qr_ws));
+            k_refl = std::min<int64_t>(block_rank, std::min(rows, b_sz));
+        }
+        // ---- trailing update with k_refl reflectors (:541-562)
+        if (k_refl > 0 && nc > 0) {
+            const int64_t k = k_refl;
+            if (qr_tall != 1) {
+                // T factor from tau: larft on G = V^T V
+                {
+                    LaunchScope ls(ctx, RLB200_TIMER_SMALL);
+                    unit_lower_kernel<T><<<(unsigned)std::min<int64_t>((k * k + 255) / 256, 1024), 256, 0, ctx->stream>>>((int)k, A_work, lda, V1c, (int)k);
+                }
+                RLB_CHECK(gemm_tn<T>(ctx, k, k, k, 1.0, V1c, k, V1c, k, 0.0, Gs, k, 0));
+                if (m_apply > k) RLB_CHECK(gemm_tn<T>(ctx, m_apply - k, k, k, 1.0, A_work + k, lda, A_work + k, lda, 1.0, Gs, k, 0));
+                RLB_CUDA_OK(ctx, cudaMemsetAsync(T_dat, 0, sizeof(T) * b_const * b_const, ctx->stream));
+                LaunchScope ls(ctx, RLB200_TIMER_SMALL);
+                larft_gram_kernel<T><<<1, 1024, sizeof(double) * k, ctx->stream>>>((int)k, Gs, (int)k, tau_sub, T_dat, (int)b_const);
+                RLB_CUDA_OK(ctx, cudaGetLastError());
+            }
+            RLB_CHECK(apply_qt_wy<T>(ctx, m_apply, k, nc, V1c, A_work + k, lda, T_dat, b_const, Work1, lda, Wa, Wb));
+        }
+        if (qr_tall == 1 && block_rank > 0) {
+            // finish R11 (:486-492): (br x b) = R_tall(br x b) * triu(R_sk)(b x b), then lacpy(Upper) into A
+            const int64_t br = block_rank;
+            T* R11n = Wa;   // br x b_sz scratch (the W buffers are free again)
+            T* Rin = Wb;
+            RLB_CUDA_OK(ctx, cudaMemcpy2DAsync(Rin, br * sizeof(T), R_tall, b_const * sizeof(T), br * sizeof(T), b_sz, cudaMemcpyDeviceToDevice, ctx->stream));
+            RLB_CHECK(gemm_nn<T>(ctx, br, b_sz, b_sz, 1.0, Rin, br, Gs, b_sz, 0.0, R11n, br));
+            RLB_CHECK(tri_op<T>(ctx, 0, br, b_sz, R11n, br, A_work, lda));
+        }
+        curr_sz += b_sz;
+        if (curr_sz >= std::min(m, n) || block_rank != b_const) return finish(curr_sz);   // :583-598
+        // ---- update the sketch (:602-628)
+        T* R11 = A_work;
+        T* R12 = R11 + lda * b_sz;
+        A_work = Work1 + b_sz;
+        RLB_CHECK(tri_op<T>(ctx, 1, b_sz, b_sz, R_sk, d, R_sk, d));                                         // get_U
+        RLB_CHECK(trsm_right_upper<T>(ctx, b_sz, b_sz, R11, lda, R_sk, d));                                 // R_sk11 <- R_sk11 R11^{-1}
+        RLB_CHECK(gemm_nn<T>(ctx, b_sz, cols - b_sz, b_sz, -1.0, R_sk, d, R12, lda, 1.0, R_sk + d * b_sz, d));   // R_sk12 -= R_sk11 R12
+        sd = std::min(sd, cols);
+        if (sd - b_sz > 0) RLB_CHECK(tri_op<T>(ctx, 1, sd - b_sz, sd - b_sz, R_sk + (d + 1) * b_sz, d, R_sk + (d + 1) * b_sz, d));
+        A_sk = A_sk + d * b_sz;
+        rows -= b_sz;
+        cols -= b_sz;
+    }
+    return finish(curr_sz);
+}
+
+#define INST(T)                                                                                                      \
+    template int transpose<T>(Ctx*, int64_t, int64_t, const T*, int64_t, T*, int64_t);                               \
+    template int make_unit_lower<T>(Ctx*, int64_t, const T*, int64_t, T*, int64_t);                                  \
+    template int larft_from_gram<T>(Ctx*, int64_t, const T*, int64_t, const T*, T*, int64_t);                        \
+    template int set_upper_diag<T>(Ctx*, int64_t, T*, int64_t, T, bool);                                             \
+    template int bqrrp_call<T>(Ctx*, int64_t, int64_t, T*, int64_t, T, int64_t, int, int, T*, int64_t*, int64_t*, uint32_t*);
+INST(double)
+INST(float)
+
+}  // namespace rlb

@@ -220,6 +220,32 @@ int rlb200_philox_stream_dev(rlb200_ctx* ctx, const uint32_t state[6], int64_t n
         RLB_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));                                                                       \
         return rc;                                                                                                                  \
     }                                                                                                                               \
+    int rlb200_bqrrp_##SUF##_dev(rlb200_ctx* ctx, int64_t m, int64_t n, T* A_dev, int64_t lda, T d_factor, int64_t block_size,      \
+                                 int qrcp_wide, int qr_tall, T* tau_dev, int64_t* J_dev, int64_t* rank, uint32_t state[6]) {        \
+        CTX_OK(ctx); RLB_CHECK(bind(ctx)); RLB_REQUIRE(ctx, state && rank);                                                         \
+        return bqrrp_call<T>(ctx, m, n, A_dev, lda, d_factor, block_size, qrcp_wide, qr_tall, tau_dev, J_dev, rank, state);         \
+    }                                                                                                                               \
+    int rlb200_bqrrp_##SUF##_host(rlb200_ctx* ctx, int64_t m, int64_t n, T* A, int64_t lda, T d_factor, int64_t block_size,         \
+                                  int qrcp_wide, int qr_tall, T* tau, int64_t* J, int64_t* rank, uint32_t state[6]) {               \
+        CTX_OK(ctx); RLB_CHECK(bind(ctx)); RLB_REQUIRE(ctx, state && rank);                                                         \
+        RLB_REQUIRE(ctx, m >= 0 && n >= 0 && lda >= m);                                                                             \
+        *rank = 0;                                                                                                                  \
+        if (m == 0 || n == 0) return bqrrp_call<T>(ctx, m, n, A, lda, d_factor, block_size, qrcp_wide, qr_tall, tau, J, rank, state); \
+        RLB_REQUIRE(ctx, A && tau && J);                                                                                            \
+        ArenaScope as(ctx);                                                                                                         \
+        T* dA = as.take<T>((size_t)m * n); if (!dA) return RLB200_ERR_ALLOC;                                                        \
+        T* dtau = as.take<T>((size_t)n); if (!dtau) return RLB200_ERR_ALLOC;                                                        \
+        int64_t* dJ = as.take<int64_t>((size_t)n); if (!dJ) return RLB200_ERR_ALLOC;                                                \
+        RLB_CUDA_OK(ctx, cudaMemcpy2DAsync(dA, m * sizeof(T), A, lda * sizeof(T), m * sizeof(T), n, cudaMemcpyHostToDevice, ctx->stream)); \
+        RLB_CUDA_OK(ctx, cudaMemcpyAsync(dtau, tau, sizeof(T) * n, cudaMemcpyHostToDevice, ctx->stream));                           \
+        int rc = bqrrp_call<T>(ctx, m, n, dA, m, d_factor, block_size, qrcp_wide, qr_tall, dtau, dJ, rank, state);                  \
+        if (rc < 0) return rc;                                                                                                      \
+        RLB_CUDA_OK(ctx, cudaMemcpy2DAsync(A, lda * sizeof(T), dA, m * sizeof(T), m * sizeof(T), n, cudaMemcpyDeviceToHost, ctx->stream)); \
+        RLB_CUDA_OK(ctx, cudaMemcpyAsync(tau, dtau, sizeof(T) * n, cudaMemcpyDeviceToHost, ctx->stream));                           \
+        RLB_CUDA_OK(ctx, cudaMemcpyAsync(J, dJ, sizeof(int64_t) * n, cudaMemcpyDeviceToHost, ctx->stream));                         \
+        RLB_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));                                                                       \
+        return rc;                                                                                                                  \
+    }                                                                                                                               \
     int rlb200_qr_small_##SUF##_dev(rlb200_ctx* ctx, int pivot, int64_t d, int64_t n, T* A_dev, int64_t lda, int64_t* J_dev,        \
                                     T* tau_dev) {                                                                                   \
         CTX_OK(ctx); RLB_CHECK(bind(ctx));                                                                                          \

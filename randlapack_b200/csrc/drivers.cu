@@ -141,6 +141,33 @@ static int cholqrq(Ctx* ctx, int64_t m, int64_t k, T* A, bool cond_check, bool r
     return 0;
 }
 
+// HQRQ::call (rl_orth.hh:144-164): geqrf + ungqr.  Householder QR of the tall panel, then Q = (I - V T V^T) [I; 0] = E - V (T V1^T)
+// formed in place by one tall tensor-pipe GEMM.
+template <typename T>
+static int hqrq(Ctx* ctx, int64_t m, int64_t k, T* A) {
+    if (m == 0 || k == 0) return 0;
+    const int64_t kk = std::min(m, k);
+    RLB_REQUIRE(ctx, k <= 256 && m >= k);   // (the in-place product needs one CTA tile across all k columns)
+    ArenaScope as(ctx);
+    T* tau = as.take<T>(kk); RLB_ALLOC(ctx, tau);
+    T* G = as.take<T>(kk * kk); RLB_ALLOC(ctx, G);
+    T* Tm = as.take<T>(kk * kk); RLB_ALLOC(ctx, Tm);
+    T* V1 = as.take<T>(kk * kk); RLB_ALLOC(ctx, V1);
+    T* M = as.take<T>(kk * kk); RLB_ALLOC(ctx, M);
+    void* ws = arena_push(ctx, qrcp_ws_bytes(k)); RLB_ALLOC(ctx, ws);
+    RLB_CHECK(qr_small<T>(ctx, false, m, k, A, m, nullptr, tau, ws));
+    RLB_CHECK(set_upper_diag<T>(ctx, kk, A, m, (T)1, false));                       // A <- V (unit lower trapezoidal, clean)
+    RLB_CUDA_OK(ctx, cudaMemsetAsync(G, 0, sizeof(T) * kk * kk, ctx->stream));
+    RLB_CHECK(gemm_tn<T>(ctx, m, kk, kk, 1.0, A, m, A, m, 0.0, G, kk, 0));          // G = V^T V
+    RLB_CUDA_OK(ctx, cudaMemsetAsync(Tm, 0, sizeof(T) * kk * kk, ctx->stream));
+    RLB_CHECK(larft_from_gram<T>(ctx, kk, G, kk, tau, Tm, kk));
+    RLB_CUDA_OK(ctx, cudaMemcpy2DAsync(V1, kk * sizeof(T), A, m * sizeof(T), kk * sizeof(T), kk, cudaMemcpyDeviceToDevice, ctx->stream));
+    RLB_CHECK(gemm_nt<T>(ctx, kk, kk, kk, 1.0, Tm, kk, V1, kk, 0.0, M, kk));        // M = T V1^T
+    RLB_CHECK(gemm_nn_inplace<T>(ctx, m, kk, kk, -1.0, A, m, M, kk));               // A <- -V M
+    RLB_CHECK(set_upper_diag<T>(ctx, kk, A, m, (T)1, true));                        // + [I; 0]
+    return 0;
+}
+
 template <typename T>
 int stab_call(Ctx* ctx, int kind, int64_t m, int64_t k, T* A, bool cond_check, bool rows_sharded, int* chol_fail) {
     RLB_REQUIRE(ctx, m >= 0 && k >= 0);
@@ -155,9 +182,13 @@ int stab_call(Ctx* ctx, int kind, int64_t m, int64_t k, T* A, bool cond_check, b
             void* ws = arena_push(ctx, plul_ws_bytes(ctx, k)); RLB_ALLOC(ctx, ws);
             return plul<T>(ctx, m, k, A, m, ws);   // rl_orth.hh:211-230: always returns 0
         }
-        case RLB200_STAB_HQRQ:
-            ctx->err = "HQRQ stabiliser is not implemented on the device yet (see DESIGN.md, scope table)";
-            return RLB200_ERR_UNSUPPORTED;
+        case RLB200_STAB_HQRQ: {
+            if (rows_sharded && ctx->allreduce) {
+                ctx->err = "HQRQ on a row-sharded iterate needs a TSQR tree; not offered yet (use CholQRQ)";
+                return RLB200_ERR_UNSUPPORTED;
+            }
+            return hqrq<T>(ctx, m, k, A);
+        }
     }
     RLB_REQUIRE(ctx, !"unknown stabiliser kind");
     return RLB200_ERR_ARG;

@@ -64,6 +64,13 @@ size_t qrcp_ws_bytes(int64_t n);
 template <typename T>
 int qr_small(Ctx* ctx, bool pivot, int64_t d, int64_t n, T* A, int64_t lda, int64_t* jpvt_dev, T* tau_dev, void* ws);
 
+template <typename T>
+int make_unit_lower(Ctx* ctx, int64_t n, const T* src, int64_t lds, T* dst, int64_t ldd);
+template <typename T>
+int larft_from_gram(Ctx* ctx, int64_t k, const T* G, int64_t ldg, const T* tau, T* Tm, int64_t ldt);
+template <typename T>
+int set_upper_diag(Ctx* ctx, int64_t n, T* A, int64_t lda, T dval, bool add_to_diag);
+
 // ---- arena: stack allocator for driver-level device buffers ---------------------------------------
 void* arena_push(Ctx* ctx, size_t bytes);          // nullptr on failure (ctx->err set)
 void arena_release(Ctx* ctx, size_t mark_total);   // pop back to a previous mark
@@ -97,5 +104,10 @@ int rsvd_call(Ctx* ctx, int64_t m, int64_t n, T* A, int64_t* k, T tol, T* U, T* 
 template <typename T>
 int cqrrpt_call(Ctx* ctx, int64_t m, int64_t n, T* A, int64_t lda, T* R, int64_t ldr, int64_t* J_dev, T d_factor, T eps, int64_t nnz,
                 int64_t* rank_out, uint32_t state[6]);
+
+// BQRRP::call (rl_bqrrp.hh:154-665).  qrcp_wide: 0 luqr (default), 1 geqp3; qr_tall: 0 geqrf (default), 1 cholqr (+orhr_col), 2 geqrt.
+template <typename T>
+int bqrrp_call(Ctx* ctx, int64_t m, int64_t n, T* A, int64_t lda, T d_factor, int64_t block_size, int qrcp_wide, int qr_tall, T* tau,
+               int64_t* J_dev, int64_t* rank_out, uint32_t state[6]);
 
 }  // namespace rlb

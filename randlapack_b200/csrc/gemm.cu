@@ -378,6 +378,7 @@ int launch_tn(Ctx* ctx, int64_t m, int N1, int N2, double alpha, const T* A, int
     const int64_t slots = (int64_t)ctx->num_sms * MINB;   // CTAs resident at once
     int64_t want = slots / gcd(active, slots);
     while (want * active < 2 * slots) want *= 2;
+    if (active >= 4 * slots) want = 1;   // enough tiles to fill the machine several times over: no split, no partial-sum traffic
     const int64_t max_splits = std::max<int64_t>(1, m / (8 * KS));
     want = std::min(want, max_splits);
     int64_t rows_per_split = (m + want - 1) / want;

@@ -6,6 +6,7 @@
 // This first version is the unblocked right-looking form (BLAS-2, HBM-bound: 8*m*n^2 bytes for an m x n iterate);
 // everything stays on the device, no host round trips (pivot indices live in device memory).
 #include "common.cuh"
+#include <algorithm>
 
 namespace rlb {
 
@@ -123,16 +124,12 @@ size_t plul_ws_bytes(Ctx* ctx, int64_t n) {
     return ws_round(sizeof(PivCand) * (size_t)ctx->num_sms * 8) + ws_round(sizeof(long long) * n) + ws_round(sizeof(int) * n);
 }
 
+// lapack::getrf(m, n, A, lda, ipiv) without host round trips: ipiv_dev[j] = 0-based pivot row of step j, nonzero_dev[j] = pivot != 0.
+// ws: plul_ws_bytes(ctx, n) scratch (the partial-argmax candidates live at its start).
 template <typename T>
-int plul(Ctx* ctx, int64_t m, int64_t n, T* A, int64_t lda, void* ws) {
-    RLB_REQUIRE(ctx, m >= 0 && n >= 0 && n < (1 << 30));
-    if (m == 0 || n == 0) return 0;
-    WsCarver cv(ws);
-    PivCand* part = cv.take<PivCand>((size_t)ctx->num_sms * 8);
-    long long* ipiv = cv.take<long long>(n);
-    int* nonzero = cv.take<int>(n);
+int getrf_nopiv_out(Ctx* ctx, int64_t m, int64_t n, T* A, int64_t lda, PivCand* part, long long* ipiv, int* nonzero) {
     const int kmin = (int)std::min<int64_t>(m, n);
-    LaunchScope ls(ctx, RLB200_TIMER_SMALL, 3 * kmin + 2);
+    LaunchScope ls(ctx, RLB200_TIMER_SMALL, 3 * kmin);
     for (int j = 0; j < kmin; ++j) {
         const int64_t rows = m - j;
         const int nb = (int)std::max<int64_t>(1, std::min<int64_t>((rows + 255) / 256, (int64_t)ctx->num_sms * 8));
@@ -143,13 +140,48 @@ int plul(Ctx* ctx, int64_t m, int64_t n, T* A, int64_t lda, void* ws) {
             lu_scale_update<T><<<ub, 256, 0, ctx->stream>>>(A, m, lda, (int)n, j, nonzero);
         }
     }
+    RLB_CUDA_OK(ctx, cudaGetLastError());
+    return 0;
+}
+
+template <typename T>
+int plul(Ctx* ctx, int64_t m, int64_t n, T* A, int64_t lda, void* ws) {
+    RLB_REQUIRE(ctx, m >= 0 && n >= 0 && n < (1 << 30));
+    if (m == 0 || n == 0) return 0;
+    WsCarver cv(ws);
+    PivCand* part = cv.take<PivCand>((size_t)ctx->num_sms * 8);
+    long long* ipiv = cv.take<long long>(n);
+    int* nonzero = cv.take<int>(n);
+    const int kmin = (int)std::min<int64_t>(m, n);
+    RLB_CHECK(getrf_nopiv_out<T>(ctx, m, n, A, lda, part, ipiv, nonzero));
+    LaunchScope ls(ctx, RLB200_TIMER_SMALL, 2);
     lu_make_L<T><<<(unsigned)std::min<int64_t>((n * std::min<int64_t>(n, m) + 255) / 256, 4096), 256, 0, ctx->stream>>>(A, m, lda, (int)n);
     lu_laswp_forward<T><<<1, 1024, 0, ctx->stream>>>(A, lda, (int)n, kmin, ipiv);
     RLB_CUDA_OK(ctx, cudaGetLastError());
     return 0;
 }
 
+// getrf with the pivot vector returned to the HOST (0-based rows), for BQRRP's LU-based QRCP (rl_bqrrp.hh:341-356)
+template <typename T>
+int getrf_pivots(Ctx* ctx, int64_t m, int64_t n, T* A, int64_t lda, void* ws, std::vector<int64_t>& ipiv_host) {
+    RLB_REQUIRE(ctx, m >= 0 && n >= 0 && n < (1 << 30));
+    const int kmin = (int)std::min<int64_t>(m, n);
+    ipiv_host.assign((size_t)kmin, 0);
+    if (kmin == 0) return 0;
+    WsCarver cv(ws);
+    PivCand* part = cv.take<PivCand>((size_t)ctx->num_sms * 8);
+    long long* ipiv = cv.take<long long>(n);
+    int* nonzero = cv.take<int>(n);
+    RLB_CHECK(getrf_nopiv_out<T>(ctx, m, n, A, lda, part, ipiv, nonzero));
+    static_assert(sizeof(long long) == sizeof(int64_t), "");
+    RLB_CUDA_OK(ctx, cudaMemcpyAsync(ipiv_host.data(), ipiv, sizeof(int64_t) * kmin, cudaMemcpyDeviceToHost, ctx->stream));
+    RLB_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
 template int plul<double>(Ctx*, int64_t, int64_t, double*, int64_t, void*);
 template int plul<float>(Ctx*, int64_t, int64_t, float*, int64_t, void*);
+template int getrf_pivots<double>(Ctx*, int64_t, int64_t, double*, int64_t, void*, std::vector<int64_t>&);
+template int getrf_pivots<float>(Ctx*, int64_t, int64_t, float*, int64_t, void*, std::vector<int64_t>&);
 
 }  // namespace rlb

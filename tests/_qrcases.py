@@ -50,3 +50,20 @@ def qr_invariants(A, Q, R, J, rank):
     j = int(np.argmax(cn))
     return (np.linalg.norm(E) / np.linalg.norm(A64), cn[j] / max(np.linalg.norm(AP[:, j]), 1e-300),
             np.linalg.norm(Q64.T @ Q64 - np.eye(rank)) / np.sqrt(A.shape[1]))
+
+
+def geqp3_format_invariants(A, F, tau, J, rank):
+    """test/drivers/test_bqrrp.cc:62-107: Q = ungqr(F[:, :rank], tau), R = triu(F)[:rank]; the three error measures
+    (each must be <= eps^0.75): ||A[:,J] - QR||_F/||A||_F, worst column residual, ||Q'Q - I||_F/sqrt(n)."""
+    from scipy.linalg import lapack
+    m, n = A.shape
+    k = int(rank)
+    F64 = np.asfortranarray(F.astype(np.float64))
+    q, _, info = lapack.dorgqr(np.asfortranarray(F64[:, :k]), np.asarray(tau[:k], dtype=np.float64))
+    R = np.triu(F64)[:k, :]
+    return qr_invariants(A, q, R, J, k)
+
+
+def numerical_rank(F, rel=1e-10):
+    dg = np.abs(np.diag(F))
+    return int(np.sum(dg > rel * dg[0]))

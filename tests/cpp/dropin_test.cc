@@ -15,6 +15,8 @@
 #include "RandLAPACK/comps/rl_rf.hh"
 #include "RandLAPACK/comps/rl_qb.hh"
 #include "RandLAPACK/drivers/rl_rsvd.hh"
+#include "RandLAPACK/drivers/rl_cqrrpt.hh"
+#include "RandLAPACK/drivers/rl_bqrrp.hh"
 #include "RandLAPACK/testing/rl_gen.hh"
 #define RLB200_WITH_RANDLAPACK
 #endif
@@ -86,6 +88,23 @@ int main() {
     struct HostStab : rlb200::Stabilization<double> { int call(int64_t, int64_t, double*) override { return 0; } } hs;
     rlb200::RS<double> bad(hs, 0, 1, false, false);
     try { rlb200_stack_opts o{}; bad.fill(o); fails += 1; } catch (const std::invalid_argument&) {}
+    {
+        // CQRRPT and BQRRP on the same planted matrix: the invariants test/drivers/test_cqrrpt.cc:98-104 asserts
+        std::vector<double> Aq = A, Rq(n * n, 0.0), tauq(n, 0.0);
+        std::vector<int64_t> Jq(n);
+        rlb200::CQRRPT<double> cq(false, std::pow(std::numeric_limits<double>::epsilon(), 0.85));
+        rlb200::RNGState st(0);
+        int rcq = cq.call(m, n, Aq.data(), m, Rq.data(), n, Jq.data(), 2.0, st);
+        double eq = orth_err(m, cq.rank, Aq.data());
+        std::printf("standalone CQRRPT: rc=%d rank=%lld ||Q'Q-I||=%.2e\n", rcq, (long long)cq.rank, eq);
+        fails += !(rcq == 0 && cq.rank >= k && cq.rank <= n && eq <= 1e-9);
+        std::vector<double> Ab = A;
+        rlb200::BQRRP<double> bq(false, 16);
+        rlb200::RNGState st2(0);
+        int rcb = bq.call(m, n, Ab.data(), m, 1.0, tauq.data(), Jq.data(), st2);
+        std::printf("standalone BQRRP: rc=%d rank=%lld\n", rcb, (long long)bq.rank);
+        fails += !(rcb == 0 && bq.rank > 0 && bq.rank <= n);
+    }
 #else
     using RNG = r123::Philox4x32;
     auto run = [&](int which, std::vector<double>& Sout, double& res, double& eu) {
@@ -136,6 +155,50 @@ int main() {
     std::printf("with-ref: max rel sigma diff  B200-QB under ref RSVD: %.2e   B200-RF under ref QB: %.2e\n", d1, d2);
     // device Gaussian entries differ from the host libm path by a few float ulps => 2e-6 (see tests/test_gpu_fill.py)
     fails += !(c0 == c1 && c1 == c2 && d1 <= 2e-6 && d2 <= 2e-6 && std::abs(r1 - r0) <= 2e-6 && std::abs(r2 - r0) <= 2e-6 && e1 <= 1e-9 && e2 <= 1e-9);
+    {
+        // CQRRPT and BQRRP called through the reference's abstract bases (CQRRPTalg / BQRRPalg): same pivots, rank and RNG state
+        const int64_t mq = 900, nq = 96;
+        auto gen = [&](std::vector<double>& A, RandBLAS::RNGState<RNG>& st) {
+            A.assign(mq * nq, 0.0);
+            RandLAPACK::gen::mat_gen_info<double> info((int64_t&)mq, (int64_t&)nq, RandLAPACK::gen::polynomial);
+            info.cond_num = 100; info.rank = nq; info.exponent = 2.0;
+            RandLAPACK::gen::mat_gen(info, A.data(), st);
+        };
+        const double tol = std::pow(std::numeric_limits<double>::epsilon(), 0.85);
+        RandLAPACK::CQRRPT<double, RNG> cq_ref(false, tol);
+        rlb200::CQRRPT<double> cq_dev(false, tol);
+        std::vector<int64_t> J0(nq), J1(nq);
+        std::vector<double> R0(nq * nq, 0.0), R1(nq * nq, 0.0), A0, A1;
+        auto call_cq = [&](RandLAPACK::CQRRPTalg<double, RNG>& alg, std::vector<double>& A, std::vector<double>& R, std::vector<int64_t>& J) {
+            auto st = RandBLAS::RNGState<RNG>();
+            gen(A, st);
+            alg.call(mq, nq, A.data(), mq, R.data(), nq, J.data(), 2.0, st);
+            return (int)st.counter.v[0];
+        };
+        int s0 = call_cq(cq_ref, A0, R0, J0), s1 = call_cq(cq_dev, A1, R1, J1);
+        double dR = 0, nR = 0;
+        for (int64_t i = 0; i < nq * nq; ++i) { dR = std::max(dR, std::abs(R0[i] - R1[i])); nR = std::max(nR, std::abs(R0[i])); }
+        std::printf("with-ref CQRRPT: rank %lld / %lld  J equal %d  max|dR|/max|R| %.2e  state %d / %d\n", (long long)cq_ref.rank, (long long)cq_dev.rank,
+                    (int)(J0 == J1), dR / nR, s0, s1);
+        fails += !(cq_ref.rank == cq_dev.rank && J0 == J1 && dR <= 1e-9 * nR && s0 == s1);
+
+        RandLAPACK::BQRRP<double, RNG> bq_ref(false, 32);
+        rlb200::BQRRP<double> bq_dev(false, 32);
+        std::vector<double> t0(nq, 0.0), t1(nq, 0.0);
+        auto call_bq = [&](RandLAPACK::BQRRPalg<double, RNG>& alg, std::vector<double>& A, std::vector<double>& tau, std::vector<int64_t>& J) {
+            auto st = RandBLAS::RNGState<RNG>();
+            gen(A, st);
+            alg.call(mq, nq, A.data(), mq, 1.0, tau.data(), J.data(), st);
+            return (int)st.counter.v[0];
+        };
+        s0 = call_bq(bq_ref, A0, t0, J0); s1 = call_bq(bq_dev, A1, t1, J1);
+        double dA = 0, dt = 0;
+        for (int64_t i = 0; i < mq * nq; ++i) dA = std::max(dA, std::abs(A0[i] - A1[i]));
+        for (int64_t i = 0; i < nq; ++i) dt = std::max(dt, std::abs(t0[i] - t1[i]));
+        std::printf("with-ref BQRRP: rank %lld / %lld  J equal %d  max|dA| %.2e  max|dtau| %.2e  state %d / %d\n", (long long)bq_ref.rank,
+                    (long long)bq_dev.rank, (int)(J0 == J1), dA, dt, s0, s1);
+        fails += !(bq_ref.rank == bq_dev.rank && J0 == J1 && dA <= 1e-9 && dt <= 1e-9 && s0 == s1);
+    }
 #endif
     std::printf(fails ? "DROPIN_FAIL\n" : "DROPIN_OK\n");
     return fails;

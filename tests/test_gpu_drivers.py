@@ -294,11 +294,22 @@ def test_canonical_stack_with_plul(ctx):
     assert _ref.subspace_sin(U_o, host(U)) <= 1e-9
 
 
-def test_hqrq_reports_unsupported(ctx):
-    A = dev(np.asfortranarray(np.random.default_rng(0).standard_normal((50, 5)))).clone()
-    with pytest.raises(rl.Error) as e:
-        rl.HQRQ().call(ctx, A)
-    assert e.value.code == -5
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("shape", [(50, 5), (2000, 64), (257, 256), (1, 1), (4096, 33)])
+def test_hqrq_vs_oracle(ctx, dtype, shape):
+    """HQRQ::call (rl_orth.hh:144-164, geqrf + ungqr): Householder QR is unique, so Q equals the oracle's to round-off —
+    also on an ill-conditioned iterate (cond 1e10), which is what HQRQ exists for."""
+    m, k = shape
+    rng = np.random.default_rng(m + k)
+    A = np.asfortranarray((rng.standard_normal((m, k)) * np.logspace(0, -10 if dtype == np.float64 else -4, k)).astype(dtype))
+    Ad = dev(A).clone()
+    rc = rl.HQRQ(False, False).call(ctx, Ad)
+    rc_o, Qo = O.HQRQ(False).call(A.copy(order="F"))
+    Q = host(Ad)
+    tol = 1e-12 if dtype == np.float64 else 1e-4
+    assert rc == rc_o == 0
+    assert np.linalg.norm(Q.T.astype(np.float64) @ Q - np.eye(k)) <= tol * k
+    assert np.abs(Q - Qo).max() <= tol * 10
 
 
 def test_rsvd_large_properties(ctx):

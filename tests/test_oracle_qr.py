@@ -41,3 +41,29 @@ def test_cqrrpt_vs_compiled_reference():
         assert (rc, rank) == (rc2, o.rank) and np.array_equal(J, J2) and st2 == list(st3.words())
         tol = 1e-11 if dt == np.float64 else 1e-4
         assert np.abs(R - R2).max() <= tol * np.abs(R).max() and np.abs(Q[:, :rank] - Q2[:, :rank]).max() <= tol * 10
+
+
+from _qrcases import bq_input, geqp3_format_invariants, numerical_rank  # noqa: E402
+
+
+@pytest.mark.parametrize("i", range(int(G["bq_count"])))
+def test_bqrrp_golden(i):
+    """Oracle BQRRP vs the real reference's output: return code, rank, RNG state exact; pivots exact over the numerical rank;
+    R diagonal / tau / leading block to round-off; the reference's acceptance invariants (test_bqrrp.cc:104-107)."""
+    A, st, c = bq_input(i)
+    alg = O.BQRRP(c["b"], "geqp3" if c["qrcp_wide"] else "luqr", "cholqr" if c["qr_tall"] else "geqrf")
+    rc, F, tau, J, st2 = alg.call(A, c["d_factor"], st)
+    rc_ref, rank_ref = [int(x) for x in G[f"bq{i}_rc_rank"]]
+    assert (rc, alg.rank) == (rc_ref, rank_ref)
+    assert list(st2.words()) == list(G[f"bq{i}_state_out"])
+    kn = min(numerical_rank(F), rank_ref)
+    assert np.array_equal(J[:kn], G[f"bq{i}_J"][:kn])
+    tol = 1e-9 if c["dtype"] == np.float64 else 2e-3
+    dref = G[f"bq{i}_Rdiag"]
+    assert np.abs(np.diag(F)[:kn] - dref[:kn]).max() <= tol * np.abs(dref).max()
+    assert np.abs(tau[:kn] - G[f"bq{i}_tau"][:kn]).max() <= tol * 10
+    h = min(48, kn)
+    assert np.abs(F[:h, :h] - G[f"bq{i}_Fhead"][:h, :h]).max() <= tol * 10 * np.abs(dref).max()
+    e = geqp3_format_invariants(A, F, tau, J, min(alg.rank, kn) if kn < rank_ref else alg.rank)
+    atol = np.finfo(c["dtype"]).eps ** 0.75
+    assert e[2] <= atol and (kn < rank_ref or max(e) <= atol), e
