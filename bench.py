@@ -37,20 +37,24 @@ def rsvd_flops(m, n, k, p, q=1):
     return f
 
 
-def class_flops(m, n, k, p, q=1):
-    """Algorithmic flops per kernel class for one step: NN (A*Omega), TN (A^T*Y and the Gram syrk's), RIGHTMUL (Y*R^-1, Q*W)."""
+def class_flops(m, n, k, p, q=1, folded=True):
+    """Flops EXECUTED per kernel class for one step: NN (A*Omega), TN (A^T*Y and the Gram syrk's), RIGHTMUL (Y*R^-1, Q*W).
+    With folded solves (the default: A^T(Y R^-1) computed as (A^T Y) R^-1, Q W as Y (R^-1 W)) the m x k triangular solves of
+    CholQR are not executed; the n x k / k x k ones that replace them are O(n k^2) and not counted."""
     n_even = p // 2
     nn = (n_even + 1) * 2.0 * m * n * k
     tn = (p - n_even + 1) * 2.0 * m * n * k
     rm = 2.0 * m * k * k        # U = Q W
     tn += 1.0 * m * k * k       # syrk of CholQR(Q)
-    rm += 1.0 * m * k * k       # trsm of CholQR(Q)
+    if not folded:
+        rm += 1.0 * m * k * k   # trsm of CholQR(Q)
     for pass_idx in range(1, p + 1):
         if pass_idx % q == 0:
             tall = (pass_idx % 2 == 1) if p % 2 == 0 else (pass_idx % 2 == 0)
             d = m if tall else n
             tn += 1.0 * d * k * k
-            rm += 1.0 * d * k * k
+            if not (folded and tall):
+                rm += 1.0 * d * k * k
     return {"gemm_nn": nn, "gemm_tn": tn, "rightmul": rm}
 
 
@@ -164,6 +168,132 @@ def cpu_sample(n, k, p, q, m_cpu, steps, warmup):
     return gf, t, kind, cores
 
 
+# --------------------------------------------------------------------------------------------------
+# secondary workloads (BASELINE.json configs[2], configs[3] and the sketch micro-kernels): not the headline line; run by hand,
+# results kept under profiles/.  Same timing rules: CUDA events, warm-up >= 3, inputs far larger than L2.
+# --------------------------------------------------------------------------------------------------
+def run_secondary(args):
+    import torch
+    import randlapack_b200 as rl
+    torch.cuda.set_device(0)
+    dev = torch.device("cuda", 0)
+    ctx = rl.Context(0)
+    peaks = load_peaks()
+    hbm = peaks.get("hbm_gbs", 6650.0)
+    hbm_src = "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    wl = args.workload
+    fill64, fill32 = ctx._lib.rlb200_fill_dense_f64_dev, ctx._lib.rlb200_fill_dense_f32_dev
+
+    def gen(m, n, dtype, key):
+        A = rl.empty_f(m, n, dtype, dev)
+        fn = fill64 if dtype == torch.float64 else fill32
+        ctx.check(fn(ctx._h, m, n, rl.FAMILY_GAUSSIAN, rl.AXIS_LONG, rl.LAYOUT_NATURAL, m, n, 0, 0, A.data_ptr(), rl.RNGState(key).words()))
+        return A
+
+    def timed(step, prep, steps, warmup):
+        ts = []
+        for i in range(warmup + steps):
+            prep()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            step()
+            e1.record()
+            torch.cuda.synchronize()
+            if i >= warmup:
+                ts.append(e0.elapsed_time(e1))
+        return sum(ts) / len(ts)
+
+    sampler = ClockSampler(0)
+    sampler.start()
+    if wl in ("sketch_sparse", "sketch_dense"):
+        m, n = args.m if args.m != (1 << 24) else (1 << 23), args.n if args.n != 1024 else 2048
+        dtype = torch.float32 if args.dtype == "f32" else torch.float64
+        es = 4 if dtype == torch.float32 else 8
+        d = args.d
+        A = gen(m, n, dtype, 0xA3)
+        B = rl.empty_f(d, n, dtype, dev)
+        if wl == "sketch_sparse":
+            D = rl.SparseDist(d, m, args.nnz)
+            ms = timed(lambda: rl.sketch_general_left(ctx, D, rl.RNGState(0), A, d, 1.0, 0.0, B), lambda: None, args.steps, args.warmup)
+            by = es * (m * n + 2 * d * n)                      # the reference's own model minus index bytes
+            out = {"metric": "sparse_sketch_gbps", "value": by / ms / 1e6, "unit": "GB/s", "ms_per_step": ms,
+                   "roofline": {"bound": "hbm", "achieved": by / ms / 1e6, "peak": hbm, "unit": "GB/s", "frac": by / ms / 1e6 / hbm,
+                                "traffic": None, "peak_source": hbm_src},
+                   "config": {"workload": f"SASO left sketch d={d} vec_nnz={args.nnz} of a {m} x {n} {args.dtype} matrix (configs[2] shape)"}}
+        else:
+            D = rl.DenseDist(d, m)
+            ms = timed(lambda: rl.sketch_general_left(ctx, D, rl.RNGState(0), A, d, 1.0, 0.0, B), lambda: None, args.steps, args.warmup)
+            fl = 2.0 * d * m * n
+            peak, src, _ = measured_fp64_peak()
+            out = {"metric": "dense_sketch_gflops", "value": fl / ms / 1e6, "unit": "Gflop/s", "ms_per_step": ms,
+                   "roofline": {"bound": "tensor", "achieved": fl / ms / 1e9, "peak": peak, "unit": "TFLOP/s", "frac": fl / ms / 1e9 / peak,
+                                "traffic": None, "peak_source": src},
+                   "config": {"workload": f"Gaussian left sketch d={d} (operator regenerated on chip) of a {m} x {n} {args.dtype} matrix"}}
+    elif wl == "cqrrpt":
+        m, n = args.m if args.m != (1 << 24) else (1 << 23), args.n if args.n != 1024 else 2048
+        dtype = torch.float32 if args.dtype == "f32" else torch.float64
+        d_factor, nnz = args.d_factor, args.nnz
+        d = int(d_factor * n)
+        A = rl.empty_f(m, n, dtype, dev)
+        fn = fill32 if dtype == torch.float32 else fill64
+        R = torch.zeros((n, n), dtype=dtype, device=dev).t()
+        J = torch.zeros(n, dtype=torch.int64, device=dev)
+        alg = rl.CQRRPT(False, None)
+        alg.nnz = nnz
+
+        def prep():
+            ctx.check(fn(ctx._h, m, n, rl.FAMILY_GAUSSIAN, rl.AXIS_LONG, rl.LAYOUT_NATURAL, m, n, 0, 0, A.data_ptr(), rl.RNGState(0xA3).words()))
+            R.zero_()
+
+        def step():
+            rc, _, _ = alg.call(ctx, A, d_factor, rl.RNGState(0), R=R, J=J)
+            assert rc == 0 and alg.rank == n, (rc, alg.rank)
+        ms = timed(step, prep, args.steps, args.warmup)
+        fl = 3.0 * m * n * n + m * n * nnz + (2.0 * d * n * n - 2.0 / 3.0 * n ** 3)
+        peak, src, _ = measured_fp64_peak()
+        out = {"metric": "cqrrpt_gflops", "value": fl / ms / 1e6, "unit": "Gflop/s", "ms_per_step": ms,
+               "roofline": {"bound": "tensor", "achieved": fl / ms / 1e9, "peak": peak, "unit": "TFLOP/s", "frac": fl / ms / 1e9 / peak,
+                            "traffic": None, "peak_source": src + " (fp32 storage, fp64 DMMA arithmetic)"},
+               "config": {"workload": f"CQRRPT of a {m} x {n} {args.dtype} Gaussian matrix, SASO d={d} vec_nnz={nnz}, geqp3 (configs[2])"}}
+    elif wl == "bqrrp":
+        n = args.n if args.n != 1024 else 65536
+        m = args.m if args.m != (1 << 24) else n
+        dtype = torch.float32 if args.dtype == "f32" else torch.float64
+        b = args.block
+        A = rl.empty_f(m, n, dtype, dev)
+        fn = fill32 if dtype == torch.float32 else fill64
+        tau = torch.zeros(n, dtype=dtype, device=dev)
+        J = torch.zeros(n, dtype=torch.int64, device=dev)
+        alg = rl.BQRRP(False, b)
+        alg.qr_tall = rl.QRTALL_CHOLQR
+
+        def prep():
+            ctx.check(fn(ctx._h, max(m, n), min(m, n), rl.FAMILY_GAUSSIAN, rl.AXIS_LONG, rl.LAYOUT_COLMAJOR if m >= n else rl.LAYOUT_ROWMAJOR,
+                         max(m, n), min(m, n), 0, 0, A.data_ptr(), rl.RNGState(0xA4).words()))
+
+        def step():
+            rc, _, _ = alg.call(ctx, A, args.d_factor, rl.RNGState(0), tau=tau, J=J)
+            assert rc == 0 and alg.rank == min(m, n), (rc, alg.rank)
+        ms = timed(step, prep, args.steps, args.warmup)
+        d = int(args.d_factor * b)
+        fl = 2.0 * m * n * n - 2.0 / 3.0 * n ** 3 + 2.0 * d * m * n
+        peak, src, _ = measured_fp64_peak()
+        out = {"metric": "bqrrp_gflops", "value": fl / ms / 1e6, "unit": "Gflop/s", "ms_per_step": ms,
+               "roofline": {"bound": "tensor", "achieved": fl / ms / 1e9, "peak": peak, "unit": "TFLOP/s", "frac": fl / ms / 1e9 / peak,
+                            "traffic": None, "peak_source": src},
+               "config": {"workload": f"BQRRP of a {m} x {n} {args.dtype} Gaussian matrix, b={b}, d_factor={args.d_factor}, luqr + cholqr/orhr_col "
+                                      "panels + compact-WY update (configs[3])"}}
+    else:
+        raise SystemExit(f"unknown workload {wl}")
+    clocks = sampler.stop()
+    out.update({"n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": args.dtype, "data": "synthetic", "clocks": clocks, "gpu_launches": ctx.launch_count(), "cpu_baseline": None, "e2e": None})
+    out["config"]["l2"] = "inputs exceed the 126 MB L2 by >100x; no flush needed"
+    print(json.dumps(out))
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -177,9 +307,21 @@ def main():
     ap.add_argument("--q", type=int, default=1, help="RS passes_per_stab")
     ap.add_argument("--m-cpu", type=int, default=1 << 17, help="rows of the bounded CPU-baseline sample")
     ap.add_argument("--m-e2e", type=int, default=1 << 20, help="rows of the host-buffer (e2e) measurement")
+    ap.add_argument("--workload", default="rsvd", choices=["rsvd", "cqrrpt", "bqrrp", "sketch_sparse", "sketch_dense"])
+    ap.add_argument("--dtype", default=None, help="secondary workloads: f32 | f64")
+    ap.add_argument("--d", type=int, default=4096, help="sketch rows (sketch workloads)")
+    ap.add_argument("--nnz", type=int, default=1, help="SASO non-zeros per column")
+    ap.add_argument("--d-factor", type=float, default=None)
+    ap.add_argument("--block", type=int, default=256, help="BQRRP block size")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
+    if args.workload != "rsvd":
+        if args.dtype is None:
+            args.dtype = "f64" if args.workload == "bqrrp" else "f32"
+        if args.d_factor is None:
+            args.d_factor = 1.0 if args.workload == "bqrrp" else 2.0
+        return run_secondary(args)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -297,8 +439,13 @@ def main():
     dom_ms = max(nn_ms, tn_ms) / args.steps
     dom_flops = (cf["gemm_nn"] + cf["rightmul"]) if dom == "gemm_nn" else cf["gemm_tn"]
     achieved = dom_flops / (dom_ms * 1e-3) / 1e12 if dom_ms > 0 else 0.0
+    # DRAM traffic of the dominant kernel per launch: dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture
+    # of gemm_nn_kernel<128,64,...> at m = 2^21 (profiles/ncu_gemm_nn_r1.txt: 17.193 GB + 4.280 GB for 17.180 + 4.295 GB of
+    # algorithmic bytes, i.e. A and Y each cross HBM exactly once), scaled by m; ~the same per launch for A^T*Y (reads A and Y).
+    traffic = (17.193092e9 + 4.279688e9) * (m_local / float(1 << 21)) * (n / 1024.0) if k == 256 else None
     roofline = {"bound": "tensor", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                "frac": achieved / peak if peak else None, "traffic": None,
+                "frac": achieved / peak if peak else None, "traffic": traffic,
+                "traffic_source": "ncu --set full capture at m=2^21 scaled by m (profiles/ncu_gemm_nn_r1.txt)",
                 "peak_source": peak_src + "; fp64 pipe (MEASURED_PEAKS.json has no fp64 figure)",
                 "class_ms_per_step": {kname: v[0] / args.steps for kname, v in tms.items()},
                 "class_launches_per_step": {kname: v[1] / args.steps for kname, v in tms.items()},
@@ -349,7 +496,10 @@ def main():
     out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
            "data": "synthetic", "config": config, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
-           "gpu_launches": launches, "flops_per_step": rsvd_flops(m_global, n, k, p, q)}
+           "gpu_launches": launches, "flops_per_step": rsvd_flops(m_global, n, k, p, q),
+           "flops_executed_per_step": sum(class_flops(m_global, n, k, p, q).values()),
+           "note": "value = nominal algorithm flops F(m,n,k,p) (DESIGN.md, same F as the reference arm) / time; CholQR's m x k "
+                   "triangular solves are folded into the next product and not executed (flops_executed_per_step)"}
     print(json.dumps(out))
     if dist is not None:
         dist.destroy_process_group()

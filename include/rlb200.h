@@ -69,7 +69,7 @@ typedef struct rlb200_stack_opts {
     int32_t orth_qb;           /* QB re-orthogonaliser                 */
     int32_t cond_check;        /* bool: CholQRQ cond check (rl_orth.hh:88-93); RS/RF cond logging is not offered */
     int32_t orth_check;        /* bool: QB orthogonality_check (rl_qb.hh:199-207,236-244) */
-    int32_t reserved;
+    int32_t reserved;          /* bit 0: 1 = do NOT fold CholQR's triangular solve into the next product (default 0 = fold; same outputs) */
 } rlb200_stack_opts;
 
 /* Sum-allreduce hook for row-sharded operation (net-new; the reference is single-address-space).

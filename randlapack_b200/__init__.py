@@ -376,10 +376,13 @@ class RS:
     def __init__(self, stab_obj, p, q, verbose=False, cond_check=False):
         self.Stab_Obj, self.passes_over_data, self.passes_per_stab = stab_obj, p, q
         self.verbose, self.cond_check = verbose, cond_check
+        # fold CholQR's m x k triangular solve into the next product ((A^T Y) R^-1 instead of A^T (Y R^-1)); same outputs to round-off
+        self.fold_solves = True
 
     def _opts(self, o: StackOpts):
         o.passes_over_data, o.passes_per_stab, o.stab = self.passes_over_data, self.passes_per_stab, self.Stab_Obj.kind
         o.cond_check = int(self.cond_check or self.Stab_Obj.cond_check)
+        o.reserved = 0 if self.fold_solves else 1
 
     def call(self, ctx: Context, A, k, state: RNGState):
         """-> (rc, Omega n x k).  `state` is advanced in place like the reference's in/out reference."""

@@ -168,6 +168,29 @@ static int hqrq(Ctx* ctx, int64_t m, int64_t k, T* A) {
     return 0;
 }
 
+// R = chol(A^T A) (upper, k x k in G, ld k) without applying it: the first half of CholQRQ::call (rl_orth.hh:78-93).
+// Returns 0, 1 (potrf failure / cond check) like the stabiliser.  Used where the triangular solve can be folded into the NEXT
+// product algebraically:  A^T (Y R^-1) = (A^T Y) R^-1  and  (Y R^-1) W = Y (R^-1 W)  — the m x k solve (m k^2 flops, a full
+// read+write of the tall iterate) becomes an n x k or k x k one.
+template <typename T>
+static int cholqr_factor(Ctx* ctx, int64_t m, int64_t k, const T* A, bool cond_check, bool rows_sharded, T* G, int* chol_fail) {
+    RLB_CUDA_OK(ctx, cudaMemsetAsync(G, 0, sizeof(T) * k * k, ctx->stream));
+    RLB_CHECK(gemm_tn<T>(ctx, m, k, k, 1.0, A, m, A, m, 0.0, G, k, /*upper_only=*/1));
+    if (rows_sharded) RLB_CHECK(allreduce_sum<T>(ctx, G, k * k));
+    int info = 0;
+    RLB_CHECK(potrf_blocked<T>(ctx, k, G, k, &info));
+    if (info != 0) { if (chol_fail) *chol_fail = 1; return 1; }
+    if (cond_check) {
+        if (k > 256) RLB_CHECK(tri_op<T>(ctx, 1, k, k, G, k, G, k));
+        double cond = 0;
+        RLB_CHECK(cond_of_square<T>(ctx, k, G, &cond));
+        if (cond > 1.0 / std::sqrt((double)std::numeric_limits<T>::epsilon())) return 1;
+    }
+    return 0;
+}
+
+static inline bool fuse_ok(const rlb200_stack_opts& o) { return (o.reserved & 1) == 0; }
+
 template <typename T>
 int stab_call(Ctx* ctx, int kind, int64_t m, int64_t k, T* A, bool cond_check, bool rows_sharded, int* chol_fail) {
     RLB_REQUIRE(ctx, m >= 0 && k >= 0);
@@ -250,13 +273,23 @@ int rs_call(Ctx* ctx, int64_t m, int64_t n, const T* A, int64_t k, T* Omega, T* 
         // Omega_1 = A Omega (:153)
         RLB_CHECK(gemm_nn<T>(ctx, m, k, n, 1.0, A, m, Omega, n, 0.0, Omega_1, m));
         ++p_done;
+        T* Rfold = nullptr;
+        ArenaScope as_fold(ctx);
         if (p_done % q == 0) {
-            int rc = stab_call<T>(ctx, o.stab, m, k, Omega_1, o.cond_check, sharded, nullptr);
-            if (rc) return rc < 0 ? rc : 1;
+            if (o.stab == RLB200_STAB_CHOLQRQ && fuse_ok(o)) {
+                // stabilise Omega_1 = Q R implicitly: Omega = A^T Q = (A^T Omega_1) R^-1; Omega_1 itself is scratch (:130) and is never read again
+                Rfold = as_fold.take<T>(k * k); RLB_ALLOC(ctx, Rfold);
+                int rc = cholqr_factor<T>(ctx, m, k, Omega_1, o.cond_check, sharded, Rfold, nullptr);
+                if (rc) return rc < 0 ? rc : 1;
+            } else {
+                int rc = stab_call<T>(ctx, o.stab, m, k, Omega_1, o.cond_check, sharded, nullptr);
+                if (rc) return rc < 0 ? rc : 1;
+            }
         }
         // Omega = A^T Omega_1 (:165)
         RLB_CHECK(gemm_tn<T>(ctx, m, n, k, 1.0, A, m, Omega_1, m, 0.0, Omega, n, 0));
         if (sharded) RLB_CHECK(allreduce_sum<T>(ctx, Omega, n * k));
+        if (Rfold) RLB_CHECK(trsm_right_upper<T>(ctx, n, k, Rfold, k, Omega, n));
         ++p_done;
         if (p_done % q == 0) {
             int rc = stab_call<T>(ctx, o.stab, n, k, Omega, o.cond_check, false, nullptr);
@@ -395,6 +428,52 @@ int qb_call(Ctx* ctx, int64_t m, int64_t n, T* A, int64_t* k_io, int64_t b_sz, T
 // ------------------------------------------------------------------------------------------------
 // RSVD  (rl_rsvd.hh:113-154)
 // ------------------------------------------------------------------------------------------------
+// RSVD with a single QB block and CholQRQ as RF's orthogonaliser (the configuration BASELINE.json names), with Q = Y R^-1 never
+// formed: B^T = A^T Q = (A^T Y) R^-1 and U = Q W = Y (R^-1 W).  Same quantities, return codes, k and RNG advancement as
+// RF::call -> QB::call -> RSVD::call (rl_rf.hh:106-137, rl_qb.hh:133-268, rl_rsvd.hh:137-148); two m x k triangular solves fewer.
+template <typename T>
+static int rsvd_single_block_fused(Ctx* ctx, int64_t m, int64_t n, T* A, int64_t* k_io, T tol_in, T* U, T* S, T* V, uint32_t state[6],
+                                   const rlb200_stack_opts& o, int* qb_code) {
+    const bool sharded = ctx->m_global >= 0;
+    const int64_t k = *k_io;
+    const T tol = std::max(tol_in, (T)100 * std::numeric_limits<T>::epsilon());       // rl_qb.hh:149
+    ArenaScope as(ctx);
+    T* Omega = as.take<T>(n * k); RLB_ALLOC(ctx, Omega);
+    T* R = as.take<T>(k * k); RLB_ALLOC(ctx, R);
+    T* W = as.take<T>(k * k); RLB_ALLOC(ctx, W);
+    T* Rinv = as.take<T>(k * k); RLB_ALLOC(ctx, Rinv);
+    T* M = as.take<T>(k * k); RLB_ALLOC(ctx, M);
+    double* nA_dev = as.take<double>(1); RLB_ALLOC(ctx, nA_dev);
+    if (qb_code) *qb_code = 0;
+    // RF (rl_rf.hh:118-129)
+    int rc = rs_call<T>(ctx, m, n, A, k, Omega, U, state, o);
+    if (rc < 0) return rc;
+    if (!rc) {
+        RLB_CHECK(gemm_nn<T>(ctx, m, k, n, 1.0, A, m, Omega, n, 0.0, U, m));           // Y = A Omega
+        rc = cholqr_factor<T>(ctx, m, k, U, o.cond_check, sharded, R, nullptr);        // Y = Q R (Q implicit)
+        if (rc < 0) return rc;
+    }
+    if (rc) { *k_io = 0; if (qb_code) *qb_code = 6; return 0; }                        // rl_qb.hh:191-197 -> rl_rsvd.hh:137
+    // B^T = A^T Q = (A^T Y) R^-1 (rl_qb.hh:218), ||A||_F fused into the same sweep of A (:168)
+    RLB_CHECK(gemm_tn<T>(ctx, m, n, k, 1.0, A, m, U, m, 0.0, V, n, 0, nA_dev));
+    if (sharded) { RLB_CHECK(allreduce_sum<T>(ctx, V, n * k)); RLB_CHECK(allreduce_sum<double>(ctx, nA_dev, 1)); }
+    RLB_CHECK(trsm_right_upper<T>(ctx, n, k, R, k, V, n));
+    double ss = 0, nB = 0;
+    RLB_CHECK(read_scalar<double>(ctx, nA_dev, &ss));
+    const T norm_A = (T)std::sqrt(ss);
+    RLB_CHECK(fro_norm<T>(ctx, V, n, k, n, false, &nB));                               // :221
+    const T norm_B = (T)std::hypot((T)0, (T)nB);                                       // :222
+    const T approx_err = std::sqrt(std::abs(norm_A - norm_B)) * (std::sqrt(norm_A + norm_B) / norm_A);   // :225
+    if (qb_code) *qb_code = approx_err < tol ? 0 : 3;                                  // :250-256 / :267
+    // SVD of B^T and U = Q W = Y (R^-1 W) (rl_rsvd.hh:146-148)
+    void* ws = arena_push(ctx, svd_ws_bytes(n, k, sizeof(T))); RLB_ALLOC(ctx, ws);
+    RLB_CHECK(svd_tall<T>(ctx, n, k, V, n, S, W, ws, nullptr));
+    RLB_CHECK(trtri_upper<T>(ctx, (int)k, R, (int)k, Rinv));
+    RLB_CHECK(gemm_nn<T>(ctx, k, k, k, 1.0, Rinv, k, W, k, 0.0, M, k));
+    RLB_CHECK(gemm_nn_inplace<T>(ctx, m, k, k, 1.0, U, m, M, k));
+    return 0;
+}
+
 template <typename T>
 int rsvd_call(Ctx* ctx, int64_t m, int64_t n, T* A, int64_t* k_io, T tol, T* U, T* S, T* V, T* Acpy, uint32_t state[6],
               const rlb200_stack_opts& o, int* qb_code) {
@@ -407,6 +486,8 @@ int rsvd_call(Ctx* ctx, int64_t m, int64_t n, T* A, int64_t* k_io, T tol, T* U, 
     RLB_REQUIRE(ctx, m > 0 && n > 0 && *k_io <= n && o.block_sz > 0);
     // Q lives in U, BT in V; the SVD of BT (n x k) overwrites V with its left singular vectors, which is exactly
     // what the reference returns in V (gesdd's U argument, :146)
+    if (o.block_sz >= *k_io && *k_io <= 256 && o.orth_rf == RLB200_STAB_CHOLQRQ && !o.orth_check && fuse_ok(o))
+        return rsvd_single_block_fused<T>(ctx, m, n, A, k_io, tol, U, S, V, state, o, qb_code);
     int rc = qb_call<T>(ctx, m, n, A, k_io, o.block_sz, tol, U, V, Acpy, state, o);   // :137 (code ignored by the reference)
     if (rc < 0) return rc;
     if (qb_code) *qb_code = rc;

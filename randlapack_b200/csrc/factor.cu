@@ -154,12 +154,15 @@ int potrf_blocked(Ctx* ctx, int64_t k, T* A, int64_t lda, int* info_host) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// X <- X * R^{-1}, X m x k (tall, in place), R k x k upper triangular (ldr).  Column blocks of 256, left to right:
+// X <- X * R^{-1}, X m x k (tall, in place), R k x k upper triangular (ldr).  Column blocks of 64, left to right:
 //   X_j <- (X_j - X[:, 0:j0] * R[0:j0, j]) * R_jj^{-1}
+// The off-diagonal products run through the 128x64x32 two-CTA-per-SM tile (the fastest DMMA configuration measured); the
+// diagonal 64 x 64 solves are triangular-skipping in-place products with the explicit inverse of the diagonal block.
+// (One 256-wide in-place tile instead costs 2.2x the time at k = 256: 1 CTA/SM, 204 registers — profiles/launches_full_r1.csv.)
 // ------------------------------------------------------------------------------------------------
 template <typename T>
 int trsm_right_upper(Ctx* ctx, int64_t m, int64_t k, const T* R, int64_t ldr, T* X, int64_t ldx) {
-    constexpr int NB = 256;
+    constexpr int NB = 64;
     if (m == 0 || k == 0) return 0;
     ArenaScope as(ctx);
     T* inv = as.take<T>(NB * NB); if (!inv) return RLB200_ERR_ALLOC;

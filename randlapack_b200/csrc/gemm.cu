@@ -277,7 +277,8 @@ gemm_tn_kernel(int64_t m, int N1, int N2, const T* __restrict__ A, int64_t lda, 
         cp_async_commit();
     }
     const int arow = w1 * Cfg::W1 + (lane >> 2), bcol = w2 * Cfg::W2 + (lane >> 2), kq = lane & 3;
-    const bool do_sq = (sq_part != nullptr) && (t2 == 0);
+    const bool do_sq = (sq_part != nullptr) && (t2 == 0) && (w2 == 0);
+    const bool cta_sq = (sq_part != nullptr) && (t2 == 0);
     double sq = 0.0;
     for (int kt = 0; kt < nk; ++kt) {
         cp_async_wait<STAGES - 2>();
@@ -289,12 +290,6 @@ gemm_tn_kernel(int64_t m, int N1, int N2, const T* __restrict__ A, int64_t lda, 
         }
         const T* a = sA + (size_t)(kt % STAGES) * Cfg::A_ELEMS;
         const T* b = sB + (size_t)(kt % STAGES) * Cfg::B_ELEMS;
-        if (do_sq) {   // fused lange(Fro, A) (rl_qb.hh:168): the A tile is already on chip, zero-filled outside the matrix
-            for (int e = tid; e < T1 * KS; e += Cfg::THREADS) {
-                const double v = (double)a[(e / KS) * Cfg::SK + (e % KS)];
-                sq = fma(v, v, sq);
-            }
-        }
 #pragma unroll
         for (int kk = 0; kk < KS; kk += 4) {
             double af[Cfg::MI], bf[Cfg::NI];
@@ -302,6 +297,12 @@ gemm_tn_kernel(int64_t m, int N1, int N2, const T* __restrict__ A, int64_t lda, 
             for (int i = 0; i < Cfg::MI; ++i) af[i] = (double)a[(arow + i * 8) * Cfg::SK + kk + kq];
 #pragma unroll
             for (int j = 0; j < Cfg::NI; ++j) bf[j] = (double)b[(bcol + j * 8) * Cfg::SK + kk + kq];
+            // fused lange(Fro, A) (rl_qb.hh:168): the warps of the first column group hold every element of the A tile exactly once
+            // in their MMA fragments (zero outside the matrix), so the sum of squares costs MI DFMAs per 16 DMMAs and no extra loads
+            if (do_sq) {
+#pragma unroll
+                for (int i = 0; i < Cfg::MI; ++i) sq = fma(af[i], af[i], sq);
+            }
 #pragma unroll
             for (int i = 0; i < Cfg::MI; ++i)
 #pragma unroll
@@ -309,7 +310,7 @@ gemm_tn_kernel(int64_t m, int N1, int N2, const T* __restrict__ A, int64_t lda, 
         }
     }
     cp_async_wait<0>();
-    if (do_sq) {
+    if (cta_sq) {
         __shared__ double sq_sh[32];
         sq = warp_sum(sq);
         if (lane == 0) sq_sh[warp] = sq;

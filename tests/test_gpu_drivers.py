@@ -312,6 +312,26 @@ def test_hqrq_vs_oracle(ctx, dtype, shape):
     assert np.abs(Q - Qo).max() <= tol * 10
 
 
+def test_folded_solves_match_explicit(ctx):
+    """CholQR's triangular solve folded into the next product (default) vs the reference's explicit order of operations:
+    identical return codes / k / RNG state, U, S, V equal to round-off."""
+    A, st0 = poly(3000, 200, 200)
+    for p in (0, 2, 3):
+        outs = []
+        for fold in (True, False):
+            RS, RF, QB, RSVD = _stack(p, 1, 24)
+            RS.fold_solves = fold
+            s = rl.RNGState(st0.key, st0.counter)
+            rc, kk, U, S, V = RSVD.call(ctx, dev(A), 24, 0.0, s)
+            outs.append((rc, kk, RSVD.qb_code, s.counter, host(U), S.cpu().numpy(), host(V)))
+        a, b = outs
+        assert a[:4] == b[:4]
+        assert np.abs(a[5] - b[5]).max() <= 1e-12 * a[5][0]
+        assert _ref.subspace_sin(a[4], b[4]) <= 1e-9 and _ref.subspace_sin(a[6], b[6]) <= 1e-9
+        Ur = (a[4] * a[5]) @ a[6].T - (b[4] * b[5]) @ b[6].T
+        assert np.linalg.norm(Ur) <= 1e-11 * a[5][0]
+
+
 def test_rsvd_large_properties(ctx):
     """Size-independent properties at a size the oracle cannot reach in seconds (2^22 x 512, k = 64):
     planted low-rank + noise => recovered spectrum, orthonormal factors, residual at the noise floor."""
