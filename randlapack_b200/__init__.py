@@ -140,6 +140,10 @@ class Context:
         self.check(self._lib.rlb200_timer_read(self._h, which, ctypes.byref(ms), ctypes.byref(n), int(reset)))
         return ms.value, n.value
 
+    def set_fp64_engine(self, engine):
+        """Tall fp64 products of the drivers: "dmma" (default) or "i8" (tcgen05 int8 digit slices)."""
+        self.check(self._lib.rlb200_set_fp64_engine(self._h, {"dmma": 0, "i8": 1}[engine]))
+
     # ---- row sharding over torch.distributed -------------------------------------------------
     def set_shard(self, row_offset, m_global, group=None):
         """This rank holds rows [row_offset, row_offset + m_local) of an m_global-row A.  Gram / B^T / norm
@@ -320,8 +324,9 @@ def philox_stream(ctx: Context, state: RNGState, n: int):
     return out[:n]
 
 
-def gemm(ctx: Context, transa, transb, alpha, A, B, beta=0.0, C=None):
-    """blas::gemm(ColMajor, ...) on column-major device tensors, shapes as BLAS defines them."""
+def gemm(ctx: Context, transa, transb, alpha, A, B, beta=0.0, C=None, engine="dmma"):
+    """blas::gemm(ColMajor, ...) on column-major device tensors, shapes as BLAS defines them.
+    engine: "dmma" (fp64 tensor pipe) or "i8" (fp64 through tcgen05 int8 digit slices; fp64 only)."""
     m = A.shape[1] if transa else A.shape[0]
     k = A.shape[0] if transa else A.shape[1]
     n = B.shape[0] if transb else B.shape[1]
@@ -329,7 +334,7 @@ def gemm(ctx: Context, transa, transb, alpha, A, B, beta=0.0, C=None):
     if C is None:
         C = empty_f(m, n, A.dtype, A.device)
         beta = 0.0
-    fn = getattr(ctx._lib, f"rlb200_gemm_{_suffix(A.dtype)}_dev")
+    fn = getattr(ctx._lib, f"rlb200_gemm_{_suffix(A.dtype)}_dev" if engine == "dmma" else "rlb200_gemm_f64_i8_dev")
     ctx.check(fn(ctx._h, int(transa), int(transb), m, n, k, alpha, A.data_ptr(), _ld(A), B.data_ptr(), _ld(B), beta, C.data_ptr(), _ld(C)))
     return C
 

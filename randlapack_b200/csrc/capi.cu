@@ -127,6 +127,21 @@ int rlb200_philox_stream_dev(rlb200_ctx* ctx, const uint32_t state[6], int64_t n
     return philox_stream(ctx, state, n, out_dev);
 }
 
+int rlb200_gemm_f64_i8_dev(rlb200_ctx* ctx, int transa, int transb, int64_t m, int64_t n, int64_t k, double alpha, const double* A, int64_t lda,
+                           const double* B, int64_t ldb, double beta, double* C, int64_t ldc) {
+    CTX_OK(ctx); RLB_CHECK(bind(ctx));
+    if (!transa && !transb) return ozaki_gemm_nn(ctx, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc);
+    if (transa && !transb) return ozaki_gemm_tn(ctx, k, m, n, alpha, A, lda, B, ldb, beta, C, ldc);
+    ctx->err = "only the NN (tall) and TN (long contraction) shapes of the path are offered";
+    return RLB200_ERR_UNSUPPORTED;
+}
+int rlb200_set_fp64_engine(rlb200_ctx* ctx, int engine) {
+    CTX_OK(ctx);
+    RLB_REQUIRE(ctx, engine == RLB200_FP64_DMMA || engine == RLB200_FP64_I8SLICES);
+    ctx->fp64_engine = engine;
+    return 0;
+}
+
 #define DEFINE_TYPED(T, SUF)                                                                                                        \
     int rlb200_fill_dense_##SUF##_dev(rlb200_ctx* ctx, int64_t n_rows, int64_t n_cols, int family, int major_axis, int layout,      \
                                       int64_t sub_rows, int64_t sub_cols, int64_t ro, int64_t co, T* buff_dev, uint32_t state[6]) { \

@@ -42,6 +42,8 @@ struct Ctx {
     int64_t m_global = -1;
     rlb200_allreduce_fn allreduce = nullptr;
     void* allreduce_user = nullptr;
+    // fp64 tall-GEMM engine of the drivers: 0 = DMMA (fp64 tensor pipe), 1 = tcgen05 int8 digit slices (ozaki.cu)
+    int fp64_engine = 0;
     // stats
     int64_t launches = 0;
     bool timers_on = false;

@@ -217,6 +217,33 @@ int stab_call(Ctx* ctx, int kind, int64_t m, int64_t k, T* A, bool cond_check, b
     return RLB200_ERR_ARG;
 }
 
+// tall products over the m x n data matrix: the fp64 engine is selectable (DMMA fp64 pipe / tcgen05 int8 digit slices, ozaki.cu);
+// Gram matrices of CholQR always stay on the fp64 pipe (their conditioning is squared).
+template <typename T>
+static int tall_nn(Ctx* ctx, int64_t m, int64_t N, int64_t K, double alpha, const T* A, int64_t lda, const T* B, int64_t ldb, double beta, T* C,
+                   int64_t ldc) {
+    if constexpr (sizeof(T) == 8) {
+        if (ctx->fp64_engine == RLB200_FP64_I8SLICES && m >= 1024)
+            return ozaki_gemm_nn(ctx, m, N, K, alpha, (const double*)A, lda, (const double*)B, ldb, beta, (double*)C, ldc);
+    }
+    return gemm_nn<T>(ctx, m, N, K, alpha, A, lda, B, ldb, beta, C, ldc);
+}
+template <typename T>
+static int tall_tn(Ctx* ctx, int64_t m, int64_t N1, int64_t N2, double alpha, const T* A, int64_t lda, const T* B, int64_t ldb, double beta, T* C,
+                   int64_t ldc, double* a_sumsq_out = nullptr) {
+    if constexpr (sizeof(T) == 8) {
+        if (ctx->fp64_engine == RLB200_FP64_I8SLICES && m >= 1024) {
+            if (a_sumsq_out) {
+                ArenaScope as(ctx);
+                double* part = as.take<double>(sumsq_ws_doubles(ctx)); if (!part) return RLB200_ERR_ALLOC;
+                RLB_CHECK(sumsq<T>(ctx, A, m, N1, lda, part, a_sumsq_out));
+            }
+            return ozaki_gemm_tn(ctx, m, N1, N2, alpha, (const double*)A, lda, (const double*)B, ldb, beta, (double*)C, ldc);
+        }
+    }
+    return gemm_tn<T>(ctx, m, N1, N2, alpha, A, lda, B, ldb, beta, C, ldc, 0, a_sumsq_out);
+}
+
 // ------------------------------------------------------------------------------------------------
 // RS  (rl_rs.hh:116-178)
 // ------------------------------------------------------------------------------------------------
@@ -261,7 +288,7 @@ int rs_call(Ctx* ctx, int64_t m, int64_t n, const T* A, int64_t k, T* Omega, T* 
         dense_next_state(mg, k, st_full);
         std::memcpy(state, st_full, sizeof st_full);
         // Omega = A^T Omega_1 (:142)
-        RLB_CHECK(gemm_tn<T>(ctx, m, n, k, 1.0, A, m, Omega_1, m, 0.0, Omega, n, 0));
+        RLB_CHECK(tall_tn<T>(ctx, m, n, k, 1.0, A, m, Omega_1, m, 0.0, Omega, n));
         if (sharded) RLB_CHECK(allreduce_sum<T>(ctx, Omega, n * k));
         ++p_done;
         if (p_done % q == 0) {
@@ -271,7 +298,7 @@ int rs_call(Ctx* ctx, int64_t m, int64_t n, const T* A, int64_t k, T* Omega, T* 
     }
     while (p - p_done > 0) {
         // Omega_1 = A Omega (:153)
-        RLB_CHECK(gemm_nn<T>(ctx, m, k, n, 1.0, A, m, Omega, n, 0.0, Omega_1, m));
+        RLB_CHECK(tall_nn<T>(ctx, m, k, n, 1.0, A, m, Omega, n, 0.0, Omega_1, m));
         ++p_done;
         T* Rfold = nullptr;
         ArenaScope as_fold(ctx);
@@ -287,7 +314,7 @@ int rs_call(Ctx* ctx, int64_t m, int64_t n, const T* A, int64_t k, T* Omega, T* 
             }
         }
         // Omega = A^T Omega_1 (:165)
-        RLB_CHECK(gemm_tn<T>(ctx, m, n, k, 1.0, A, m, Omega_1, m, 0.0, Omega, n, 0));
+        RLB_CHECK(tall_tn<T>(ctx, m, n, k, 1.0, A, m, Omega_1, m, 0.0, Omega, n));
         if (sharded) RLB_CHECK(allreduce_sum<T>(ctx, Omega, n * k));
         if (Rfold) RLB_CHECK(trsm_right_upper<T>(ctx, n, k, Rfold, k, Omega, n));
         ++p_done;
@@ -310,7 +337,7 @@ int rf_call(Ctx* ctx, int64_t m, int64_t n, const T* A, int64_t k, T* Q, uint32_
     // RS's m x k scratch (Omega_1) lives in Q, which is overwritten afterwards anyway
     int rc = rs_call<T>(ctx, m, n, A, k, Omega, Q, state, o);
     if (rc) return rc < 0 ? rc : 1;                                           // :118-120
-    RLB_CHECK(gemm_nn<T>(ctx, m, k, n, 1.0, A, m, Omega, n, 0.0, Q, m));      // :123
+    RLB_CHECK(tall_nn<T>(ctx, m, k, n, 1.0, A, m, Omega, n, 0.0, Q, m));      // :123
     rc = stab_call<T>(ctx, o.orth_rf, m, k, Q, o.cond_check, ctx->m_global >= 0, nullptr);   // :129
     if (rc) return rc < 0 ? rc : 2;
     return 0;
@@ -396,7 +423,7 @@ int qb_call(Ctx* ctx, int64_t m, int64_t n, T* A, int64_t* k_io, int64_t b_sz, T
             int rc2 = stab_call<T>(ctx, o.orth_qb, m, b_sz, Q_i, o.cond_check, sharded, nullptr);
             if (rc2 < 0) return rc2;   // (the reference ignores a numeric failure here, :214)
         }
-        RLB_CHECK(gemm_tn<T>(ctx, m, n, b_sz, 1.0, A_work, m, Q_i, m, 0.0, BT_i, n, 0, curr_sz == 0 ? nA_dev : nullptr));   // :218
+        RLB_CHECK(tall_tn<T>(ctx, m, n, b_sz, 1.0, A_work, m, Q_i, m, 0.0, BT_i, n, curr_sz == 0 ? nA_dev : nullptr));   // :218
         if (sharded) RLB_CHECK(allreduce_sum<T>(ctx, BT_i, n * b_sz));
         if (curr_sz == 0) {
             if (sharded) RLB_CHECK(allreduce_sum<double>(ctx, nA_dev, 1));
@@ -449,13 +476,13 @@ static int rsvd_single_block_fused(Ctx* ctx, int64_t m, int64_t n, T* A, int64_t
     int rc = rs_call<T>(ctx, m, n, A, k, Omega, U, state, o);
     if (rc < 0) return rc;
     if (!rc) {
-        RLB_CHECK(gemm_nn<T>(ctx, m, k, n, 1.0, A, m, Omega, n, 0.0, U, m));           // Y = A Omega
+        RLB_CHECK(tall_nn<T>(ctx, m, k, n, 1.0, A, m, Omega, n, 0.0, U, m));           // Y = A Omega
         rc = cholqr_factor<T>(ctx, m, k, U, o.cond_check, sharded, R, nullptr);        // Y = Q R (Q implicit)
         if (rc < 0) return rc;
     }
     if (rc) { *k_io = 0; if (qb_code) *qb_code = 6; return 0; }                        // rl_qb.hh:191-197 -> rl_rsvd.hh:137
     // B^T = A^T Q = (A^T Y) R^-1 (rl_qb.hh:218), ||A||_F fused into the same sweep of A (:168)
-    RLB_CHECK(gemm_tn<T>(ctx, m, n, k, 1.0, A, m, U, m, 0.0, V, n, 0, nA_dev));
+    RLB_CHECK(tall_tn<T>(ctx, m, n, k, 1.0, A, m, U, m, 0.0, V, n, nA_dev));
     if (sharded) { RLB_CHECK(allreduce_sum<T>(ctx, V, n * k)); RLB_CHECK(allreduce_sum<double>(ctx, nA_dev, 1)); }
     RLB_CHECK(trsm_right_upper<T>(ctx, n, k, R, k, V, n));
     double ss = 0, nB = 0;

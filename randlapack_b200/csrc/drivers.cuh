@@ -37,6 +37,12 @@ int plul(Ctx* ctx, int64_t m, int64_t n, T* A, int64_t lda, void* ws);
 template <typename T>
 int svd_tall(Ctx* ctx, int64_t n, int64_t k, T* B, int64_t ldb, T* S, T* W, void* ws, int* sweeps_out);
 
+// ---- fp64 GEMMs on tcgen05 int8 tensor cores through exact digit slices (ozaki.cu) -------------------
+int ozaki_gemm_nn(Ctx* ctx, int64_t m, int64_t N, int64_t K, double alpha, const double* A, int64_t lda, const double* B, int64_t ldb, double beta,
+                  double* C, int64_t ldc);
+int ozaki_gemm_tn(Ctx* ctx, int64_t m, int64_t N1, int64_t N2, double alpha, const double* X, int64_t ldx, const double* Y, int64_t ldy, double beta,
+                  double* C, int64_t ldc);
+
 // ---- sketch-apply (sketch.cu) -----------------------------------------------------------------------
 template <typename T>
 int fill_sparse_unpacked(Ctx* ctx, int64_t n_rows, int64_t n_cols, int64_t vec_nnz, int major_axis, int64_t sub_rows, int64_t sub_cols,

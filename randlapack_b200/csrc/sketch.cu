@@ -438,9 +438,11 @@ int sketch_dense_left(Ctx* ctx, int64_t S_rows, int64_t S_cols, int family, int 
             T* P = panel + (size_t)buf * d * pc;
             uint32_t st[6];
             std::memcpy(st, state, sizeof st);
-            // the d x w block of S at (ro, co + shard_off + j0), column-major with ld = d
-            RLB_CHECK(fill_dense_unpacked<T>(ctx, S_rows, S_cols, family, major_axis, RLB200_LAYOUT_COLMAJOR, d, w, ro, co + shard_off + j0, P, st));
-            RLB_CHECK(gemm_nn<T>(ctx, d, n, w, (double)alpha, P, d, A + j0, lda, j0 == 0 ? (double)beta0 : 1.0, B, ldb));
+            // the d x w block of S at (ro, co + shard_off + j0) in ROW-major order (= the natural, contiguous-write layout of a wide
+            // Long-axis operator), i.e. the w x d column-major matrix S_block^T with ld = w: the product is then the long-contraction
+            // (split-K, whole-machine) form  B += (S_block^T)^T A_block
+            RLB_CHECK(fill_dense_unpacked<T>(ctx, S_rows, S_cols, family, major_axis, RLB200_LAYOUT_ROWMAJOR, d, w, ro, co + shard_off + j0, P, st));
+            RLB_CHECK(gemm_tn<T>(ctx, w, d, n, (double)alpha, P, w, A + j0, lda, j0 == 0 ? (double)beta0 : 1.0, B, ldb, 0));
         }
         if (sharded && ctx->allreduce) {
             for (int64_t c = 0; c < (ldb == d ? 1 : n); ++c) {
