@@ -76,16 +76,29 @@ __global__ void __launch_bounds__(256) oz_colmax_kernel(const double* __restrict
 // slicers.  Digit tiles: tile (rb, kb, t) of TR rows x 32 K-bytes at ((rb * nkb + kb) * S + t) * TR * 32, inside it the byte of
 // (row r, k) sits at ((r / 8) * 2 + k / 16) * 128 + (r % 8) * 16 + k % 16  (K-major, no swizzle: SBO = 256 B, LBO = 128 B).
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void oz_digits(double x, int sh, int8_t* d /* [S] */) {
-    long long F = __double2ll_rn(scalbn(x, sh));
+// digits of one value.  `scale` = 2^(P - E) (exact power of two), |x * scale| <= 2^P = 2^48.
+//   y = x * scale + 1.5 * 2^52   puts F = rn(x * scale) (two's complement) in the low mantissa bits of y;
+//   adding BIAS = sum_t 64 * 128^t makes every 7-bit field u_t = d_t + 64 non-negative, so the digits are plain shifts and masks
+//   (the top field is left unmasked: it may reach 128, i.e. d_0 = 64, which is a valid int8).
+// Returned packed: digit t of this value in byte lane `lane` (0..3) of w[t], already re-centred (u - 64 as two's complement byte).
+constexpr long long OZ_MAGIC_BITS = 0x4338000000000000ll;                       // bit pattern of 1.5 * 2^52
+constexpr long long OZ_BIAS = 64ll * ((1ll << 49) - 1) / 127;                   // sum_{t<7} 64 * 128^t
+__device__ __forceinline__ void oz_digits_packed(double x, double scale, int lane, uint32_t* w /* [S] */) {
+    const double y = fma(x, scale, 6755399441055744.0);
+    const unsigned long long Fp = (unsigned long long)(__double_as_longlong(y) - OZ_MAGIC_BITS + OZ_BIAS);
+    const int sh8 = lane * 8;
 #pragma unroll
-    for (int t = OZ_S - 1; t >= 1; --t) {
-        const int dd = (((int)(F & 127) + 64) & 127) - 64;
-        d[t] = (int8_t)dd;
-        F = (F - dd) >> 7;
+    for (int t = 0; t < OZ_S; ++t) {
+        uint32_t u = (uint32_t)(Fp >> (7 * (OZ_S - 1 - t)));
+        if (t > 0) u &= 127u;
+        w[t] |= ((u - 64u) & 0xFFu) << sh8;
     }
-    d[0] = (int8_t)F;
 }
+__device__ __forceinline__ double oz_pow2(int e) {      // 2^e for e in [-1022, 1023]
+    return __longlong_as_double((long long)(e + 1023) << 52);
+}
+// scale = 2^(P - E), clamped to the normal range (inputs below 2^-970 of magnitude lose digits, never correctness of the bound)
+__device__ __forceinline__ double oz_scale_of(int E) { return oz_pow2(max(-1022, min(1023, OZ_P - E))); }
 
 // First operand of the NN product: tile rows = rows of A, K = columns of A, scale per row.  CTA = (row block, group of 8 K-blocks).
 template <int TR>
@@ -95,27 +108,28 @@ __global__ void __launch_bounds__(TR) oz_slice_rows_kernel(const double* __restr
     const int64_t rb = blockIdx.x;
     const int64_t row = rb * TR + r;
     const bool rv = row < rows;
-    const int sh = rv ? OZ_P - E[row] : 0;
+    const double scale = rv ? oz_scale_of(E[row]) : 0.0;
     for (int kb = blockIdx.y * 8; kb < min(nkb, (int)blockIdx.y * 8 + 8); ++kb) {
         int8_t* tile0 = out + ((rb * nkb + kb) * OZ_S) * (int64_t)(TR * OZ_KB);
 #pragma unroll
         for (int kc = 0; kc < 2; ++kc) {
-            uint32_t pk[OZ_S][4];
+            uint32_t pk[4][OZ_S];
 #pragma unroll
-            for (int t = 0; t < OZ_S; ++t) pk[t][0] = pk[t][1] = pk[t][2] = pk[t][3] = 0;
+            for (int q = 0; q < 4; ++q)
+#pragma unroll
+                for (int t = 0; t < OZ_S; ++t) pk[q][t] = 0;
+            double xv[16];
 #pragma unroll
             for (int kk = 0; kk < 16; ++kk) {
                 const int col = kb * OZ_KB + kc * 16 + kk;
-                const double x = (rv && col < K) ? A[row + (int64_t)col * lda] : 0.0;
-                int8_t d[OZ_S];
-                oz_digits(x, sh, d);
-#pragma unroll
-                for (int t = 0; t < OZ_S; ++t) pk[t][kk >> 2] |= (uint32_t)(uint8_t)d[t] << (8 * (kk & 3));
+                xv[kk] = (rv && col < K) ? A[row + (int64_t)col * lda] : 0.0;
             }
+#pragma unroll
+            for (int kk = 0; kk < 16; ++kk) oz_digits_packed(xv[kk], scale, kk & 3, pk[kk >> 2]);
             const int off = ((r >> 3) * 2 + kc) * 128 + (r & 7) * 16;
 #pragma unroll
             for (int t = 0; t < OZ_S; ++t)
-                *reinterpret_cast<uint4*>(tile0 + (int64_t)t * (TR * OZ_KB) + off) = make_uint4(pk[t][0], pk[t][1], pk[t][2], pk[t][3]);
+                *reinterpret_cast<uint4*>(tile0 + (int64_t)t * (TR * OZ_KB) + off) = make_uint4(pk[0][t], pk[1][t], pk[2][t], pk[3][t]);
         }
     }
 }
@@ -132,24 +146,28 @@ __global__ void __launch_bounds__(128) oz_slice_cols_kernel(const double* __rest
             const int cl = item >> 1, kc = item & 1;
             const int64_t c = cb * TR + cl;
             const bool cv = c < ncols;
-            const int sh = cv ? OZ_P - E[c] : 0;
+            const double scale = cv ? oz_scale_of(E[c]) : 0.0;
             const int64_t kbase = (int64_t)kb * OZ_KB + kc * 16;
             const double* x = X + (cv ? c : 0) * ldx + kbase;
-            uint32_t pk[OZ_S][4];
+            uint32_t pk[4][OZ_S];
 #pragma unroll
-            for (int t = 0; t < OZ_S; ++t) pk[t][0] = pk[t][1] = pk[t][2] = pk[t][3] = 0;
+            for (int q = 0; q < 4; ++q)
 #pragma unroll
-            for (int kk = 0; kk < 16; ++kk) {
-                const double v = (cv && kbase + kk < klen) ? x[kk] : 0.0;
-                int8_t d[OZ_S];
-                oz_digits(v, sh, d);
+                for (int t = 0; t < OZ_S; ++t) pk[q][t] = 0;
+            double xv[16];
+            if (cv && kbase + 16 <= klen && ((reinterpret_cast<uintptr_t>(x) & 15) == 0)) {
 #pragma unroll
-                for (int t = 0; t < OZ_S; ++t) pk[t][kk >> 2] |= (uint32_t)(uint8_t)d[t] << (8 * (kk & 3));
+                for (int kk = 0; kk < 16; kk += 2) { const double2 t2 = *reinterpret_cast<const double2*>(x + kk); xv[kk] = t2.x; xv[kk + 1] = t2.y; }
+            } else {
+#pragma unroll
+                for (int kk = 0; kk < 16; ++kk) xv[kk] = (cv && kbase + kk < klen) ? x[kk] : 0.0;
             }
+#pragma unroll
+            for (int kk = 0; kk < 16; ++kk) oz_digits_packed(xv[kk], scale, kk & 3, pk[kk >> 2]);
             const int off = ((cl >> 3) * 2 + kc) * 128 + (cl & 7) * 16;
 #pragma unroll
             for (int t = 0; t < OZ_S; ++t)
-                *reinterpret_cast<uint4*>(tile0 + (int64_t)t * (TR * OZ_KB) + off) = make_uint4(pk[t][0], pk[t][1], pk[t][2], pk[t][3]);
+                *reinterpret_cast<uint4*>(tile0 + (int64_t)t * (TR * OZ_KB) + off) = make_uint4(pk[0][t], pk[1][t], pk[2][t], pk[3][t]);
         }
     }
 }
@@ -172,8 +190,9 @@ __device__ __forceinline__ void oz_bulk_load(uint32_t dst, const void* src, uint
                  ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
 
-// grid: (first-operand row blocks, second-operand row blocks, groups).  Group g (TN: an accumulation chunk; NN: always 0) uses the
-// digit tiles a_tiles + g * a_group_stride (tile-row block blockIdx.x) and b_tiles + g * b_group_stride (block blockIdx.y), nkb K
+// grid: (second-operand row blocks, first-operand row blocks, groups) — the CTAs that share the (larger) first-operand tiles are
+// adjacent in launch order, so those tiles are fetched from HBM once and hit L2 for the other N tiles.  Group g (TN: an accumulation chunk; NN: always 0) uses the
+// digit tiles a_tiles + g * a_group_stride (tile-row block blockIdx.y) and b_tiles + g * b_group_stride (block blockIdx.x), nkb K
 // blocks each.  Output: out[g * out_group_stride + i + j * ldo] = alpha * 2^(Ea[g*ea_stride + i] + Eb[g*eb_stride + j] - 12) * sum + beta * out
 // for i < rows_a, j < rows_b.
 __global__ void __launch_bounds__(128, 1)
@@ -185,8 +204,8 @@ ozaki_mma_kernel(const int8_t* __restrict__ a_tiles, int64_t a_group_stride, con
     __shared__ uint32_t tmem_base_sh;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int g = blockIdx.z;
-    const int8_t* ga = a_tiles + g * a_group_stride + (int64_t)blockIdx.x * nkb * (OZ_S * OZ_TILE_A);
-    const int8_t* gb = b_tiles + g * b_group_stride + (int64_t)blockIdx.y * nkb * (OZ_S * OZ_TILE_B);
+    const int8_t* ga = a_tiles + g * a_group_stride + (int64_t)blockIdx.y * nkb * (OZ_S * OZ_TILE_A);
+    const int8_t* gb = b_tiles + g * b_group_stride + (int64_t)blockIdx.x * nkb * (OZ_S * OZ_TILE_B);
 
     if (tid == 0) {
         for (int s = 0; s < OZ_STAGES; ++s) {
@@ -248,30 +267,34 @@ ozaki_mma_kernel(const int8_t* __restrict__ a_tiles, int64_t a_group_stride, con
     // ---- epilogue: TMEM lane = tile row; warp w reads lanes [32w, 32w + 32)
     oz_mbar_wait(oz_smem(&bar_acc), 0);
     asm volatile("tcgen05.fence::after_thread_sync;");
-    const int64_t i = (int64_t)blockIdx.x * OZ_BM + tid;
+    const int64_t i = (int64_t)blockIdx.y * OZ_BM + tid;
     const int ea = (i < rows_a) ? Ea[g * ea_stride + i] : 0;
     double* og = out + g * out_group_stride;
-    for (int c0 = 0; c0 < OZ_BN; c0 += 8) {
-        double v[8];
+    const uint32_t lane_addr = tmem + ((uint32_t)(warp * 32) << 16);
+    for (int c0 = 0; c0 < OZ_BN; c0 += 16) {
+        // all S diagonals of 16 columns in flight, one wait
+        uint32_t r[OZ_S][16];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] = 0.0;
-#pragma unroll
-        for (int d = OZ_S - 1; d >= 0; --d) {
-            uint32_t r[8];
-            const uint32_t addr = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(d * OZ_BN + c0);
-            asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                         : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "r"(addr));
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] = v[j] * 0.0078125 + (double)(int32_t)r[j];
+        for (int d = 0; d < OZ_S; ++d) {
+            asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                         : "=r"(r[d][0]), "=r"(r[d][1]), "=r"(r[d][2]), "=r"(r[d][3]), "=r"(r[d][4]), "=r"(r[d][5]), "=r"(r[d][6]), "=r"(r[d][7]),
+                           "=r"(r[d][8]), "=r"(r[d][9]), "=r"(r[d][10]), "=r"(r[d][11]), "=r"(r[d][12]), "=r"(r[d][13]), "=r"(r[d][14]), "=r"(r[d][15])
+                         : "r"(lane_addr + (uint32_t)(d * OZ_BN + c0)));
         }
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
         if (i < rows_a) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const int jj = blockIdx.y * OZ_BN + c0 + j;
+            for (int j = 0; j < 16; ++j) {
+                const int jj = blockIdx.x * OZ_BN + c0 + j;
                 if (jj < rows_b) {
+                    double v = 0.0;
+#pragma unroll
+                    for (int d = OZ_S - 1; d >= 0; --d) v = fma(v, 0.0078125, (double)(int32_t)r[d][j]);
+                    // v * 2^(ea + eb - 12), split in two exact power-of-two factors so that neither leaves the normal range early
+                    const int e = ea + Eb[g * eb_stride + jj] - 12;
+                    const int e1 = e / 2, e2 = e - e1;
+                    double val = alpha * ((v * oz_pow2(max(-1022, min(1023, e1)))) * oz_pow2(max(-1022, min(1023, e2))));
                     double* p = og + i + (int64_t)jj * ldo;
-                    double val = alpha * scalbn(v[j], ea + Eb[g * eb_stride + jj] - 12);
                     if (beta != 0.0) val += beta * (*p);
                     *p = val;
                 }
@@ -337,7 +360,7 @@ int ozaki_gemm_nn(Ctx* ctx, int64_t m, int64_t N, int64_t K, double alpha, const
             oz_slice_rows_kernel<OZ_BM><<<dim3(nrb, (nkb + 7) / 8), OZ_BM, 0, ctx->stream>>>(A + r0, lda, rows, (int)K, nkb, Ea, at);
         }
         LaunchScope ls(ctx, RLB200_TIMER_GEMM_NN);
-        ozaki_mma_kernel<<<dim3(nrb, nnb, 1), 128, OZ_STAGES * OZ_STAGE_BYTES, ctx->stream>>>(at, 0, bt, 0, nkb, Ea, 0, Eb, 0, rows, (int)N, C + r0, ldc,
+        ozaki_mma_kernel<<<dim3(nnb, nrb, 1), 128, OZ_STAGES * OZ_STAGE_BYTES, ctx->stream>>>(at, 0, bt, 0, nkb, Ea, 0, Eb, 0, rows, (int)N, C + r0, ldc,
                                                                                             0, alpha, beta);
         RLB_CUDA_OK(ctx, cudaGetLastError());
     }
@@ -384,7 +407,7 @@ int ozaki_gemm_tn(Ctx* ctx, int64_t m, int64_t N1, int64_t N2, double alpha, con
             }
         }
         LaunchScope ls(ctx, RLB200_TIMER_GEMM_TN);
-        ozaki_mma_kernel<<<dim3(nb1, nb2, g), 128, OZ_STAGES * OZ_STAGE_BYTES, ctx->stream>>>(xt, xs, yt, ys, nkb, Ex + c0 * N1, N1, Ey + c0 * N2, N2, N1,
+        ozaki_mma_kernel<<<dim3(nb2, nb1, g), 128, OZ_STAGES * OZ_STAGE_BYTES, ctx->stream>>>(xt, xs, yt, ys, nkb, Ex + c0 * N1, N1, Ey + c0 * N2, N2, N1,
                                                                                             (int)N2, part + c0 * total, N1, total, 1.0, 0.0);
         RLB_CUDA_OK(ctx, cudaGetLastError());
     }
