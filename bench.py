@@ -313,6 +313,9 @@ def main():
     ap.add_argument("--nnz", type=int, default=1, help="SASO non-zeros per column")
     ap.add_argument("--d-factor", type=float, default=None)
     ap.add_argument("--block", type=int, default=256, help="BQRRP block size")
+    ap.add_argument("--engine", default="i8", choices=["dmma", "i8"],
+                    help="tall fp64 products over A: tcgen05 int8 digit slices (default) or the fp64 DMMA pipe")
+    ap.add_argument("--digits", type=int, default=0, help="int8 digits per value (0 = default: 6 for fp64, 46 bits)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -358,6 +361,9 @@ def main():
         torch.cuda.set_device(0)
     dev = torch.device("cuda", torch.cuda.current_device())
     ctx = rl.Context(dev.index)
+    ctx.set_fp64_engine(args.engine)
+    ctx.set_i8_digits(args.digits)
+    config["fp64_engine"] = ("tcgen05 kind::i8 digit slices, %d digits" % (args.digits or 6)) if args.engine == "i8" else "DMMA fp64 pipe"
 
     def barrier():
         if dist is not None:

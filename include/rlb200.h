@@ -168,15 +168,19 @@ RLB200_API int rlb200_gemm_f64_dev(rlb200_ctx* ctx, int transa, int transb, int6
 RLB200_API int rlb200_gemm_f32_dev(rlb200_ctx* ctx, int transa, int transb, int64_t m, int64_t n, int64_t k, float alpha,
                         const float* A_dev, int64_t lda, const float* B_dev, int64_t ldb, float beta, float* C_dev, int64_t ldc);
 
-/* ---- the same blas::gemm call sites for fp64 on the tcgen05 tensor cores: operands are split on the fly into exact int8 digit
- *      slices (7 digits, 48 bits below each row's / column-chunk's largest magnitude), multiplied with tcgen05.mma.kind::i8 with
- *      exact int32 accumulation in TMEM and recombined in fp64 (Ozaki scheme; normwise DGEMM accuracy).  Shapes: NN (tall A) and
+/* ---- the same blas::gemm call sites on the tcgen05 tensor cores: operands are split on the fly into exact balanced base-256
+ *      int8 digit slices (S digits keep 8S-2 bits below each row's / column-chunk's largest magnitude), multiplied with
+ *      tcgen05.mma.kind::i8 with exact int32 accumulation in TMEM and recombined in fp64 (Ozaki scheme).  Shapes: NN (tall A) and
  *      TN (long contraction), as rlb200_gemm_f64_dev. */
 RLB200_API int rlb200_gemm_f64_i8_dev(rlb200_ctx* ctx, int transa, int transb, int64_t m, int64_t n, int64_t k, double alpha,
                            const double* A_dev, int64_t lda, const double* B_dev, int64_t ldb, double beta, double* C_dev, int64_t ldc);
-/* Engine used by the fp64 drivers (RS/RF/QB/RSVD) for their tall products: RLB200_FP64_DMMA (default) or RLB200_FP64_I8SLICES. */
+RLB200_API int rlb200_gemm_f32_i8_dev(rlb200_ctx* ctx, int transa, int transb, int64_t m, int64_t n, int64_t k, float alpha,
+                           const float* A_dev, int64_t lda, const float* B_dev, int64_t ldb, float beta, float* C_dev, int64_t ldc);
+/* Engine used by the drivers (RS/RF/QB/RSVD) for their tall products: RLB200_FP64_DMMA (default) or RLB200_FP64_I8SLICES. */
 enum { RLB200_FP64_DMMA = 0, RLB200_FP64_I8SLICES = 1 };
 RLB200_API int rlb200_set_fp64_engine(rlb200_ctx* ctx, int engine);
+/* Digits per value of the int8-slice engine: 0 = default (6 for fp64 storage: 46 bits; 4 for fp32: 30 bits), else 3..7. */
+RLB200_API int rlb200_set_i8_digits(rlb200_ctx* ctx, int digits);
 
 /* ---- a8/a9: Stabilization<T>::call(m, k, A) (rl_orth.hh:13-23): CholQRQ :68-98, HQRQ :144-164,
  *      PLUL :211-230.  In place on the m x k column-major A_dev (lda = m).

@@ -144,6 +144,10 @@ class Context:
         """Tall fp64 products of the drivers: "dmma" (default) or "i8" (tcgen05 int8 digit slices)."""
         self.check(self._lib.rlb200_set_fp64_engine(self._h, {"dmma": 0, "i8": 1}[engine]))
 
+    def set_i8_digits(self, digits):
+        """Digits per value of the int8-slice engine: 0 = default (6 for fp64 storage, 4 for fp32), else 3..7 (8*digits - 2 bits)."""
+        self.check(self._lib.rlb200_set_i8_digits(self._h, int(digits)))
+
     # ---- row sharding over torch.distributed -------------------------------------------------
     def set_shard(self, row_offset, m_global, group=None):
         """This rank holds rows [row_offset, row_offset + m_local) of an m_global-row A.  Gram / B^T / norm
@@ -326,7 +330,7 @@ def philox_stream(ctx: Context, state: RNGState, n: int):
 
 def gemm(ctx: Context, transa, transb, alpha, A, B, beta=0.0, C=None, engine="dmma"):
     """blas::gemm(ColMajor, ...) on column-major device tensors, shapes as BLAS defines them.
-    engine: "dmma" (fp64 tensor pipe) or "i8" (fp64 through tcgen05 int8 digit slices; fp64 only)."""
+    engine: "dmma" (fp64 tensor pipe) or "i8" (tcgen05 int8 digit slices)."""
     m = A.shape[1] if transa else A.shape[0]
     k = A.shape[0] if transa else A.shape[1]
     n = B.shape[0] if transb else B.shape[1]
@@ -334,7 +338,7 @@ def gemm(ctx: Context, transa, transb, alpha, A, B, beta=0.0, C=None, engine="dm
     if C is None:
         C = empty_f(m, n, A.dtype, A.device)
         beta = 0.0
-    fn = getattr(ctx._lib, f"rlb200_gemm_{_suffix(A.dtype)}_dev" if engine == "dmma" else "rlb200_gemm_f64_i8_dev")
+    fn = getattr(ctx._lib, f"rlb200_gemm_{_suffix(A.dtype)}_dev" if engine == "dmma" else f"rlb200_gemm_{_suffix(A.dtype)}_i8_dev")
     ctx.check(fn(ctx._h, int(transa), int(transb), m, n, k, alpha, A.data_ptr(), _ld(A), B.data_ptr(), _ld(B), beta, C.data_ptr(), _ld(C)))
     return C
 

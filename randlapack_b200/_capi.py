@@ -68,7 +68,10 @@ SIGNATURES = {
     "rlb200_philox_stream_dev": (c_int, [c_vp, P_u32, c_i64, c_vp]),
     "rlb200_gemm_f64_i8_dev": (c_int, [c_vp, c_int, c_int, c_i64, c_i64, c_i64, ctypes.c_double, c_vp, c_i64, c_vp, c_i64, ctypes.c_double, c_vp,
                                        c_i64]),
+    "rlb200_gemm_f32_i8_dev": (c_int, [c_vp, c_int, c_int, c_i64, c_i64, c_i64, ctypes.c_float, c_vp, c_i64, c_vp, c_i64, ctypes.c_float, c_vp,
+                                       c_i64]),
     "rlb200_set_fp64_engine": (c_int, [c_vp, c_int]),
+    "rlb200_set_i8_digits": (c_int, [c_vp, c_int]),
     "rlb200_dev_alloc": (c_int, [c_vp, ctypes.c_size_t, ctypes.POINTER(c_vp)]),
     "rlb200_dev_free": (c_int, [c_vp, c_vp]),
     "rlb200_copy_h2d": (c_int, [c_vp, c_vp, c_vp, ctypes.c_size_t]),

@@ -45,6 +45,9 @@ int rlb200_destroy(rlb200_ctx* ctx) {
     arena_destroy(ctx);
     if (ctx->ws) cudaFree(ctx->ws);
     if (ctx->hbox) cudaFreeHost(ctx->hbox);
+    oz_cache_destroy(ctx);
+    if (ctx->aux_stream) { cudaStreamSynchronize(ctx->aux_stream); cudaStreamDestroy(ctx->aux_stream); }
+    for (auto& e : ctx->aux_ev) if (e) cudaEventDestroy(e);
     for (auto& t : ctx->timers) { if (t.e0) cudaEventDestroy(t.e0); if (t.e1) cudaEventDestroy(t.e1); }
     delete ctx;
     return 0;
@@ -130,8 +133,16 @@ int rlb200_philox_stream_dev(rlb200_ctx* ctx, const uint32_t state[6], int64_t n
 int rlb200_gemm_f64_i8_dev(rlb200_ctx* ctx, int transa, int transb, int64_t m, int64_t n, int64_t k, double alpha, const double* A, int64_t lda,
                            const double* B, int64_t ldb, double beta, double* C, int64_t ldc) {
     CTX_OK(ctx); RLB_CHECK(bind(ctx));
-    if (!transa && !transb) return ozaki_gemm_nn(ctx, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc);
-    if (transa && !transb) return ozaki_gemm_tn(ctx, k, m, n, alpha, A, lda, B, ldb, beta, C, ldc);
+    if (!transa && !transb) return ozaki_gemm_nn<double>(ctx, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc);
+    if (transa && !transb) return ozaki_gemm_tn<double>(ctx, k, m, n, alpha, A, lda, B, ldb, beta, C, ldc);
+    ctx->err = "only the NN (tall) and TN (long contraction) shapes of the path are offered";
+    return RLB200_ERR_UNSUPPORTED;
+}
+int rlb200_gemm_f32_i8_dev(rlb200_ctx* ctx, int transa, int transb, int64_t m, int64_t n, int64_t k, float alpha, const float* A, int64_t lda,
+                           const float* B, int64_t ldb, float beta, float* C, int64_t ldc) {
+    CTX_OK(ctx); RLB_CHECK(bind(ctx));
+    if (!transa && !transb) return ozaki_gemm_nn<float>(ctx, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc);
+    if (transa && !transb) return ozaki_gemm_tn<float>(ctx, k, m, n, alpha, A, lda, B, ldb, beta, C, ldc);
     ctx->err = "only the NN (tall) and TN (long contraction) shapes of the path are offered";
     return RLB200_ERR_UNSUPPORTED;
 }
@@ -139,6 +150,12 @@ int rlb200_set_fp64_engine(rlb200_ctx* ctx, int engine) {
     CTX_OK(ctx);
     RLB_REQUIRE(ctx, engine == RLB200_FP64_DMMA || engine == RLB200_FP64_I8SLICES);
     ctx->fp64_engine = engine;
+    return 0;
+}
+int rlb200_set_i8_digits(rlb200_ctx* ctx, int digits) {
+    CTX_OK(ctx);
+    RLB_REQUIRE(ctx, digits == 0 || (digits >= 3 && digits <= 7));
+    ctx->i8_digits = digits;
     return 0;
 }
 

@@ -25,6 +25,17 @@ struct Timer {
 
 struct ArenaChunk { char* p; size_t cap; size_t used; };
 
+// exponents (and column sums of squares) of the constant data matrix of a driver call, kept across its passes (ozaki.cu)
+struct OzCacheEntry {
+    const void* ptr = nullptr;
+    int64_t m = 0, n = 0, ld = 0, L = 0;
+    int P = 0, elem = 0;
+    int* E = nullptr;
+    double* ss = nullptr;
+    size_t cap_e = 0, cap_s = 0;
+    bool valid = false;
+};
+
 struct Ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -44,6 +55,14 @@ struct Ctx {
     void* allreduce_user = nullptr;
     // fp64 tall-GEMM engine of the drivers: 0 = DMMA (fp64 tensor pipe), 1 = tcgen05 int8 digit slices (ozaki.cu)
     int fp64_engine = 0;
+    // digits per value of the int8-slice engine: 0 = default (6 for fp64 storage, 4 for fp32), else 3..7
+    int i8_digits = 0;
+    // second stream + events of the int8-slice engine: digit slicing of chunk c+1 runs beside the tensor-core kernel of chunk c
+    cudaStream_t aux_stream = nullptr;
+    cudaEvent_t aux_ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // fork, sliced[2], consumed[2]
+    // the matrix a driver declared constant for the duration of a scope (OzConstScope) and its cached exponents
+    const void* oz_const_ptr = nullptr;
+    OzCacheEntry oz_row, oz_col;
     // stats
     int64_t launches = 0;
     bool timers_on = false;

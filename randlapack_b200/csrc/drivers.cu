@@ -222,25 +222,14 @@ int stab_call(Ctx* ctx, int kind, int64_t m, int64_t k, T* A, bool cond_check, b
 template <typename T>
 static int tall_nn(Ctx* ctx, int64_t m, int64_t N, int64_t K, double alpha, const T* A, int64_t lda, const T* B, int64_t ldb, double beta, T* C,
                    int64_t ldc) {
-    if constexpr (sizeof(T) == 8) {
-        if (ctx->fp64_engine == RLB200_FP64_I8SLICES && m >= 1024)
-            return ozaki_gemm_nn(ctx, m, N, K, alpha, (const double*)A, lda, (const double*)B, ldb, beta, (double*)C, ldc);
-    }
+    if (ctx->fp64_engine == RLB200_FP64_I8SLICES && m >= 1024) return ozaki_gemm_nn<T>(ctx, m, N, K, alpha, A, lda, B, ldb, beta, C, ldc);
     return gemm_nn<T>(ctx, m, N, K, alpha, A, lda, B, ldb, beta, C, ldc);
 }
 template <typename T>
 static int tall_tn(Ctx* ctx, int64_t m, int64_t N1, int64_t N2, double alpha, const T* A, int64_t lda, const T* B, int64_t ldb, double beta, T* C,
                    int64_t ldc, double* a_sumsq_out = nullptr) {
-    if constexpr (sizeof(T) == 8) {
-        if (ctx->fp64_engine == RLB200_FP64_I8SLICES && m >= 1024) {
-            if (a_sumsq_out) {
-                ArenaScope as(ctx);
-                double* part = as.take<double>(sumsq_ws_doubles(ctx)); if (!part) return RLB200_ERR_ALLOC;
-                RLB_CHECK(sumsq<T>(ctx, A, m, N1, lda, part, a_sumsq_out));
-            }
-            return ozaki_gemm_tn(ctx, m, N1, N2, alpha, (const double*)A, lda, (const double*)B, ldb, beta, (double*)C, ldc);
-        }
-    }
+    if (ctx->fp64_engine == RLB200_FP64_I8SLICES && m >= 1024)
+        return ozaki_gemm_tn<T>(ctx, m, N1, N2, alpha, A, lda, B, ldb, beta, C, ldc, a_sumsq_out);
     return gemm_tn<T>(ctx, m, N1, N2, alpha, A, lda, B, ldb, beta, C, ldc, 0, a_sumsq_out);
 }
 
@@ -262,6 +251,7 @@ int rs_call(Ctx* ctx, int64_t m, int64_t n, const T* A, int64_t k, T* Omega, T* 
     const int64_t p = o.passes_over_data, q = o.passes_per_stab;
     RLB_REQUIRE(ctx, p >= 0 && (p == 0 || q >= 1));
     RLB_REQUIRE(ctx, p == 0 || work != nullptr);
+    OzConstScope a_const(ctx, A);
     const bool sharded = ctx->m_global >= 0;
     const int64_t mg = sharded ? ctx->m_global : m;
     int64_t p_done = 0;
@@ -332,6 +322,7 @@ int rs_call(Ctx* ctx, int64_t m, int64_t n, const T* A, int64_t k, T* Omega, T* 
 template <typename T>
 int rf_call(Ctx* ctx, int64_t m, int64_t n, const T* A, int64_t k, T* Q, uint32_t state[6], const rlb200_stack_opts& o) {
     RLB_REQUIRE(ctx, m > 0 && n > 0 && k > 0);
+    OzConstScope a_const(ctx, A);
     ArenaScope as(ctx);
     T* Omega = as.take<T>(n * k); RLB_ALLOC(ctx, Omega);
     // RS's m x k scratch (Omega_1) lives in Q, which is overwritten afterwards anyway
@@ -407,6 +398,7 @@ int qb_call(Ctx* ctx, int64_t m, int64_t n, T* A, int64_t* k_io, int64_t b_sz, T
         next_sz = curr_sz + b_sz;
         T* Q_i = Q + m * curr_sz;
         T* BT_i = BT + n * curr_sz;
+        OzConstScope a_const(ctx, A_work);     // A_work is constant until the deflation at the end of the block
         int rc = rf_call<T>(ctx, m, n, A_work, b_sz, Q_i, state, o);             // :191
         if (rc < 0) return rc;
         if (rc) { *k_io = curr_sz; return 6; }
@@ -446,8 +438,10 @@ int qb_call(Ctx* ctx, int64_t m, int64_t n, T* A, int64_t* k_io, int64_t b_sz, T
         if (approx_err < tol) { *k_io = curr_sz; return 0; }                      // :250-256
         // A_work -= Q_i BT_i^T (:260) — only needed when another block follows (the reference also runs it after
         // the last block, where its result is never read)
-        if (curr_sz < k)
+        if (curr_sz < k) {
+            ctx->oz_row.valid = false; ctx->oz_col.valid = false;
             RLB_CHECK(gemm_nt<T>(ctx, m, n, b_sz, -1.0, Q_i, m, BT_i, n, 1.0, A_work, m));
+        }
     }
     return 3;
 }
@@ -464,6 +458,7 @@ static int rsvd_single_block_fused(Ctx* ctx, int64_t m, int64_t n, T* A, int64_t
     const bool sharded = ctx->m_global >= 0;
     const int64_t k = *k_io;
     const T tol = std::max(tol_in, (T)100 * std::numeric_limits<T>::epsilon());       // rl_qb.hh:149
+    OzConstScope a_const(ctx, A);
     ArenaScope as(ctx);
     T* Omega = as.take<T>(n * k); RLB_ALLOC(ctx, Omega);
     T* R = as.take<T>(k * k); RLB_ALLOC(ctx, R);

@@ -37,11 +37,24 @@ int plul(Ctx* ctx, int64_t m, int64_t n, T* A, int64_t lda, void* ws);
 template <typename T>
 int svd_tall(Ctx* ctx, int64_t n, int64_t k, T* B, int64_t ldb, T* S, T* W, void* ws, int* sweeps_out);
 
-// ---- fp64 GEMMs on tcgen05 int8 tensor cores through exact digit slices (ozaki.cu) -------------------
-int ozaki_gemm_nn(Ctx* ctx, int64_t m, int64_t N, int64_t K, double alpha, const double* A, int64_t lda, const double* B, int64_t ldb, double beta,
-                  double* C, int64_t ldc);
-int ozaki_gemm_tn(Ctx* ctx, int64_t m, int64_t N1, int64_t N2, double alpha, const double* X, int64_t ldx, const double* Y, int64_t ldy, double beta,
-                  double* C, int64_t ldc);
+// ---- tall GEMMs on tcgen05 int8 tensor cores through exact digit slices (ozaki.cu) ------------------------
+template <typename T>
+int ozaki_gemm_nn(Ctx* ctx, int64_t m, int64_t N, int64_t K, double alpha, const T* A, int64_t lda, const T* B, int64_t ldb, double beta,
+                  T* C, int64_t ldc);
+// x_sumsq_out (device scalar, optional): ||X||_F^2, accumulated in the exponent pass over X (no extra sweep)
+template <typename T>
+int ozaki_gemm_tn(Ctx* ctx, int64_t m, int64_t N1, int64_t N2, double alpha, const T* X, int64_t ldx, const T* Y, int64_t ldy, double beta,
+                  T* C, int64_t ldc, double* x_sumsq_out = nullptr);
+void oz_cache_destroy(Ctx* ctx);
+// While alive, the first operand `A` of the tall products is known not to change: its row / column-chunk exponents are computed once
+// and reused by every pass (outermost scope wins; nested scopes on the same or another pointer are no-ops).
+struct OzConstScope {
+    Ctx* ctx; bool owner;
+    OzConstScope(Ctx* c, const void* A) : ctx(c), owner(c->oz_const_ptr == nullptr) {
+        if (owner) { c->oz_const_ptr = A; c->oz_row.valid = false; c->oz_col.valid = false; }
+    }
+    ~OzConstScope() { if (owner) { ctx->oz_const_ptr = nullptr; ctx->oz_row.valid = false; ctx->oz_col.valid = false; } }
+};
 
 // ---- sketch-apply (sketch.cu) -----------------------------------------------------------------------
 template <typename T>

@@ -1,173 +1,242 @@
-// fp64 tall-skinny GEMMs on the 5th-generation tensor cores: tcgen05.mma.kind::i8 on error-free int8 slices (Ozaki scheme).
+// Tall-skinny GEMMs of the path on the 5th-generation tensor cores: tcgen05.mma.kind::i8 on error-free int8 digit slices
+// (Ozaki scheme), for fp64 and fp32 storage.
 //
 // sm_100a has no fp64 kind of tcgen05.mma; its fp64 pipe (DMMA, gemm.cu) peaks at 37 TFLOP/s measured, its int8 tensor pipe at
-// 4.5 Pop/s nominal.  An fp64 operand x with a scale 2^E bounding its group is written EXACTLY as fixed-point digits
-//     x * 2^(P-E) ~ F = sum_t d_t * 128^(S-1-t),   d_t in [-64, 64] (int8),  P = 7S - 1,
+// 4.5 Pop/s nominal.  An operand value x with a power-of-two scale 2^E bounding its group (|x| < 2^E) is written EXACTLY as
+// fixed-point balanced base-256 digits
+//     rn(x * 2^(P-E)) = F = sum_t d_t * 256^(S-1-t),   d_t in [-128, 127] (int8),  P = 8S - 2,
 // so a product over K terms becomes S(S+1)/2 int8 GEMMs (digit pairs s + t <= S - 1) whose int32 accumulation in TMEM is exact
-// (|d d'| <= 2^12, K <= 2^16 per accumulation group, <= S products per anti-diagonal), recombined in fp64 in the epilogue:
-//     C_ij = 2^(EA_i + EB_j - 12) * sum_d 128^(-d) * acc_d(i, j).
-// S = 7 keeps 48 bits below each group's largest magnitude (truncation ~ 128^-7 = 2e-15 relative to max|a| max|b| per term):
-// the result is normwise as accurate as a DGEMM, at 28 int8 MMAs per fp64 MMA-equivalent (4.5 P / 28 = 160 TF nominal ceiling).
+// (|d d'| <= 2^14, <= S products per anti-diagonal and k, K <= 2^14 per accumulation group), recombined in fp64 in the epilogue:
+//     C_ij = 2^(EA_i + EB_j - 12) * sum_d 256^(-d) * acc_d(i, j).
+// S = 6 (default for fp64) keeps 46 bits below each group's largest magnitude at 21 int8 MMAs per fp64 MMA-equivalent
+// (4.5 P / 21 = 214 TF nominal ceiling); S = 7 keeps 54 bits (every mantissa bit of entries within 2x of the group maximum) at 28;
+// S = 4 holds an fp32 mantissa with 6 guard bits at 10.
 //
 //   NN  (rl_rs.hh:153, rl_rf.hh:123):  C(m x N) = A(m x K) B(K x N)        scales: per row of A, per column of B
 //   TN  (rl_rs.hh:165, rl_qb.hh:218):  C(N1 x N2) = X(m x N1)^T Y(m x N2)   scales: per column and per chunk of L rows (int32 range),
 //                                                                            fp64 accumulation across chunks in a fixed order
 //
-// Pipeline per product: (1) max-magnitude pre-pass -> exponents; (2) slicer kernels write the digits to HBM pre-tiled in the
+// Pipeline per product: (1) exponent pre-pass (biased-exponent maxima); (2) slicer kernels write the digits to HBM pre-tiled in the
 // tensor core's no-swizzle K-major core-matrix order (8 rows x 16 bytes), one contiguous block per pipeline stage, so the GEMM
-// kernel needs no tensor maps: (3) ozaki_mma_kernel: one thread streams stages with cp.async.bulk + mbarrier and issues the
-// tcgen05.mma's; accumulators (S anti-diagonals x 64 columns) live in TMEM; four warps run the fp64 epilogue from tcgen05.ld.
+// kernel needs no tensor maps; (3) ozaki_mma_kernel: a producer thread streams stages with cp.async.bulk + mbarrier, an issuer thread
+// drives the tensor core.  The S digit tiles of the second operand are contiguous in a stage, i.e. they form ONE stacked K-major
+// tile of 64*S rows, so digit s of the first operand is multiplied with digits 0..S-1-s of the second in ceil((S-s)/4)
+// instructions of N <= 256 whose output columns are exactly the accumulators of anti-diagonals s..S-1 (S*64 TMEM columns):
+// 8 instructions per K step for S = 6 instead of 21, and the first-operand tile is read from shared memory 8 times, not 21.
+// Four warps run the fp64 epilogue from tcgen05.ld.
 #include "drivers.cuh"
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 
 namespace rlb {
 
-constexpr int OZ_S = 7;            // digits per value
-constexpr int OZ_P = 7 * OZ_S - 1; // fixed-point bits below the group scale
 constexpr int OZ_KB = 32;          // K bytes (= int8 elements) per stage = one tcgen05.mma K step
 constexpr int OZ_BM = 128;         // UMMA M: tile rows of the first operand
-constexpr int OZ_BN = 64;          // UMMA N: tile rows of the second operand
-constexpr int OZ_STAGES = 5;
+constexpr int OZ_BN = 64;          // tile rows of the second operand (per digit)
 constexpr int OZ_TILE_A = OZ_BM * OZ_KB;   // bytes of one digit tile of the first operand
 constexpr int OZ_TILE_B = OZ_BN * OZ_KB;
-constexpr int OZ_STAGE_BYTES = OZ_S * (OZ_TILE_A + OZ_TILE_B);
-constexpr int OZ_TMEM_COLS = 512;          // S * 64 = 448 accumulator columns -> next power of two
-constexpr int64_t OZ_CHUNK = 32768;        // rows per int32 accumulation group of the TN product (7 * 2^15 * 2^12 < 2^31)
+constexpr int64_t OZ_CHUNK = 16384;        // rows per int32 accumulation group of the TN product (7 * 2^14 * 2^14 < 2^31)
+constexpr int64_t OZ_KMAX = 16384;         // largest K of one NN accumulation group
+constexpr int OZ_SMEM_BUDGET = 225 * 1024;
+
+template <int S>
+struct OzCfg {
+    static_assert(S >= 2 && S <= 7, "digits");
+    static constexpr int P = 8 * S - 2;                       // fixed-point bits below the group scale
+    static constexpr int STAGE_BYTES = S * (OZ_TILE_A + OZ_TILE_B);
+    static constexpr int STAGES = (OZ_SMEM_BUDGET / STAGE_BYTES) > 12 ? 12 : (OZ_SMEM_BUDGET / STAGE_BYTES);
+    static constexpr int ACC_COLS = S * OZ_BN;
+    static constexpr int TMEM_COLS = ACC_COLS <= 128 ? 128 : (ACC_COLS <= 256 ? 256 : 512);
+    // 0x80 in each of the S-1 low bytes: added as a bias it makes those bytes the unsigned digits d + 128, xor-ed it re-centres them
+    static constexpr unsigned long long LOWMASK = 0x8080808080808080ull >> (8 * (9 - S));
+};
 
 __device__ __forceinline__ uint32_t oz_smem(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 // ------------------------------------------------------------------------------------------------
-// exponents
+// exponents.  Stored value E = max(biased exponent - 1022, P - 1023): |x| < 2^E for the whole group, and 2^(P-E) is a normal
+// double (groups whose largest magnitude is below 2^(P-1023) keep fewer digits).
 // ------------------------------------------------------------------------------------------------
-// E such that |x| < 2^E for every |x| <= mx (mx > 0); mx == 0 -> 0
-__device__ __forceinline__ int oz_exp_of(double mx) {
-    if (!(mx > 0.0)) return 0;
-    int e;
-    frexp(mx, &e);
-    return e;
-}
+template <typename T>
+__device__ __forceinline__ int oz_expfield(T x) { return (int)((__double_as_longlong((double)x) >> 52) & 0x7ff); }
+__device__ __forceinline__ int oz_exp_from_field(int f, int P) { return max(f - 1022, P - 1023); }
 
-// E_row[i] for rows [r0, r0 + rows) of A (col-major, lda), K columns.  One thread per row, coalesced across rows.
-__global__ void __launch_bounds__(256) oz_rowmax_kernel(const double* __restrict__ A, int64_t lda, int64_t rows, int K, int* __restrict__ E) {
+// E_row[i] for rows [0, rows) of A (col-major, lda), K columns.  One thread per row, coalesced across rows.
+template <typename T>
+__global__ void __launch_bounds__(256) oz_rowexp_kernel(const T* __restrict__ A, int64_t lda, int64_t rows, int K, int P, int* __restrict__ E) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= rows) return;
-    double mx = 0.0;
-    for (int c = 0; c < K; ++c) mx = fmax(mx, fabs(A[i + (int64_t)c * lda]));
-    E[i] = oz_exp_of(mx);
+    int f = 0;
+    int c = 0;
+    for (; c + 4 <= K; c += 4) {
+        const T a0 = A[i + (int64_t)c * lda], a1 = A[i + (int64_t)(c + 1) * lda], a2 = A[i + (int64_t)(c + 2) * lda], a3 = A[i + (int64_t)(c + 3) * lda];
+        f = max(max(f, oz_expfield(a0)), max(oz_expfield(a1), max(oz_expfield(a2), oz_expfield(a3))));
+    }
+    for (; c < K; ++c) f = max(f, oz_expfield(A[i + (int64_t)c * lda]));
+    E[i] = oz_exp_from_field(f, P);
 }
 // E[chunk * ncols + c] over rows [chunk*L, (chunk+1)*L) of column c of X (col-major).  One warp per (column, chunk).
-__global__ void __launch_bounds__(256) oz_colmax_kernel(const double* __restrict__ X, int64_t ldx, int64_t rows, int ncols, int64_t L, int nchunks,
-                                                        int* __restrict__ E) {
+// ss (optional): sum of squares of the same entries, same indexing (fixed summation order).
+template <typename T>
+__global__ void __launch_bounds__(256) oz_colexp_kernel(const T* __restrict__ X, int64_t ldx, int64_t rows, int ncols, int64_t L, int nchunks, int P,
+                                                        int* __restrict__ E, double* __restrict__ ss) {
     const int lane = threadIdx.x & 31;
     const int64_t w = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
     if (w >= (int64_t)ncols * nchunks) return;
     const int c = (int)(w % ncols), ch = (int)(w / ncols);
     const int64_t r0 = (int64_t)ch * L, r1 = min(rows, r0 + L);
-    const double* x = X + (int64_t)c * ldx;
-    double mx = 0.0;
-    for (int64_t r = r0 + lane; r < r1; r += 32) mx = fmax(mx, fabs(x[r]));
+    const T* x = X + (int64_t)c * ldx;
+    int f = 0;
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    int64_t r = r0 + lane;
+    for (; r + 96 < r1; r += 128) {
+        const double a0 = (double)x[r], a1 = (double)x[r + 32], a2 = (double)x[r + 64], a3 = (double)x[r + 96];
+        f = max(max(f, oz_expfield(a0)), max(oz_expfield(a1), max(oz_expfield(a2), oz_expfield(a3))));
+        s0 = fma(a0, a0, s0); s1 = fma(a1, a1, s1); s2 = fma(a2, a2, s2); s3 = fma(a3, a3, s3);
+    }
+    for (; r < r1; r += 32) { const double a0 = (double)x[r]; f = max(f, oz_expfield(a0)); s0 = fma(a0, a0, s0); }
+    f = __reduce_max_sync(0xffffffffu, f);
+    if (ss) {
+        double sv = (s0 + s1) + (s2 + s3);
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-    if (lane == 0) E[(int64_t)ch * ncols + c] = oz_exp_of(mx);
+        for (int o = 16; o > 0; o >>= 1) sv += __shfl_xor_sync(0xffffffffu, sv, o);
+        if (lane == 0) ss[(int64_t)ch * ncols + c] = sv;
+    }
+    if (lane == 0) E[(int64_t)ch * ncols + c] = oz_exp_from_field(f, P);
+}
+// out[0] = sum of v[0..n) in a fixed order (one CTA)
+__global__ void __launch_bounds__(1024) oz_sum_kernel(const double* __restrict__ v, int64_t n, double* __restrict__ out) {
+    __shared__ double sh[1024];
+    double s = 0.0;
+    for (int64_t i = threadIdx.x; i < n; i += 1024) s += v[i];
+    sh[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = 512; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[0] = sh[0];
 }
 
 // ------------------------------------------------------------------------------------------------
 // slicers.  Digit tiles: tile (rb, kb, t) of TR rows x 32 K-bytes at ((rb * nkb + kb) * S + t) * TR * 32, inside it the byte of
 // (row r, k) sits at ((r / 8) * 2 + k / 16) * 128 + (r % 8) * 16 + k % 16  (K-major, no swizzle: SBO = 256 B, LBO = 128 B).
 // ------------------------------------------------------------------------------------------------
-// digits of one value.  `scale` = 2^(P - E) (exact power of two), |x * scale| <= 2^P = 2^48.
-//   y = x * scale + 1.5 * 2^52   puts F = rn(x * scale) (two's complement) in the low mantissa bits of y;
-//   adding BIAS = sum_t 64 * 128^t makes every 7-bit field u_t = d_t + 64 non-negative, so the digits are plain shifts and masks
-//   (the top field is left unmasked: it may reach 128, i.e. d_0 = 64, which is a valid int8).
-// Returned packed: digit t of this value in byte lane `lane` (0..3) of w[t], already re-centred (u - 64 as two's complement byte).
-constexpr long long OZ_MAGIC_BITS = 0x4338000000000000ll;                       // bit pattern of 1.5 * 2^52
-constexpr long long OZ_BIAS = 64ll * ((1ll << 49) - 1) / 127;                   // sum_{t<7} 64 * 128^t
-__device__ __forceinline__ void oz_digits_packed(double x, double scale, int lane, uint32_t* w /* [S] */) {
-    const double y = fma(x, scale, 6755399441055744.0);
-    const unsigned long long Fp = (unsigned long long)(__double_as_longlong(y) - OZ_MAGIC_BITS + OZ_BIAS);
-    const int sh8 = lane * 8;
-#pragma unroll
-    for (int t = 0; t < OZ_S; ++t) {
-        uint32_t u = (uint32_t)(Fp >> (7 * (OZ_S - 1 - t)));
-        if (t > 0) u &= 127u;
-        w[t] |= ((u - 64u) & 0xFFu) << sh8;
-    }
-}
 __device__ __forceinline__ double oz_pow2(int e) {      // 2^e for e in [-1022, 1023]
     return __longlong_as_double((long long)(e + 1023) << 52);
 }
-// scale = 2^(P - E), clamped to the normal range (inputs below 2^-970 of magnitude lose digits, never correctness of the bound)
-__device__ __forceinline__ double oz_scale_of(int E) { return oz_pow2(max(-1022, min(1023, OZ_P - E))); }
+// F + bias as raw bits: byte b (b < S - 1) is the unsigned digit d + 128 of weight 256^b, byte S - 1 the (two's complement) top digit.
+template <int S>
+__device__ __forceinline__ unsigned long long oz_fixed(double x, double scale) {
+    unsigned long long F;
+    if constexpr (OzCfg<S>::P <= 50) {
+        // x * scale + 1.5 * 2^52 leaves rn(x * scale) (two's complement) in the low mantissa bits
+        F = (unsigned long long)__double_as_longlong(fma(x, scale, 6755399441055744.0)) - 0x4338000000000000ull;
+    } else {
+        F = (unsigned long long)__double2ll_rn(x * scale);
+    }
+    return (F + OzCfg<S>::LOWMASK) ^ OzCfg<S>::LOWMASK;
+}
+// digits of 4 consecutive-k values -> w[t] = the 4 bytes of digit t (t = 0 most significant), k order = byte order
+template <int S>
+__device__ __forceinline__ void oz_pack4(const unsigned long long f[4], uint32_t* w /* [S] */) {
+    uint32_t lo[4], hi[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) { lo[e] = (uint32_t)f[e]; hi[e] = (uint32_t)(f[e] >> 32); }
+    uint32_t B[8];
+    {
+        const uint32_t t0 = __byte_perm(lo[0], lo[1], 0x5140), t1 = __byte_perm(lo[2], lo[3], 0x5140);
+        const uint32_t t2 = __byte_perm(lo[0], lo[1], 0x7362), t3 = __byte_perm(lo[2], lo[3], 0x7362);
+        B[0] = __byte_perm(t0, t1, 0x5410); B[1] = __byte_perm(t0, t1, 0x7632);
+        B[2] = __byte_perm(t2, t3, 0x5410); B[3] = __byte_perm(t2, t3, 0x7632);
+    }
+    if constexpr (S > 4) {
+        const uint32_t t0 = __byte_perm(hi[0], hi[1], 0x5140), t1 = __byte_perm(hi[2], hi[3], 0x5140);
+        const uint32_t t2 = __byte_perm(hi[0], hi[1], 0x7362), t3 = __byte_perm(hi[2], hi[3], 0x7362);
+        B[4] = __byte_perm(t0, t1, 0x5410); B[5] = __byte_perm(t0, t1, 0x7632);
+        B[6] = __byte_perm(t2, t3, 0x5410); B[7] = __byte_perm(t2, t3, 0x7632);
+    }
+#pragma unroll
+    for (int t = 0; t < S; ++t) w[t] = B[S - 1 - t];
+}
+// 16 consecutive-k values of one tile row -> one 16-byte chunk per digit
+template <int S>
+__device__ __forceinline__ void oz_emit16(const double* xv, double scale, int8_t* tile0, int64_t tile_bytes, int off) {
+    uint32_t pk[4][S];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        unsigned long long f[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) f[e] = oz_fixed<S>(xv[4 * q + e], scale);
+        oz_pack4<S>(f, pk[q]);
+    }
+#pragma unroll
+    for (int t = 0; t < S; ++t)
+        *reinterpret_cast<uint4*>(tile0 + (int64_t)t * tile_bytes + off) = make_uint4(pk[0][t], pk[1][t], pk[2][t], pk[3][t]);
+}
 
 // First operand of the NN product: tile rows = rows of A, K = columns of A, scale per row.  CTA = (row block, group of 8 K-blocks).
-template <int TR>
-__global__ void __launch_bounds__(TR) oz_slice_rows_kernel(const double* __restrict__ A, int64_t lda, int64_t rows, int K, int nkb,
-                                                           const int* __restrict__ E, int8_t* __restrict__ out) {
+template <int S, typename T>
+__global__ void __launch_bounds__(OZ_BM) oz_slice_rows_kernel(const T* __restrict__ A, int64_t lda, int64_t rows, int K, int nkb,
+                                                              const int* __restrict__ E, int8_t* __restrict__ out) {
+    constexpr int TR = OZ_BM;
     const int r = threadIdx.x;
     const int64_t rb = blockIdx.x;
     const int64_t row = rb * TR + r;
     const bool rv = row < rows;
-    const double scale = rv ? oz_scale_of(E[row]) : 0.0;
+    const double scale = rv ? oz_pow2(OzCfg<S>::P - E[row]) : 0.0;
+    const T* a = A + (rv ? row : 0);
     for (int kb = blockIdx.y * 8; kb < min(nkb, (int)blockIdx.y * 8 + 8); ++kb) {
-        int8_t* tile0 = out + ((rb * nkb + kb) * OZ_S) * (int64_t)(TR * OZ_KB);
+        int8_t* tile0 = out + ((rb * nkb + kb) * S) * (int64_t)(TR * OZ_KB);
+        T raw[32];
+#pragma unroll
+        for (int kk = 0; kk < 32; ++kk) {
+            const int col = kb * OZ_KB + kk;
+            raw[kk] = (rv && col < K) ? a[(int64_t)col * lda] : T(0);
+        }
 #pragma unroll
         for (int kc = 0; kc < 2; ++kc) {
-            uint32_t pk[4][OZ_S];
-#pragma unroll
-            for (int q = 0; q < 4; ++q)
-#pragma unroll
-                for (int t = 0; t < OZ_S; ++t) pk[q][t] = 0;
             double xv[16];
 #pragma unroll
-            for (int kk = 0; kk < 16; ++kk) {
-                const int col = kb * OZ_KB + kc * 16 + kk;
-                xv[kk] = (rv && col < K) ? A[row + (int64_t)col * lda] : 0.0;
-            }
-#pragma unroll
-            for (int kk = 0; kk < 16; ++kk) oz_digits_packed(xv[kk], scale, kk & 3, pk[kk >> 2]);
-            const int off = ((r >> 3) * 2 + kc) * 128 + (r & 7) * 16;
-#pragma unroll
-            for (int t = 0; t < OZ_S; ++t)
-                *reinterpret_cast<uint4*>(tile0 + (int64_t)t * (TR * OZ_KB) + off) = make_uint4(pk[0][t], pk[1][t], pk[2][t], pk[3][t]);
+            for (int kk = 0; kk < 16; ++kk) xv[kk] = (double)raw[kc * 16 + kk];
+            oz_emit16<S>(xv, scale, tile0, TR * OZ_KB, ((r >> 3) * 2 + kc) * 128 + (r & 7) * 16);
         }
     }
 }
 
-// Operands whose K runs along the contiguous direction: tile rows = columns of X, K = rows [k0, k0 + klen) of X, scale per column
+// Operands whose K runs along the contiguous direction: tile rows = columns of X, K = rows [0, klen) of X, scale per column
 // (E[c], already offset to the chunk).  CTA = (column block, group of 8 K-blocks); thread = (column, 16-element K chunk).
-template <int TR>
-__global__ void __launch_bounds__(128) oz_slice_cols_kernel(const double* __restrict__ X, int64_t ldx, int64_t klen, int ncols, int nkb,
+template <int S, int TR, typename T>
+__global__ void __launch_bounds__(128) oz_slice_cols_kernel(const T* __restrict__ X, int64_t ldx, int64_t klen, int ncols, int nkb,
                                                             const int* __restrict__ E, int8_t* __restrict__ out) {
     const int64_t cb = blockIdx.x;
     for (int kb = blockIdx.y * 8; kb < min(nkb, (int)blockIdx.y * 8 + 8); ++kb) {
-        int8_t* tile0 = out + ((cb * nkb + kb) * OZ_S) * (int64_t)(TR * OZ_KB);
+        int8_t* tile0 = out + ((cb * nkb + kb) * S) * (int64_t)(TR * OZ_KB);
         for (int item = threadIdx.x; item < TR * 2; item += 128) {
             const int cl = item >> 1, kc = item & 1;
             const int64_t c = cb * TR + cl;
             const bool cv = c < ncols;
-            const double scale = cv ? oz_scale_of(E[c]) : 0.0;
+            const double scale = cv ? oz_pow2(OzCfg<S>::P - E[c]) : 0.0;
             const int64_t kbase = (int64_t)kb * OZ_KB + kc * 16;
-            const double* x = X + (cv ? c : 0) * ldx + kbase;
-            uint32_t pk[4][OZ_S];
-#pragma unroll
-            for (int q = 0; q < 4; ++q)
-#pragma unroll
-                for (int t = 0; t < OZ_S; ++t) pk[q][t] = 0;
+            const T* x = X + (cv ? c : 0) * ldx + kbase;
             double xv[16];
             if (cv && kbase + 16 <= klen && ((reinterpret_cast<uintptr_t>(x) & 15) == 0)) {
+                if constexpr (sizeof(T) == 8) {
 #pragma unroll
-                for (int kk = 0; kk < 16; kk += 2) { const double2 t2 = *reinterpret_cast<const double2*>(x + kk); xv[kk] = t2.x; xv[kk + 1] = t2.y; }
+                    for (int kk = 0; kk < 16; kk += 2) { const double2 t2 = *reinterpret_cast<const double2*>(x + kk); xv[kk] = t2.x; xv[kk + 1] = t2.y; }
+                } else {
+#pragma unroll
+                    for (int kk = 0; kk < 16; kk += 4) {
+                        const float4 t4 = *reinterpret_cast<const float4*>(x + kk);
+                        xv[kk] = t4.x; xv[kk + 1] = t4.y; xv[kk + 2] = t4.z; xv[kk + 3] = t4.w;
+                    }
+                }
             } else {
 #pragma unroll
-                for (int kk = 0; kk < 16; ++kk) xv[kk] = (cv && kbase + kk < klen) ? x[kk] : 0.0;
+                for (int kk = 0; kk < 16; ++kk) xv[kk] = (cv && kbase + kk < klen) ? (double)x[kk] : 0.0;
             }
-#pragma unroll
-            for (int kk = 0; kk < 16; ++kk) oz_digits_packed(xv[kk], scale, kk & 3, pk[kk >> 2]);
-            const int off = ((cl >> 3) * 2 + kc) * 128 + (cl & 7) * 16;
-#pragma unroll
-            for (int t = 0; t < OZ_S; ++t)
-                *reinterpret_cast<uint4*>(tile0 + (int64_t)t * (TR * OZ_KB) + off) = make_uint4(pk[0][t], pk[1][t], pk[2][t], pk[3][t]);
+            oz_emit16<S>(xv, scale, tile0, TR * OZ_KB, ((cl >> 3) * 2 + kc) * 128 + (cl & 7) * 16);
         }
     }
 }
@@ -189,77 +258,105 @@ __device__ __forceinline__ void oz_bulk_load(uint32_t dst, const void* src, uint
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
+__device__ __forceinline__ void oz_bulk_load_mc(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, uint16_t mask) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void oz_cluster_sync() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void oz_mma_i8(uint32_t d_tmem, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}\n"
+                 ::"r"(d_tmem), "l"(da), "l"(db), "r"(idesc), "r"(acc) : "memory");
+}
 
 // grid: (second-operand row blocks, first-operand row blocks, groups) — the CTAs that share the (larger) first-operand tiles are
-// adjacent in launch order, so those tiles are fetched from HBM once and hit L2 for the other N tiles.  Group g (TN: an accumulation chunk; NN: always 0) uses the
-// digit tiles a_tiles + g * a_group_stride (tile-row block blockIdx.y) and b_tiles + g * b_group_stride (block blockIdx.x), nkb K
-// blocks each.  Output: out[g * out_group_stride + i + j * ldo] = alpha * 2^(Ea[g*ea_stride + i] + Eb[g*eb_stride + j] - 12) * sum + beta * out
+// adjacent in launch order, so those tiles are fetched from HBM once and hit L2 for the other N tiles.  Group g (TN: an
+// accumulation chunk; NN: always 0) uses the digit tiles a_tiles + g * a_group_stride (tile-row block blockIdx.y) and
+// b_tiles + g * b_group_stride (block blockIdx.x), nkb K blocks each.
+// Output: out[g * out_group_stride + i + j * ldo] = alpha * 2^(Ea[g*ea_stride + i] + Eb[g*eb_stride + j] - 12) * sum + beta * out
 // for i < rows_a, j < rows_b.
+// Launched with a thread-block cluster of cs CTAs along x (cs = 1, 2 or 4): the cs CTAs share the first-operand tiles, so each loads
+// 1/cs of every first-operand stage and multicasts it to the whole cluster (L2 -> SM traffic per CTA and K step drops from
+// S * 6 KB to S * (4/cs + 2) KB); a stage slot is free again when the tensor cores of ALL cs CTAs have consumed it (multicast commit).
+template <int S, typename TO>
 __global__ void __launch_bounds__(128, 1)
 ozaki_mma_kernel(const int8_t* __restrict__ a_tiles, int64_t a_group_stride, const int8_t* __restrict__ b_tiles, int64_t b_group_stride, int nkb,
                  const int* __restrict__ Ea, int64_t ea_stride, const int* __restrict__ Eb, int64_t eb_stride, int64_t rows_a, int rows_b,
-                 double* __restrict__ out, int64_t ldo, int64_t out_group_stride, double alpha, double beta) {
+                 TO* __restrict__ out, int64_t ldo, int64_t out_group_stride, double alpha, double beta) {
+    using Cfg = OzCfg<S>;
+    constexpr int STAGES = Cfg::STAGES;
     extern __shared__ __align__(1024) unsigned char oz_smem_raw[];
-    __shared__ __align__(8) uint64_t bar_full[OZ_STAGES], bar_empty[OZ_STAGES], bar_acc;
+    __shared__ __align__(8) uint64_t bar_full[STAGES], bar_empty[STAGES], bar_acc;
     __shared__ uint32_t tmem_base_sh;
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, warp = tid >> 5;
     const int g = blockIdx.z;
-    const int8_t* ga = a_tiles + g * a_group_stride + (int64_t)blockIdx.y * nkb * (OZ_S * OZ_TILE_A);
-    const int8_t* gb = b_tiles + g * b_group_stride + (int64_t)blockIdx.x * nkb * (OZ_S * OZ_TILE_B);
+    uint32_t cs, crank;
+    asm volatile("mov.u32 %0, %%cluster_nctaid.x;" : "=r"(cs));
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
+    const uint16_t cmask = (uint16_t)((1u << cs) - 1u);
+    const int8_t* ga = a_tiles + g * a_group_stride + (int64_t)blockIdx.y * nkb * (S * OZ_TILE_A);
+    const int8_t* gb = b_tiles + g * b_group_stride + (int64_t)blockIdx.x * nkb * (S * OZ_TILE_B);
 
     if (tid == 0) {
-        for (int s = 0; s < OZ_STAGES; ++s) {
+        for (int s = 0; s < STAGES; ++s) {
             asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(oz_smem(&bar_full[s])));
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(oz_smem(&bar_empty[s])));
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(oz_smem(&bar_empty[s])), "r"(cs));
         }
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(oz_smem(&bar_acc)));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(oz_smem(&tmem_base_sh)), "n"(OZ_TMEM_COLS));
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(oz_smem(&tmem_base_sh)), "n"(Cfg::TMEM_COLS));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
     asm volatile("tcgen05.fence::before_thread_sync;");
     __syncthreads();
+    if (cs > 1) oz_cluster_sync();      // every CTA's barriers are initialised before any peer multicasts into them
     asm volatile("tcgen05.fence::after_thread_sync;");
     const uint32_t tmem = tmem_base_sh;
+    const uint32_t sbase = oz_smem(oz_smem_raw);
 
     if (tid == 0) {
-        const uint32_t sbase = oz_smem(oz_smem_raw);
-        // s32 accumulate, signed int8 A and B, both K-major, N = 64, M = 128 (cute/arch/mma_sm100_desc.hpp InstrDescriptor)
-        const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(OZ_BN >> 3) << 17) | ((uint32_t)(OZ_BM >> 4) << 24);
-        auto load_stage = [&](int kb) {
-            const int slot = kb % OZ_STAGES;
-            const uint32_t bar = oz_smem(&bar_full[slot]);
-            const uint32_t dst = sbase + slot * OZ_STAGE_BYTES;
-            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)OZ_STAGE_BYTES) : "memory");
-            oz_bulk_load(dst, ga + (int64_t)kb * (OZ_S * OZ_TILE_A), OZ_S * OZ_TILE_A, bar);
-            oz_bulk_load(dst + OZ_S * OZ_TILE_A, gb + (int64_t)kb * (OZ_S * OZ_TILE_B), OZ_S * OZ_TILE_B, bar);
-        };
-        for (int kb = 0; kb < min(nkb, OZ_STAGES); ++kb) load_stage(kb);
+        // ---- producer: one bulk copy per operand per stage
         for (int kb = 0; kb < nkb; ++kb) {
-            const int slot = kb % OZ_STAGES;
-            oz_mbar_wait(oz_smem(&bar_full[slot]), (uint32_t)((kb / OZ_STAGES) & 1));
+            const int slot = kb % STAGES;
+            if (kb >= STAGES) oz_mbar_wait(oz_smem(&bar_empty[slot]), (uint32_t)(((kb / STAGES) - 1) & 1));
+            const uint32_t bar = oz_smem(&bar_full[slot]);
+            const uint32_t dst = sbase + slot * Cfg::STAGE_BYTES;
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)Cfg::STAGE_BYTES) : "memory");
+            if (cs == 1) {
+                oz_bulk_load(dst, ga + (int64_t)kb * (S * OZ_TILE_A), S * OZ_TILE_A, bar);
+            } else {
+                const uint32_t piece = (uint32_t)(S * OZ_TILE_A) / cs;
+                oz_bulk_load_mc(dst + crank * piece, ga + (int64_t)kb * (S * OZ_TILE_A) + crank * piece, piece, bar, cmask);
+            }
+            oz_bulk_load(dst + S * OZ_TILE_A, gb + (int64_t)kb * (S * OZ_TILE_B), S * OZ_TILE_B, bar);
+        }
+    } else if (tid == 32) {
+        // ---- issuer.  s32 accumulate, signed int8 A and B, both K-major, M = 128 (cute/arch/mma_sm100_desc.hpp InstrDescriptor)
+        const uint32_t idesc0 = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(OZ_BM >> 4) << 24);
+        for (int kb = 0; kb < nkb; ++kb) {
+            const int slot = kb % STAGES;
+            oz_mbar_wait(oz_smem(&bar_full[slot]), (uint32_t)((kb / STAGES) & 1));
             asm volatile("tcgen05.fence::after_thread_sync;");
-            const uint32_t sa = sbase + slot * OZ_STAGE_BYTES, sb = sa + OZ_S * OZ_TILE_A;
+            const uint32_t sa = sbase + slot * Cfg::STAGE_BYTES, sb = sa + S * OZ_TILE_A;
 #pragma unroll
-            for (int d = 0; d < OZ_S; ++d) {
+            for (int s = 0; s < S; ++s) {
+                const uint64_t da = oz_desc(sa + s * OZ_TILE_A);
 #pragma unroll
-                for (int s = 0; s <= d; ++s) {
-                    const uint64_t da = oz_desc(sa + s * OZ_TILE_A), db = oz_desc(sb + (d - s) * OZ_TILE_B);
-                    const uint32_t acc = (kb > 0 || s > 0) ? 1u : 0u;
-                    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-                                 "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}\n"
-                                 ::"r"(tmem + (uint32_t)(d * OZ_BN)), "l"(da), "l"(db), "r"(idesc), "r"(acc));
+                for (int t0 = 0; t0 < S - s; t0 += 4) {
+                    const int nt = (S - s - t0) < 4 ? (S - s - t0) : 4;      // digit tiles of the second operand in this instruction
+                    const uint32_t idesc = idesc0 | ((uint32_t)((nt * OZ_BN) >> 3) << 17);
+                    oz_mma_i8(tmem + (uint32_t)((s + t0) * OZ_BN), da, oz_desc(sb + t0 * OZ_TILE_B), idesc, (kb > 0 || s > 0) ? 1u : 0u);
                 }
             }
-            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(oz_smem(&bar_empty[slot])) : "memory");
-            // refill the slot used one iteration ago: its MMAs were committed a whole stage of tensor work earlier
-            if (kb >= 1 && kb - 1 + OZ_STAGES < nkb) {
-                const int ps = (kb - 1) % OZ_STAGES;
-                oz_mbar_wait(oz_smem(&bar_empty[ps]), (uint32_t)(((kb - 1) / OZ_STAGES) & 1));
-                load_stage(kb - 1 + OZ_STAGES);
-            }
+            if (cs == 1)
+                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(oz_smem(&bar_empty[slot])) : "memory");
+            else
+                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                             ::"r"(oz_smem(&bar_empty[slot])), "h"(cmask) : "memory");
         }
         asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(oz_smem(&bar_acc)) : "memory");
     }
@@ -269,13 +366,13 @@ ozaki_mma_kernel(const int8_t* __restrict__ a_tiles, int64_t a_group_stride, con
     asm volatile("tcgen05.fence::after_thread_sync;");
     const int64_t i = (int64_t)blockIdx.y * OZ_BM + tid;
     const int ea = (i < rows_a) ? Ea[g * ea_stride + i] : 0;
-    double* og = out + g * out_group_stride;
+    TO* og = out + g * out_group_stride;
     const uint32_t lane_addr = tmem + ((uint32_t)(warp * 32) << 16);
     for (int c0 = 0; c0 < OZ_BN; c0 += 16) {
         // all S diagonals of 16 columns in flight, one wait
-        uint32_t r[OZ_S][16];
+        uint32_t r[S][16];
 #pragma unroll
-        for (int d = 0; d < OZ_S; ++d) {
+        for (int d = 0; d < S; ++d) {
             asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
                          : "=r"(r[d][0]), "=r"(r[d][1]), "=r"(r[d][2]), "=r"(r[d][3]), "=r"(r[d][4]), "=r"(r[d][5]), "=r"(r[d][6]), "=r"(r[d][7]),
                            "=r"(r[d][8]), "=r"(r[d][9]), "=r"(r[d][10]), "=r"(r[d][11]), "=r"(r[d][12]), "=r"(r[d][13]), "=r"(r[d][14]), "=r"(r[d][15])
@@ -289,80 +386,219 @@ ozaki_mma_kernel(const int8_t* __restrict__ a_tiles, int64_t a_group_stride, con
                 if (jj < rows_b) {
                     double v = 0.0;
 #pragma unroll
-                    for (int d = OZ_S - 1; d >= 0; --d) v = fma(v, 0.0078125, (double)(int32_t)r[d][j]);
+                    for (int d = S - 1; d >= 0; --d) v = fma(v, 0.00390625, (double)(int32_t)r[d][j]);
                     // v * 2^(ea + eb - 12), split in two exact power-of-two factors so that neither leaves the normal range early
-                    const int e = ea + Eb[g * eb_stride + jj] - 12;
+                    const int e = ea + Eb[g * eb_stride + jj] - (2 * Cfg::P - 16 * (S - 1));
                     const int e1 = e / 2, e2 = e - e1;
                     double val = alpha * ((v * oz_pow2(max(-1022, min(1023, e1)))) * oz_pow2(max(-1022, min(1023, e2))));
-                    double* p = og + i + (int64_t)jj * ldo;
-                    if (beta != 0.0) val += beta * (*p);
-                    *p = val;
+                    TO* p = og + i + (int64_t)jj * ldo;
+                    if (beta != 0.0) val += beta * (double)(*p);
+                    *p = (TO)val;
                 }
             }
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;");
     __syncthreads();
-    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(OZ_TMEM_COLS));
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(Cfg::TMEM_COLS));
+    if (cs > 1) oz_cluster_sync();      // no CTA exits while a peer's commit may still arrive on its barriers
 }
 
 // C = alpha * sum_g part[g] + beta * C  (fixed order)
+template <typename T>
 __global__ void __launch_bounds__(256) oz_reduce_kernel(const double* __restrict__ part, int groups, int64_t total, int n1, double alpha, double beta,
-                                                        double* __restrict__ C, int64_t ldc) {
+                                                        T* __restrict__ C, int64_t ldc) {
     for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
         double s = 0.0;
         for (int g = 0; g < groups; ++g) s += part[(int64_t)g * total + e];
-        double* c = C + (e % n1) + (e / n1) * ldc;
+        T* c = C + (e % n1) + (e / n1) * ldc;
         double v = alpha * s;
-        if (beta != 0.0) v += beta * (*c);
-        *c = v;
+        if (beta != 0.0) v += beta * (double)(*c);
+        *c = (T)v;
     }
 }
 
-static int oz_configure(Ctx* ctx) {
+// cluster size along x for a grid of nxb second-operand blocks: the largest of {4, 2, 1} that divides nxb and still lets
+// (almost) every SM hold a CTA (GPCs whose SM count is not a multiple of the cluster size strand SMs).  RLB200_OZ_CLUSTER overrides.
+template <int S, typename TO>
+static int oz_configure(Ctx* ctx, int* cs_ok /* [5] */) {
     static bool done = false;
+    static int ok[5] = {0, 1, 0, 0, 0};
     if (!done) {
-        RLB_CUDA_OK(ctx, cudaFuncSetAttribute(ozaki_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, OZ_STAGES * OZ_STAGE_BYTES));
+        const int smem = OzCfg<S>::STAGES * OzCfg<S>::STAGE_BYTES;
+        RLB_CUDA_OK(ctx, cudaFuncSetAttribute(ozaki_mma_kernel<S, TO>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        for (int cs = 2; cs <= 4; cs *= 2) {
+            cudaLaunchConfig_t cfg{};
+            cfg.gridDim = dim3(cs * ctx->num_sms, 1, 1);
+            cfg.blockDim = dim3(128);
+            cfg.dynamicSmemBytes = smem;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension;
+            at[0].val.clusterDim.x = cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+            cfg.attrs = at; cfg.numAttrs = 1;
+            int ncl = 0;
+            if (cudaOccupancyMaxActiveClusters(&ncl, ozaki_mma_kernel<S, TO>, &cfg) != cudaSuccess) { cudaGetLastError(); ncl = 0; }
+            ok[cs] = (ncl * cs * 100 >= ctx->num_sms * 97) ? 1 : 0;
+        }
+        if (const char* e = getenv("RLB200_OZ_CLUSTER")) {
+            const int force = atoi(e);
+            for (int cs = 2; cs <= 4; cs *= 2) ok[cs] = (cs <= force) ? 1 : 0;
+        }
         done = true;
     }
+    for (int i = 0; i < 5; ++i) cs_ok[i] = ok[i];
+    return 0;
+}
+static int oz_pick_cluster(const int* cs_ok, int nxb) {
+    if (cs_ok[4] && nxb % 4 == 0) return 4;
+    if (cs_ok[2] && nxb % 2 == 0) return 2;
+    return 1;
+}
+template <int S, typename TO>
+static int oz_launch_mma(Ctx* ctx, dim3 grid, int cs, cudaStream_t stream, const int8_t* a_tiles, int64_t a_group_stride, const int8_t* b_tiles,
+                         int64_t b_group_stride, int nkb, const int* Ea, int64_t ea_stride, const int* Eb, int64_t eb_stride, int64_t rows_a, int rows_b,
+                         TO* out, int64_t ldo, int64_t out_group_stride, double alpha, double beta) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(128);
+    cfg.dynamicSmemBytes = OzCfg<S>::STAGES * OzCfg<S>::STAGE_BYTES;
+    cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    RLB_CUDA_OK(ctx, cudaLaunchKernelEx(&cfg, ozaki_mma_kernel<S, TO>, a_tiles, a_group_stride, b_tiles, b_group_stride, nkb, Ea, ea_stride, Eb, eb_stride,
+                                        rows_a, rows_b, out, ldo, out_group_stride, alpha, beta));
     return 0;
 }
 
 // ------------------------------------------------------------------------------------------------
-// C(m x N) = alpha * A(m x K) * B(K x N) + beta * C, tall A (col-major fp64)
+// C(m x N) = alpha * A(m x K) * B(K x N) + beta * C, tall A (col-major)
 // ------------------------------------------------------------------------------------------------
-int ozaki_gemm_nn(Ctx* ctx, int64_t m, int64_t N, int64_t K, double alpha, const double* A, int64_t lda, const double* B, int64_t ldb, double beta,
-                  double* C, int64_t ldc) {
-    RLB_REQUIRE(ctx, m >= 0 && N >= 0 && K >= 0 && K <= 65536 && N < (1 << 20));
-    if (m == 0 || N == 0) return 0;
-    if (K == 0) return gemm_nn<double>(ctx, m, N, 0, 0.0, A, lda, B, ldb, beta, C, ldc);
-    RLB_CHECK(oz_configure(ctx));
+// second stream: slicing of chunk c + 1 overlaps the tensor-core kernel of chunk c (double-buffered digit tiles)
+template <int S, typename T>
+static int oz_configure_slicers(Ctx* ctx) {
+    // the slicers run beside the tensor-core kernel (which needs the maximum shared-memory carveout): ask for the same carveout so
+    // that both can be resident on one SM
+    static bool done = false;
+    if (!done) {
+        RLB_CUDA_OK(ctx, cudaFuncSetAttribute(oz_slice_rows_kernel<S, T>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        RLB_CUDA_OK(ctx, cudaFuncSetAttribute(oz_slice_cols_kernel<S, OZ_BM, T>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        RLB_CUDA_OK(ctx, cudaFuncSetAttribute(oz_slice_cols_kernel<S, OZ_BN, T>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        RLB_CUDA_OK(ctx, cudaFuncSetAttribute(oz_rowexp_kernel<T>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        RLB_CUDA_OK(ctx, cudaFuncSetAttribute(oz_colexp_kernel<T>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        done = true;
+    }
+    return 0;
+}
+static int oz_aux(Ctx* ctx) {
+    if (!ctx->aux_stream) {
+        RLB_CUDA_OK(ctx, cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking));
+        for (auto& e : ctx->aux_ev) RLB_CUDA_OK(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    }
+    return 0;
+}
+enum { OZ_EV_FORK = 0, OZ_EV_SLICED = 1, OZ_EV_CONSUMED = 3 };
+
+// cached exponents of the constant data matrix (OzConstScope, drivers.cuh)
+static int oz_cache_reserve(Ctx* ctx, OzCacheEntry& e, size_t n_e, size_t n_s) {
+    if (n_e > e.cap_e || n_s > e.cap_s) {
+        RLB_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+        if (ctx->aux_stream) RLB_CUDA_OK(ctx, cudaStreamSynchronize(ctx->aux_stream));
+        if (n_e > e.cap_e) {
+            if (e.E) cudaFree(e.E);
+            e.E = nullptr; e.cap_e = 0;
+            if (cudaMalloc(&e.E, n_e * sizeof(int)) != cudaSuccess) { cudaGetLastError(); ctx->err = "exponent cache allocation failed"; return RLB200_ERR_ALLOC; }
+            e.cap_e = n_e;
+        }
+        if (n_s > e.cap_s) {
+            if (e.ss) cudaFree(e.ss);
+            e.ss = nullptr; e.cap_s = 0;
+            if (cudaMalloc(&e.ss, n_s * sizeof(double)) != cudaSuccess) { cudaGetLastError(); ctx->err = "exponent cache allocation failed"; return RLB200_ERR_ALLOC; }
+            e.cap_s = n_s;
+        }
+    }
+    return 0;
+}
+static bool oz_cache_hit(const OzCacheEntry& e, const void* ptr, int64_t m, int64_t n, int64_t ld, int64_t L, int P, int elem) {
+    return e.valid && e.ptr == ptr && e.m == m && e.n == n && e.ld == ld && e.L == L && e.P == P && e.elem == elem;
+}
+static void oz_cache_set(OzCacheEntry& e, const void* ptr, int64_t m, int64_t n, int64_t ld, int64_t L, int P, int elem) {
+    e.ptr = ptr; e.m = m; e.n = n; e.ld = ld; e.L = L; e.P = P; e.elem = elem; e.valid = true;
+}
+void oz_cache_destroy(Ctx* ctx) {
+    for (OzCacheEntry* e : {&ctx->oz_row, &ctx->oz_col}) {
+        if (e->E) cudaFree(e->E);
+        if (e->ss) cudaFree(e->ss);
+        *e = OzCacheEntry();
+    }
+}
+
+template <int S, typename T>
+static int oz_nn(Ctx* ctx, int64_t m, int64_t N, int64_t K, double alpha, const T* A, int64_t lda, const T* B, int64_t ldb, double beta, T* C,
+                 int64_t ldc) {
+    using Cfg = OzCfg<S>;
+    int cs_ok[5];
+    RLB_CHECK((oz_configure<S, T>(ctx, cs_ok)));
+    RLB_CHECK((oz_configure_slicers<S, T>(ctx)));
+    RLB_CHECK(oz_aux(ctx));
     const int nkb = (int)((K + OZ_KB - 1) / OZ_KB);
     const int nnb = (int)((N + OZ_BN - 1) / OZ_BN);
-    const int64_t RC = 32768;                       // rows of A sliced per launch
+    const int cs = oz_pick_cluster(cs_ok, nnb);
+    // rows of A sliced per launch: ~256 MB of digits per buffer, whole 128-row blocks
+    const int64_t RC = std::max<int64_t>(OZ_BM, std::min<int64_t>(((m + OZ_BM - 1) / OZ_BM) * OZ_BM,
+                                                                  ((int64_t)(256 << 20) / ((int64_t)nkb * OZ_KB * S)) / OZ_BM * OZ_BM));
+    const int nbuf = m > RC ? 2 : 1;
     ArenaScope as(ctx);
     int* Eb = as.take<int>(N); if (!Eb) return RLB200_ERR_ALLOC;
-    int8_t* bt = as.take<int8_t>((size_t)nnb * nkb * OZ_S * OZ_TILE_B); if (!bt) return RLB200_ERR_ALLOC;
-    int* Ea = as.take<int>(RC); if (!Ea) return RLB200_ERR_ALLOC;
-    int8_t* at = as.take<int8_t>((size_t)(RC / OZ_BM) * nkb * OZ_S * OZ_TILE_A); if (!at) return RLB200_ERR_ALLOC;
+    int8_t* bt = as.take<int8_t>((size_t)nnb * nkb * S * OZ_TILE_B); if (!bt) return RLB200_ERR_ALLOC;
+    const bool cached = ctx->oz_const_ptr == (const void*)A;     // A does not change during the enclosing driver scope
+    int* Ea[2]; int8_t* at[2];
+    for (int b = 0; b < nbuf; ++b) {
+        Ea[b] = nullptr;
+        if (!cached) { Ea[b] = as.take<int>(RC); if (!Ea[b]) return RLB200_ERR_ALLOC; }
+        at[b] = as.take<int8_t>((size_t)(RC / OZ_BM) * nkb * S * OZ_TILE_A); if (!at[b]) return RLB200_ERR_ALLOC;
+    }
+    cudaStream_t main = ctx->stream, aux = ctx->aux_stream;
+    bool fill_cache = false;
+    if (cached && !oz_cache_hit(ctx->oz_row, A, m, K, lda, 0, Cfg::P, (int)sizeof(T))) {
+        RLB_CHECK(oz_cache_reserve(ctx, ctx->oz_row, (size_t)m, 0));
+        fill_cache = true;
+    }
+    RLB_CUDA_OK(ctx, cudaEventRecord(ctx->aux_ev[OZ_EV_FORK], main));
+    RLB_CUDA_OK(ctx, cudaStreamWaitEvent(aux, ctx->aux_ev[OZ_EV_FORK], 0));
+    if (fill_cache) {
+        ctx->launches += 1;
+        ctx->timers[RLB200_TIMER_SKETCH].launches += 1;
+        oz_rowexp_kernel<T><<<(unsigned)((m + 255) / 256), 256, 0, aux>>>(A, lda, m, (int)K, Cfg::P, ctx->oz_row.E);
+        RLB_CUDA_OK(ctx, cudaGetLastError());
+        oz_cache_set(ctx->oz_row, A, m, K, lda, 0, Cfg::P, (int)sizeof(T));
+    }
     {
         LaunchScope ls(ctx, RLB200_TIMER_SKETCH, 2);
-        oz_colmax_kernel<<<(unsigned)((N + 7) / 8), 256, 0, ctx->stream>>>(B, ldb, K, (int)N, K, 1, Eb);
-        oz_slice_cols_kernel<OZ_BN><<<dim3(nnb, (nkb + 7) / 8), 128, 0, ctx->stream>>>(B, ldb, K, (int)N, nkb, Eb, bt);
+        oz_colexp_kernel<T><<<(unsigned)((N + 7) / 8), 256, 0, main>>>(B, ldb, K, (int)N, K, 1, Cfg::P, Eb, nullptr);
+        oz_slice_cols_kernel<S, OZ_BN, T><<<dim3(nnb, (nkb + 7) / 8), 128, 0, main>>>(B, ldb, K, (int)N, nkb, Eb, bt);
         RLB_CUDA_OK(ctx, cudaGetLastError());
     }
-    for (int64_t r0 = 0; r0 < m; r0 += RC) {
+    int64_t c = 0;
+    for (int64_t r0 = 0; r0 < m; r0 += RC, ++c) {
         const int64_t rows = std::min(RC, m - r0);
         const int nrb = (int)((rows + OZ_BM - 1) / OZ_BM);
-        {
-            LaunchScope ls(ctx, RLB200_TIMER_SKETCH, 2);
-            oz_rowmax_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, ctx->stream>>>(A + r0, lda, rows, (int)K, Ea);
-            oz_slice_rows_kernel<OZ_BM><<<dim3(nrb, (nkb + 7) / 8), OZ_BM, 0, ctx->stream>>>(A + r0, lda, rows, (int)K, nkb, Ea, at);
-        }
-        LaunchScope ls(ctx, RLB200_TIMER_GEMM_NN);
-        ozaki_mma_kernel<<<dim3(nnb, nrb, 1), 128, OZ_STAGES * OZ_STAGE_BYTES, ctx->stream>>>(at, 0, bt, 0, nkb, Ea, 0, Eb, 0, rows, (int)N, C + r0, ldc,
-                                                                                            0, alpha, beta);
+        const int b = (int)(c % nbuf);
+        if (c >= nbuf) RLB_CUDA_OK(ctx, cudaStreamWaitEvent(aux, ctx->aux_ev[OZ_EV_CONSUMED + b], 0));
+        const int* Ea_c = cached ? ctx->oz_row.E + r0 : Ea[b];
+        ctx->launches += cached ? 1 : 2;
+        ctx->timers[RLB200_TIMER_SKETCH].launches += cached ? 1 : 2;
+        if (!cached) oz_rowexp_kernel<T><<<(unsigned)((rows + 255) / 256), 256, 0, aux>>>(A + r0, lda, rows, (int)K, Cfg::P, Ea[b]);
+        oz_slice_rows_kernel<S, T><<<dim3(nrb, (nkb + 7) / 8), OZ_BM, 0, aux>>>(A + r0, lda, rows, (int)K, nkb, Ea_c, at[b]);
         RLB_CUDA_OK(ctx, cudaGetLastError());
+        RLB_CUDA_OK(ctx, cudaEventRecord(ctx->aux_ev[OZ_EV_SLICED + b], aux));
+        RLB_CUDA_OK(ctx, cudaStreamWaitEvent(main, ctx->aux_ev[OZ_EV_SLICED + b], 0));
+        {
+            LaunchScope ls(ctx, RLB200_TIMER_GEMM_NN);
+            RLB_CHECK((oz_launch_mma<S, T>(ctx, dim3(nnb, nrb, 1), cs, main, at[b], 0, bt, 0, nkb, Ea_c, 0, Eb, 0, rows, (int)N, C + r0, ldc, 0, alpha, beta)));
+        }
+        RLB_CUDA_OK(ctx, cudaEventRecord(ctx->aux_ev[OZ_EV_CONSUMED + b], main));
     }
     return 0;
 }
@@ -370,52 +606,125 @@ int ozaki_gemm_nn(Ctx* ctx, int64_t m, int64_t N, int64_t K, double alpha, const
 // ------------------------------------------------------------------------------------------------
 // C(N1 x N2) = alpha * X(m x N1)^T * Y(m x N2) + beta * C, contraction over the long dimension
 // ------------------------------------------------------------------------------------------------
-int ozaki_gemm_tn(Ctx* ctx, int64_t m, int64_t N1, int64_t N2, double alpha, const double* X, int64_t ldx, const double* Y, int64_t ldy, double beta,
-                  double* C, int64_t ldc) {
-    RLB_REQUIRE(ctx, m >= 0 && N1 >= 0 && N2 >= 0 && N1 < (1 << 20) && N2 < (1 << 20));
-    if (N1 == 0 || N2 == 0) return 0;
-    if (m == 0) return gemm_tn<double>(ctx, 0, N1, N2, 0.0, X, ldx, Y, ldy, beta, C, ldc, 0);
-    RLB_CHECK(oz_configure(ctx));
+template <int S, typename T>
+static int oz_tn(Ctx* ctx, int64_t m, int64_t N1, int64_t N2, double alpha, const T* X, int64_t ldx, const T* Y, int64_t ldy, double beta, T* C,
+                 int64_t ldc, double* x_sumsq_out) {
+    using Cfg = OzCfg<S>;
+    int cs_ok[5];
+    RLB_CHECK((oz_configure<S, double>(ctx, cs_ok)));
+    RLB_CHECK((oz_configure_slicers<S, T>(ctx)));
+    RLB_CHECK(oz_aux(ctx));
     const int64_t L = std::min<int64_t>(OZ_CHUNK, ((m + OZ_KB - 1) / OZ_KB) * OZ_KB);
     const int64_t nchunks = (m + L - 1) / L;
     const int nkb = (int)(L / OZ_KB);
     const int nb1 = (int)((N1 + OZ_BM - 1) / OZ_BM), nb2 = (int)((N2 + OZ_BN - 1) / OZ_BN);
-    // chunks per launch: enough CTAs for ~2 waves
-    const int G = (int)std::max<int64_t>(1, std::min<int64_t>(nchunks, (2 * ctx->num_sms + nb1 * nb2 - 1) / (nb1 * nb2)));
+    // chunks per launch: as many as fill two waves of CTAs; chunk slot q of every launch accumulates into partial q
+    const int G = (int)std::max<int64_t>(1, std::min<int64_t>(nchunks, (2 * ctx->num_sms) / (nb1 * nb2)));
+    const int nbuf = nchunks > G ? 2 : 1;
+    const int cs = oz_pick_cluster(cs_ok, nb2);
     ArenaScope as(ctx);
     const int64_t total = N1 * N2;
-    double* part = as.take<double>((size_t)nchunks * total); if (!part) return RLB200_ERR_ALLOC;
-    int* Ex = as.take<int>((size_t)nchunks * N1); if (!Ex) return RLB200_ERR_ALLOC;
-    int* Ey = as.take<int>((size_t)nchunks * N2); if (!Ey) return RLB200_ERR_ALLOC;
-    const int64_t xs = (int64_t)nb1 * nkb * OZ_S * OZ_TILE_A, ys = (int64_t)nb2 * nkb * OZ_S * OZ_TILE_B;   // bytes per chunk
-    int8_t* xt = as.take<int8_t>((size_t)G * xs); if (!xt) return RLB200_ERR_ALLOC;
-    int8_t* yt = as.take<int8_t>((size_t)G * ys); if (!yt) return RLB200_ERR_ALLOC;
-    {
-        LaunchScope ls(ctx, RLB200_TIMER_SKETCH, 2);
-        oz_colmax_kernel<<<(unsigned)((N1 * nchunks + 7) / 8), 256, 0, ctx->stream>>>(X, ldx, m, (int)N1, L, (int)nchunks, Ex);
-        oz_colmax_kernel<<<(unsigned)((N2 * nchunks + 7) / 8), 256, 0, ctx->stream>>>(Y, ldy, m, (int)N2, L, (int)nchunks, Ey);
-        RLB_CUDA_OK(ctx, cudaGetLastError());
+    double* part = as.take<double>((size_t)G * total); if (!part) return RLB200_ERR_ALLOC;
+    const bool cached = ctx->oz_const_ptr == (const void*)X;     // X does not change during the enclosing driver scope
+    int* Ex = nullptr;
+    double* ssx = nullptr;
+    bool fill_x = true;
+    if (cached) {
+        if (oz_cache_hit(ctx->oz_col, X, m, N1, ldx, L, Cfg::P, (int)sizeof(T))) fill_x = false;
+        else RLB_CHECK(oz_cache_reserve(ctx, ctx->oz_col, (size_t)nchunks * N1, (size_t)nchunks * N1));
+        Ex = ctx->oz_col.E; ssx = ctx->oz_col.ss;
+    } else {
+        Ex = as.take<int>((size_t)nchunks * N1); if (!Ex) return RLB200_ERR_ALLOC;
+        if (x_sumsq_out) { ssx = as.take<double>((size_t)nchunks * N1); if (!ssx) return RLB200_ERR_ALLOC; }
     }
-    for (int64_t c0 = 0; c0 < nchunks; c0 += G) {
+    int* Ey = as.take<int>((size_t)nchunks * N2); if (!Ey) return RLB200_ERR_ALLOC;
+    const int64_t xs = (int64_t)nb1 * nkb * S * OZ_TILE_A, ys = (int64_t)nb2 * nkb * S * OZ_TILE_B;   // bytes per chunk
+    int8_t* xt[2]; int8_t* yt[2];
+    for (int b = 0; b < nbuf; ++b) {
+        xt[b] = as.take<int8_t>((size_t)G * xs); if (!xt[b]) return RLB200_ERR_ALLOC;
+        yt[b] = as.take<int8_t>((size_t)G * ys); if (!yt[b]) return RLB200_ERR_ALLOC;
+    }
+    cudaStream_t main = ctx->stream, aux = ctx->aux_stream;
+    RLB_CUDA_OK(ctx, cudaEventRecord(ctx->aux_ev[OZ_EV_FORK], main));
+    RLB_CUDA_OK(ctx, cudaStreamWaitEvent(aux, ctx->aux_ev[OZ_EV_FORK], 0));
+    ctx->launches += fill_x ? 2 : 1;
+    ctx->timers[RLB200_TIMER_SKETCH].launches += fill_x ? 2 : 1;
+    if (fill_x) {
+        oz_colexp_kernel<T><<<(unsigned)((N1 * nchunks + 7) / 8), 256, 0, aux>>>(X, ldx, m, (int)N1, L, (int)nchunks, Cfg::P, Ex, ssx);
+        if (cached) oz_cache_set(ctx->oz_col, X, m, N1, ldx, L, Cfg::P, (int)sizeof(T));
+    }
+    oz_colexp_kernel<T><<<(unsigned)((N2 * nchunks + 7) / 8), 256, 0, aux>>>(Y, ldy, m, (int)N2, L, (int)nchunks, Cfg::P, Ey, nullptr);
+    RLB_CUDA_OK(ctx, cudaGetLastError());
+    int64_t it = 0;
+    for (int64_t c0 = 0; c0 < nchunks; c0 += G, ++it) {
         const int g = (int)std::min<int64_t>(G, nchunks - c0);
-        {
-            LaunchScope ls(ctx, RLB200_TIMER_SKETCH, 2 * g);
-            for (int q = 0; q < g; ++q) {
-                const int64_t r0 = (c0 + q) * L, klen = std::min(L, m - r0);
-                oz_slice_cols_kernel<OZ_BM><<<dim3(nb1, (nkb + 7) / 8), 128, 0, ctx->stream>>>(X + r0, ldx, klen, (int)N1, nkb, Ex + (c0 + q) * N1, xt + q * xs);
-                oz_slice_cols_kernel<OZ_BN><<<dim3(nb2, (nkb + 7) / 8), 128, 0, ctx->stream>>>(Y + r0, ldy, klen, (int)N2, nkb, Ey + (c0 + q) * N2, yt + q * ys);
-            }
+        const int b = (int)(it % nbuf);
+        if (it >= nbuf) RLB_CUDA_OK(ctx, cudaStreamWaitEvent(aux, ctx->aux_ev[OZ_EV_CONSUMED + b], 0));
+        ctx->launches += 2 * g;
+        ctx->timers[RLB200_TIMER_SKETCH].launches += 2 * g;
+        for (int q = 0; q < g; ++q) {
+            const int64_t r0 = (c0 + q) * L, klen = std::min(L, m - r0);
+            oz_slice_cols_kernel<S, OZ_BM, T><<<dim3(nb1, (nkb + 7) / 8), 128, 0, aux>>>(X + r0, ldx, klen, (int)N1, nkb, Ex + (c0 + q) * N1, xt[b] + q * xs);
+            oz_slice_cols_kernel<S, OZ_BN, T><<<dim3(nb2, (nkb + 7) / 8), 128, 0, aux>>>(Y + r0, ldy, klen, (int)N2, nkb, Ey + (c0 + q) * N2, yt[b] + q * ys);
         }
-        LaunchScope ls(ctx, RLB200_TIMER_GEMM_TN);
-        ozaki_mma_kernel<<<dim3(nb2, nb1, g), 128, OZ_STAGES * OZ_STAGE_BYTES, ctx->stream>>>(xt, xs, yt, ys, nkb, Ex + c0 * N1, N1, Ey + c0 * N2, N2, N1,
-                                                                                            (int)N2, part + c0 * total, N1, total, 1.0, 0.0);
         RLB_CUDA_OK(ctx, cudaGetLastError());
+        RLB_CUDA_OK(ctx, cudaEventRecord(ctx->aux_ev[OZ_EV_SLICED + b], aux));
+        RLB_CUDA_OK(ctx, cudaStreamWaitEvent(main, ctx->aux_ev[OZ_EV_SLICED + b], 0));
+        {
+            LaunchScope ls(ctx, RLB200_TIMER_GEMM_TN);
+            RLB_CHECK((oz_launch_mma<S, double>(ctx, dim3(nb2, nb1, g), cs, main, xt[b], xs, yt[b], ys, nkb, Ex + c0 * N1, N1, Ey + c0 * N2, N2, N1, (int)N2,
+                                                part, N1, total, 1.0, c0 > 0 ? 1.0 : 0.0)));
+        }
+        RLB_CUDA_OK(ctx, cudaEventRecord(ctx->aux_ev[OZ_EV_CONSUMED + b], main));
     }
     LaunchScope ls(ctx, RLB200_TIMER_GEMM_TN);
-    oz_reduce_kernel<<<(unsigned)std::min<int64_t>((total + 255) / 256, (int64_t)ctx->num_sms * 8), 256, 0, ctx->stream>>>(part, (int)nchunks, total, (int)N1,
-                                                                                                                       alpha, beta, C, ldc);
+    oz_reduce_kernel<T><<<(unsigned)std::min<int64_t>((total + 255) / 256, (int64_t)ctx->num_sms * 8), 256, 0, main>>>(
+        part, (int)std::min<int64_t>(G, nchunks), total, (int)N1, alpha, beta, C, ldc);
     RLB_CUDA_OK(ctx, cudaGetLastError());
+    if (x_sumsq_out) {      // main has waited for the slicing events, which follow the exponent pass on the second stream
+        ctx->launches += 1;
+        oz_sum_kernel<<<1, 1024, 0, main>>>(ssx, nchunks * N1, x_sumsq_out);
+        RLB_CUDA_OK(ctx, cudaGetLastError());
+    }
     return 0;
 }
+
+static int oz_default_digits(Ctx* ctx, size_t elem) {
+    if (ctx->i8_digits > 0) return ctx->i8_digits;
+    return elem == 8 ? 6 : 4;
+}
+
+template <typename T>
+int ozaki_gemm_nn(Ctx* ctx, int64_t m, int64_t N, int64_t K, double alpha, const T* A, int64_t lda, const T* B, int64_t ldb, double beta, T* C,
+                  int64_t ldc) {
+    RLB_REQUIRE(ctx, m >= 0 && N >= 0 && K >= 0 && N < (1 << 20));
+    if (m == 0 || N == 0) return 0;
+    if (K == 0 || K > OZ_KMAX) return gemm_nn<T>(ctx, m, N, K, alpha, A, lda, B, ldb, beta, C, ldc);
+    switch (oz_default_digits(ctx, sizeof(T))) {
+        case 3: return oz_nn<3, T>(ctx, m, N, K, alpha, A, lda, B, ldb, beta, C, ldc);
+        case 4: return oz_nn<4, T>(ctx, m, N, K, alpha, A, lda, B, ldb, beta, C, ldc);
+        case 5: return oz_nn<5, T>(ctx, m, N, K, alpha, A, lda, B, ldb, beta, C, ldc);
+        case 6: return oz_nn<6, T>(ctx, m, N, K, alpha, A, lda, B, ldb, beta, C, ldc);
+        default: return oz_nn<7, T>(ctx, m, N, K, alpha, A, lda, B, ldb, beta, C, ldc);
+    }
+}
+template <typename T>
+int ozaki_gemm_tn(Ctx* ctx, int64_t m, int64_t N1, int64_t N2, double alpha, const T* X, int64_t ldx, const T* Y, int64_t ldy, double beta, T* C,
+                  int64_t ldc, double* x_sumsq_out) {
+    RLB_REQUIRE(ctx, m >= 0 && N1 >= 0 && N2 >= 0 && N1 < (1 << 20) && N2 < (1 << 20));
+    if (N1 == 0 || N2 == 0) return 0;
+    if (m == 0) return gemm_tn<T>(ctx, 0, N1, N2, 0.0, X, ldx, Y, ldy, beta, C, ldc, 0, x_sumsq_out);
+    switch (oz_default_digits(ctx, sizeof(T))) {
+        case 3: return oz_tn<3, T>(ctx, m, N1, N2, alpha, X, ldx, Y, ldy, beta, C, ldc, x_sumsq_out);
+        case 4: return oz_tn<4, T>(ctx, m, N1, N2, alpha, X, ldx, Y, ldy, beta, C, ldc, x_sumsq_out);
+        case 5: return oz_tn<5, T>(ctx, m, N1, N2, alpha, X, ldx, Y, ldy, beta, C, ldc, x_sumsq_out);
+        case 6: return oz_tn<6, T>(ctx, m, N1, N2, alpha, X, ldx, Y, ldy, beta, C, ldc, x_sumsq_out);
+        default: return oz_tn<7, T>(ctx, m, N1, N2, alpha, X, ldx, Y, ldy, beta, C, ldc, x_sumsq_out);
+    }
+}
+template int ozaki_gemm_nn<double>(Ctx*, int64_t, int64_t, int64_t, double, const double*, int64_t, const double*, int64_t, double, double*, int64_t);
+template int ozaki_gemm_nn<float>(Ctx*, int64_t, int64_t, int64_t, double, const float*, int64_t, const float*, int64_t, double, float*, int64_t);
+template int ozaki_gemm_tn<double>(Ctx*, int64_t, int64_t, int64_t, double, const double*, int64_t, const double*, int64_t, double, double*, int64_t, double*);
+template int ozaki_gemm_tn<float>(Ctx*, int64_t, int64_t, int64_t, double, const float*, int64_t, const float*, int64_t, double, float*, int64_t, double*);
 
 }  // namespace rlb

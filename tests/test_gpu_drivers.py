@@ -208,6 +208,36 @@ def test_qb_rsvd_vs_oracle_same_operator(ctx, m, n, k, p, q, b):
     assert np.linalg.norm(U.T @ U - np.eye(kk)) <= EPS ** 0.625 and np.linalg.norm(V.T @ V - np.eye(kk)) <= EPS ** 0.625
 
 
+@pytest.mark.parametrize("digits", [6, 7])
+@pytest.mark.parametrize("m,n,k,p", [(4096, 256, 32, 0), (4096, 256, 32, 2), (20000, 300, 40, 3)])
+def test_rsvd_i8_engine_vs_oracle(ctx, m, n, k, p, digits):
+    """The same parity rule with the tall products over A on the tcgen05 int8 digit-slice engine (ozaki.cu): subspace angle,
+    residual and singular values within 1e-10 / 1e-9 of the oracle's on the same operator, identical codes and RNG state."""
+    A, st0 = poly(m, n, n)
+    Ad = dev(A)
+    st_d = rl.RNGState(st0.key, st0.counter)
+    _, _, QB, RSVD = _stack(p, 1, k)
+    o = O.StackOpts(p, 1, k, O.STAB_CHOLQRQ, O.STAB_CHOLQRQ, O.STAB_CHOLQRQ)
+    *_, rsvd_o = O.make_stack(o)
+    Om_dev = _device_operator(ctx, m, n, k, p, st_d)
+    ctx.set_fp64_engine("i8")
+    ctx.set_i8_digits(digits)
+    try:
+        s = st_d.copy()
+        rc, kk, U, S, V = RSVD.call(ctx, Ad, k, 0.0, s)
+    finally:
+        ctx.set_fp64_engine("dmma")
+        ctx.set_i8_digits(0)
+    rc_o, kk_o, U_o, S_o, V_o, s_o = rsvd_o.call(A, k, 0.0, st0.copy(), omega_override=Om_dev)
+    assert (rc, kk) == (rc_o, kk_o) and s.counter == s_o.counter and s.key == s_o.key
+    U, S, V = host(U), S.cpu().numpy(), host(V)
+    nrmA = np.linalg.norm(A)
+    assert np.abs(S - S_o).max() <= 1e-10 * S_o[0]
+    assert abs(np.linalg.norm(A - (U * S) @ V.T) - np.linalg.norm(A - (U_o * S_o) @ V_o.T)) <= 1e-10 * nrmA
+    assert _ref.subspace_sin(U_o, U) <= 1e-9
+    assert np.linalg.norm(U.T @ U - np.eye(kk)) <= EPS ** 0.625 and np.linalg.norm(V.T @ V - np.eye(kk)) <= EPS ** 0.625
+
+
 def test_rsvd_f32(ctx):
     m, n, k = 2000, 128, 16
     A, st0 = poly(m, n, n, dtype=np.float32)

@@ -24,7 +24,9 @@ Y = rl.empty_f(m, k, torch.float64, dev)
 Z = rl.empty_f(n, k, torch.float64, dev)
 out = {"m": m, "n": n, "k": k}
 names = ["gemm_nn", "gemm_tn", "rightmul", "small", "fill", "sketch", "factor"]
-for eng in ("dmma", "i8"):
+for engname in ("dmma", "i8s6", "i8s7"):
+    eng = "dmma" if engname == "dmma" else "i8"
+    ctx.set_i8_digits(int(engname[-1]) if eng == "i8" else 0)
     for op in ("nn", "tn"):
         def run():
             if op == "nn":
@@ -47,5 +49,5 @@ for eng in ("dmma", "i8"):
         ms = e0.elapsed_time(e1) / reps
         tm = {nm: round(ctx.timer_read(i)[0] / reps, 3) for i, nm in enumerate(names)}
         ctx.timers_enable(False)
-        out[f"{eng}_{op}"] = {"ms": round(ms, 3), "tflops": round(2.0 * m * n * k / ms / 1e9, 2), "timers_ms": {a: b for a, b in tm.items() if b}}
+        out[f"{engname}_{op}"] = {"ms": round(ms, 3), "tflops": round(2.0 * m * n * k / ms / 1e9, 2), "timers_ms": {a: b for a, b in tm.items() if b}}
 print(json.dumps(out))
