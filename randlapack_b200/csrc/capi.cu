@@ -1,6 +1,7 @@
 // extern "C" surface of librlb200.so (see include/rlb200.h for the contract of every entry point).
 #include "drivers.cuh"
 #include <new>
+#include <cstdlib>
 
 using namespace rlb;
 
@@ -133,6 +134,9 @@ int rlb200_philox_stream_dev(rlb200_ctx* ctx, const uint32_t state[6], int64_t n
 int rlb200_gemm_f64_i8_dev(rlb200_ctx* ctx, int transa, int transb, int64_t m, int64_t n, int64_t k, double alpha, const double* A, int64_t lda,
                            const double* B, int64_t ldb, double beta, double* C, int64_t ldc) {
     CTX_OK(ctx); RLB_CHECK(bind(ctx));
+    // diagnostics: treat the first operand as constant across calls (what the drivers declare through OzConstScope)
+    static const bool assume_const = getenv("RLB200_OZ_ASSUME_CONST") != nullptr;
+    ctx->oz_const_ptr = assume_const ? (const void*)A : nullptr;
     if (!transa && !transb) return ozaki_gemm_nn<double>(ctx, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc);
     if (transa && !transb) return ozaki_gemm_tn<double>(ctx, k, m, n, alpha, A, lda, B, ldb, beta, C, ldc);
     ctx->err = "only the NN (tall) and TN (long contraction) shapes of the path are offered";

@@ -23,11 +23,12 @@
 // tile of 64*S rows, so digit s of the first operand is multiplied with digits 0..S-1-s of the second in ceil((S-s)/4)
 // instructions of N <= 256 whose output columns are exactly the accumulators of anti-diagonals s..S-1 (S*64 TMEM columns):
 // 8 instructions per K step for S = 6 instead of 21, and the first-operand tile is read from shared memory 8 times, not 21.
-// Four warps run the fp64 epilogue from tcgen05.ld.
+// Eight warps run the fp64 epilogue from tcgen05.ld.
 #include "drivers.cuh"
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
+#include <vector>
 
 namespace rlb {
 
@@ -51,6 +52,8 @@ struct OzCfg {
     // 0x80 in each of the S-1 low bytes: added as a bias it makes those bytes the unsigned digits d + 128, xor-ed it re-centres them
     static constexpr unsigned long long LOWMASK = 0x8080808080808080ull >> (8 * (9 - S));
 };
+
+__device__ int oz_dbg_mode = 0;      // diagnostics (RLB200_OZ_DBG): 1 = epilogue without math/stores, 2 = without stores
 
 __device__ __forceinline__ uint32_t oz_smem(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -241,11 +244,58 @@ __global__ void __launch_bounds__(128) oz_slice_cols_kernel(const T* __restrict_
     }
 }
 
+// TN operands, MN-major tiles: tile rows (MN) = columns of X, K = rows [0, klen) of X, scale per column (E[c], already offset to
+// the chunk).  Inside a tile the byte of (column c, row k) sits at ((c / 16) * 4 + k / 8) * 128 + (k % 8) * 16 + c % 16, i.e. the
+// same 8 x 16-byte core matrix as above read the other way round (LBO = 128 B between 8-row K groups, SBO = 512 B between 16-column
+// groups).  This lets a thread own one ROW: a warp reads 32 consecutive rows of a column (256 contiguous bytes per load) and writes 512
+// contiguous bytes per digit - the access pattern of the NN slicer, which the K-major column slicer above cannot have.
+// CTA = 4 warps = 4 consecutive K-blocks of one column block.
+template <int S, int TR, typename T>
+__global__ void __launch_bounds__(128) oz_slice_tn_kernel(const T* __restrict__ X, int64_t ldx, int64_t klen, int ncols, int nkb,
+                                                          const int* __restrict__ E, int8_t* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int kb = blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (kb >= nkb) return;
+    const int64_t cb = blockIdx.y;
+    const int64_t row = (int64_t)kb * OZ_KB + lane;
+    const bool rv = row < klen;
+    const T* x = X + (rv ? row : 0);
+    int8_t* tile0 = out + ((cb * nkb + kb) * S) * (int64_t)(TR * OZ_KB);
+#pragma unroll 1
+    for (int cg = 0; cg < TR / 16; ++cg) {
+        const int64_t c0 = cb * TR + cg * 16;
+        double xv[16];
+#pragma unroll
+        for (int kk = 0; kk < 16; ++kk) xv[kk] = (rv && c0 + kk < ncols) ? (double)x[(c0 + kk) * ldx] : 0.0;
+        uint32_t pk[4][S];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            unsigned long long f[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int64_t c = c0 + 4 * q + e;
+                const double scale = oz_pow2(OzCfg<S>::P - E[c < ncols ? c : 0]);
+                f[e] = oz_fixed<S>(xv[4 * q + e], scale);
+            }
+            oz_pack4<S>(f, pk[q]);
+        }
+        const int off = (cg * 4 + (lane >> 3)) * 128 + (lane & 7) * 16;
+#pragma unroll
+        for (int t = 0; t < S; ++t)
+            *reinterpret_cast<uint4*>(tile0 + (int64_t)t * (TR * OZ_KB) + off) = make_uint4(pk[0][t], pk[1][t], pk[2][t], pk[3][t]);
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // the tensor-core kernel
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint64_t oz_desc(uint32_t saddr) {   // K-major, SWIZZLE_NONE, LBO = 128 B, SBO = 256 B, version 1
-    return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)(128 >> 4) << 16) | ((uint64_t)(256 >> 4) << 32) | ((uint64_t)1 << 46);
+// SWIZZLE_NONE shared-memory matrix descriptor (version 1); core matrix = 8 x 16 bytes = 128 contiguous bytes.
+//   K-major  (MN = false): 8 tile rows x 16 K-bytes;  LBO = 128 B between the two K halves, SBO = 256 B between 8-row groups
+//   MN-major (MN = true):  16 MN-bytes x 8 K-rows;    LBO = 128 B between 8-row K groups,   SBO = 512 B between 16-wide MN groups
+template <bool MN>
+__device__ __forceinline__ uint64_t oz_desc(uint32_t saddr) {
+    constexpr uint64_t SBO = MN ? 512 : 256;
+    return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)(128 >> 4) << 16) | ((SBO >> 4) << 32) | ((uint64_t)1 << 46);
 }
 __device__ __forceinline__ void oz_mbar_wait(uint32_t bar, uint32_t parity) {
     uint32_t done = 0;
@@ -280,16 +330,19 @@ __device__ __forceinline__ void oz_mma_i8(uint32_t d_tmem, uint64_t da, uint64_t
 // Launched with a thread-block cluster of cs CTAs along x (cs = 1, 2 or 4): the cs CTAs share the first-operand tiles, so each loads
 // 1/cs of every first-operand stage and multicasts it to the whole cluster (L2 -> SM traffic per CTA and K step drops from
 // S * 6 KB to S * (4/cs + 2) KB); a stage slot is free again when the tensor cores of ALL cs CTAs have consumed it (multicast commit).
-template <int S, typename TO>
-__global__ void __launch_bounds__(128, 1)
+template <int S, typename TO, bool MN>
+__global__ void __launch_bounds__(256, 1)
 ozaki_mma_kernel(const int8_t* __restrict__ a_tiles, int64_t a_group_stride, const int8_t* __restrict__ b_tiles, int64_t b_group_stride, int nkb,
                  const int* __restrict__ Ea, int64_t ea_stride, const int* __restrict__ Eb, int64_t eb_stride, int64_t rows_a, int rows_b,
-                 TO* __restrict__ out, int64_t ldo, int64_t out_group_stride, double alpha, double beta) {
+                 TO* __restrict__ out, int64_t ldo, int64_t out_group_stride, double alpha, double beta, long long* __restrict__ dbg) {
     using Cfg = OzCfg<S>;
     constexpr int STAGES = Cfg::STAGES;
+    long long t_start = 0, t_ready = 0, t_first = 0, t_acc = 0;
+    if (dbg) t_start = clock64();
     extern __shared__ __align__(1024) unsigned char oz_smem_raw[];
     __shared__ __align__(8) uint64_t bar_full[STAGES], bar_empty[STAGES], bar_acc;
     __shared__ uint32_t tmem_base_sh;
+    __shared__ int s_eb20[OZ_BN], s_ebmin, s_ebmax;      // column exponents << 20 and their range over the tile
     const int tid = threadIdx.x, warp = tid >> 5;
     const int g = blockIdx.z;
     uint32_t cs, crank;
@@ -310,6 +363,14 @@ ozaki_mma_kernel(const int8_t* __restrict__ a_tiles, int64_t a_group_stride, con
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(oz_smem(&tmem_base_sh)), "n"(Cfg::TMEM_COLS));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    } else if (warp == 2) {
+        // column exponents of this tile (out-of-range columns mirror an in-range one so that they do not widen the range)
+        const int l = tid & 31;
+        const int j0 = blockIdx.x * OZ_BN + l, j1 = j0 + 32;
+        const int e0 = Eb[g * eb_stride + min(j0, rows_b - 1)], e1 = Eb[g * eb_stride + min(j1, rows_b - 1)];
+        s_eb20[l] = e0 << 20; s_eb20[l + 32] = e1 << 20;
+        const int mn = __reduce_min_sync(0xffffffffu, min(e0, e1)), mx = __reduce_max_sync(0xffffffffu, max(e0, e1));
+        if (l == 0) { s_ebmin = mn; s_ebmax = mx; }
     }
     asm volatile("tcgen05.fence::before_thread_sync;");
     __syncthreads();
@@ -317,6 +378,7 @@ ozaki_mma_kernel(const int8_t* __restrict__ a_tiles, int64_t a_group_stride, con
     asm volatile("tcgen05.fence::after_thread_sync;");
     const uint32_t tmem = tmem_base_sh;
     const uint32_t sbase = oz_smem(oz_smem_raw);
+    if (dbg) t_ready = clock64();
 
     if (tid == 0) {
         // ---- producer: one bulk copy per operand per stage
@@ -336,20 +398,21 @@ ozaki_mma_kernel(const int8_t* __restrict__ a_tiles, int64_t a_group_stride, con
         }
     } else if (tid == 32) {
         // ---- issuer.  s32 accumulate, signed int8 A and B, both K-major, M = 128 (cute/arch/mma_sm100_desc.hpp InstrDescriptor)
-        const uint32_t idesc0 = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(OZ_BM >> 4) << 24);
+        const uint32_t idesc0 = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(OZ_BM >> 4) << 24) | (MN ? ((1u << 15) | (1u << 16)) : 0u);
         for (int kb = 0; kb < nkb; ++kb) {
             const int slot = kb % STAGES;
             oz_mbar_wait(oz_smem(&bar_full[slot]), (uint32_t)((kb / STAGES) & 1));
+            if (dbg && kb == 0) dbg[((int64_t)(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 8 + 2] = clock64();
             asm volatile("tcgen05.fence::after_thread_sync;");
             const uint32_t sa = sbase + slot * Cfg::STAGE_BYTES, sb = sa + S * OZ_TILE_A;
 #pragma unroll
             for (int s = 0; s < S; ++s) {
-                const uint64_t da = oz_desc(sa + s * OZ_TILE_A);
+                const uint64_t da = oz_desc<MN>(sa + s * OZ_TILE_A);
 #pragma unroll
                 for (int t0 = 0; t0 < S - s; t0 += 4) {
                     const int nt = (S - s - t0) < 4 ? (S - s - t0) : 4;      // digit tiles of the second operand in this instruction
                     const uint32_t idesc = idesc0 | ((uint32_t)((nt * OZ_BN) >> 3) << 17);
-                    oz_mma_i8(tmem + (uint32_t)((s + t0) * OZ_BN), da, oz_desc(sb + t0 * OZ_TILE_B), idesc, (kb > 0 || s > 0) ? 1u : 0u);
+                    oz_mma_i8(tmem + (uint32_t)((s + t0) * OZ_BN), da, oz_desc<MN>(sb + t0 * OZ_TILE_B), idesc, (kb > 0 || s > 0) ? 1u : 0u);
                 }
             }
             if (cs == 1)
@@ -361,14 +424,21 @@ ozaki_mma_kernel(const int8_t* __restrict__ a_tiles, int64_t a_group_stride, con
         asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(oz_smem(&bar_acc)) : "memory");
     }
     __syncwarp();
-    // ---- epilogue: TMEM lane = tile row; warp w reads lanes [32w, 32w + 32)
+    // ---- epilogue: TMEM lane = tile row.  Warps w and w + 4 share lane quarter w % 4 (a warp may only touch its own quarter) and
+    // take 32 of the 64 columns each.
     oz_mbar_wait(oz_smem(&bar_acc), 0);
     asm volatile("tcgen05.fence::after_thread_sync;");
-    const int64_t i = (int64_t)blockIdx.y * OZ_BM + tid;
+    if (dbg) t_acc = clock64();
+    const int quarter = warp & 3, chalf = warp >> 2;
+    const int64_t i = (int64_t)blockIdx.y * OZ_BM + quarter * 32 + (tid & 31);
     const int ea = (i < rows_a) ? Ea[g * ea_stride + i] : 0;
+    constexpr int ESHIFT = (2 * Cfg::P - 16 * (S - 1)) + 16;
+    // fast scaling: when 2^(ea + eb - ESHIFT) is a normal double for every column of the tile, its high word is one integer add
+    const bool fast = (ea + s_ebmin - ESHIFT >= -1022) && (ea + s_ebmax - ESHIFT <= 1023);
+    const int ea_hi = (ea - ESHIFT + 1023) << 20;
     TO* og = out + g * out_group_stride;
-    const uint32_t lane_addr = tmem + ((uint32_t)(warp * 32) << 16);
-    for (int c0 = 0; c0 < OZ_BN; c0 += 16) {
+    const uint32_t lane_addr = tmem + ((uint32_t)(quarter * 32) << 16);
+    for (int c0 = chalf * 32; c0 < chalf * 32 + 32; c0 += 16) {
         // all S diagonals of 16 columns in flight, one wait
         uint32_t r[S][16];
 #pragma unroll
@@ -384,13 +454,29 @@ ozaki_mma_kernel(const int8_t* __restrict__ a_tiles, int64_t a_group_stride, con
             for (int j = 0; j < 16; ++j) {
                 const int jj = blockIdx.x * OZ_BN + c0 + j;
                 if (jj < rows_b) {
+                    // v = 2^16 * sum_d acc_d 256^-d.  Three diagonals at a time are combined exactly in int64 (|acc| < 2^31 -> < 2^48)
+                    // and turned into a double by adding 1.5 * 2^52 as an integer to the high word (int -> fp64 conversion
+                    // instructions run at a fraction of the DFMA rate), then chained in fp64.
                     double v = 0.0;
 #pragma unroll
-                    for (int d = S - 1; d >= 0; --d) v = fma(v, 0.00390625, (double)(int32_t)r[d][j]);
-                    // v * 2^(ea + eb - 12), split in two exact power-of-two factors so that neither leaves the normal range early
-                    const int e = ea + Eb[g * eb_stride + jj] - (2 * Cfg::P - 16 * (S - 1));
-                    const int e1 = e / 2, e2 = e - e1;
-                    double val = alpha * ((v * oz_pow2(max(-1022, min(1023, e1)))) * oz_pow2(max(-1022, min(1023, e2))));
+                    for (int gq = (S - 1) / 3; gq >= 0; --gq) {
+                        const long long a0 = (int32_t)r[3 * gq][j];
+                        const long long a1 = (3 * gq + 1 < S) ? (int32_t)r[(3 * gq + 1 < S) ? 3 * gq + 1 : 0][j] : 0;
+                        const long long a2 = (3 * gq + 2 < S) ? (int32_t)r[(3 * gq + 2 < S) ? 3 * gq + 2 : 0][j] : 0;
+                        const long long t = a0 * 65536 + a1 * 256 + a2;
+                        const double tv = __hiloint2double((int)(t >> 32) + 0x43380000, (int)(uint32_t)t) - 6755399441055744.0;
+                        v = (gq == (S - 1) / 3) ? tv : fma(v, 5.9604644775390625e-08 /* 2^-24 */, tv);
+                    }
+                    double val;
+                    if (fast) {
+                        val = v * __hiloint2double(ea_hi + s_eb20[c0 + j], 0);
+                    } else {
+                        // v * 2^(ea + eb - ESHIFT), split in two exact power-of-two factors so that neither leaves the normal range early
+                        const int e = ea + (s_eb20[c0 + j] >> 20) - ESHIFT;
+                        const int e1 = e / 2, e2 = e - e1;
+                        val = (v * oz_pow2(max(-1022, min(1023, e1)))) * oz_pow2(max(-1022, min(1023, e2)));
+                    }
+                    if (alpha != 1.0) val *= alpha;
                     TO* p = og + i + (int64_t)jj * ldo;
                     if (beta != 0.0) val += beta * (double)(*p);
                     *p = (TO)val;
@@ -401,6 +487,12 @@ ozaki_mma_kernel(const int8_t* __restrict__ a_tiles, int64_t a_group_stride, con
     asm volatile("tcgen05.fence::before_thread_sync;");
     __syncthreads();
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(Cfg::TMEM_COLS));
+    if (dbg && tid == 0) {
+        long long* d = dbg + ((int64_t)(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 8;
+        d[0] = t_start; d[1] = t_ready; d[3] = t_acc; d[4] = clock64();
+        uint32_t smid; asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        d[5] = smid; d[6] = t_first;
+    }
     if (cs > 1) oz_cluster_sync();      // no CTA exits while a peer's commit may still arrive on its barriers
 }
 
@@ -420,24 +512,24 @@ __global__ void __launch_bounds__(256) oz_reduce_kernel(const double* __restrict
 
 // cluster size along x for a grid of nxb second-operand blocks: the largest of {4, 2, 1} that divides nxb and still lets
 // (almost) every SM hold a CTA (GPCs whose SM count is not a multiple of the cluster size strand SMs).  RLB200_OZ_CLUSTER overrides.
-template <int S, typename TO>
+template <int S, typename TO, bool MN>
 static int oz_configure(Ctx* ctx, int* cs_ok /* [5] */) {
     static bool done = false;
     static int ok[5] = {0, 1, 0, 0, 0};
     if (!done) {
         const int smem = OzCfg<S>::STAGES * OzCfg<S>::STAGE_BYTES;
-        RLB_CUDA_OK(ctx, cudaFuncSetAttribute(ozaki_mma_kernel<S, TO>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        RLB_CUDA_OK(ctx, cudaFuncSetAttribute(ozaki_mma_kernel<S, TO, MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         for (int cs = 2; cs <= 4; cs *= 2) {
             cudaLaunchConfig_t cfg{};
             cfg.gridDim = dim3(cs * ctx->num_sms, 1, 1);
-            cfg.blockDim = dim3(128);
+            cfg.blockDim = dim3(256);
             cfg.dynamicSmemBytes = smem;
             cudaLaunchAttribute at[1];
             at[0].id = cudaLaunchAttributeClusterDimension;
             at[0].val.clusterDim.x = cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
             cfg.attrs = at; cfg.numAttrs = 1;
             int ncl = 0;
-            if (cudaOccupancyMaxActiveClusters(&ncl, ozaki_mma_kernel<S, TO>, &cfg) != cudaSuccess) { cudaGetLastError(); ncl = 0; }
+            if (cudaOccupancyMaxActiveClusters(&ncl, ozaki_mma_kernel<S, TO, MN>, &cfg) != cudaSuccess) { cudaGetLastError(); ncl = 0; }
             ok[cs] = (ncl * cs * 100 >= ctx->num_sms * 97) ? 1 : 0;
         }
         if (const char* e = getenv("RLB200_OZ_CLUSTER")) {
@@ -454,22 +546,38 @@ static int oz_pick_cluster(const int* cs_ok, int nxb) {
     if (cs_ok[2] && nxb % 2 == 0) return 2;
     return 1;
 }
-template <int S, typename TO>
+template <int S, typename TO, bool MN>
 static int oz_launch_mma(Ctx* ctx, dim3 grid, int cs, cudaStream_t stream, const int8_t* a_tiles, int64_t a_group_stride, const int8_t* b_tiles,
                          int64_t b_group_stride, int nkb, const int* Ea, int64_t ea_stride, const int* Eb, int64_t eb_stride, int64_t rows_a, int rows_b,
-                         TO* out, int64_t ldo, int64_t out_group_stride, double alpha, double beta) {
+                         TO* out, int64_t ldo, int64_t out_group_stride, double alpha, double beta, long long* dbg = nullptr) {
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = grid;
-    cfg.blockDim = dim3(128);
+    cfg.blockDim = dim3(256);
     cfg.dynamicSmemBytes = OzCfg<S>::STAGES * OzCfg<S>::STAGE_BYTES;
     cfg.stream = stream;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
-    RLB_CUDA_OK(ctx, cudaLaunchKernelEx(&cfg, ozaki_mma_kernel<S, TO>, a_tiles, a_group_stride, b_tiles, b_group_stride, nkb, Ea, ea_stride, Eb, eb_stride,
-                                        rows_a, rows_b, out, ldo, out_group_stride, alpha, beta));
+    RLB_CUDA_OK(ctx, cudaLaunchKernelEx(&cfg, ozaki_mma_kernel<S, TO, MN>, a_tiles, a_group_stride, b_tiles, b_group_stride, nkb, Ea, ea_stride, Eb, eb_stride,
+                                        rows_a, rows_b, out, ldo, out_group_stride, alpha, beta, dbg));
     return 0;
+}
+// RLB200_OZ_DBG=1: per-CTA cycle stamps of one launch (start, barriers/TMEM ready, first stage landed, accumulators complete, end),
+// averaged and printed to stderr.  Diagnostic only.
+static void oz_dbg_report(const char* what, cudaStream_t stream, long long* dbg, int64_t nctas) {
+    cudaStreamSynchronize(stream);
+    std::vector<long long> h((size_t)nctas * 8);
+    cudaMemcpy(h.data(), dbg, h.size() * 8, cudaMemcpyDeviceToHost);
+    double a = 0, b = 0, c = 0, d = 0;
+    long long t0 = h[0], t1 = h[4];
+    for (int64_t i = 0; i < nctas; ++i) {
+        const long long* x = &h[(size_t)i * 8];
+        a += double(x[1] - x[0]); b += double(x[2] - x[1]); c += double(x[3] - x[2]); d += double(x[4] - x[3]);
+        t0 = std::min(t0, x[0]); t1 = std::max(t1, x[4]);
+    }
+    fprintf(stderr, "[oz dbg] %s: %lld CTAs; cycles/CTA: setup %.0f, first stage %.0f, mainloop %.0f, epilogue %.0f; kernel span %lld cycles (clock64 is per SM)\n",
+            what, (long long)nctas, a / nctas, b / nctas, c / nctas, d / nctas, t1 - t0);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -485,6 +593,8 @@ static int oz_configure_slicers(Ctx* ctx) {
         RLB_CUDA_OK(ctx, cudaFuncSetAttribute(oz_slice_rows_kernel<S, T>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         RLB_CUDA_OK(ctx, cudaFuncSetAttribute(oz_slice_cols_kernel<S, OZ_BM, T>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         RLB_CUDA_OK(ctx, cudaFuncSetAttribute(oz_slice_cols_kernel<S, OZ_BN, T>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        RLB_CUDA_OK(ctx, cudaFuncSetAttribute(oz_slice_tn_kernel<S, OZ_BM, T>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        RLB_CUDA_OK(ctx, cudaFuncSetAttribute(oz_slice_tn_kernel<S, OZ_BN, T>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         RLB_CUDA_OK(ctx, cudaFuncSetAttribute(oz_rowexp_kernel<T>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         RLB_CUDA_OK(ctx, cudaFuncSetAttribute(oz_colexp_kernel<T>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         done = true;
@@ -534,12 +644,37 @@ void oz_cache_destroy(Ctx* ctx) {
     }
 }
 
+// RLB200_OZ_TIMELINE=1: event pairs around every slicing batch (second stream) and every tensor-core launch (main stream) of one
+// product, printed relative to the first event.  Diagnostic only.
+struct OzTimeline {
+    bool on;
+    std::vector<cudaEvent_t> ev;
+    std::vector<char> tag;
+    OzTimeline() : on(getenv("RLB200_OZ_TIMELINE") != nullptr) {}
+    void mark(char t, cudaStream_t st) {
+        if (!on) return;
+        cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st); ev.push_back(e); tag.push_back(t);
+    }
+    void report(const char* what) {
+        if (!on || ev.empty()) return;
+        cudaDeviceSynchronize();
+        fprintf(stderr, "[oz timeline] %s (ms from first event; s/S = slicing begin/end, m/M = mma begin/end):", what);
+        for (size_t i = 0; i < ev.size() && i < 80; ++i) {
+            float ms = 0; cudaEventElapsedTime(&ms, ev[0], ev[i]);
+            fprintf(stderr, " %c%.3f", tag[i], ms);
+        }
+        float tot = 0; cudaEventElapsedTime(&tot, ev[0], ev.back());
+        fprintf(stderr, " ... total %.3f\n", tot);
+        for (auto e : ev) cudaEventDestroy(e);
+    }
+};
+
 template <int S, typename T>
 static int oz_nn(Ctx* ctx, int64_t m, int64_t N, int64_t K, double alpha, const T* A, int64_t lda, const T* B, int64_t ldb, double beta, T* C,
                  int64_t ldc) {
     using Cfg = OzCfg<S>;
     int cs_ok[5];
-    RLB_CHECK((oz_configure<S, T>(ctx, cs_ok)));
+    RLB_CHECK((oz_configure<S, T, false>(ctx, cs_ok)));
     RLB_CHECK((oz_configure_slicers<S, T>(ctx)));
     RLB_CHECK(oz_aux(ctx));
     const int nkb = (int)((K + OZ_KB - 1) / OZ_KB);
@@ -580,26 +715,39 @@ static int oz_nn(Ctx* ctx, int64_t m, int64_t N, int64_t K, double alpha, const 
         oz_slice_cols_kernel<S, OZ_BN, T><<<dim3(nnb, (nkb + 7) / 8), 128, 0, main>>>(B, ldb, K, (int)N, nkb, Eb, bt);
         RLB_CUDA_OK(ctx, cudaGetLastError());
     }
+    OzTimeline tl;
     int64_t c = 0;
     for (int64_t r0 = 0; r0 < m; r0 += RC, ++c) {
         const int64_t rows = std::min(RC, m - r0);
         const int nrb = (int)((rows + OZ_BM - 1) / OZ_BM);
         const int b = (int)(c % nbuf);
         if (c >= nbuf) RLB_CUDA_OK(ctx, cudaStreamWaitEvent(aux, ctx->aux_ev[OZ_EV_CONSUMED + b], 0));
+        tl.mark('s', aux);
         const int* Ea_c = cached ? ctx->oz_row.E + r0 : Ea[b];
         ctx->launches += cached ? 1 : 2;
         ctx->timers[RLB200_TIMER_SKETCH].launches += cached ? 1 : 2;
         if (!cached) oz_rowexp_kernel<T><<<(unsigned)((rows + 255) / 256), 256, 0, aux>>>(A + r0, lda, rows, (int)K, Cfg::P, Ea[b]);
         oz_slice_rows_kernel<S, T><<<dim3(nrb, (nkb + 7) / 8), OZ_BM, 0, aux>>>(A + r0, lda, rows, (int)K, nkb, Ea_c, at[b]);
         RLB_CUDA_OK(ctx, cudaGetLastError());
+        tl.mark('S', aux);
         RLB_CUDA_OK(ctx, cudaEventRecord(ctx->aux_ev[OZ_EV_SLICED + b], aux));
         RLB_CUDA_OK(ctx, cudaStreamWaitEvent(main, ctx->aux_ev[OZ_EV_SLICED + b], 0));
+        tl.mark('m', main);
         {
             LaunchScope ls(ctx, RLB200_TIMER_GEMM_NN);
-            RLB_CHECK((oz_launch_mma<S, T>(ctx, dim3(nnb, nrb, 1), cs, main, at[b], 0, bt, 0, nkb, Ea_c, 0, Eb, 0, rows, (int)N, C + r0, ldc, 0, alpha, beta)));
+            long long* dbg = nullptr;
+            if (c == 0 && getenv("RLB200_OZ_DBG")) {
+                cudaMalloc(&dbg, (size_t)nnb * nrb * 64);
+                const int mode = atoi(getenv("RLB200_OZ_DBG")) - 1;
+                cudaMemcpyToSymbol(oz_dbg_mode, &mode, sizeof(int));
+            }
+            RLB_CHECK((oz_launch_mma<S, T, false>(ctx, dim3(nnb, nrb, 1), cs, main, at[b], 0, bt, 0, nkb, Ea_c, 0, Eb, 0, rows, (int)N, C + r0, ldc, 0, alpha, beta, dbg)));
+            if (dbg) { oz_dbg_report("NN", main, dbg, (int64_t)nnb * nrb); cudaFree(dbg); }
         }
+        tl.mark('M', main);
         RLB_CUDA_OK(ctx, cudaEventRecord(ctx->aux_ev[OZ_EV_CONSUMED + b], main));
     }
+    tl.report("NN");
     return 0;
 }
 
@@ -611,7 +759,9 @@ static int oz_tn(Ctx* ctx, int64_t m, int64_t N1, int64_t N2, double alpha, cons
                  int64_t ldc, double* x_sumsq_out) {
     using Cfg = OzCfg<S>;
     int cs_ok[5];
-    RLB_CHECK((oz_configure<S, double>(ctx, cs_ok)));
+    static const bool kmajor = getenv("RLB200_OZ_TN_KMAJOR") != nullptr;      // diagnostics: the K-major column slicer
+    if (kmajor) RLB_CHECK((oz_configure<S, double, false>(ctx, cs_ok)));
+    else RLB_CHECK((oz_configure<S, double, true>(ctx, cs_ok)));
     RLB_CHECK((oz_configure_slicers<S, T>(ctx)));
     RLB_CHECK(oz_aux(ctx));
     const int64_t L = std::min<int64_t>(OZ_CHUNK, ((m + OZ_KB - 1) / OZ_KB) * OZ_KB);
@@ -655,28 +805,46 @@ static int oz_tn(Ctx* ctx, int64_t m, int64_t N1, int64_t N2, double alpha, cons
     }
     oz_colexp_kernel<T><<<(unsigned)((N2 * nchunks + 7) / 8), 256, 0, aux>>>(Y, ldy, m, (int)N2, L, (int)nchunks, Cfg::P, Ey, nullptr);
     RLB_CUDA_OK(ctx, cudaGetLastError());
+    OzTimeline tl;
     int64_t it = 0;
     for (int64_t c0 = 0; c0 < nchunks; c0 += G, ++it) {
         const int g = (int)std::min<int64_t>(G, nchunks - c0);
         const int b = (int)(it % nbuf);
         if (it >= nbuf) RLB_CUDA_OK(ctx, cudaStreamWaitEvent(aux, ctx->aux_ev[OZ_EV_CONSUMED + b], 0));
+        tl.mark('s', aux);
         ctx->launches += 2 * g;
         ctx->timers[RLB200_TIMER_SKETCH].launches += 2 * g;
         for (int q = 0; q < g; ++q) {
             const int64_t r0 = (c0 + q) * L, klen = std::min(L, m - r0);
-            oz_slice_cols_kernel<S, OZ_BM, T><<<dim3(nb1, (nkb + 7) / 8), 128, 0, aux>>>(X + r0, ldx, klen, (int)N1, nkb, Ex + (c0 + q) * N1, xt[b] + q * xs);
-            oz_slice_cols_kernel<S, OZ_BN, T><<<dim3(nb2, (nkb + 7) / 8), 128, 0, aux>>>(Y + r0, ldy, klen, (int)N2, nkb, Ey + (c0 + q) * N2, yt[b] + q * ys);
+            if (kmajor) {
+                oz_slice_cols_kernel<S, OZ_BM, T><<<dim3(nb1, (nkb + 7) / 8), 128, 0, aux>>>(X + r0, ldx, klen, (int)N1, nkb, Ex + (c0 + q) * N1, xt[b] + q * xs);
+                oz_slice_cols_kernel<S, OZ_BN, T><<<dim3(nb2, (nkb + 7) / 8), 128, 0, aux>>>(Y + r0, ldy, klen, (int)N2, nkb, Ey + (c0 + q) * N2, yt[b] + q * ys);
+            } else {
+                oz_slice_tn_kernel<S, OZ_BM, T><<<dim3((nkb + 3) / 4, nb1), 128, 0, aux>>>(X + r0, ldx, klen, (int)N1, nkb, Ex + (c0 + q) * N1, xt[b] + q * xs);
+                oz_slice_tn_kernel<S, OZ_BN, T><<<dim3((nkb + 3) / 4, nb2), 128, 0, aux>>>(Y + r0, ldy, klen, (int)N2, nkb, Ey + (c0 + q) * N2, yt[b] + q * ys);
+            }
         }
         RLB_CUDA_OK(ctx, cudaGetLastError());
+        tl.mark('S', aux);
         RLB_CUDA_OK(ctx, cudaEventRecord(ctx->aux_ev[OZ_EV_SLICED + b], aux));
         RLB_CUDA_OK(ctx, cudaStreamWaitEvent(main, ctx->aux_ev[OZ_EV_SLICED + b], 0));
+        tl.mark('m', main);
         {
             LaunchScope ls(ctx, RLB200_TIMER_GEMM_TN);
-            RLB_CHECK((oz_launch_mma<S, double>(ctx, dim3(nb2, nb1, g), cs, main, xt[b], xs, yt[b], ys, nkb, Ex + c0 * N1, N1, Ey + c0 * N2, N2, N1, (int)N2,
-                                                part, N1, total, 1.0, c0 > 0 ? 1.0 : 0.0)));
+            long long* dbg = nullptr;
+            if (c0 == 0 && getenv("RLB200_OZ_DBG")) cudaMalloc(&dbg, (size_t)nb2 * nb1 * g * 64);
+            if (kmajor)
+                RLB_CHECK((oz_launch_mma<S, double, false>(ctx, dim3(nb2, nb1, g), cs, main, xt[b], xs, yt[b], ys, nkb, Ex + c0 * N1, N1, Ey + c0 * N2, N2, N1,
+                                                           (int)N2, part, N1, total, 1.0, c0 > 0 ? 1.0 : 0.0, dbg)));
+            else
+                RLB_CHECK((oz_launch_mma<S, double, true>(ctx, dim3(nb2, nb1, g), cs, main, xt[b], xs, yt[b], ys, nkb, Ex + c0 * N1, N1, Ey + c0 * N2, N2, N1,
+                                                          (int)N2, part, N1, total, 1.0, c0 > 0 ? 1.0 : 0.0, dbg)));
+            if (dbg) { oz_dbg_report("TN", main, dbg, (int64_t)nb2 * nb1 * g); cudaFree(dbg); }
         }
+        tl.mark('M', main);
         RLB_CUDA_OK(ctx, cudaEventRecord(ctx->aux_ev[OZ_EV_CONSUMED + b], main));
     }
+    tl.report("TN");
     LaunchScope ls(ctx, RLB200_TIMER_GEMM_TN);
     oz_reduce_kernel<T><<<(unsigned)std::min<int64_t>((total + 255) / 256, (int64_t)ctx->num_sms * 8), 256, 0, main>>>(
         part, (int)std::min<int64_t>(G, nchunks), total, (int)N1, alpha, beta, C, ldc);
