@@ -19,6 +19,10 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+# dram__bytes_read.sum + dram__bytes_write.sum of ozaki_mma_kernel per row of A (n = 1024, k = 256, 6 digits), from the ncu --set full
+# capture named below; None until a capture is committed
+OZ_TRAFFIC_PER_ROW_BYTES = 0.0
+OZ_TRAFFIC_SOURCE = "not captured yet"
 METRIC = "rsvd_gflops"
 UNIT = "Gflop/s"
 
@@ -373,10 +377,10 @@ def main():
     # ---- synthetic resident input: A = Gaussian DenseDist(m_global, n) sample, generated ON DEVICE by our own fill kernel
     m_local = args.m
     free_b, total_b = torch.cuda.mem_get_info()
-    need = 8 * (m_local * n + m_local * k) + (2 << 30)
+    need = 8 * (m_local * n + m_local * k) + (4 << 30)
     while need > free_b and m_local > (1 << 16):
         m_local //= 2
-        need = 8 * (m_local * n + m_local * k) + (2 << 30)
+        need = 8 * (m_local * n + m_local * k) + (4 << 30)
     if m_local != args.m:
         config["workload"] += f" [REDUCED to {m_local} rows per GPU: only {free_b / 1e9:.1f} GB free]"
         config["m_per_gpu"] = m_local
@@ -398,12 +402,10 @@ def main():
         rc, kk, *_ = stack.call(ctx, A, k, 0.0, rl.RNGState(0), U=U, S=S, V=V)
         assert rc == 0 and kk == k, (rc, kk, stack.qb_code)
 
+    TIMER_NAMES = ["gemm_nn", "gemm_tn", "rightmul", "small", "fill", "sketch", "factor", "i8_mma_nn", "i8_mma_tn", "i8_slice"]
     for _ in range(args.warmup):
         step()
     barrier()
-    ctx.timers_enable(True)
-    for w in range(5):
-        ctx.timer_read(w, reset=True)
     ctx.launch_count(reset=True)
     sampler = ClockSampler(dev.index)
     if rank == 0:
@@ -417,8 +419,15 @@ def main():
     barrier()
     ms_total = e0.elapsed_time(e1)
     clocks = sampler.stop() if rank == 0 else None
-    launches = ctx.launch_count()
-    tms = {nm: ctx.timer_read(i) for i, nm in enumerate(["gemm_nn", "gemm_tn", "rightmul", "small", "fill"])}
+    launches = ctx.launch_count() / args.steps
+    # per-class CUDA-event times on the launching streams: one extra, untimed step (the class timers synchronise the host between
+    # launches, so they are kept out of the timed region)
+    ctx.timers_enable(True)
+    for w in range(len(TIMER_NAMES)):
+        ctx.timer_read(w, reset=True)
+    step()
+    torch.cuda.synchronize()
+    tms = {nm: ctx.timer_read(i) for i, nm in enumerate(TIMER_NAMES)}
     ctx.timers_enable(False)
     if dist is not None:
         t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
@@ -437,25 +446,50 @@ def main():
 
     # ---- roofline of the dominant kernel (per-class CUDA-event times were recorded on the launching stream)
     cf = class_flops(m_local, n, k, p, q)
-    # the in-place right-multiplies run through the NN kernel class timer as well: split them analytically
-    nn_ms, nn_l = tms["gemm_nn"]
-    tn_ms, tn_l = tms["gemm_tn"]
-    peak, peak_src, peak_detail = measured_fp64_peak()
-    dom = "gemm_nn" if nn_ms >= tn_ms else "gemm_tn"
-    dom_ms = max(nn_ms, tn_ms) / args.steps
-    dom_flops = (cf["gemm_nn"] + cf["rightmul"]) if dom == "gemm_nn" else cf["gemm_tn"]
-    achieved = dom_flops / (dom_ms * 1e-3) / 1e12 if dom_ms > 0 else 0.0
-    # DRAM traffic of the dominant kernel per launch: dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture
-    # of gemm_nn_kernel<128,64,...> at m = 2^21 (profiles/ncu_gemm_nn_r1.txt: 17.193 GB + 4.280 GB for 17.180 + 4.295 GB of
-    # algorithmic bytes, i.e. A and Y each cross HBM exactly once), scaled by m; ~the same per launch for A^T*Y (reads A and Y).
-    traffic = (17.193092e9 + 4.279688e9) * (m_local / float(1 << 21)) * (n / 1024.0) if k == 256 else None
-    roofline = {"bound": "tensor", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                "frac": achieved / peak if peak else None, "traffic": traffic,
-                "traffic_source": "ncu --set full capture at m=2^21 scaled by m (profiles/ncu_gemm_nn_r1.txt)",
-                "peak_source": peak_src + "; fp64 pipe (MEASURED_PEAKS.json has no fp64 figure)",
-                "class_ms_per_step": {kname: v[0] / args.steps for kname, v in tms.items()},
-                "class_launches_per_step": {kname: v[1] / args.steps for kname, v in tms.items()},
-                "whole_step_frac_of_fp64_peak": (value / 1e3) / peak if peak else None}
+    peaks = load_peaks()
+    class_ms = {kname: v[0] for kname, v in tms.items() if v[1]}
+    class_launches = {kname: v[1] for kname, v in tms.items() if v[1]}
+    fp64_peak, fp64_src, _ = measured_fp64_peak()
+    if args.engine == "i8":
+        # dominant kernel: ozaki_mma_kernel (tcgen05.mma.kind::i8).  Algorithmic work per launch class: the (p + 2) tall products,
+        # 2*m*n*k flops each, executed as S(S+1)/2 int8 digit-pair GEMMs of the same shape.
+        S_dig = args.digits or 6
+        pairs = S_dig * (S_dig + 1) // 2
+        mma_ms = tms["i8_mma_nn"][0] + tms["i8_mma_tn"][0]
+        i8_ops = (p + 2) * 2.0 * m_local * n * k * pairs
+        achieved = i8_ops / (mma_ms * 1e-3) / 1e12 if mma_ms > 0 else 0.0
+        if "bf16_tflops_sustained" in peaks:
+            peak = 2.0 * peaks["bf16_tflops_sustained"]
+            peak_src = ("2 x MEASURED_PEAKS.json bf16_tflops_sustained (the kernel is timed inside a long step; the int8 tensor rate of "
+                        "sm_100 is twice the bf16 rate, the file has no int8 figure)")
+        else:
+            peak = 2.0 * 1361.4
+            peak_src = "fallback: 2 x 1361.4 TFLOP/s sustained bf16 (B200_PROFILING.md); int8 tensor rate is twice the bf16 rate"
+        roofline = {"bound": "tensor", "kernel": "ozaki_mma_kernel (tcgen05.mma.kind::i8, NN + TN launches)", "achieved": achieved, "peak": peak,
+                    "unit": "TFLOP/s", "frac": achieved / peak, "op": "int8 multiply-add = 2 ops",
+                    "fp64_equivalent_tflops": (p + 2) * 2.0 * m_local * n * k / (mma_ms * 1e-3) / 1e12 if mma_ms > 0 else None,
+                    "digits": S_dig, "digit_pairs": pairs,
+                    "traffic": OZ_TRAFFIC_PER_ROW_BYTES * m_local if (OZ_TRAFFIC_PER_ROW_BYTES and k == 256 and n == 1024 and S_dig == 6) else None,
+                    "traffic_source": OZ_TRAFFIC_SOURCE, "peak_source": peak_src,
+                    "class_ms_per_step": class_ms, "class_launches_per_step": class_launches,
+                    "fp64_pipe_peak_tflops": fp64_peak, "fp64_pipe_peak_source": fp64_src,
+                    "whole_step_vs_fp64_pipe_peak": (value / 1e3) / fp64_peak if fp64_peak else None}
+    else:
+        nn_ms, tn_ms = tms["gemm_nn"][0], tms["gemm_tn"][0]
+        dom = "gemm_nn" if nn_ms >= tn_ms else "gemm_tn"
+        dom_ms = max(nn_ms, tn_ms)
+        dom_flops = (cf["gemm_nn"] + cf["rightmul"]) if dom == "gemm_nn" else cf["gemm_tn"]
+        achieved = dom_flops / (dom_ms * 1e-3) / 1e12 if dom_ms > 0 else 0.0
+        # DRAM traffic of the dominant kernel per launch: dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture
+        # of gemm_nn_kernel<128,64,...> at m = 2^21 (profiles/ncu_gemm_nn_r1.txt: 17.193 GB + 4.280 GB for 17.180 + 4.295 GB of
+        # algorithmic bytes, i.e. A and Y each cross HBM exactly once), scaled by m; ~the same per launch for A^T*Y (reads A and Y).
+        traffic = (17.193092e9 + 4.279688e9) * (m_local / float(1 << 21)) * (n / 1024.0) if k == 256 else None
+        roofline = {"bound": "tensor", "kernel": dom, "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
+                    "frac": achieved / fp64_peak if fp64_peak else None, "traffic": traffic,
+                    "traffic_source": "ncu --set full capture at m=2^21 scaled by m (profiles/ncu_gemm_nn_r1.txt)",
+                    "peak_source": fp64_src + "; fp64 pipe (MEASURED_PEAKS.json has no fp64 figure)",
+                    "class_ms_per_step": class_ms, "class_launches_per_step": class_launches,
+                    "whole_step_frac_of_fp64_peak": (value / 1e3) / fp64_peak if fp64_peak else None}
 
     # ---- e2e: the reference-facing call with HOST buffers (pinned), copies inside the timed region
     e2e = None

@@ -91,7 +91,7 @@ RLB200_API int rlb200_set_shard(rlb200_ctx* ctx, int64_t row_offset, int64_t m_g
 RLB200_API int64_t rlb200_launch_count(rlb200_ctx* ctx, int reset);
 /* CUDA-event timing of the kernels tagged `which` (see RLB200_TIMER_*), ms since last reset. */
 enum { RLB200_TIMER_GEMM_NN = 0, RLB200_TIMER_GEMM_TN = 1, RLB200_TIMER_RIGHTMUL = 2, RLB200_TIMER_SMALL = 3, RLB200_TIMER_FILL = 4, RLB200_TIMER_SKETCH = 5,
-       RLB200_TIMER_FACTOR = 6, RLB200_TIMER_COUNT = 7 };
+       RLB200_TIMER_FACTOR = 6, RLB200_TIMER_I8_MMA_NN = 7, RLB200_TIMER_I8_MMA_TN = 8, RLB200_TIMER_I8_SLICE = 9, RLB200_TIMER_COUNT = 10 };
 RLB200_API int rlb200_timers_enable(rlb200_ctx* ctx, int on);
 RLB200_API int rlb200_timer_read(rlb200_ctx* ctx, int which, double* ms, int64_t* launches, int reset);
 

@@ -115,19 +115,21 @@ inline size_t ws_round(size_t bytes) { return ((bytes + 255) / 256) * 256; }
 struct LaunchScope {
     Ctx* ctx;
     int which;
-    LaunchScope(Ctx* c, int w, int n_kernels = 1) : ctx(c), which(w) {
+    cudaStream_t stream;
+    LaunchScope(Ctx* c, int w, int n_kernels = 1) : LaunchScope(c, w, n_kernels, c->stream) {}
+    LaunchScope(Ctx* c, int w, int n_kernels, cudaStream_t st) : ctx(c), which(w), stream(st) {
         ctx->launches += n_kernels;
         Timer& t = ctx->timers[which];
         t.launches += n_kernels;
         if (ctx->timers_on) {
             if (!t.e0) { cudaEventCreate(&t.e0); cudaEventCreate(&t.e1); }
             if (t.pending) { cudaEventSynchronize(t.e1); float ms = 0; cudaEventElapsedTime(&ms, t.e0, t.e1); t.ms += ms; t.pending = false; }
-            cudaEventRecord(t.e0, ctx->stream);
+            cudaEventRecord(t.e0, stream);
         }
     }
     ~LaunchScope() {
         Timer& t = ctx->timers[which];
-        if (ctx->timers_on) { cudaEventRecord(t.e1, ctx->stream); t.pending = true; }
+        if (ctx->timers_on) { cudaEventRecord(t.e1, stream); t.pending = true; }
     }
 };
 

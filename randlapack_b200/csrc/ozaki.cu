@@ -436,50 +436,60 @@ ozaki_mma_kernel(const int8_t* __restrict__ a_tiles, int64_t a_group_stride, con
     // fast scaling: when 2^(ea + eb - ESHIFT) is a normal double for every column of the tile, its high word is one integer add
     const bool fast = (ea + s_ebmin - ESHIFT >= -1022) && (ea + s_ebmax - ESHIFT <= 1023);
     const int ea_hi = (ea - ESHIFT + 1023) << 20;
+    const bool simple = fast && alpha == 1.0 && beta == 0.0 && (int)(blockIdx.x + 1) * OZ_BN <= rows_b;
     TO* og = out + g * out_group_stride;
     const uint32_t lane_addr = tmem + ((uint32_t)(quarter * 32) << 16);
-    for (int c0 = chalf * 32; c0 < chalf * 32 + 32; c0 += 16) {
-        // all S diagonals of 16 columns in flight, one wait
-        uint32_t r[S][16];
+    for (int c0 = chalf * 32; c0 < chalf * 32 + 32; c0 += 8) {
+        // all S diagonals of 8 columns in flight, one wait
+        uint32_t r[S][8];
 #pragma unroll
         for (int d = 0; d < S; ++d) {
-            asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-                         : "=r"(r[d][0]), "=r"(r[d][1]), "=r"(r[d][2]), "=r"(r[d][3]), "=r"(r[d][4]), "=r"(r[d][5]), "=r"(r[d][6]), "=r"(r[d][7]),
-                           "=r"(r[d][8]), "=r"(r[d][9]), "=r"(r[d][10]), "=r"(r[d][11]), "=r"(r[d][12]), "=r"(r[d][13]), "=r"(r[d][14]), "=r"(r[d][15])
+            asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                         : "=r"(r[d][0]), "=r"(r[d][1]), "=r"(r[d][2]), "=r"(r[d][3]), "=r"(r[d][4]), "=r"(r[d][5]), "=r"(r[d][6]), "=r"(r[d][7])
                          : "r"(lane_addr + (uint32_t)(d * OZ_BN + c0)));
         }
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        // v = 2^16 * sum_d acc_d 256^-d.  Three diagonals at a time are combined exactly in int64 (|acc| < 2^31 -> < 2^48) and turned
+        // into a double by adding 1.5 * 2^52 as an integer to the high word (int -> fp64 conversion instructions run at a fraction of
+        // the DFMA rate), then chained in fp64.
+        auto combine = [&](int j) -> double {
+            double v = 0.0;
+#pragma unroll
+            for (int gq = (S - 1) / 3; gq >= 0; --gq) {
+                const long long a0 = (int32_t)r[3 * gq][j];
+                const long long a1 = (3 * gq + 1 < S) ? (int32_t)r[(3 * gq + 1 < S) ? 3 * gq + 1 : 0][j] : 0;
+                const long long a2 = (3 * gq + 2 < S) ? (int32_t)r[(3 * gq + 2 < S) ? 3 * gq + 2 : 0][j] : 0;
+                const long long t = a0 * 65536 + a1 * 256 + a2;
+                const double tv = __hiloint2double((int)(t >> 32) + 0x43380000, (int)(uint32_t)t) - 6755399441055744.0;
+                v = (gq == (S - 1) / 3) ? tv : fma(v, 5.9604644775390625e-08 /* 2^-24 */, tv);
+            }
+            return v;
+        };
         if (i < rows_a) {
+            if (simple) {
+                TO* p = og + i + (int64_t)(blockIdx.x * OZ_BN + c0) * ldo;
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                const int jj = blockIdx.x * OZ_BN + c0 + j;
-                if (jj < rows_b) {
-                    // v = 2^16 * sum_d acc_d 256^-d.  Three diagonals at a time are combined exactly in int64 (|acc| < 2^31 -> < 2^48)
-                    // and turned into a double by adding 1.5 * 2^52 as an integer to the high word (int -> fp64 conversion
-                    // instructions run at a fraction of the DFMA rate), then chained in fp64.
-                    double v = 0.0;
+                for (int j = 0; j < 8; ++j) p[(int64_t)j * ldo] = (TO)(combine(j) * __hiloint2double(ea_hi + s_eb20[c0 + j], 0));
+            } else {
 #pragma unroll
-                    for (int gq = (S - 1) / 3; gq >= 0; --gq) {
-                        const long long a0 = (int32_t)r[3 * gq][j];
-                        const long long a1 = (3 * gq + 1 < S) ? (int32_t)r[(3 * gq + 1 < S) ? 3 * gq + 1 : 0][j] : 0;
-                        const long long a2 = (3 * gq + 2 < S) ? (int32_t)r[(3 * gq + 2 < S) ? 3 * gq + 2 : 0][j] : 0;
-                        const long long t = a0 * 65536 + a1 * 256 + a2;
-                        const double tv = __hiloint2double((int)(t >> 32) + 0x43380000, (int)(uint32_t)t) - 6755399441055744.0;
-                        v = (gq == (S - 1) / 3) ? tv : fma(v, 5.9604644775390625e-08 /* 2^-24 */, tv);
+                for (int j = 0; j < 8; ++j) {
+                    const int jj = blockIdx.x * OZ_BN + c0 + j;
+                    if (jj < rows_b) {
+                        const double v = combine(j);
+                        double val;
+                        if (fast) {
+                            val = v * __hiloint2double(ea_hi + s_eb20[c0 + j], 0);
+                        } else {
+                            // v * 2^(ea + eb - ESHIFT), split in two exact power-of-two factors so that neither leaves the normal range early
+                            const int e = ea + (s_eb20[c0 + j] >> 20) - ESHIFT;
+                            const int e1 = e / 2, e2 = e - e1;
+                            val = (v * oz_pow2(max(-1022, min(1023, e1)))) * oz_pow2(max(-1022, min(1023, e2)));
+                        }
+                        if (alpha != 1.0) val *= alpha;
+                        TO* p = og + i + (int64_t)jj * ldo;
+                        if (beta != 0.0) val += beta * (double)(*p);
+                        *p = (TO)val;
                     }
-                    double val;
-                    if (fast) {
-                        val = v * __hiloint2double(ea_hi + s_eb20[c0 + j], 0);
-                    } else {
-                        // v * 2^(ea + eb - ESHIFT), split in two exact power-of-two factors so that neither leaves the normal range early
-                        const int e = ea + (s_eb20[c0 + j] >> 20) - ESHIFT;
-                        const int e1 = e / 2, e2 = e - e1;
-                        val = (v * oz_pow2(max(-1022, min(1023, e1)))) * oz_pow2(max(-1022, min(1023, e2)));
-                    }
-                    if (alpha != 1.0) val *= alpha;
-                    TO* p = og + i + (int64_t)jj * ldo;
-                    if (beta != 0.0) val += beta * (double)(*p);
-                    *p = (TO)val;
                 }
             }
         }
@@ -532,10 +542,11 @@ static int oz_configure(Ctx* ctx, int* cs_ok /* [5] */) {
             if (cudaOccupancyMaxActiveClusters(&ncl, ozaki_mma_kernel<S, TO, MN>, &cfg) != cudaSuccess) { cudaGetLastError(); ncl = 0; }
             ok[cs] = (ncl * cs * 100 >= ctx->num_sms * 97) ? 1 : 0;
         }
-        if (const char* e = getenv("RLB200_OZ_CLUSTER")) {
-            const int force = atoi(e);
-            for (int cs = 2; cs <= 4; cs *= 2) ok[cs] = (cs <= force) ? 1 : 0;
-        }
+        // measured (profiles/): the kernel is bound by shared-memory bandwidth, not by L2 -> SM traffic, so multicast buys nothing and
+        // cluster scheduling costs a little; clusters stay opt-in (RLB200_OZ_CLUSTER = 2 or 4)
+        const char* e = getenv("RLB200_OZ_CLUSTER");
+        const int force = e ? atoi(e) : 1;
+        for (int cs = 2; cs <= 4; cs *= 2) ok[cs] = (ok[cs] && cs <= force) ? 1 : 0;
         done = true;
     }
     for (int i = 0; i < 5; ++i) cs_ok[i] = ok[i];
@@ -681,8 +692,16 @@ static int oz_nn(Ctx* ctx, int64_t m, int64_t N, int64_t K, double alpha, const 
     const int nnb = (int)((N + OZ_BN - 1) / OZ_BN);
     const int cs = oz_pick_cluster(cs_ok, nnb);
     // rows of A sliced per launch: ~256 MB of digits per buffer, whole 128-row blocks
-    const int64_t RC = std::max<int64_t>(OZ_BM, std::min<int64_t>(((m + OZ_BM - 1) / OZ_BM) * OZ_BM,
-                                                                  ((int64_t)(256 << 20) / ((int64_t)nkb * OZ_KB * S)) / OZ_BM * OZ_BM));
+    int64_t RC = std::max<int64_t>(OZ_BM, std::min<int64_t>(((m + OZ_BM - 1) / OZ_BM) * OZ_BM,
+                                                            ((int64_t)(256 << 20) / ((int64_t)nkb * OZ_KB * S)) / OZ_BM * OZ_BM));
+    if (m > RC) {
+        // whole waves: row blocks per launch * nnb a multiple of the SM count
+        int64_t ga = ctx->num_sms, gb = nnb;
+        while (gb) { const int64_t t = ga % gb; ga = gb; gb = t; }
+        const int64_t unit = ctx->num_sms / ga;
+        const int64_t nrb_q = (RC / OZ_BM) / unit * unit;
+        if (nrb_q > 0) RC = nrb_q * OZ_BM;
+    }
     const int nbuf = m > RC ? 2 : 1;
     ArenaScope as(ctx);
     int* Eb = as.take<int>(N); if (!Eb) return RLB200_ERR_ALLOC;
@@ -703,14 +722,13 @@ static int oz_nn(Ctx* ctx, int64_t m, int64_t N, int64_t K, double alpha, const 
     RLB_CUDA_OK(ctx, cudaEventRecord(ctx->aux_ev[OZ_EV_FORK], main));
     RLB_CUDA_OK(ctx, cudaStreamWaitEvent(aux, ctx->aux_ev[OZ_EV_FORK], 0));
     if (fill_cache) {
-        ctx->launches += 1;
-        ctx->timers[RLB200_TIMER_SKETCH].launches += 1;
+        LaunchScope ls(ctx, RLB200_TIMER_I8_SLICE, 1, aux);
         oz_rowexp_kernel<T><<<(unsigned)((m + 255) / 256), 256, 0, aux>>>(A, lda, m, (int)K, Cfg::P, ctx->oz_row.E);
         RLB_CUDA_OK(ctx, cudaGetLastError());
         oz_cache_set(ctx->oz_row, A, m, K, lda, 0, Cfg::P, (int)sizeof(T));
     }
     {
-        LaunchScope ls(ctx, RLB200_TIMER_SKETCH, 2);
+        LaunchScope ls(ctx, RLB200_TIMER_I8_SLICE, 2);
         oz_colexp_kernel<T><<<(unsigned)((N + 7) / 8), 256, 0, main>>>(B, ldb, K, (int)N, K, 1, Cfg::P, Eb, nullptr);
         oz_slice_cols_kernel<S, OZ_BN, T><<<dim3(nnb, (nkb + 7) / 8), 128, 0, main>>>(B, ldb, K, (int)N, nkb, Eb, bt);
         RLB_CUDA_OK(ctx, cudaGetLastError());
@@ -724,17 +742,18 @@ static int oz_nn(Ctx* ctx, int64_t m, int64_t N, int64_t K, double alpha, const 
         if (c >= nbuf) RLB_CUDA_OK(ctx, cudaStreamWaitEvent(aux, ctx->aux_ev[OZ_EV_CONSUMED + b], 0));
         tl.mark('s', aux);
         const int* Ea_c = cached ? ctx->oz_row.E + r0 : Ea[b];
-        ctx->launches += cached ? 1 : 2;
-        ctx->timers[RLB200_TIMER_SKETCH].launches += cached ? 1 : 2;
-        if (!cached) oz_rowexp_kernel<T><<<(unsigned)((rows + 255) / 256), 256, 0, aux>>>(A + r0, lda, rows, (int)K, Cfg::P, Ea[b]);
-        oz_slice_rows_kernel<S, T><<<dim3(nrb, (nkb + 7) / 8), OZ_BM, 0, aux>>>(A + r0, lda, rows, (int)K, nkb, Ea_c, at[b]);
-        RLB_CUDA_OK(ctx, cudaGetLastError());
+        {
+            LaunchScope ls(ctx, RLB200_TIMER_I8_SLICE, cached ? 1 : 2, aux);
+            if (!cached) oz_rowexp_kernel<T><<<(unsigned)((rows + 255) / 256), 256, 0, aux>>>(A + r0, lda, rows, (int)K, Cfg::P, Ea[b]);
+            oz_slice_rows_kernel<S, T><<<dim3(nrb, (nkb + 7) / 8), OZ_BM, 0, aux>>>(A + r0, lda, rows, (int)K, nkb, Ea_c, at[b]);
+            RLB_CUDA_OK(ctx, cudaGetLastError());
+        }
         tl.mark('S', aux);
         RLB_CUDA_OK(ctx, cudaEventRecord(ctx->aux_ev[OZ_EV_SLICED + b], aux));
         RLB_CUDA_OK(ctx, cudaStreamWaitEvent(main, ctx->aux_ev[OZ_EV_SLICED + b], 0));
         tl.mark('m', main);
         {
-            LaunchScope ls(ctx, RLB200_TIMER_GEMM_NN);
+            LaunchScope ls(ctx, RLB200_TIMER_I8_MMA_NN);
             long long* dbg = nullptr;
             if (c == 0 && getenv("RLB200_OZ_DBG")) {
                 cudaMalloc(&dbg, (size_t)nnb * nrb * 64);
@@ -797,14 +816,15 @@ static int oz_tn(Ctx* ctx, int64_t m, int64_t N1, int64_t N2, double alpha, cons
     cudaStream_t main = ctx->stream, aux = ctx->aux_stream;
     RLB_CUDA_OK(ctx, cudaEventRecord(ctx->aux_ev[OZ_EV_FORK], main));
     RLB_CUDA_OK(ctx, cudaStreamWaitEvent(aux, ctx->aux_ev[OZ_EV_FORK], 0));
-    ctx->launches += fill_x ? 2 : 1;
-    ctx->timers[RLB200_TIMER_SKETCH].launches += fill_x ? 2 : 1;
+    {
+    LaunchScope ls(ctx, RLB200_TIMER_I8_SLICE, fill_x ? 2 : 1, aux);
     if (fill_x) {
         oz_colexp_kernel<T><<<(unsigned)((N1 * nchunks + 7) / 8), 256, 0, aux>>>(X, ldx, m, (int)N1, L, (int)nchunks, Cfg::P, Ex, ssx);
         if (cached) oz_cache_set(ctx->oz_col, X, m, N1, ldx, L, Cfg::P, (int)sizeof(T));
     }
     oz_colexp_kernel<T><<<(unsigned)((N2 * nchunks + 7) / 8), 256, 0, aux>>>(Y, ldy, m, (int)N2, L, (int)nchunks, Cfg::P, Ey, nullptr);
     RLB_CUDA_OK(ctx, cudaGetLastError());
+    }
     OzTimeline tl;
     int64_t it = 0;
     for (int64_t c0 = 0; c0 < nchunks; c0 += G, ++it) {
@@ -812,8 +832,8 @@ static int oz_tn(Ctx* ctx, int64_t m, int64_t N1, int64_t N2, double alpha, cons
         const int b = (int)(it % nbuf);
         if (it >= nbuf) RLB_CUDA_OK(ctx, cudaStreamWaitEvent(aux, ctx->aux_ev[OZ_EV_CONSUMED + b], 0));
         tl.mark('s', aux);
-        ctx->launches += 2 * g;
-        ctx->timers[RLB200_TIMER_SKETCH].launches += 2 * g;
+        {
+        LaunchScope lsl(ctx, RLB200_TIMER_I8_SLICE, 2 * g, aux);
         for (int q = 0; q < g; ++q) {
             const int64_t r0 = (c0 + q) * L, klen = std::min(L, m - r0);
             if (kmajor) {
@@ -825,12 +845,13 @@ static int oz_tn(Ctx* ctx, int64_t m, int64_t N1, int64_t N2, double alpha, cons
             }
         }
         RLB_CUDA_OK(ctx, cudaGetLastError());
+        }
         tl.mark('S', aux);
         RLB_CUDA_OK(ctx, cudaEventRecord(ctx->aux_ev[OZ_EV_SLICED + b], aux));
         RLB_CUDA_OK(ctx, cudaStreamWaitEvent(main, ctx->aux_ev[OZ_EV_SLICED + b], 0));
         tl.mark('m', main);
         {
-            LaunchScope ls(ctx, RLB200_TIMER_GEMM_TN);
+            LaunchScope ls(ctx, RLB200_TIMER_I8_MMA_TN);
             long long* dbg = nullptr;
             if (c0 == 0 && getenv("RLB200_OZ_DBG")) cudaMalloc(&dbg, (size_t)nb2 * nb1 * g * 64);
             if (kmajor)
@@ -845,7 +866,7 @@ static int oz_tn(Ctx* ctx, int64_t m, int64_t N1, int64_t N2, double alpha, cons
         RLB_CUDA_OK(ctx, cudaEventRecord(ctx->aux_ev[OZ_EV_CONSUMED + b], main));
     }
     tl.report("TN");
-    LaunchScope ls(ctx, RLB200_TIMER_GEMM_TN);
+    LaunchScope ls(ctx, RLB200_TIMER_I8_MMA_TN);
     oz_reduce_kernel<T><<<(unsigned)std::min<int64_t>((total + 255) / 256, (int64_t)ctx->num_sms * 8), 256, 0, main>>>(
         part, (int)std::min<int64_t>(G, nchunks), total, (int)N1, alpha, beta, C, ldc);
     RLB_CUDA_OK(ctx, cudaGetLastError());

@@ -13,6 +13,7 @@ import randlapack_b200 as rl  # noqa: E402
 lm = int(sys.argv[1]) if len(sys.argv) > 1 else 22
 n = int(sys.argv[2]) if len(sys.argv) > 2 else 1024
 k = int(sys.argv[3]) if len(sys.argv) > 3 else 256
+only = sys.argv[4] if len(sys.argv) > 4 else ""   # "nn" / "tn": only that product on the i8 engine (6 digits); "i8": both, i8 only
 m = 1 << lm
 ctx = rl.Context(0)
 dev = torch.device("cuda", 0)
@@ -24,10 +25,10 @@ Y = rl.empty_f(m, k, torch.float64, dev)
 Z = rl.empty_f(n, k, torch.float64, dev)
 out = {"m": m, "n": n, "k": k}
 names = ["gemm_nn", "gemm_tn", "rightmul", "small", "fill", "sketch", "factor"]
-for engname in ("dmma", "i8s6", "i8s7"):
+for engname in (("i8s6",) if only else ("dmma", "i8s6", "i8s7")):
     eng = "dmma" if engname == "dmma" else "i8"
     ctx.set_i8_digits(int(engname[-1]) if eng == "i8" else 0)
-    for op in ("nn", "tn"):
+    for op in (("nn", "tn") if only in ("", "i8") else (only,)):
         def run():
             if op == "nn":
                 rl.gemm(ctx, False, False, 1.0, A, Om, 0.0, Y, engine=eng)
