@@ -182,6 +182,8 @@ def run_secondary(args):
     torch.cuda.set_device(0)
     dev = torch.device("cuda", 0)
     ctx = rl.Context(0)
+    ctx.set_fp64_engine(args.engine)
+    ctx.set_i8_digits(args.digits)
     peaks = load_peaks()
     hbm = peaks.get("hbm_gbs", 6650.0)
     hbm_src = "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
@@ -258,8 +260,10 @@ def run_secondary(args):
         peak, src, _ = measured_fp64_peak()
         out = {"metric": "cqrrpt_gflops", "value": fl / ms / 1e6, "unit": "Gflop/s", "ms_per_step": ms,
                "roofline": {"bound": "tensor", "achieved": fl / ms / 1e9, "peak": peak, "unit": "TFLOP/s", "frac": fl / ms / 1e9 / peak,
-                            "traffic": None, "peak_source": src + " (fp32 storage, fp64 DMMA arithmetic)"},
-               "config": {"workload": f"CQRRPT of a {m} x {n} {args.dtype} Gaussian matrix, SASO d={d} vec_nnz={nnz}, geqp3 (configs[2])"}}
+                            "traffic": None, "peak_source": src + " (fp64 DMMA pipe; with --engine i8 the O(m n^2) work runs on tcgen05 "
+                                                                  "int8 digit slices instead, so frac can exceed 1)"},
+               "config": {"workload": f"CQRRPT of a {m} x {n} {args.dtype} Gaussian matrix, SASO d={d} vec_nnz={nnz}, geqp3 (configs[2])",
+                          "engine": args.engine}}
     elif wl == "bqrrp":
         n = args.n if args.n != 1024 else 65536
         m = args.m if args.m != (1 << 24) else n

@@ -542,6 +542,38 @@ static int read_diag(Ctx* ctx, const T* M, int64_t ld, int64_t k, std::vector<T>
     return 0;
 }
 
+// A <- A * R^-1 (blas::trsm Right/Upper, rl_cqrrpt.hh:306,342) and the Gram matrix of CholQR (syrk, :314) for tall A.
+// On the int8-slice engine the solve is one in-place tall product with the explicit inverse (R^-1 = I * R^-1 through the blocked
+// solver on the k x k identity), which keeps all O(m k^2) work on tcgen05; the triangular zeros of R^-1 are skipped.
+// fp64 QR factors must pass the reference's eps^0.75 acceptance tests (test_cqrrpt.cc:98-104): 7 digits (54 bits) unless the caller
+// fixed the digit count; fp32 storage keeps its default (4 digits, 30 bits).
+struct OzQrDigits {
+    Ctx* ctx; int old;
+    OzQrDigits(Ctx* c, size_t elem) : ctx(c), old(c->i8_digits) { if (!old && elem == 8) c->i8_digits = 7; }
+    ~OzQrDigits() { ctx->i8_digits = old; }
+};
+template <typename T>
+static int tall_right_solve(Ctx* ctx, int64_t m, int64_t k, const T* R, int64_t ldr, T* A, int64_t lda) {
+    if (ctx->fp64_engine == RLB200_FP64_I8SLICES && m >= 8192 && k >= 64 && k <= 16384) {
+        OzQrDigits dg(ctx, sizeof(T));
+        ArenaScope as(ctx);
+        T* Rinv = as.take<T>((size_t)k * k); RLB_ALLOC(ctx, Rinv);
+        RLB_CUDA_OK(ctx, cudaMemsetAsync(Rinv, 0, sizeof(T) * k * k, ctx->stream));
+        RLB_CHECK(set_upper_diag<T>(ctx, k, Rinv, k, (T)1, false));
+        RLB_CHECK(trsm_right_upper<T>(ctx, k, k, R, ldr, Rinv, k));
+        return ozaki_gemm_nn<T>(ctx, m, k, k, 1.0, A, lda, Rinv, k, 0.0, A, lda, /*b_upper_tri=*/true);
+    }
+    return trsm_right_upper<T>(ctx, m, k, R, ldr, A, lda);
+}
+template <typename T>
+static int tall_gram_upper(Ctx* ctx, int64_t m, int64_t k, const T* A, int64_t lda, T* G, int64_t ldg) {
+    if (ctx->fp64_engine == RLB200_FP64_I8SLICES && m >= 8192 && k >= 64) {
+        OzQrDigits dg(ctx, sizeof(T));
+        return ozaki_gemm_tn<T>(ctx, m, k, k, 1.0, A, lda, A, lda, 0.0, G, ldg, nullptr, /*upper_only=*/true);
+    }
+    return gemm_tn<T>(ctx, m, k, k, 1.0, A, lda, A, lda, 0.0, G, ldg, 1);
+}
+
 template <typename T>
 int cqrrpt_call(Ctx* ctx, int64_t m, int64_t n, T* A, int64_t lda, T* R, int64_t ldr, int64_t* J_dev, T d_factor, T eps_user, int64_t nnz,
                 int64_t* rank_out, uint32_t state[6]) {
@@ -593,11 +625,11 @@ int cqrrpt_call(Ctx* ctx, int64_t m, int64_t n, T* A, int64_t lda, T* R, int64_t
         RLB_CHECK(col_permute<T>(ctx, m, n, A, lda, J.data()));
     }
     for (int64_t i = 0; i < k; ++i) if (dg[i] == (T)0) return 1;                              // diag_is_nonzero :300-305
-    RLB_CHECK(trsm_right_upper<T>(ctx, m, k, R, ldr, A, lda));                                // :306
+    RLB_CHECK(tall_right_solve<T>(ctx, m, k, R, ldr, A, lda));                                // :306
     // CholQR (:314-339): the Gram / Cholesky factor is built in scratch so that only the upper triangle of R is written
     T* G = as.take<T>((size_t)k * k); RLB_ALLOC(ctx, G);
     RLB_CUDA_OK(ctx, cudaMemsetAsync(G, 0, sizeof(T) * k * k, ctx->stream));
-    RLB_CHECK(gemm_tn<T>(ctx, m, k, k, 1.0, A, lda, A, lda, 0.0, G, k, 1));
+    RLB_CHECK(tall_gram_upper<T>(ctx, m, k, A, lda, G, k));
     if (sharded) RLB_CHECK(allreduce_sum<T>(ctx, G, k * k));
     int info = 0;
     RLB_CHECK(potrf_blocked<T>(ctx, k, G, k, &info));
@@ -615,7 +647,7 @@ int cqrrpt_call(Ctx* ctx, int64_t m, int64_t n, T* A, int64_t lda, T* R, int64_t
         }
     }
     *rank_out = new_rank;                                                                     // :339
-    RLB_CHECK(trsm_right_upper<T>(ctx, m, new_rank, R, ldr, A, lda));                         // :342
+    RLB_CHECK(tall_right_solve<T>(ctx, m, new_rank, R, ldr, A, lda));                         // :342
     // R <- R[0:new_rank, 0:n] * triu(A_hat[0:n, 0:n])  (trmm :349)
     if (new_rank > 0) {
         T* U = as.take<T>((size_t)n * n); RLB_ALLOC(ctx, U);

@@ -38,13 +38,16 @@ template <typename T>
 int svd_tall(Ctx* ctx, int64_t n, int64_t k, T* B, int64_t ldb, T* S, T* W, void* ws, int* sweeps_out);
 
 // ---- tall GEMMs on tcgen05 int8 tensor cores through exact digit slices (ozaki.cu) ------------------------
+// C may alias A (in place: every row chunk is sliced before its rows are overwritten).  b_upper_tri: B is upper triangular
+// (zeros below the diagonal are not multiplied).
 template <typename T>
 int ozaki_gemm_nn(Ctx* ctx, int64_t m, int64_t N, int64_t K, double alpha, const T* A, int64_t lda, const T* B, int64_t ldb, double beta,
-                  T* C, int64_t ldc);
-// x_sumsq_out (device scalar, optional): ||X||_F^2, accumulated in the exponent pass over X (no extra sweep)
+                  T* C, int64_t ldc, bool b_upper_tri = false);
+// x_sumsq_out (device scalar, optional): ||X||_F^2, accumulated in the exponent pass over X (no extra sweep).
+// upper_only: only the tiles touching the upper triangle of C are computed (Gram matrices; the rest of C is set to alpha * 0 + beta * C).
 template <typename T>
 int ozaki_gemm_tn(Ctx* ctx, int64_t m, int64_t N1, int64_t N2, double alpha, const T* X, int64_t ldx, const T* Y, int64_t ldy, double beta,
-                  T* C, int64_t ldc, double* x_sumsq_out = nullptr);
+                  T* C, int64_t ldc, double* x_sumsq_out = nullptr, bool upper_only = false);
 void oz_cache_destroy(Ctx* ctx);
 // While alive, the first operand `A` of the tall products is known not to change: its row / column-chunk exponents are computed once
 // and reused by every pass (outermost scope wins; nested scopes on the same or another pointer are no-ops).

@@ -334,8 +334,13 @@ template <int S, typename TO, bool MN>
 __global__ void __launch_bounds__(256, 1)
 ozaki_mma_kernel(const int8_t* __restrict__ a_tiles, int64_t a_group_stride, const int8_t* __restrict__ b_tiles, int64_t b_group_stride, int nkb,
                  const int* __restrict__ Ea, int64_t ea_stride, const int* __restrict__ Eb, int64_t eb_stride, int64_t rows_a, int rows_b,
-                 TO* __restrict__ out, int64_t ldo, int64_t out_group_stride, double alpha, double beta, long long* __restrict__ dbg) {
+                 TO* __restrict__ out, int64_t ldo, int64_t out_group_stride, double alpha, double beta, long long* __restrict__ dbg, int flags) {
     using Cfg = OzCfg<S>;
+    // flags & 1: the second operand is an upper-triangular K x N matrix (tile column block x only has non-zeros in K < 64 (x + 1)):
+    //            the K loop stops there.  flags & 2: only tiles that touch the upper triangle of the output are computed (Gram).
+    if ((flags & 2) && (int)blockIdx.y * OZ_BM > (int)blockIdx.x * OZ_BN + OZ_BN - 1) return;
+    const int nkb_stride = nkb;                     // K blocks per tile row in memory
+    if (flags & 1) nkb = min(nkb, ((int)blockIdx.x + 1) * (OZ_BN / OZ_KB));
     constexpr int STAGES = Cfg::STAGES;
     long long t_start = 0, t_ready = 0, t_first = 0, t_acc = 0;
     if (dbg) t_start = clock64();
@@ -349,8 +354,8 @@ ozaki_mma_kernel(const int8_t* __restrict__ a_tiles, int64_t a_group_stride, con
     asm volatile("mov.u32 %0, %%cluster_nctaid.x;" : "=r"(cs));
     asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
     const uint16_t cmask = (uint16_t)((1u << cs) - 1u);
-    const int8_t* ga = a_tiles + g * a_group_stride + (int64_t)blockIdx.y * nkb * (S * OZ_TILE_A);
-    const int8_t* gb = b_tiles + g * b_group_stride + (int64_t)blockIdx.x * nkb * (S * OZ_TILE_B);
+    const int8_t* ga = a_tiles + g * a_group_stride + (int64_t)blockIdx.y * nkb_stride * (S * OZ_TILE_A);
+    const int8_t* gb = b_tiles + g * b_group_stride + (int64_t)blockIdx.x * nkb_stride * (S * OZ_TILE_B);
 
     if (tid == 0) {
         for (int s = 0; s < STAGES; ++s) {
@@ -560,7 +565,7 @@ static int oz_pick_cluster(const int* cs_ok, int nxb) {
 template <int S, typename TO, bool MN>
 static int oz_launch_mma(Ctx* ctx, dim3 grid, int cs, cudaStream_t stream, const int8_t* a_tiles, int64_t a_group_stride, const int8_t* b_tiles,
                          int64_t b_group_stride, int nkb, const int* Ea, int64_t ea_stride, const int* Eb, int64_t eb_stride, int64_t rows_a, int rows_b,
-                         TO* out, int64_t ldo, int64_t out_group_stride, double alpha, double beta, long long* dbg = nullptr) {
+                         TO* out, int64_t ldo, int64_t out_group_stride, double alpha, double beta, long long* dbg = nullptr, int flags = 0) {
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = grid;
     cfg.blockDim = dim3(256);
@@ -571,7 +576,7 @@ static int oz_launch_mma(Ctx* ctx, dim3 grid, int cs, cudaStream_t stream, const
     at[0].val.clusterDim.x = cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
     RLB_CUDA_OK(ctx, cudaLaunchKernelEx(&cfg, ozaki_mma_kernel<S, TO, MN>, a_tiles, a_group_stride, b_tiles, b_group_stride, nkb, Ea, ea_stride, Eb, eb_stride,
-                                        rows_a, rows_b, out, ldo, out_group_stride, alpha, beta, dbg));
+                                        rows_a, rows_b, out, ldo, out_group_stride, alpha, beta, dbg, flags));
     return 0;
 }
 // RLB200_OZ_DBG=1: per-CTA cycle stamps of one launch (start, barriers/TMEM ready, first stage landed, accumulators complete, end),
@@ -682,7 +687,7 @@ struct OzTimeline {
 
 template <int S, typename T>
 static int oz_nn(Ctx* ctx, int64_t m, int64_t N, int64_t K, double alpha, const T* A, int64_t lda, const T* B, int64_t ldb, double beta, T* C,
-                 int64_t ldc) {
+                 int64_t ldc, bool b_upper_tri) {
     using Cfg = OzCfg<S>;
     int cs_ok[5];
     RLB_CHECK((oz_configure<S, T, false>(ctx, cs_ok)));
@@ -760,7 +765,7 @@ static int oz_nn(Ctx* ctx, int64_t m, int64_t N, int64_t K, double alpha, const 
                 const int mode = atoi(getenv("RLB200_OZ_DBG")) - 1;
                 cudaMemcpyToSymbol(oz_dbg_mode, &mode, sizeof(int));
             }
-            RLB_CHECK((oz_launch_mma<S, T, false>(ctx, dim3(nnb, nrb, 1), cs, main, at[b], 0, bt, 0, nkb, Ea_c, 0, Eb, 0, rows, (int)N, C + r0, ldc, 0, alpha, beta, dbg)));
+            RLB_CHECK((oz_launch_mma<S, T, false>(ctx, dim3(nnb, nrb, 1), cs, main, at[b], 0, bt, 0, nkb, Ea_c, 0, Eb, 0, rows, (int)N, C + r0, ldc, 0, alpha, beta, dbg, b_upper_tri ? 1 : 0)));
             if (dbg) { oz_dbg_report("NN", main, dbg, (int64_t)nnb * nrb); cudaFree(dbg); }
         }
         tl.mark('M', main);
@@ -775,7 +780,7 @@ static int oz_nn(Ctx* ctx, int64_t m, int64_t N, int64_t K, double alpha, const 
 // ------------------------------------------------------------------------------------------------
 template <int S, typename T>
 static int oz_tn(Ctx* ctx, int64_t m, int64_t N1, int64_t N2, double alpha, const T* X, int64_t ldx, const T* Y, int64_t ldy, double beta, T* C,
-                 int64_t ldc, double* x_sumsq_out) {
+                 int64_t ldc, double* x_sumsq_out, bool upper_only) {
     using Cfg = OzCfg<S>;
     int cs_ok[5];
     static const bool kmajor = getenv("RLB200_OZ_TN_KMAJOR") != nullptr;      // diagnostics: the K-major column slicer
@@ -806,7 +811,10 @@ static int oz_tn(Ctx* ctx, int64_t m, int64_t N1, int64_t N2, double alpha, cons
         Ex = as.take<int>((size_t)nchunks * N1); if (!Ex) return RLB200_ERR_ALLOC;
         if (x_sumsq_out) { ssx = as.take<double>((size_t)nchunks * N1); if (!ssx) return RLB200_ERR_ALLOC; }
     }
-    int* Ey = as.take<int>((size_t)nchunks * N2); if (!Ey) return RLB200_ERR_ALLOC;
+    const bool same_xy = (const void*)X == (const void*)Y && ldx == ldy && N1 == N2;     // Gram: one exponent pass serves both sides
+    int* Ey = Ex;
+    if (!same_xy) { Ey = as.take<int>((size_t)nchunks * N2); if (!Ey) return RLB200_ERR_ALLOC; }
+    if (upper_only) RLB_CUDA_OK(ctx, cudaMemsetAsync(part, 0, sizeof(double) * (size_t)G * total, ctx->stream));
     const int64_t xs = (int64_t)nb1 * nkb * S * OZ_TILE_A, ys = (int64_t)nb2 * nkb * S * OZ_TILE_B;   // bytes per chunk
     int8_t* xt[2]; int8_t* yt[2];
     for (int b = 0; b < nbuf; ++b) {
@@ -817,12 +825,12 @@ static int oz_tn(Ctx* ctx, int64_t m, int64_t N1, int64_t N2, double alpha, cons
     RLB_CUDA_OK(ctx, cudaEventRecord(ctx->aux_ev[OZ_EV_FORK], main));
     RLB_CUDA_OK(ctx, cudaStreamWaitEvent(aux, ctx->aux_ev[OZ_EV_FORK], 0));
     {
-    LaunchScope ls(ctx, RLB200_TIMER_I8_SLICE, fill_x ? 2 : 1, aux);
+    LaunchScope ls(ctx, RLB200_TIMER_I8_SLICE, (fill_x ? 1 : 0) + (same_xy ? 0 : 1), aux);
     if (fill_x) {
         oz_colexp_kernel<T><<<(unsigned)((N1 * nchunks + 7) / 8), 256, 0, aux>>>(X, ldx, m, (int)N1, L, (int)nchunks, Cfg::P, Ex, ssx);
         if (cached) oz_cache_set(ctx->oz_col, X, m, N1, ldx, L, Cfg::P, (int)sizeof(T));
     }
-    oz_colexp_kernel<T><<<(unsigned)((N2 * nchunks + 7) / 8), 256, 0, aux>>>(Y, ldy, m, (int)N2, L, (int)nchunks, Cfg::P, Ey, nullptr);
+    if (!same_xy) oz_colexp_kernel<T><<<(unsigned)((N2 * nchunks + 7) / 8), 256, 0, aux>>>(Y, ldy, m, (int)N2, L, (int)nchunks, Cfg::P, Ey, nullptr);
     RLB_CUDA_OK(ctx, cudaGetLastError());
     }
     OzTimeline tl;
@@ -856,10 +864,10 @@ static int oz_tn(Ctx* ctx, int64_t m, int64_t N1, int64_t N2, double alpha, cons
             if (c0 == 0 && getenv("RLB200_OZ_DBG")) cudaMalloc(&dbg, (size_t)nb2 * nb1 * g * 64);
             if (kmajor)
                 RLB_CHECK((oz_launch_mma<S, double, false>(ctx, dim3(nb2, nb1, g), cs, main, xt[b], xs, yt[b], ys, nkb, Ex + c0 * N1, N1, Ey + c0 * N2, N2, N1,
-                                                           (int)N2, part, N1, total, 1.0, c0 > 0 ? 1.0 : 0.0, dbg)));
+                                                           (int)N2, part, N1, total, 1.0, c0 > 0 ? 1.0 : 0.0, dbg, upper_only ? 2 : 0)));
             else
                 RLB_CHECK((oz_launch_mma<S, double, true>(ctx, dim3(nb2, nb1, g), cs, main, xt[b], xs, yt[b], ys, nkb, Ex + c0 * N1, N1, Ey + c0 * N2, N2, N1,
-                                                          (int)N2, part, N1, total, 1.0, c0 > 0 ? 1.0 : 0.0, dbg)));
+                                                          (int)N2, part, N1, total, 1.0, c0 > 0 ? 1.0 : 0.0, dbg, upper_only ? 2 : 0)));
             if (dbg) { oz_dbg_report("TN", main, dbg, (int64_t)nb2 * nb1 * g); cudaFree(dbg); }
         }
         tl.mark('M', main);
@@ -885,35 +893,35 @@ static int oz_default_digits(Ctx* ctx, size_t elem) {
 
 template <typename T>
 int ozaki_gemm_nn(Ctx* ctx, int64_t m, int64_t N, int64_t K, double alpha, const T* A, int64_t lda, const T* B, int64_t ldb, double beta, T* C,
-                  int64_t ldc) {
+                  int64_t ldc, bool b_upper_tri) {
     RLB_REQUIRE(ctx, m >= 0 && N >= 0 && K >= 0 && N < (1 << 20));
     if (m == 0 || N == 0) return 0;
     if (K == 0 || K > OZ_KMAX) return gemm_nn<T>(ctx, m, N, K, alpha, A, lda, B, ldb, beta, C, ldc);
     switch (oz_default_digits(ctx, sizeof(T))) {
-        case 3: return oz_nn<3, T>(ctx, m, N, K, alpha, A, lda, B, ldb, beta, C, ldc);
-        case 4: return oz_nn<4, T>(ctx, m, N, K, alpha, A, lda, B, ldb, beta, C, ldc);
-        case 5: return oz_nn<5, T>(ctx, m, N, K, alpha, A, lda, B, ldb, beta, C, ldc);
-        case 6: return oz_nn<6, T>(ctx, m, N, K, alpha, A, lda, B, ldb, beta, C, ldc);
-        default: return oz_nn<7, T>(ctx, m, N, K, alpha, A, lda, B, ldb, beta, C, ldc);
+        case 3: return oz_nn<3, T>(ctx, m, N, K, alpha, A, lda, B, ldb, beta, C, ldc, b_upper_tri);
+        case 4: return oz_nn<4, T>(ctx, m, N, K, alpha, A, lda, B, ldb, beta, C, ldc, b_upper_tri);
+        case 5: return oz_nn<5, T>(ctx, m, N, K, alpha, A, lda, B, ldb, beta, C, ldc, b_upper_tri);
+        case 6: return oz_nn<6, T>(ctx, m, N, K, alpha, A, lda, B, ldb, beta, C, ldc, b_upper_tri);
+        default: return oz_nn<7, T>(ctx, m, N, K, alpha, A, lda, B, ldb, beta, C, ldc, b_upper_tri);
     }
 }
 template <typename T>
 int ozaki_gemm_tn(Ctx* ctx, int64_t m, int64_t N1, int64_t N2, double alpha, const T* X, int64_t ldx, const T* Y, int64_t ldy, double beta, T* C,
-                  int64_t ldc, double* x_sumsq_out) {
+                  int64_t ldc, double* x_sumsq_out, bool upper_only) {
     RLB_REQUIRE(ctx, m >= 0 && N1 >= 0 && N2 >= 0 && N1 < (1 << 20) && N2 < (1 << 20));
     if (N1 == 0 || N2 == 0) return 0;
     if (m == 0) return gemm_tn<T>(ctx, 0, N1, N2, 0.0, X, ldx, Y, ldy, beta, C, ldc, 0, x_sumsq_out);
     switch (oz_default_digits(ctx, sizeof(T))) {
-        case 3: return oz_tn<3, T>(ctx, m, N1, N2, alpha, X, ldx, Y, ldy, beta, C, ldc, x_sumsq_out);
-        case 4: return oz_tn<4, T>(ctx, m, N1, N2, alpha, X, ldx, Y, ldy, beta, C, ldc, x_sumsq_out);
-        case 5: return oz_tn<5, T>(ctx, m, N1, N2, alpha, X, ldx, Y, ldy, beta, C, ldc, x_sumsq_out);
-        case 6: return oz_tn<6, T>(ctx, m, N1, N2, alpha, X, ldx, Y, ldy, beta, C, ldc, x_sumsq_out);
-        default: return oz_tn<7, T>(ctx, m, N1, N2, alpha, X, ldx, Y, ldy, beta, C, ldc, x_sumsq_out);
+        case 3: return oz_tn<3, T>(ctx, m, N1, N2, alpha, X, ldx, Y, ldy, beta, C, ldc, x_sumsq_out, upper_only);
+        case 4: return oz_tn<4, T>(ctx, m, N1, N2, alpha, X, ldx, Y, ldy, beta, C, ldc, x_sumsq_out, upper_only);
+        case 5: return oz_tn<5, T>(ctx, m, N1, N2, alpha, X, ldx, Y, ldy, beta, C, ldc, x_sumsq_out, upper_only);
+        case 6: return oz_tn<6, T>(ctx, m, N1, N2, alpha, X, ldx, Y, ldy, beta, C, ldc, x_sumsq_out, upper_only);
+        default: return oz_tn<7, T>(ctx, m, N1, N2, alpha, X, ldx, Y, ldy, beta, C, ldc, x_sumsq_out, upper_only);
     }
 }
-template int ozaki_gemm_nn<double>(Ctx*, int64_t, int64_t, int64_t, double, const double*, int64_t, const double*, int64_t, double, double*, int64_t);
-template int ozaki_gemm_nn<float>(Ctx*, int64_t, int64_t, int64_t, double, const float*, int64_t, const float*, int64_t, double, float*, int64_t);
-template int ozaki_gemm_tn<double>(Ctx*, int64_t, int64_t, int64_t, double, const double*, int64_t, const double*, int64_t, double, double*, int64_t, double*);
-template int ozaki_gemm_tn<float>(Ctx*, int64_t, int64_t, int64_t, double, const float*, int64_t, const float*, int64_t, double, float*, int64_t, double*);
+template int ozaki_gemm_nn<double>(Ctx*, int64_t, int64_t, int64_t, double, const double*, int64_t, const double*, int64_t, double, double*, int64_t, bool);
+template int ozaki_gemm_nn<float>(Ctx*, int64_t, int64_t, int64_t, double, const float*, int64_t, const float*, int64_t, double, float*, int64_t, bool);
+template int ozaki_gemm_tn<double>(Ctx*, int64_t, int64_t, int64_t, double, const double*, int64_t, const double*, int64_t, double, double*, int64_t, double*, bool);
+template int ozaki_gemm_tn<float>(Ctx*, int64_t, int64_t, int64_t, double, const float*, int64_t, const float*, int64_t, double, float*, int64_t, double*, bool);
 
 }  // namespace rlb

@@ -206,7 +206,7 @@ __global__ void __launch_bounds__(256) saso_plan_kernel(Ctr128 seed, uint32_t k0
         const uint32_t bound = (r >= d_sub) ? 0xFFFFFFFFu : ((uint32_t)r << 12);
         int lo = 0, hi = E2;   // first index with key >= bound
         while (lo < hi) { const int mid = (lo + hi) >> 1; if (keys[mid] < bound) lo = mid + 1; else hi = mid; }
-        off[(int64_t)q * (d_pad + 1) + r] = (uint16_t)lo;
+        off[(int64_t)q * (d_pad + 8) + r] = (uint16_t)lo;     // pitch d_pad + 8: every chunk's list starts 16-byte aligned
     }
 }
 
@@ -220,6 +220,10 @@ saso_apply_kernel(const T* __restrict__ A, int64_t lda, int64_t m, int n, int d_
     extern __shared__ __align__(16) unsigned char smem_raw[];
     T* tile = reinterpret_cast<T*>(smem_raw);
     const int RP = R + EV;                       // row pitch of one staged column (keeps 16-byte alignment, shifts banks)
+    // the chunk's CSR (entries + row offsets) is staged next to the tile: the list walk below reads shared memory only
+    constexpr int OP = d_pad + 8;
+    uint16_t* s_ent = reinterpret_cast<uint16_t*>(smem_raw + (size_t)2 * CW * RP * sizeof(T));
+    uint16_t* s_off = s_ent + (size_t)2 * E;
     const int tid = threadIdx.x;
     const int c0 = blockIdx.x * CW;
     const int split = blockIdx.y;
@@ -235,6 +239,10 @@ saso_apply_kernel(const T* __restrict__ A, int64_t lda, int64_t m, int n, int d_
             const T* src = A + (J0 + jl) + (int64_t)(c0 + c) * lda;
             load_chunk<T>(t + c * RP + jl, valid > 0 ? src : A, valid, a_al16);
         }
+        const uint16_t* ge = ent + (int64_t)q * E;
+        for (int i = tid; i < E / 8; i += kSasoThreads) cp_async_16(s_ent + (size_t)buf * E + i * 8, ge + i * 8, true);
+        const uint16_t* go = off + (int64_t)q * OP;
+        for (int i = tid; i < OP / 8; i += kSasoThreads) cp_async_16(s_off + (size_t)buf * OP + i * 8, go + i * 8, true);
     };
 
     T acc[RPT][CW];
@@ -249,15 +257,14 @@ saso_apply_kernel(const T* __restrict__ A, int64_t lda, int64_t m, int n, int d_
         const int buf = (q - q0) & 1;
         if (q + 1 < q1) stage(buf ^ 1, q + 1);
         cp_async_commit();
-        // this thread's CSR offsets (global/L2; contiguous across the CTA)
-        const uint16_t* op = off + (int64_t)q * (d_pad + 1) + tid * RPT;
+        cp_async_wait<1>();
+        __syncthreads();
+        const uint16_t* op = s_off + (size_t)buf * OP + tid * RPT;
         int o[RPT + 1];
 #pragma unroll
         for (int i = 0; i <= RPT; ++i) o[i] = op[i];
-        cp_async_wait<1>();
-        __syncthreads();
         const T* t = tile + (size_t)buf * CW * RP;
-        const uint16_t* ep = ent + (int64_t)q * E;
+        const uint16_t* ep = s_ent + (size_t)buf * E;
 #pragma unroll
         for (int i = 0; i < RPT; ++i) {
             for (int e = o[i]; e < o[i + 1]; ++e) {
@@ -309,7 +316,7 @@ static int saso_apply_launch(Ctx* ctx, const T* A, int64_t lda, int64_t m, int n
     splits = (nchunks + cps - 1) / cps;
     ArenaScope as(ctx);
     T* partial = as.take<T>((size_t)splits * d_sub * n); if (!partial) return RLB200_ERR_ALLOC;
-    const size_t smem = (size_t)2 * CW * (R + EV) * sizeof(T);
+    const size_t smem = (size_t)2 * CW * (R + EV) * sizeof(T) + (size_t)2 * (E + kSasoThreads * RPT + 8) * sizeof(uint16_t);
     auto kern = saso_apply_kernel<T, RPT, CW>;
     RLB_CUDA_OK(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int al = (reinterpret_cast<uintptr_t>(A) % 16 == 0) && (lda % EV == 0);
@@ -356,7 +363,7 @@ int sketch_sparse_left(Ctx* ctx, int64_t S_rows, int64_t S_cols, int64_t vec_nnz
             const int d_pad = kSasoThreads * rpt;
             ArenaScope as(ctx);
             uint16_t* ent = as.take<uint16_t>((size_t)nchunks * E); if (!ent) return RLB200_ERR_ALLOC;
-            uint16_t* off = as.take<uint16_t>((size_t)nchunks * (d_pad + 1)); if (!off) return RLB200_ERR_ALLOC;
+            uint16_t* off = as.take<uint16_t>((size_t)nchunks * (d_pad + 8)); if (!off) return RLB200_ERR_ALLOC;
             {
                 RLB_CUDA_OK(ctx, cudaFuncSetAttribute(saso_plan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, E2 * 4));
                 LaunchScope ls(ctx, RLB200_TIMER_SKETCH);

@@ -18,7 +18,9 @@ def main():
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     ctx = rl.Context(local)
     out = {}
-    for (m, n, k, p) in [(40000, 256, 32, 2), (70001, 128, 16, 3), (12800, 64, 64, 0)]:
+    for (m, n, k, p, engine) in [(40000, 256, 32, 2, "dmma"), (70001, 128, 16, 3, "dmma"), (12800, 64, 64, 0, "dmma"),
+                                 (40000, 256, 32, 2, "i8"), (70001, 128, 16, 3, "i8")]:
+        ctx.set_fp64_engine(engine)      # "i8": the tall products over A on the tcgen05 int8 digit-slice engine
         # global matrix: planted decaying spectrum so that the factors are well defined; identical on every rank
         g = torch.Generator(device="cuda").manual_seed(1234)
         G1 = torch.randn((m, n), dtype=torch.float64, device="cuda", generator=g)
@@ -39,7 +41,7 @@ def main():
                "S_rel": ((S[:kk] - S1[:kk]).abs().max() / S1[0]).item() if kk else 0.0,
                "V_abs": (V[:, :kk].abs() - V1[:, :kk].abs()).abs().max().item() if kk else 0.0,
                "U_abs": (U[:, :kk].abs() - U1[r0:r1, :kk].abs()).abs().max().item() if kk else 0.0}
-        out[f"{m}x{n}_k{k}_p{p}"] = res
+        out[f"{m}x{n}_k{k}_p{p}_{engine}"] = res
     gathered = [None] * world
     dist.all_gather_object(gathered, out)
     if rank == 0:

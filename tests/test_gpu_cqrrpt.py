@@ -150,3 +150,36 @@ def test_cqrrpt_large_property(ctx):
     rows = torch.randint(0, m, (4096,), device="cuda")
     E = A0[rows][:, J - 1].double() - A[rows].double() @ R.double()
     assert float(E.norm() / A0[rows].double().norm()) <= 1e-4
+
+
+@pytest.mark.parametrize("dtype,m,n", [(torch.float64, 40000, 300), (torch.float32, 40000, 300), (torch.float32, 1 << 18, 512)])
+def test_cqrrpt_i8_engine(ctx, dtype, m, n):
+    """CQRRPT with its O(m n^2) work (A R^-1 as one in-place product with the explicit inverse, Gram matrix) on the tcgen05 int8
+    digit-slice engine: same return code, rank and pivots (bit-exact) as the fp64-pipe path, R to the path's tolerance, and the
+    reference's acceptance test (test_cqrrpt.cc:98-104) on the result."""
+    g = torch.Generator(device="cuda").manual_seed(11)
+    A0 = rl.to_f(torch.randn((m, n), dtype=dtype, device="cuda", generator=g))
+    A0 *= (1.0 + torch.arange(n, device="cuda", dtype=dtype))[None, :] ** -0.75
+    outs = []
+    for engine in ("dmma", "i8"):
+        ctx.set_fp64_engine(engine)
+        try:
+            A = A0.clone()
+            alg = rl.CQRRPT(False, None)
+            alg.nnz = 2
+            rc, R, J = alg.call(ctx, A, 1.5, rl.RNGState(7))
+        finally:
+            ctx.set_fp64_engine("dmma")
+        outs.append((rc, alg.rank, J.cpu().numpy(), R, A))
+    (rc0, rk0, J0, R0, Q0), (rc1, rk1, J1, R1, Q1) = outs
+    assert (rc0, rk0) == (rc1, rk1) == (0, n)
+    assert np.array_equal(J0, J1)
+    tol = 1e-8 if dtype == torch.float64 else 2e-3
+    assert float((R1 - R0).abs().max() / R0.abs().max()) <= tol
+    eps = np.finfo(np.float64 if dtype == torch.float64 else np.float32).eps
+    QtQ = rl.gemm(ctx, True, False, 1.0, Q1, Q1)
+    assert float((QtQ - torch.eye(n, device="cuda", dtype=dtype)).norm()) / n ** 0.5 <= eps ** 0.75
+    rows = torch.randint(0, m, (4096,), device="cuda")
+    Jt = torch.from_numpy(J1 - 1).cuda()
+    E = A0[rows][:, Jt].double() - Q1[rows].double() @ R1.double()
+    assert float(E.norm() / A0[rows].double().norm()) <= eps ** 0.75

@@ -24,4 +24,5 @@ def test_sharded_rsvd_matches_single_gpu():
         for name, res in per_rank.items():
             assert res["rc"][0] == res["rc"][1] and res["k"][0] == res["k"][1], (name, res)
             assert res["state_equal"], (name, res)
-            assert res["S_rel"] <= 1e-12 and res["V_abs"] <= 1e-9 and res["U_abs"] <= 1e-9, (name, res)
+            # int8 digit-slice engine: 46 bits below each scaling group's maximum, and the groups differ between the two runs
+            assert res["S_rel"] <= (1e-11 if name.endswith("i8") else 1e-12) and res["V_abs"] <= 1e-9 and res["U_abs"] <= 1e-9, (name, res)
