@@ -295,6 +295,19 @@ def run_secondary(args):
     else:
         raise SystemExit(f"unknown workload {wl}")
     clocks = sampler.stop()
+    # per-class CUDA-event times of one extra, untimed step
+    if wl in ("cqrrpt", "bqrrp"):
+        names = ["gemm_nn", "gemm_tn", "rightmul", "small", "fill", "sketch", "factor", "i8_mma_nn", "i8_mma_tn", "i8_slice"]
+        ctx.timers_enable(True)
+        for w in range(len(names)):
+            ctx.timer_read(w, reset=True)
+        prep()
+        step()
+        torch.cuda.synchronize()
+        tm = {nm: ctx.timer_read(i) for i, nm in enumerate(names)}
+        ctx.timers_enable(False)
+        out["class_ms_per_step"] = {k_: round(v[0], 3) for k_, v in tm.items() if v[1]}
+        out["class_launches_per_step"] = {k_: v[1] for k_, v in tm.items() if v[1]}
     out.update({"n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": args.dtype, "data": "synthetic", "clocks": clocks, "gpu_launches": ctx.launch_count(), "cpu_baseline": None, "e2e": None})
     out["config"]["l2"] = "inputs exceed the 126 MB L2 by >100x; no flush needed"

@@ -254,12 +254,22 @@ template <typename T>
 static int apply_qt_wy(Ctx* ctx, int64_t rows, int64_t k, int64_t nc, const T* V1c, const T* V2, int64_t ldv, const T* Tm, int64_t ldt, T* C,
                        int64_t ldc, T* W, T* W2) {
     if (nc == 0 || k == 0) return 0;
-    RLB_CHECK(gemm_tn<T>(ctx, k, k, nc, 1.0, V1c, k, C, ldc, 0.0, W, k, 0));                                  // W = V1^T C1
-    if (rows > k) RLB_CHECK(gemm_tn<T>(ctx, rows - k, k, nc, 1.0, V2, ldv, C + k, ldc, 1.0, W, k, 0));        //   + V2^T C2
-    RLB_CHECK(gemm_tn<T>(ctx, k, k, nc, 1.0, Tm, ldt, W, k, 0.0, W2, k, 0));                                  // W2 = T^T W
-    RLB_CHECK(gemm_nn<T>(ctx, k, nc, k, -1.0, V1c, k, W2, k, 1.0, C, ldc));                                   // C1 -= V1 W2
-    if (rows > k) RLB_CHECK(gemm_nn<T>(ctx, rows - k, nc, k, -1.0, V2, ldv, W2, k, 1.0, C + k, ldc));         // C2 -= V2 W2
-    return 0;
+    // the two tall products run on the int8-slice engine when it is selected (7 digits for fp64: the factors must pass the
+    // reference's eps^0.75 acceptance tests, test_bqrrp.cc:105-107)
+    const bool i8 = ctx->fp64_engine == RLB200_FP64_I8SLICES && rows - k >= 8192 && k >= 64 && nc >= 64;
+    const int old_digits = ctx->i8_digits;
+    if (i8 && !old_digits && sizeof(T) == 8) ctx->i8_digits = 7;
+    int rc = gemm_tn<T>(ctx, k, k, nc, 1.0, V1c, k, C, ldc, 0.0, W, k, 0);                                       // W = V1^T C1
+    if (rc >= 0 && rows > k)                                                                                      //   + V2^T C2
+        rc = i8 ? ozaki_gemm_tn<T>(ctx, rows - k, k, nc, 1.0, V2, ldv, C + k, ldc, 1.0, W, k)
+                : gemm_tn<T>(ctx, rows - k, k, nc, 1.0, V2, ldv, C + k, ldc, 1.0, W, k, 0);
+    if (rc >= 0) rc = gemm_tn<T>(ctx, k, k, nc, 1.0, Tm, ldt, W, k, 0.0, W2, k, 0);                               // W2 = T^T W
+    if (rc >= 0) rc = gemm_nn<T>(ctx, k, nc, k, -1.0, V1c, k, W2, k, 1.0, C, ldc);                                // C1 -= V1 W2
+    if (rc >= 0 && rows > k)                                                                                      // C2 -= V2 W2
+        rc = i8 ? ozaki_gemm_nn<T>(ctx, rows - k, nc, k, -1.0, V2, ldv, W2, k, 1.0, C + k, ldc)
+                : gemm_nn<T>(ctx, rows - k, nc, k, -1.0, V2, ldv, W2, k, 1.0, C + k, ldc);
+    ctx->i8_digits = old_digits;
+    return rc < 0 ? rc : 0;
 }
 
 template <typename T>

@@ -492,7 +492,9 @@ static int rsvd_single_block_fused(Ctx* ctx, int64_t m, int64_t n, T* A, int64_t
     RLB_CHECK(svd_tall<T>(ctx, n, k, V, n, S, W, ws, nullptr));
     RLB_CHECK(trtri_upper<T>(ctx, (int)k, R, (int)k, Rinv));
     RLB_CHECK(gemm_nn<T>(ctx, k, k, k, 1.0, Rinv, k, W, k, 0.0, M, k));
-    RLB_CHECK(gemm_nn_inplace<T>(ctx, m, k, k, 1.0, U, m, M, k));
+    // U = Y (R^-1 W) in place (rl_rsvd.hh:148 with Q = Y R^-1 never formed); on the int8-slice engine when it is selected
+    if (ctx->fp64_engine == RLB200_FP64_I8SLICES && m >= 8192 && k >= 64) RLB_CHECK(ozaki_gemm_nn<T>(ctx, m, k, k, 1.0, U, m, M, k, 0.0, U, m));
+    else RLB_CHECK(gemm_nn_inplace<T>(ctx, m, k, k, 1.0, U, m, M, k));
     return 0;
 }
 
