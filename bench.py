@@ -21,8 +21,10 @@ sys.path.insert(0, ROOT)
 
 # dram__bytes_read.sum + dram__bytes_write.sum of ozaki_mma_kernel per row of A (n = 1024, k = 256, 6 digits), from the ncu --set full
 # capture named below; None until a capture is committed
-OZ_TRAFFIC_PER_ROW_BYTES = 0.0
-OZ_TRAFFIC_SOURCE = "not captured yet"
+OZ_TRAFFIC_NN_PER_ROW = (263.686656e6 + 71.827968e6) / 42624.0     # profiles/ncu_oz_nn_r1.txt: one launch = 42624 rows of A
+OZ_TRAFFIC_TN_PER_ROW = (1.176578e9 + 14.035200e6) / 147456.0      # profiles/ncu_oz_tn_r1.txt: one launch = 9 x 16384 rows of A
+OZ_TRAFFIC_SOURCE = ("ncu --set full captures of ozaki_mma_kernel (profiles/ncu_oz_nn_r1.txt, ncu_oz_tn_r1.txt), DRAM bytes per row of A "
+                     "x rows x passes; algorithmic bytes per row and pass: 6 B x n digits + 8 B x k (NN: 8192) / 6 B x (n + k) (TN: 7680)")
 METRIC = "rsvd_gflops"
 UNIT = "Gflop/s"
 
@@ -486,7 +488,8 @@ def main():
                     "unit": "TFLOP/s", "frac": achieved / peak, "op": "int8 multiply-add = 2 ops",
                     "fp64_equivalent_tflops": (p + 2) * 2.0 * m_local * n * k / (mma_ms * 1e-3) / 1e12 if mma_ms > 0 else None,
                     "digits": S_dig, "digit_pairs": pairs,
-                    "traffic": OZ_TRAFFIC_PER_ROW_BYTES * m_local if (OZ_TRAFFIC_PER_ROW_BYTES and k == 256 and n == 1024 and S_dig == 6) else None,
+                    "traffic": (m_local * (OZ_TRAFFIC_NN_PER_ROW * (p // 2 + 1) + OZ_TRAFFIC_TN_PER_ROW * (p - p // 2 + 1))
+                                if (k == 256 and n == 1024 and S_dig == 6) else None),
                     "traffic_source": OZ_TRAFFIC_SOURCE, "peak_source": peak_src,
                     "class_ms_per_step": class_ms, "class_launches_per_step": class_launches,
                     "fp64_pipe_peak_tflops": fp64_peak, "fp64_pipe_peak_source": fp64_src,

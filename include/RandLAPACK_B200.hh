@@ -55,6 +55,9 @@ public:
     Context(const Context&) = delete;
     Context& operator=(const Context&) = delete;
     rlb200_ctx* get() const { return h_; }
+    // engine of the tall products: RLB200_FP64_I8SLICES (tcgen05 int8 digit slices, default) or RLB200_FP64_DMMA (fp64 pipe);
+    // digits: 0 = default (6 for fp64 storage, 7 inside the QR drivers, 4 for fp32), else 3..7
+    void set_engine(int engine, int digits = 0) { check(rlb200_set_fp64_engine(h_, engine)); check(rlb200_set_i8_digits(h_, digits)); }
     int check(int rc) const {
         if (rc < 0) throw Error(rc, rlb200_last_error(h_));
         return rc;

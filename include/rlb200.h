@@ -176,7 +176,8 @@ RLB200_API int rlb200_gemm_f64_i8_dev(rlb200_ctx* ctx, int transa, int transb, i
                            const double* A_dev, int64_t lda, const double* B_dev, int64_t ldb, double beta, double* C_dev, int64_t ldc);
 RLB200_API int rlb200_gemm_f32_i8_dev(rlb200_ctx* ctx, int transa, int transb, int64_t m, int64_t n, int64_t k, float alpha,
                            const float* A_dev, int64_t lda, const float* B_dev, int64_t ldb, float beta, float* C_dev, int64_t ldc);
-/* Engine used by the drivers (RS/RF/QB/RSVD) for their tall products: RLB200_FP64_DMMA (default) or RLB200_FP64_I8SLICES. */
+/* Engine used by the drivers (RS/RF/QB/RSVD, CQRRPT, BQRRP) for their tall products (m >= 16384 rows; shorter ones always use the
+ * fp64 pipe): RLB200_FP64_I8SLICES (default) or RLB200_FP64_DMMA. */
 enum { RLB200_FP64_DMMA = 0, RLB200_FP64_I8SLICES = 1 };
 RLB200_API int rlb200_set_fp64_engine(rlb200_ctx* ctx, int engine);
 /* Digits per value of the int8-slice engine: 0 = default (6 for fp64 storage: 46 bits; 4 for fp32: 30 bits), else 3..7. */

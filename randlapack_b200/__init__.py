@@ -141,7 +141,7 @@ class Context:
         return ms.value, n.value
 
     def set_fp64_engine(self, engine):
-        """Tall fp64 products of the drivers: "dmma" (default) or "i8" (tcgen05 int8 digit slices)."""
+        """Tall products of the drivers: "i8" (tcgen05 int8 digit slices, default) or "dmma" (fp64 tensor pipe)."""
         self.check(self._lib.rlb200_set_fp64_engine(self._h, {"dmma": 0, "i8": 1}[engine]))
 
     def set_i8_digits(self, digits):

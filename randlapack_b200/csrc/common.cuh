@@ -53,8 +53,8 @@ struct Ctx {
     int64_t m_global = -1;
     rlb200_allreduce_fn allreduce = nullptr;
     void* allreduce_user = nullptr;
-    // fp64 tall-GEMM engine of the drivers: 0 = DMMA (fp64 tensor pipe), 1 = tcgen05 int8 digit slices (ozaki.cu)
-    int fp64_engine = 0;
+    // tall-GEMM engine of the drivers: 1 = tcgen05 int8 digit slices (ozaki.cu, default), 0 = DMMA (fp64 tensor pipe)
+    int fp64_engine = 1;
     // digits per value of the int8-slice engine: 0 = default (6 for fp64 storage, 4 for fp32), else 3..7
     int i8_digits = 0;
     // second stream + events of the int8-slice engine: digit slicing of chunk c+1 runs beside the tensor-core kernel of chunk c

@@ -219,16 +219,18 @@ int stab_call(Ctx* ctx, int kind, int64_t m, int64_t k, T* A, bool cond_check, b
 
 // tall products over the m x n data matrix: the fp64 engine is selectable (DMMA fp64 pipe / tcgen05 int8 digit slices, ozaki.cu);
 // Gram matrices of CholQR always stay on the fp64 pipe (their conditioning is squared).
+// the digit-slice engine pays off on tall operands only (slicing + launch overheads); shorter products stay on the fp64 pipe
+constexpr int64_t kI8MinRows = 16384;
 template <typename T>
 static int tall_nn(Ctx* ctx, int64_t m, int64_t N, int64_t K, double alpha, const T* A, int64_t lda, const T* B, int64_t ldb, double beta, T* C,
                    int64_t ldc) {
-    if (ctx->fp64_engine == RLB200_FP64_I8SLICES && m >= 1024) return ozaki_gemm_nn<T>(ctx, m, N, K, alpha, A, lda, B, ldb, beta, C, ldc);
+    if (ctx->fp64_engine == RLB200_FP64_I8SLICES && m >= kI8MinRows) return ozaki_gemm_nn<T>(ctx, m, N, K, alpha, A, lda, B, ldb, beta, C, ldc);
     return gemm_nn<T>(ctx, m, N, K, alpha, A, lda, B, ldb, beta, C, ldc);
 }
 template <typename T>
 static int tall_tn(Ctx* ctx, int64_t m, int64_t N1, int64_t N2, double alpha, const T* A, int64_t lda, const T* B, int64_t ldb, double beta, T* C,
                    int64_t ldc, double* a_sumsq_out = nullptr) {
-    if (ctx->fp64_engine == RLB200_FP64_I8SLICES && m >= 1024)
+    if (ctx->fp64_engine == RLB200_FP64_I8SLICES && m >= kI8MinRows)
         return ozaki_gemm_tn<T>(ctx, m, N1, N2, alpha, A, lda, B, ldb, beta, C, ldc, a_sumsq_out);
     return gemm_tn<T>(ctx, m, N1, N2, alpha, A, lda, B, ldb, beta, C, ldc, 0, a_sumsq_out);
 }
@@ -493,7 +495,7 @@ static int rsvd_single_block_fused(Ctx* ctx, int64_t m, int64_t n, T* A, int64_t
     RLB_CHECK(trtri_upper<T>(ctx, (int)k, R, (int)k, Rinv));
     RLB_CHECK(gemm_nn<T>(ctx, k, k, k, 1.0, Rinv, k, W, k, 0.0, M, k));
     // U = Y (R^-1 W) in place (rl_rsvd.hh:148 with Q = Y R^-1 never formed); on the int8-slice engine when it is selected
-    if (ctx->fp64_engine == RLB200_FP64_I8SLICES && m >= 8192 && k >= 64) RLB_CHECK(ozaki_gemm_nn<T>(ctx, m, k, k, 1.0, U, m, M, k, 0.0, U, m));
+    if (ctx->fp64_engine == RLB200_FP64_I8SLICES && m >= kI8MinRows && k >= 64) RLB_CHECK(ozaki_gemm_nn<T>(ctx, m, k, k, 1.0, U, m, M, k, 0.0, U, m));
     else RLB_CHECK(gemm_nn_inplace<T>(ctx, m, k, k, 1.0, U, m, M, k));
     return 0;
 }

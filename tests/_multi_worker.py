@@ -42,6 +42,7 @@ def main():
                "V_abs": (V[:, :kk].abs() - V1[:, :kk].abs()).abs().max().item() if kk else 0.0,
                "U_abs": (U[:, :kk].abs() - U1[r0:r1, :kk].abs()).abs().max().item() if kk else 0.0}
         out[f"{m}x{n}_k{k}_p{p}_{engine}"] = res
+    ctx.set_fp64_engine("i8")
     gathered = [None] * world
     dist.all_gather_object(gathered, out)
     if rank == 0:

@@ -169,7 +169,7 @@ def test_cqrrpt_i8_engine(ctx, dtype, m, n):
             alg.nnz = 2
             rc, R, J = alg.call(ctx, A, 1.5, rl.RNGState(7))
         finally:
-            ctx.set_fp64_engine("dmma")
+            ctx.set_fp64_engine("i8")
         outs.append((rc, alg.rank, J.cpu().numpy(), R, A))
     (rc0, rk0, J0, R0, Q0), (rc1, rk1, J1, R1, Q1) = outs
     assert (rc0, rk0) == (rc1, rk1) == (0, n)

@@ -208,11 +208,12 @@ def test_qb_rsvd_vs_oracle_same_operator(ctx, m, n, k, p, q, b):
     assert np.linalg.norm(U.T @ U - np.eye(kk)) <= EPS ** 0.625 and np.linalg.norm(V.T @ V - np.eye(kk)) <= EPS ** 0.625
 
 
-@pytest.mark.parametrize("digits", [6, 7])
-@pytest.mark.parametrize("m,n,k,p", [(4096, 256, 32, 0), (4096, 256, 32, 2), (20000, 300, 40, 3)])
+@pytest.mark.parametrize("digits", [6, 7, -1])
+@pytest.mark.parametrize("m,n,k,p", [(32768, 256, 32, 0), (32768, 256, 32, 2), (20000, 300, 40, 3)])
 def test_rsvd_i8_engine_vs_oracle(ctx, m, n, k, p, digits):
-    """The same parity rule with the tall products over A on the tcgen05 int8 digit-slice engine (ozaki.cu): subspace angle,
-    residual and singular values within 1e-10 / 1e-9 of the oracle's on the same operator, identical codes and RNG state."""
+    """The same parity rule on each engine of the tall products over A — the tcgen05 int8 digit-slice engine (ozaki.cu, the
+    default; 6 and 7 digits) and the fp64 DMMA pipe (digits = -1): subspace angle, residual and singular values within
+    1e-10 / 1e-9 of the oracle's on the same operator, identical codes and RNG state."""
     A, st0 = poly(m, n, n)
     Ad = dev(A)
     st_d = rl.RNGState(st0.key, st0.counter)
@@ -220,13 +221,13 @@ def test_rsvd_i8_engine_vs_oracle(ctx, m, n, k, p, digits):
     o = O.StackOpts(p, 1, k, O.STAB_CHOLQRQ, O.STAB_CHOLQRQ, O.STAB_CHOLQRQ)
     *_, rsvd_o = O.make_stack(o)
     Om_dev = _device_operator(ctx, m, n, k, p, st_d)
-    ctx.set_fp64_engine("i8")
-    ctx.set_i8_digits(digits)
+    ctx.set_fp64_engine("i8" if digits > 0 else "dmma")
+    ctx.set_i8_digits(max(digits, 0))
     try:
         s = st_d.copy()
         rc, kk, U, S, V = RSVD.call(ctx, Ad, k, 0.0, s)
     finally:
-        ctx.set_fp64_engine("dmma")
+        ctx.set_fp64_engine("i8")
         ctx.set_i8_digits(0)
     rc_o, kk_o, U_o, S_o, V_o, s_o = rsvd_o.call(A, k, 0.0, st0.copy(), omega_override=Om_dev)
     assert (rc, kk) == (rc_o, kk_o) and s.counter == s_o.counter and s.key == s_o.key
