@@ -18,6 +18,7 @@
 #include "drivers.cuh"
 #include "philox.cuh"
 #include <algorithm>
+#include <cstdlib>
 
 namespace rlb {
 
@@ -168,7 +169,8 @@ template int fill_sparse_unpacked<float>(Ctx*, int64_t, int64_t, int64_t, int, i
 // key = (sketch row - ro) << 12 | jl << 1 | neg ; invalid = 0xFFFFFFFF.  ent[q*E + i] = key & 0xFFF, off[q*(d_pad+1) + r] = #keys < r<<12.
 __global__ void __launch_bounds__(256) saso_plan_kernel(Ctr128 seed, uint32_t k0, uint32_t k1, int64_t col0, int64_t m_sub, int64_t d_full,
                                                         int64_t ro, int d_sub, int nnz, int R, int E2, int d_pad,
-                                                        uint16_t* __restrict__ ent, uint16_t* __restrict__ off) {
+                                                        uint16_t* __restrict__ ent, uint16_t* __restrict__ off,
+                                                        uint32_t* __restrict__ key_out = nullptr, int rows_per_group = 0, int ngroups = 0) {
     extern __shared__ uint32_t keys[];
     const int q = blockIdx.x;
     const int E = R * nnz;
@@ -200,6 +202,19 @@ __global__ void __launch_bounds__(256) saso_plan_kernel(Ctr128 seed, uint32_t k0
             }
             __syncthreads();
         }
+    }
+    if (key_out) {
+        // strip kernel format: the sorted 32-bit keys themselves (sketch row << 12 | source row << 1 | sign) and one offset per group of
+        // rows_per_group sketch rows (ngroups + 1 values, padded to a multiple of 8)
+        for (int i = threadIdx.x; i < E; i += blockDim.x) key_out[(int64_t)q * E + i] = keys[i];
+        for (int gq = threadIdx.x; gq <= ngroups; gq += blockDim.x) {
+            const int64_t r = (int64_t)gq * rows_per_group;
+            const uint32_t bound = (r >= d_sub) ? 0xFFFFFFFFu : ((uint32_t)r << 12);
+            int lo = 0, hi = E2;
+            while (lo < hi) { const int mid = (lo + hi) >> 1; if (keys[mid] < bound) lo = mid + 1; else hi = mid; }
+            off[(int64_t)q * (ngroups + 8) + gq] = (uint16_t)lo;
+        }
+        return;
     }
     for (int i = threadIdx.x; i < E; i += blockDim.x) ent[(int64_t)q * E + i] = (uint16_t)(keys[i] & 0xFFFu);
     for (int r = threadIdx.x; r <= d_pad; r += blockDim.x) {
@@ -328,6 +343,194 @@ static int saso_apply_launch(Ctx* ctx, const T* A, int64_t lda, int64_t m, int n
     return 0;
 }
 
+// ---- apply, strip kernel -------------------------------------------------------------------------------------------------------------------
+// A CTA owns CPS columns of A and ALL sketch rows, with its d x CPS accumulator tile in SHARED memory.  The 16 * (32 / CPS) lane
+// groups each own a contiguous range of sketch rows; inside a group lane l owns column l % CPS.  The chunk's entries arrive sorted by
+// sketch row (32-bit keys: row << 12 | source row << 1 | sign), so every group walks ONE flat list and adds tile[column][source row]
+// into acc[row][column] - no per-row loops, no dynamic register indexing, and an accumulator is only ever touched by its owner lane in
+// list order (deterministic, no atomics).  Chunks of R rows are fetched by one producer thread with cp.async.bulk (one copy per column
+// + the chunk's keys and group offsets) into a double buffer guarded by full/empty mbarriers.  ncu on the generic kernel showed it
+// issue-bound (~62 thread instructions per element); this form executes ~10x fewer.
+__device__ __forceinline__ uint32_t ss_smem(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void ss_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done = 0;
+    while (!done) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                     : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    }
+}
+__device__ __forceinline__ void ss_bulk(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+constexpr int kStripThreads = 512;      // consumer threads (16 warps); one more warp produces
+constexpr int kStripBufs = 2;           // chunk buffers (measured: 4 buffers of half the size are not faster - the loop is bound by the
+                                        // shared-memory pipe, ~4 accesses per entry and lane group, not by load latency)
+
+template <typename T, int CPS>
+__global__ void __launch_bounds__(kStripThreads + 32, 1)
+saso_strip_kernel(const T* __restrict__ A, int64_t lda, int n, int d_sub, int d_pad, int R, int E, int nchunks, int chunks_per_split,
+                  const uint32_t* __restrict__ keys, const uint16_t* __restrict__ goff, T* __restrict__ partial) {
+    constexpr int NG = 16 * (32 / CPS);            // lane groups = row ranges
+    constexpr int OP = NG + 8;                     // group offsets per chunk (pitch of `goff`)
+    constexpr int EV = 16 / sizeof(T);
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    constexpr int NB = kStripBufs;
+    __shared__ __align__(8) uint64_t bar_full[NB], bar_empty[NB];
+    const int RP = R + EV;
+    T* acc = reinterpret_cast<T*>(smem_raw);                                                     // [d_pad][CPS]
+    T* tile = acc + (size_t)d_pad * CPS;                                                         // [NB][CPS][RP]
+    uint32_t* s_key = reinterpret_cast<uint32_t*>(tile + (size_t)NB * CPS * RP);                 // [NB][E]
+    uint16_t* s_off = reinterpret_cast<uint16_t*>(s_key + (size_t)NB * E);                       // [NB][OP]
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int c0 = blockIdx.x * CPS, split = blockIdx.y;
+    const int q0 = split * chunks_per_split, q1 = min(nchunks, q0 + chunks_per_split);
+    const int ncv = min(CPS, n - c0);                                                            // valid columns of this strip
+    if (tid == 0) {
+        for (int b = 0; b < NB; ++b) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(ss_smem(&bar_full[b])));
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(ss_smem(&bar_empty[b])), "n"(kStripThreads / 32));   // one arrive per consumer warp
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (int i = tid; i < d_pad * CPS; i += blockDim.x) acc[i] = (T)0;
+    __syncthreads();
+
+    if (warp == kStripThreads / 32) {
+        // ---- producer
+        if (lane == 0) {
+            const uint32_t bytes = (uint32_t)ncv * R * sizeof(T) + (uint32_t)E * 4u + (uint32_t)OP * 2u;
+            for (int q = q0; q < q1; ++q) {
+                const int i = q - q0, b = i % NB;
+                if (i >= NB) ss_wait(ss_smem(&bar_empty[b]), (uint32_t)(((i / NB) - 1) & 1));
+                const uint32_t bar = ss_smem(&bar_full[b]);
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+                for (int c = 0; c < ncv; ++c)
+                    ss_bulk(ss_smem(tile + ((size_t)b * CPS + c) * RP), A + (int64_t)q * R + (int64_t)(c0 + c) * lda, (uint32_t)(R * sizeof(T)), bar);
+                ss_bulk(ss_smem(s_key + (size_t)b * E), keys + (int64_t)q * E, (uint32_t)E * 4u, bar);
+                ss_bulk(ss_smem(s_off + (size_t)b * OP), goff + (int64_t)q * OP, (uint32_t)OP * 2u, bar);
+            }
+        }
+    } else {
+        // ---- consumers
+        const int col = lane % CPS, grp = warp * (32 / CPS) + lane / CPS;
+        for (int q = q0; q < q1; ++q) {
+            const int i = q - q0, b = i % NB;
+            ss_wait(ss_smem(&bar_full[b]), (uint32_t)((i / NB) & 1));
+            const T* t = tile + ((size_t)b * CPS + col) * RP;
+            const uint32_t* kp = s_key + (size_t)b * E;
+            const int e1 = s_off[(size_t)b * OP + grp + 1];
+            int e = s_off[(size_t)b * OP + grp];
+            // four entries per step: their key / tile / accumulator loads are independent and in flight together; equal sketch rows are
+            // adjacent in the sorted list, so a repeated accumulator address only needs the previous entry's updated value
+            for (; e + 4 <= e1; e += 4) {
+                uint32_t k[4]; T v[4]; T* a[4]; T x[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) k[u] = kp[e + u];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) { v[u] = t[(k[u] >> 1) & 0x7FFu]; a[u] = acc + (size_t)(k[u] >> 12) * CPS + col; }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) x[u] = *a[u];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    if (u > 0 && a[u] == a[u - 1]) x[u] = x[u - 1];
+                    x[u] += (k[u] & 1u) ? -v[u] : v[u];
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) *a[u] = x[u];
+            }
+            for (; e < e1; ++e) {
+                const uint32_t k = kp[e];
+                const T v = t[(k >> 1) & 0x7FFu];
+                T* a = acc + (size_t)(k >> 12) * CPS + col;
+                *a += (k & 1u) ? -v : v;
+            }
+            // release the buffer: one arrive per warp (no CTA-wide barrier, warps may run a few chunks apart)
+            __syncwarp();
+            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(ss_smem(&bar_empty[b])) : "memory");
+        }
+    }
+    __syncthreads();
+    T* P = partial + (int64_t)split * d_sub * n;
+    for (int i = tid; i < d_sub * ncv; i += blockDim.x) {
+        const int c = i / d_sub, r = i - c * d_sub;
+        P[r + (int64_t)(c0 + c) * d_sub] = acc[(size_t)r * CPS + c];
+    }
+}
+
+// generic path (any alignment, any m): thread-owned sketch rows, saso_apply_kernel
+template <typename T>
+static int saso_apply_generic(Ctx* ctx, Ctr128 seed, const uint32_t* state, int64_t col0, int64_t m, int64_t S_rows, int64_t ro, int64_t d, int64_t vec_nnz,
+                              int64_t n, const T* A, int64_t lda, T alpha, T beta, T* B, int64_t ldb) {
+            int R = 2048;
+            while (R > 256 && (int64_t)R * vec_nnz > 16384) R >>= 1;
+            const int E = R * (int)vec_nnz;
+            int E2 = 1; while (E2 < E) E2 <<= 1;
+            const int nchunks = (int)((m + R - 1) / R);
+            const int rpt = d <= 512 ? 1 : d <= 1024 ? 2 : d <= 4096 ? 8 : 32;
+            const int d_pad = kSasoThreads * rpt;
+            ArenaScope as(ctx);
+            uint16_t* ent = as.take<uint16_t>((size_t)nchunks * E); if (!ent) return RLB200_ERR_ALLOC;
+            uint16_t* off = as.take<uint16_t>((size_t)nchunks * (d_pad + 8)); if (!off) return RLB200_ERR_ALLOC;
+            {
+                RLB_CUDA_OK(ctx, cudaFuncSetAttribute(saso_plan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, E2 * 4));
+                LaunchScope ls(ctx, RLB200_TIMER_SKETCH);
+                saso_plan_kernel<<<nchunks, 256, E2 * 4, ctx->stream>>>(seed, state[4], state[5], col0, m, S_rows, ro, (int)d, (int)vec_nnz, R,
+                                                                        E2, d_pad, ent, off);
+                RLB_CUDA_OK(ctx, cudaGetLastError());
+            }
+            int rc;
+            if (sizeof(T) == 4) {
+                if (rpt == 1)      rc = saso_apply_launch<T, 1, 8>(ctx, A, lda, m, (int)n, (int)d, R, E, nchunks, ent, off, alpha, beta, B, ldb);
+                else if (rpt == 2) rc = saso_apply_launch<T, 2, 8>(ctx, A, lda, m, (int)n, (int)d, R, E, nchunks, ent, off, alpha, beta, B, ldb);
+                else if (rpt == 8) rc = saso_apply_launch<T, 8, 8>(ctx, A, lda, m, (int)n, (int)d, R, E, nchunks, ent, off, alpha, beta, B, ldb);
+                else               rc = saso_apply_launch<T, 32, 2>(ctx, A, lda, m, (int)n, (int)d, R, E, nchunks, ent, off, alpha, beta, B, ldb);
+            } else {
+                if (rpt == 1)      rc = saso_apply_launch<T, 1, 4>(ctx, A, lda, m, (int)n, (int)d, R, E, nchunks, ent, off, alpha, beta, B, ldb);
+                else if (rpt == 2) rc = saso_apply_launch<T, 2, 4>(ctx, A, lda, m, (int)n, (int)d, R, E, nchunks, ent, off, alpha, beta, B, ldb);
+                else if (rpt == 8) rc = saso_apply_launch<T, 8, 4>(ctx, A, lda, m, (int)n, (int)d, R, E, nchunks, ent, off, alpha, beta, B, ldb);
+                else               rc = saso_apply_launch<T, 32, 1>(ctx, A, lda, m, (int)n, (int)d, R, E, nchunks, ent, off, alpha, beta, B, ldb);
+            }
+            return rc;
+}
+
+// strip path: whole chunks of R rows of a 16-byte aligned A (saso_strip_kernel)
+template <typename T, int CPS>
+static int saso_apply_strips(Ctx* ctx, Ctr128 seed, const uint32_t* state, int64_t col0, int64_t m_full, int R, int64_t S_rows, int64_t ro, int64_t d,
+                             int64_t vec_nnz, int64_t n, const T* A, int64_t lda, T alpha, T beta, T* B, int64_t ldb) {
+    constexpr int NG = 16 * (32 / CPS);
+    constexpr int EV = 16 / sizeof(T);
+    const int nchunks = (int)(m_full / R);
+    const int E = R * (int)vec_nnz;
+    int E2 = 1; while (E2 < E) E2 <<= 1;
+    const int rpg = (int)((d + NG - 1) / NG);          // sketch rows per lane group
+    const int d_pad = rpg * NG, OP = NG + 8;
+    ArenaScope as(ctx);
+    uint32_t* keys = as.take<uint32_t>((size_t)nchunks * E); if (!keys) return RLB200_ERR_ALLOC;
+    uint16_t* goff = as.take<uint16_t>((size_t)nchunks * OP); if (!goff) return RLB200_ERR_ALLOC;
+    {
+        RLB_CUDA_OK(ctx, cudaFuncSetAttribute(saso_plan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, E2 * 4));
+        LaunchScope ls(ctx, RLB200_TIMER_SKETCH);
+        saso_plan_kernel<<<nchunks, 256, E2 * 4, ctx->stream>>>(seed, state[4], state[5], col0, m_full, S_rows, ro, (int)d, (int)vec_nnz, R, E2, d_pad, nullptr,
+                                                                goff, keys, rpg, NG);
+        RLB_CUDA_OK(ctx, cudaGetLastError());
+    }
+    const int strips = (int)((n + CPS - 1) / CPS);
+    int splits = (int)std::max<int64_t>(1, std::min<int64_t>(nchunks, (4ll * ctx->num_sms + strips - 1) / strips));
+    const int cps = (nchunks + splits - 1) / splits;
+    splits = (nchunks + cps - 1) / cps;
+    T* partial = as.take<T>((size_t)splits * d * n); if (!partial) return RLB200_ERR_ALLOC;
+    const size_t smem = (size_t)d_pad * CPS * sizeof(T) + (size_t)kStripBufs * (CPS * (R + EV) * sizeof(T) + E * 4 + OP * 2);
+    auto kern = saso_strip_kernel<T, CPS>;
+    RLB_CUDA_OK(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    LaunchScope ls(ctx, RLB200_TIMER_SKETCH, 2);
+    kern<<<dim3(strips, splits), kStripThreads + 32, smem, ctx->stream>>>(A, lda, (int)n, (int)d, d_pad, R, E, nchunks, cps, keys, goff, partial);
+    const int64_t total = d * n;
+    saso_reduce_kernel<T><<<(unsigned)std::min<int64_t>((total + 255) / 256, (int64_t)ctx->num_sms * 8), 256, 0, ctx->stream>>>(partial, splits, (int)d, (int)n, alpha, beta, B, ldb);
+    RLB_CUDA_OK(ctx, cudaGetLastError());
+    return 0;
+}
+
 // B(d x n) = alpha * S[ro:ro+d, co:co+m] * A(m x n) + beta * B ; S ~ SparseDist(S_rows, S_cols, vec_nnz, Axis::Short) sampled at `state`.
 // With a row shard set on the context, A holds rows [row_offset, row_offset + m) of the global matrix: the matching columns of S
 // are used and B is sum-allreduced (beta is applied by the shard that owns row 0).  state <- S.next_state.
@@ -354,35 +557,36 @@ int sketch_sparse_left(Ctx* ctx, int64_t S_rows, int64_t S_cols, int64_t vec_nnz
             saso_reduce_kernel<T><<<(unsigned)std::min<int64_t>((d * n + 255) / 256, 1184), 256, 0, ctx->stream>>>(B, 0, (int)d, (int)n, (T)0, bz, B, ldb);
             RLB_CUDA_OK(ctx, cudaGetLastError());
         } else {
-            int R = 2048;
-            while (R > 256 && (int64_t)R * vec_nnz > 16384) R >>= 1;
-            const int E = R * (int)vec_nnz;
-            int E2 = 1; while (E2 < E) E2 <<= 1;
-            const int nchunks = (int)((m + R - 1) / R);
-            const int rpt = d <= 512 ? 1 : d <= 1024 ? 2 : d <= 4096 ? 8 : 32;
-            const int d_pad = kSasoThreads * rpt;
-            ArenaScope as(ctx);
-            uint16_t* ent = as.take<uint16_t>((size_t)nchunks * E); if (!ent) return RLB200_ERR_ALLOC;
-            uint16_t* off = as.take<uint16_t>((size_t)nchunks * (d_pad + 8)); if (!off) return RLB200_ERR_ALLOC;
-            {
-                RLB_CUDA_OK(ctx, cudaFuncSetAttribute(saso_plan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, E2 * 4));
-                LaunchScope ls(ctx, RLB200_TIMER_SKETCH);
-                saso_plan_kernel<<<nchunks, 256, E2 * 4, ctx->stream>>>(seed, state[4], state[5], co + shard_off, m, S_rows, ro, (int)d, (int)vec_nnz, R,
-                                                                        E2, d_pad, ent, off);
-                RLB_CUDA_OK(ctx, cudaGetLastError());
-            }
             const T beta_eff = (sharded && shard_off != 0) ? (T)0 : beta;
-            int rc;
-            if (sizeof(T) == 4) {
-                if (rpt == 1)      rc = saso_apply_launch<T, 1, 8>(ctx, A, lda, m, (int)n, (int)d, R, E, nchunks, ent, off, alpha, beta_eff, B, ldb);
-                else if (rpt == 2) rc = saso_apply_launch<T, 2, 8>(ctx, A, lda, m, (int)n, (int)d, R, E, nchunks, ent, off, alpha, beta_eff, B, ldb);
-                else if (rpt == 8) rc = saso_apply_launch<T, 8, 8>(ctx, A, lda, m, (int)n, (int)d, R, E, nchunks, ent, off, alpha, beta_eff, B, ldb);
-                else               rc = saso_apply_launch<T, 32, 2>(ctx, A, lda, m, (int)n, (int)d, R, E, nchunks, ent, off, alpha, beta_eff, B, ldb);
+            const int64_t col0 = co + shard_off;
+            // whole chunks of a 16-byte aligned A go through the strip kernel (lanes = columns, cluster multicast of the strip);
+            // the ragged tail (and unaligned / very wide-sketch cases) through the generic kernel.  The tail is applied first
+            // (alpha, beta), the strips then accumulate with beta = 1: a fixed order.
+            constexpr int EV = 16 / sizeof(T);
+            // shared-memory budget of the strip kernel (<= 220 KB): accumulators d_pad x CPS, kStripBufs tile buffers CPS x (R + EV), keys E x 4 B each
+            const int64_t acc_cap = (128 * 1024) / ((d + 127) / 128 * 128 * (int64_t)sizeof(T));       // columns per strip the accumulators allow
+            const int cps_sel = acc_cap >= 8 ? 8 : acc_cap >= 4 ? 4 : acc_cap >= 2 ? 2 : 0;
+            int Rs = 1024;
+            while (Rs > 64 && ((int64_t)Rs * vec_nnz > 3072 || (int64_t)kStripBufs * cps_sel * (Rs + EV) * (int64_t)sizeof(T) > 68 * 1024)) Rs >>= 1;
+            // measured (profiles/sec_sketch_sparse_*): the strip kernel wins for vec_nnz <= 2 (count-sketch and the CQRRPT default), the generic
+            // one for denser columns; RLB200_SASO_STRIPS=1 / RLB200_SASO_GENERIC=1 force either for experiments
+            const bool strips_ok = cps_sel > 0 && (reinterpret_cast<uintptr_t>(A) % 16 == 0) && (lda % EV == 0) && (int64_t)Rs * vec_nnz <= 3072 &&
+                                   m >= 4 * (int64_t)Rs && getenv("RLB200_SASO_GENERIC") == nullptr && (vec_nnz <= 2 || getenv("RLB200_SASO_STRIPS") != nullptr);
+            int rc = 0;
+            if (strips_ok) {
+                const int64_t m_full = (m / Rs) * Rs, tail = m - m_full;
+                T beta_s = beta_eff;
+                if (tail > 0) {
+                    rc = saso_apply_generic<T>(ctx, seed, state, col0 + m_full, tail, S_rows, ro, d, vec_nnz, n, A + m_full, lda, alpha, beta_eff, B, ldb);
+                    beta_s = (T)1;
+                }
+                if (rc >= 0) {
+                    if (cps_sel == 8)      rc = saso_apply_strips<T, 8>(ctx, seed, state, col0, m_full, Rs, S_rows, ro, d, vec_nnz, n, A, lda, alpha, beta_s, B, ldb);
+                    else if (cps_sel == 4) rc = saso_apply_strips<T, 4>(ctx, seed, state, col0, m_full, Rs, S_rows, ro, d, vec_nnz, n, A, lda, alpha, beta_s, B, ldb);
+                    else                   rc = saso_apply_strips<T, 2>(ctx, seed, state, col0, m_full, Rs, S_rows, ro, d, vec_nnz, n, A, lda, alpha, beta_s, B, ldb);
+                }
             } else {
-                if (rpt == 1)      rc = saso_apply_launch<T, 1, 4>(ctx, A, lda, m, (int)n, (int)d, R, E, nchunks, ent, off, alpha, beta_eff, B, ldb);
-                else if (rpt == 2) rc = saso_apply_launch<T, 2, 4>(ctx, A, lda, m, (int)n, (int)d, R, E, nchunks, ent, off, alpha, beta_eff, B, ldb);
-                else if (rpt == 8) rc = saso_apply_launch<T, 8, 4>(ctx, A, lda, m, (int)n, (int)d, R, E, nchunks, ent, off, alpha, beta_eff, B, ldb);
-                else               rc = saso_apply_launch<T, 32, 1>(ctx, A, lda, m, (int)n, (int)d, R, E, nchunks, ent, off, alpha, beta_eff, B, ldb);
+                rc = saso_apply_generic<T>(ctx, seed, state, col0, m, S_rows, ro, d, vec_nnz, n, A, lda, alpha, beta_eff, B, ldb);
             }
             RLB_CHECK(rc);
         }

@@ -82,7 +82,9 @@ def test_sparse_apply_golden(ctx, i):
 # (d, m, n, nnz): covers every rows-per-thread variant of the kernel (d <= 512, 1024, 4096, 16384), ragged m (not a multiple of
 # the 2048-row chunk), n not a multiple of the column tile, single-row / single-column inputs
 APPLY = [(1, 1, 1, 1), (16, 16, 3, 16), (16, 333, 5, 3), (600, 5000, 17, 2), (2000, 9000, 9, 1), (4096, 20000, 24, 1), (5000, 12000, 6, 4),
-         (64, 70000, 33, 8), (300, 4097, 8, 16)]
+         (64, 70000, 33, 8), (300, 4097, 8, 16),
+         # strip kernel (16-byte aligned A, whole 512/256-row chunks + ragged tail): 1 / 2 / 4 / 8 row blocks per cluster, partial strips
+         (4096, 65536, 70, 4), (1024, 33000, 40, 1), (3000, 16384, 32, 2), (8192, 40960, 31, 1)]
 
 
 @pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
