@@ -386,7 +386,8 @@ def main():
     ctx = rl.Context(dev.index)
     ctx.set_fp64_engine(args.engine)
     ctx.set_i8_digits(args.digits)
-    config["fp64_engine"] = ("tcgen05 kind::i8 digit slices, %d digits" % (args.digits or 6)) if args.engine == "i8" else "DMMA fp64 pipe"
+    config["fp64_engine"] = ("tcgen05 kind::i8 digit slices, %d digits (A^T*Y with the fused Gram matrix: %d)" % (args.digits or 6, args.digits or 7)) \
+        if args.engine == "i8" else "DMMA fp64 pipe"
 
     def barrier():
         if dist is not None:
@@ -472,10 +473,16 @@ def main():
     if args.engine == "i8":
         # dominant kernel: ozaki_mma_kernel (tcgen05.mma.kind::i8).  Algorithmic work per launch class: the (p + 2) tall products,
         # 2*m*n*k flops each, executed as S(S+1)/2 int8 digit-pair GEMMs of the same shape.
+        # A*Omega passes and U = Y*M: 6 digits (21 pairs); A^T*Y passes carry the fused Gram matrix Y^T*Y and run with 7 digits (28 pairs).
         S_dig = args.digits or 6
-        pairs = S_dig * (S_dig + 1) // 2
+        S_tn = args.digits or 7
+        pairs, pairs_tn = S_dig * (S_dig + 1) // 2, S_tn * (S_tn + 1) // 2
+        nn_passes, tn_passes = p // 2 + 1, p - p // 2 + 1
+        gram_rows, gram_cols = -(-k // 128), -(-k // 64)
+        gram_frac = sum(1 for y in range(gram_rows) for x in range(gram_cols) if y * 128 <= x * 64 + 63) / float(gram_rows * gram_cols)
         mma_ms = tms["i8_mma_nn"][0] + tms["i8_mma_tn"][0]
-        i8_ops = (p + 2) * 2.0 * m_local * n * k * pairs
+        i8_ops = (nn_passes * 2.0 * m_local * n * k + 2.0 * m_local * k * k) * pairs \
+            + tn_passes * (2.0 * m_local * n * k + 2.0 * m_local * k * k * gram_frac) * pairs_tn
         achieved = i8_ops / (mma_ms * 1e-3) / 1e12 if mma_ms > 0 else 0.0
         if "bf16_tflops_sustained" in peaks:
             peak = 2.0 * peaks["bf16_tflops_sustained"]
@@ -486,9 +493,10 @@ def main():
             peak_src = "fallback: 2 x 1361.4 TFLOP/s sustained bf16 (B200_PROFILING.md); int8 tensor rate is twice the bf16 rate"
         roofline = {"bound": "tensor", "kernel": "ozaki_mma_kernel (tcgen05.mma.kind::i8, NN + TN launches)", "achieved": achieved, "peak": peak,
                     "unit": "TFLOP/s", "frac": achieved / peak, "op": "int8 multiply-add = 2 ops",
-                    "fp64_equivalent_tflops": (p + 2) * 2.0 * m_local * n * k / (mma_ms * 1e-3) / 1e12 if mma_ms > 0 else None,
-                    "digits": S_dig, "digit_pairs": pairs,
-                    "traffic": (m_local * (OZ_TRAFFIC_NN_PER_ROW * (p // 2 + 1) + OZ_TRAFFIC_TN_PER_ROW * (p - p // 2 + 1))
+                    "fp64_equivalent_tflops": ((p + 2) * 2.0 * m_local * n * k + 2.0 * m_local * k * k * (1 + tn_passes * gram_frac))
+                    / (mma_ms * 1e-3) / 1e12 if mma_ms > 0 else None,
+                    "digits": {"a_omega_and_u": S_dig, "at_y_with_fused_gram": S_tn}, "digit_pairs": {"a_omega_and_u": pairs, "at_y_with_fused_gram": pairs_tn},
+                    "traffic": (m_local * (OZ_TRAFFIC_NN_PER_ROW * (p // 2 + 1) + OZ_TRAFFIC_TN_PER_ROW * (7.0 / 6.0) * (p - p // 2 + 1))
                                 if (k == 256 and n == 1024 and S_dig == 6) else None),
                     "traffic_source": OZ_TRAFFIC_SOURCE, "peak_source": peak_src,
                     "class_ms_per_step": class_ms, "class_launches_per_step": class_launches,

@@ -173,9 +173,16 @@ static int hqrq(Ctx* ctx, int64_t m, int64_t k, T* A) {
 // product algebraically:  A^T (Y R^-1) = (A^T Y) R^-1  and  (Y R^-1) W = Y (R^-1 W)  — the m x k solve (m k^2 flops, a full
 // read+write of the tall iterate) becomes an n x k or k x k one.
 template <typename T>
+static int cholqr_finish(Ctx* ctx, int64_t k, bool cond_check, bool rows_sharded, T* G, int* chol_fail);
+template <typename T>
 static int cholqr_factor(Ctx* ctx, int64_t m, int64_t k, const T* A, bool cond_check, bool rows_sharded, T* G, int* chol_fail) {
     RLB_CUDA_OK(ctx, cudaMemsetAsync(G, 0, sizeof(T) * k * k, ctx->stream));
     RLB_CHECK(gemm_tn<T>(ctx, m, k, k, 1.0, A, m, A, m, 0.0, G, k, /*upper_only=*/1));
+    return cholqr_finish<T>(ctx, k, cond_check, rows_sharded, G, chol_fail);
+}
+// G (upper triangle of the local Gram matrix) -> R = chol(G) in place, with the reference's failure / condition rules (rl_orth.hh:81-93)
+template <typename T>
+static int cholqr_finish(Ctx* ctx, int64_t k, bool cond_check, bool rows_sharded, T* G, int* chol_fail) {
     if (rows_sharded) RLB_CHECK(allreduce_sum<T>(ctx, G, k * k));
     int info = 0;
     RLB_CHECK(potrf_blocked<T>(ctx, k, G, k, &info));
@@ -233,6 +240,24 @@ static int tall_tn(Ctx* ctx, int64_t m, int64_t N1, int64_t N2, double alpha, co
     if (ctx->fp64_engine == RLB200_FP64_I8SLICES && m >= kI8MinRows)
         return ozaki_gemm_tn<T>(ctx, m, N1, N2, alpha, A, lda, B, ldb, beta, C, ldc, a_sumsq_out);
     return gemm_tn<T>(ctx, m, N1, N2, alpha, A, lda, B, ldb, beta, C, ldc, 0, a_sumsq_out);
+}
+
+// Z = A^T Y and G = Y^T Y (upper triangle) in ONE sweep: on the int8-slice engine the Gram tiles ride in the launches of the A^T Y
+// product, fed from the same digits of Y (the A^T Y pass is bound by slicing, so they are nearly free).  The fused pass runs with 7
+// digits for fp64 (54 bits: the Gram matrix squares the conditioning and potrf must fail exactly where the reference's does).
+template <typename T>
+static int tall_tn_gram(Ctx* ctx, int64_t m, int64_t n, int64_t k, const T* A, int64_t lda, const T* Y, int64_t ldy, T* Z, int64_t ldz, T* G,
+                        double* a_sumsq_out = nullptr) {
+    if (ctx->fp64_engine == RLB200_FP64_I8SLICES && m >= kI8MinRows && k >= 64 && getenv("RLB200_NO_GRAM_FUSION") == nullptr) {
+        const int old = ctx->i8_digits;
+        if (!old && sizeof(T) == 8) ctx->i8_digits = 7;
+        const int rc = ozaki_gemm_tn<T>(ctx, m, n, k, 1.0, A, lda, Y, ldy, 0.0, Z, ldz, a_sumsq_out, false, G, k);
+        ctx->i8_digits = old;
+        return rc;
+    }
+    RLB_CUDA_OK(ctx, cudaMemsetAsync(G, 0, sizeof(T) * k * k, ctx->stream));
+    RLB_CHECK(gemm_tn<T>(ctx, m, k, k, 1.0, Y, ldy, Y, ldy, 0.0, G, k, /*upper_only=*/1));
+    return tall_tn<T>(ctx, m, n, k, 1.0, A, lda, Y, ldy, 0.0, Z, ldz, a_sumsq_out);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -297,8 +322,10 @@ int rs_call(Ctx* ctx, int64_t m, int64_t n, const T* A, int64_t k, T* Omega, T* 
         if (p_done % q == 0) {
             if (o.stab == RLB200_STAB_CHOLQRQ && fuse_ok(o)) {
                 // stabilise Omega_1 = Q R implicitly: Omega = A^T Q = (A^T Omega_1) R^-1; Omega_1 itself is scratch (:130) and is never read again
+                // (the Gram matrix and A^T Omega_1 come out of one sweep; the Cholesky factor, and its failure code, follow)
                 Rfold = as_fold.take<T>(k * k); RLB_ALLOC(ctx, Rfold);
-                int rc = cholqr_factor<T>(ctx, m, k, Omega_1, o.cond_check, sharded, Rfold, nullptr);
+                RLB_CHECK(tall_tn_gram<T>(ctx, m, n, k, A, m, Omega_1, m, Omega, n, Rfold));
+                int rc = cholqr_finish<T>(ctx, k, o.cond_check, sharded, Rfold, nullptr);
                 if (rc) return rc < 0 ? rc : 1;
             } else {
                 int rc = stab_call<T>(ctx, o.stab, m, k, Omega_1, o.cond_check, sharded, nullptr);
@@ -306,7 +333,7 @@ int rs_call(Ctx* ctx, int64_t m, int64_t n, const T* A, int64_t k, T* Omega, T* 
             }
         }
         // Omega = A^T Omega_1 (:165)
-        RLB_CHECK(tall_tn<T>(ctx, m, n, k, 1.0, A, m, Omega_1, m, 0.0, Omega, n));
+        if (!Rfold) RLB_CHECK(tall_tn<T>(ctx, m, n, k, 1.0, A, m, Omega_1, m, 0.0, Omega, n));
         if (sharded) RLB_CHECK(allreduce_sum<T>(ctx, Omega, n * k));
         if (Rfold) RLB_CHECK(trsm_right_upper<T>(ctx, n, k, Rfold, k, Omega, n));
         ++p_done;
@@ -474,12 +501,13 @@ static int rsvd_single_block_fused(Ctx* ctx, int64_t m, int64_t n, T* A, int64_t
     if (rc < 0) return rc;
     if (!rc) {
         RLB_CHECK(tall_nn<T>(ctx, m, k, n, 1.0, A, m, Omega, n, 0.0, U, m));           // Y = A Omega
-        rc = cholqr_factor<T>(ctx, m, k, U, o.cond_check, sharded, R, nullptr);        // Y = Q R (Q implicit)
+        // Y = Q R (Q implicit) and B^T = A^T Q = (A^T Y) R^-1 (rl_qb.hh:218): the Gram matrix of Y, A^T Y and ||A||_F (:168) come out of
+        // one sweep of A and Y; the Cholesky factor, and the failure code of RF's orthogonaliser (rl_rf.hh:129), follow
+        RLB_CHECK(tall_tn_gram<T>(ctx, m, n, k, A, m, U, m, V, n, R, nA_dev));
+        rc = cholqr_finish<T>(ctx, k, o.cond_check, sharded, R, nullptr);
         if (rc < 0) return rc;
     }
     if (rc) { *k_io = 0; if (qb_code) *qb_code = 6; return 0; }                        // rl_qb.hh:191-197 -> rl_rsvd.hh:137
-    // B^T = A^T Q = (A^T Y) R^-1 (rl_qb.hh:218), ||A||_F fused into the same sweep of A (:168)
-    RLB_CHECK(tall_tn<T>(ctx, m, n, k, 1.0, A, m, U, m, 0.0, V, n, nA_dev));
     if (sharded) { RLB_CHECK(allreduce_sum<T>(ctx, V, n * k)); RLB_CHECK(allreduce_sum<double>(ctx, nA_dev, 1)); }
     RLB_CHECK(trsm_right_upper<T>(ctx, n, k, R, k, V, n));
     double ss = 0, nB = 0;

@@ -44,10 +44,11 @@ template <typename T>
 int ozaki_gemm_nn(Ctx* ctx, int64_t m, int64_t N, int64_t K, double alpha, const T* A, int64_t lda, const T* B, int64_t ldb, double beta,
                   T* C, int64_t ldc, bool b_upper_tri = false);
 // x_sumsq_out (device scalar, optional): ||X||_F^2, accumulated in the exponent pass over X (no extra sweep).
+// gram_out (optional, N2 x N2, ldg): Y^T Y computed in the same launches from the same digits of Y (tiles touching the upper triangle).
 // upper_only: only the tiles touching the upper triangle of C are computed (Gram matrices; the rest of C is set to alpha * 0 + beta * C).
 template <typename T>
 int ozaki_gemm_tn(Ctx* ctx, int64_t m, int64_t N1, int64_t N2, double alpha, const T* X, int64_t ldx, const T* Y, int64_t ldy, double beta,
-                  T* C, int64_t ldc, double* x_sumsq_out = nullptr, bool upper_only = false);
+                  T* C, int64_t ldc, double* x_sumsq_out = nullptr, bool upper_only = false, T* gram_out = nullptr, int64_t ldg = 0);
 void oz_cache_destroy(Ctx* ctx);
 // While alive, the first operand `A` of the tall products is known not to change: its row / column-chunk exponents are computed once
 // and reused by every pass (outermost scope wins; nested scopes on the same or another pointer are no-ops).

@@ -321,6 +321,12 @@ __device__ __forceinline__ void oz_mma_i8(uint32_t d_tmem, uint64_t da, uint64_t
                  ::"r"(d_tmem), "l"(da), "l"(db), "r"(idesc), "r"(acc) : "memory");
 }
 
+struct OzGram {            // fused Gram output of the TN product (see the kernel)
+    int nb_main;
+    double* out2;
+    int64_t out2_group_stride;
+};
+
 // grid: (second-operand row blocks, first-operand row blocks, groups) — the CTAs that share the (larger) first-operand tiles are
 // adjacent in launch order, so those tiles are fetched from HBM once and hit L2 for the other N tiles.  Group g (TN: an
 // accumulation chunk; NN: always 0) uses the digit tiles a_tiles + g * a_group_stride (tile-row block blockIdx.y) and
@@ -334,11 +340,21 @@ template <int S, typename TO, bool MN>
 __global__ void __launch_bounds__(256, 1)
 ozaki_mma_kernel(const int8_t* __restrict__ a_tiles, int64_t a_group_stride, const int8_t* __restrict__ b_tiles, int64_t b_group_stride, int nkb,
                  const int* __restrict__ Ea, int64_t ea_stride, const int* __restrict__ Eb, int64_t eb_stride, int64_t rows_a, int rows_b,
-                 TO* __restrict__ out, int64_t ldo, int64_t out_group_stride, double alpha, double beta, long long* __restrict__ dbg, int flags) {
+                 TO* __restrict__ out, int64_t ldo, int64_t out_group_stride, double alpha, double beta, long long* __restrict__ dbg, int flags,
+                 OzGram gp) {
     using Cfg = OzCfg<S>;
+    // Fused Gram matrix (TN, MN-major only): tile rows blockIdx.y >= gp.nb_main compute Y^T Y next to X^T Y - their first operand is
+    // assembled from two 64-column tiles of the SECOND operand's digits, their output goes to gp.out2 (rows_b x rows_b per group).
+    const bool gram = gp.out2 != nullptr && (int)blockIdx.y >= gp.nb_main;
+    const int by = gram ? (int)blockIdx.y - gp.nb_main : (int)blockIdx.y;
+    if (gram) {
+        if (by * OZ_BM > (int)blockIdx.x * OZ_BN + OZ_BN - 1) return;      // upper tiles only
+        rows_a = rows_b; Ea = Eb; ea_stride = eb_stride;
+        out = reinterpret_cast<TO*>(gp.out2); ldo = rows_b; out_group_stride = gp.out2_group_stride;
+    }
     // flags & 1: the second operand is an upper-triangular K x N matrix (tile column block x only has non-zeros in K < 64 (x + 1)):
     //            the K loop stops there.  flags & 2: only tiles that touch the upper triangle of the output are computed (Gram).
-    if ((flags & 2) && (int)blockIdx.y * OZ_BM > (int)blockIdx.x * OZ_BN + OZ_BN - 1) return;
+    if ((flags & 2) && by * OZ_BM > (int)blockIdx.x * OZ_BN + OZ_BN - 1) return;
     const int nkb_stride = nkb;                     // K blocks per tile row in memory
     if (flags & 1) nkb = min(nkb, ((int)blockIdx.x + 1) * (OZ_BN / OZ_KB));
     constexpr int STAGES = Cfg::STAGES;
@@ -354,7 +370,7 @@ ozaki_mma_kernel(const int8_t* __restrict__ a_tiles, int64_t a_group_stride, con
     asm volatile("mov.u32 %0, %%cluster_nctaid.x;" : "=r"(cs));
     asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
     const uint16_t cmask = (uint16_t)((1u << cs) - 1u);
-    const int8_t* ga = a_tiles + g * a_group_stride + (int64_t)blockIdx.y * nkb_stride * (S * OZ_TILE_A);
+    const int8_t* ga = a_tiles + g * a_group_stride + (int64_t)by * nkb_stride * (S * OZ_TILE_A);
     const int8_t* gb = b_tiles + g * b_group_stride + (int64_t)blockIdx.x * nkb_stride * (S * OZ_TILE_B);
 
     if (tid == 0) {
@@ -392,6 +408,20 @@ ozaki_mma_kernel(const int8_t* __restrict__ a_tiles, int64_t a_group_stride, con
             if (kb >= STAGES) oz_mbar_wait(oz_smem(&bar_empty[slot]), (uint32_t)(((kb / STAGES) - 1) & 1));
             const uint32_t bar = oz_smem(&bar_full[slot]);
             const uint32_t dst = sbase + slot * Cfg::STAGE_BYTES;
+            if (gram) {
+                // first operand = columns [128 by, 128 by + 128) of Y = second-operand tiles 2 by and 2 by + 1 (the MN-major layout of a
+                // 128-column tile is two 64-column tiles back to back, per digit)
+                const bool has1 = 2 * by + 1 < (int)gridDim.x;
+                const int8_t* y0 = b_tiles + g * b_group_stride + ((int64_t)(2 * by) * nkb_stride + kb) * (S * OZ_TILE_B);
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
+                             ::"r"(bar), "r"((uint32_t)(S * OZ_TILE_B * (has1 ? 3 : 2))) : "memory");
+                for (int t = 0; t < S; ++t) {
+                    oz_bulk_load(dst + t * OZ_TILE_A, y0 + t * OZ_TILE_B, OZ_TILE_B, bar);
+                    if (has1) oz_bulk_load(dst + t * OZ_TILE_A + OZ_TILE_B, y0 + (int64_t)nkb_stride * (S * OZ_TILE_B) + t * OZ_TILE_B, OZ_TILE_B, bar);
+                }
+                oz_bulk_load(dst + S * OZ_TILE_A, gb + (int64_t)kb * (S * OZ_TILE_B), S * OZ_TILE_B, bar);
+                continue;
+            }
             asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)Cfg::STAGE_BYTES) : "memory");
             if (cs == 1) {
                 oz_bulk_load(dst, ga + (int64_t)kb * (S * OZ_TILE_A), S * OZ_TILE_A, bar);
@@ -435,7 +465,7 @@ ozaki_mma_kernel(const int8_t* __restrict__ a_tiles, int64_t a_group_stride, con
     asm volatile("tcgen05.fence::after_thread_sync;");
     if (dbg) t_acc = clock64();
     const int quarter = warp & 3, chalf = warp >> 2;
-    const int64_t i = (int64_t)blockIdx.y * OZ_BM + quarter * 32 + (tid & 31);
+    const int64_t i = (int64_t)by * OZ_BM + quarter * 32 + (tid & 31);
     const int ea = (i < rows_a) ? Ea[g * ea_stride + i] : 0;
     constexpr int ESHIFT = (2 * Cfg::P - 16 * (S - 1)) + 16;
     // fast scaling: when 2^(ea + eb - ESHIFT) is a normal double for every column of the tile, its high word is one integer add
@@ -565,7 +595,8 @@ static int oz_pick_cluster(const int* cs_ok, int nxb) {
 template <int S, typename TO, bool MN>
 static int oz_launch_mma(Ctx* ctx, dim3 grid, int cs, cudaStream_t stream, const int8_t* a_tiles, int64_t a_group_stride, const int8_t* b_tiles,
                          int64_t b_group_stride, int nkb, const int* Ea, int64_t ea_stride, const int* Eb, int64_t eb_stride, int64_t rows_a, int rows_b,
-                         TO* out, int64_t ldo, int64_t out_group_stride, double alpha, double beta, long long* dbg = nullptr, int flags = 0) {
+                         TO* out, int64_t ldo, int64_t out_group_stride, double alpha, double beta, long long* dbg = nullptr, int flags = 0,
+                         OzGram gp = OzGram{0, nullptr, 0}) {
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = grid;
     cfg.blockDim = dim3(256);
@@ -576,7 +607,7 @@ static int oz_launch_mma(Ctx* ctx, dim3 grid, int cs, cudaStream_t stream, const
     at[0].val.clusterDim.x = cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
     RLB_CUDA_OK(ctx, cudaLaunchKernelEx(&cfg, ozaki_mma_kernel<S, TO, MN>, a_tiles, a_group_stride, b_tiles, b_group_stride, nkb, Ea, ea_stride, Eb, eb_stride,
-                                        rows_a, rows_b, out, ldo, out_group_stride, alpha, beta, dbg, flags));
+                                        rows_a, rows_b, out, ldo, out_group_stride, alpha, beta, dbg, flags, gp));
     return 0;
 }
 // RLB200_OZ_DBG=1: per-CTA cycle stamps of one launch (start, barriers/TMEM ready, first stage landed, accumulators complete, end),
@@ -780,7 +811,7 @@ static int oz_nn(Ctx* ctx, int64_t m, int64_t N, int64_t K, double alpha, const 
 // ------------------------------------------------------------------------------------------------
 template <int S, typename T>
 static int oz_tn(Ctx* ctx, int64_t m, int64_t N1, int64_t N2, double alpha, const T* X, int64_t ldx, const T* Y, int64_t ldy, double beta, T* C,
-                 int64_t ldc, double* x_sumsq_out, bool upper_only) {
+                 int64_t ldc, double* x_sumsq_out, bool upper_only, T* gram_out, int64_t ldg) {
     using Cfg = OzCfg<S>;
     int cs_ok[5];
     static const bool kmajor = getenv("RLB200_OZ_TN_KMAJOR") != nullptr;      // diagnostics: the K-major column slicer
@@ -792,13 +823,23 @@ static int oz_tn(Ctx* ctx, int64_t m, int64_t N1, int64_t N2, double alpha, cons
     const int64_t nchunks = (m + L - 1) / L;
     const int nkb = (int)(L / OZ_KB);
     const int nb1 = (int)((N1 + OZ_BM - 1) / OZ_BM), nb2 = (int)((N2 + OZ_BN - 1) / OZ_BN);
+    // fused Gram matrix Y^T Y: nb1g more tile rows (upper tiles only) fed from the second operand's digits
+    const int nb1g = gram_out ? (int)((N2 + OZ_BM - 1) / OZ_BM) : 0;
+    int gram_tiles = 0;
+    for (int y = 0; y < nb1g; ++y) for (int x = 0; x < nb2; ++x) gram_tiles += (y * OZ_BM <= x * OZ_BN + OZ_BN - 1) ? 1 : 0;
     // chunks per launch: as many as fill two waves of CTAs; chunk slot q of every launch accumulates into partial q
-    const int G = (int)std::max<int64_t>(1, std::min<int64_t>(nchunks, (2 * ctx->num_sms) / (nb1 * nb2)));
+    const int G = (int)std::max<int64_t>(1, std::min<int64_t>(nchunks, (2 * ctx->num_sms) / (nb1 * nb2 + gram_tiles)));
     const int nbuf = nchunks > G ? 2 : 1;
     const int cs = oz_pick_cluster(cs_ok, nb2);
     ArenaScope as(ctx);
     const int64_t total = N1 * N2;
     double* part = as.take<double>((size_t)G * total); if (!part) return RLB200_ERR_ALLOC;
+    double* part_g = nullptr;
+    if (gram_out) {
+        RLB_REQUIRE(ctx, !kmajor);
+        part_g = as.take<double>((size_t)G * N2 * N2); if (!part_g) return RLB200_ERR_ALLOC;
+        RLB_CUDA_OK(ctx, cudaMemsetAsync(part_g, 0, sizeof(double) * (size_t)G * N2 * N2, ctx->stream));
+    }
     const bool cached = ctx->oz_const_ptr == (const void*)X;     // X does not change during the enclosing driver scope
     int* Ex = nullptr;
     double* ssx = nullptr;
@@ -866,8 +907,9 @@ static int oz_tn(Ctx* ctx, int64_t m, int64_t N1, int64_t N2, double alpha, cons
                 RLB_CHECK((oz_launch_mma<S, double, false>(ctx, dim3(nb2, nb1, g), cs, main, xt[b], xs, yt[b], ys, nkb, Ex + c0 * N1, N1, Ey + c0 * N2, N2, N1,
                                                            (int)N2, part, N1, total, 1.0, c0 > 0 ? 1.0 : 0.0, dbg, upper_only ? 2 : 0)));
             else
-                RLB_CHECK((oz_launch_mma<S, double, true>(ctx, dim3(nb2, nb1, g), cs, main, xt[b], xs, yt[b], ys, nkb, Ex + c0 * N1, N1, Ey + c0 * N2, N2, N1,
-                                                          (int)N2, part, N1, total, 1.0, c0 > 0 ? 1.0 : 0.0, dbg, upper_only ? 2 : 0)));
+                RLB_CHECK((oz_launch_mma<S, double, true>(ctx, dim3(nb2, nb1 + nb1g, g), gram_out ? 1 : cs, main, xt[b], xs, yt[b], ys, nkb, Ex + c0 * N1, N1,
+                                                          Ey + c0 * N2, N2, N1, (int)N2, part, N1, total, 1.0, c0 > 0 ? 1.0 : 0.0, dbg, upper_only ? 2 : 0,
+                                                          OzGram{nb1, part_g, N2 * N2})));
             if (dbg) { oz_dbg_report("TN", main, dbg, (int64_t)nb2 * nb1 * g); cudaFree(dbg); }
         }
         tl.mark('M', main);
@@ -878,6 +920,12 @@ static int oz_tn(Ctx* ctx, int64_t m, int64_t N1, int64_t N2, double alpha, cons
     oz_reduce_kernel<T><<<(unsigned)std::min<int64_t>((total + 255) / 256, (int64_t)ctx->num_sms * 8), 256, 0, main>>>(
         part, (int)std::min<int64_t>(G, nchunks), total, (int)N1, alpha, beta, C, ldc);
     RLB_CUDA_OK(ctx, cudaGetLastError());
+    if (gram_out) {
+        ctx->launches += 1;
+        oz_reduce_kernel<T><<<(unsigned)std::min<int64_t>((N2 * N2 + 255) / 256, (int64_t)ctx->num_sms * 8), 256, 0, main>>>(
+            part_g, (int)std::min<int64_t>(G, nchunks), N2 * N2, (int)N2, 1.0, 0.0, gram_out, ldg);
+        RLB_CUDA_OK(ctx, cudaGetLastError());
+    }
     if (x_sumsq_out) {      // main has waited for the slicing events, which follow the exponent pass on the second stream
         ctx->launches += 1;
         oz_sum_kernel<<<1, 1024, 0, main>>>(ssx, nchunks * N1, x_sumsq_out);
@@ -907,21 +955,23 @@ int ozaki_gemm_nn(Ctx* ctx, int64_t m, int64_t N, int64_t K, double alpha, const
 }
 template <typename T>
 int ozaki_gemm_tn(Ctx* ctx, int64_t m, int64_t N1, int64_t N2, double alpha, const T* X, int64_t ldx, const T* Y, int64_t ldy, double beta, T* C,
-                  int64_t ldc, double* x_sumsq_out, bool upper_only) {
+                  int64_t ldc, double* x_sumsq_out, bool upper_only, T* gram_out, int64_t ldg) {
     RLB_REQUIRE(ctx, m >= 0 && N1 >= 0 && N2 >= 0 && N1 < (1 << 20) && N2 < (1 << 20));
     if (N1 == 0 || N2 == 0) return 0;
     if (m == 0) return gemm_tn<T>(ctx, 0, N1, N2, 0.0, X, ldx, Y, ldy, beta, C, ldc, 0, x_sumsq_out);
     switch (oz_default_digits(ctx, sizeof(T))) {
-        case 3: return oz_tn<3, T>(ctx, m, N1, N2, alpha, X, ldx, Y, ldy, beta, C, ldc, x_sumsq_out, upper_only);
-        case 4: return oz_tn<4, T>(ctx, m, N1, N2, alpha, X, ldx, Y, ldy, beta, C, ldc, x_sumsq_out, upper_only);
-        case 5: return oz_tn<5, T>(ctx, m, N1, N2, alpha, X, ldx, Y, ldy, beta, C, ldc, x_sumsq_out, upper_only);
-        case 6: return oz_tn<6, T>(ctx, m, N1, N2, alpha, X, ldx, Y, ldy, beta, C, ldc, x_sumsq_out, upper_only);
-        default: return oz_tn<7, T>(ctx, m, N1, N2, alpha, X, ldx, Y, ldy, beta, C, ldc, x_sumsq_out, upper_only);
+        case 3: return oz_tn<3, T>(ctx, m, N1, N2, alpha, X, ldx, Y, ldy, beta, C, ldc, x_sumsq_out, upper_only, gram_out, ldg);
+        case 4: return oz_tn<4, T>(ctx, m, N1, N2, alpha, X, ldx, Y, ldy, beta, C, ldc, x_sumsq_out, upper_only, gram_out, ldg);
+        case 5: return oz_tn<5, T>(ctx, m, N1, N2, alpha, X, ldx, Y, ldy, beta, C, ldc, x_sumsq_out, upper_only, gram_out, ldg);
+        case 6: return oz_tn<6, T>(ctx, m, N1, N2, alpha, X, ldx, Y, ldy, beta, C, ldc, x_sumsq_out, upper_only, gram_out, ldg);
+        default: return oz_tn<7, T>(ctx, m, N1, N2, alpha, X, ldx, Y, ldy, beta, C, ldc, x_sumsq_out, upper_only, gram_out, ldg);
     }
 }
 template int ozaki_gemm_nn<double>(Ctx*, int64_t, int64_t, int64_t, double, const double*, int64_t, const double*, int64_t, double, double*, int64_t, bool);
 template int ozaki_gemm_nn<float>(Ctx*, int64_t, int64_t, int64_t, double, const float*, int64_t, const float*, int64_t, double, float*, int64_t, bool);
-template int ozaki_gemm_tn<double>(Ctx*, int64_t, int64_t, int64_t, double, const double*, int64_t, const double*, int64_t, double, double*, int64_t, double*, bool);
-template int ozaki_gemm_tn<float>(Ctx*, int64_t, int64_t, int64_t, double, const float*, int64_t, const float*, int64_t, double, float*, int64_t, double*, bool);
+template int ozaki_gemm_tn<double>(Ctx*, int64_t, int64_t, int64_t, double, const double*, int64_t, const double*, int64_t, double, double*, int64_t, double*, bool,
+                                   double*, int64_t);
+template int ozaki_gemm_tn<float>(Ctx*, int64_t, int64_t, int64_t, double, const float*, int64_t, const float*, int64_t, double, float*, int64_t, double*, bool,
+                                  float*, int64_t);
 
 }  // namespace rlb
