@@ -304,6 +304,17 @@ __device__ __forceinline__ void oz_mbar_wait(uint32_t bar, uint32_t parity) {
                      : "=r"(done) : "r"(bar), "r"(parity) : "memory");
     }
 }
+// long waits (the epilogue warps wait for a whole tile's main loop): back off so that the spinning warps do not take issue slots from
+// the slicer CTAs that share the SM
+__device__ __forceinline__ void oz_mbar_wait_sleep(uint32_t bar, uint32_t parity) {
+    uint32_t done = 0;
+    while (true) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                     : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+        if (done) break;
+        __nanosleep(256);
+    }
+}
 __device__ __forceinline__ void oz_bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
@@ -461,7 +472,7 @@ ozaki_mma_kernel(const int8_t* __restrict__ a_tiles, int64_t a_group_stride, con
     __syncwarp();
     // ---- epilogue: TMEM lane = tile row.  Warps w and w + 4 share lane quarter w % 4 (a warp may only touch its own quarter) and
     // take 32 of the 64 columns each.
-    oz_mbar_wait(oz_smem(&bar_acc), 0);
+    oz_mbar_wait_sleep(oz_smem(&bar_acc), 0);
     asm volatile("tcgen05.fence::after_thread_sync;");
     if (dbg) t_acc = clock64();
     const int quarter = warp & 3, chalf = warp >> 2;

@@ -640,6 +640,9 @@ int sketch_dense_left(Ctx* ctx, int64_t S_rows, int64_t S_cols, int family, int 
         const T beta0 = (sharded && shard_off != 0) ? (T)0 : beta;
         int64_t pc = std::max<int64_t>(64, (int64_t)(kDensePanelBytes / sizeof(T)) / std::max<int64_t>(d, 1));
         pc = std::min<int64_t>((pc / 64) * 64, std::max<int64_t>(m, 1));
+        // tcgen05 int8 digit-slice engine for the long contraction: panels of four 16384-row accumulation chunks keep every SM busy
+        const bool i8 = ctx->fp64_engine == RLB200_FP64_I8SLICES && m >= 16384 && d >= 64 && n >= 64;
+        if (i8) pc = std::min<int64_t>(std::max<int64_t>(pc, 65536), ((m + 63) / 64) * 64);
         ArenaScope as(ctx);
         T* panel = as.take<T>((size_t)2 * d * pc); if (!panel) return RLB200_ERR_ALLOC;
         if (m == 0) RLB_CHECK(gemm_nn<T>(ctx, d, n, 0, 0.0, panel, d, A, lda, (double)beta0, B, ldb));
@@ -653,7 +656,8 @@ int sketch_dense_left(Ctx* ctx, int64_t S_rows, int64_t S_cols, int family, int 
             // Long-axis operator), i.e. the w x d column-major matrix S_block^T with ld = w: the product is then the long-contraction
             // (split-K, whole-machine) form  B += (S_block^T)^T A_block
             RLB_CHECK(fill_dense_unpacked<T>(ctx, S_rows, S_cols, family, major_axis, RLB200_LAYOUT_ROWMAJOR, d, w, ro, co + shard_off + j0, P, st));
-            RLB_CHECK(gemm_tn<T>(ctx, w, d, n, (double)alpha, P, w, A + j0, lda, j0 == 0 ? (double)beta0 : 1.0, B, ldb, 0));
+            if (i8) RLB_CHECK(ozaki_gemm_tn<T>(ctx, w, d, n, (double)alpha, P, w, A + j0, lda, j0 == 0 ? (double)beta0 : 1.0, B, ldb));
+            else RLB_CHECK(gemm_tn<T>(ctx, w, d, n, (double)alpha, P, w, A + j0, lda, j0 == 0 ? (double)beta0 : 1.0, B, ldb, 0));
         }
         if (sharded && ctx->allreduce) {
             for (int64_t c = 0; c < (ldb == d ? 1 : n); ++c) {
