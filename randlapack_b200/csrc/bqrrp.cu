@@ -108,6 +108,24 @@ __global__ void __launch_bounds__(256) orhr_tfactor_kernel(int n, const T* __res
     }
 }
 
+// right-hand side of the same computation as a triangular solve: Tm = -U S (upper, strictly-lower part zero); T = Tm V1^{-T} follows
+// as one blocked right-solve with the unit upper triangular V1^T on the tensor-pipe GEMMs (the one-thread-per-row kernel above walks
+// n^2/2 dependent global loads per thread: 4.4 ms for n = 256 under ncu, 19 % of a BQRRP step)
+template <typename T>
+__global__ void __launch_bounds__(256) orhr_rhs_kernel(int n, const T* __restrict__ A, int64_t lda, const T* __restrict__ D, T* __restrict__ Tm, int ldt) {
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n * n; e += gridDim.x * blockDim.x) {
+        const int i = e % n, j = e / n;
+        T v = (T)0;
+        if (j >= i) { const T u = A[i + (int64_t)j * lda]; v = ((double)D[j] == 1.0) ? -u : u; }
+        Tm[i + (size_t)j * ldt] = v;
+    }
+}
+template <typename T>
+__global__ void __launch_bounds__(256) diag_copy_kernel(int n, const T* __restrict__ Tm, int ldt, T* __restrict__ tau) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) tau[i] = Tm[i + (size_t)i * ldt];
+}
+
 // rows of the upper triangle scaled by D: R[j][i] *= D[j] for j <= i   (rl_bqrrp.hh:471-473)
 template <typename T>
 __global__ void __launch_bounds__(256) scale_rows_upper_kernel(int n, T* __restrict__ R, int ldr, const T* __restrict__ D) {
@@ -415,10 +433,19 @@ int bqrrp_call(Ctx* ctx, int64_t m, int64_t n, T* A, int64_t lda, T d_factor, in
             }
             if (rows > br) RLB_CHECK(trsm_right_upper<T>(ctx, rows - br, br, A_work, lda, A_work + br, lda));
             {
-                LaunchScope ls(ctx, RLB200_TIMER_SMALL, 3);
-                orhr_tfactor_kernel<T><<<(unsigned)((br + 255) / 256), 256, 0, ctx->stream>>>((int)br, A_work, lda, Dv, T_dat, (int)b_const, tau_sub);
-                scale_rows_upper_kernel<T><<<(unsigned)std::min<int64_t>((br * br + 255) / 256, 1024), 256, 0, ctx->stream>>>((int)br, R_tall, (int)b_const, Dv);
-                unit_lower_kernel<T><<<(unsigned)std::min<int64_t>((br * br + 255) / 256, 1024), 256, 0, ctx->stream>>>((int)br, A_work, lda, V1c, (int)br);
+                // T = (-U S) V1^{-T} (dorhr_col steps 2-1 .. 2-4): right-hand side, then one blocked right-solve with V1^T (Gs is free here)
+                const unsigned nbk = (unsigned)std::min<int64_t>((br * br + 255) / 256, 1024);
+                {
+                    LaunchScope ls(ctx, RLB200_TIMER_SMALL, 2);
+                    unit_lower_kernel<T><<<nbk, 256, 0, ctx->stream>>>((int)br, A_work, lda, V1c, (int)br);
+                    orhr_rhs_kernel<T><<<nbk, 256, 0, ctx->stream>>>((int)br, A_work, lda, Dv, T_dat, (int)b_const);
+                    RLB_CUDA_OK(ctx, cudaGetLastError());
+                }
+                RLB_CHECK(transpose<T>(ctx, br, br, V1c, br, Gs, br));
+                RLB_CHECK(trsm_right_upper<T>(ctx, br, br, Gs, br, T_dat, b_const));
+                LaunchScope ls(ctx, RLB200_TIMER_SMALL, 2);
+                diag_copy_kernel<T><<<(unsigned)((br + 255) / 256), 256, 0, ctx->stream>>>((int)br, T_dat, (int)b_const, tau_sub);
+                scale_rows_upper_kernel<T><<<nbk, 256, 0, ctx->stream>>>((int)br, R_tall, (int)b_const, Dv);
                 RLB_CUDA_OK(ctx, cudaGetLastError());
             }
             // R11 = R11_full(0:br, :) * R_sk(0:b, 0:b)  (trmm :486) — computed now, stored into A after the trailing update because the

@@ -9,6 +9,8 @@
 // HBM traffic drops from 8*m*n^2 bytes to ~8*m*n^2/32; everything stays on the device (pivot indices live in device memory).
 #include "drivers.cuh"
 #include <algorithm>
+#include <cstdlib>
+#include <cooperative_groups.h>
 
 namespace rlb {
 
@@ -147,6 +149,85 @@ __global__ void __launch_bounds__(128) lu_trsm_unit_lower(const T* __restrict__ 
     for (int i = 1; i < 32; ++i) if (i < nb) col[i] = (T)x[i];
 }
 
+// One 32-column panel [jb, jend) of the blocked LU in ONE cooperative launch: per column a grid-wide pivot reduction, the row
+// interchange across all n columns, and the scale + rank-1 update of the panel's remaining columns, which also yields the pivot
+// candidates of the next column (two grid syncs per column instead of three launches).
+template <typename T>
+__global__ void __launch_bounds__(256) lu_panel_coop_kernel(T* __restrict__ A, int64_t m, int64_t lda, int n, int jb, int jend,
+                                                            PivCand* __restrict__ part, long long* __restrict__ ipiv, int* __restrict__ nonzero) {
+    namespace cg = cooperative_groups;
+    cg::grid_group grid = cg::this_grid();
+    __shared__ PivCand sh[8];
+    __shared__ PivCand sbest;
+    __shared__ double urow[32];
+    const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, gsz = (int64_t)gridDim.x * blockDim.x;
+    auto block_publish = [&](PivCand best) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            PivCand c{__shfl_xor_sync(0xffffffffu, best.v, o), __shfl_xor_sync(0xffffffffu, best.i, o)};
+            best = better(best, c);
+        }
+        if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = best;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            for (int w = 1; w < 8; ++w) best = better(best, sh[w]);
+            part[blockIdx.x] = best;
+        }
+        __syncthreads();
+    };
+    {   // pivot candidates of the first column of the panel
+        PivCand best{-1.0, (long long)m};
+        const T* col = A + (int64_t)jb * lda;
+        for (int64_t i = jb + gtid; i < m; i += gsz) best = better(best, PivCand{fabs((double)col[i]), (long long)i});
+        block_publish(best);
+    }
+    for (int j = jb; j < jend; ++j) {
+        grid.sync();
+        // every CTA reduces the candidates (same order everywhere); CTA 0 records the pivot and interchanges rows j and p
+        if (threadIdx.x < 32) {
+            PivCand best{-1.0, (long long)1 << 62};
+            for (int q = threadIdx.x; q < (int)gridDim.x; q += 32) best = better(best, part[q]);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                PivCand c{__shfl_xor_sync(0xffffffffu, best.v, o), __shfl_xor_sync(0xffffffffu, best.i, o)};
+                best = better(best, c);
+            }
+            if (threadIdx.x == 0) sbest = best;
+        }
+        __syncthreads();
+        const long long p = sbest.i;
+        const bool nz = sbest.v != 0.0;
+        if (blockIdx.x == 0) {
+            if (threadIdx.x == 0) { ipiv[j] = p; nonzero[j] = nz ? 1 : 0; }
+            if (nz && p != j) {
+                for (int c = threadIdx.x; c < n; c += blockDim.x) {
+                    T* col = A + (int64_t)c * lda;
+                    const T t = col[j]; col[j] = col[p]; col[p] = t;
+                }
+            }
+        }
+        grid.sync();
+        // scale the pivot column, rank-1 update of the panel's remaining columns; candidates of column j + 1 on the fly
+        const int nc = jend - j - 1;
+        T* colj = A + (int64_t)j * lda;
+        if (threadIdx.x < nc) urow[threadIdx.x] = (double)A[j + (int64_t)(j + 1 + threadIdx.x) * lda];
+        __syncthreads();
+        const T rinv = nz ? (T)1 / colj[j] : (T)1;
+        PivCand best{-1.0, (long long)m};
+        for (int64_t i = j + 1 + gtid; i < m; i += gsz) {
+            T l = colj[i];
+            if (nz) { l = l * rinv; colj[i] = l; }
+            for (int c = 0; c < nc; ++c) {
+                T* a = A + i + (int64_t)(j + 1 + c) * lda;
+                const T v = (T)((double)*a - (double)l * urow[c]);
+                *a = v;
+                if (c == 0) best = better(best, PivCand{fabs((double)v), (long long)i});
+            }
+        }
+        if (j + 1 < jend) block_publish(best);
+    }
+}
+
 size_t plul_ws_bytes(Ctx* ctx, int64_t n) {
     return ws_round(sizeof(PivCand) * (size_t)ctx->num_sms * 8) + ws_round(sizeof(long long) * n) + ws_round(sizeof(int) * n);
 }
@@ -159,7 +240,17 @@ int getrf_nopiv_out(Ctx* ctx, int64_t m, int64_t n, T* A, int64_t lda, PivCand* 
     constexpr int NB = 32;
     for (int jb = 0; jb < kmin; jb += NB) {
         const int jend = std::min(jb + NB, kmin);
-        {
+        const int64_t prow = m - jb;
+        int occ = 0;
+        RLB_CUDA_OK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, lu_panel_coop_kernel<T>, 256, 0));
+        if (occ > 0 && prow >= 4096 && getenv("RLB200_LU_NOCOOP") == nullptr) {
+            // one cooperative launch per panel (grid = all co-resident CTAs that have rows to own)
+            const int gridc = (int)std::max<int64_t>(1, std::min<int64_t>((prow + 255) / 256, std::min<int64_t>((int64_t)occ * ctx->num_sms, (int64_t)ctx->num_sms * 8)));
+            LaunchScope ls(ctx, RLB200_TIMER_SMALL);
+            int n_ = (int)n, jb_ = jb, jend_ = jend;
+            void* args[] = {&A, &m, &lda, &n_, &jb_, &jend_, &part, &ipiv, &nonzero};
+            RLB_CUDA_OK(ctx, cudaLaunchCooperativeKernel((void*)lu_panel_coop_kernel<T>, dim3(gridc), dim3(256), args, 0, ctx->stream));
+        } else {
             LaunchScope ls(ctx, RLB200_TIMER_SMALL, 3 * (jend - jb));
             for (int j = jb; j < jend; ++j) {
                 const int64_t rows = m - j;
