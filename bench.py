@@ -439,7 +439,7 @@ def main():
     barrier()
     ms_total = e0.elapsed_time(e1)
     clocks = sampler.stop() if rank == 0 else None
-    launches = ctx.launch_count() / args.steps
+    launches = int(round(ctx.launch_count() / args.steps))
     # per-class CUDA-event times on the launching streams: one extra, untimed step (the class timers synchronise the host between
     # launches, so they are kept out of the timed region)
     ctx.timers_enable(True)
