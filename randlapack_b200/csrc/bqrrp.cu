@@ -91,26 +91,10 @@ __global__ void __launch_bounds__(1024) orhr_getrfnp_kernel(int n, T* __restrict
     }
 }
 
-// T (n x n upper, ldt; strictly-lower part zeroed) = (-U S) V1^{-T}  (dorhr_col steps 2-1 .. 2-4 with one block);
-// U = upper triangle of A (incl. diagonal), V1 = unit lower triangle of A.  Row i of T only depends on row i: one thread per row.
-template <typename T>
-__global__ void __launch_bounds__(256) orhr_tfactor_kernel(int n, const T* __restrict__ A, int64_t lda, const T* __restrict__ D, T* __restrict__ Tm, int ldt,
-                                                           T* __restrict__ tau) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    for (int j = 0; j < i; ++j) Tm[i + (size_t)j * ldt] = (T)0;
-    for (int j = i; j < n; ++j) {
-        const double u = (double)A[i + (int64_t)j * lda];
-        double acc = ((double)D[j] == 1.0) ? -u : u;
-        for (int l = i; l < j; ++l) acc -= (double)Tm[i + (size_t)l * ldt] * (double)A[j + (int64_t)l * lda];
-        Tm[i + (size_t)j * ldt] = (T)acc;
-        if (j == i && tau) tau[i] = (T)acc;
-    }
-}
-
-// right-hand side of the same computation as a triangular solve: Tm = -U S (upper, strictly-lower part zero); T = Tm V1^{-T} follows
-// as one blocked right-solve with the unit upper triangular V1^T on the tensor-pipe GEMMs (the one-thread-per-row kernel above walks
-// n^2/2 dependent global loads per thread: 4.4 ms for n = 256 under ncu, 19 % of a BQRRP step)
+// T (n x n upper, ldt) = (-U S) V1^{-T}  (dorhr_col steps 2-1 .. 2-4 with one block); U = upper triangle of A (incl. diagonal),
+// V1 = unit lower triangle of A.  Right-hand side Tm = -U S (upper, strictly-lower part zero); T = Tm V1^{-T} follows as one blocked
+// right-solve with the unit upper triangular V1^T on the tensor-pipe GEMMs (a one-thread-per-row substitution walks n^2/2 dependent
+// global loads per thread: 4.4 ms for n = 256 under ncu, 19 % of a BQRRP step, in the first version)
 template <typename T>
 __global__ void __launch_bounds__(256) orhr_rhs_kernel(int n, const T* __restrict__ A, int64_t lda, const T* __restrict__ D, T* __restrict__ Tm, int ldt) {
     for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n * n; e += gridDim.x * blockDim.x) {

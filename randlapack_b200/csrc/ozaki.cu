@@ -53,8 +53,6 @@ struct OzCfg {
     static constexpr unsigned long long LOWMASK = 0x8080808080808080ull >> (8 * (9 - S));
 };
 
-__device__ int oz_dbg_mode = 0;      // diagnostics (RLB200_OZ_DBG): 1 = epilogue without math/stores, 2 = without stores
-
 __device__ __forceinline__ uint32_t oz_smem(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 // ------------------------------------------------------------------------------------------------
@@ -802,11 +800,7 @@ static int oz_nn(Ctx* ctx, int64_t m, int64_t N, int64_t K, double alpha, const 
         {
             LaunchScope ls(ctx, RLB200_TIMER_I8_MMA_NN);
             long long* dbg = nullptr;
-            if (c == 0 && getenv("RLB200_OZ_DBG")) {
-                cudaMalloc(&dbg, (size_t)nnb * nrb * 64);
-                const int mode = atoi(getenv("RLB200_OZ_DBG")) - 1;
-                cudaMemcpyToSymbol(oz_dbg_mode, &mode, sizeof(int));
-            }
+            if (c == 0 && getenv("RLB200_OZ_DBG")) cudaMalloc(&dbg, (size_t)nnb * nrb * 64);
             RLB_CHECK((oz_launch_mma<S, T, false>(ctx, dim3(nnb, nrb, 1), cs, main, at[b], 0, bt, 0, nkb, Ea_c, 0, Eb, 0, rows, (int)N, C + r0, ldc, 0, alpha, beta, dbg, b_upper_tri ? 1 : 0)));
             if (dbg) { oz_dbg_report("NN", main, dbg, (int64_t)nnb * nrb); cudaFree(dbg); }
         }

@@ -252,6 +252,23 @@ def test_rsvd_f32(ctx):
     assert np.abs(S.cpu().numpy() - S_o).max() <= 1e-4 * S_o[0]
 
 
+def test_rsvd_f32_tall_on_the_digit_slice_engine(ctx):
+    """fp32 storage, tall enough (m >= 16384) for the tall products to run on the int8 digit-slice engine with 4 digits (30 bits):
+    singular values against the fp64 oracle on the same fp32 input, orthonormal factors."""
+    m, n, k = 40000, 128, 16
+    A, st0 = poly(m, n, n, dtype=np.float32)
+    *_, RSVD = _stack(2, 1, k)
+    o = O.StackOpts(2, 1, k, O.STAB_CHOLQRQ, O.STAB_CHOLQRQ, O.STAB_CHOLQRQ)
+    *_, rsvd_o = O.make_stack(o)
+    st = rl.RNGState(st0.key, st0.counter)
+    rc, kk, U, S, V = RSVD.call(ctx, dev(A), k, 0.0, st)
+    rc_o, kk_o, U_o, S_o, V_o, s_o = rsvd_o.call(A, k, 0.0, st0.copy())
+    assert (rc, kk) == (rc_o, kk_o) and st.counter == s_o.counter
+    assert np.abs(S.cpu().numpy() - S_o).max() <= 1e-4 * S_o[0]
+    Uh = host(U).astype(np.float64)
+    assert np.linalg.norm(Uh.T @ Uh - np.eye(kk)) <= 1e-3
+
+
 def test_rsvd_host_entry_point(ctx):
     # the reference-facing form: host buffers in, host buffers out (what e2e measures)
     m, n, k = 3000, 128, 16
