@@ -659,7 +659,13 @@ static int oz_configure_slicers(Ctx* ctx) {
 }
 static int oz_aux(Ctx* ctx) {
     if (!ctx->aux_stream) {
-        RLB_CUDA_OK(ctx, cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking));
+        // the slicers are the critical path of a pass: their CTAs go first whenever an SM has room (RLB200_OZ_AUX_PRIO=0: plain stream)
+        int lo = 0, hi = 0;
+        const char* pe = getenv("RLB200_OZ_AUX_PRIO");
+        if ((pe == nullptr || atoi(pe) != 0) && cudaDeviceGetStreamPriorityRange(&lo, &hi) == cudaSuccess)
+            RLB_CUDA_OK(ctx, cudaStreamCreateWithPriority(&ctx->aux_stream, cudaStreamNonBlocking, hi));
+        else
+            RLB_CUDA_OK(ctx, cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking));
         for (auto& e : ctx->aux_ev) RLB_CUDA_OK(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     }
     return 0;
