@@ -568,8 +568,10 @@ __global__ void __launch_bounds__(256) oz_reduce_kernel(const double* __restrict
 // (almost) every SM hold a CTA (GPCs whose SM count is not a multiple of the cluster size strand SMs).  RLB200_OZ_CLUSTER overrides.
 template <int S, typename TO, bool MN>
 static int oz_configure(Ctx* ctx, int* cs_ok /* [5] */) {
-    static bool done = false;
+    // function attributes are per device: one flag per device id (one process may drive several contexts)
+    static bool done_dev[64] = {};
     static int ok[5] = {0, 1, 0, 0, 0};
+    bool& done = done_dev[ctx->device & 63];
     if (!done) {
         const int smem = OzCfg<S>::STAGES * OzCfg<S>::STAGE_BYTES;
         RLB_CUDA_OK(ctx, cudaFuncSetAttribute(ozaki_mma_kernel<S, TO, MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -644,7 +646,8 @@ template <int S, typename T>
 static int oz_configure_slicers(Ctx* ctx) {
     // the slicers run beside the tensor-core kernel (which needs the maximum shared-memory carveout): ask for the same carveout so
     // that both can be resident on one SM
-    static bool done = false;
+    static bool done_dev[64] = {};
+    bool& done = done_dev[ctx->device & 63];
     if (!done) {
         RLB_CUDA_OK(ctx, cudaFuncSetAttribute(oz_slice_rows_kernel<S, T>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         RLB_CUDA_OK(ctx, cudaFuncSetAttribute(oz_slice_cols_kernel<S, OZ_BM, T>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
