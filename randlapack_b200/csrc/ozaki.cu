@@ -120,6 +120,65 @@ __global__ void __launch_bounds__(1024) oz_sum_kernel(const double* __restrict__
     if (threadIdx.x == 0) out[0] = sh[0];
 }
 
+// Row exponents AND column-chunk exponent fields AND ||A||_F^2 partials of the constant data matrix in ONE sweep (the drivers use A as
+// the first operand of both products).  CTA = 256 consecutive rows (never straddling a chunk: L is a multiple of 256), thread = row.
+// Column maxima: warp REDUX + one shared-memory atomicMax per warp and column, then one global atomicMax per CTA and column on the
+// (pre-zeroed) field array - maxima are order-independent; the sums of squares are combined in a fixed order (lane, warp, CTA).
+template <typename T>
+__global__ void __launch_bounds__(256) oz_rowcolexp_kernel(const T* __restrict__ A, int64_t lda, int64_t rows, int K, int64_t L, int P_row,
+                                                           int* __restrict__ Erow, int* __restrict__ colfield, double* __restrict__ ss_part) {
+    extern __shared__ int s_col[];            // [K]
+    __shared__ double s_ss[8];
+    for (int c = threadIdx.x; c < K; c += 256) s_col[c] = 0;
+    __syncthreads();
+    const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    const bool rv = i < rows;
+    const T* a = A + (rv ? i : 0);
+    int rowf = 0;
+    double ss = 0.0;
+    const int lane = threadIdx.x & 31;
+    int c = 0;
+    for (; c + 4 <= K; c += 4) {
+        double x[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) x[u] = rv ? (double)a[(int64_t)(c + u) * lda] : 0.0;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int f = oz_expfield(x[u]);
+            rowf = max(rowf, f);
+            ss = fma(x[u], x[u], ss);
+            const int wf = __reduce_max_sync(0xffffffffu, f);
+            if (lane == 0 && wf > 0) atomicMax(&s_col[c + u], wf);
+        }
+    }
+    for (; c < K; ++c) {
+        const double x = rv ? (double)a[(int64_t)c * lda] : 0.0;
+        const int f = oz_expfield(x);
+        rowf = max(rowf, f);
+        ss = fma(x, x, ss);
+        const int wf = __reduce_max_sync(0xffffffffu, f);
+        if (lane == 0 && wf > 0) atomicMax(&s_col[c], wf);
+    }
+    if (rv) Erow[i] = oz_exp_from_field(rowf, P_row);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    if (lane == 0) s_ss[threadIdx.x >> 5] = ss;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int w = 0; w < 8; ++w) t += s_ss[w];
+        ss_part[blockIdx.x] = t;
+    }
+    const int64_t chunk = ((int64_t)blockIdx.x * 256) / L;
+    for (int cc = threadIdx.x; cc < K; cc += 256)
+        if (s_col[cc] > 0) atomicMax(&colfield[chunk * K + cc], s_col[cc]);
+}
+// fields -> exponents, in place
+__global__ void __launch_bounds__(256) oz_field_to_exp_kernel(int* __restrict__ E, int64_t n, int P) {
+    const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (i < n) E[i] = oz_exp_from_field(E[i], P);
+}
+
 // ------------------------------------------------------------------------------------------------
 // slicers.  Digit tiles: tile (rb, kb, t) of TR rows x 32 K-bytes at ((rb * nkb + kb) * S + t) * TR * 32, inside it the byte of
 // (row r, k) sits at ((r / 8) * 2 + k / 16) * 128 + (r % 8) * 16 + k % 16  (K-major, no swizzle: SBO = 256 B, LBO = 128 B).
@@ -776,8 +835,24 @@ static int oz_nn(Ctx* ctx, int64_t m, int64_t N, int64_t K, double alpha, const 
     RLB_CUDA_OK(ctx, cudaEventRecord(ctx->aux_ev[OZ_EV_FORK], main));
     RLB_CUDA_OK(ctx, cudaStreamWaitEvent(aux, ctx->aux_ev[OZ_EV_FORK], 0));
     if (fill_cache) {
-        LaunchScope ls(ctx, RLB200_TIMER_I8_SLICE, 1, aux);
-        oz_rowexp_kernel<T><<<(unsigned)((m + 255) / 256), 256, 0, aux>>>(A, lda, m, (int)K, Cfg::P, ctx->oz_row.E);
+        // the same sweep also prepares what the A^T Y products of this driver scope will ask for: the column-chunk exponents (for the digit
+        // count those products use) and ||A||_F^2 - one pass over A instead of two
+        const int S_tn = ctx->i8_digits ? ctx->i8_digits : (sizeof(T) == 8 ? 7 : 4);
+        const int P_tn = 8 * S_tn - 2;
+        const int64_t L = std::min<int64_t>(OZ_CHUNK, ((m + OZ_KB - 1) / OZ_KB) * OZ_KB);
+        const int64_t nchunks = (m + L - 1) / L, ncta = (m + 255) / 256;
+        const bool both = (L % 256 == 0) && K <= 8192 && (size_t)nchunks * K >= (size_t)ncta && getenv("RLB200_OZ_NO_FUSED_EXP") == nullptr;
+        LaunchScope ls(ctx, RLB200_TIMER_I8_SLICE, both ? 2 : 1, aux);
+        if (both) {
+            RLB_CHECK(oz_cache_reserve(ctx, ctx->oz_col, (size_t)nchunks * K, (size_t)nchunks * K));
+            RLB_CUDA_OK(ctx, cudaMemsetAsync(ctx->oz_col.E, 0, sizeof(int) * (size_t)nchunks * K, aux));
+            RLB_CUDA_OK(ctx, cudaMemsetAsync(ctx->oz_col.ss, 0, sizeof(double) * (size_t)nchunks * K, aux));
+            oz_rowcolexp_kernel<T><<<(unsigned)ncta, 256, (size_t)K * sizeof(int), aux>>>(A, lda, m, (int)K, L, Cfg::P, ctx->oz_row.E, ctx->oz_col.E, ctx->oz_col.ss);
+            oz_field_to_exp_kernel<<<(unsigned)((nchunks * K + 255) / 256), 256, 0, aux>>>(ctx->oz_col.E, nchunks * K, P_tn);
+            oz_cache_set(ctx->oz_col, A, m, K, lda, L, P_tn, (int)sizeof(T));
+        } else {
+            oz_rowexp_kernel<T><<<(unsigned)((m + 255) / 256), 256, 0, aux>>>(A, lda, m, (int)K, Cfg::P, ctx->oz_row.E);
+        }
         RLB_CUDA_OK(ctx, cudaGetLastError());
         oz_cache_set(ctx->oz_row, A, m, K, lda, 0, Cfg::P, (int)sizeof(T));
     }
