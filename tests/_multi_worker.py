@@ -19,7 +19,9 @@ def main():
     ctx = rl.Context(local)
     out = {}
     for (m, n, k, p, engine) in [(40000, 256, 32, 2, "dmma"), (70001, 128, 16, 3, "dmma"), (12800, 64, 64, 0, "dmma"),
-                                 (40000, 256, 32, 2, "i8"), (70001, 128, 16, 3, "i8")]:
+                                 (40000, 256, 32, 2, "i8"), (70001, 128, 16, 3, "i8"),
+                                 # the headline path: k >= 64 on the engine (fused Gram, R folded in RS, U = Y M on the engine)
+                                 (65536, 512, 128, 2, "i8"), (65536, 512, 256, 0, "i8"), (40960, 256, 64, 3, "i8")]:
         ctx.set_fp64_engine(engine)      # "i8": the tall products over A on the tcgen05 int8 digit-slice engine
         # global matrix: planted decaying spectrum so that the factors are well defined; identical on every rank
         g = torch.Generator(device="cuda").manual_seed(1234)
@@ -42,6 +44,29 @@ def main():
                "V_abs": (V[:, :kk].abs() - V1[:, :kk].abs()).abs().max().item() if kk else 0.0,
                "U_abs": (U[:, :kk].abs() - U1[r0:r1, :kk].abs()).abs().max().item() if kk else 0.0}
         out[f"{m}x{n}_k{k}_p{p}_{engine}"] = res
+    ctx.set_fp64_engine("i8")
+    # row-sharded CQRRPT (sketch + Gram allreduce, R / J / rank replicated) == single-GPU CQRRPT on the same matrix and state
+    for (m, n, engine) in [(40000, 200, "dmma"), (65536, 384, "i8")]:
+        ctx.set_fp64_engine(engine)
+        g = torch.Generator(device="cuda").manual_seed(77)
+        A_full = rl.to_f(torch.randn((m, n), dtype=torch.float64, device="cuda", generator=g))
+        A_full *= (1.0 + torch.arange(n, device="cuda", dtype=torch.float64))[None, :] ** -1.0
+        dist.broadcast(A_full.t(), src=0)
+        r0, r1 = rl.shard_rows(m, world, rank)
+        A_loc = rl.to_f(A_full[r0:r1].clone())
+        A_one = A_full.clone()
+        alg = rl.CQRRPT(False, None)
+        ctx.set_shard(r0, m)
+        st = rl.RNGState(5)
+        rc, R, J = alg.call(ctx, A_loc, 1.5, st)
+        rk = alg.rank
+        ctx.clear_shard()
+        st1 = rl.RNGState(5)
+        rc1, R1, J1 = alg.call(ctx, A_one, 1.5, st1)
+        out[f"cqrrpt_{m}x{n}_{engine}"] = {
+            "rc": [rc, rc1], "k": [rk, alg.rank], "state_equal": st == st1, "J_equal": bool(torch.equal(J, J1)),
+            "R_rel": ((R - R1).abs().max() / R1.abs().max()).item(),
+            "Q_abs": (A_loc[:, :rk] - A_one[r0:r1, :rk]).abs().max().item()}
     ctx.set_fp64_engine("i8")
     gathered = [None] * world
     dist.all_gather_object(gathered, out)

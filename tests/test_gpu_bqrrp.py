@@ -131,3 +131,24 @@ def test_bqrrp_large_property(ctx):
     dg = R.diagonal().abs()
     blocks = dg.view(-1, b).max(dim=1).values
     assert bool((blocks[1:] <= blocks[:-1] * 1.5).all())
+
+
+@pytest.mark.parametrize("qr_tall", ["geqrf", "cholqr"])
+def test_bqrrp_engine_trailing_update_vs_oracle(ctx, qr_tall):
+    """the trailing update only runs on the int8 digit-slice engine when rows - k >= 8192 (bqrrp.cu), which no r1 test
+    reached.  20000 x 768, b = 256: the first two panels update 19744 / 19488 rows on tcgen05.  Against the ORACLE (numpy/LAPACK restatement
+    of rl_bqrrp.hh) on the same input and state: code, rank, state and pivots exact; R and tau to 1e-9; the reference's eps^0.75 test."""
+    m, n, b = 20000, 768, 256
+    A, st = O.gen_poly_mat(m, n, n, 1.0e4, 2.0, O.RNGState(0))
+    c = dict(b=b, qrcp_wide=0, qr_tall=1 if qr_tall == "cholqr" else 0, d_factor=1.0, n=n, dtype=np.float64)
+    rc, rank, F, tau, J, s = _run(ctx, A, c, st)
+    o = O.BQRRP(b, "luqr", qr_tall)
+    rc2, F2, tau2, J2, st2 = o.call(A, 1.0, O.RNGState(st.key, st.counter))
+    assert (rc, rank) == (rc2, o.rank)
+    assert list(s.words()) == list(st2.words())
+    assert np.array_equal(J, J2), "pivot vector differs from the oracle's"
+    sc = np.abs(np.diag(F2)).max()
+    assert np.abs(np.triu(F)[:n, :n] - np.triu(F2)[:n, :n]).max() <= 1e-9 * sc
+    assert np.abs(tau - tau2).max() <= 1e-9
+    e = geqp3_format_invariants(A, F, tau, J, rank)
+    assert max(e) <= np.finfo(np.float64).eps ** 0.75, e

@@ -183,3 +183,28 @@ def test_cqrrpt_i8_engine(ctx, dtype, m, n):
     Jt = torch.from_numpy(J1 - 1).cuda()
     E = A0[rows][:, Jt].double() - Q1[rows].double() @ R1.double()
     assert float(E.norm() / A0[rows].double().norm()) <= eps ** 0.75
+
+
+@pytest.mark.parametrize("cond", [1.0e2, 1.0e10])
+def test_cqrrpt_engine_vs_oracle_blocked_sizes(ctx, cond):
+    """CQRRPT on the int8 engine against the ORACLE (not the repo's own DMMA path) at n > 300, where the blocked
+    Cholesky and the in-place product with the explicit inverse R^-1 run (drivers.cu: tall_right_solve / tall_gram_upper), with a
+    well- and an ill-conditioned sketch factor (cond(A) = 1e10: R^-1 has entries ~1e10, the stress case for the explicit inverse).
+    Pivots, rank, code, state exact; R to 1e-8 relative; the reference's three eps^0.75 measures (test_cqrrpt.cc:98-104) computed in numpy."""
+    m, n = 40000, 640
+    A, st = O.gen_poly_mat(m, n, n, cond, 2.0, O.RNGState(0))
+    alg = rl.CQRRPT(False, None)
+    alg.nnz = 2
+    Ad = dev(A)
+    s = rl.RNGState(st.key, st.counter)
+    rc, R, J = alg.call(ctx, Ad, 1.25, s)
+    o = O.CQRRPT(np.finfo(np.float64).eps ** 0.85, nnz=2)
+    rc2, Q2, R2, J2, st2 = o.call(A, 1.25, O.RNGState(st.key, st.counter))
+    assert (rc, alg.rank) == (rc2, o.rank)
+    assert list(s.words()) == list(st2.words())
+    Q, R, J = host(Ad), host(R), J.cpu().numpy()
+    r = alg.rank
+    assert np.array_equal(J[:r], np.asarray(J2)[:r]), "pivot vector differs from the oracle's"
+    assert np.abs(R[:r] - R2[:r]).max() <= 1e-8 * np.abs(R2).max()
+    e = qr_invariants(A, Q, R, J, r)
+    assert max(e) <= np.finfo(np.float64).eps ** 0.75, e

@@ -239,6 +239,58 @@ def test_rsvd_i8_engine_vs_oracle(ctx, m, n, k, p, digits):
     assert np.linalg.norm(U.T @ U - np.eye(kk)) <= EPS ** 0.625 and np.linalg.norm(V.T @ V - np.eye(kk)) <= EPS ** 0.625
 
 
+@pytest.mark.parametrize("graded", [False, True])
+@pytest.mark.parametrize("k,p", [(64, 0), (64, 3), (128, 2), (256, 0), (256, 2), (256, 3)])
+def test_rsvd_headline_engine_path_vs_oracle(ctx, k, p, graded):
+    """The code path every BASELINE config takes on the int8 engine (k >= 64, m >= 16384): Gram matrix fused into the A^T Y launch,
+    R folded into the next product inside RS, U = Y (R^-1 W) on the engine (drivers.cu: tall_tn_gram / rs_call / rsvd_single_block_fused).
+    Planted sigma_i = i^-2 (gen_poly_mat, cond 2025) and a column-graded variant (columns scaled over 12 decades: the worst case of the
+    per-row digit scaling).  Same-operator rule: sigma 1e-10 relative to sigma_1, residual within 1e-10, subspace sin 1e-9, codes/state equal."""
+    m, n = 32768, 512
+    A, st0 = poly(m, n, n)
+    if graded:
+        A = np.asfortranarray(A * np.logspace(0, -12, n)[None, :])
+    Ad = dev(A)
+    st_d = rl.RNGState(st0.key, st0.counter)
+    *_, RSVD = _stack(p, 1, k)
+    o = O.StackOpts(p, 1, k, O.STAB_CHOLQRQ, O.STAB_CHOLQRQ, O.STAB_CHOLQRQ)
+    *_, rsvd_o = O.make_stack(o)
+    Om_dev = _device_operator(ctx, m, n, k, p, st_d)
+    s = st_d.copy()
+    rc, kk, U, S, V = RSVD.call(ctx, Ad, k, 0.0, s)
+    rc_o, kk_o, U_o, S_o, V_o, s_o = rsvd_o.call(A, k, 0.0, st0.copy(), omega_override=Om_dev)
+    assert (rc, kk) == (rc_o, kk_o) and s.counter == s_o.counter and s.key == s_o.key
+    if kk == 0:
+        return
+    U, S, V = host(U)[:, :kk], S.cpu().numpy()[:kk], host(V)[:, :kk]
+    nrmA = np.linalg.norm(A)
+    assert np.abs(S - S_o).max() <= 1e-10 * S_o[0]
+    assert abs(np.linalg.norm(A - (U * S) @ V.T) - np.linalg.norm(A - (U_o * S_o) @ V_o.T)) <= 1e-10 * nrmA
+    # subspaces: compare the part of the basis whose singular values are resolved at 1e-10 (directions below that are round-off
+    # in the reference as well); with the graded matrix the trailing directions carry sigma ~ 1e-12 sigma_1
+    r = int(np.sum(S_o > 1e-6 * S_o[0])) if graded else kk
+    assert _ref.subspace_sin(U_o[:, :r], U[:, :r]) <= (1e-6 if graded else 1e-9)
+    assert np.linalg.norm(U.T @ U - np.eye(kk)) <= EPS ** 0.625 and np.linalg.norm(V.T @ V - np.eye(kk)) <= EPS ** 0.625
+
+
+def test_rsvd_nonfinite_input_propagates(ctx):
+    """a NaN / Inf entry must not come back as plausible finite factors.  The reference's BLAS path propagates the NaN into the
+    Gram matrix, potrf fails, RF returns 2 and QB/RSVD report k = 0 (rl_qb.hh:191-197).  Both engines must do the same."""
+    m, n, k = 20000, 128, 64
+    A, st0 = poly(m, n, n)
+    for bad in (np.nan, np.inf):
+        Ab = A.copy(order="F")
+        Ab[1234, 17] = bad
+        for engine in ("dmma", "i8"):
+            ctx.set_fp64_engine(engine)
+            try:
+                *_, RSVD = _stack(2, 1, k)
+                rc, kk, U, S, V = RSVD.call(ctx, dev(Ab), k, 0.0, rl.RNGState(st0.key, st0.counter))
+            finally:
+                ctx.set_fp64_engine("i8")
+            assert kk == 0 or not np.isfinite(S.cpu().numpy()).all(), (bad, engine, rc, kk)
+
+
 def test_rsvd_f32(ctx):
     m, n, k = 2000, 128, 16
     A, st0 = poly(m, n, n, dtype=np.float32)

@@ -17,12 +17,16 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def test_sharded_rsvd_matches_single_gpu():
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
            "--master-port", "29533", os.path.join(ROOT, "tests", "_multi_worker.py")]
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
     line = [ln for ln in r.stdout.splitlines() if ln.startswith("MULTI_RESULT ")]
     assert line, r.stdout[-2000:] + r.stderr[-4000:]
     for per_rank in json.loads(line[0][len("MULTI_RESULT "):]):
         for name, res in per_rank.items():
             assert res["rc"][0] == res["rc"][1] and res["k"][0] == res["k"][1], (name, res)
             assert res["state_equal"], (name, res)
+            if name.startswith("cqrrpt"):
+                # the sharded sketch sums each shard's rows first (different summation order): pivots must still be identical
+                assert res["J_equal"] and res["R_rel"] <= 1e-9 and res["Q_abs"] <= 1e-8, (name, res)
+                continue
             # int8 digit-slice engine: 46 bits below each scaling group's maximum, and the groups differ between the two runs
             assert res["S_rel"] <= (1e-11 if name.endswith("i8") else 1e-12) and res["V_abs"] <= 1e-9 and res["U_abs"] <= 1e-9, (name, res)

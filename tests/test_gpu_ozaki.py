@@ -95,3 +95,49 @@ def test_i8_gemm_f32_storage(ctx, shape):
     refz = A.double().t() @ Y.double()
     boundz = A.double().abs().t() @ Y.double().abs()
     assert ((Z.double() - refz).abs() / boundz).max().item() <= 2e-7
+
+
+@pytest.mark.parametrize("digits", [6, 7])
+def test_i8_gemm_column_graded_first_operand_is_normwise(ctx, digits):
+    """the per-row scale of the NN product cannot remove a grading ALONG a row.  With the columns of A spread over
+    14 decades an entry 1e-14 below its row maximum keeps none of its bits: the scheme is fp64-accurate NORM-wise per row
+    (|C - AB|_ij <= K 2^-(8S-3) max_k|a_ik| max_k|b_kj|), not component-wise in |A||B|.  This test pins exactly that statement: the
+    normwise bound holds, and the componentwise-by-|A||B| error of a product that is dominated by the small columns is NOT small."""
+    m, K, N = 20000, 256, 128
+    A = _mk(m, K, 21, scale_cols=False)
+    A = rl.to_f(A * torch.pow(10.0, torch.linspace(0, -14, K, dtype=torch.float64, device="cuda"))[None, :])
+    B = _mk(K, N, 22)
+    ctx.set_i8_digits(digits)
+    C = rl.gemm(ctx, False, False, 1.0, A, B, engine="i8")
+    ctx.set_i8_digits(0)
+    ref = A @ B
+    bound = A.abs().max(dim=1).values[:, None] * B.abs().max(dim=0).values[None, :] * K
+    P = 8 * digits - 2
+    assert ((C - ref).abs() / bound).max().item() <= 2.0 ** -(P - 1)
+    # a right-hand side that only sees the tiny columns: the product is ~1e-14 of the row scale and inherits the absolute error
+    B2 = B.clone()
+    B2[: K - 8] = 0
+    C2 = rl.gemm(ctx, False, False, 1.0, A, B2, engine="i8")
+    ref2 = A @ B2
+    bound2 = A.abs().max(dim=1).values[:, None] * B2.abs().max(dim=0).values[None, :] * K
+    assert ((C2 - ref2).abs() / bound2).max().item() <= 2.0 ** -(P - 1)
+
+
+@pytest.mark.parametrize("bad", [float("nan"), float("inf")])
+def test_i8_gemm_nonfinite_propagates(ctx, bad):
+    """a NaN / Inf entry of an operand must reach the output (the reference BLAS path propagates it), not turn into finite
+    garbage.  Rows (NN) / columns (TN) that contain the entry come back non-finite; the others stay accurate."""
+    m, K, N = 20000, 256, 128
+    A = _mk(m, K, 31)
+    B = _mk(K, N, 32)
+    A[777, 5] = bad
+    C = rl.gemm(ctx, False, False, 1.0, A, B, engine="i8")
+    assert not torch.isfinite(C[777]).any()
+    ok = torch.ones(m, dtype=torch.bool, device="cuda"); ok[777] = False
+    Az = A.clone(); Az[777] = 0
+    assert ((C[ok] - (Az @ B)[ok]).abs().max() / (Az.abs() @ B.abs()).max()).item() <= 2e-12
+    Y = _mk(m, N, 33)
+    Z = rl.gemm(ctx, True, False, 1.0, A, Y, engine="i8")
+    assert not torch.isfinite(Z[5]).any()
+    okc = torch.ones(K, dtype=torch.bool, device="cuda"); okc[5] = False
+    assert torch.isfinite(Z[okc]).all()
