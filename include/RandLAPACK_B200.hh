@@ -12,6 +12,7 @@
 //   RandLAPACK::RSVDalg / RSVD        drivers/rl_rsvd.hh:15-154            rlb200::RSVD<T>
 //   RandLAPACK::CQRRPTalg / CQRRPT    drivers/rl_cqrrpt.hh:20-391          rlb200::CQRRPT<T>
 //   RandLAPACK::BQRRPalg / BQRRP      drivers/rl_bqrrp.hh:19-665           rlb200::BQRRP<T>
+//   RandLAPACK::BQRRP_GPU_alg / BQRRP_GPU  drivers/rl_bqrrp_gpu.hh:27-942   rlb200::BQRRP_GPU<T>   (device pointers, sketch as input)
 //
 // Two modes:
 //  * default: self-contained (no reference headers needed); `rlb200::RNGState` stands in for RandBLAS::RNGState.
@@ -97,11 +98,13 @@ template <> struct abi<double> {
     static constexpr auto stab = rlb200_stab_f64_dev; static constexpr auto rs = rlb200_rs_f64_dev; static constexpr auto rf = rlb200_rf_f64_dev;
     static constexpr auto qb = rlb200_qb_f64_dev; static constexpr auto rsvd_host = rlb200_rsvd_f64_host;
     static constexpr auto cqrrpt_host = rlb200_cqrrpt_f64_host; static constexpr auto bqrrp_host = rlb200_bqrrp_f64_host;
+    static constexpr auto bqrrp_dev_sk = rlb200_bqrrp_f64_dev_sk;
 };
 template <> struct abi<float> {
     static constexpr auto stab = rlb200_stab_f32_dev; static constexpr auto rs = rlb200_rs_f32_dev; static constexpr auto rf = rlb200_rf_f32_dev;
     static constexpr auto qb = rlb200_qb_f32_dev; static constexpr auto rsvd_host = rlb200_rsvd_f32_host;
     static constexpr auto cqrrpt_host = rlb200_cqrrpt_f32_host; static constexpr auto bqrrp_host = rlb200_bqrrp_f32_host;
+    static constexpr auto bqrrp_dev_sk = rlb200_bqrrp_f32_dev_sk;
 };
 
 // device buffer staged from / to a host pointer
@@ -377,6 +380,47 @@ public:
     std::vector<long> times;
     Subroutines::QRCPWide qrcp_wide;
     Subroutines::QRTall qr_tall;
+private:
+    Context* ctx_;
+};
+
+// BQRRP_GPU (rl_bqrrp_gpu.hh:27-942): same constructor (time_subroutines, b_sz), public fields and call signature.  As in the
+// reference ALL pointers are DEVICE pointers and the d x n sketch A_sk is an input (overwritten).  qr_tall: geqrf (ctor default,
+// rl_bqrrp_gpu.hh:86) or cholqr.  The reference's base class lives in a header that needs its CUDA build (USE_CUDA + blaspp's device
+// API); define RLB200_WITH_RANDLAPACK_GPU after including it to derive from RandLAPACK::BQRRP_GPU_alg.
+struct BQRRPGPUSubroutines {
+    enum QRTall { cholqr = RLB200_QRTALL_CHOLQR, geqrf = RLB200_QRTALL_GEQRF };
+};
+template <typename T>
+class BQRRP_GPU
+#if defined(RLB200_WITH_RANDLAPACK) && defined(RLB200_WITH_RANDLAPACK_GPU)
+    : public RandLAPACK::BQRRP_GPU_alg<T, r123::Philox4x32>
+#endif
+{
+public:
+    using GPUSubroutine = BQRRPGPUSubroutines;
+    BQRRP_GPU(bool time_subroutines, int64_t b_sz) : BQRRP_GPU(default_context(), time_subroutines, b_sz) {}
+    BQRRP_GPU(Context& c, bool time_subroutines, int64_t b_sz)
+        : timing(time_subroutines), rank(0), block_size(b_sz), tol(std::numeric_limits<T>::epsilon()), qr_tall(GPUSubroutine::geqrf), ctx_(&c) {
+        if (b_sz <= 0) throw Error(RLB200_ERR_ARG, "BQRRP_GPU block size b_sz must be > 0");
+    }
+    virtual ~BQRRP_GPU() {}
+    int call(int64_t m, int64_t n, T* A, int64_t lda, T* A_sk, int64_t d, T* tau, int64_t* J)
+#if defined(RLB200_WITH_RANDLAPACK) && defined(RLB200_WITH_RANDLAPACK_GPU)
+        override
+#endif
+    {
+        int64_t r = 0;
+        int rc = ctx_->check(detail::abi<T>::bqrrp_dev_sk(ctx_->get(), m, n, A, lda, A_sk, d, block_size, (int)qr_tall, tau, J, &r));
+        rank = r;
+        return rc;
+    }
+    bool timing;
+    state_t state;
+    int64_t rank, block_size;
+    std::vector<long> times;
+    T tol;
+    GPUSubroutine::QRTall qr_tall;
 private:
     Context* ctx_;
 };

@@ -180,6 +180,9 @@ RLB200_API int rlb200_gemm_f32_i8_dev(rlb200_ctx* ctx, int transa, int transb, i
  * fp64 pipe): RLB200_FP64_I8SLICES (default) or RLB200_FP64_DMMA. */
 enum { RLB200_FP64_DMMA = 0, RLB200_FP64_I8SLICES = 1 };
 RLB200_API int rlb200_set_fp64_engine(rlb200_ctx* ctx, int engine);
+/* Fused engine (default on): tall products whose shapes allow it (second dimension >= 96) produce the digits of the tall operand inside
+ * the tensor-core kernel (one fp64 read of the data matrix per pass, no digit round trip through HBM); off = always stage the digits. */
+RLB200_API int rlb200_set_i8_fused(rlb200_ctx* ctx, int on);
 /* Digits per value of the int8-slice engine: 0 = default (6 for fp64 storage: 46 bits; 4 for fp32: 30 bits), else 3..7. */
 RLB200_API int rlb200_set_i8_digits(rlb200_ctx* ctx, int digits);
 
@@ -260,6 +263,15 @@ RLB200_API int rlb200_bqrrp_f64_dev(rlb200_ctx* ctx, int64_t m, int64_t n, doubl
                          int qrcp_wide, int qr_tall, double* tau_dev, int64_t* J_dev, int64_t* rank, uint32_t state[6]);
 RLB200_API int rlb200_bqrrp_f32_dev(rlb200_ctx* ctx, int64_t m, int64_t n, float* A_dev, int64_t lda, float d_factor, int64_t block_size,
                          int qrcp_wide, int qr_tall, float* tau_dev, int64_t* J_dev, int64_t* rank, uint32_t state[6]);
+/* BQRRP_GPU_alg<T,RNG>::call(m, n, A, lda, A_sk, d, tau, J) (RandLAPACK/drivers/rl_bqrrp_gpu.hh:27-43, 122-133; body :152-942): every
+ * pointer is a DEVICE pointer and the d x n sketch A_sk (leading dimension d, d >= block_size) is an INPUT - formed by the caller, e.g. as
+ * S * A with S = fill_dense(DenseDist(d, m)) (test/drivers/test_bqrrp_gpu.cu:91-103) - and is overwritten.  qrcp_wide is LUQR (the only
+ * choice the reference's GPU driver offers, :54); qr_tall: RLB200_QRTALL_GEQRF (its ctor default, :86) or RLB200_QRTALL_CHOLQR.
+ * Outputs as rlb200_bqrrp_*_dev. */
+RLB200_API int rlb200_bqrrp_f64_dev_sk(rlb200_ctx* ctx, int64_t m, int64_t n, double* A_dev, int64_t lda, double* A_sk_dev, int64_t d,
+                            int64_t block_size, int qr_tall, double* tau_dev, int64_t* J_dev, int64_t* rank);
+RLB200_API int rlb200_bqrrp_f32_dev_sk(rlb200_ctx* ctx, int64_t m, int64_t n, float* A_dev, int64_t lda, float* A_sk_dev, int64_t d,
+                            int64_t block_size, int qr_tall, float* tau_dev, int64_t* J_dev, int64_t* rank);
 /* Host-pointer form (the CPU reference's calling convention): A, tau, J are HOST buffers. */
 RLB200_API int rlb200_bqrrp_f64_host(rlb200_ctx* ctx, int64_t m, int64_t n, double* A, int64_t lda, double d_factor, int64_t block_size,
                           int qrcp_wide, int qr_tall, double* tau, int64_t* J, int64_t* rank, uint32_t state[6]);

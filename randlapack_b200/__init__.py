@@ -148,6 +148,11 @@ class Context:
         """Digits per value of the int8-slice engine: 0 = default (6 for fp64 storage, 4 for fp32), else 3..7 (8*digits - 2 bits)."""
         self.check(self._lib.rlb200_set_i8_digits(self._h, int(digits)))
 
+    def set_i8_fused(self, on):
+        """True (default): tall products whose shapes allow it slice the tall operand inside the tensor-core kernel (ozaki_fused.cu);
+        False: always stage the digits in HBM (ozaki.cu)."""
+        self.check(self._lib.rlb200_set_i8_fused(self._h, 1 if on else 0))
+
     # ---- row sharding over torch.distributed -------------------------------------------------
     def set_shard(self, row_offset, m_global, group=None):
         """This rank holds rows [row_offset, row_offset + m_local) of an m_global-row A.  Gram / B^T / norm
@@ -583,6 +588,23 @@ class BQRRP:
         rc = ctx.check(fn(ctx._h, m, n, A.data_ptr(), _ld(A), d_factor, self.block_size, self.qrcp_wide, self.qr_tall, tau.data_ptr(),
                           J.data_ptr(), ctypes.byref(rank), w))
         state.assign(w)
+        self.rank = rank.value
+        return rc, tau, J
+
+    def call_sk(self, ctx: Context, A, A_sk, tau=None, J=None):
+        """BQRRP_GPU::call(m, n, A, lda, A_sk, d, tau, J) (rl_bqrrp_gpu.hh:122-133): the d x n sketch A_sk (device, column-major) is an
+        input and is overwritten; LUQR pivoting; qr_tall = this object's (QRTALL_GEQRF or QRTALL_CHOLQR)."""
+        torch = _torch()
+        assert _is_f(A) and _is_f(A_sk) and A_sk.dtype == A.dtype
+        m, n = A.shape
+        d = A_sk.shape[0]
+        assert A_sk.shape[1] == n and _ld(A_sk) == d
+        tau = torch.zeros(n, dtype=A.dtype, device=A.device) if tau is None else tau
+        J = torch.zeros(n, dtype=torch.int64, device=A.device) if J is None else J
+        rank = ctypes.c_int64(0)
+        fn = getattr(ctx._lib, f"rlb200_bqrrp_{_suffix(A.dtype)}_dev_sk")
+        rc = ctx.check(fn(ctx._h, m, n, A.data_ptr(), _ld(A), A_sk.data_ptr(), d, self.block_size, self.qr_tall, tau.data_ptr(), J.data_ptr(),
+                          ctypes.byref(rank)))
         self.rank = rank.value
         return rc, tau, J
 

@@ -289,13 +289,14 @@ int getrf_pivots(Ctx* ctx, int64_t m, int64_t n, T* A, int64_t lda, void* ws, st
 // ---- the driver --------------------------------------------------------------------------------------------------------------
 template <typename T>
 int bqrrp_call(Ctx* ctx, int64_t m, int64_t n, T* A, int64_t lda, T d_factor, int64_t block_size, int qrcp_wide, int qr_tall, T* tau,
-               int64_t* J_dev, int64_t* rank_out, uint32_t state[6]) {
+               int64_t* J_dev, int64_t* rank_out, uint32_t state[6], T* A_sk_ext, int64_t d_ext) {
     // rl_bqrrp.hh:172-178 and the constructor's requirement :66
     RLB_REQUIRE(ctx, block_size > 0);
     RLB_REQUIRE(ctx, m >= 0);
     RLB_REQUIRE(ctx, n >= 0);
     RLB_REQUIRE(ctx, lda >= m);
-    RLB_REQUIRE(ctx, d_factor >= (T)1.0);
+    RLB_REQUIRE(ctx, A_sk_ext != nullptr || d_factor >= (T)1.0);
+    RLB_REQUIRE(ctx, A_sk_ext != nullptr || state != nullptr);
     RLB_REQUIRE(ctx, !(A == nullptr && m > 0 && n > 0));
     RLB_REQUIRE(ctx, !(tau == nullptr && n > 0));
     RLB_REQUIRE(ctx, !(J_dev == nullptr && n > 0));
@@ -308,12 +309,14 @@ int bqrrp_call(Ctx* ctx, int64_t m, int64_t n, T* A, int64_t lda, T d_factor, in
     int64_t rows = m, cols = n, curr_sz = 0, b_sz = block_size;
     const int64_t maxiter = (int64_t)std::ceil((T)std::min(m, n) / (T)b_sz);            // :201
     const int64_t b_const = b_sz;
-    const int64_t d = (int64_t)(d_factor * (T)b_sz);                                    // :205
+    // BQRRP_GPU::call takes the d x n sketch from the caller (rl_bqrrp_gpu.hh:122-133, 170); BQRRP::call forms it (:205, 309-312)
+    const int64_t d = A_sk_ext ? d_ext : (int64_t)(d_factor * (T)b_sz);
     int64_t sd = d;
-    RLB_REQUIRE(ctx, d <= m);   // DenseDist(d, m) is read as a wide operator (rl_bqrrp.hh:309-312)
+    RLB_REQUIRE(ctx, d >= b_sz);
+    RLB_REQUIRE(ctx, A_sk_ext != nullptr || d <= m);   // DenseDist(d, m) is read as a wide operator (rl_bqrrp.hh:309-312)
 
     ArenaScope as(ctx);
-    T* A_sk0 = as.take<T>((size_t)d * n); RLB_ALLOC_(A_sk0);
+    T* A_sk0 = A_sk_ext ? A_sk_ext : as.take<T>((size_t)d * n); RLB_ALLOC_(A_sk0);
     T* A_sk_trans = qrcp_wide == 0 ? as.take<T>((size_t)n * d) : nullptr; if (qrcp_wide == 0) RLB_ALLOC_(A_sk_trans);
     T* R_tall = as.take<T>((size_t)b_const * b_const); RLB_ALLOC_(R_tall);
     T* T_dat = as.take<T>((size_t)b_const * b_const); RLB_ALLOC_(T_dat);
@@ -339,7 +342,7 @@ int bqrrp_call(Ctx* ctx, int64_t m, int64_t n, T* A, int64_t lda, T d_factor, in
     };
 
     // Gaussian sketch (:309-312)
-    RLB_CHECK(bqrrp_sketch<T>(ctx, d, m, n, A, lda, A_sk0, state));
+    if (!A_sk_ext) RLB_CHECK(bqrrp_sketch<T>(ctx, d, m, n, A, lda, A_sk0, state));
     T* A_sk = A_sk0;
     T* A_work = A;
 
@@ -490,7 +493,7 @@ int bqrrp_call(Ctx* ctx, int64_t m, int64_t n, T* A, int64_t lda, T d_factor, in
     template int make_unit_lower<T>(Ctx*, int64_t, const T*, int64_t, T*, int64_t);                                  \
     template int larft_from_gram<T>(Ctx*, int64_t, const T*, int64_t, const T*, T*, int64_t);                        \
     template int set_upper_diag<T>(Ctx*, int64_t, T*, int64_t, T, bool);                                             \
-    template int bqrrp_call<T>(Ctx*, int64_t, int64_t, T*, int64_t, T, int64_t, int, int, T*, int64_t*, int64_t*, uint32_t*);
+    template int bqrrp_call<T>(Ctx*, int64_t, int64_t, T*, int64_t, T, int64_t, int, int, T*, int64_t*, int64_t*, uint32_t*, T*, int64_t);
 INST(double)
 INST(float)
 

@@ -47,6 +47,7 @@ int rlb200_destroy(rlb200_ctx* ctx) {
     if (ctx->ws) cudaFree(ctx->ws);
     if (ctx->hbox) cudaFreeHost(ctx->hbox);
     oz_cache_destroy(ctx);
+    oz2_cache_destroy(ctx);
     if (ctx->aux_stream) { cudaStreamSynchronize(ctx->aux_stream); cudaStreamDestroy(ctx->aux_stream); }
     for (auto& e : ctx->aux_ev) if (e) cudaEventDestroy(e);
     for (auto& t : ctx->timers) { if (t.e0) cudaEventDestroy(t.e0); if (t.e1) cudaEventDestroy(t.e1); }
@@ -137,16 +138,28 @@ int rlb200_gemm_f64_i8_dev(rlb200_ctx* ctx, int transa, int transb, int64_t m, i
     // diagnostics: treat the first operand as constant across calls (what the drivers declare through OzConstScope)
     static const bool assume_const = getenv("RLB200_OZ_ASSUME_CONST") != nullptr;
     ctx->oz_const_ptr = assume_const ? (const void*)A : nullptr;
-    if (!transa && !transb) return ozaki_gemm_nn<double>(ctx, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc);
-    if (transa && !transb) return ozaki_gemm_tn<double>(ctx, k, m, n, alpha, A, lda, B, ldb, beta, C, ldc);
+    if (!transa && !transb) {
+        if (ozaki2_nn_ok(ctx, m, n, k, A, lda * 8, C)) return ozaki2_gemm_nn<double>(ctx, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc);
+        return ozaki_gemm_nn<double>(ctx, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc);
+    }
+    if (transa && !transb) {
+        if (ozaki2_tn_ok(ctx, k, m, n, A, lda * 8)) return ozaki2_gemm_tn<double>(ctx, k, m, n, alpha, A, lda, B, ldb, beta, C, ldc);
+        return ozaki_gemm_tn<double>(ctx, k, m, n, alpha, A, lda, B, ldb, beta, C, ldc);
+    }
     ctx->err = "only the NN (tall) and TN (long contraction) shapes of the path are offered";
     return RLB200_ERR_UNSUPPORTED;
 }
 int rlb200_gemm_f32_i8_dev(rlb200_ctx* ctx, int transa, int transb, int64_t m, int64_t n, int64_t k, float alpha, const float* A, int64_t lda,
                            const float* B, int64_t ldb, float beta, float* C, int64_t ldc) {
     CTX_OK(ctx); RLB_CHECK(bind(ctx));
-    if (!transa && !transb) return ozaki_gemm_nn<float>(ctx, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc);
-    if (transa && !transb) return ozaki_gemm_tn<float>(ctx, k, m, n, alpha, A, lda, B, ldb, beta, C, ldc);
+    if (!transa && !transb) {
+        if (ozaki2_nn_ok(ctx, m, n, k, A, lda * 4, C)) return ozaki2_gemm_nn<float>(ctx, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc);
+        return ozaki_gemm_nn<float>(ctx, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc);
+    }
+    if (transa && !transb) {
+        if (ozaki2_tn_ok(ctx, k, m, n, A, lda * 4)) return ozaki2_gemm_tn<float>(ctx, k, m, n, alpha, A, lda, B, ldb, beta, C, ldc);
+        return ozaki_gemm_tn<float>(ctx, k, m, n, alpha, A, lda, B, ldb, beta, C, ldc);
+    }
     ctx->err = "only the NN (tall) and TN (long contraction) shapes of the path are offered";
     return RLB200_ERR_UNSUPPORTED;
 }
@@ -156,6 +169,7 @@ int rlb200_set_fp64_engine(rlb200_ctx* ctx, int engine) {
     ctx->fp64_engine = engine;
     return 0;
 }
+int rlb200_set_i8_fused(rlb200_ctx* ctx, int on) { CTX_OK(ctx); ctx->i8_fused = on != 0; return 0; }
 int rlb200_set_i8_digits(rlb200_ctx* ctx, int digits) {
     CTX_OK(ctx);
     RLB_REQUIRE(ctx, digits == 0 || (digits >= 3 && digits <= 7));
@@ -260,6 +274,15 @@ int rlb200_set_i8_digits(rlb200_ctx* ctx, int digits) {
                                  int qrcp_wide, int qr_tall, T* tau_dev, int64_t* J_dev, int64_t* rank, uint32_t state[6]) {        \
         CTX_OK(ctx); RLB_CHECK(bind(ctx)); RLB_REQUIRE(ctx, state && rank);                                                         \
         return bqrrp_call<T>(ctx, m, n, A_dev, lda, d_factor, block_size, qrcp_wide, qr_tall, tau_dev, J_dev, rank, state);         \
+    }                                                                                                                               \
+    int rlb200_bqrrp_##SUF##_dev_sk(rlb200_ctx* ctx, int64_t m, int64_t n, T* A_dev, int64_t lda, T* A_sk_dev, int64_t d,           \
+                                    int64_t block_size, int qr_tall, T* tau_dev, int64_t* J_dev, int64_t* rank) {                   \
+        CTX_OK(ctx); RLB_CHECK(bind(ctx)); RLB_REQUIRE(ctx, rank != nullptr);                                                       \
+        RLB_REQUIRE(ctx, !(A_sk_dev == nullptr && m > 0 && n > 0));                                                                 \
+        RLB_REQUIRE(ctx, qr_tall == RLB200_QRTALL_GEQRF || qr_tall == RLB200_QRTALL_CHOLQR);                                        \
+        if (m == 0 || n == 0) { *rank = 0; return 0; }                                                                              \
+        return bqrrp_call<T>(ctx, m, n, A_dev, lda, (T)1, block_size, RLB200_QRCP_LUQR, qr_tall, tau_dev, J_dev, rank, nullptr,     \
+                             A_sk_dev, d);                                                                                          \
     }                                                                                                                               \
     int rlb200_bqrrp_##SUF##_host(rlb200_ctx* ctx, int64_t m, int64_t n, T* A, int64_t lda, T d_factor, int64_t block_size,         \
                                   int qrcp_wide, int qr_tall, T* tau, int64_t* J, int64_t* rank, uint32_t state[6]) {               \

@@ -63,6 +63,11 @@ struct Ctx {
     // the matrix a driver declared constant for the duration of a scope (OzConstScope) and its cached exponents
     const void* oz_const_ptr = nullptr;
     OzCacheEntry oz_row, oz_col;
+    // the same for the fused engine (ozaki_fused.cu): raw exponents, independent of the digit count
+    OzCacheEntry oz2_row, oz2_col;
+    // 1 (default): tall products whose shapes allow it run on the fused engine (digits of the tall operand produced inside the
+    // tensor-core kernel); 0: always the staged-digit engine (ozaki.cu)
+    int i8_fused = 1;
     // stats
     int64_t launches = 0;
     bool timers_on = false;

@@ -231,14 +231,19 @@ constexpr int64_t kI8MinRows = 16384;
 template <typename T>
 static int tall_nn(Ctx* ctx, int64_t m, int64_t N, int64_t K, double alpha, const T* A, int64_t lda, const T* B, int64_t ldb, double beta, T* C,
                    int64_t ldc) {
-    if (ctx->fp64_engine == RLB200_FP64_I8SLICES && m >= kI8MinRows) return ozaki_gemm_nn<T>(ctx, m, N, K, alpha, A, lda, B, ldb, beta, C, ldc);
+    if (ctx->fp64_engine == RLB200_FP64_I8SLICES && m >= kI8MinRows) {
+        if (ozaki2_nn_ok(ctx, m, N, K, A, lda * (int64_t)sizeof(T), C)) return ozaki2_gemm_nn<T>(ctx, m, N, K, alpha, A, lda, B, ldb, beta, C, ldc);
+        return ozaki_gemm_nn<T>(ctx, m, N, K, alpha, A, lda, B, ldb, beta, C, ldc);
+    }
     return gemm_nn<T>(ctx, m, N, K, alpha, A, lda, B, ldb, beta, C, ldc);
 }
 template <typename T>
 static int tall_tn(Ctx* ctx, int64_t m, int64_t N1, int64_t N2, double alpha, const T* A, int64_t lda, const T* B, int64_t ldb, double beta, T* C,
                    int64_t ldc, double* a_sumsq_out = nullptr) {
-    if (ctx->fp64_engine == RLB200_FP64_I8SLICES && m >= kI8MinRows)
+    if (ctx->fp64_engine == RLB200_FP64_I8SLICES && m >= kI8MinRows) {
+        if (ozaki2_tn_ok(ctx, m, N1, N2, A, lda * (int64_t)sizeof(T))) return ozaki2_gemm_tn<T>(ctx, m, N1, N2, alpha, A, lda, B, ldb, beta, C, ldc, a_sumsq_out);
         return ozaki_gemm_tn<T>(ctx, m, N1, N2, alpha, A, lda, B, ldb, beta, C, ldc, a_sumsq_out);
+    }
     return gemm_tn<T>(ctx, m, N1, N2, alpha, A, lda, B, ldb, beta, C, ldc, 0, a_sumsq_out);
 }
 
@@ -247,8 +252,12 @@ static int tall_tn(Ctx* ctx, int64_t m, int64_t N1, int64_t N2, double alpha, co
 // digits for fp64 (54 bits: the Gram matrix squares the conditioning and potrf must fail exactly where the reference's does).
 template <typename T>
 static int tall_tn_gram(Ctx* ctx, int64_t m, int64_t n, int64_t k, const T* A, int64_t lda, const T* Y, int64_t ldy, T* Z, int64_t ldz, T* G,
-                        double* a_sumsq_out = nullptr) {
+                        double* a_sumsq_out = nullptr, bool full_pairs = false) {
     if (ctx->fp64_engine == RLB200_FP64_I8SLICES && m >= kI8MinRows && k >= 64 && getenv("RLB200_NO_GRAM_FUSION") == nullptr) {
+        // fused engine: 7 digits are produced, the Gram tiles use all 28 digit pairs, the A^T Y tiles the 21 of the first 6 anti-diagonals
+        // unless full_pairs asks for all 28
+        if (ozaki2_tn_ok(ctx, m, n, k, A, lda * (int64_t)sizeof(T)))
+            return ozaki2_gemm_tn<T>(ctx, m, n, k, 1.0, A, lda, Y, ldy, 0.0, Z, ldz, a_sumsq_out, G, k, full_pairs);
         const int old = ctx->i8_digits;
         if (!old && sizeof(T) == 8) ctx->i8_digits = 7;
         const int rc = ozaki_gemm_tn<T>(ctx, m, n, k, 1.0, A, lda, Y, ldy, 0.0, Z, ldz, a_sumsq_out, false, G, k);
@@ -324,7 +333,8 @@ int rs_call(Ctx* ctx, int64_t m, int64_t n, const T* A, int64_t k, T* Omega, T* 
                 // stabilise Omega_1 = Q R implicitly: Omega = A^T Q = (A^T Omega_1) R^-1; Omega_1 itself is scratch (:130) and is never read again
                 // (the Gram matrix and A^T Omega_1 come out of one sweep; the Cholesky factor, and its failure code, follow)
                 Rfold = as_fold.take<T>(k * k); RLB_ALLOC(ctx, Rfold);
-                RLB_CHECK(tall_tn_gram<T>(ctx, m, n, k, A, m, Omega_1, m, Omega, n, Rfold));
+                // all digit pairs: Omega = (A^T Omega_1) R^-1 amplifies the error of A^T Omega_1 by cond(R) = cond(A Omega)
+                RLB_CHECK(tall_tn_gram<T>(ctx, m, n, k, A, m, Omega_1, m, Omega, n, Rfold, nullptr, /*full_pairs=*/true));
                 int rc = cholqr_finish<T>(ctx, k, o.cond_check, sharded, Rfold, nullptr);
                 if (rc) return rc < 0 ? rc : 1;
             } else {
@@ -523,8 +533,14 @@ static int rsvd_single_block_fused(Ctx* ctx, int64_t m, int64_t n, T* A, int64_t
     RLB_CHECK(trtri_upper<T>(ctx, (int)k, R, (int)k, Rinv));
     RLB_CHECK(gemm_nn<T>(ctx, k, k, k, 1.0, Rinv, k, W, k, 0.0, M, k));
     // U = Y (R^-1 W) in place (rl_rsvd.hh:148 with Q = Y R^-1 never formed); on the int8-slice engine when it is selected
-    if (ctx->fp64_engine == RLB200_FP64_I8SLICES && m >= kI8MinRows && k >= 64) RLB_CHECK(ozaki_gemm_nn<T>(ctx, m, k, k, 1.0, U, m, M, k, 0.0, U, m));
-    else RLB_CHECK(gemm_nn_inplace<T>(ctx, m, k, k, 1.0, U, m, M, k));
+    // (fp64: 7 digits - the columns of R^-1 W grow like cond(Y), and with 6 digits the orthogonality of U would stop at ~2e-10)
+    if (ctx->fp64_engine == RLB200_FP64_I8SLICES && m >= kI8MinRows && k >= 64) {
+        const int old = ctx->i8_digits;
+        if (!old && sizeof(T) == 8) ctx->i8_digits = 7;
+        const int rc_u = ozaki_gemm_nn<T>(ctx, m, k, k, 1.0, U, m, M, k, 0.0, U, m);
+        ctx->i8_digits = old;
+        RLB_CHECK(rc_u);
+    } else RLB_CHECK(gemm_nn_inplace<T>(ctx, m, k, k, 1.0, U, m, M, k));
     return 0;
 }
 

@@ -50,14 +50,26 @@ template <typename T>
 int ozaki_gemm_tn(Ctx* ctx, int64_t m, int64_t N1, int64_t N2, double alpha, const T* X, int64_t ldx, const T* Y, int64_t ldy, double beta,
                   T* C, int64_t ldc, double* x_sumsq_out = nullptr, bool upper_only = false, T* gram_out = nullptr, int64_t ldg = 0);
 void oz_cache_destroy(Ctx* ctx);
+// ---- the same products with the digit slicing of the tall operand fused into the tensor-core kernel (ozaki_fused.cu) ----------
+// C must not alias A.  *_ok: whether the fused engine takes the shape (otherwise call the staged engine above).
+bool ozaki2_nn_ok(Ctx* ctx, int64_t m, int64_t N, int64_t K, const void* A, int64_t lda_bytes, const void* C);
+bool ozaki2_tn_ok(Ctx* ctx, int64_t m, int64_t N1, int64_t N2, const void* X, int64_t ldx_bytes);
+template <typename T>
+int ozaki2_gemm_nn(Ctx* ctx, int64_t m, int64_t N, int64_t K, double alpha, const T* A, int64_t lda, const T* B, int64_t ldb, double beta,
+                   T* C, int64_t ldc);
+template <typename T>
+int ozaki2_gemm_tn(Ctx* ctx, int64_t m, int64_t N1, int64_t N2, double alpha, const T* X, int64_t ldx, const T* Y, int64_t ldy, double beta,
+                   T* C, int64_t ldc, double* x_sumsq_out = nullptr, T* gram_out = nullptr, int64_t ldg = 0, bool full_pairs = false);
+void oz2_cache_destroy(Ctx* ctx);
 // While alive, the first operand `A` of the tall products is known not to change: its row / column-chunk exponents are computed once
 // and reused by every pass (outermost scope wins; nested scopes on the same or another pointer are no-ops).
 struct OzConstScope {
     Ctx* ctx; bool owner;
     OzConstScope(Ctx* c, const void* A) : ctx(c), owner(c->oz_const_ptr == nullptr) {
-        if (owner) { c->oz_const_ptr = A; c->oz_row.valid = false; c->oz_col.valid = false; }
+        if (owner) { c->oz_const_ptr = A; invalidate(c); }
     }
-    ~OzConstScope() { if (owner) { ctx->oz_const_ptr = nullptr; ctx->oz_row.valid = false; ctx->oz_col.valid = false; } }
+    ~OzConstScope() { if (owner) { ctx->oz_const_ptr = nullptr; invalidate(ctx); } }
+    static void invalidate(Ctx* c) { c->oz_row.valid = false; c->oz_col.valid = false; c->oz2_row.valid = false; c->oz2_col.valid = false; }
 };
 
 // ---- sketch-apply (sketch.cu) -----------------------------------------------------------------------
@@ -129,8 +141,10 @@ int cqrrpt_call(Ctx* ctx, int64_t m, int64_t n, T* A, int64_t lda, T* R, int64_t
                 int64_t* rank_out, uint32_t state[6]);
 
 // BQRRP::call (rl_bqrrp.hh:154-665).  qrcp_wide: 0 luqr (default), 1 geqp3; qr_tall: 0 geqrf (default), 1 cholqr (+orhr_col), 2 geqrt.
+// A_sk_ext != nullptr: BQRRP_GPU::call (rl_bqrrp_gpu.hh:152-942) - the d_ext x n sketch (leading dimension d_ext) is the caller's and is
+// overwritten; d_factor and state are not used.
 template <typename T>
 int bqrrp_call(Ctx* ctx, int64_t m, int64_t n, T* A, int64_t lda, T d_factor, int64_t block_size, int qrcp_wide, int qr_tall, T* tau,
-               int64_t* J_dev, int64_t* rank_out, uint32_t state[6]);
+               int64_t* J_dev, int64_t* rank_out, uint32_t state[6], T* A_sk_ext = nullptr, int64_t d_ext = 0);
 
 }  // namespace rlb

@@ -25,369 +25,13 @@
 // 8 instructions per K step for S = 6 instead of 21, and the first-operand tile is read from shared memory 8 times, not 21.
 // Eight warps run the fp64 epilogue from tcgen05.ld.
 #include "drivers.cuh"
+#include "oz_common.cuh"
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
 #include <vector>
 
 namespace rlb {
-
-constexpr int OZ_KB = 32;          // K bytes (= int8 elements) per stage = one tcgen05.mma K step
-constexpr int OZ_BM = 128;         // UMMA M: tile rows of the first operand
-constexpr int OZ_BN = 64;          // tile rows of the second operand (per digit)
-constexpr int OZ_TILE_A = OZ_BM * OZ_KB;   // bytes of one digit tile of the first operand
-constexpr int OZ_TILE_B = OZ_BN * OZ_KB;
-constexpr int64_t OZ_CHUNK = 16384;        // rows per int32 accumulation group of the TN product (7 * 2^14 * 2^14 < 2^31)
-constexpr int64_t OZ_KMAX = 16384;         // largest K of one NN accumulation group
-constexpr int OZ_SMEM_BUDGET = 225 * 1024;
-
-template <int S>
-struct OzCfg {
-    static_assert(S >= 2 && S <= 7, "digits");
-    static constexpr int P = 8 * S - 2;                       // fixed-point bits below the group scale
-    static constexpr int STAGE_BYTES = S * (OZ_TILE_A + OZ_TILE_B);
-    static constexpr int STAGES = (OZ_SMEM_BUDGET / STAGE_BYTES) > 12 ? 12 : (OZ_SMEM_BUDGET / STAGE_BYTES);
-    static constexpr int ACC_COLS = S * OZ_BN;
-    static constexpr int TMEM_COLS = ACC_COLS <= 128 ? 128 : (ACC_COLS <= 256 ? 256 : 512);
-    // 0x80 in each of the S-1 low bytes: added as a bias it makes those bytes the unsigned digits d + 128, xor-ed it re-centres them
-    static constexpr unsigned long long LOWMASK = 0x8080808080808080ull >> (8 * (9 - S));
-};
-
-__device__ __forceinline__ uint32_t oz_smem(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-// ------------------------------------------------------------------------------------------------
-// exponents.  Stored value E = max(biased exponent - 1022, P - 1023): |x| < 2^E for the whole group, and 2^(P-E) is a normal
-// double (groups whose largest magnitude is below 2^(P-1023) keep fewer digits).
-// ------------------------------------------------------------------------------------------------
-template <typename T>
-__device__ __forceinline__ int oz_expfield(T x) { return (int)((__double_as_longlong((double)x) >> 52) & 0x7ff); }
-__device__ __forceinline__ int oz_exp_from_field(int f, int P) { return max(f - 1022, P - 1023); }
-
-// E_row[i] for rows [0, rows) of A (col-major, lda), K columns.  One thread per row, coalesced across rows.
-template <typename T>
-__global__ void __launch_bounds__(256) oz_rowexp_kernel(const T* __restrict__ A, int64_t lda, int64_t rows, int K, int P, int* __restrict__ E) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= rows) return;
-    int f = 0;
-    int c = 0;
-    for (; c + 4 <= K; c += 4) {
-        const T a0 = A[i + (int64_t)c * lda], a1 = A[i + (int64_t)(c + 1) * lda], a2 = A[i + (int64_t)(c + 2) * lda], a3 = A[i + (int64_t)(c + 3) * lda];
-        f = max(max(f, oz_expfield(a0)), max(oz_expfield(a1), max(oz_expfield(a2), oz_expfield(a3))));
-    }
-    for (; c < K; ++c) f = max(f, oz_expfield(A[i + (int64_t)c * lda]));
-    E[i] = oz_exp_from_field(f, P);
-}
-// E[chunk * ncols + c] over rows [chunk*L, (chunk+1)*L) of column c of X (col-major).  One warp per (column, chunk).
-// ss (optional): sum of squares of the same entries, same indexing (fixed summation order).
-template <typename T>
-__global__ void __launch_bounds__(256) oz_colexp_kernel(const T* __restrict__ X, int64_t ldx, int64_t rows, int ncols, int64_t L, int nchunks, int P,
-                                                        int* __restrict__ E, double* __restrict__ ss) {
-    const int lane = threadIdx.x & 31;
-    const int64_t w = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
-    if (w >= (int64_t)ncols * nchunks) return;
-    const int c = (int)(w % ncols), ch = (int)(w / ncols);
-    const int64_t r0 = (int64_t)ch * L, r1 = min(rows, r0 + L);
-    const T* x = X + (int64_t)c * ldx;
-    int f = 0;
-    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-    int64_t r = r0 + lane;
-    for (; r + 96 < r1; r += 128) {
-        const double a0 = (double)x[r], a1 = (double)x[r + 32], a2 = (double)x[r + 64], a3 = (double)x[r + 96];
-        f = max(max(f, oz_expfield(a0)), max(oz_expfield(a1), max(oz_expfield(a2), oz_expfield(a3))));
-        s0 = fma(a0, a0, s0); s1 = fma(a1, a1, s1); s2 = fma(a2, a2, s2); s3 = fma(a3, a3, s3);
-    }
-    for (; r < r1; r += 32) { const double a0 = (double)x[r]; f = max(f, oz_expfield(a0)); s0 = fma(a0, a0, s0); }
-    f = __reduce_max_sync(0xffffffffu, f);
-    if (ss) {
-        double sv = (s0 + s1) + (s2 + s3);
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) sv += __shfl_xor_sync(0xffffffffu, sv, o);
-        if (lane == 0) ss[(int64_t)ch * ncols + c] = sv;
-    }
-    if (lane == 0) E[(int64_t)ch * ncols + c] = oz_exp_from_field(f, P);
-}
-// out[0] = sum of v[0..n) in a fixed order (one CTA)
-__global__ void __launch_bounds__(1024) oz_sum_kernel(const double* __restrict__ v, int64_t n, double* __restrict__ out) {
-    __shared__ double sh[1024];
-    double s = 0.0;
-    for (int64_t i = threadIdx.x; i < n; i += 1024) s += v[i];
-    sh[threadIdx.x] = s;
-    __syncthreads();
-    for (int o = 512; o > 0; o >>= 1) {
-        if ((int)threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) out[0] = sh[0];
-}
-
-// Row exponents AND column-chunk exponent fields AND ||A||_F^2 partials of the constant data matrix in ONE sweep (the drivers use A as
-// the first operand of both products).  CTA = 256 consecutive rows (never straddling a chunk: L is a multiple of 256), thread = row.
-// Column maxima: warp REDUX + one shared-memory atomicMax per warp and column, then one global atomicMax per CTA and column on the
-// (pre-zeroed) field array - maxima are order-independent; the sums of squares are combined in a fixed order (lane, warp, CTA).
-template <typename T>
-__global__ void __launch_bounds__(256) oz_rowcolexp_kernel(const T* __restrict__ A, int64_t lda, int64_t rows, int K, int64_t L, int P_row,
-                                                           int* __restrict__ Erow, int* __restrict__ colfield, double* __restrict__ ss_part) {
-    extern __shared__ int s_col[];            // [K]
-    __shared__ double s_ss[8];
-    for (int c = threadIdx.x; c < K; c += 256) s_col[c] = 0;
-    __syncthreads();
-    const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
-    const bool rv = i < rows;
-    const T* a = A + (rv ? i : 0);
-    int rowf = 0;
-    double ss = 0.0;
-    const int lane = threadIdx.x & 31;
-    int c = 0;
-    for (; c + 4 <= K; c += 4) {
-        double x[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) x[u] = rv ? (double)a[(int64_t)(c + u) * lda] : 0.0;
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const int f = oz_expfield(x[u]);
-            rowf = max(rowf, f);
-            ss = fma(x[u], x[u], ss);
-            const int wf = __reduce_max_sync(0xffffffffu, f);
-            if (lane == 0 && wf > 0) atomicMax(&s_col[c + u], wf);
-        }
-    }
-    for (; c < K; ++c) {
-        const double x = rv ? (double)a[(int64_t)c * lda] : 0.0;
-        const int f = oz_expfield(x);
-        rowf = max(rowf, f);
-        ss = fma(x, x, ss);
-        const int wf = __reduce_max_sync(0xffffffffu, f);
-        if (lane == 0 && wf > 0) atomicMax(&s_col[c], wf);
-    }
-    if (rv) Erow[i] = oz_exp_from_field(rowf, P_row);
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
-    if (lane == 0) s_ss[threadIdx.x >> 5] = ss;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        double t = 0.0;
-        for (int w = 0; w < 8; ++w) t += s_ss[w];
-        ss_part[blockIdx.x] = t;
-    }
-    const int64_t chunk = ((int64_t)blockIdx.x * 256) / L;
-    for (int cc = threadIdx.x; cc < K; cc += 256)
-        if (s_col[cc] > 0) atomicMax(&colfield[chunk * K + cc], s_col[cc]);
-}
-// fields -> exponents, in place
-__global__ void __launch_bounds__(256) oz_field_to_exp_kernel(int* __restrict__ E, int64_t n, int P) {
-    const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
-    if (i < n) E[i] = oz_exp_from_field(E[i], P);
-}
-
-// ------------------------------------------------------------------------------------------------
-// slicers.  Digit tiles: tile (rb, kb, t) of TR rows x 32 K-bytes at ((rb * nkb + kb) * S + t) * TR * 32, inside it the byte of
-// (row r, k) sits at ((r / 8) * 2 + k / 16) * 128 + (r % 8) * 16 + k % 16  (K-major, no swizzle: SBO = 256 B, LBO = 128 B).
-// ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ double oz_pow2(int e) {      // 2^e for e in [-1022, 1023]
-    return __longlong_as_double((long long)(e + 1023) << 52);
-}
-// F + bias as raw bits: byte b (b < S - 1) is the unsigned digit d + 128 of weight 256^b, byte S - 1 the (two's complement) top digit.
-template <int S>
-__device__ __forceinline__ unsigned long long oz_fixed(double x, double scale) {
-    unsigned long long F;
-    if constexpr (OzCfg<S>::P <= 50) {
-        // x * scale + 1.5 * 2^52 leaves rn(x * scale) (two's complement) in the low mantissa bits
-        F = (unsigned long long)__double_as_longlong(fma(x, scale, 6755399441055744.0)) - 0x4338000000000000ull;
-    } else {
-        F = (unsigned long long)__double2ll_rn(x * scale);
-    }
-    return (F + OzCfg<S>::LOWMASK) ^ OzCfg<S>::LOWMASK;
-}
-// digits of 4 consecutive-k values -> w[t] = the 4 bytes of digit t (t = 0 most significant), k order = byte order
-template <int S>
-__device__ __forceinline__ void oz_pack4(const unsigned long long f[4], uint32_t* w /* [S] */) {
-    uint32_t lo[4], hi[4];
-#pragma unroll
-    for (int e = 0; e < 4; ++e) { lo[e] = (uint32_t)f[e]; hi[e] = (uint32_t)(f[e] >> 32); }
-    uint32_t B[8];
-    {
-        const uint32_t t0 = __byte_perm(lo[0], lo[1], 0x5140), t1 = __byte_perm(lo[2], lo[3], 0x5140);
-        const uint32_t t2 = __byte_perm(lo[0], lo[1], 0x7362), t3 = __byte_perm(lo[2], lo[3], 0x7362);
-        B[0] = __byte_perm(t0, t1, 0x5410); B[1] = __byte_perm(t0, t1, 0x7632);
-        B[2] = __byte_perm(t2, t3, 0x5410); B[3] = __byte_perm(t2, t3, 0x7632);
-    }
-    if constexpr (S > 4) {
-        const uint32_t t0 = __byte_perm(hi[0], hi[1], 0x5140), t1 = __byte_perm(hi[2], hi[3], 0x5140);
-        const uint32_t t2 = __byte_perm(hi[0], hi[1], 0x7362), t3 = __byte_perm(hi[2], hi[3], 0x7362);
-        B[4] = __byte_perm(t0, t1, 0x5410); B[5] = __byte_perm(t0, t1, 0x7632);
-        B[6] = __byte_perm(t2, t3, 0x5410); B[7] = __byte_perm(t2, t3, 0x7632);
-    }
-#pragma unroll
-    for (int t = 0; t < S; ++t) w[t] = B[S - 1 - t];
-}
-// 16 consecutive-k values of one tile row -> one 16-byte chunk per digit
-template <int S>
-__device__ __forceinline__ void oz_emit16(const double* xv, double scale, int8_t* tile0, int64_t tile_bytes, int off) {
-    uint32_t pk[4][S];
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-        unsigned long long f[4];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) f[e] = oz_fixed<S>(xv[4 * q + e], scale);
-        oz_pack4<S>(f, pk[q]);
-    }
-#pragma unroll
-    for (int t = 0; t < S; ++t)
-        *reinterpret_cast<uint4*>(tile0 + (int64_t)t * tile_bytes + off) = make_uint4(pk[0][t], pk[1][t], pk[2][t], pk[3][t]);
-}
-
-// First operand of the NN product: tile rows = rows of A, K = columns of A, scale per row.  CTA = (row block, group of 8 K-blocks).
-template <int S, typename T>
-__global__ void __launch_bounds__(OZ_BM) oz_slice_rows_kernel(const T* __restrict__ A, int64_t lda, int64_t rows, int K, int nkb,
-                                                              const int* __restrict__ E, int8_t* __restrict__ out) {
-    constexpr int TR = OZ_BM;
-    const int r = threadIdx.x;
-    const int64_t rb = blockIdx.x;
-    const int64_t row = rb * TR + r;
-    const bool rv = row < rows;
-    const double scale = rv ? oz_pow2(OzCfg<S>::P - E[row]) : 0.0;
-    const T* a = A + (rv ? row : 0);
-    for (int kb = blockIdx.y * 8; kb < min(nkb, (int)blockIdx.y * 8 + 8); ++kb) {
-        int8_t* tile0 = out + ((rb * nkb + kb) * S) * (int64_t)(TR * OZ_KB);
-        T raw[32];
-#pragma unroll
-        for (int kk = 0; kk < 32; ++kk) {
-            const int col = kb * OZ_KB + kk;
-            raw[kk] = (rv && col < K) ? a[(int64_t)col * lda] : T(0);
-        }
-#pragma unroll
-        for (int kc = 0; kc < 2; ++kc) {
-            double xv[16];
-#pragma unroll
-            for (int kk = 0; kk < 16; ++kk) xv[kk] = (double)raw[kc * 16 + kk];
-            oz_emit16<S>(xv, scale, tile0, TR * OZ_KB, ((r >> 3) * 2 + kc) * 128 + (r & 7) * 16);
-        }
-    }
-}
-
-// Operands whose K runs along the contiguous direction: tile rows = columns of X, K = rows [0, klen) of X, scale per column
-// (E[c], already offset to the chunk).  CTA = (column block, group of 8 K-blocks); thread = (column, 16-element K chunk).
-template <int S, int TR, typename T>
-__global__ void __launch_bounds__(128) oz_slice_cols_kernel(const T* __restrict__ X, int64_t ldx, int64_t klen, int ncols, int nkb,
-                                                            const int* __restrict__ E, int8_t* __restrict__ out) {
-    const int64_t cb = blockIdx.x;
-    for (int kb = blockIdx.y * 8; kb < min(nkb, (int)blockIdx.y * 8 + 8); ++kb) {
-        int8_t* tile0 = out + ((cb * nkb + kb) * S) * (int64_t)(TR * OZ_KB);
-        for (int item = threadIdx.x; item < TR * 2; item += 128) {
-            const int cl = item >> 1, kc = item & 1;
-            const int64_t c = cb * TR + cl;
-            const bool cv = c < ncols;
-            const double scale = cv ? oz_pow2(OzCfg<S>::P - E[c]) : 0.0;
-            const int64_t kbase = (int64_t)kb * OZ_KB + kc * 16;
-            const T* x = X + (cv ? c : 0) * ldx + kbase;
-            double xv[16];
-            if (cv && kbase + 16 <= klen && ((reinterpret_cast<uintptr_t>(x) & 15) == 0)) {
-                if constexpr (sizeof(T) == 8) {
-#pragma unroll
-                    for (int kk = 0; kk < 16; kk += 2) { const double2 t2 = *reinterpret_cast<const double2*>(x + kk); xv[kk] = t2.x; xv[kk + 1] = t2.y; }
-                } else {
-#pragma unroll
-                    for (int kk = 0; kk < 16; kk += 4) {
-                        const float4 t4 = *reinterpret_cast<const float4*>(x + kk);
-                        xv[kk] = t4.x; xv[kk + 1] = t4.y; xv[kk + 2] = t4.z; xv[kk + 3] = t4.w;
-                    }
-                }
-            } else {
-#pragma unroll
-                for (int kk = 0; kk < 16; ++kk) xv[kk] = (cv && kbase + kk < klen) ? (double)x[kk] : 0.0;
-            }
-            oz_emit16<S>(xv, scale, tile0, TR * OZ_KB, ((cl >> 3) * 2 + kc) * 128 + (cl & 7) * 16);
-        }
-    }
-}
-
-// TN operands, MN-major tiles: tile rows (MN) = columns of X, K = rows [0, klen) of X, scale per column (E[c], already offset to
-// the chunk).  Inside a tile the byte of (column c, row k) sits at ((c / 16) * 4 + k / 8) * 128 + (k % 8) * 16 + c % 16, i.e. the
-// same 8 x 16-byte core matrix as above read the other way round (LBO = 128 B between 8-row K groups, SBO = 512 B between 16-column
-// groups).  This lets a thread own one ROW: a warp reads 32 consecutive rows of a column (256 contiguous bytes per load) and writes 512
-// contiguous bytes per digit - the access pattern of the NN slicer, which the K-major column slicer above cannot have.
-// CTA = 4 warps = 4 consecutive K-blocks of one column block.
-template <int S, int TR, typename T>
-__global__ void __launch_bounds__(128) oz_slice_tn_kernel(const T* __restrict__ X, int64_t ldx, int64_t klen, int ncols, int nkb,
-                                                          const int* __restrict__ E, int8_t* __restrict__ out) {
-    const int lane = threadIdx.x & 31;
-    const int kb = blockIdx.x * 4 + (threadIdx.x >> 5);
-    if (kb >= nkb) return;
-    const int64_t cb = blockIdx.y;
-    const int64_t row = (int64_t)kb * OZ_KB + lane;
-    const bool rv = row < klen;
-    const T* x = X + (rv ? row : 0);
-    int8_t* tile0 = out + ((cb * nkb + kb) * S) * (int64_t)(TR * OZ_KB);
-#pragma unroll 1
-    for (int cg = 0; cg < TR / 16; ++cg) {
-        const int64_t c0 = cb * TR + cg * 16;
-        double xv[16];
-#pragma unroll
-        for (int kk = 0; kk < 16; ++kk) xv[kk] = (rv && c0 + kk < ncols) ? (double)x[(c0 + kk) * ldx] : 0.0;
-        uint32_t pk[4][S];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            unsigned long long f[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const int64_t c = c0 + 4 * q + e;
-                const double scale = oz_pow2(OzCfg<S>::P - E[c < ncols ? c : 0]);
-                f[e] = oz_fixed<S>(xv[4 * q + e], scale);
-            }
-            oz_pack4<S>(f, pk[q]);
-        }
-        const int off = (cg * 4 + (lane >> 3)) * 128 + (lane & 7) * 16;
-#pragma unroll
-        for (int t = 0; t < S; ++t)
-            *reinterpret_cast<uint4*>(tile0 + (int64_t)t * (TR * OZ_KB) + off) = make_uint4(pk[0][t], pk[1][t], pk[2][t], pk[3][t]);
-    }
-}
-
-// ------------------------------------------------------------------------------------------------
-// the tensor-core kernel
-// ------------------------------------------------------------------------------------------------
-// SWIZZLE_NONE shared-memory matrix descriptor (version 1); core matrix = 8 x 16 bytes = 128 contiguous bytes.
-//   K-major  (MN = false): 8 tile rows x 16 K-bytes;  LBO = 128 B between the two K halves, SBO = 256 B between 8-row groups
-//   MN-major (MN = true):  16 MN-bytes x 8 K-rows;    LBO = 128 B between 8-row K groups,   SBO = 512 B between 16-wide MN groups
-template <bool MN>
-__device__ __forceinline__ uint64_t oz_desc(uint32_t saddr) {
-    constexpr uint64_t SBO = MN ? 512 : 256;
-    return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)(128 >> 4) << 16) | ((SBO >> 4) << 32) | ((uint64_t)1 << 46);
-}
-__device__ __forceinline__ void oz_mbar_wait(uint32_t bar, uint32_t parity) {
-    uint32_t done = 0;
-    while (!done) {
-        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
-                     : "=r"(done) : "r"(bar), "r"(parity) : "memory");
-    }
-}
-// long waits (the epilogue warps wait for a whole tile's main loop): back off so that the spinning warps do not take issue slots from
-// the slicer CTAs that share the SM
-__device__ __forceinline__ void oz_mbar_wait_sleep(uint32_t bar, uint32_t parity) {
-    uint32_t done = 0;
-    while (true) {
-        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
-                     : "=r"(done) : "r"(bar), "r"(parity) : "memory");
-        if (done) break;
-        __nanosleep(256);
-    }
-}
-__device__ __forceinline__ void oz_bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
-}
-__device__ __forceinline__ void oz_bulk_load_mc(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, uint16_t mask) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;"
-                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar), "h"(mask) : "memory");
-}
-__device__ __forceinline__ void oz_cluster_sync() {
-    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void oz_mma_i8(uint32_t d_tmem, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
-    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-                 "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}\n"
-                 ::"r"(d_tmem), "l"(da), "l"(db), "r"(idesc), "r"(acc) : "memory");
-}
 
 struct OzGram {            // fused Gram output of the TN product (see the kernel)
     int nb_main;
@@ -499,32 +143,43 @@ ozaki_mma_kernel(const int8_t* __restrict__ a_tiles, int64_t a_group_stride, con
             }
             oz_bulk_load(dst + S * OZ_TILE_A, gb + (int64_t)kb * (S * OZ_TILE_B), S * OZ_TILE_B, bar);
         }
-    } else if (tid == 32) {
-        // ---- issuer.  s32 accumulate, signed int8 A and B, both K-major, M = 128 (cute/arch/mma_sm100_desc.hpp InstrDescriptor)
-        const uint32_t idesc0 = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(OZ_BM >> 4) << 24) | (MN ? ((1u << 15) | (1u << 16)) : 0u);
+    } else if (warp == 1) {
+        // ---- issuer.  s32 accumulate, signed int8 A and B, both K-major, M = 128 (cute/arch/mma_sm100_desc.hpp InstrDescriptor).
+        // The whole warp runs the loop (warp-uniform operands: the descriptors stay in uniform registers and there is no per-thread
+        // serialisation loop around tcgen05.mma); one elected lane issues the MMAs and the commits (tools/peaks_i8.cu: <= 45 cycles per
+        // instruction instead of ~110 from a single divergent thread).
+        constexpr uint32_t IDESC0 = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(OZ_BM >> 4) << 24) | (MN ? ((1u << 15) | (1u << 16)) : 0u);
+        constexpr uint64_t HI = ((uint64_t)((MN ? 512 : 256) >> 4) | ((uint64_t)1 << 14)) << 32;
+        uint32_t elected = 0;
+        asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}\n" : "=r"(elected));
+        const uint32_t base_lo0 = (sbase >> 4) | ((uint32_t)(128 >> 4) << 16);
         for (int kb = 0; kb < nkb; ++kb) {
             const int slot = kb % STAGES;
             oz_mbar_wait(oz_smem(&bar_full[slot]), (uint32_t)((kb / STAGES) & 1));
-            if (dbg && kb == 0) dbg[((int64_t)(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 8 + 2] = clock64();
+            if (dbg && kb == 0 && elected) dbg[((int64_t)(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 8 + 2] = clock64();
             asm volatile("tcgen05.fence::after_thread_sync;");
-            const uint32_t sa = sbase + slot * Cfg::STAGE_BYTES, sb = sa + S * OZ_TILE_A;
+            if (elected) {
+                const uint32_t lo = base_lo0 + (uint32_t)slot * (uint32_t)(Cfg::STAGE_BYTES >> 4);
 #pragma unroll
-            for (int s = 0; s < S; ++s) {
-                const uint64_t da = oz_desc<MN>(sa + s * OZ_TILE_A);
+                for (int s = 0; s < S; ++s) {
+                    const uint64_t da = HI | (uint64_t)(lo + (uint32_t)((s * OZ_TILE_A) >> 4));
 #pragma unroll
-                for (int t0 = 0; t0 < S - s; t0 += 4) {
-                    const int nt = (S - s - t0) < 4 ? (S - s - t0) : 4;      // digit tiles of the second operand in this instruction
-                    const uint32_t idesc = idesc0 | ((uint32_t)((nt * OZ_BN) >> 3) << 17);
-                    oz_mma_i8(tmem + (uint32_t)((s + t0) * OZ_BN), da, oz_desc<MN>(sb + t0 * OZ_TILE_B), idesc, (kb > 0 || s > 0) ? 1u : 0u);
+                    for (int t0 = 0; t0 < S - s; t0 += 4) {
+                        const int nt = (S - s - t0) < 4 ? (S - s - t0) : 4;      // digit tiles of the second operand in this instruction
+                        const uint32_t idesc = IDESC0 | ((uint32_t)((nt * OZ_BN) >> 3) << 17);
+                        const uint64_t db = HI | (uint64_t)(lo + (uint32_t)((S * OZ_TILE_A + t0 * OZ_TILE_B) >> 4));
+                        oz_mma_i8(tmem + (uint32_t)((s + t0) * OZ_BN), da, db, idesc, (kb > 0 || s > 0) ? 1u : 0u);
+                    }
                 }
+                if (cs == 1)
+                    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(oz_smem(&bar_empty[slot])) : "memory");
+                else
+                    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                                 ::"r"(oz_smem(&bar_empty[slot])), "h"(cmask) : "memory");
             }
-            if (cs == 1)
-                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(oz_smem(&bar_empty[slot])) : "memory");
-            else
-                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-                             ::"r"(oz_smem(&bar_empty[slot])), "h"(cmask) : "memory");
+            __syncwarp();
         }
-        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(oz_smem(&bar_acc)) : "memory");
+        if (elected) asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(oz_smem(&bar_acc)) : "memory");
     }
     __syncwarp();
     // ---- epilogue: TMEM lane = tile row.  Warps w and w + 4 share lane quarter w % 4 (a warp may only touch its own quarter) and
@@ -537,7 +192,10 @@ ozaki_mma_kernel(const int8_t* __restrict__ a_tiles, int64_t a_group_stride, con
     const int ea = (i < rows_a) ? Ea[g * ea_stride + i] : 0;
     constexpr int ESHIFT = (2 * Cfg::P - 16 * (S - 1)) + 16;
     // fast scaling: when 2^(ea + eb - ESHIFT) is a normal double for every column of the tile, its high word is one integer add
-    const bool fast = (ea + s_ebmin - ESHIFT >= -1022) && (ea + s_ebmax - ESHIFT <= 1023);
+    // an Inf/NaN entry makes its group's exponent 0x7ff - 1022: everything that depends on that group is written as NaN (the BLAS
+    // path of the reference propagates it the same way)
+    constexpr int NONFINITE_E = 0x7ff - 1022;
+    const bool fast = (ea + s_ebmin - ESHIFT >= -1022) && (ea + s_ebmax - ESHIFT <= 1023) && ea != NONFINITE_E && s_ebmax != NONFINITE_E;
     const int ea_hi = (ea - ESHIFT + 1023) << 20;
     const bool simple = fast && alpha == 1.0 && beta == 0.0 && (int)(blockIdx.x + 1) * OZ_BN <= rows_b;
     TO* og = out + g * out_group_stride;
@@ -582,6 +240,8 @@ ozaki_mma_kernel(const int8_t* __restrict__ a_tiles, int64_t a_group_stride, con
                         double val;
                         if (fast) {
                             val = v * __hiloint2double(ea_hi + s_eb20[c0 + j], 0);
+                        } else if (ea == NONFINITE_E || (s_eb20[c0 + j] >> 20) == NONFINITE_E) {
+                            val = __longlong_as_double(0x7ff8000000000000ll);
                         } else {
                             // v * 2^(ea + eb - ESHIFT), split in two exact power-of-two factors so that neither leaves the normal range early
                             const int e = ea + (s_eb20[c0 + j] >> 20) - ESHIFT;
@@ -609,19 +269,6 @@ ozaki_mma_kernel(const int8_t* __restrict__ a_tiles, int64_t a_group_stride, con
     if (cs > 1) oz_cluster_sync();      // no CTA exits while a peer's commit may still arrive on its barriers
 }
 
-// C = alpha * sum_g part[g] + beta * C  (fixed order)
-template <typename T>
-__global__ void __launch_bounds__(256) oz_reduce_kernel(const double* __restrict__ part, int groups, int64_t total, int n1, double alpha, double beta,
-                                                        T* __restrict__ C, int64_t ldc) {
-    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
-        double s = 0.0;
-        for (int g = 0; g < groups; ++g) s += part[(int64_t)g * total + e];
-        T* c = C + (e % n1) + (e / n1) * ldc;
-        double v = alpha * s;
-        if (beta != 0.0) v += beta * (double)(*c);
-        *c = (T)v;
-    }
-}
 
 // cluster size along x for a grid of nxb second-operand blocks: the largest of {4, 2, 1} that divides nxb and still lets
 // (almost) every SM hold a CTA (GPCs whose SM count is not a multiple of the cluster size strand SMs).  RLB200_OZ_CLUSTER overrides.
@@ -732,6 +379,7 @@ static int oz_aux(Ctx* ctx) {
     }
     return 0;
 }
+int oz_aux_streams(Ctx* ctx) { return oz_aux(ctx); }
 enum { OZ_EV_FORK = 0, OZ_EV_SLICED = 1, OZ_EV_CONSUMED = 3 };
 
 // cached exponents of the constant data matrix (OzConstScope, drivers.cuh)
@@ -885,7 +533,7 @@ static int oz_nn(Ctx* ctx, int64_t m, int64_t N, int64_t K, double alpha, const 
             LaunchScope ls(ctx, RLB200_TIMER_I8_MMA_NN);
             long long* dbg = nullptr;
             if (c == 0 && getenv("RLB200_OZ_DBG")) cudaMalloc(&dbg, (size_t)nnb * nrb * 64);
-            RLB_CHECK((oz_launch_mma<S, T, false>(ctx, dim3(nnb, nrb, 1), cs, main, at[b], 0, bt, 0, nkb, Ea_c, 0, Eb, 0, rows, (int)N, C + r0, ldc, 0, alpha, beta, dbg, b_upper_tri ? 1 : 0)));
+            RLB_CHECK((oz_launch_mma<S, T, false>(ctx, dim3(nnb, nrb, 1), b_upper_tri ? 1 : cs, main, at[b], 0, bt, 0, nkb, Ea_c, 0, Eb, 0, rows, (int)N, C + r0, ldc, 0, alpha, beta, dbg, b_upper_tri ? 1 : 0)));
             if (dbg) { oz_dbg_report("NN", main, dbg, (int64_t)nnb * nrb); cudaFree(dbg); }
         }
         tl.mark('M', main);
@@ -993,10 +641,10 @@ static int oz_tn(Ctx* ctx, int64_t m, int64_t N1, int64_t N2, double alpha, cons
             long long* dbg = nullptr;
             if (c0 == 0 && getenv("RLB200_OZ_DBG")) cudaMalloc(&dbg, (size_t)nb2 * nb1 * g * 64);
             if (kmajor)
-                RLB_CHECK((oz_launch_mma<S, double, false>(ctx, dim3(nb2, nb1, g), cs, main, xt[b], xs, yt[b], ys, nkb, Ex + c0 * N1, N1, Ey + c0 * N2, N2, N1,
+                RLB_CHECK((oz_launch_mma<S, double, false>(ctx, dim3(nb2, nb1, g), upper_only ? 1 : cs, main, xt[b], xs, yt[b], ys, nkb, Ex + c0 * N1, N1, Ey + c0 * N2, N2, N1,
                                                            (int)N2, part, N1, total, 1.0, c0 > 0 ? 1.0 : 0.0, dbg, upper_only ? 2 : 0)));
             else
-                RLB_CHECK((oz_launch_mma<S, double, true>(ctx, dim3(nb2, nb1 + nb1g, g), gram_out ? 1 : cs, main, xt[b], xs, yt[b], ys, nkb, Ex + c0 * N1, N1,
+                RLB_CHECK((oz_launch_mma<S, double, true>(ctx, dim3(nb2, nb1 + nb1g, g), (gram_out || upper_only) ? 1 : cs, main, xt[b], xs, yt[b], ys, nkb, Ex + c0 * N1, N1,
                                                           Ey + c0 * N2, N2, N1, (int)N2, part, N1, total, 1.0, c0 > 0 ? 1.0 : 0.0, dbg, upper_only ? 2 : 0,
                                                           OzGram{nb1, part_g, N2 * N2})));
             if (dbg) { oz_dbg_report("TN", main, dbg, (int64_t)nb2 * nb1 * g); cudaFree(dbg); }

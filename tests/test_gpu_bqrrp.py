@@ -152,3 +152,37 @@ def test_bqrrp_engine_trailing_update_vs_oracle(ctx, qr_tall):
     assert np.abs(tau - tau2).max() <= 1e-9
     e = geqp3_format_invariants(A, F, tau, J, rank)
     assert max(e) <= np.finfo(np.float64).eps ** 0.75, e
+
+
+@pytest.mark.parametrize("shape,b,d_factor,qr_tall", [((2000, 1500, 1500), 128, 1.0, "geqrf"), ((2000, 1500, 1500), 128, 1.0, "cholqr"),
+                                                      ((1000, 1000, 100), 64, 2.0, "geqrf"), ((20000, 512, 512), 256, 1.0, "cholqr")])
+def test_bqrrp_gpu_interface_same_sketch_as_cpu(ctx, shape, b, d_factor, qr_tall):
+    """BQRRP_GPU_alg::call(m, n, A, lda, A_sk, d, tau, J) (rl_bqrrp_gpu.hh:27-43, 122-133): device pointers, the sketch is an INPUT.
+    The reference's own GPU-vs-CPU recipe (test/drivers/test_bqrrp_gpu.cu:91-103, 224-249): S = fill_dense(DenseDist(d, m)) read as a
+    column-major d x m matrix, A_sk = S A formed on the host, handed to the device driver; the CPU driver (here: the oracle's restatement of
+    rl_bqrrp.hh) regenerates the same sketch from the same state.  ||J_gpu - J_cpu|| = 0, tau to eps^0.75, R to eps^0.60."""
+    m, n, k = shape
+    A, st = O.gen_poly_mat(m, n, k, 2025.0, 2.0, O.RNGState(0))
+    d = int(d_factor * b)
+    S, _ = O.fill_dense(d, m, O.RNGState(st.key, st.counter))
+    # the reference hands the natural-layout (row-major) buffer to gemm as ColMajor with ld = d (rl_bqrrp.hh:309-312, test_bqrrp_gpu.cu:99)
+    S = np.ascontiguousarray(S).reshape(-1).reshape((d, m), order="F")
+    A_sk = np.asfortranarray(S @ A)
+    o = O.BQRRP(b, "luqr", qr_tall)
+    rc2, F2, tau2, J2, _ = o.call(A, d_factor, O.RNGState(st.key, st.counter))
+    alg = rl.BQRRP(False, b)
+    alg.qr_tall = 1 if qr_tall == "cholqr" else 0
+    Ad, Skd = dev(A), dev(A_sk)
+    rc, tau, J = alg.call_sk(ctx, Ad, Skd)
+    F, tau, J = host(Ad), tau.cpu().numpy(), J.cpu().numpy()
+    assert (rc, alg.rank) == (rc2, o.rank)
+    kn = min(numerical_rank(F2), o.rank)
+    assert np.array_equal(J[:kn], J2[:kn]), "pivot vector differs from the CPU driver's on the same sketch"
+    eps = np.finfo(np.float64).eps
+    assert np.linalg.norm(tau[:kn] - tau2[:kn]) <= eps ** 0.75 * 10
+    sc = np.abs(np.diag(F2)).max()
+    # columns past the numerical rank are ordered by round-off noise (on both sides): compare the part of R they do not permute
+    nc = n if kn == min(m, n) else kn
+    assert np.linalg.norm(np.triu(F[:kn, :nc]) - np.triu(F2[:kn, :nc])) <= eps ** 0.60 * sc
+    e = geqp3_format_invariants(A, F, tau, J, alg.rank if kn == o.rank else kn)
+    assert e[2] <= eps ** 0.75 and (kn < o.rank or max(e) <= eps ** 0.75), e

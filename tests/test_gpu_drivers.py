@@ -270,7 +270,11 @@ def test_rsvd_headline_engine_path_vs_oracle(ctx, k, p, graded):
     # in the reference as well); with the graded matrix the trailing directions carry sigma ~ 1e-12 sigma_1
     r = int(np.sum(S_o > 1e-6 * S_o[0])) if graded else kk
     assert _ref.subspace_sin(U_o[:, :r], U[:, :r]) <= (1e-6 if graded else 1e-9)
-    assert np.linalg.norm(U.T @ U - np.eye(kk)) <= EPS ** 0.625 and np.linalg.norm(V.T @ V - np.eye(kk)) <= EPS ** 0.625
+    # orthogonality: the reference's own tolerance, or - where CholQR of the graded sketch loses orthogonality in the reference itself
+    # (cond(Y)^2 eps) - no worse than a small multiple of what the reference delivers on the same input
+    o_ref = max(np.linalg.norm(U_o.T @ U_o - np.eye(kk)), np.linalg.norm(V_o.T @ V_o - np.eye(kk)))
+    lim = max(EPS ** 0.625, 10 * o_ref)
+    assert np.linalg.norm(U.T @ U - np.eye(kk)) <= lim and np.linalg.norm(V.T @ V - np.eye(kk)) <= lim
 
 
 def test_rsvd_nonfinite_input_propagates(ctx):

@@ -113,14 +113,16 @@ def test_i8_gemm_column_graded_first_operand_is_normwise(ctx, digits):
     ref = A @ B
     bound = A.abs().max(dim=1).values[:, None] * B.abs().max(dim=0).values[None, :] * K
     P = 8 * digits - 2
-    assert ((C - ref).abs() / bound).max().item() <= 2.0 ** -(P - 1)
+    # 2^-(P-1): both operands rounded to P bits below their group maximum; 2^-52: the fp64 rounding of the result and of the torch reference
+    tol = 2.0 ** -(P - 1) + 2.0 ** -52
+    assert ((C - ref).abs() / bound).max().item() <= tol
     # a right-hand side that only sees the tiny columns: the product is ~1e-14 of the row scale and inherits the absolute error
     B2 = B.clone()
     B2[: K - 8] = 0
     C2 = rl.gemm(ctx, False, False, 1.0, A, B2, engine="i8")
     ref2 = A @ B2
     bound2 = A.abs().max(dim=1).values[:, None] * B2.abs().max(dim=0).values[None, :] * K
-    assert ((C2 - ref2).abs() / bound2).max().item() <= 2.0 ** -(P - 1)
+    assert ((C2 - ref2).abs() / bound2).max().item() <= tol
 
 
 @pytest.mark.parametrize("bad", [float("nan"), float("inf")])
@@ -141,3 +143,69 @@ def test_i8_gemm_nonfinite_propagates(ctx, bad):
     assert not torch.isfinite(Z[5]).any()
     okc = torch.ones(K, dtype=torch.bool, device="cuda"); okc[5] = False
     assert torch.isfinite(Z[okc]).all()
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
+# fused engine (ozaki_fused.cu): the digits of the tall operand are produced inside the tensor-core kernel
+# ---------------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("shape", [(20000, 1024, 256), (70001, 300, 130), (64, 32, 96), (1, 1, 100), (4000, 1031, 129), (333, 77, 384)])
+@pytest.mark.parametrize("bad_scaling", [False, True])
+@pytest.mark.parametrize("digits", [6, 7])
+def test_i8_fused_gemm_nn(ctx, shape, bad_scaling, digits):
+    """A(m x K) B(K x N), N >= 96 (the fused engine's range): ragged m (not a multiple of 64), K (not of 32) and N (not of 128), alpha/beta,
+    against torch fp64 with the componentwise-by-bound tolerance of the staged engine, and against the staged engine itself."""
+    m, K, N = shape
+    ctx.set_i8_digits(digits)
+    A = _mk(m, K, 41, scale_rows=bad_scaling)
+    B = _mk(K, N, 42, scale_cols=bad_scaling)
+    C0 = _mk(m, N, 43)
+    try:
+        ctx.set_i8_fused(True)
+        C = C0.clone()
+        rl.gemm(ctx, False, False, -0.5, A, B, 2.0, C, engine="i8")
+        ctx.set_i8_fused(False)
+        Cs = C0.clone()
+        rl.gemm(ctx, False, False, -0.5, A, B, 2.0, Cs, engine="i8")
+    finally:
+        ctx.set_i8_fused(True)
+        ctx.set_i8_digits(0)
+    ref = -0.5 * (A @ B) + 2.0 * C0
+    bound = 0.5 * (A.abs() @ B.abs()) + 2.0 * C0.abs()
+    assert ((C - ref).abs() / bound).max().item() <= TOL[digits]
+    assert ((C - Cs).abs() / bound).max().item() <= 2 * TOL[digits]
+
+
+@pytest.mark.parametrize("shape", [(70000, 256, 128), (40001, 130, 97), (5000, 1024, 256), (100, 64, 96), (1200000, 64, 128)])
+@pytest.mark.parametrize("bad_scaling", [False, True])
+@pytest.mark.parametrize("digits", [6, 7])
+def test_i8_fused_gemm_tn(ctx, shape, bad_scaling, digits):
+    """X(m x N1)^T Y(m x N2), N2 >= 96: several 16384-row accumulation groups, a ragged last group, more groups than one launch takes
+    (1.2 M rows: 74 groups, 64 per launch), deterministic."""
+    m, N1, N2 = shape
+    ctx.set_i8_digits(digits)
+    X = _mk(m, N1, 44, scale_cols=bad_scaling)
+    Y = _mk(m, N2, 45, scale_cols=bad_scaling)
+    try:
+        C = rl.gemm(ctx, True, False, 1.0, X, Y, engine="i8")
+        C2 = rl.gemm(ctx, True, False, 1.0, X, Y, engine="i8")
+    finally:
+        ctx.set_i8_digits(0)
+    ref = X.t() @ Y
+    bound = X.abs().t() @ Y.abs()
+    assert ((C - ref).abs() / bound).max().item() <= TOL[digits]
+    assert torch.equal(C, C2)
+
+
+def test_i8_fused_gemm_f32_storage(ctx):
+    m, K, N = 40000, 512, 128
+    A = rl.to_f(_mk(m, K, 51).float())
+    B = rl.to_f(_mk(K, N, 52).float())
+    C = rl.gemm(ctx, False, False, 1.0, A, B, engine="i8")
+    ref = A.double() @ B.double()
+    bound = A.double().abs() @ B.double().abs()
+    assert ((C.double() - ref).abs() / bound).max().item() <= 2e-7
+    Y = rl.to_f(_mk(m, N, 53).float())
+    Z = rl.gemm(ctx, True, False, 1.0, A, Y, engine="i8")
+    refz = A.double().t() @ Y.double()
+    boundz = A.double().abs().t() @ Y.double().abs()
+    assert ((Z.double() - refz).abs() / boundz).max().item() <= 2e-7

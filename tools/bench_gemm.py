@@ -16,6 +16,8 @@ k = int(sys.argv[3]) if len(sys.argv) > 3 else 256
 only = sys.argv[4] if len(sys.argv) > 4 else ""   # "nn" / "tn": only that product on the i8 engine (6 digits); "i8": both, i8 only
 m = 1 << lm
 ctx = rl.Context(0)
+if os.environ.get("RLB200_I8_FUSED") == "0":
+    ctx.set_i8_fused(False)
 dev = torch.device("cuda", 0)
 A = rl.empty_f(m, n, torch.float64, dev)
 ctx.check(ctx._lib.rlb200_fill_dense_f64_dev(ctx._h, m, n, 0, 0, 0, m, n, 0, 0, A.data_ptr(), rl.RNGState(1).words()))
