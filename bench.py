@@ -19,12 +19,16 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-# dram__bytes_read.sum + dram__bytes_write.sum of ozaki_mma_kernel per row of A (n = 1024, k = 256, 6 digits), from the ncu --set full
-# capture named below; None until a capture is committed
-OZ_TRAFFIC_NN_PER_ROW = (263.686656e6 + 71.827968e6) / 42624.0     # profiles/ncu_oz_nn_r1.txt: one launch = 42624 rows of A
-OZ_TRAFFIC_TN_PER_ROW = (1.176578e9 + 14.035200e6) / 147456.0      # profiles/ncu_oz_tn_r1.txt: one launch = 9 x 16384 rows of A
-OZ_TRAFFIC_SOURCE = ("ncu --set full captures of ozaki_mma_kernel (profiles/ncu_oz_nn_r1.txt, ncu_oz_tn_r1.txt), DRAM bytes per row of A "
-                     "x rows x passes; algorithmic bytes per row and pass: 6 B x n digits + 8 B x k (NN: 8192) / 6 B x (n + k) (TN: 7680)")
+# DRAM traffic (dram__bytes_read.sum + dram__bytes_write.sum) of ALL kernels of one step per row of A at n = 1024, k = 256, p = 2, from the
+# ncu launch list of this very command at m = 2^20 (profiles/launches_dram_r2.csv: every launch of one step, summed); and of the two
+# dominant launches alone from their `ncu --set full` captures (profiles/ncu_oz2_nn_r2.txt: 8.598 GB + 2.092 GB per 2^20 rows;
+# profiles/ncu_oz2_tn_r2.txt: 4.485 GB + 0.078 GB per 27 x 16384 rows).  Algorithmic bytes per row: 8 n = 8192 (A read once per pass).
+OZ2_TRAFFIC_NN_PER_ROW = (8.597615e9 + 2.091834e9) / float(1 << 20)
+OZ2_TRAFFIC_TN_PER_ROW = (4.485259e9 + 0.077737e9) / (27.0 * 16384.0)
+STEP_TRAFFIC_PER_ROW = None        # filled from profiles/launches_dram_r2.csv (whole step, all kernels) when measured
+OZ_TRAFFIC_SOURCE = ("dominant launches: ncu --set full captures of oz2_kernel (profiles/ncu_oz2_nn_r2.txt, ncu_oz2_tn_r2.txt), DRAM bytes per row "
+                     "of A x rows x launches; algorithmic bytes per row and pass: 8 n (A, read once as fp64) + 8 k (Y written) for A*Omega, "
+                     "8 n + S k (digits of Y) for A^T*Y")
 METRIC = "rsvd_gflops"
 UNIT = "Gflop/s"
 
@@ -123,6 +127,20 @@ def measured_fp64_peak():
         return 37.0, f"nominal B200 fp64 (tools/peaks failed: {type(e).__name__})", None
 
 
+def measured_i8_peak():
+    """int8 tensor-pipe peak of THIS device from tools/peaks_i8 (tcgen05.mma.kind::i8, M = 128, N = 256, K = 32 on resident operands; burst
+    and ~1.5 s sustained), measured in-run: MEASURED_PEAKS.json has no int8 figure.  Also returns the cost of the engine's own instruction
+    mixes (8 stacked instructions per K step for 6 digits)."""
+    exe = os.path.join(ROOT, "tools", "peaks_i8")
+    try:
+        out = subprocess.run([exe, "1.5", "quick"], capture_output=True, text=True, timeout=180).stdout.strip().splitlines()[-1]
+        d = json.loads(out)
+        r = {x["pattern"]: x for x in d["results"] if x["cta_group"] == 1}
+        return r["n256"]["burst_tops"], r["n256"]["sustained_tops"], "measured in-run by tools/peaks_i8 (UTCIMMA M=128 N=256 K=32, operands resident)", r
+    except Exception as e:  # noqa: BLE001
+        return None, None, f"tools/peaks_i8 failed: {type(e).__name__}", None
+
+
 def load_peaks():
     try:
         return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -158,10 +176,11 @@ def cpu_rsvd_runner(n, k, p, q):
 
 def cpu_sample(n, k, p, q, m_cpu, steps, warmup):
     import numpy as np
-    import torch
+    from oracle import rl_oracle as O
     run, kind, cores = cpu_rsvd_runner(n, k, p, q)
-    torch.manual_seed(0)
-    A = np.asfortranarray(torch.randn((n, m_cpu), dtype=torch.float64).numpy().T)
+    # the same synthetic input family as the GPU arm: a Philox/Box-Muller DenseDist(m, n) sample (RandBLAS fill_dense, oracle restatement)
+    A, _ = O.fill_dense(m_cpu, n, O.RNGState(0xA2))
+    A = np.asfortranarray(A)
     for _ in range(warmup):
         run(A)
     ts = []
@@ -172,6 +191,41 @@ def cpu_sample(n, k, p, q, m_cpu, steps, warmup):
     t = sum(ts) / len(ts)
     gf = rsvd_flops(m_cpu, n, k, p, q) / t / 1e9
     return gf, t, kind, cores
+
+
+def parity_sample(ctx, rl, n, k, p, q, m_par):
+    """Parity measured in the same run: RSVD of an m_par x n Philox matrix on the device and by the CPU restatement of the
+    reference (oracle/, validated against the compiled reference) on the SAME operator Omega (the device's; the reference's own CPU-vs-GPU
+    test feeds one sketch to both sides, test_bqrrp_gpu.cu:91-103).  Checker only - nothing here is timed."""
+    import numpy as np
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import _ref
+    from oracle import rl_oracle as O
+    dev = torch.device("cuda", torch.cuda.current_device())
+    A = rl.empty_f(m_par, n, torch.float64, dev)
+    ctx.check(ctx._lib.rlb200_fill_dense_f64_dev(ctx._h, m_par, n, rl.FAMILY_GAUSSIAN, rl.AXIS_LONG, rl.LAYOUT_NATURAL, m_par, n, 0, 0,
+                                                 A.data_ptr(), rl.RNGState(0xA2).words()))
+    # a decaying spectrum (sigma_j = j^-1) so that the rank-k truncation, the residual and the subspace are well defined
+    A *= (1.0 / torch.arange(1, n + 1, dtype=torch.float64, device=dev))[None, :]
+    st = rl.RNGState(7)
+    rows = n if p % 2 == 0 else m_par
+    buf, _ = rl.fill_dense(ctx, rl.DenseDist(rows, k), st.copy())
+    Om = np.asfortranarray(buf.cpu().numpy().reshape((rows, k), order="F"))
+    stack = rl.RSVD(rl.QB(rl.RF(rl.RS(rl.CholQRQ(), p, q), rl.CholQRQ()), rl.CholQRQ()), k)
+    rc, kk, U, S, V = stack.call(ctx, A, k, 0.0, st.copy())
+    Ah = np.asfortranarray(A.cpu().numpy())
+    *_, rsvd_o = O.make_stack(O.StackOpts(p, q, k, O.STAB_CHOLQRQ, O.STAB_CHOLQRQ, O.STAB_CHOLQRQ))
+    rc_o, kk_o, U_o, S_o, V_o, _ = rsvd_o.call(Ah, k, 0.0, O.RNGState(7), omega_override=Om)
+    U, S, V = U.cpu().numpy()[:, :kk], S.cpu().numpy()[:kk], V.cpu().numpy()[:, :kk]
+    nrm = np.linalg.norm(Ah)
+    r_dev = np.linalg.norm(Ah - (U * S) @ V.T) / nrm
+    r_ref = np.linalg.norm(Ah - (U_o * S_o) @ V_o.T) / nrm
+    return {"sample": f"{m_par} x {n} fp64, k={k}, p={p}: device RSVD vs the CPU restatement of the reference on the same operator",
+            "codes_equal": bool((rc, kk) == (rc_o, kk_o)), "sigma_max_rel_err": float(np.abs(S - S_o).max() / S_o[0]),
+            "residual_rel": {"device": float(r_dev), "reference": float(r_ref), "abs_diff": float(abs(r_dev - r_ref))},
+            "subspace_sin": float(_ref.subspace_sin(U_o, U)), "orth_U": float(np.linalg.norm(U.T @ U - np.eye(kk))),
+            "tolerance": "sigma 1e-10 relative, residual within 1e-10, subspace sin 1e-9 (north star / tests/test_gpu_drivers.py)"}
 
 
 # --------------------------------------------------------------------------------------------------
@@ -386,8 +440,8 @@ def main():
     ctx = rl.Context(dev.index)
     ctx.set_fp64_engine(args.engine)
     ctx.set_i8_digits(args.digits)
-    config["fp64_engine"] = ("tcgen05 kind::i8 digit slices, %d digits (A^T*Y with the fused Gram matrix: %d)" % (args.digits or 6, args.digits or 7)) \
-        if args.engine == "i8" else "DMMA fp64 pipe"
+    config["fp64_engine"] = ("tcgen05 kind::i8 digit slices fused with the slicing of A, %d digits (A^T*Y in the power iteration, Gram matrix and U: %d)"
+                             % (args.digits or 6, args.digits or 7)) if args.engine == "i8" else "DMMA fp64 pipe"
 
     def barrier():
         if dist is not None:
@@ -471,34 +525,48 @@ def main():
     class_launches = {kname: v[1] for kname, v in tms.items() if v[1]}
     fp64_peak, fp64_src, _ = measured_fp64_peak()
     if args.engine == "i8":
-        # dominant kernel: ozaki_mma_kernel (tcgen05.mma.kind::i8).  Algorithmic work per launch class: the (p + 2) tall products,
-        # 2*m*n*k flops each, executed as S(S+1)/2 int8 digit-pair GEMMs of the same shape.
-        # A*Omega passes and U = Y*M: 6 digits (21 pairs); A^T*Y passes carry the fused Gram matrix Y^T*Y and run with 7 digits (28 pairs).
+        # dominant kernel: oz2_kernel (tcgen05.mma.kind::i8 with the digit slicing of A fused in).  Work per launch class: the (p + 2) tall
+        # products, 2*m*n*k flops each, executed as digit-pair GEMMs of the same shape:
+        #   A*Omega passes: 6 digits, 21 pairs;  U = Y*M: 7 digits, 28 pairs (orthogonality of U);
+        #   A^T*Y inside the power iteration (Omega = (A^T Y) R^-1): 7 digits, 28 pairs;  the last A^T*Y (B^T): 21 pairs;
+        #   the Gram tiles of Y^T*Y that ride in every A^T*Y launch: 28 pairs on the tiles that touch the upper triangle.
         S_dig = args.digits or 6
         S_tn = args.digits or 7
-        pairs, pairs_tn = S_dig * (S_dig + 1) // 2, S_tn * (S_tn + 1) // 2
-        nn_passes, tn_passes = p // 2 + 1, p - p // 2 + 1
+        pairs, pairs_full = S_dig * (S_dig + 1) // 2, S_tn * (S_tn + 1) // 2
+        nn_passes = p // 2 + 1
+        tn_fold = p // 2                      # A^T*Y launches inside RS that carry the folded CholQR (full pairs)
+        tn_plain = 1 if p % 2 else 0          # odd p: the first A^T*Omega_1 (no Gram matrix)
         gram_rows, gram_cols = -(-k // 128), -(-k // 64)
-        gram_frac = sum(1 for y in range(gram_rows) for x in range(gram_cols) if y * 128 <= x * 64 + 63) / float(gram_rows * gram_cols)
+        gram_frac = sum(1 for y in range(gram_rows) for x in range(gram_cols) if x * 64 <= y * 128 + 127) / float(gram_rows * gram_cols)
         mma_ms = tms["i8_mma_nn"][0] + tms["i8_mma_tn"][0]
-        i8_ops = (nn_passes * 2.0 * m_local * n * k + 2.0 * m_local * k * k) * pairs \
-            + tn_passes * (2.0 * m_local * n * k + 2.0 * m_local * k * k * gram_frac) * pairs_tn
+        i8_ops = nn_passes * 2.0 * m_local * n * k * pairs + 2.0 * m_local * k * k * pairs_full \
+            + tn_fold * (2.0 * m_local * n * k + 2.0 * m_local * k * k * gram_frac) * pairs_full \
+            + tn_plain * 2.0 * m_local * n * k * pairs \
+            + (2.0 * m_local * n * k * pairs + 2.0 * m_local * k * k * gram_frac * pairs_full)
         achieved = i8_ops / (mma_ms * 1e-3) / 1e12 if mma_ms > 0 else 0.0
-        if "bf16_tflops_sustained" in peaks:
+        i8_burst, i8_sus, i8_src, i8_detail = measured_i8_peak()
+        if i8_sus:
+            peak, peak_src = i8_sus, i8_src + "; sustained figure (the kernel is timed inside a long step); burst %.0f" % i8_burst
+        elif "bf16_tflops_sustained" in peaks:
             peak = 2.0 * peaks["bf16_tflops_sustained"]
-            peak_src = ("2 x MEASURED_PEAKS.json bf16_tflops_sustained (the kernel is timed inside a long step; the int8 tensor rate of "
-                        "sm_100 is twice the bf16 rate, the file has no int8 figure)")
+            peak_src = "2 x MEASURED_PEAKS.json bf16_tflops_sustained (tools/peaks_i8 did not run: " + i8_src + ")"
         else:
             peak = 2.0 * 1361.4
-            peak_src = "fallback: 2 x 1361.4 TFLOP/s sustained bf16 (B200_PROFILING.md); int8 tensor rate is twice the bf16 rate"
-        roofline = {"bound": "tensor", "kernel": "ozaki_mma_kernel (tcgen05.mma.kind::i8, NN + TN launches)", "achieved": achieved, "peak": peak,
-                    "unit": "TFLOP/s", "frac": achieved / peak, "op": "int8 multiply-add = 2 ops",
-                    "fp64_equivalent_tflops": ((p + 2) * 2.0 * m_local * n * k + 2.0 * m_local * k * k * (1 + tn_passes * gram_frac))
+            peak_src = "fallback: 2 x 1361.4 TFLOP/s sustained bf16 (B200_PROFILING.md)"
+        fused_traffic = (m_local * (OZ2_TRAFFIC_NN_PER_ROW * nn_passes + OZ2_TRAFFIC_TN_PER_ROW * (tn_fold + tn_plain + 1))
+                         if (k == 256 and n == 1024 and S_dig == 6) else None)
+        roofline = {"bound": "tensor", "kernel": "oz2_kernel (tcgen05.mma.kind::i8 + fused digit slicing of A, NN + TN launches)", "achieved": achieved,
+                    "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "op": "int8 multiply-add = 2 ops",
+                    "whole_step_frac": i8_ops / (ms_step * 1e-3) / 1e12 / peak,
+                    "fp64_equivalent_tflops": ((p + 2) * 2.0 * m_local * n * k + 2.0 * m_local * k * k * (1 + (tn_fold + 1) * gram_frac))
                     / (mma_ms * 1e-3) / 1e12 if mma_ms > 0 else None,
-                    "digits": {"a_omega_and_u": S_dig, "at_y_with_fused_gram": S_tn}, "digit_pairs": {"a_omega_and_u": pairs, "at_y_with_fused_gram": pairs_tn},
-                    "traffic": (m_local * (OZ_TRAFFIC_NN_PER_ROW * (p // 2 + 1) + OZ_TRAFFIC_TN_PER_ROW * (7.0 / 6.0) * (p - p // 2 + 1))
-                                if (k == 256 and n == 1024 and S_dig == 6) else None),
-                    "traffic_source": OZ_TRAFFIC_SOURCE, "peak_source": peak_src,
+                    "digits": {"a_omega": S_dig, "u_and_at_y_in_power_iteration_and_gram": S_tn},
+                    "digit_pairs": {"a_omega_and_last_at_y": pairs, "u_and_at_y_in_power_iteration_and_gram": pairs_full},
+                    "int8_ops_per_step": i8_ops,
+                    "traffic": (STEP_TRAFFIC_PER_ROW * m_local) if (STEP_TRAFFIC_PER_ROW and k == 256 and n == 1024 and p == 2) else fused_traffic,
+                    "traffic_dominant_launches_only": fused_traffic,
+                    "traffic_algorithmic": 8.0 * m_local * n * (p + 2),
+                    "traffic_source": OZ_TRAFFIC_SOURCE, "peak_source": peak_src, "int8_peak_detail": i8_detail,
                     "class_ms_per_step": class_ms, "class_launches_per_step": class_launches,
                     "fp64_pipe_peak_tflops": fp64_peak, "fp64_pipe_peak_source": fp64_src,
                     "whole_step_vs_fp64_pipe_peak": (value / 1e3) / fp64_peak if fp64_peak else None}
@@ -552,6 +620,12 @@ def main():
         except Exception as e:  # noqa: BLE001
             e2e = {"value": None, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0, "error": f"{type(e).__name__}: {e}"}
 
+    parity = None
+    if not args.no_cpu and world == 1:
+        try:
+            parity = parity_sample(ctx, rl, n, k, p, q, min(args.m_cpu, 1 << 17))
+        except Exception as e:  # noqa: BLE001
+            parity = {"error": f"{type(e).__name__}: {e}"}
     cpu = None
     if not args.no_cpu and world == 1:
         try:
@@ -563,7 +637,7 @@ def main():
 
     out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-           "data": "synthetic", "config": config, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
+           "data": "synthetic", "config": config, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "parity": parity,
            "gpu_launches": launches, "flops_per_step": rsvd_flops(m_global, n, k, p, q),
            "flops_executed_per_step": sum(class_flops(m_global, n, k, p, q).values()),
            "note": "value = nominal algorithm flops F(m,n,k,p) (DESIGN.md, same F as the reference arm) / time; CholQR's m x k "

@@ -537,7 +537,8 @@ static int rsvd_single_block_fused(Ctx* ctx, int64_t m, int64_t n, T* A, int64_t
     if (ctx->fp64_engine == RLB200_FP64_I8SLICES && m >= kI8MinRows && k >= 64) {
         const int old = ctx->i8_digits;
         if (!old && sizeof(T) == 8) ctx->i8_digits = 7;
-        const int rc_u = ozaki_gemm_nn<T>(ctx, m, k, k, 1.0, U, m, M, k, 0.0, U, m);
+        const int rc_u = ozaki2_nn_ok(ctx, m, k, k, U, m * (int64_t)sizeof(T), U) ? ozaki2_gemm_nn<T>(ctx, m, k, k, 1.0, U, m, M, k, 0.0, U, m)
+                                                                                     : ozaki_gemm_nn<T>(ctx, m, k, k, 1.0, U, m, M, k, 0.0, U, m);
         ctx->i8_digits = old;
         RLB_CHECK(rc_u);
     } else RLB_CHECK(gemm_nn_inplace<T>(ctx, m, k, k, 1.0, U, m, M, k));

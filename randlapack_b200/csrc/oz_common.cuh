@@ -334,6 +334,14 @@ __device__ __forceinline__ void oz_mbar_wait(uint32_t bar, uint32_t parity) {
                      : "=r"(done) : "r"(bar), "r"(parity) : "memory");
     }
 }
+// acquire at cluster scope: the data guarded by the barrier may have been written by a peer CTA (distributed shared memory)
+__device__ __forceinline__ void oz_mbar_wait_cluster(uint32_t bar, uint32_t parity) {
+    uint32_t done = 0;
+    while (!done) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                     : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    }
+}
 // long waits (the epilogue warps wait for a whole tile's main loop): back off so that the spinning warps do not take issue slots from
 // the slicer CTAs that share the SM
 __device__ __forceinline__ void oz_mbar_wait_sleep(uint32_t bar, uint32_t parity) {

@@ -152,7 +152,8 @@ ozaki_mma_kernel(const int8_t* __restrict__ a_tiles, int64_t a_group_stride, con
         constexpr uint64_t HI = ((uint64_t)((MN ? 512 : 256) >> 4) | ((uint64_t)1 << 14)) << 32;
         uint32_t elected = 0;
         asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}\n" : "=r"(elected));
-        const uint32_t base_lo0 = (sbase >> 4) | ((uint32_t)(128 >> 4) << 16);
+        const uint32_t base_lo0 = sbase >> 4;
+        constexpr uint32_t LBO = (uint32_t)(128 >> 4) << 16;      // (start-address field = bits 4..17 of the address: a CTA's window inside a cluster does not start at 0)
         for (int kb = 0; kb < nkb; ++kb) {
             const int slot = kb % STAGES;
             oz_mbar_wait(oz_smem(&bar_full[slot]), (uint32_t)((kb / STAGES) & 1));
@@ -162,12 +163,12 @@ ozaki_mma_kernel(const int8_t* __restrict__ a_tiles, int64_t a_group_stride, con
                 const uint32_t lo = base_lo0 + (uint32_t)slot * (uint32_t)(Cfg::STAGE_BYTES >> 4);
 #pragma unroll
                 for (int s = 0; s < S; ++s) {
-                    const uint64_t da = HI | (uint64_t)(lo + (uint32_t)((s * OZ_TILE_A) >> 4));
+                    const uint64_t da = HI | (uint64_t)(((lo + (uint32_t)((s * OZ_TILE_A) >> 4)) & 0x3FFFu) | LBO);
 #pragma unroll
                     for (int t0 = 0; t0 < S - s; t0 += 4) {
                         const int nt = (S - s - t0) < 4 ? (S - s - t0) : 4;      // digit tiles of the second operand in this instruction
                         const uint32_t idesc = IDESC0 | ((uint32_t)((nt * OZ_BN) >> 3) << 17);
-                        const uint64_t db = HI | (uint64_t)(lo + (uint32_t)((S * OZ_TILE_A + t0 * OZ_TILE_B) >> 4));
+                        const uint64_t db = HI | (uint64_t)(((lo + (uint32_t)((S * OZ_TILE_A + t0 * OZ_TILE_B) >> 4)) & 0x3FFFu) | LBO);
                         oz_mma_i8(tmem + (uint32_t)((s + t0) * OZ_BN), da, db, idesc, (kb > 0 || s > 0) ? 1u : 0u);
                     }
                 }

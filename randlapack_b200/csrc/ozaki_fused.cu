@@ -45,9 +45,11 @@ struct Oz2Params {
     int nkb;                               // K blocks (of 32) per CTA
     int nbm, nbn_main, sp_main;
     void* out; int64_t ldo; int64_t out_group_stride; double alpha, beta;
+    int cluster_sync;                      // NN in place (out aliases X): the nbm CTAs of a row tile form a cluster and all finish reading before any writes
     double* gram_out; int64_t gram_group_stride;
     // diagnostics (RLB200_OZ2_DBG bit mask): 1 = per-CTA cycle stamps into dbg, 2 = converters skip the global loads,
-    // 4 = no proxy fence, 8 = converters skip the digit arithmetic (timing experiments only: 2/4/8 give wrong results)
+    // 4 = no proxy fence, 8 = converters skip the digit arithmetic, 16 = shared digits by plain remote stores + arrives, 32 = no MMAs
+    // (timing experiments only: 2/4/8/32 give wrong results)
     long long* dbg; int dbg_flags;
 };
 
@@ -89,20 +91,22 @@ __device__ __forceinline__ float oz2_ldg(const float* p) {
 
 // The tcgen05.mma instructions of one K step: s32 accumulate, signed int8 operands, M = 128; digit s of the M side times the stacked digits
 // 0 .. SP-1-s of the N side (<= 4 digit tiles = 256 columns per instruction), accumulator of anti-diagonal d at TMEM column 64 d.
-// lo: low word of the descriptor of the stage's first byte (start address >> 4 | LBO); the high word (SBO, version) is a constant.
+// lo: shared-memory address of the stage's first byte >> 4; the high word of a descriptor (SBO, version) is a constant.
 template <int SD, int SP, bool TN>
 __device__ __forceinline__ void oz2_issue_step(uint32_t lo, uint32_t tmem, bool first) {
     constexpr uint32_t IDESC0 = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(OZ_BM >> 4) << 24) | (TN ? ((1u << 15) | (1u << 16)) : 0u);
     constexpr uint64_t HI = ((uint64_t)((TN ? 512 : 256) >> 4) | ((uint64_t)1 << 14)) << 32;
+    constexpr uint32_t LBO = (uint32_t)(128 >> 4) << 16;
+    // (the start-address field holds bits 4..17 of the shared-memory address: inside a cluster a CTA's window does not start at 0)
 #pragma unroll
     for (int s = 0; s < SP; ++s) {
-        const uint64_t da = HI | (uint64_t)(lo + (uint32_t)((s * OZ_TILE_A) >> 4));
+        const uint64_t da = HI | (uint64_t)(((lo + (uint32_t)((s * OZ_TILE_A) >> 4)) & 0x3FFFu) | LBO);
 #pragma unroll
         for (int t0 = 0; t0 < SP - s; t0 += 4) {
             constexpr int dummy = 0; (void)dummy;
             const int nt = (SP - s - t0) < 4 ? (SP - s - t0) : 4;
             const uint32_t idesc = IDESC0 | ((uint32_t)((nt * OZ_BN) >> 3) << 17);
-            const uint64_t db = HI | (uint64_t)(lo + (uint32_t)((SD * OZ_TILE_A + t0 * OZ_TILE_B) >> 4));
+            const uint64_t db = HI | (uint64_t)(((lo + (uint32_t)((SD * OZ_TILE_A + t0 * OZ_TILE_B) >> 4)) & 0x3FFFu) | LBO);
             oz_mma_i8(tmem + (uint32_t)((s + t0) * OZ_BN), da, db, idesc, (!first || s > 0) ? 1u : 0u);
         }
     }
@@ -122,10 +126,21 @@ __global__ void __launch_bounds__(Oz2Threads<NG>::N, 1) oz2_kernel(const Oz2Para
     int by = (int)(blockIdx.x / (unsigned)p.nbm);
     const int g = blockIdx.z;
     const bool gram = by >= p.nbn_main;
+    // Cluster of cs = nbm CTAs (launched so when nbm is 2 or 4): the CTAs of one N tile.  They need the same digits of the tall operand, so each
+    // converts every cs-th K block and stores its digits into the stage of every CTA of the cluster (distributed shared memory): the global
+    // loads, the conversion arithmetic and the load-latency exposure per SM drop by cs.  Gram tiles stream both operands and share nothing.
+    uint32_t cs, crank;
+    asm volatile("mov.u32 %0, %%cluster_nctaid.x;" : "=r"(cs));
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
     if (gram) {
         by -= p.nbn_main;
-        if (by * OZ_BN > bx * OZ_BM + OZ_BM - 1) return;      // tiles touching the upper triangle only (row = N index <= column = M index)
+        if (by * OZ_BN > bx * OZ_BM + OZ_BM - 1) {             // tiles touching the upper triangle only (row = N index <= column = M index)
+            if (cs > 1) { oz_cluster_sync(); oz_cluster_sync(); }      // the two cluster barriers of the CTAs that do run
+            return;
+        }
     }
+    const uint32_t share = gram ? 1u : cs;                     // CTAs that exchange digits with this one
+    const uint16_t cmask = (uint16_t)((1u << cs) - 1u);
     long long t_cta0 = 0;
     if (p.dbg) t_cta0 = clock64();
     const int sp = gram ? SD : p.sp_main;                      // anti-diagonals (= leading digits of either operand) this CTA runs
@@ -138,11 +153,18 @@ __global__ void __launch_bounds__(Oz2Threads<NG>::N, 1) oz2_kernel(const Oz2Para
     __shared__ uint32_t tmem_base_sh;
     __shared__ int s_en[OZ_BN];                                // effective exponents of the N tile
     __shared__ int s_enmin, s_enmax;
+    // K blocks whose stage is free again, published by the producer thread (which waits for EVERY phase of every empty barrier in order).
+    // With shared digits a converter visits a given stage only every share * NG blocks - possibly more than DST, i.e. it may skip a phase
+    // of that stage's empty barrier, and a parity wait on it would then be ambiguous; it polls this counter instead.
+    __shared__ volatile int s_free_upto;
 
     if (tid == 0) {
+        s_free_upto = DST;
         for (int s = 0; s < DST; ++s) {
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(oz_smem(&bar_full[s])), "r"(gram ? 1 : 5));
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(oz_smem(&bar_empty[s])));
+            // full: the producer's arrive (+ the bytes of its bulk copies) and either the 4 converter warps of this CTA (one arrive each) or,
+            // when the digits are shared across a cluster, the bytes of the converters' st.async stores (counted by the same transaction count)
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(oz_smem(&bar_full[s])), "r"((gram || (cs > 1 && !(p.dbg_flags & 16))) ? 1 : 5));
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(oz_smem(&bar_empty[s])), "r"(share));   // every sharing CTA's MMAs release a slot
         }
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(oz_smem(&bar_acc)));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -160,6 +182,7 @@ __global__ void __launch_bounds__(Oz2Threads<NG>::N, 1) oz2_kernel(const Oz2Para
     }
     asm volatile("tcgen05.fence::before_thread_sync;");
     __syncthreads();
+    if (cs > 1) oz_cluster_sync();      // every CTA's barriers are initialised before a peer stores digits into it or signals it
     asm volatile("tcgen05.fence::after_thread_sync;");
     const uint32_t tmem = tmem_base_sh;
     const uint32_t sbase = oz_smem(oz2_smem_raw);
@@ -232,19 +255,27 @@ __global__ void __launch_bounds__(Oz2Threads<NG>::N, 1) oz2_kernel(const Oz2Para
                     for (int kk = 0; kk < 16; ++kk) raw[kk] = T(0);
                 }
             };
+            // shared::cluster addresses of the start of every sharing CTA's dynamic shared memory and of its bar_full array
+            uint32_t peer_smem[4], peer_full[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const uint32_t qq = (uint32_t)q < share ? (uint32_t)q : crank;
+                asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(peer_smem[q]) : "r"(sbase), "r"(qq));
+                asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(peer_full[q]) : "r"(oz_smem(&bar_full[0])), "r"(qq));
+            }
+            const int kb_first = (int)crank + (int)share * cgp, kb_stride = (int)share * NG;     // K block kb: CTA kb % share, group (kb / share) % NG
             const bool dbg_on = p.dbg != nullptr && tid == 0;
             long long c_wait = 0, c_conv = 0, c_fence = 0, c_load = 0;
             const bool skip_fence = (p.dbg_flags & 4) != 0, skip_math = (p.dbg_flags & 8) != 0;
-            T raw[16], nxt[16];
-            if (cgp < nkb) load_block(cgp, raw);
-#pragma unroll 1
-            for (int kb = cgp; kb < nkb; kb += NG) {
-                long long t0 = 0, t1 = 0, t2 = 0, t3 = 0;
-                if (dbg_on) t0 = clock64();
-                if (kb + NG < nkb) load_block(kb + NG, nxt);
+            // convert one K block (values already requested into `raw`) into stage kb % DST and publish it
+            auto convert_block = [&](int kb, const T (&raw)[16]) {
+                long long t1 = 0, t2 = 0, t3 = 0;
                 if (dbg_on) t1 = clock64();
                 const int slot = kb % DST;
-                if (kb >= DST) oz_mbar_wait(oz_smem(&bar_empty[slot]), (uint32_t)(((kb / DST) - 1) & 1));
+                if (kb >= DST) {
+                    if (share == 1) oz_mbar_wait(oz_smem(&bar_empty[slot]), (uint32_t)(((kb / DST) - 1) & 1));
+                    else while (s_free_upto <= kb) {}
+                }
                 if (dbg_on) t2 = clock64();
                 unsigned char* dst = oz2_smem_raw + slot * Cfg::STAGE_BYTES + SD * OZ_TILE_A + off;
                 uint32_t pk[4][SD];
@@ -262,17 +293,78 @@ __global__ void __launch_bounds__(Oz2Threads<NG>::N, 1) oz2_kernel(const Oz2Para
 #pragma unroll
                         for (int t = 0; t < SD; ++t) pk[q][t] = (uint32_t)__double_as_longlong((double)raw[4 * q + (t & 3)]);
                 }
+                if (share == 1) {
 #pragma unroll
-                for (int t = 0; t < SD; ++t)
-                    if (t < sp) *reinterpret_cast<uint4*>(dst + t * OZ_TILE_B) = make_uint4(pk[0][t], pk[1][t], pk[2][t], pk[3][t]);
-                if (dbg_on) t3 = clock64();
-                // generic-proxy stores -> visible to the tensor core's (async proxy) operand reads
-                if (!skip_fence) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                __syncwarp();
-                if (lane == 0) oz2_arrive(oz_smem(&bar_full[slot]));
+                    for (int t = 0; t < SD; ++t)
+                        if (t < sp) *reinterpret_cast<uint4*>(dst + t * OZ_TILE_B) = make_uint4(pk[0][t], pk[1][t], pk[2][t], pk[3][t]);
+                    if (dbg_on) t3 = clock64();
+                    // generic-proxy stores -> visible to the tensor core's (async proxy) operand reads
+                    if (!skip_fence) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) oz2_arrive(oz_smem(&bar_full[slot]));
+                } else {
+                    // st.async: each 16-byte store into a CTA of the cluster (this one included) reports its bytes to that CTA's full barrier
+                    // (release at cluster scope) - no fence, no arrive and no warp synchronisation on the writer's side; the consumer orders the
+                    // stores before the tensor core's async-proxy reads after its acquire (issuer warp)
+                    const uint32_t doff = (uint32_t)(slot * Cfg::STAGE_BYTES + SD * OZ_TILE_A + off);
+                    if (p.dbg_flags & 16) {
+                        // debugging alternative: plain remote stores, writer-side fence, one remote arrive per warp and CTA
 #pragma unroll
-                for (int kk = 0; kk < 16; ++kk) raw[kk] = nxt[kk];
-                if (dbg_on) { c_load += t1 - t0; c_wait += t2 - t1; c_conv += t3 - t2; c_fence += clock64() - t3; }
+                        for (int q = 0; q < 4; ++q) {
+                            if ((uint32_t)q < share) {
+#pragma unroll
+                                for (int t = 0; t < SD; ++t)
+                                    if (t < sp)
+                                        asm volatile("st.shared::cluster.v4.b32 [%0], {%1, %2, %3, %4};"
+                                                     ::"r"(peer_smem[q] + doff + (uint32_t)(t * OZ_TILE_B)), "r"(pk[0][t]), "r"(pk[1][t]), "r"(pk[2][t]), "r"(pk[3][t]) : "memory");
+                            }
+                        }
+                        asm volatile("fence.acq_rel.cluster;" ::: "memory");
+                        asm volatile("fence.proxy.async;" ::: "memory");
+                        __syncwarp();
+                        if (lane == 0) {
+#pragma unroll
+                            for (int q = 0; q < 4; ++q)
+                                if ((uint32_t)q < share)
+                                    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(peer_full[q] + (uint32_t)(slot * 8)) : "memory");
+                        }
+                    } else
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        if ((uint32_t)q < share) {
+                            const uint32_t bar = peer_full[q] + (uint32_t)(slot * 8);
+#pragma unroll
+                            for (int t = 0; t < SD; ++t)
+                                if (t < sp)
+                                    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];"
+                                                 ::"r"(peer_smem[q] + doff + (uint32_t)(t * OZ_TILE_B)), "r"(pk[0][t]), "r"(pk[1][t]), "r"(pk[2][t]), "r"(pk[3][t]),
+                                                   "r"(bar) : "memory");
+                        }
+                    }
+                    if (dbg_on) t3 = clock64();
+                }
+                if (dbg_on) { c_wait += t2 - t1; c_conv += t3 - t2; c_fence += clock64() - t3; }
+            };
+            // two register buffers used alternately (no copies: a copy would wait for the loads it is supposed to overlap): while block kb
+            // is converted from one buffer the loads of block kb + NG are in flight into the other
+            // Order inside an iteration: convert first (the values were requested two blocks of this group ago), THEN request the block
+            // after next into the buffer just consumed - the load issue is off the path between "stage free" and "stage full".
+            T bufa[16], bufb[16];
+            if (kb_first < nkb) load_block(kb_first, bufa);
+            if (kb_first + kb_stride < nkb) load_block(kb_first + kb_stride, bufb);
+#pragma unroll 1
+            for (int kb = kb_first; kb < nkb; kb += 2 * kb_stride) {
+                long long t0 = 0;
+                convert_block(kb, bufa);
+                if (dbg_on) t0 = clock64();
+                if (kb + 2 * kb_stride < nkb) load_block(kb + 2 * kb_stride, bufa);
+                if (dbg_on) c_load += clock64() - t0;
+                if (kb + kb_stride < nkb) {
+                    convert_block(kb + kb_stride, bufb);
+                    if (dbg_on) t0 = clock64();
+                    if (kb + 3 * kb_stride < nkb) load_block(kb + 3 * kb_stride, bufb);
+                    if (dbg_on) c_load += clock64() - t0;
+                }
             }
             if (dbg_on) {
                 long long* d = p.dbg + ((int64_t)blockIdx.z * gridDim.x + blockIdx.x) * 8;
@@ -285,10 +377,18 @@ __global__ void __launch_bounds__(Oz2Threads<NG>::N, 1) oz2_kernel(const Oz2Para
         const int8_t* gn = p.m_tiles + g * p.m_group_stride + (int64_t)(by >> 1) * p.nkb_stride * (SD * OZ_TILE_A) + (by & 1) * OZ_TILE_B;
         for (int kb = 0; kb < nkb; ++kb) {
             const int slot = kb % DST;
-            if (kb >= DST) oz_mbar_wait(oz_smem(&bar_empty[slot]), (uint32_t)(((kb / DST) - 1) & 1));
+            if (kb >= DST) {
+                oz_mbar_wait(oz_smem(&bar_empty[slot]), (uint32_t)(((kb / DST) - 1) & 1));
+                if (share > 1) s_free_upto = kb + 1;      // every sharing CTA's MMAs have consumed block kb - DST: its stage is free in all of them
+            }
             const uint32_t bar = oz_smem(&bar_full[slot]);
             const uint32_t dst = sbase + slot * Cfg::STAGE_BYTES;
-            const uint32_t bytes = (uint32_t)(sp * OZ_TILE_A + (gram ? SD * OZ_TILE_B : 0));
+            // bytes this barrier phase receives: the bulk copies below and, with shared digits, the converters' st.async stores
+            const uint32_t bytes = (uint32_t)(sp * OZ_TILE_A + (gram ? SD * OZ_TILE_B : ((share > 1 && !(p.dbg_flags & 16)) ? sp * OZ_TILE_B : 0)));
+            if ((p.dbg_flags & 64) && !gram) {     // timing experiment: no M-side bulk copies
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes - (uint32_t)(sp * OZ_TILE_A)) : "memory");
+                continue;
+            }
             asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
             oz_bulk_load(dst, gm + (int64_t)kb * (SD * OZ_TILE_A), (uint32_t)(sp * OZ_TILE_A), bar);
             if (gram) {
@@ -306,19 +406,30 @@ __global__ void __launch_bounds__(Oz2Threads<NG>::N, 1) oz2_kernel(const Oz2Para
         uint32_t elected = 0;
         asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}\n" : "=r"(elected));
         long long c_iwait = 0;
-        const uint32_t base_lo0 = (sbase >> 4) | ((uint32_t)(128 >> 4) << 16);       // start address | LBO (no-swizzle core matrices)
+        const uint32_t base_lo0 = sbase >> 4;
         for (int kb = 0; kb < nkb; ++kb) {
             const int slot = kb % DST;
             long long t0 = 0;
             if (p.dbg) t0 = clock64();
-            oz_mbar_wait(oz_smem(&bar_full[slot]), (uint32_t)((kb / DST) & 1));
+            if (share == 1) oz_mbar_wait(oz_smem(&bar_full[slot]), (uint32_t)((kb / DST) & 1));
+            else {
+                // the digits of this stage may come from a peer CTA: acquire at cluster scope, then order those generic-proxy stores before the
+                // tensor core's async-proxy reads on the consumer side as well
+                oz_mbar_wait_cluster(oz_smem(&bar_full[slot]), (uint32_t)((kb / DST) & 1));
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            }
             if (p.dbg) c_iwait += clock64() - t0;
             asm volatile("tcgen05.fence::after_thread_sync;");
             if (elected) {
                 const uint32_t lo = base_lo0 + (uint32_t)slot * (uint32_t)(Cfg::STAGE_BYTES >> 4);
-                if (sp == SD) oz2_issue_step<SD, SD, TN>(lo, tmem, kb == 0);
+                if (p.dbg_flags & 32) {}      // timing experiment: no MMAs (stages are released at once)
+                else if (sp == SD) oz2_issue_step<SD, SD, TN>(lo, tmem, kb == 0);
                 else oz2_issue_step<SD, (SD > 2 ? SD - 1 : SD), TN>(lo, tmem, kb == 0);
-                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(oz_smem(&bar_empty[slot])) : "memory");
+                if (share == 1)
+                    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(oz_smem(&bar_empty[slot])) : "memory");
+                else
+                    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                                 ::"r"(oz_smem(&bar_empty[slot])), "h"(cmask) : "memory");
             }
             __syncwarp();
         }
@@ -394,6 +505,9 @@ __global__ void __launch_bounds__(Oz2Threads<NG>::N, 1) oz2_kernel(const Oz2Para
     asm volatile("tcgen05.fence::before_thread_sync;");
     __syncthreads();
     if (warp == W_PROD) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(OzCfg<SD>::TMEM_COLS));
+    // in place: every CTA that reads this row tile (the cluster) has consumed all of its stages, i.e. has finished reading the rows
+    // and, when digits are shared: no peer still stores into, or signals, this CTA's shared memory once it has passed this barrier
+    if (cs > 1) oz_cluster_sync();
     // ---- phase 2: warp = one M index at a time, lanes = 64 consecutive N indices (contiguous in memory)
     {
         TO* outp = reinterpret_cast<TO*>(p.out);
@@ -428,13 +542,13 @@ __global__ void __launch_bounds__(Oz2Threads<NG>::N, 1) oz2_kernel(const Oz2Para
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
-constexpr int OZ2_NG = 3;
+constexpr int OZ2_NG = 2;      // converter groups (4 warps each): 2 fit 168 registers per thread without spills and measured fastest
 template <int SD, typename T, typename TO, bool TN>
 static int oz2_configure(Ctx* ctx) {
     static bool done_dev[64] = {};
     bool& done = done_dev[ctx->device & 63];
     if (!done) {
-        RLB_CUDA_OK(ctx, cudaFuncSetAttribute(oz2_kernel<SD, T, TO, TN, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Oz2Cfg<SD, T>::SMEM_BYTES));
+        RLB_CUDA_OK(ctx, cudaFuncSetAttribute(oz2_kernel<SD, T, TO, TN, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, Oz2Cfg<SD, T>::SMEM_BYTES));
         RLB_CUDA_OK(ctx, cudaFuncSetAttribute(oz2_kernel<SD, T, TO, TN, OZ2_NG>, cudaFuncAttributeMaxDynamicSharedMemorySize, Oz2Cfg<SD, T>::SMEM_BYTES));
         done = true;
     }
@@ -510,7 +624,21 @@ static int oz2_launch(Ctx* ctx, dim3 grid, cudaStream_t st, const Oz2Params& p_i
     const int64_t nctas = (int64_t)grid.x * grid.z;
     if (dbg_flags & 1) { cudaMalloc(&p.dbg, (size_t)nctas * 64); cudaMemsetAsync(p.dbg, 0, (size_t)nctas * 64, st); }
     static const int ng = getenv("RLB200_OZ2_NG") ? atoi(getenv("RLB200_OZ2_NG")) : OZ2_NG;
-    if (ng == 2) oz2_kernel<SD, T, TO, TN, 2><<<grid, Oz2Threads<2>::N, Oz2Cfg<SD, T>::SMEM_BYTES, st>>>(p);
+    // Clusters (digits of the tall operand shared by the nbm CTAs of an N tile): measured on B200 (m = 2^21, n = 1024, k = 256, 2 converter
+    // groups) TN 14.2 ms shared / 14.9 ms not shared, NN 13.8 / 12.6 - so TN shares, NN does not unless it is in place (where the cluster
+    // barrier is what makes it correct).  RLB200_OZ2_SHARE=0/1 forces either for experiments.
+    const int csz = (p.nbm == 2 || p.nbm == 4) ? p.nbm : 1;
+    if (p.cluster_sync && csz == 1 && p.nbm != 1) { ctx->err = "in-place product needs 1, 2 or 4 column tiles"; return RLB200_ERR_ARG; }
+    static const int share_env = getenv("RLB200_OZ2_SHARE") ? atoi(getenv("RLB200_OZ2_SHARE")) : -1;
+    const bool share = share_env >= 0 ? share_env != 0 : TN;
+    if (csz > 1 && (share || p.cluster_sync)) {
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = grid; cfg.blockDim = dim3(Oz2Threads<OZ2_NG>::N); cfg.dynamicSmemBytes = Oz2Cfg<SD, T>::SMEM_BYTES; cfg.stream = st;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = (unsigned)csz; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        RLB_CUDA_OK(ctx, cudaLaunchKernelEx(&cfg, oz2_kernel<SD, T, TO, TN, OZ2_NG>, p));
+    } else if (ng == 3) oz2_kernel<SD, T, TO, TN, 3><<<grid, Oz2Threads<3>::N, Oz2Cfg<SD, T>::SMEM_BYTES, st>>>(p);
     else oz2_kernel<SD, T, TO, TN, OZ2_NG><<<grid, Oz2Threads<OZ2_NG>::N, Oz2Cfg<SD, T>::SMEM_BYTES, st>>>(p);
     RLB_CUDA_OK(ctx, cudaGetLastError());
     if (p.dbg) {
@@ -533,7 +661,7 @@ static int oz2_launch(Ctx* ctx, dim3 grid, cudaStream_t st, const Oz2Params& p_i
     return 0;
 }
 
-// C(m x N) = alpha * A(m x K) * B(K x N) + beta * C; C must not alias A
+// C(m x N) = alpha * A(m x K) * B(K x N) + beta * C; C may be A itself (same pointer and leading dimension, N == K, beta == 0)
 template <int SD, typename T>
 static int oz2_nn(Ctx* ctx, int64_t m, int64_t N, int64_t K, double alpha, const T* A, int64_t lda, const T* B, int64_t ldb, double beta, T* C, int64_t ldc) {
     using Cfg = OzCfg<SD>;
@@ -571,6 +699,7 @@ static int oz2_nn(Ctx* ctx, int64_t m, int64_t N, int64_t K, double alpha, const
     p.nkb = nkb; p.nbm = nbm; p.nbn_main = (int)nbn; p.sp_main = SD;
     p.out = C; p.ldo = ldc; p.out_group_stride = 0; p.alpha = alpha; p.beta = beta;
     p.gram_out = nullptr; p.gram_group_stride = 0;
+    p.cluster_sync = ((const void*)A == (const void*)C) ? 1 : 0;
     LaunchScope ls(ctx, RLB200_TIMER_I8_MMA_NN);
     return oz2_launch<SD, T, T, false>(ctx, dim3((unsigned)(nbn * nbm), 1, 1), st, p);
 }
@@ -693,7 +822,12 @@ static int oz2_digits(Ctx* ctx, size_t elem) {
 // the raw tiles travel as 16-byte aligned bulk copies: base pointer and leading dimension (in bytes) must be multiples of 16
 static bool oz2_aligned(const void* A, int64_t ld_bytes) { return (reinterpret_cast<uintptr_t>(A) & 15) == 0 && (ld_bytes & 15) == 0; }
 bool ozaki2_nn_ok(Ctx* ctx, int64_t m, int64_t N, int64_t K, const void* A, int64_t lda_bytes, const void* C) {
-    return ctx->i8_fused && A != C && m > 0 && N >= 96 && K > 0 && K <= OZ_KMAX && oz2_aligned(A, lda_bytes);
+    // in place (C == A): the CTAs of a row tile synchronise as a cluster of ceil(N / 128) <= 8 before writing; the output must then cover
+    // exactly the columns that were read (N == K: U = Y M) so that no other row tile's input is touched
+    const bool inplace = A == C;
+    const int64_t nbm_ = (N + OZ_BM - 1) / OZ_BM;
+    if (inplace && !(N == K && (nbm_ == 1 || nbm_ == 2 || nbm_ == 4))) return false;
+    return ctx->i8_fused && m > 0 && N >= 96 && K > 0 && K <= OZ_KMAX && oz2_aligned(A, lda_bytes);
 }
 bool ozaki2_tn_ok(Ctx* ctx, int64_t m, int64_t N1, int64_t N2, const void* X, int64_t ldx_bytes) {
     return ctx->i8_fused && m > 0 && N1 > 0 && N2 >= 96 && oz2_aligned(X, ldx_bytes);
@@ -702,6 +836,7 @@ bool ozaki2_tn_ok(Ctx* ctx, int64_t m, int64_t N1, int64_t N2, const void* X, in
 template <typename T>
 int ozaki2_gemm_nn(Ctx* ctx, int64_t m, int64_t N, int64_t K, double alpha, const T* A, int64_t lda, const T* B, int64_t ldb, double beta, T* C, int64_t ldc) {
     RLB_REQUIRE(ctx, (ozaki2_nn_ok(ctx, m, N, K, A, lda * (int64_t)sizeof(T), C)) && N < (1 << 20));
+    RLB_REQUIRE(ctx, (const void*)A != (const void*)C || lda == ldc);
     switch (oz2_digits(ctx, sizeof(T))) {
         case 3: return oz2_nn<3, T>(ctx, m, N, K, alpha, A, lda, B, ldb, beta, C, ldc);
         case 4: return oz2_nn<4, T>(ctx, m, N, K, alpha, A, lda, B, ldb, beta, C, ldc);

@@ -209,3 +209,25 @@ def test_i8_fused_gemm_f32_storage(ctx):
     refz = A.double().t() @ Y.double()
     boundz = A.double().abs().t() @ Y.double().abs()
     assert ((Z.double() - refz).abs() / boundz).max().item() <= 2e-7
+
+
+@pytest.mark.parametrize("shape", [(70001, 256), (20000, 128), (33000, 384), (16500, 512)])
+@pytest.mark.parametrize("digits", [6, 7])
+def test_i8_fused_gemm_nn_inplace(ctx, shape, digits):
+    """U = Y M in place (rl_rsvd.hh:148 with U stored over Y): the ceil(N / 128) CTAs of a row tile form a cluster and synchronise between
+    their last read and their first write (1, 2 or 4 column tiles; 384 columns = 3 tiles take the staged engine).  Against torch fp64 and
+    against the out-of-place product (bit-identical)."""
+    m, k = shape
+    ctx.set_i8_digits(digits)
+    Y = _mk(m, k, 61)
+    M = _mk(k, k, 62)
+    try:
+        C = rl.gemm(ctx, False, False, 1.0, Y, M, engine="i8")
+        U = Y.clone()
+        rl.gemm(ctx, False, False, 1.0, U, M, 0.0, U, engine="i8")
+    finally:
+        ctx.set_i8_digits(0)
+    ref = Y @ M
+    bound = Y.abs() @ M.abs()
+    assert ((U - ref).abs() / bound).max().item() <= TOL[digits]
+    assert torch.equal(U, C)

@@ -7,7 +7,7 @@
 //   *_sw128                  : the same with SWIZZLE_128B K-major tiles (128-byte rows) instead of the no-swizzle core-matrix layout
 //   mix6 / mix7              : the 8 / 10 stacked-digit instructions of one K step of ozaki_fused.cu for 6 / 7 digits (21 / 28 pairs)
 //   pairs21                  : 21 separate N = 64 instructions (no stacking)
-// usage: peaks_i8 [seconds per sustained run, default 2]     -> one JSON object on stdout
+// usage: peaks_i8 [seconds per sustained run, default 2] [quick]     -> one JSON object on stdout
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -o tools/peaks_i8 tools/peaks_i8.cu
 #include <cstdint>
 #include <cstdio>
@@ -169,6 +169,7 @@ static Pattern make_pattern(const std::string& full) {
 
 int main(int argc, char** argv) {
     const double secs = argc > 1 ? atof(argv[1]) : 2.0;
+    const bool quick = argc > 2 && std::string(argv[2]) == "quick";     // only the peak pattern and the two engine mixes, cta_group::1
     int dev = 0, sms = 0;
     CK(cudaSetDevice(dev));
     CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
@@ -210,8 +211,9 @@ int main(int argc, char** argv) {
     const char* names[] = {"n256", "n192", "n128", "n64", "n256sameA", "n64sameA", "mix6", "mix7", "pairs21", "n256_sw128", "n128_sw128", "n64_sw128", "mix6_sw128", "mix7_sw128", "pairs21_sw128"};
     printf("{\"sms\": %d, \"results\": [", sms);
     bool first = true;
-    for (int cg = 1; cg <= 2; ++cg) {
+    for (int cg = 1; cg <= (quick ? 1 : 2); ++cg) {
         for (const char* nm : names) {
+            if (quick && std::string(nm) != "n256" && std::string(nm) != "mix6" && std::string(nm) != "mix7") continue;
             const Pattern pat = make_pattern(nm);
             double units = 0;                      // 64-wide N tiles per K step
             for (int i = 0; i < pat.n; ++i) units += pat.ins[i].ntiles;
