@@ -11,6 +11,7 @@
 //   RandLAPACK::QBalg / QB            comps/rl_qb.hh:17-268                rlb200::QB<T>
 //   RandLAPACK::RSVDalg / RSVD        drivers/rl_rsvd.hh:15-154            rlb200::RSVD<T>
 //   RandLAPACK::CQRRPTalg / CQRRPT    drivers/rl_cqrrpt.hh:20-391          rlb200::CQRRPT<T>
+//   RandLAPACK::CQRRTalg / CQRRT      drivers/rl_cqrrt.hh:20-297           rlb200::CQRRT<T>
 //   RandLAPACK::BQRRPalg / BQRRP      drivers/rl_bqrrp.hh:19-665           rlb200::BQRRP<T>
 //   RandLAPACK::BQRRP_GPU_alg / BQRRP_GPU  drivers/rl_bqrrp_gpu.hh:27-942   rlb200::BQRRP_GPU<T>   (device pointers, sketch as input)
 //
@@ -98,13 +99,13 @@ template <> struct abi<double> {
     static constexpr auto stab = rlb200_stab_f64_dev; static constexpr auto rs = rlb200_rs_f64_dev; static constexpr auto rf = rlb200_rf_f64_dev;
     static constexpr auto qb = rlb200_qb_f64_dev; static constexpr auto rsvd_host = rlb200_rsvd_f64_host;
     static constexpr auto cqrrpt_host = rlb200_cqrrpt_f64_host; static constexpr auto bqrrp_host = rlb200_bqrrp_f64_host;
-    static constexpr auto bqrrp_dev_sk = rlb200_bqrrp_f64_dev_sk;
+    static constexpr auto bqrrp_dev_sk = rlb200_bqrrp_f64_dev_sk; static constexpr auto cqrrt_host = rlb200_cqrrt_f64_host;
 };
 template <> struct abi<float> {
     static constexpr auto stab = rlb200_stab_f32_dev; static constexpr auto rs = rlb200_rs_f32_dev; static constexpr auto rf = rlb200_rf_f32_dev;
     static constexpr auto qb = rlb200_qb_f32_dev; static constexpr auto rsvd_host = rlb200_rsvd_f32_host;
     static constexpr auto cqrrpt_host = rlb200_cqrrpt_f32_host; static constexpr auto bqrrp_host = rlb200_bqrrp_f32_host;
-    static constexpr auto bqrrp_dev_sk = rlb200_bqrrp_f32_dev_sk;
+    static constexpr auto bqrrp_dev_sk = rlb200_bqrrp_f32_dev_sk; static constexpr auto cqrrt_host = rlb200_cqrrt_f32_host;
 };
 
 // device buffer staged from / to a host pointer
@@ -340,6 +341,39 @@ public:
     int64_t rank;
     std::vector<long> times;   // kept for source compatibility; per-phase host timing is not offered (see rlb200_timer_read)
     int64_t nnz;
+private:
+    Context* ctx_;
+};
+
+// ---------------------------------------------------------------------------------------------------------------------
+// CQRRT (rl_cqrrt.hh:20-297): unpivoted sketched Cholesky QR; same constructor (time_subroutines, eps), public fields and call signature
+// (HOST pointers).
+// ---------------------------------------------------------------------------------------------------------------------
+template <typename T>
+class CQRRT
+#ifdef RLB200_WITH_RANDLAPACK
+    : public RandLAPACK::CQRRTalg<T, r123::Philox4x32>
+#endif
+{
+public:
+    CQRRT(bool time_subroutines, T ep) : CQRRT(default_context(), time_subroutines, ep) {}
+    CQRRT(Context& c, bool time_subroutines, T ep)
+        : timing(time_subroutines), eps(ep), nnz(2), orthogonalization(false), compute_Q(true), ctx_(&c) {}
+    virtual ~CQRRT() {}
+    // A (m x n, lda) <- Q; R (ldr >= n): n x n upper triangular (rl_cqrrt.hh:91-101)
+    int call(int64_t m, int64_t n, T* A, int64_t lda, T* R, int64_t ldr, T d_factor, state_t& state) RLB200_OVERRIDE {
+        uint32_t w[6]; state_to_words(state, w);
+        int rc = ctx_->check(detail::abi<T>::cqrrt_host(ctx_->get(), m, n, A, lda, R, ldr, d_factor, nnz, orthogonalization ? 1 : 0,
+                                                        compute_Q ? 1 : 0, w));
+        words_to_state(w, state);
+        return rc;
+    }
+    bool timing;
+    T eps;
+    std::vector<long> times;
+    int64_t nnz;
+    bool orthogonalization;
+    bool compute_Q;
 private:
     Context* ctx_;
 };

@@ -249,6 +249,20 @@ RLB200_API int rlb200_cqrrpt_f64_host(rlb200_ctx* ctx, int64_t m, int64_t n, dou
 RLB200_API int rlb200_cqrrpt_f32_host(rlb200_ctx* ctx, int64_t m, int64_t n, float* A, int64_t lda, float* R, int64_t ldr, int64_t* J,
                            float d_factor, float eps, int64_t nnz, int64_t* rank, uint32_t state[6]);
 
+/* ---- f1: CQRRT<T,RNG>::call(m, n, A, lda, R, ldr, d_factor, state) (RandLAPACK/drivers/rl_cqrrt.hh:20-37 base, :91-297 body): unpivoted
+ *      sketched Cholesky QR.  nnz, orthogonalization, compute_Q are the object's public fields (ctor defaults 2, false, true, :46-50).
+ * On exit A holds Q (m x n; A R_sk^-1 only, when compute_Q == 0), the upper triangle of R the n x n factor (R_chol itself when
+ * orthogonalization != 0); state <- S.next_state.  Returns the reference's codes: 0, or 1 when the sketch's R has a zero diagonal entry
+ * (:173-177) or the Cholesky factorization fails (:194-198).  Row-shardable like CQRRPT (sketch and Gram matrix are sum-allreduced). */
+RLB200_API int rlb200_cqrrt_f64_dev(rlb200_ctx* ctx, int64_t m, int64_t n, double* A_dev, int64_t lda, double* R_dev, int64_t ldr, double d_factor,
+                         int64_t nnz, int orthogonalization, int compute_Q, uint32_t state[6]);
+RLB200_API int rlb200_cqrrt_f32_dev(rlb200_ctx* ctx, int64_t m, int64_t n, float* A_dev, int64_t lda, float* R_dev, int64_t ldr, float d_factor,
+                         int64_t nnz, int orthogonalization, int compute_Q, uint32_t state[6]);
+RLB200_API int rlb200_cqrrt_f64_host(rlb200_ctx* ctx, int64_t m, int64_t n, double* A, int64_t lda, double* R, int64_t ldr, double d_factor,
+                          int64_t nnz, int orthogonalization, int compute_Q, uint32_t state[6]);
+RLB200_API int rlb200_cqrrt_f32_host(rlb200_ctx* ctx, int64_t m, int64_t n, float* A, int64_t lda, float* R, int64_t ldr, float d_factor,
+                          int64_t nnz, int orthogonalization, int compute_Q, uint32_t state[6]);
+
 /* ---- a15: BQRRP<T,RNG>::call(m, n, A, lda, d_factor, tau, J, state) (RandLAPACK/drivers/rl_bqrrp.hh:154-665), and the
  *      device-pointer convention of BQRRP_GPU::call (rl_bqrrp_gpu.hh:152-942).  block_size, qrcp_wide, qr_tall are the object's
  *      fields: block_size = ctor's b_sz; qrcp_wide: 0 = luqr (default), 1 = geqp3; qr_tall: 0 = geqrf (default), 1 = cholqr

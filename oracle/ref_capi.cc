@@ -18,6 +18,7 @@
 #include "RandLAPACK/comps/rl_qb.hh"
 #include "RandLAPACK/drivers/rl_rsvd.hh"
 #include "RandLAPACK/drivers/rl_cqrrpt.hh"
+#include "RandLAPACK/drivers/rl_cqrrt.hh"
 #include "RandLAPACK/drivers/rl_bqrrp.hh"
 #include "RandLAPACK/testing/rl_gen.hh"
 
@@ -225,6 +226,22 @@ static int cqrrpt_impl(int64_t m, int64_t n, T* A, int64_t lda, T* R, int64_t ld
     RL_CATCH
 }
 
+// CQRRT (RandLAPACK/drivers/rl_cqrrt.hh:91-297)
+template <typename T>
+static int cqrrt_impl(int64_t m, int64_t n, T* A, int64_t lda, T* R, int64_t ldr, T d_factor, T eps, int64_t nnz, int orthogonalization,
+                      int compute_Q, uint32_t state[6]) {
+    RL_TRY
+    RandLAPACK::CQRRT<T, RNG> alg(false, eps);
+    alg.nnz = nnz;
+    alg.orthogonalization = orthogonalization != 0;
+    alg.compute_Q = compute_Q != 0;
+    State st = load_state(state);
+    int rc = alg.call(m, n, A, lda, R, ldr, d_factor, st);
+    store_state(st, state);
+    return rc;
+    RL_CATCH
+}
+
 // BQRRP (RandLAPACK/drivers/rl_bqrrp.hh:154-665). qrcp_wide: 0 luqr (default), 1 geqp3; qr_tall: 0 geqrf (default), 1 cholqr, 2 geqrt
 template <typename T>
 static int bqrrp_impl(int64_t m, int64_t n, T* A, int64_t lda, T d_factor, int64_t b_sz, int qrcp_wide, int qr_tall, T* tau, int64_t* J,
@@ -350,6 +367,10 @@ int rlref_mat_gen_f32(int type, int64_t m, int64_t n, int64_t rank, float cond, 
     int rlref_cqrrpt_##SUF(int64_t m, int64_t n, T* A, int64_t lda, T* R, int64_t ldr, int64_t* J, T d_factor, T eps, int64_t nnz,         \
                            int qrcp, int64_t* rank, uint32_t state[6]) {                                                                   \
         return cqrrpt_impl<T>(m, n, A, lda, R, ldr, J, d_factor, eps, nnz, qrcp, rank, state);                                             \
+    }                                                                                                                                     \
+    int rlref_cqrrt_##SUF(int64_t m, int64_t n, T* A, int64_t lda, T* R, int64_t ldr, T d_factor, T eps, int64_t nnz, int orthogonalization,     \
+                          int compute_Q, uint32_t state[6]) {                                                                              \
+        return cqrrt_impl<T>(m, n, A, lda, R, ldr, d_factor, eps, nnz, orthogonalization, compute_Q, state);                               \
     }                                                                                                                                     \
     int rlref_bqrrp_##SUF(int64_t m, int64_t n, T* A, int64_t lda, T d_factor, int64_t b_sz, int qrcp_wide, int qr_tall, T* tau,           \
                           int64_t* J, int64_t* rank, uint32_t state[6]) {                                                                  \

@@ -555,6 +555,40 @@ class CQRRPT:
         return 0, A, R, J, state
 
 
+class CQRRT:
+    """RandLAPACK::CQRRT(timing, eps) (rl_cqrrt.hh:39-297); fields nnz (= 2), orthogonalization (False), compute_Q (True)."""
+
+    def __init__(self, eps=None, nnz=2):
+        self.eps, self.nnz, self.orthogonalization, self.compute_Q = eps, nnz, False, True
+
+    def call(self, A, d_factor, state: RNGState, R=None):
+        """-> (rc, Q m x n, R n x n, next state)."""
+        A = _F(np.array(A, copy=True))
+        m, n = A.shape
+        dt = A.dtype
+        R = np.zeros((n, n), dtype=dt, order="F") if R is None else _F(np.array(R, copy=True))
+        d = int(dt.type(d_factor) * dt.type(n))                                     # :135
+        A_hat, state = sketch_sparse_left(d, m, self.nnz, d, A, state)              # :144-152
+        geqrf, potrf = get_lapack_funcs(("geqrf", "potrf"), (A_hat,))
+        (trsm_,) = get_blas_funcs(("trsm",), (A,))
+        wq = geqrf(A_hat, lwork=-1)
+        A_hat, tau = geqrf(A_hat, lwork=int(wq[-2][0]))[:2]                         # :160
+        R[:n, :n] = np.triu(A_hat[:n, :n]) + np.tril(R[:n, :n], -1)                 # lacpy(Upper) :167
+        if np.any(np.diag(R) == 0):                                                 # :173-177
+            return 1, A, R, state
+        A = trsm_(1.0, _F(R), A, side=1, lower=0)                                   # :178
+        G = np.triu(_gemm(A, A, ta=True))                                           # syrk(Upper) :186
+        c, info = potrf(_F(G + np.tril(R, -1)), lower=0, clean=0)                   # :194
+        R[:, :] = c
+        if info:
+            return 1, A, R, state
+        if self.compute_Q:
+            A = trsm_(1.0, _F(R), A, side=1, lower=0)                               # :238
+        if not self.orthogonalization:
+            R[:, :] = np.triu(R) @ np.triu(A_hat[:n, :n]) + np.tril(R, -1)          # trmm :249
+        return 0, A, R, state
+
+
 # --------------------------------------------------------------------------------------------
 # BQRRP (RandLAPACK/drivers/rl_bqrrp.hh:154-665)
 # --------------------------------------------------------------------------------------------

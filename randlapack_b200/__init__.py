@@ -565,6 +565,39 @@ class CQRRPT:
         return rc, R, J
 
 
+class CQRRT:
+    """RandLAPACK::CQRRT(time_subroutines, eps) (rl_cqrrt.hh:39-89); public fields nnz (= 2), orthogonalization (False), compute_Q (True)."""
+
+    def __init__(self, time_subroutines=False, eps=None):
+        self.timing, self.eps = time_subroutines, eps
+        self.nnz, self.orthogonalization, self.compute_Q = 2, False, True
+
+    def call(self, ctx: Context, A, d_factor, state: RNGState, R=None):
+        """A (m x n device, column-major) is overwritten by Q; -> (rc, R n x n column-major device)."""
+        torch = _torch()
+        assert _is_f(A)
+        m, n = A.shape
+        R = torch.zeros((n, n), dtype=A.dtype, device=A.device).t() if R is None else R
+        w = state.words()
+        fn = getattr(ctx._lib, f"rlb200_cqrrt_{_suffix(A.dtype)}_dev")
+        rc = ctx.check(fn(ctx._h, m, n, A.data_ptr(), _ld(A), R.data_ptr(), _ld(R), d_factor, self.nnz, int(self.orthogonalization),
+                          int(self.compute_Q), w))
+        state.assign(w)
+        return rc, R
+
+    def call_host(self, ctx: Context, A_host, d_factor, state: RNGState, R=None):
+        torch = _torch()
+        assert _is_f(A_host) and not A_host.is_cuda
+        m, n = A_host.shape
+        R = torch.zeros((n, n), dtype=A_host.dtype).t() if R is None else R
+        w = state.words()
+        fn = getattr(ctx._lib, f"rlb200_cqrrt_{_suffix(A_host.dtype)}_host")
+        rc = ctx.check(fn(ctx._h, m, n, A_host.data_ptr(), _ld(A_host), R.data_ptr(), _ld(R), d_factor, self.nnz, int(self.orthogonalization),
+                          int(self.compute_Q), w))
+        state.assign(w)
+        return rc, R
+
+
 class BQRRP:
     """RandLAPACK::BQRRP(time_subroutines, b_sz) (rl_bqrrp.hh:43-152); public fields block_size, qrcp_wide, qr_tall, rank.
     Defaults are the reference's (luqr + geqrf); BQRRP_GPU's configuration is qr_tall = QRTALL_CHOLQR."""

@@ -83,6 +83,8 @@ for _suf, _ft in (("f64", ctypes.c_double), ("f32", ctypes.c_float)):
         SIGNATURES[f"rlb200_{_name}_{_suf}_dev"] = _sig
     SIGNATURES[f"rlb200_cqrrpt_{_suf}_host"] = (c_int, [c_vp, c_i64, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, _ft, _ft, c_i64, P_i64, P_u32])
     SIGNATURES[f"rlb200_bqrrp_{_suf}_host"] = (c_int, [c_vp, c_i64, c_i64, c_vp, c_i64, _ft, c_i64, c_int, c_int, c_vp, c_vp, P_i64, P_u32])
+    SIGNATURES[f"rlb200_cqrrt_{_suf}_dev"] = (c_int, [c_vp, c_i64, c_i64, c_vp, c_i64, c_vp, c_i64, _ft, c_i64, c_int, c_int, P_u32])
+    SIGNATURES[f"rlb200_cqrrt_{_suf}_host"] = (c_int, [c_vp, c_i64, c_i64, c_vp, c_i64, c_vp, c_i64, _ft, c_i64, c_int, c_int, P_u32])
     SIGNATURES[f"rlb200_bqrrp_{_suf}_dev_sk"] = (c_int, [c_vp, c_i64, c_i64, c_vp, c_i64, c_vp, c_i64, c_i64, c_int, c_vp, c_vp, P_i64])
     SIGNATURES[f"rlb200_rsvd_{_suf}_host"] = (c_int, [c_vp, c_i64, c_i64, c_vp, P_i64, _ft, c_vp, c_vp, c_vp, P_u32,
                                                       ctypes.POINTER(StackOpts), P_int])

@@ -270,6 +270,29 @@ int rlb200_set_i8_digits(rlb200_ctx* ctx, int digits) {
         RLB_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));                                                                       \
         return rc;                                                                                                                  \
     }                                                                                                                               \
+    int rlb200_cqrrt_##SUF##_dev(rlb200_ctx* ctx, int64_t m, int64_t n, T* A_dev, int64_t lda, T* R_dev, int64_t ldr, T d_factor, int64_t nnz,   \
+                                 int orthogonalization, int compute_Q, uint32_t state[6]) {                                         \
+        CTX_OK(ctx); RLB_CHECK(bind(ctx)); RLB_REQUIRE(ctx, state != nullptr);                                                      \
+        return cqrrt_call<T>(ctx, m, n, A_dev, lda, R_dev, ldr, d_factor, nnz, orthogonalization, compute_Q, state);                \
+    }                                                                                                                               \
+    int rlb200_cqrrt_##SUF##_host(rlb200_ctx* ctx, int64_t m, int64_t n, T* A, int64_t lda, T* R, int64_t ldr, T d_factor, int64_t nnz,  \
+                                  int orthogonalization, int compute_Q, uint32_t state[6]) {                                        \
+        CTX_OK(ctx); RLB_CHECK(bind(ctx)); RLB_REQUIRE(ctx, state != nullptr);                                                      \
+        RLB_REQUIRE(ctx, m >= 0 && n >= 0 && lda >= m && ldr >= n);                                                                 \
+        if (m == 0 || n == 0) return cqrrt_call<T>(ctx, m, n, A, lda, R, ldr, d_factor, nnz, orthogonalization, compute_Q, state);  \
+        RLB_REQUIRE(ctx, A && R);                                                                                                   \
+        ArenaScope as(ctx);                                                                                                         \
+        T* dA = as.take<T>((size_t)m * n); if (!dA) return RLB200_ERR_ALLOC;                                                        \
+        T* dR = as.take<T>((size_t)n * n); if (!dR) return RLB200_ERR_ALLOC;                                                        \
+        RLB_CUDA_OK(ctx, cudaMemcpy2DAsync(dA, m * sizeof(T), A, lda * sizeof(T), m * sizeof(T), n, cudaMemcpyHostToDevice, ctx->stream)); \
+        RLB_CUDA_OK(ctx, cudaMemcpy2DAsync(dR, n * sizeof(T), R, ldr * sizeof(T), n * sizeof(T), n, cudaMemcpyHostToDevice, ctx->stream)); \
+        int rc = cqrrt_call<T>(ctx, m, n, dA, m, dR, n, d_factor, nnz, orthogonalization, compute_Q, state);                        \
+        if (rc < 0) return rc;                                                                                                      \
+        RLB_CUDA_OK(ctx, cudaMemcpy2DAsync(A, lda * sizeof(T), dA, m * sizeof(T), m * sizeof(T), n, cudaMemcpyDeviceToHost, ctx->stream)); \
+        RLB_CUDA_OK(ctx, cudaMemcpy2DAsync(R, ldr * sizeof(T), dR, n * sizeof(T), n * sizeof(T), n, cudaMemcpyDeviceToHost, ctx->stream)); \
+        RLB_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));                                                                       \
+        return rc;                                                                                                                  \
+    }                                                                                                                               \
     int rlb200_bqrrp_##SUF##_dev(rlb200_ctx* ctx, int64_t m, int64_t n, T* A_dev, int64_t lda, T d_factor, int64_t block_size,      \
                                  int qrcp_wide, int qr_tall, T* tau_dev, int64_t* J_dev, int64_t* rank, uint32_t state[6]) {        \
         CTX_OK(ctx); RLB_CHECK(bind(ctx)); RLB_REQUIRE(ctx, state && rank);                                                         \

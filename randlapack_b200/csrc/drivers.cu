@@ -709,7 +709,67 @@ int cqrrpt_call(Ctx* ctx, int64_t m, int64_t n, T* A, int64_t lda, T* R, int64_t
     return 0;
 }
 
+// ------------------------------------------------------------------------------------------------
+// CQRRT  (RandLAPACK/drivers/rl_cqrrt.hh:91-297): unpivoted sketched Cholesky QR - CQRRPT without the column pivoting
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+int cqrrt_call(Ctx* ctx, int64_t m, int64_t n, T* A, int64_t lda, T* R, int64_t ldr, T d_factor, int64_t nnz, int orthogonalization, int compute_Q,
+               uint32_t state[6]) {
+    // :103-109
+    RLB_REQUIRE(ctx, m >= 0);
+    RLB_REQUIRE(ctx, n >= 0);
+    RLB_REQUIRE(ctx, lda >= m);
+    RLB_REQUIRE(ctx, ldr >= n);
+    RLB_REQUIRE(ctx, d_factor >= (T)1.0);
+    RLB_REQUIRE(ctx, !(A == nullptr && m > 0 && n > 0));
+    RLB_REQUIRE(ctx, !(R == nullptr && n > 0));
+    const bool sharded = ctx->m_global >= 0;
+    const int64_t mg = sharded ? ctx->m_global : m;
+    if (n == 0) return 0;
+    RLB_REQUIRE(ctx, mg > 0);
+    const int64_t d = (int64_t)(d_factor * (T)n);                                             // :135
+    RLB_REQUIRE(ctx, d <= mg);                                                                // SparseDist(d, m): the operator must be wide
+    ArenaScope as(ctx);
+    T* A_hat = as.take<T>((size_t)d * n); RLB_ALLOC(ctx, A_hat);
+    T* tau = as.take<T>((size_t)n); RLB_ALLOC(ctx, tau);
+    // SASO (:144-152); state <- S.next_state
+    RLB_CHECK(sketch_sparse_left<T>(ctx, d, mg, nnz, d, n, m, (T)1, 0, 0, A, lda, (T)0, A_hat, d, state));
+    // geqrf of the sketch (:160)
+    {
+        ArenaScope as2(ctx);
+        void* ws = arena_push(ctx, qrcp_ws_bytes(n)); RLB_ALLOC(ctx, ws);
+        RLB_CHECK(qr_small<T>(ctx, false, d, n, A_hat, d, nullptr, tau, ws));
+    }
+    RLB_CHECK(tri_op<T>(ctx, 0, n, n, A_hat, d, R, ldr));                                     // lacpy(Upper) :167
+    std::vector<T> dg;
+    RLB_CHECK(read_diag<T>(ctx, A_hat, d, n, dg));
+    for (int64_t i = 0; i < n; ++i) if (dg[i] == (T)0) return 1;                              // diag_is_nonzero :173-177
+    RLB_CHECK(tall_right_solve<T>(ctx, m, n, R, ldr, A, lda));                                // :178 A <- A R_sk^-1
+    // Gram matrix and its Cholesky factor (:186, :194): built in scratch so that only the upper triangle of R is written
+    T* G = as.take<T>((size_t)n * n); RLB_ALLOC(ctx, G);
+    RLB_CUDA_OK(ctx, cudaMemsetAsync(G, 0, sizeof(T) * n * n, ctx->stream));
+    RLB_CHECK(tall_gram_upper<T>(ctx, m, n, A, lda, G, n));
+    if (sharded) RLB_CHECK(allreduce_sum<T>(ctx, G, n * n));
+    int info = 0;
+    RLB_CHECK(potrf_blocked<T>(ctx, n, G, n, &info));
+    RLB_CHECK(tri_op<T>(ctx, 0, n, n, G, n, R, ldr));
+    if (info != 0) { RLB_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream)); return 1; }        // :194-198
+    if (compute_Q) RLB_CHECK(tall_right_solve<T>(ctx, m, n, R, ldr, A, lda));                 // :238 Q = A R_chol^-1
+    if (!orthogonalization) {
+        // R <- R_chol * triu(A_hat[0:n, 0:n])  (trmm :249)
+        T* U = as.take<T>((size_t)n * n); RLB_ALLOC(ctx, U);
+        T* Rin = as.take<T>((size_t)n * n); RLB_ALLOC(ctx, Rin);
+        RLB_CHECK(tri_op<T>(ctx, 2, n, n, A_hat, d, U, n));
+        RLB_CHECK(tri_op<T>(ctx, 2, n, n, R, ldr, Rin, n));
+        RLB_CHECK(gemm_nn<T>(ctx, n, n, n, 1.0, Rin, n, U, n, 0.0, G, n));
+        RLB_CHECK(tri_op<T>(ctx, 0, n, n, G, n, R, ldr));
+    }
+    RLB_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));   // scratch is released on return
+    return 0;
+}
+
 #define INST(T)                                                                                                             \
+    template int cqrrt_call<T>(Ctx*, int64_t, int64_t, T*, int64_t, T*, int64_t, T, int64_t, int, int, uint32_t*);          \
     template int stab_call<T>(Ctx*, int, int64_t, int64_t, T*, bool, bool, int*);                                           \
     template int rs_call<T>(Ctx*, int64_t, int64_t, const T*, int64_t, T*, T*, uint32_t*, const rlb200_stack_opts&);         \
     template int rf_call<T>(Ctx*, int64_t, int64_t, const T*, int64_t, T*, uint32_t*, const rlb200_stack_opts&);             \

@@ -140,6 +140,11 @@ template <typename T>
 int cqrrpt_call(Ctx* ctx, int64_t m, int64_t n, T* A, int64_t lda, T* R, int64_t ldr, int64_t* J_dev, T d_factor, T eps, int64_t nnz,
                 int64_t* rank_out, uint32_t state[6]);
 
+// CQRRT::call (rl_cqrrt.hh:91-297): unpivoted; returns 0, or 1 when the sketch's R has a zero diagonal entry or the Cholesky factorization fails.
+template <typename T>
+int cqrrt_call(Ctx* ctx, int64_t m, int64_t n, T* A, int64_t lda, T* R, int64_t ldr, T d_factor, int64_t nnz, int orthogonalization, int compute_Q,
+               uint32_t state[6]);
+
 // BQRRP::call (rl_bqrrp.hh:154-665).  qrcp_wide: 0 luqr (default), 1 geqp3; qr_tall: 0 geqrf (default), 1 cholqr (+orhr_col), 2 geqrt.
 // A_sk_ext != nullptr: BQRRP_GPU::call (rl_bqrrp_gpu.hh:152-942) - the d_ext x n sketch (leading dimension d_ext) is the caller's and is
 // overwritten; d_factor and state are not used.

@@ -154,6 +154,20 @@ def ref_cqrrpt(lib, A, d_factor, seed6, eps=None, nnz=2, qrcp=0):
     return rc, rank.value, Q, R, J, list(st)
 
 
+def ref_cqrrt(lib, A, d_factor, seed6, nnz=2, orthogonalization=False, compute_Q=True):
+    """RandLAPACK::CQRRT::call via the compiled reference -> (rc, Q m x n, R n x n, state)."""
+    m, n = A.shape
+    dt = A.dtype
+    Q = np.asfortranarray(A.copy())
+    R = np.zeros((n, n), dtype=dt, order="F")
+    st = (u32 * 6)(*seed6)
+    ft = _ft(dt)
+    f = getattr(lib, f"rlref_cqrrt_{_suf(dt)}")
+    f.argtypes = [i64, i64, ctypes.c_void_p, i64, ctypes.c_void_p, i64, ft, ft, i64, ctypes.c_int, ctypes.c_int, ctypes.POINTER(u32)]
+    rc = f(m, n, Q.ctypes.data, m, R.ctypes.data, n, d_factor, float(np.finfo(dt).eps), nnz, int(orthogonalization), int(compute_Q), st)
+    return rc, Q, R, list(st)
+
+
 def ref_bqrrp(lib, A, d_factor, b_sz, seed6, qrcp_wide=0, qr_tall=0):
     """RandLAPACK::BQRRP::call via the compiled reference -> (rc, rank, A_out [GEQP3 format], tau, J, state)."""
     m, n = A.shape

@@ -16,6 +16,7 @@
 #include "RandLAPACK/comps/rl_qb.hh"
 #include "RandLAPACK/drivers/rl_rsvd.hh"
 #include "RandLAPACK/drivers/rl_cqrrpt.hh"
+#include "RandLAPACK/drivers/rl_cqrrt.hh"
 #include "RandLAPACK/drivers/rl_bqrrp.hh"
 #include "RandLAPACK/testing/rl_gen.hh"
 #define RLB200_WITH_RANDLAPACK

@@ -208,3 +208,51 @@ def test_cqrrpt_engine_vs_oracle_blocked_sizes(ctx, cond):
     assert np.abs(R[:r] - R2[:r]).max() <= 1e-8 * np.abs(R2).max()
     e = qr_invariants(A, Q, R, J, r)
     assert max(e) <= np.finfo(np.float64).eps ** 0.75, e
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
+# CQRRT (rl_cqrrt.hh:91-297): unpivoted sketched Cholesky QR on the same kernels
+# ---------------------------------------------------------------------------------------------------------------------------
+from _qrcases import GT, ct_input, check_cqrrt_against_golden  # noqa: E402
+
+
+@pytest.mark.parametrize("i", range(int(GT["ct_count"])))
+def test_cqrrt_golden(ctx, i):
+    A, st, c = ct_input(i)
+    alg = rl.CQRRT(False, None)
+    alg.nnz, alg.orthogonalization, alg.compute_Q = c["nnz"], c["orth"], c["compute_Q"]
+    Ad = dev(A)
+    s = rl.RNGState(st.key, st.counter)
+    rc, R = alg.call(ctx, Ad, c["d_factor"], s)
+    check_cqrrt_against_golden(i, c, A, rc, host(Ad), host(R), s.words())
+
+
+def test_cqrrt_engine_vs_oracle_and_host_call(ctx):
+    """Tall enough for the tall products to run on the tcgen05 digit-slice engine (m >= 16384), n > 256 (blocked Cholesky / right-solve),
+    against the oracle on the same input and state; then the host-pointer entry (the reference's calling convention)."""
+    m, n = 40000, 320
+    A, st = O.gen_poly_mat(m, n, n, 1.0e3, 2.0, O.RNGState(0))
+    o = O.CQRRT(None, 2)
+    rc_o, Q_o, R_o, st_o = o.call(A, 1.5, O.RNGState(st.key, st.counter))
+    alg = rl.CQRRT(False, None)
+    Ad = dev(A)
+    s = rl.RNGState(st.key, st.counter)
+    rc, R = alg.call(ctx, Ad, 1.5, s)
+    assert rc == rc_o == 0 and list(s.words()) == list(st_o.words())
+    Q, R = host(Ad), host(R)
+    sc = np.abs(np.diag(R_o)).max()
+    assert np.abs(np.triu(R) - np.triu(R_o)).max() <= 1e-9 * sc
+    assert np.abs(Q - Q_o).max() <= 1e-9
+    e = qr_invariants(A, Q, np.triu(R), np.arange(1, n + 1), n)
+    assert max(e) <= np.finfo(np.float64).eps ** 0.75, e
+    Ah = torch.from_numpy(np.ascontiguousarray(A.T)).t()
+    s2 = rl.RNGState(st.key, st.counter)
+    rc2, R2 = alg.call_host(ctx, Ah, 1.5, s2)
+    assert rc2 == 0 and np.abs(np.triu(R2.numpy()) - np.triu(R)).max() <= 1e-12 * sc
+
+
+def test_cqrrt_zero_column_returns_1(ctx):
+    A, st = O.gen_poly_mat(500, 20, 20, 10.0, 2.0, O.RNGState(0))
+    A[:, 7] = 0
+    rc, _ = rl.CQRRT(False, None).call(ctx, dev(A), 2.0, rl.RNGState(st.key, st.counter))
+    assert rc == 1

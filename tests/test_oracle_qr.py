@@ -67,3 +67,26 @@ def test_bqrrp_golden(i):
     e = geqp3_format_invariants(A, F, tau, J, min(alg.rank, kn) if kn < rank_ref else alg.rank)
     atol = np.finfo(c["dtype"]).eps ** 0.75
     assert e[2] <= atol and (kn < rank_ref or max(e) <= atol), e
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
+# CQRRT (rl_cqrrt.hh:91-297): the oracle's restatement against the goldens of the compiled reference
+# ---------------------------------------------------------------------------------------------------------------------------
+from _qrcases import GT, ct_input, check_cqrrt_against_golden  # noqa: E402
+
+
+@pytest.mark.parametrize("i", range(int(GT["ct_count"])))
+def test_cqrrt_golden(i):
+    A, st, c = ct_input(i)
+    alg = O.CQRRT(None, c["nnz"])
+    alg.orthogonalization, alg.compute_Q = c["orth"], c["compute_Q"]
+    rc, Q, R, st2 = alg.call(A, c["d_factor"], st)
+    check_cqrrt_against_golden(i, c, A, rc, Q, R, st2.words())
+
+
+def test_cqrrt_zero_column_returns_1():
+    """rl_cqrrt.hh:173-177: a zero diagonal entry of the sketch's R (here: a zero column) -> return 1."""
+    A, st = O.gen_poly_mat(500, 20, 20, 10.0, 2.0, O.RNGState(0))
+    A[:, 7] = 0
+    rc, *_ = O.CQRRT(None, 2).call(A, 2.0, st)
+    assert rc == 1
