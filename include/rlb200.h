@@ -87,6 +87,16 @@ RLB200_API int rlb200_set_stream(rlb200_ctx* ctx, void* stream);
 RLB200_API int rlb200_synchronize(rlb200_ctx* ctx);
 /* Row-sharding: this process holds rows [row_offset, row_offset+m_local) of an m_global-row matrix. */
 RLB200_API int rlb200_set_shard(rlb200_ctx* ctx, int64_t row_offset, int64_t m_global, rlb200_allreduce_fn fn, void* user);
+/* Position of this shard among the row shards, needed by the TSQR orthogonaliser (HQRQ on a sharded iterate stacks the k x k
+ * factors in rank order).  rlb200_comm_init sets it; hosts that use the hook declare it here. */
+RLB200_API int rlb200_set_shard_rank(rlb200_ctx* ctx, int rank, int world);
+/* Native data plane: an NCCL communicator owned by the context (libnccl is opened at run time; RLB200_NCCL_LIB overrides the name).
+ * One rank calls rlb200_comm_unique_id and distributes the 128 bytes by any means (MPI, a file, torch.distributed); every rank then
+ * calls rlb200_comm_init on its context (collective).  From then on the Gram / B^T / norm / R-factor sum-allreduces of the row-sharded
+ * drivers are ncclAllReduce calls on the context's stream, and rlb200_set_shard(.., NULL, NULL) keeps using them. */
+RLB200_API int rlb200_comm_unique_id(unsigned char id_out[128]);
+RLB200_API int rlb200_comm_init(rlb200_ctx* ctx, int nranks, int rank, const unsigned char id[128]);
+RLB200_API int rlb200_comm_destroy(rlb200_ctx* ctx);
 /* kernels launched since creation / last reset (for bench.py's gpu_launches). */
 RLB200_API int64_t rlb200_launch_count(rlb200_ctx* ctx, int reset);
 /* CUDA-event timing of the kernels tagged `which` (see RLB200_TIMER_*), ms since last reset. */

@@ -12,6 +12,7 @@ Matrices are torch CUDA tensors in COLUMN-MAJOR storage (shape (m, n), strides (
 from __future__ import annotations
 
 import ctypes
+import os
 from dataclasses import dataclass
 
 from . import _capi
@@ -154,11 +155,40 @@ class Context:
         self.check(self._lib.rlb200_set_i8_fused(self._h, 1 if on else 0))
 
     # ---- row sharding over torch.distributed -------------------------------------------------
-    def set_shard(self, row_offset, m_global, group=None):
-        """This rank holds rows [row_offset, row_offset + m_local) of an m_global-row A.  Gram / B^T / norm
-        partials are sum-allreduced over `group` (torch.distributed; NCCL on GPUs)."""
-        self._hook = _capi.ALLREDUCE_FN(make_allreduce_hook(group))
-        self.check(self._lib.rlb200_set_shard(self._h, row_offset, m_global, self._hook, None))
+    def set_shard(self, row_offset, m_global, group=None, native=None):
+        """This rank holds rows [row_offset, row_offset + m_local) of an m_global-row A.  Gram / B^T / norm / R-factor partials are
+        sum-allreduced over the shards.  native=True: through the context's own NCCL communicator (ncclAllReduce issued from C++ on the
+        context's stream; created on first use, its unique id travels over torch.distributed); native=False: through a callback into
+        torch.distributed (`group`; gloo in the CPU tests of this plumbing).  Default: native on NCCL process groups."""
+        import torch.distributed as dist
+        if native is None:
+            native = dist.is_initialized() and dist.get_backend(group) == "nccl" and os.environ.get("RLB200_NATIVE_COMM", "1") != "0"
+        if dist.is_initialized():
+            self.check(self._lib.rlb200_set_shard_rank(self._h, dist.get_rank(group), dist.get_world_size(group)))
+        if native:
+            if not getattr(self, "_native_comm", False):
+                self.comm_init_from_torch(group)
+            self._hook = None
+            self.check(self._lib.rlb200_set_shard(self._h, row_offset, m_global, ctypes.cast(None, _capi.ALLREDUCE_FN), None))
+        else:
+            self._hook = _capi.ALLREDUCE_FN(make_allreduce_hook(group))
+            self.check(self._lib.rlb200_set_shard(self._h, row_offset, m_global, self._hook, None))
+
+    def comm_init_from_torch(self, group=None):
+        """rlb200_comm_unique_id on rank 0, broadcast of the 128 bytes over torch.distributed, rlb200_comm_init on every rank."""
+        torch = _torch()
+        import torch.distributed as dist
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        idb = (ctypes.c_ubyte * 128)()
+        if rank == 0:
+            rc = self._lib.rlb200_comm_unique_id(idb)
+            if rc:
+                raise Error(rc, "rlb200_comm_unique_id failed (libnccl not found?)")
+        t = torch.tensor(list(idb), dtype=torch.uint8, device=self.device if dist.get_backend(group) == "nccl" else "cpu")
+        dist.broadcast(t, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+        idb = (ctypes.c_ubyte * 128)(*t.cpu().tolist())
+        self.check(self._lib.rlb200_comm_init(self._h, world, rank, idb))
+        self._native_comm = True
 
     def clear_shard(self):
         self._hook = None

@@ -73,6 +73,10 @@ SIGNATURES = {
     "rlb200_set_fp64_engine": (c_int, [c_vp, c_int]),
     "rlb200_set_i8_digits": (c_int, [c_vp, c_int]),
     "rlb200_set_i8_fused": (c_int, [c_vp, c_int]),
+    "rlb200_set_shard_rank": (c_int, [c_vp, c_int, c_int]),
+    "rlb200_comm_unique_id": (c_int, [c_vp]),
+    "rlb200_comm_init": (c_int, [c_vp, c_int, c_int, c_vp]),
+    "rlb200_comm_destroy": (c_int, [c_vp]),
     "rlb200_dev_alloc": (c_int, [c_vp, ctypes.c_size_t, ctypes.POINTER(c_vp)]),
     "rlb200_dev_free": (c_int, [c_vp, c_vp]),
     "rlb200_copy_h2d": (c_int, [c_vp, c_vp, c_vp, ctypes.c_size_t]),

@@ -46,6 +46,7 @@ int rlb200_destroy(rlb200_ctx* ctx) {
     arena_destroy(ctx);
     if (ctx->ws) cudaFree(ctx->ws);
     if (ctx->hbox) cudaFreeHost(ctx->hbox);
+    comm_destroy(ctx);
     oz_cache_destroy(ctx);
     oz2_cache_destroy(ctx);
     if (ctx->aux_stream) { cudaStreamSynchronize(ctx->aux_stream); cudaStreamDestroy(ctx->aux_stream); }
@@ -68,11 +69,33 @@ int rlb200_synchronize(rlb200_ctx* ctx) {
 
 int rlb200_set_shard(rlb200_ctx* ctx, int64_t row_offset, int64_t m_global, rlb200_allreduce_fn fn, void* user) {
     CTX_OK(ctx);
-    if (m_global < 0) { ctx->row_offset = 0; ctx->m_global = -1; ctx->allreduce = nullptr; ctx->allreduce_user = nullptr; return 0; }
+    const bool native = comm_is_native(ctx);
+    if (m_global < 0) {
+        ctx->row_offset = 0; ctx->m_global = -1;
+        if (!native) { ctx->allreduce = nullptr; ctx->allreduce_user = nullptr; }
+        return 0;
+    }
     RLB_REQUIRE(ctx, row_offset >= 0 && row_offset <= m_global);
-    ctx->row_offset = row_offset; ctx->m_global = m_global; ctx->allreduce = fn; ctx->allreduce_user = user;
+    ctx->row_offset = row_offset; ctx->m_global = m_global;
+    // fn == NULL keeps the context's own NCCL communicator (rlb200_comm_init) when there is one
+    if (fn != nullptr || !native) { ctx->allreduce = fn; ctx->allreduce_user = user; }
     return 0;
 }
+int rlb200_set_shard_rank(rlb200_ctx* ctx, int rank, int world) {
+    CTX_OK(ctx);
+    RLB_REQUIRE(ctx, world >= 1 && rank >= 0 && rank < world);
+    ctx->shard_rank = rank; ctx->shard_world = world;
+    return 0;
+}
+int rlb200_comm_unique_id(unsigned char id_out[128]) {
+    if (!id_out) return RLB200_ERR_ARG;
+    return comm_unique_id(id_out, nullptr);
+}
+int rlb200_comm_init(rlb200_ctx* ctx, int nranks, int rank, const unsigned char id[128]) {
+    CTX_OK(ctx); RLB_CHECK(bind(ctx));
+    return comm_init(ctx, nranks, rank, id);
+}
+int rlb200_comm_destroy(rlb200_ctx* ctx) { CTX_OK(ctx); comm_destroy(ctx); return 0; }
 
 int64_t rlb200_launch_count(rlb200_ctx* ctx, int reset) {
     if (!ctx) return -1;

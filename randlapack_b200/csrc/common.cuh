@@ -53,6 +53,11 @@ struct Ctx {
     int64_t m_global = -1;
     rlb200_allreduce_fn allreduce = nullptr;
     void* allreduce_user = nullptr;
+    // position of this shard among the row shards (TSQR stacks the k x k factors in this order); -1 = not declared
+    int shard_rank = -1, shard_world = 0;
+    // native collectives (comm.cu): an NCCL communicator owned by the context, libnccl opened at run time
+    void* nccl_comm = nullptr;
+    void* nccl_lib = nullptr;
     // tall-GEMM engine of the drivers: 1 = tcgen05 int8 digit slices (ozaki.cu, default), 0 = DMMA (fp64 tensor pipe)
     int fp64_engine = 1;
     // digits per value of the int8-slice engine: 0 = default (6 for fp64 storage, 4 for fp32), else 3..7

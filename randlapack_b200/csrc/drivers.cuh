@@ -72,6 +72,12 @@ struct OzConstScope {
     static void invalidate(Ctx* c) { c->oz_row.valid = false; c->oz_col.valid = false; c->oz2_row.valid = false; c->oz2_col.valid = false; }
 };
 
+// ---- native collectives (comm.cu): NCCL communicator owned by the context, libnccl opened at run time -------------------
+int comm_unique_id(unsigned char out[128], std::string* err);
+int comm_init(Ctx* ctx, int nranks, int rank, const unsigned char id_bytes[128]);
+void comm_destroy(Ctx* ctx);
+bool comm_is_native(const Ctx* ctx);
+
 // ---- sketch-apply (sketch.cu) -----------------------------------------------------------------------
 template <typename T>
 int fill_sparse_unpacked(Ctx* ctx, int64_t n_rows, int64_t n_cols, int64_t vec_nnz, int major_axis, int64_t sub_rows, int64_t sub_cols,
