@@ -144,7 +144,7 @@ static int cholqrq(Ctx* ctx, int64_t m, int64_t k, T* A, bool cond_check, bool r
 // HQRQ::call (rl_orth.hh:144-164): geqrf + ungqr.  Householder QR of the tall panel, then Q = (I - V T V^T) [I; 0] = E - V (T V1^T)
 // formed in place by one tall tensor-pipe GEMM.
 template <typename T>
-static int hqrq(Ctx* ctx, int64_t m, int64_t k, T* A) {
+static int hqrq(Ctx* ctx, int64_t m, int64_t k, T* A, T* R_out = nullptr) {
     if (m == 0 || k == 0) return 0;
     const int64_t kk = std::min(m, k);
     RLB_REQUIRE(ctx, k <= 256 && m >= k);   // (the in-place product needs one CTA tile across all k columns)
@@ -156,6 +156,7 @@ static int hqrq(Ctx* ctx, int64_t m, int64_t k, T* A) {
     T* M = as.take<T>(kk * kk); RLB_ALLOC(ctx, M);
     void* ws = arena_push(ctx, qrcp_ws_bytes(k)); RLB_ALLOC(ctx, ws);
     RLB_CHECK(qr_small<T>(ctx, false, m, k, A, m, nullptr, tau, ws));
+    if (R_out) RLB_CHECK(tri_op<T>(ctx, 2, kk, kk, A, m, R_out, kk));               // the triangular factor (clean upper copy, ld kk)
     RLB_CHECK(set_upper_diag<T>(ctx, kk, A, m, (T)1, false));                       // A <- V (unit lower trapezoidal, clean)
     RLB_CUDA_OK(ctx, cudaMemsetAsync(G, 0, sizeof(T) * kk * kk, ctx->stream));
     RLB_CHECK(gemm_tn<T>(ctx, m, kk, kk, 1.0, A, m, A, m, 0.0, G, kk, 0));          // G = V^T V
@@ -165,6 +166,30 @@ static int hqrq(Ctx* ctx, int64_t m, int64_t k, T* A) {
     RLB_CHECK(gemm_nt<T>(ctx, kk, kk, kk, 1.0, Tm, kk, V1, kk, 0.0, M, kk));        // M = T V1^T
     RLB_CHECK(gemm_nn_inplace<T>(ctx, m, kk, kk, -1.0, A, m, M, kk));               // A <- -V M
     RLB_CHECK(set_upper_diag<T>(ctx, kk, A, m, (T)1, true));                        // + [I; 0]
+    return 0;
+}
+
+// HQRQ on a row-sharded iterate: TSQR (net-new; the reference has no distributed layer).  One level, as wide as the shard count:
+//   local Householder QR  A_g = Q_g R_g   (rl_orth.hh:144-164 semantics on the shard's rows),
+//   the k x k factors stacked in rank order [R_0; ...; R_{W-1}] on every rank (a sum-allreduce of a zero-padded buffer: adding zeros is
+//   exact, so all ranks hold bit-identical stacks), its Householder QR  = Q2 R  computed redundantly, and  Q_g <- Q_g Q2[g k : (g+1) k, :].
+// Unlike CholQR this does not square the condition number of the iterate.
+template <typename T>
+static int hqrq_tsqr(Ctx* ctx, int64_t m, int64_t k, T* A) {
+    const int W = ctx->shard_world, g = ctx->shard_rank;
+    if (W <= 0 || g < 0) { ctx->err = "HQRQ on a row-sharded iterate (TSQR) needs the shard's rank: rlb200_set_shard_rank / rlb200_comm_init"; return RLB200_ERR_ARG; }
+    RLB_REQUIRE(ctx, k <= 256 && m >= k);      // every shard holds at least k rows
+    ArenaScope as(ctx);
+    T* Rl = as.take<T>(k * k); RLB_ALLOC(ctx, Rl);
+    T* St = as.take<T>((int64_t)W * k * k); RLB_ALLOC(ctx, St);
+    T* M = as.take<T>(k * k); RLB_ALLOC(ctx, M);
+    RLB_CHECK(hqrq<T>(ctx, m, k, A, Rl));
+    RLB_CUDA_OK(ctx, cudaMemsetAsync(St, 0, sizeof(T) * (size_t)W * k * k, ctx->stream));
+    RLB_CUDA_OK(ctx, cudaMemcpy2DAsync(St + (int64_t)g * k, (size_t)W * k * sizeof(T), Rl, k * sizeof(T), k * sizeof(T), k, cudaMemcpyDeviceToDevice, ctx->stream));
+    RLB_CHECK(allreduce_sum<T>(ctx, St, (int64_t)W * k * k));
+    RLB_CHECK(hqrq<T>(ctx, (int64_t)W * k, k, St));                                 // St <- Q2 (W k x k)
+    RLB_CUDA_OK(ctx, cudaMemcpy2DAsync(M, k * sizeof(T), St + (int64_t)g * k, (size_t)W * k * sizeof(T), k * sizeof(T), k, cudaMemcpyDeviceToDevice, ctx->stream));
+    RLB_CHECK(gemm_nn_inplace<T>(ctx, m, k, k, 1.0, A, m, M, k));
     return 0;
 }
 
@@ -213,10 +238,7 @@ int stab_call(Ctx* ctx, int kind, int64_t m, int64_t k, T* A, bool cond_check, b
             return plul<T>(ctx, m, k, A, m, ws);   // rl_orth.hh:211-230: always returns 0
         }
         case RLB200_STAB_HQRQ: {
-            if (rows_sharded && ctx->allreduce) {
-                ctx->err = "HQRQ on a row-sharded iterate needs a TSQR tree; not offered yet (use CholQRQ)";
-                return RLB200_ERR_UNSUPPORTED;
-            }
+            if (rows_sharded && ctx->allreduce) return hqrq_tsqr<T>(ctx, m, k, A);
             return hqrq<T>(ctx, m, k, A);
         }
     }

@@ -1,4 +1,5 @@
-"""Row-sharded RSVD over NCCL (2 GPUs) == single-GPU RSVD on the same matrix and RNG state.
+"""Row-sharded RSVD / CQRRPT / CQRRT over NCCL (2 GPUs) == the single-GPU run on the same matrix and RNG state, incl. the TSQR
+orthogonaliser (HQRQ on a sharded iterate) and both data planes (the context's own NCCL communicator; the torch.distributed callback).
 Tolerances: the sharded path reduces Gram / A^T Y partials in a different order (fp64 round-off only): sigma to 1e-12
 relative, factors to 1e-9 (up to sign)."""
 import json
@@ -24,6 +25,13 @@ def test_sharded_rsvd_matches_single_gpu():
         for name, res in per_rank.items():
             assert res["rc"][0] == res["rc"][1] and res["k"][0] == res["k"][1], (name, res)
             assert res["state_equal"], (name, res)
+            if name.startswith("cqrrt"):
+                assert res["R_rel"] <= 1e-9 and res["Q_abs"] <= 1e-8, (name, res)
+                continue
+            if name.startswith("tsqr"):
+                # TSQR: the stacked-R QR differs from the single-GPU Householder QR in round-off only; factors up to sign
+                assert res["S_rel"] <= 1e-11 and res["V_abs"] <= 1e-8 and res["U_abs"] <= 1e-8 and res["orth"] <= 1e-12, (name, res)
+                continue
             if name.startswith("cqrrpt"):
                 # the sharded sketch sums each shard's rows first (different summation order): pivots must still be identical
                 assert res["J_equal"] and res["R_rel"] <= 1e-9 and res["Q_abs"] <= 1e-8, (name, res)
