@@ -316,11 +316,22 @@ def run_secondary(args):
             assert rc == 0 and alg.rank == n, (rc, alg.rank)
         ms = timed(step, prep, args.steps, args.warmup)
         fl = 3.0 * m * n * n + m * n * nnz + (2.0 * d * n * n - 2.0 / 3.0 * n ** 3)
-        peak, src, _ = measured_fp64_peak()
+        if args.engine == "i8":
+            # the three O(m n^2) products (A R_sk^-1, Gram, A R^-1: m n^2 flops each with the triangular / upper-only skipping) run as digit-pair
+            # GEMMs on tcgen05: 4 digits (10 pairs) for fp32 storage, 7 digits (28 pairs) for fp64
+            dg = args.digits or (4 if dtype == torch.float32 else 7)
+            i8_ops = 3.0 * m * n * n * (dg * (dg + 1) // 2)
+            b_, s_, src, _ = measured_i8_peak()
+            peak = s_ or 2.0 * peaks.get("bf16_tflops_sustained", 1361.4)
+            roof = {"bound": "tensor", "achieved": i8_ops / ms / 1e9, "peak": peak, "unit": "TFLOP/s", "frac": i8_ops / ms / 1e9 / peak,
+                    "op": "int8 multiply-add = 2 ops; whole step (sketch, QRCP of the sketch and permutation included in the time)",
+                    "digits": dg, "traffic": None, "peak_source": src}
+        else:
+            peak, src, _ = measured_fp64_peak()
+            roof = {"bound": "tensor", "achieved": fl / ms / 1e9, "peak": peak, "unit": "TFLOP/s", "frac": fl / ms / 1e9 / peak, "traffic": None,
+                    "peak_source": src}
         out = {"metric": "cqrrpt_gflops", "value": fl / ms / 1e6, "unit": "Gflop/s", "ms_per_step": ms,
-               "roofline": {"bound": "tensor", "achieved": fl / ms / 1e9, "peak": peak, "unit": "TFLOP/s", "frac": fl / ms / 1e9 / peak,
-                            "traffic": None, "peak_source": src + " (fp64 DMMA pipe; with --engine i8 the O(m n^2) work runs on tcgen05 "
-                                                                  "int8 digit slices instead, so frac can exceed 1)"},
+               "roofline": roof,
                "config": {"workload": f"CQRRPT of a {m} x {n} {args.dtype} Gaussian matrix, SASO d={d} vec_nnz={nnz}, geqp3 (configs[2])",
                           "engine": args.engine}}
     elif wl == "bqrrp":
@@ -345,10 +356,20 @@ def run_secondary(args):
         ms = timed(step, prep, args.steps, args.warmup)
         d = int(args.d_factor * b)
         fl = 2.0 * m * n * n - 2.0 / 3.0 * n ** 3 + 2.0 * d * m * n
-        peak, src, _ = measured_fp64_peak()
+        if args.engine == "i8":
+            # the trailing updates (the O(m n^2) part) run as 28 digit pairs (7 digits) on tcgen05; panels and the sketch on the fp64 pipe
+            dg = args.digits or 7
+            i8_ops = (2.0 * m * n * n - 2.0 / 3.0 * n ** 3) * (dg * (dg + 1) // 2)
+            b_, s_, src, _ = measured_i8_peak()
+            peak = s_ or 2.0 * peaks.get("bf16_tflops_sustained", 1361.4)
+            roof = {"bound": "tensor", "achieved": i8_ops / ms / 1e9, "peak": peak, "unit": "TFLOP/s", "frac": i8_ops / ms / 1e9 / peak,
+                    "op": "int8 multiply-add = 2 ops; whole step", "digits": dg, "traffic": None, "peak_source": src}
+        else:
+            peak, src, _ = measured_fp64_peak()
+            roof = {"bound": "tensor", "achieved": fl / ms / 1e9, "peak": peak, "unit": "TFLOP/s", "frac": fl / ms / 1e9 / peak, "traffic": None,
+                    "peak_source": src}
         out = {"metric": "bqrrp_gflops", "value": fl / ms / 1e6, "unit": "Gflop/s", "ms_per_step": ms,
-               "roofline": {"bound": "tensor", "achieved": fl / ms / 1e9, "peak": peak, "unit": "TFLOP/s", "frac": fl / ms / 1e9 / peak,
-                            "traffic": None, "peak_source": src},
+               "roofline": roof,
                "config": {"workload": f"BQRRP of a {m} x {n} {args.dtype} Gaussian matrix, b={b}, d_factor={args.d_factor}, luqr + cholqr/orhr_col "
                                       "panels + compact-WY update (configs[3])"}}
     else:
@@ -367,8 +388,43 @@ def run_secondary(args):
         ctx.timers_enable(False)
         out["class_ms_per_step"] = {k_: round(v[0], 3) for k_, v in tm.items() if v[1]}
         out["class_launches_per_step"] = {k_: v[1] for k_, v in tm.items() if v[1]}
+    cpu = None
+    if wl in ("cqrrpt", "bqrrp") and not args.no_cpu:
+        # the reference's own CPU driver (oracle/_ref/librl_ref.so = its unmodified headers over OpenBLAS) on a bounded sample of the same
+        # workload, all host threads; rates are size-normalised with the same flop formula
+        try:
+            import numpy as np
+            sys.path.insert(0, os.path.join(ROOT, "tests"))
+            import _ref
+            from oracle import rl_oracle as O
+            Rl = _ref.ref_lib()
+            cores = os.cpu_count() or 1
+            Rl.rlref_set_num_threads(cores)
+            npdt = np.float32 if args.dtype == "f32" else np.float64
+            if wl == "cqrrpt":
+                mc, nc = 1 << 17, n
+                Ac, _ = O.fill_dense(mc, nc, O.RNGState(0xA3), dtype=npdt)
+                Ac = np.asfortranarray(Ac)
+                t0 = time.perf_counter()
+                _ref.ref_cqrrpt(Rl, Ac, d_factor, [0] * 6, None, nnz)
+                tc = time.perf_counter() - t0
+                dc = int(d_factor * nc)
+                flc = 3.0 * mc * nc * nc + mc * nc * nnz + (2.0 * dc * nc * nc - 2.0 / 3.0 * nc ** 3)
+                sample = f"{mc} x {nc} {args.dtype} rows of the same workload, RandLAPACK::CQRRPT (geqp3), {cores} threads, one run"
+            else:
+                nc = 8192
+                Ac, _ = O.fill_dense(nc, nc, O.RNGState(0xA4), dtype=npdt)
+                Ac = np.asfortranarray(Ac)
+                t0 = time.perf_counter()
+                _ref.ref_bqrrp(Rl, Ac, args.d_factor, args.block, [0] * 6, 0, 1)
+                tc = time.perf_counter() - t0
+                flc = 2.0 * nc ** 3 - 2.0 / 3.0 * nc ** 3 + 2.0 * int(args.d_factor * args.block) * nc * nc
+                sample = f"{nc} x {nc} {args.dtype}, RandLAPACK::BQRRP (luqr + cholqr, b={args.block}), {cores} threads, one run"
+            cpu = {"value": flc / tc / 1e9, "unit": "Gflop/s", "cores": cores, "kind": "reference", "sample": sample, "seconds": tc}
+        except Exception as e:  # noqa: BLE001
+            cpu = {"value": None, "unit": "Gflop/s", "cores": os.cpu_count(), "kind": "reference", "sample": f"failed: {type(e).__name__}: {e}"}
     out.update({"n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": args.dtype, "data": "synthetic", "clocks": clocks, "gpu_launches": ctx.launch_count(), "cpu_baseline": None, "e2e": None})
+                "dtype": args.dtype, "data": "synthetic", "clocks": clocks, "gpu_launches": ctx.launch_count(), "cpu_baseline": cpu, "e2e": None})
     out["config"]["l2"] = "inputs exceed the 126 MB L2 by >100x; no flush needed"
     print(json.dumps(out))
     return 0
@@ -396,6 +452,9 @@ def main():
     ap.add_argument("--engine", default="i8", choices=["dmma", "i8"],
                     help="tall fp64 products over A: tcgen05 int8 digit slices (default) or the fp64 DMMA pipe")
     ap.add_argument("--digits", type=int, default=0, help="int8 digits per value (0 = default: 6 for fp64, 46 bits)")
+    ap.add_argument("--config", default="c2", choices=["c2", "c5"],
+                    help="c2 (default): BASELINE.json configs[1], 2^24 x 1024 k=256 per GPU (weak scaling); c5: configs[4], 128M x 512 k=128 "
+                         "row-sharded - strong scaling where 2^27 / N rows fit one GPU (N >= 4), else 2^25 rows per GPU (weak)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -408,8 +467,14 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    scaling = "weak"
+    if args.config == "c5":
+        args.n, args.k = 512, 128
+        total = 1 << 27
+        args.m = min(total // world, 1 << 25)
+        scaling = "strong" if args.m * world == total else "weak"
     n, k, p, q = args.n, args.k, args.p, args.q
-    config = {"workload": f"rank-{k} RSVD of a ({world}x{args.m}) x {n} fp64 Gaussian matrix (BASELINE.json configs[1] per GPU), "
+    config = {"workload": f"rank-{k} RSVD of a ({world}x{args.m}) x {n} fp64 Gaussian matrix (BASELINE.json {'configs[4], ' + scaling + ' scaling' if args.config == 'c5' else 'configs[1] per GPU'}), "
                           f"RS(p={p}, q={q}, CholQRQ) + RF(CholQRQ) + QB(block={k}, CholQRQ) + RSVD",
               "m_per_gpu": args.m, "n": n, "k": k, "passes_over_data": p, "passes_per_stab": q, "stabiliser": "CholQRQ",
               "l2": "inputs (A: m*n*8 bytes per GPU) exceed the 126 MB L2 by >1000x; no flush needed",
@@ -422,7 +487,7 @@ def main():
         gf, t, kind, cores = cpu_sample(n, k, p, q, args.m_cpu, max(1, args.steps), max(0, min(args.warmup, 1)))
         sample = f"{args.m_cpu} x {n} fp64 rows of the same workload (k={k}, p={p}), {cores} threads"
         print(json.dumps({"impl": "reference", "metric": METRIC, "value": gf, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-                          "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak",
+                          "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": scaling,
                           "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
                           "cpu_baseline": {"value": gf, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
                           "e2e": {"value": gf, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -639,7 +704,7 @@ def main():
             cpu = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "reference", "sample": f"failed: {type(e).__name__}: {e}"}
 
     out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-           "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+           "ms_per_step": ms_step, "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "f64",
            "data": "synthetic", "config": config, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "parity": parity,
            "gpu_launches": launches, "flops_per_step": rsvd_flops(m_global, n, k, p, q),
            "flops_executed_per_step": sum(class_flops(m_global, n, k, p, q).values()),

@@ -13,6 +13,7 @@ from __future__ import annotations
 
 import ctypes
 import os
+import sys
 from dataclasses import dataclass
 
 from . import _capi
@@ -187,7 +188,17 @@ class Context:
         t = torch.tensor(list(idb), dtype=torch.uint8, device=self.device if dist.get_backend(group) == "nccl" else "cpu")
         dist.broadcast(t, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
         idb = (ctypes.c_ubyte * 128)(*t.cpu().tolist())
-        self.check(self._lib.rlb200_comm_init(self._h, world, rank, idb))
+        # NCCL may print its version banner on stdout while a communicator is created: keep the process's stdout clean (bench.py prints
+        # exactly one JSON line there) by pointing fd 1 at stderr for the duration of the call
+        sys.stdout.flush()
+        saved = os.dup(1)
+        try:
+            os.dup2(2, 1)
+            rc = self._lib.rlb200_comm_init(self._h, world, rank, idb)
+        finally:
+            os.dup2(saved, 1)
+            os.close(saved)
+        self.check(rc)
         self._native_comm = True
 
     def clear_shard(self):
@@ -200,6 +211,10 @@ def shard_rows(m_global, world_size, rank, align=128):
     shard's first row on a Philox counter boundary of the odd-p operator, RandBLAS dense_skops.hh:109-123)."""
     per = -(-m_global // world_size)
     per = -(-per // align) * align
+    if (world_size - 1) * per >= m_global:
+        # a trailing rank would hold no rows: the drivers require m > 0 on every shard, and an empty shard returning early would leave
+        # the other ranks waiting in a collective (ADVICE r1) - fail on every rank alike, before any collective
+        raise ValueError(f"shard_rows: {m_global} rows cannot be split into {world_size} non-empty blocks of multiples of {align} rows")
     r0 = min(m_global, rank * per)
     r1 = min(m_global, r0 + per)
     return r0, r1

@@ -69,16 +69,15 @@ int rlb200_synchronize(rlb200_ctx* ctx) {
 
 int rlb200_set_shard(rlb200_ctx* ctx, int64_t row_offset, int64_t m_global, rlb200_allreduce_fn fn, void* user) {
     CTX_OK(ctx);
-    const bool native = comm_is_native(ctx);
     if (m_global < 0) {
-        ctx->row_offset = 0; ctx->m_global = -1;
-        if (!native) { ctx->allreduce = nullptr; ctx->allreduce_user = nullptr; }
+        ctx->row_offset = 0; ctx->m_global = -1; ctx->allreduce = nullptr; ctx->allreduce_user = nullptr;
         return 0;
     }
     RLB_REQUIRE(ctx, row_offset >= 0 && row_offset <= m_global);
     ctx->row_offset = row_offset; ctx->m_global = m_global;
-    // fn == NULL keeps the context's own NCCL communicator (rlb200_comm_init) when there is one
-    if (fn != nullptr || !native) { ctx->allreduce = fn; ctx->allreduce_user = user; }
+    // a hook wins; fn == NULL selects the context's own NCCL communicator (rlb200_comm_init) when there is one, else a single shard
+    if (fn != nullptr) { ctx->allreduce = fn; ctx->allreduce_user = user; }
+    else if (!comm_use_native(ctx)) { ctx->allreduce = nullptr; ctx->allreduce_user = nullptr; }
     return 0;
 }
 int rlb200_set_shard_rank(rlb200_ctx* ctx, int rank, int world) {

@@ -101,5 +101,12 @@ void comm_destroy(Ctx* ctx) {
 }
 
 bool comm_is_native(const Ctx* ctx) { return ctx->nccl_comm != nullptr && ctx->allreduce == native_allreduce; }
+// (re)install the context's own communicator as the sum-allreduce; false when the context has none
+bool comm_use_native(Ctx* ctx) {
+    if (!ctx->nccl_comm) return false;
+    ctx->allreduce = native_allreduce;
+    ctx->allreduce_user = ctx;
+    return true;
+}
 
 }  // namespace rlb

@@ -77,6 +77,7 @@ int comm_unique_id(unsigned char out[128], std::string* err);
 int comm_init(Ctx* ctx, int nranks, int rank, const unsigned char id_bytes[128]);
 void comm_destroy(Ctx* ctx);
 bool comm_is_native(const Ctx* ctx);
+bool comm_use_native(Ctx* ctx);
 
 // ---- sketch-apply (sketch.cu) -----------------------------------------------------------------------
 template <typename T>

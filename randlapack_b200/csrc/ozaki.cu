@@ -315,6 +315,9 @@ static int oz_launch_mma(Ctx* ctx, dim3 grid, int cs, cudaStream_t stream, const
                          int64_t b_group_stride, int nkb, const int* Ea, int64_t ea_stride, const int* Eb, int64_t eb_stride, int64_t rows_a, int rows_b,
                          TO* out, int64_t ldo, int64_t out_group_stride, double alpha, double beta, long long* dbg = nullptr, int flags = 0,
                          OzGram gp = OzGram{0, nullptr, 0}) {
+    // flag-dependent control flow (K loop cut at the diagonal, upper-tile-only output, Gram tiles) makes the CTAs of a cluster run different
+    // K-loop lengths or return early, which the multicast / commit protocol cannot tolerate: such launches never use clusters
+    if (flags != 0 || gp.out2 != nullptr) cs = 1;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = grid;
     cfg.blockDim = dim3(256);

@@ -267,6 +267,31 @@ __global__ void __launch_bounds__(Oz2Threads<NG>::N, 1) oz2_kernel(const Oz2Para
             const bool dbg_on = p.dbg != nullptr && tid == 0;
             long long c_wait = 0, c_conv = 0, c_fence = 0, c_load = 0;
             const bool skip_fence = (p.dbg_flags & 4) != 0, skip_math = (p.dbg_flags & 8) != 0;
+            // L2 prefetch of the tile of K block kb (one 128-byte line per thread: the tile is 64 x 32 elements = 16 KB in fp64): issued
+            // several blocks before the register loads, which then find their lines in L2 (~700 cycles) instead of DRAM (> 2000 under load) -
+            // the register double buffer alone covers only about one block time (~1200 cycles).  Costs one instruction and no registers.
+            const int pf_lines = (int)(OZ_BN * OZ_KB * sizeof(T) / 128);
+            const T* pf_src = nullptr;
+            {
+                const int t = cw * 32 + lane;
+                if (t < pf_lines) {
+                    if constexpr (!TN) {
+                        constexpr int LPC = (int)(OZ_BN * sizeof(T) / 128);              // lines per column of the tile
+                        const int64_t row0 = (int64_t)by * OZ_BN + (t % LPC) * (128 / (int)sizeof(T));
+                        if (row0 < rows_n) pf_src = X + row0 + (int64_t)(t / LPC) * p.ldx;
+                    } else {
+                        constexpr int LPC = (int)(OZ_KB * sizeof(T) / 128) > 0 ? (int)(OZ_KB * sizeof(T) / 128) : 1;   // lines per column (32 K rows)
+                        const int64_t col = (int64_t)by * OZ_BN + t / LPC;
+                        if (col < rows_n) pf_src = X + (int64_t)g * p.L + (t % LPC) * (128 / (int)sizeof(T)) + col * p.ldx;
+                    }
+                }
+            }
+            auto prefetch_block = [&](int kb) {
+                if (pf_src != nullptr && kb < kb_full) {
+                    const T* a = TN ? pf_src + (int64_t)kb * OZ_KB : pf_src + (int64_t)kb * OZ_KB * p.ldx;
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(a));
+                }
+            };
             // convert one K block (values already requested into `raw`) into stage kb % DST and publish it
             auto convert_block = [&](int kb, const T (&raw)[16]) {
                 long long t1 = 0, t2 = 0, t3 = 0;
@@ -353,8 +378,12 @@ __global__ void __launch_bounds__(Oz2Threads<NG>::N, 1) oz2_kernel(const Oz2Para
             if (kb_first < nkb) load_block(kb_first, bufa);
             if (kb_first + kb_stride < nkb) load_block(kb_first + kb_stride, bufb);
 #pragma unroll 1
+            constexpr int PF = 5;       // prefetch distance in blocks of this group (the register loads run 2 blocks ahead)
+            for (int j = 2; j < PF; ++j) prefetch_block(kb_first + j * kb_stride);
             for (int kb = kb_first; kb < nkb; kb += 2 * kb_stride) {
                 long long t0 = 0;
+                prefetch_block(kb + PF * kb_stride);
+                prefetch_block(kb + (PF + 1) * kb_stride);
                 convert_block(kb, bufa);
                 if (dbg_on) t0 = clock64();
                 if (kb + 2 * kb_stride < nkb) load_block(kb + 2 * kb_stride, bufa);

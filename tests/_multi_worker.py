@@ -115,7 +115,9 @@ def main():
         rc1, R1 = alg.call(ctx, A_one, 1.5, st1)
         out[f"cqrrt_{m}x{n}"] = {"rc": [rc, rc1], "k": [n, n], "state_equal": st == st1,
                                  "R_rel": ((R.triu() - R1.triu()).abs().max() / R1.abs().max()).item(),
-                                 "Q_abs": (A_loc - A_one[r0:r1]).abs().max().item()}
+                                 "R_abs_rel": ((R.triu().abs() - R1.triu().abs()).abs().max() / R1.abs().max()).item(),
+                                 "Q_abs": (A_loc - A_one[r0:r1]).abs().max().item(),
+                                 "Q_absabs": (A_loc.abs() - A_one[r0:r1].abs()).abs().max().item()}
     gathered = [None] * world
     dist.all_gather_object(gathered, out)
     if rank == 0:

@@ -19,13 +19,22 @@ from oracle import rl_oracle as O
 
 
 def test_shard_rows_cover():
+    import pytest
     for m in (1, 127, 128, 129, 1000, 1 << 20, (1 << 24) + 5):
         for w in (1, 2, 3, 4, 8):
+            per = -(-(-(-m // w)) // 128) * 128
+            if (w - 1) * per >= m:
+                # a trailing rank would be empty: every rank must fail alike, before any collective
+                with pytest.raises(ValueError):
+                    rl.shard_rows(m, w, w - 1)
+                with pytest.raises(ValueError):
+                    rl.shard_rows(m, w, 0)
+                continue
             blocks = [rl.shard_rows(m, w, r) for r in range(w)]
             assert blocks[0][0] == 0 and blocks[-1][1] == m
             for (a0, a1), (b0, b1) in zip(blocks, blocks[1:]):
-                assert a1 == b0 and a0 <= a1
-            assert all(b0 % 128 == 0 for b0, b1 in blocks if b1 > b0)
+                assert a1 == b0 and a0 < a1
+            assert all(b0 % 128 == 0 for b0, b1 in blocks)
 
 
 def _free_port():
