@@ -290,10 +290,20 @@ def run_secondary(args):
             D = rl.DenseDist(d, m)
             ms = timed(lambda: rl.sketch_general_left(ctx, D, rl.RNGState(0), A, d, 1.0, 0.0, B), lambda: None, args.steps, args.warmup)
             fl = 2.0 * d * m * n
-            peak, src, _ = measured_fp64_peak()
+            if args.engine == "i8":
+                dg = args.digits or (4 if dtype == torch.float32 else 6)
+                i8_ops = fl * (dg * (dg + 1) // 2)
+                b_, s_, src, _ = measured_i8_peak()
+                peak = s_ or 2.0 * peaks.get("bf16_tflops_sustained", 1361.4)
+                roof = {"bound": "tensor", "achieved": i8_ops / ms / 1e9, "peak": peak, "unit": "TFLOP/s", "frac": i8_ops / ms / 1e9 / peak,
+                        "op": "int8 multiply-add = 2 ops; whole call (regeneration of S included in the time)", "digits": dg,
+                        "traffic": None, "traffic_algorithmic": es * (m * n + d * n), "peak_source": src}
+            else:
+                peak, src, _ = measured_fp64_peak()
+                roof = {"bound": "tensor", "achieved": fl / ms / 1e9, "peak": peak, "unit": "TFLOP/s", "frac": fl / ms / 1e9 / peak, "traffic": None,
+                        "peak_source": src}
             out = {"metric": "dense_sketch_gflops", "value": fl / ms / 1e6, "unit": "Gflop/s", "ms_per_step": ms,
-                   "roofline": {"bound": "tensor", "achieved": fl / ms / 1e9, "peak": peak, "unit": "TFLOP/s", "frac": fl / ms / 1e9 / peak,
-                                "traffic": None, "peak_source": src},
+                   "roofline": roof,
                    "config": {"workload": f"Gaussian left sketch d={d} (operator regenerated on chip) of a {m} x {n} {args.dtype} matrix"}}
     elif wl == "cqrrpt":
         m, n = args.m if args.m != (1 << 24) else (1 << 23), args.n if args.n != 1024 else 2048

@@ -627,6 +627,28 @@ static void dense_next_state_axis(int64_t n_rows, int64_t n_cols, int major_axis
 
 constexpr size_t kDensePanelBytes = (size_t)32 << 20;
 
+// B(d x n, ldb) = alpha * Z(n x d, ldz)^T + beta * B
+template <typename T>
+__global__ void __launch_bounds__(256) sk_transpose_axpby_kernel(const T* __restrict__ Z, int64_t ldz, int64_t d, int64_t n, double alpha, double beta,
+                                                                T* __restrict__ B, int64_t ldb) {
+    __shared__ double tile[32][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int64_t j0 = (int64_t)blockIdx.x * 32, i0 = (int64_t)blockIdx.y * 32;      // j: column of B (row of Z), i: row of B (column of Z)
+    for (int r = ty; r < 32; r += 8) {
+        const int64_t j = j0 + tx, i = i0 + r;
+        tile[r][tx] = (j < n && i < d) ? (double)Z[j + i * ldz] : 0.0;
+    }
+    __syncthreads();
+    for (int r = ty; r < 32; r += 8) {
+        const int64_t i = i0 + tx, j = j0 + r;
+        if (i < d && j < n) {
+            double v = alpha * tile[tx][r];
+            if (beta != 0.0) v += beta * (double)B[i + j * ldb];
+            B[i + j * ldb] = (T)v;
+        }
+    }
+}
+
 template <typename T>
 int sketch_dense_left(Ctx* ctx, int64_t S_rows, int64_t S_cols, int family, int major_axis, int64_t d, int64_t n, int64_t m, T alpha,
                       int64_t ro, int64_t co, const T* A, int64_t lda, T beta, T* B, int64_t ldb, uint32_t state[6]) {
@@ -643,11 +665,32 @@ int sketch_dense_left(Ctx* ctx, int64_t S_rows, int64_t S_cols, int family, int 
         // tcgen05 int8 digit-slice engine for the long contraction: panels of four 16384-row accumulation chunks keep every SM busy
         const bool i8 = ctx->fp64_engine == RLB200_FP64_I8SLICES && m >= 16384 && d >= 64 && n >= 64;
         if (i8) pc = std::min<int64_t>(std::max<int64_t>(pc, 65536), ((m + 63) / 64) * 64);
+        // Fused engine: the DATA matrix is the tall operand that is sliced inside the tensor-core kernel (read once, as fp64 / fp32), the
+        // regenerated panels of S^T are the small operand; the kernel then produces (S A)^T, accumulated over the panels in scratch and
+        // transposed into B at the end.  Panels of 65536 rows x d values stay a fraction of L2 for d <= 128 and are 134 MB at d = 256.
+        const bool fused = i8 && ozaki2_tn_ok(ctx, std::min<int64_t>(pc, m), n, d, A, lda * (int64_t)sizeof(T));
         ArenaScope as(ctx);
         T* panel = as.take<T>((size_t)2 * d * pc); if (!panel) return RLB200_ERR_ALLOC;
+        T* Zacc = nullptr;
+        if (fused) { Zacc = as.take<T>((size_t)n * d); if (!Zacc) return RLB200_ERR_ALLOC; }
         if (m == 0) RLB_CHECK(gemm_nn<T>(ctx, d, n, 0, 0.0, panel, d, A, lda, (double)beta0, B, ldb));
         int buf = 0;
-        for (int64_t j0 = 0; j0 < m; j0 += pc, buf ^= 1) {
+        for (int64_t j0 = 0; fused && j0 < m; j0 += pc, buf ^= 1) {
+            const int64_t w = std::min(pc, m - j0);
+            T* P = panel + (size_t)buf * d * pc;
+            uint32_t st[6];
+            std::memcpy(st, state, sizeof st);
+            RLB_CHECK(fill_dense_unpacked<T>(ctx, S_rows, S_cols, family, major_axis, RLB200_LAYOUT_ROWMAJOR, d, w, ro, co + shard_off + j0, P, st));
+            RLB_CHECK(ozaki2_gemm_tn<T>(ctx, w, n, d, 1.0, A + j0, lda, P, w, j0 == 0 ? 0.0 : 1.0, Zacc, n));
+        }
+        if (fused) {
+            LaunchScope ls(ctx, RLB200_TIMER_SKETCH);
+            sk_transpose_axpby_kernel<T><<<dim3((unsigned)((n + 31) / 32), (unsigned)((d + 31) / 32)), 256, 0, ctx->stream>>>(Zacc, n, d, n, (double)alpha,
+                                                                                                                          (double)beta0, B, ldb);
+            RLB_CUDA_OK(ctx, cudaGetLastError());
+            RLB_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));      // Zacc is scratch of this scope
+        }
+        for (int64_t j0 = 0; !fused && j0 < m; j0 += pc, buf ^= 1) {
             const int64_t w = std::min(pc, m - j0);
             T* P = panel + (size_t)buf * d * pc;
             uint32_t st[6];
