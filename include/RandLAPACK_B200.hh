@@ -57,6 +57,15 @@ public:
     Context(const Context&) = delete;
     Context& operator=(const Context&) = delete;
     rlb200_ctx* get() const { return h_; }
+    // the reference's `times` vectors (microseconds; rl_cqrrpt.hh:371-384, rl_cqrrt.hh:279-282, rl_bqrrp.hh:582-584)
+    void phase_timing(bool on) { check(rlb200_set_phase_timing(h_, on ? 1 : 0)); }
+    std::vector<long> phase_times() {
+        long long buf[32];
+        int n = rlb200_get_phase_times(h_, buf, 32);
+        std::vector<long> v;
+        for (int i = 0; i < n && i < 32; ++i) v.push_back((long)buf[i]);
+        return v;
+    }
     // engine of the tall products: RLB200_FP64_I8SLICES (tcgen05 int8 digit slices, default) or RLB200_FP64_DMMA (fp64 pipe);
     // digits: 0 = default (6 for fp64 storage, 7 inside the QR drivers, 4 for fp32), else 3..7
     void set_engine(int engine, int digits = 0) { check(rlb200_set_fp64_engine(h_, engine)); check(rlb200_set_i8_digits(h_, digits)); }
@@ -331,7 +340,9 @@ public:
     int call(int64_t m, int64_t n, T* A, int64_t lda, T* R, int64_t ldr, int64_t* J, T d_factor, state_t& state) RLB200_OVERRIDE {
         uint32_t w[6]; state_to_words(state, w);
         int64_t r = 0;
+        if (timing) ctx_->phase_timing(true);
         int rc = ctx_->check(detail::abi<T>::cqrrpt_host(ctx_->get(), m, n, A, lda, R, ldr, J, d_factor, eps, nnz, &r, w));
+        if (timing) { times = ctx_->phase_times(); ctx_->phase_timing(false); }
         words_to_state(w, state);
         rank = r;
         return rc;
@@ -339,7 +350,7 @@ public:
     bool timing;
     T eps;
     int64_t rank;
-    std::vector<long> times;   // kept for source compatibility; per-phase host timing is not offered (see rlb200_timer_read)
+    std::vector<long> times;   // 8 entries when `timing` (rl_cqrrpt.hh:371-384)
     int64_t nnz;
 private:
     Context* ctx_;
@@ -363,8 +374,10 @@ public:
     // A (m x n, lda) <- Q; R (ldr >= n): n x n upper triangular (rl_cqrrt.hh:91-101)
     int call(int64_t m, int64_t n, T* A, int64_t lda, T* R, int64_t ldr, T d_factor, state_t& state) RLB200_OVERRIDE {
         uint32_t w[6]; state_to_words(state, w);
+        if (timing) ctx_->phase_timing(true);
         int rc = ctx_->check(detail::abi<T>::cqrrt_host(ctx_->get(), m, n, A, lda, R, ldr, d_factor, nnz, orthogonalization ? 1 : 0,
                                                         compute_Q ? 1 : 0, w));
+        if (timing) { times = ctx_->phase_times(); ctx_->phase_timing(false); }
         words_to_state(w, state);
         return rc;
     }
@@ -403,7 +416,9 @@ public:
     int call(int64_t m, int64_t n, T* A, int64_t lda, T d_factor, T* tau, int64_t* J, state_t& state) RLB200_OVERRIDE {
         uint32_t w[6]; state_to_words(state, w);
         int64_t r = 0;
+        if (timing) ctx_->phase_timing(true);
         int rc = ctx_->check(detail::abi<T>::bqrrp_host(ctx_->get(), m, n, A, lda, d_factor, block_size, (int)qrcp_wide, (int)qr_tall, tau, J, &r, w));
+        if (timing) { times = ctx_->phase_times(); ctx_->phase_timing(false); }
         words_to_state(w, state);
         rank = r;
         return rc;
@@ -445,7 +460,9 @@ public:
 #endif
     {
         int64_t r = 0;
+        if (timing) ctx_->phase_timing(true);
         int rc = ctx_->check(detail::abi<T>::bqrrp_dev_sk(ctx_->get(), m, n, A, lda, A_sk, d, block_size, (int)qr_tall, tau, J, &r));
+        if (timing) { times = ctx_->phase_times(); ctx_->phase_timing(false); }
         rank = r;
         return rc;
     }

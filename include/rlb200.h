@@ -105,6 +105,12 @@ enum { RLB200_TIMER_GEMM_NN = 0, RLB200_TIMER_GEMM_TN = 1, RLB200_TIMER_RIGHTMUL
 RLB200_API int rlb200_timers_enable(rlb200_ctx* ctx, int on);
 RLB200_API int rlb200_timer_read(rlb200_ctx* ctx, int which, double* ms, int64_t* launches, int reset);
 
+/* Per-phase wall-clock times of the QR drivers, the reference's public `times` vectors (microseconds, same order and length:
+ * CQRRPT 8 entries rl_cqrrpt.hh:371-384, CQRRT 10 entries rl_cqrrt.hh:279-282, BQRRP 10 entries rl_bqrrp.hh:582-584).  Recorded only while
+ * enabled (every phase boundary then synchronises the stream).  rlb200_get_phase_times returns the number of entries of the last call. */
+RLB200_API int rlb200_set_phase_timing(rlb200_ctx* ctx, int on);
+RLB200_API int rlb200_get_phase_times(rlb200_ctx* ctx, long long* out_us, int cap);
+
 /* ---- device memory helpers for host-pointer callers (the C++ adapters in RandLAPACK_B200.hh stage through these so that
  *      they need no CUDA headers).  Copies are stream-ordered on the context's stream; d2h blocks until complete. */
 RLB200_API int rlb200_dev_alloc(rlb200_ctx* ctx, size_t bytes, void** out_dev);

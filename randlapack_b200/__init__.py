@@ -150,6 +150,15 @@ class Context:
         """Digits per value of the int8-slice engine: 0 = default (6 for fp64 storage, 4 for fp32), else 3..7 (8*digits - 2 bits)."""
         self.check(self._lib.rlb200_set_i8_digits(self._h, int(digits)))
 
+    def phase_timing(self, on=True):
+        """Record the reference's per-phase `times` vector (microseconds) during the next CQRRPT / CQRRT / BQRRP call."""
+        self.check(self._lib.rlb200_set_phase_timing(self._h, 1 if on else 0))
+
+    def phase_times(self):
+        buf = (ctypes.c_longlong * 32)()
+        n = self._lib.rlb200_get_phase_times(self._h, buf, 32)
+        return [int(buf[i]) for i in range(max(0, min(n, 32)))]
+
     def set_i8_fused(self, on):
         """True (default): tall products whose shapes allow it slice the tall operand inside the tensor-core kernel (ozaki_fused.cu);
         False: always stage the digits in HBM (ozaki.cu)."""

@@ -334,15 +334,27 @@ int bqrrp_call(Ctx* ctx, int64_t m, int64_t n, T* A, int64_t lda, T d_factor, in
     RLB_CUDA_OK(ctx, cudaMemsetAsync(T_dat, 0, sizeof(T) * b_const * b_const, ctx->stream));
 
     std::vector<int64_t> J((size_t)n, 0), J_buffer((size_t)n, 0), ipiv;
+    // phase times in the reference's order (rl_bqrrp.hh:582-584): skop, preallocation, qrcp_wide, panel_preprocessing, qr_tall,
+    // q_reconstruction, apply_transq, sample_update, other, total
+    PhaseTimer pt(ctx);
+    long long t_skop = 0, t_pre = 0, t_qrcp = 0, t_panel = 0, t_qr = 0, t_rec = 0, t_apply = 0, t_upd = 0;
     auto finish = [&](int64_t rank) -> int {
         *rank_out = rank;
         RLB_CUDA_OK(ctx, cudaMemcpyAsync(J_dev, J.data(), sizeof(int64_t) * n, cudaMemcpyHostToDevice, ctx->stream));
         RLB_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+        if (pt.on) {
+            pt.lap();
+            const long long tot = pt.total();
+            ctx->phase_us = {t_skop, t_pre, t_qrcp, t_panel, t_qr, t_rec, t_apply, t_upd,
+                             tot - (t_skop + t_pre + t_qrcp + t_panel + t_qr + t_rec + t_apply + t_upd), tot};
+        }
         return 0;
     };
+    t_pre = pt.lap();
 
     // Gaussian sketch (:309-312)
     if (!A_sk_ext) RLB_CHECK(bqrrp_sketch<T>(ctx, d, m, n, A, lda, A_sk0, state));
+    t_skop = pt.lap();
     T* A_sk = A_sk0;
     T* A_work = A;
 
@@ -364,6 +376,7 @@ int bqrrp_call(Ctx* ctx, int64_t m, int64_t n, T* A, int64_t lda, T d_factor, in
             RLB_CHECK(col_permute<T>(ctx, sd, cols, A_sk, d, p0.data()));
             RLB_CHECK(geqrf_wide<T>(ctx, sd, cols, A_sk, d, Work2, qr_ws));
         }
+        t_qrcp += pt.lap();
         // ---- pivot the trailing columns of A over all m rows (:365)
         {
             std::vector<int64_t> p0((size_t)cols);
@@ -396,6 +409,7 @@ int bqrrp_call(Ctx* ctx, int64_t m, int64_t n, T* A, int64_t lda, T d_factor, in
             for (int64_t i = 0; i < b_sz; ++i)
                 if (std::abs(dg[i]) / std::abs(dg[0]) < tol) { block_rank = i; break; }
         }
+        t_panel += pt.lap();
         T* tau_sub = tau + curr_sz;
         const int64_t nc = cols - b_sz;
         const int64_t m_apply = (block_rank != b_const) ? block_rank : rows;          // :549-561
@@ -443,6 +457,7 @@ int bqrrp_call(Ctx* ctx, int64_t m, int64_t n, T* A, int64_t lda, T d_factor, in
             RLB_CHECK(qr_small<T>(ctx, false, rows, b_sz, A_work, lda, nullptr, tau_sub, qr_ws));
             k_refl = std::min<int64_t>(block_rank, std::min(rows, b_sz));
         }
+        t_qr += pt.lap();     // (CholQR + Householder reconstruction, or the Householder panel QR)
         // ---- trailing update with k_refl reflectors (:541-562)
         if (k_refl > 0 && nc > 0) {
             const int64_t k = k_refl;
@@ -470,6 +485,7 @@ int bqrrp_call(Ctx* ctx, int64_t m, int64_t n, T* A, int64_t lda, T d_factor, in
             RLB_CHECK(gemm_nn<T>(ctx, br, b_sz, b_sz, 1.0, Rin, br, Gs, b_sz, 0.0, R11n, br));
             RLB_CHECK(tri_op<T>(ctx, 0, br, b_sz, R11n, br, A_work, lda));
         }
+        t_apply += pt.lap();
         curr_sz += b_sz;
         if (curr_sz >= std::min(m, n) || block_rank != b_const) return finish(curr_sz);   // :583-598
         // ---- update the sketch (:602-628)
@@ -484,6 +500,7 @@ int bqrrp_call(Ctx* ctx, int64_t m, int64_t n, T* A, int64_t lda, T d_factor, in
         A_sk = A_sk + d * b_sz;
         rows -= b_sz;
         cols -= b_sz;
+        t_upd += pt.lap();
     }
     return finish(curr_sz);
 }

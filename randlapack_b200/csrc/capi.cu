@@ -191,6 +191,13 @@ int rlb200_set_fp64_engine(rlb200_ctx* ctx, int engine) {
     ctx->fp64_engine = engine;
     return 0;
 }
+int rlb200_set_phase_timing(rlb200_ctx* ctx, int on) { CTX_OK(ctx); ctx->phase_timing = on != 0; ctx->phase_us.clear(); return 0; }
+int rlb200_get_phase_times(rlb200_ctx* ctx, long long* out_us, int cap) {
+    CTX_OK(ctx);
+    const int n = (int)ctx->phase_us.size();
+    for (int i = 0; i < n && i < cap && out_us; ++i) out_us[i] = ctx->phase_us[i];
+    return n;
+}
 int rlb200_set_i8_fused(rlb200_ctx* ctx, int on) { CTX_OK(ctx); ctx->i8_fused = on != 0; return 0; }
 int rlb200_set_i8_digits(rlb200_ctx* ctx, int digits) {
     CTX_OK(ctx);

@@ -4,6 +4,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
+#include <chrono>
 #include <string>
 #include <vector>
 
@@ -73,6 +74,11 @@ struct Ctx {
     // 1 (default): tall products whose shapes allow it run on the fused engine (digits of the tall operand produced inside the
     // tensor-core kernel); 0: always the staged-digit engine (ozaki.cu)
     int i8_fused = 1;
+    // per-phase wall-clock times of the last QR driver call (the reference's `times` vectors: rl_cqrrpt.hh:371-384, rl_cqrrt.hh:279-282,
+    // rl_bqrrp.hh:582-584), microseconds, recorded only when phase_timing is set (each lap synchronises the stream, like the reference's
+    // steady_clock around synchronous BLAS calls)
+    bool phase_timing = false;
+    std::vector<long long> phase_us;
     // stats
     int64_t launches = 0;
     bool timers_on = false;
@@ -98,6 +104,24 @@ struct Ctx {
             return RLB200_ERR_ARG;                                                                  \
         }                                                                                           \
     } while (0)
+
+struct PhaseTimer {
+    Ctx* ctx;
+    bool on;
+    std::chrono::steady_clock::time_point t0, t;
+    explicit PhaseTimer(Ctx* c) : ctx(c), on(c->phase_timing) {
+        if (on) { cudaStreamSynchronize(c->stream); t0 = t = std::chrono::steady_clock::now(); }
+    }
+    long long lap() {
+        if (!on) return 0;
+        cudaStreamSynchronize(ctx->stream);
+        const auto n = std::chrono::steady_clock::now();
+        const long long us = std::chrono::duration_cast<std::chrono::microseconds>(n - t).count();
+        t = n;
+        return us;
+    }
+    long long total() const { return on ? std::chrono::duration_cast<std::chrono::microseconds>(t - t0).count() : 0; }
+};
 
 #define RLB_CHECK(expr)                                                                             \
     do {                                                                                            \

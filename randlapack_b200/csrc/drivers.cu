@@ -670,14 +670,19 @@ int cqrrpt_call(Ctx* ctx, int64_t m, int64_t n, T* A, int64_t lda, T* R, int64_t
     ArenaScope as(ctx);
     T* A_hat = as.take<T>((size_t)d * n); RLB_ALLOC(ctx, A_hat);
     T* tau = as.take<T>((size_t)n); RLB_ALLOC(ctx, tau);
+    // phase times in the reference's order (:371-384): saso, qrcp, rank_reveal, cholqr, a_mod_piv, a_mod_trsm, rest, total
+    PhaseTimer pt(ctx);
+    long long t_saso = 0, t_qrcp = 0, t_rank = 0, t_chol = 0, t_piv = 0, t_trsm = 0;
     // SASO (:214-221); state <- S.next_state
     RLB_CHECK(sketch_sparse_left<T>(ctx, d, mg, nnz, d, n, m, (T)1, 0, 0, A, lda, (T)0, A_hat, d, state));
+    t_saso = pt.lap();
     // QRCP of the sketch (:247)
     {
         ArenaScope as2(ctx);
         void* ws = arena_push(ctx, qrcp_ws_bytes(n)); RLB_ALLOC(ctx, ws);
         RLB_CHECK(qr_small<T>(ctx, true, d, n, A_hat, d, J_dev, tau, ws));
     }
+    t_qrcp = pt.lap();
     std::vector<T> dg;
     RLB_CHECK(read_diag<T>(ctx, A_hat, d, n, dg));
     if (!dg[0]) return 0;                                                                     // :256-261 all-zero input
@@ -687,6 +692,7 @@ int cqrrpt_call(Ctx* ctx, int64_t m, int64_t n, T* A, int64_t lda, T* R, int64_t
     *rank_out = k;
     int64_t new_rank = k;
     RLB_CHECK(tri_op<T>(ctx, 0, k, k, A_hat, d, R, ldr));                                     // lacpy(Upper) :284
+    t_rank = pt.lap();
     // col_swap (:291-292)
     {
         std::vector<int64_t> J((size_t)n);
@@ -695,8 +701,10 @@ int cqrrpt_call(Ctx* ctx, int64_t m, int64_t n, T* A, int64_t lda, T* R, int64_t
         for (auto& v : J) v -= 1;
         RLB_CHECK(col_permute<T>(ctx, m, n, A, lda, J.data()));
     }
+    t_piv = pt.lap();
     for (int64_t i = 0; i < k; ++i) if (dg[i] == (T)0) return 1;                              // diag_is_nonzero :300-305
     RLB_CHECK(tall_right_solve<T>(ctx, m, k, R, ldr, A, lda));                                // :306
+    t_trsm = pt.lap();
     // CholQR (:314-339): the Gram / Cholesky factor is built in scratch so that only the upper triangle of R is written
     T* G = as.take<T>((size_t)k * k); RLB_ALLOC(ctx, G);
     RLB_CUDA_OK(ctx, cudaMemsetAsync(G, 0, sizeof(T) * k * k, ctx->stream));
@@ -728,6 +736,11 @@ int cqrrpt_call(Ctx* ctx, int64_t m, int64_t n, T* A, int64_t lda, T* R, int64_t
         RLB_CHECK(gemm_nn<T>(ctx, new_rank, n, n, 1.0, Rin, new_rank, U, n, 0.0, R, ldr));
     }
     RLB_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));   // scratch is released on return
+    t_chol = pt.lap();
+    if (pt.on) {
+        const long long tot = pt.total();
+        ctx->phase_us = {t_saso, t_qrcp, t_rank, t_chol, t_piv, t_trsm, tot - (t_saso + t_qrcp + t_rank + t_chol + t_piv + t_trsm), tot};
+    }
     return 0;
 }
 
@@ -754,29 +767,39 @@ int cqrrt_call(Ctx* ctx, int64_t m, int64_t n, T* A, int64_t lda, T* R, int64_t 
     ArenaScope as(ctx);
     T* A_hat = as.take<T>((size_t)d * n); RLB_ALLOC(ctx, A_hat);
     T* tau = as.take<T>((size_t)n); RLB_ALLOC(ctx, tau);
+    // phase times in the reference's order (:279-282): saso, qr, trtri (= 0), precond, gram, trmm_gram (= 0), potrf, finalize, rest, total
+    // (the Q-factor solve is excluded from the total, as in the reference)
+    PhaseTimer pt(ctx);
+    long long t_saso = 0, t_qr = 0, t_pre = 0, t_gram = 0, t_potrf = 0, t_q = 0, t_fin = 0;
     // SASO (:144-152); state <- S.next_state
     RLB_CHECK(sketch_sparse_left<T>(ctx, d, mg, nnz, d, n, m, (T)1, 0, 0, A, lda, (T)0, A_hat, d, state));
+    t_saso = pt.lap();
     // geqrf of the sketch (:160)
     {
         ArenaScope as2(ctx);
         void* ws = arena_push(ctx, qrcp_ws_bytes(n)); RLB_ALLOC(ctx, ws);
         RLB_CHECK(qr_small<T>(ctx, false, d, n, A_hat, d, nullptr, tau, ws));
     }
+    t_qr = pt.lap();
     RLB_CHECK(tri_op<T>(ctx, 0, n, n, A_hat, d, R, ldr));                                     // lacpy(Upper) :167
     std::vector<T> dg;
     RLB_CHECK(read_diag<T>(ctx, A_hat, d, n, dg));
     for (int64_t i = 0; i < n; ++i) if (dg[i] == (T)0) return 1;                              // diag_is_nonzero :173-177
     RLB_CHECK(tall_right_solve<T>(ctx, m, n, R, ldr, A, lda));                                // :178 A <- A R_sk^-1
+    t_pre = pt.lap();
     // Gram matrix and its Cholesky factor (:186, :194): built in scratch so that only the upper triangle of R is written
     T* G = as.take<T>((size_t)n * n); RLB_ALLOC(ctx, G);
     RLB_CUDA_OK(ctx, cudaMemsetAsync(G, 0, sizeof(T) * n * n, ctx->stream));
     RLB_CHECK(tall_gram_upper<T>(ctx, m, n, A, lda, G, n));
     if (sharded) RLB_CHECK(allreduce_sum<T>(ctx, G, n * n));
+    t_gram = pt.lap();
     int info = 0;
     RLB_CHECK(potrf_blocked<T>(ctx, n, G, n, &info));
     RLB_CHECK(tri_op<T>(ctx, 0, n, n, G, n, R, ldr));
+    t_potrf = pt.lap();
     if (info != 0) { RLB_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream)); return 1; }        // :194-198
     if (compute_Q) RLB_CHECK(tall_right_solve<T>(ctx, m, n, R, ldr, A, lda));                 // :238 Q = A R_chol^-1
+    t_q = pt.lap();
     if (!orthogonalization) {
         // R <- R_chol * triu(A_hat[0:n, 0:n])  (trmm :249)
         T* U = as.take<T>((size_t)n * n); RLB_ALLOC(ctx, U);
@@ -787,6 +810,11 @@ int cqrrt_call(Ctx* ctx, int64_t m, int64_t n, T* A, int64_t lda, T* R, int64_t 
         RLB_CHECK(tri_op<T>(ctx, 0, n, n, G, n, R, ldr));
     }
     RLB_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));   // scratch is released on return
+    t_fin = pt.lap();
+    if (pt.on) {
+        const long long tot = pt.total() - t_q;
+        ctx->phase_us = {t_saso, t_qr, 0, t_pre, t_gram, 0, t_potrf, t_fin, tot - (t_saso + t_qr + t_pre + t_gram + t_potrf + t_fin), tot};
+    }
     return 0;
 }
 

@@ -256,3 +256,23 @@ def test_cqrrt_zero_column_returns_1(ctx):
     A[:, 7] = 0
     rc, _ = rl.CQRRT(False, None).call(ctx, dev(A), 2.0, rl.RNGState(st.key, st.counter))
     assert rc == 1
+
+
+def test_phase_times_vectors(ctx):
+    """The reference's public `times` vectors (rl_cqrrpt.hh:371-384: 8 entries; rl_cqrrt.hh:279-282: 10; rl_bqrrp.hh:582-584: 10): same
+    length and order, microseconds, the last entry the total and the entries before it summing to it."""
+    A, st = O.gen_poly_mat(20000, 128, 128, 100.0, 2.0, O.RNGState(0))
+    ctx.phase_timing(True)
+    try:
+        rl.CQRRPT(True, None).call(ctx, dev(A), 1.5, rl.RNGState(st.key, st.counter))
+        t = ctx.phase_times()
+        assert len(t) == 8 and t[-1] > 0 and sum(t[:-1]) == t[-1] and all(x >= 0 for x in t[:6])
+        rl.CQRRT(True, None).call(ctx, dev(A), 1.5, rl.RNGState(st.key, st.counter))
+        t = ctx.phase_times()
+        assert len(t) == 10 and t[2] == 0 and t[5] == 0 and t[-1] > 0 and sum(t[:-1]) == t[-1]
+        alg = rl.BQRRP(True, 64)
+        alg.call(ctx, dev(A[:4000]), 1.0, rl.RNGState(st.key, st.counter))
+        t = ctx.phase_times()
+        assert len(t) == 10 and t[-1] > 0 and sum(t[:-1]) == t[-1]
+    finally:
+        ctx.phase_timing(False)
