@@ -193,16 +193,51 @@ __device__ __forceinline__ void oz_pack4(const unsigned long long f[4], uint32_t
 #pragma unroll
     for (int t = 0; t < S; ++t) w[t] = B[S - 1 - t];
 }
+// The same for 4 values at once, cheaper (S <= 6, i.e. P <= 50): the per-byte bias is folded into the addend of the DFMA (an exact integer
+// below 2^40 on top of 1.5 * 2^52), the low 48 bits of the result's bit pattern then ARE F + bias (mod 2^48) - no 64-bit subtraction -, and the
+// re-centring xor is applied to the packed words (one LOP3 per digit and 4 values instead of two per value).  Bit-identical to
+// oz_fixed + oz_pack4.  scale[e]: power-of-two scale of value e.
+template <int S>
+__device__ __forceinline__ void oz_convert4(const double* x, const double* scale, uint32_t* w /* [S] */) {
+    static_assert(OzCfg<S>::P <= 50, "the fixed-point value must fit below the 1.5 * 2^52 offset");
+    const double magic = 6755399441055744.0 + (double)OzCfg<S>::LOWMASK;
+    uint32_t lo[4], hi[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        const double t = fma(x[e], scale[e], magic);
+        lo[e] = (uint32_t)__double2loint(t);
+        hi[e] = (uint32_t)__double2hiint(t);
+    }
+    uint32_t B[8];
+    {
+        const uint32_t t0 = __byte_perm(lo[0], lo[1], 0x5140), t1 = __byte_perm(lo[2], lo[3], 0x5140);
+        const uint32_t t2 = __byte_perm(lo[0], lo[1], 0x7362), t3 = __byte_perm(lo[2], lo[3], 0x7362);
+        B[0] = __byte_perm(t0, t1, 0x5410); B[1] = __byte_perm(t0, t1, 0x7632);
+        B[2] = __byte_perm(t2, t3, 0x5410); B[3] = __byte_perm(t2, t3, 0x7632);
+    }
+    if constexpr (S > 4) {
+        const uint32_t t0 = __byte_perm(hi[0], hi[1], 0x5140), t1 = __byte_perm(hi[2], hi[3], 0x5140);
+        B[4] = __byte_perm(t0, t1, 0x5410); B[5] = __byte_perm(t0, t1, 0x7632);
+    }
+#pragma unroll
+    for (int t = 0; t < S; ++t) w[t] = (t == 0) ? B[S - 1] : (B[S - 1 - t] ^ 0x80808080u);
+}
+
 // 16 consecutive-k values of one tile row -> one 16-byte chunk per digit
 template <int S>
 __device__ __forceinline__ void oz_emit16(const double* xv, double scale, int8_t* tile0, int64_t tile_bytes, int off) {
     uint32_t pk[4][S];
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-        unsigned long long f[4];
+        if constexpr (OzCfg<S>::P <= 50) {
+            const double sv[4] = {scale, scale, scale, scale};
+            oz_convert4<S>(xv + 4 * q, sv, pk[q]);
+        } else {
+            unsigned long long f[4];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) f[e] = oz_fixed<S>(xv[4 * q + e], scale);
-        oz_pack4<S>(f, pk[q]);
+            for (int e = 0; e < 4; ++e) f[e] = oz_fixed<S>(xv[4 * q + e], scale);
+            oz_pack4<S>(f, pk[q]);
+        }
     }
 #pragma unroll
     for (int t = 0; t < S; ++t)
@@ -300,14 +335,20 @@ __global__ void __launch_bounds__(128) oz_slice_tn_kernel(const T* __restrict__ 
         uint32_t pk[4][S];
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-            unsigned long long f[4];
+            double sv[4];
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
                 const int64_t c = c0 + 4 * q + e;
-                const double scale = oz_pow2(OzCfg<S>::P - E[c < ncols ? c : 0]);
-                f[e] = oz_fixed<S>(xv[4 * q + e], scale);
+                sv[e] = oz_pow2(OzCfg<S>::P - E[c < ncols ? c : 0]);
             }
-            oz_pack4<S>(f, pk[q]);
+            if constexpr (OzCfg<S>::P <= 50) {
+                oz_convert4<S>(xv + 4 * q, sv, pk[q]);
+            } else {
+                unsigned long long f[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) f[e] = oz_fixed<S>(xv[4 * q + e], sv[e]);
+                oz_pack4<S>(f, pk[q]);
+            }
         }
         const int off = (cg * 4 + (lane >> 3)) * 128 + (lane & 7) * 16;
 #pragma unroll

@@ -307,10 +307,17 @@ __global__ void __launch_bounds__(Oz2Threads<NG>::N, 1) oz2_kernel(const Oz2Para
                 if (!skip_math) {
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
-                        unsigned long long f[4];
+                        if constexpr (OzCfg<SD>::P <= 50) {
+                            double xv[4], sv[4];
 #pragma unroll
-                        for (int e = 0; e < 4; ++e) f[e] = oz_fixed<SD>((double)raw[4 * q + e], __hiloint2double(sc_hi[TN ? 4 * q + e : 0], 0));
-                        oz_pack4<SD>(f, pk[q]);
+                            for (int e = 0; e < 4; ++e) { xv[e] = (double)raw[4 * q + e]; sv[e] = __hiloint2double(sc_hi[TN ? 4 * q + e : 0], 0); }
+                            oz_convert4<SD>(xv, sv, pk[q]);
+                        } else {
+                            unsigned long long f[4];
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) f[e] = oz_fixed<SD>((double)raw[4 * q + e], __hiloint2double(sc_hi[TN ? 4 * q + e : 0], 0));
+                            oz_pack4<SD>(f, pk[q]);
+                        }
                     }
                 } else {
 #pragma unroll
@@ -323,8 +330,10 @@ __global__ void __launch_bounds__(Oz2Threads<NG>::N, 1) oz2_kernel(const Oz2Para
                     for (int t = 0; t < SD; ++t)
                         if (t < sp) *reinterpret_cast<uint4*>(dst + t * OZ_TILE_B) = make_uint4(pk[0][t], pk[1][t], pk[2][t], pk[3][t]);
                     if (dbg_on) t3 = clock64();
-                    // generic-proxy stores -> visible to the tensor core's (async proxy) operand reads
-                    if (!skip_fence) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    // generic-proxy stores -> visible to the tensor core's (async proxy) operand reads: the proxy fence is executed by the
+                    // consumer (issuer warp, after its acquire of the full barrier), not by the 4 writer warps of every block - a fence here
+                    // costs a MEMBAR per warp and block on the path between "stage free" and "stage full" (p.dbg_flags & 128 restores it)
+                    if (p.dbg_flags & 128) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                     __syncwarp();
                     if (lane == 0) oz2_arrive(oz_smem(&bar_full[slot]));
                 } else {
@@ -440,8 +449,10 @@ __global__ void __launch_bounds__(Oz2Threads<NG>::N, 1) oz2_kernel(const Oz2Para
             const int slot = kb % DST;
             long long t0 = 0;
             if (p.dbg) t0 = clock64();
-            if (share == 1) oz_mbar_wait(oz_smem(&bar_full[slot]), (uint32_t)((kb / DST) & 1));
-            else {
+            if (share == 1) {
+                oz_mbar_wait(oz_smem(&bar_full[slot]), (uint32_t)((kb / DST) & 1));
+                if (!gram) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // the converters' stores of this stage (see there)
+            } else {
                 // the digits of this stage may come from a peer CTA: acquire at cluster scope, then order those generic-proxy stores before the
                 // tensor core's async-proxy reads on the consumer side as well
                 oz_mbar_wait_cluster(oz_smem(&bar_full[slot]), (uint32_t)((kb / DST) & 1));
