@@ -411,6 +411,20 @@ __device__ __forceinline__ void oz_mma_i8(uint32_t d_tmem, uint64_t da, uint64_t
                  ::"r"(d_tmem), "l"(da), "l"(db), "r"(idesc), "r"(acc) : "memory");
 }
 
+// v = 2^16 * sum_d acc_d 256^-d from the S int32 accumulators of one output (acc[d] = the raw TMEM word of anti-diagonal d).
+// Each accumulator becomes a double exactly with one LOP3 + one DADD (2^52 + 2^31 trick; no I2F.F64), then Horner in fp64: the first two
+// steps are exact (<= 47 bits), the rest round at 2^-53 of the running sum - far below the 2^-(8S-3) of the scheme.  12 fp64 + 6 integer
+// instructions per output for S = 6; the previous exact int64 combination cost ~32 integer + 4 fp64 and made the epilogue ALU-bound
+// (10.6 k cycles per 128 x 64 tile; the tensor pipe idles meanwhile).  Fixed evaluation order: results are reproducible run to run.
+template <int S>
+__device__ __forceinline__ double oz_combine(const uint32_t* acc /* [S], stride 8 words between diagonals */) {
+    auto cvt = [](uint32_t a) { return __hiloint2double(0x43300000, (int)(a ^ 0x80000000u)) - 4503601774854144.0; };
+    double h = cvt(acc[(S - 1) * 8]);
+#pragma unroll
+    for (int d = S - 2; d >= 0; --d) h = fma(h, 0.00390625, cvt(acc[d * 8]));
+    return h * 65536.0;
+}
+
 // C = alpha * sum_g part[g] + beta * C  (fixed order)
 template <typename T>
 __global__ void __launch_bounds__(256) oz_reduce_kernel(const double* __restrict__ part, int groups, int64_t total, int n1, double alpha, double beta,

@@ -211,22 +211,7 @@ ozaki_mma_kernel(const int8_t* __restrict__ a_tiles, int64_t a_group_stride, con
                          : "r"(lane_addr + (uint32_t)(d * OZ_BN + c0)));
         }
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        // v = 2^16 * sum_d acc_d 256^-d.  Three diagonals at a time are combined exactly in int64 (|acc| < 2^31 -> < 2^48) and turned
-        // into a double by adding 1.5 * 2^52 as an integer to the high word (int -> fp64 conversion instructions run at a fraction of
-        // the DFMA rate), then chained in fp64.
-        auto combine = [&](int j) -> double {
-            double v = 0.0;
-#pragma unroll
-            for (int gq = (S - 1) / 3; gq >= 0; --gq) {
-                const long long a0 = (int32_t)r[3 * gq][j];
-                const long long a1 = (3 * gq + 1 < S) ? (int32_t)r[(3 * gq + 1 < S) ? 3 * gq + 1 : 0][j] : 0;
-                const long long a2 = (3 * gq + 2 < S) ? (int32_t)r[(3 * gq + 2 < S) ? 3 * gq + 2 : 0][j] : 0;
-                const long long t = a0 * 65536 + a1 * 256 + a2;
-                const double tv = __hiloint2double((int)(t >> 32) + 0x43380000, (int)(uint32_t)t) - 6755399441055744.0;
-                v = (gq == (S - 1) / 3) ? tv : fma(v, 5.9604644775390625e-08 /* 2^-24 */, tv);
-            }
-            return v;
-        };
+        auto combine = [&](int j) -> double { return oz_combine<S>(&r[0][j]); };      // 2^16 * sum_d acc_d 256^-d
         if (i < rows_a) {
             if (simple) {
                 TO* p = og + i + (int64_t)(blockIdx.x * OZ_BN + c0) * ldo;

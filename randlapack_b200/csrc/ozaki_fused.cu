@@ -513,17 +513,7 @@ __global__ void __launch_bounds__(Oz2Threads<NG>::N, 1) oz2_kernel(const Oz2Para
             double v8[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-                // v = 2^16 * sum_d acc_d 256^-d: three diagonals at a time exactly in int64, converted with the 1.5 * 2^52 trick
-                double v = 0.0;
-#pragma unroll
-                for (int gq = (SD - 1) / 3; gq >= 0; --gq) {
-                    const long long a0 = (int32_t)r[3 * gq][j];
-                    const long long a1 = (3 * gq + 1 < SD) ? (int32_t)r[(3 * gq + 1 < SD) ? 3 * gq + 1 : 0][j] : 0;
-                    const long long a2 = (3 * gq + 2 < SD) ? (int32_t)r[(3 * gq + 2 < SD) ? 3 * gq + 2 : 0][j] : 0;
-                    const long long t = a0 * 65536 + a1 * 256 + a2;
-                    const double tv = __hiloint2double((int)(t >> 32) + 0x43380000, (int)(uint32_t)t) - 6755399441055744.0;
-                    v = (gq == (SD - 1) / 3) ? tv : fma(v, 5.9604644775390625e-08 /* 2^-24 */, tv);
-                }
+                const double v = oz_combine<SD>(&r[0][j]);      // 2^16 * sum_d acc_d 256^-d
                 const int en = s_en[c0 + j];
                 double val;
                 if (fast) {
@@ -577,6 +567,290 @@ __global__ void __launch_bounds__(Oz2Threads<NG>::N, 1) oz2_kernel(const Oz2Para
         const long long t_end = clock64();
         d[5] = t_acc - t_cta0; d[6] = t_end - t_acc; d[7] = gram ? 1 : 0;
     }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Persistent A * B kernel (NN): one CTA per SM walks over the output tiles, and the tail of a tile overlaps the head of the next.
+//
+// oz2_kernel spends 19 k of the 48 k cycles of a K = 1024 tile outside the steady main loop: TMEM allocation, barrier set-up, the DRAM
+// latency of the first blocks, the drain of the last DST MMAs (~9 k) and the epilogue (~10.6 k) during which the tensor pipe and the
+// converters idle.  Here the barriers' phases, the TMEM allocation and the stage ring run on across tiles: while the last MMAs of tile j
+// drain, the converters already fill the ring with the first DST blocks of tile j + 1 (they run ahead of the tensor core by the ring
+// depth anyway); then all eight converter warps run phase 1 of tile j's epilogue (TMEM -> fp64 -> a shared-memory buffer of its own),
+// release the accumulators, and write tile j to global memory while the tensor core is already consuming the pre-filled ring of tile
+// j + 1.  The accumulators are single-buffered (6 x 64 = 384 of 512 TMEM columns), so the MMAs of tile j + 1 wait for phase 1 only.
+// ------------------------------------------------------------------------------------------------
+struct Oz3Params {
+    const int8_t* m_tiles; int nkb_stride;          // M side: digit tiles of B^T, tile (bm, kb, t) at ((bm * nkb_stride + kb) * SD + t) * 4096
+    const int* Em; int rows_m;                      // exponents of the columns of B (P applied), number of columns N
+    const void* X; int64_t ldx; int64_t rows_n; int64_t kdim;      // the tall matrix A (rows_n x kdim)
+    const int* En;                                  // raw row exponents of A
+    int nkb, nbm; int64_t ntiles;                   // K blocks per tile, column tiles, tiles in all (tile t: bx = t % nbm, by = t / nbm)
+    void* out; int64_t ldo; double alpha, beta;
+};
+
+template <int SD, typename T>
+struct Oz3Cfg {
+    static constexpr int P = OzCfg<SD>::P;
+    static constexpr int STAGE_BYTES = OzCfg<SD>::STAGE_BYTES;
+    static constexpr int EPI_BYTES = OZ_BM * OZ2_EPI_LD * 8;
+    static constexpr int DST_MAX = (OZ_SMEM_BUDGET - EPI_BYTES) / STAGE_BYTES;
+    static constexpr int DST = DST_MAX > 6 ? 6 : DST_MAX;
+    static constexpr int SMEM_BYTES = DST * STAGE_BYTES + EPI_BYTES;
+    static_assert(DST >= 3, "digit stages");
+};
+
+template <int SD, typename T>
+__global__ void __launch_bounds__(Oz2Threads<2>::N, 1) oz3_kernel(const Oz3Params p) {
+    using Cfg = Oz3Cfg<SD, T>;
+    constexpr int NG = 2, DST = Cfg::DST, P = Cfg::P;
+    constexpr int W_PROD = 4 * NG, W_ISSUE = 4 * NG + 1;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int nkb = p.nkb;
+    const int64_t ntl = p.ntiles > (int64_t)blockIdx.x ? (p.ntiles - 1 - blockIdx.x) / gridDim.x + 1 : 0;      // tiles of this CTA
+
+    extern __shared__ __align__(1024) unsigned char oz3_smem_raw[];
+    __shared__ __align__(8) uint64_t bar_full[DST], bar_empty[DST], bar_acc_full, bar_acc_empty;
+    __shared__ uint32_t tmem_base_sh;
+    __shared__ int s_en[2][OZ_BN];                  // effective row exponents of the tile, by tile parity
+    __shared__ int s_enmin[2], s_enmax[2];
+    double* epi = reinterpret_cast<double*>(oz3_smem_raw + DST * Cfg::STAGE_BYTES);
+
+    if (tid == 0) {
+        for (int s = 0; s < DST; ++s) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 5;" ::"r"(oz_smem(&bar_full[s])));       // producer (+ its bytes) + 4 converter warps
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(oz_smem(&bar_empty[s])));
+        }
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(oz_smem(&bar_acc_full)));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 8;" ::"r"(oz_smem(&bar_acc_empty)));         // the 8 epilogue warps
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == W_PROD) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(oz_smem(&tmem_base_sh)), "n"(OzCfg<SD>::TMEM_COLS));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;");
+    const uint32_t tmem = tmem_base_sh;
+    const uint32_t sbase = oz_smem(oz3_smem_raw);
+
+    if (warp < 4 * NG) {
+        // ================= converters (+ epilogue) =================
+        const int cgp = warp >> 2, cw = warp & 3;
+        const T* __restrict__ X = reinterpret_cast<const T*>(p.X);
+        const int r = (cw & 1) * 32 + lane, kc = cw >> 1;
+        const int off = ((r >> 3) * 2 + kc) * 128 + (r & 7) * 16;
+        const int64_t kleft = p.kdim - kc * 16;
+        // ---- epilogue of tile (bx, by) whose exponents sit in s_en[par]
+        auto epilogue = [&](int bx, int64_t by, int par, uint32_t acc_parity) {
+            oz_mbar_wait_sleep(oz_smem(&bar_acc_full), acc_parity);
+            asm volatile("tcgen05.fence::after_thread_sync;");
+            // all phase-2 reads of the previous tile's buffer are done (and every converter warp has left its conversion loop)
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            {
+                const int quarter = warp & 3, chalf = warp >> 2;
+                const int il = quarter * 32 + lane;
+                const int64_t im = (int64_t)bx * OZ_BM + il;
+                const int em = max(p.Em[min(im, (int64_t)p.rows_m - 1)], P - 1023);
+                constexpr int ESHIFT = (2 * P - 16 * (SD - 1)) + 16;
+                const int enmin = s_enmin[par], enmax = s_enmax[par];
+                const bool finite = em != OZ_NONFINITE_E && enmax != OZ_NONFINITE_E;
+                const bool fast = finite && (em + enmin - ESHIFT >= -1022) && (em + enmax - ESHIFT <= 1023);
+                const int em_hi = (em - ESHIFT + 1023) << 20;
+                const uint32_t lane_addr = tmem + ((uint32_t)(quarter * 32) << 16);
+#pragma unroll 1
+                for (int c0 = chalf * 32; c0 < chalf * 32 + 32; c0 += 8) {
+                    uint32_t rr[SD][8];
+#pragma unroll
+                    for (int d = 0; d < SD; ++d)
+                        asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                                     : "=r"(rr[d][0]), "=r"(rr[d][1]), "=r"(rr[d][2]), "=r"(rr[d][3]), "=r"(rr[d][4]), "=r"(rr[d][5]), "=r"(rr[d][6]), "=r"(rr[d][7])
+                                     : "r"(lane_addr + (uint32_t)(d * OZ_BN + c0)));
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    double v8[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const double v = oz_combine<SD>(&rr[0][j]);
+                        const int en = s_en[par][c0 + j];
+                        double val;
+                        if (fast) val = v * __hiloint2double(em_hi + (en << 20), 0);
+                        else if (em == OZ_NONFINITE_E || en == OZ_NONFINITE_E) val = __longlong_as_double(0x7ff8000000000000ll);
+                        else {
+                            const int e = em + en - ESHIFT;
+                            const int e1 = e / 2, e2 = e - e1;
+                            val = (v * oz_pow2(max(-1022, min(1023, e1)))) * oz_pow2(max(-1022, min(1023, e2)));
+                        }
+                        v8[j] = val;
+                    }
+                    double2* dst = reinterpret_cast<double2*>(epi + il * OZ2_EPI_LD + c0);
+#pragma unroll
+                    for (int j = 0; j < 8; j += 2) dst[j >> 1] = make_double2(v8[j], v8[j + 1]);
+                }
+            }
+            // the accumulators are free for the next tile's MMAs
+            asm volatile("tcgen05.fence::before_thread_sync;");
+            __syncwarp();
+            if (lane == 0) oz2_arrive(oz_smem(&bar_acc_empty));
+            asm volatile("bar.sync 1, 256;" ::: "memory");      // phase 1 of all eight warps is in the buffer
+            {
+                T* outp = reinterpret_cast<T*>(p.out);
+                const int64_t jn = by * OZ_BN + 2 * lane;
+                const bool plain = p.alpha == 1.0 && p.beta == 0.0;
+#pragma unroll 1
+                for (int il = warp; il < OZ_BM; il += 4 * NG) {
+                    const int64_t im = (int64_t)bx * OZ_BM + il;
+                    if (im >= p.rows_m) break;
+                    const double2 v = *reinterpret_cast<const double2*>(epi + il * OZ2_EPI_LD + 2 * lane);
+                    T* o = outp + jn + im * p.ldo;
+                    if (jn < p.rows_n) o[0] = (T)(plain ? v.x : p.alpha * v.x + (p.beta != 0.0 ? p.beta * (double)o[0] : 0.0));
+                    if (jn + 1 < p.rows_n) o[1] = (T)(plain ? v.y : p.alpha * v.y + (p.beta != 0.0 ? p.beta * (double)o[1] : 0.0));
+                }
+            }
+        };
+
+        T bufa[16], bufb[16];
+        int64_t gb0 = 0;                  // blocks of the tiles before this one (ring position)
+        int prev_bx = 0; int64_t prev_by = 0;
+        const int pre = nkb < DST ? nkb : DST;      // blocks of the next tile converted before the previous tile's epilogue
+#pragma unroll 1
+        for (int64_t j = 0; j < ntl; ++j) {
+            const int64_t t = (int64_t)blockIdx.x + j * gridDim.x;
+            const int bx = (int)(t % p.nbm);
+            const int64_t by = t / p.nbm;
+            const int par = (int)(j & 1);
+            // exponents of the tile (out-of-range rows mirror an in-range one so that they do not widen the range)
+            if (warp == 0) {
+                const int64_t j0 = by * OZ_BN + lane, j1 = j0 + 32;
+                const int e0 = max(p.En[min(j0, p.rows_n - 1)], P - 1023), e1 = max(p.En[min(j1, p.rows_n - 1)], P - 1023);
+                s_en[par][lane] = e0; s_en[par][lane + 32] = e1;
+                const int mn = __reduce_min_sync(0xffffffffu, min(e0, e1)), mx = __reduce_max_sync(0xffffffffu, max(e0, e1));
+                if (lane == 0) { s_enmin[par] = mn; s_enmax[par] = mx; }
+            }
+            const int64_t row = by * OZ_BN + r;
+            const bool tv = row < p.rows_n;
+            const T* src = X + (tv ? row : 0) + (int64_t)(kc * 16) * p.ldx;
+            const int sc_hi = tv ? (P - max(p.En[tv ? row : 0], P - 1023) + 1023) << 20 : 0;
+            const int kb_zero = tv ? nkb : 0;
+            const int kb_full = tv ? (int)min((int64_t)nkb, p.kdim / OZ_KB) : 0;
+            // L2 prefetch: one 128-byte line per thread of the group
+            const T* pf_src = nullptr;
+            {
+                constexpr int LPC = (int)(OZ_BN * sizeof(T) / 128);
+                const int tt = cw * 32 + lane;
+                if (tt < (int)(OZ_BN * OZ_KB * sizeof(T) / 128)) {
+                    const int64_t row0 = by * OZ_BN + (tt % LPC) * (128 / (int)sizeof(T));
+                    if (row0 < p.rows_n) pf_src = X + row0 + (int64_t)(tt / LPC) * p.ldx;
+                }
+            }
+            auto prefetch_block = [&](int kb) {
+                if (pf_src != nullptr && kb < kb_full) asm volatile("prefetch.global.L2 [%0];" ::"l"(pf_src + (int64_t)kb * OZ_KB * p.ldx));
+            };
+            auto load_block = [&](int kb, T (&raw)[16]) {
+                const T* s0 = src + (int64_t)kb * OZ_KB * p.ldx;
+                if (kb < kb_full) {
+#pragma unroll
+                    for (int kk = 0; kk < 16; ++kk) raw[kk] = oz2_ldg(s0 + (int64_t)kk * p.ldx);
+                } else if (kb < kb_zero) {
+                    const int64_t cl = kleft - (int64_t)kb * OZ_KB;
+#pragma unroll
+                    for (int kk = 0; kk < 16; ++kk) raw[kk] = kk < cl ? oz2_ldg(s0 + (int64_t)kk * p.ldx) : T(0);
+                } else {
+#pragma unroll
+                    for (int kk = 0; kk < 16; ++kk) raw[kk] = T(0);
+                }
+            };
+            auto convert_block = [&](int kb, const T (&raw)[16]) {
+                const int64_t gb = gb0 + kb;
+                const int slot = (int)(gb % DST);
+                if (gb >= DST) oz_mbar_wait(oz_smem(&bar_empty[slot]), (uint32_t)(((gb / DST) - 1) & 1));
+                unsigned char* dst = oz3_smem_raw + slot * Cfg::STAGE_BYTES + SD * OZ_TILE_A + off;
+                uint32_t pk[4][SD];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    if constexpr (OzCfg<SD>::P <= 50) {
+                        double xv[4], sv[4];
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) { xv[e] = (double)raw[4 * q + e]; sv[e] = __hiloint2double(sc_hi, 0); }
+                        oz_convert4<SD>(xv, sv, pk[q]);
+                    } else {
+                        unsigned long long f[4];
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) f[e] = oz_fixed<SD>((double)raw[4 * q + e], __hiloint2double(sc_hi, 0));
+                        oz_pack4<SD>(f, pk[q]);
+                    }
+                }
+#pragma unroll
+                for (int t2 = 0; t2 < SD; ++t2) *reinterpret_cast<uint4*>(dst + t2 * OZ_TILE_B) = make_uint4(pk[0][t2], pk[1][t2], pk[2][t2], pk[3][t2]);
+                __syncwarp();
+                if (lane == 0) oz2_arrive(oz_smem(&bar_full[slot]));
+            };
+            constexpr int PF = 5;
+            for (int q = 2; q < PF; ++q) prefetch_block(cgp + q * NG);
+            if (cgp < nkb) load_block(cgp, bufa);
+            if (cgp + NG < nkb) load_block(cgp + NG, bufb);
+            bool epi_done = j == 0;       // the previous tile's epilogue runs once the first `pre` blocks of this tile are in the ring
+#pragma unroll 1
+            for (int kb = cgp; kb < nkb; kb += 2 * NG) {
+                if (!epi_done && kb >= pre) { epilogue(prev_bx, prev_by, par ^ 1, (uint32_t)((j - 1) & 1)); epi_done = true; }
+                prefetch_block(kb + PF * NG);
+                prefetch_block(kb + (PF + 1) * NG);
+                convert_block(kb, bufa);
+                if (kb + 2 * NG < nkb) load_block(kb + 2 * NG, bufa);
+                if (kb + NG < nkb) {
+                    if (!epi_done && kb + NG >= pre) { epilogue(prev_bx, prev_by, par ^ 1, (uint32_t)((j - 1) & 1)); epi_done = true; }
+                    convert_block(kb + NG, bufb);
+                    if (kb + 3 * NG < nkb) load_block(kb + 3 * NG, bufb);
+                }
+            }
+            if (!epi_done) epilogue(prev_bx, prev_by, par ^ 1, (uint32_t)((j - 1) & 1));
+            gb0 += nkb;
+            prev_bx = bx; prev_by = by;
+        }
+        if (ntl > 0) epilogue(prev_bx, prev_by, (int)((ntl - 1) & 1), (uint32_t)((ntl - 1) & 1));
+    } else if (tid == W_PROD * 32) {
+        // ================= M-side bulk copies =================
+        int64_t gb = 0;
+        for (int64_t j = 0; j < ntl; ++j) {
+            const int64_t t = (int64_t)blockIdx.x + j * gridDim.x;
+            const int bx = (int)(t % p.nbm);
+            const int8_t* gm = p.m_tiles + (int64_t)bx * p.nkb_stride * (SD * OZ_TILE_A);
+            for (int kb = 0; kb < nkb; ++kb, ++gb) {
+                const int slot = (int)(gb % DST);
+                if (gb >= DST) oz_mbar_wait(oz_smem(&bar_empty[slot]), (uint32_t)(((gb / DST) - 1) & 1));
+                const uint32_t bar = oz_smem(&bar_full[slot]);
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)(SD * OZ_TILE_A)) : "memory");
+                oz_bulk_load(sbase + slot * Cfg::STAGE_BYTES, gm + (int64_t)kb * (SD * OZ_TILE_A), (uint32_t)(SD * OZ_TILE_A), bar);
+            }
+        }
+    } else if (warp == W_ISSUE) {
+        // ================= MMA issue =================
+        uint32_t elected = 0;
+        asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}\n" : "=r"(elected));
+        const uint32_t base_lo0 = sbase >> 4;
+        int64_t gb = 0;
+        for (int64_t j = 0; j < ntl; ++j) {
+            for (int kb = 0; kb < nkb; ++kb, ++gb) {
+                const int slot = (int)(gb % DST);
+                oz_mbar_wait(oz_smem(&bar_full[slot]), (uint32_t)((gb / DST) & 1));
+                // the previous tile's accumulators have been read
+                if (kb == 0 && j > 0) oz_mbar_wait(oz_smem(&bar_acc_empty), (uint32_t)((j - 1) & 1));
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // the converters' generic-proxy stores of this stage
+                asm volatile("tcgen05.fence::after_thread_sync;");
+                if (elected) {
+                    const uint32_t lo = base_lo0 + (uint32_t)slot * (uint32_t)(Cfg::STAGE_BYTES >> 4);
+                    oz2_issue_step<SD, SD, false>(lo, tmem, kb == 0);
+                    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(oz_smem(&bar_empty[slot])) : "memory");
+                    if (kb == nkb - 1)
+                        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(oz_smem(&bar_acc_full)) : "memory");
+                }
+                __syncwarp();
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();
+    if (warp == W_PROD) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(OzCfg<SD>::TMEM_COLS));
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -730,6 +1004,27 @@ static int oz2_nn(Ctx* ctx, int64_t m, int64_t N, int64_t K, double alpha, const
         oz_colexp_kernel<T><<<(unsigned)((N + 7) / 8), 256, 0, st>>>(B, ldb, K, (int)N, K, 1, Cfg::P, Eb, nullptr);
         oz_slice_cols_kernel<SD, OZ_BM, T><<<dim3(nbm, (nkb + 7) / 8), 128, 0, st>>>(B, ldb, K, (int)N, nkb, Eb, bt);
         RLB_CUDA_OK(ctx, cudaGetLastError());
+    }
+    // persistent kernel (the tail of a tile overlaps the head of the next) unless the product is in place (that one needs the cluster barrier
+    // between the last read and the first write of a row tile) - RLB200_OZ3=0 falls back to one CTA per tile
+    static const bool use_oz3 = !(getenv("RLB200_OZ3") && atoi(getenv("RLB200_OZ3")) == 0);
+    if (use_oz3 && (const void*)A != (const void*)C) {
+        static bool done_dev[64] = {};
+        bool& done = done_dev[ctx->device & 63];
+        if (!done) {
+            RLB_CUDA_OK(ctx, cudaFuncSetAttribute(oz3_kernel<SD, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, Oz3Cfg<SD, T>::SMEM_BYTES));
+            done = true;
+        }
+        Oz3Params q{};
+        q.m_tiles = bt; q.nkb_stride = nkb; q.Em = Eb; q.rows_m = (int)N;
+        q.X = A; q.ldx = lda; q.rows_n = m; q.kdim = K; q.En = Ea;
+        q.nkb = nkb; q.nbm = nbm; q.ntiles = nbn * nbm;
+        q.out = C; q.ldo = ldc; q.alpha = alpha; q.beta = beta;
+        LaunchScope ls(ctx, RLB200_TIMER_I8_MMA_NN);
+        const unsigned grid = (unsigned)std::min<int64_t>(q.ntiles, (int64_t)ctx->num_sms);
+        oz3_kernel<SD, T><<<grid, Oz2Threads<2>::N, Oz3Cfg<SD, T>::SMEM_BYTES, st>>>(q);
+        RLB_CUDA_OK(ctx, cudaGetLastError());
+        return 0;
     }
     Oz2Params p{};
     p.m_tiles = bt; p.m_group_stride = 0; p.nkb_stride = nkb;
