@@ -465,6 +465,9 @@ def main():
     ap.add_argument("--config", default="c2", choices=["c2", "c5"],
                     help="c2 (default): BASELINE.json configs[1], 2^24 x 1024 k=256 per GPU (weak scaling); c5: configs[4], 128M x 512 k=128 "
                          "row-sharded - strong scaling where 2^27 / N rows fit one GPU (N >= 4), else 2^25 rows per GPU (weak)")
+    ap.add_argument("--stab", default="cholqrq", choices=["cholqrq", "plul", "hqrq"],
+                    help="RS stabiliser: cholqrq (default, row-shardable, CholQR folded into the next product) or the reference's canonical "
+                         "PLUL (test/drivers/test_rsvd.cc:69-93) / HQRQ; RF and QB always use CholQRQ")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -548,7 +551,9 @@ def main():
     V = rl.empty_f(n, k, torch.float64, dev)
     if world > 1:
         ctx.set_shard(rank * m_local, m_global)
-    stack = rl.RSVD(rl.QB(rl.RF(rl.RS(rl.CholQRQ(), p, q), rl.CholQRQ()), rl.CholQRQ()), k)
+    stab = {"cholqrq": rl.CholQRQ, "plul": rl.PLUL, "hqrq": rl.HQRQ}[args.stab]()
+    stack = rl.RSVD(rl.QB(rl.RF(rl.RS(stab, p, q), rl.CholQRQ()), rl.CholQRQ()), k)
+    config["stabiliser"] = {"cholqrq": "CholQRQ", "plul": "PLUL (RS) + CholQRQ (RF, QB)", "hqrq": "HQRQ (RS) + CholQRQ (RF, QB)"}[args.stab]
 
     def step():
         rc, kk, *_ = stack.call(ctx, A, k, 0.0, rl.RNGState(0), U=U, S=S, V=V)

@@ -539,6 +539,7 @@ class CQRRPT:
         A[:, :k] = trsm_(1.0, _F(R[:k, :k]), _F(A[:, :k]), side=1, lower=0)          # :306
         G = np.triu(_gemm(_F(A[:, :k]), _F(A[:, :k]), ta=True))                     # syrk(Upper) :309
         c, info = potrf(_F(G + np.tril(R[:k, :k], -1)), lower=0, clean=0)           # :311
+        self.potrf_info = int(info)        # (diagnostic for the tests: whether the a-posteriori rank estimate below ran)
         R[:k, :k] = c
         if info:                                                                    # :311-336
             running_max = running_min = R[0, 0]

@@ -114,6 +114,14 @@ __global__ void add_info_offset_kernel(int* info, int offset, int* out) {
     if (threadIdx.x == 0 && blockIdx.x == 0) { if (*out == 0 && *info != 0) *out = *info + offset; }
 }
 
+// dst[i] = A[i, i] (save) or A[i, i] = src[i] for i >= from (restore)
+template <typename T>
+__global__ void __launch_bounds__(256) diag_save_restore_kernel(T* __restrict__ A, int64_t lda, int64_t k, int64_t from, T* __restrict__ buf, int restore) {
+    const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (i >= k || i < from) return;
+    if (restore) A[i + i * lda] = buf[i]; else buf[i] = A[i + i * lda];
+}
+
 template <typename T>
 int potrf_blocked(Ctx* ctx, int64_t k, T* A, int64_t lda, int* info_host) {
     constexpr int NB = 128;
@@ -126,6 +134,11 @@ int potrf_blocked(Ctx* ctx, int64_t k, T* A, int64_t lda, int* info_host) {
     } else {
         T* inv = as.take<T>(NB * NB); if (!inv) return RLB200_ERR_ALLOC;
         T* tmp = as.take<T>((size_t)NB * k); if (!tmp) return RLB200_ERR_ALLOC;
+        // This factorization is right-looking (the trailing matrix carries Schur complements); LAPACK's blocked dpotrf, which the reference
+        // calls, is left-looking and on failure leaves the diagonal blocks after the failing one untouched.  CQRRPT's a-posteriori rank
+        // estimate walks the whole diagonal after a failure (rl_cqrrpt.hh:319-331), so the original diagonal is kept and restored there.
+        T* diag0 = as.take<T>((size_t)k); if (!diag0) return RLB200_ERR_ALLOC;
+        diag_save_restore_kernel<T><<<(unsigned)((k + 255) / 256), 256, 0, ctx->stream>>>(A, lda, k, 0, diag0, 0);
         for (int64_t j = 0; j < k; j += NB) {
             const int64_t jb = std::min<int64_t>(NB, k - j), rem = k - j - jb;
             T* Ajj = A + j + j * lda;
@@ -134,7 +147,12 @@ int potrf_blocked(Ctx* ctx, int64_t k, T* A, int64_t lda, int* info_host) {
             RLB_CUDA_OK(ctx, cudaMemcpyAsync(ctx->hbox, info_dev, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
             RLB_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
             info = *static_cast<int*>(ctx->hbox);
-            if (info != 0) { *info_host = info + (int)j; return 0; }
+            if (info != 0) {
+                *info_host = info + (int)j;
+                if (j + jb < k) diag_save_restore_kernel<T><<<(unsigned)((k + 255) / 256), 256, 0, ctx->stream>>>(A, lda, k, j + jb, diag0, 1);
+                RLB_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));      // diag0 is scratch of this scope
+                return 0;
+            }
             if (rem > 0) {
                 T* A12 = A + j + (j + jb) * lda;
                 RLB_CHECK(trtri_upper<T>(ctx, (int)jb, Ajj, (int)lda, inv));
