@@ -10,6 +10,7 @@
 //   * the b x b pieces (modified LU of orhr_col, T factor, larft) are one-CTA kernels;
 //   * pivot decisions are made on the device; only pivot vectors / rank scalars (O(n) integers per panel) travel to the host.
 #include "drivers.cuh"
+#include <cstdlib>
 #include "philox.cuh"
 #include <algorithm>
 #include <cmath>
@@ -267,9 +268,14 @@ static int apply_qt_wy(Ctx* ctx, int64_t rows, int64_t k, int64_t nc, const T* V
                 : gemm_tn<T>(ctx, rows - k, k, nc, 1.0, V2, ldv, C + k, ldc, 1.0, W, k, 0);
     if (rc >= 0) rc = gemm_tn<T>(ctx, k, k, nc, 1.0, Tm, ldt, W, k, 0.0, W2, k, 0);                               // W2 = T^T W
     if (rc >= 0) rc = gemm_nn<T>(ctx, k, nc, k, -1.0, V1c, k, W2, k, 1.0, C, ldc);                                // C1 -= V1 W2
+    // C2 -= V2 W2: contraction length k = the block size (256: 8 K steps per 128 x 64 output tile).  Such tiles are all set-up and epilogue
+    // on the digit-slice engine (0.65 Pop/s = 23 Tflop/s fp64-equivalent at 65536^2) - and the fp64 pipe is no faster on them (measured at
+    // 32768^2: 3.01 s either way; RLB200_BQRRP_NN_DMMA=1 selects it).
+    static const bool nn_dmma_env = getenv("RLB200_BQRRP_NN_DMMA") != nullptr && atoi(getenv("RLB200_BQRRP_NN_DMMA")) != 0;
+    const bool nn_i8 = i8 && !nn_dmma_env;
     if (rc >= 0 && rows > k)                                                                                      // C2 -= V2 W2
-        rc = i8 ? ozaki_gemm_nn<T>(ctx, rows - k, nc, k, -1.0, V2, ldv, W2, k, 1.0, C + k, ldc)
-                : gemm_nn<T>(ctx, rows - k, nc, k, -1.0, V2, ldv, W2, k, 1.0, C + k, ldc);
+        rc = nn_i8 ? ozaki_gemm_nn<T>(ctx, rows - k, nc, k, -1.0, V2, ldv, W2, k, 1.0, C + k, ldc)
+                   : gemm_nn<T>(ctx, rows - k, nc, k, -1.0, V2, ldv, W2, k, 1.0, C + k, ldc);
     ctx->i8_digits = old_digits;
     return rc < 0 ? rc : 0;
 }

@@ -559,8 +559,31 @@ static int rsvd_single_block_fused(Ctx* ctx, int64_t m, int64_t n, T* A, int64_t
     if (ctx->fp64_engine == RLB200_FP64_I8SLICES && m >= kI8MinRows && k >= 64) {
         const int old = ctx->i8_digits;
         if (!old && sizeof(T) == 8) ctx->i8_digits = 7;
-        const int rc_u = ozaki2_nn_ok(ctx, m, k, k, U, m * (int64_t)sizeof(T), U) ? ozaki2_gemm_nn<T>(ctx, m, k, k, 1.0, U, m, M, k, 0.0, U, m)
-                                                                                     : ozaki_gemm_nn<T>(ctx, m, k, k, 1.0, U, m, M, k, 0.0, U, m);
+        // Chunk-wise through a scratch copy of 2^19 rows of Y when it can be had: the out-of-place product then runs on the persistent
+        // kernel (the tail of a K = 256 tile - 8 K steps - overlaps the next tile; the in-place product pays set-up, cluster barrier and
+        // epilogue per tile: 89 ms at 2^24 x 256 against ~55 ms incl. the copies).  Same digits, same arithmetic, same result.
+        int rc_u = 1;
+        {
+            const int64_t cr = std::min<int64_t>(m, (int64_t)1 << 19);
+            ArenaScope as_u(ctx);
+            T* Ys = (ctx->i8_fused && m > cr && ozaki2_nn_ok(ctx, cr, k, k, U /*alignment only*/, cr * (int64_t)sizeof(T), nullptr))
+                        ? as_u.take<T>((size_t)cr * k) : nullptr;
+            if (Ys) {
+                rc_u = 0;
+                for (int64_t r0 = 0; r0 < m && rc_u >= 0; r0 += cr) {
+                    const int64_t rows = std::min(cr, m - r0);
+                    cudaError_t ce = cudaMemcpy2DAsync(Ys, cr * sizeof(T), U + r0, m * sizeof(T), rows * sizeof(T), k, cudaMemcpyDeviceToDevice, ctx->stream);
+                    if (ce != cudaSuccess) { ctx->err = std::string("cudaMemcpy2DAsync: ") + cudaGetErrorString(ce); rc_u = RLB200_ERR_CUDA; break; }
+                    rc_u = ozaki2_gemm_nn<T>(ctx, rows, k, k, 1.0, Ys, cr, M, k, 0.0, U + r0, m);
+                }
+                if (rc_u >= 0) { cudaError_t ce = cudaStreamSynchronize(ctx->stream); if (ce != cudaSuccess) rc_u = RLB200_ERR_CUDA; }   // scratch leaves scope
+            } else {
+                cudaGetLastError();
+            }
+        }
+        if (rc_u == 1)
+            rc_u = ozaki2_nn_ok(ctx, m, k, k, U, m * (int64_t)sizeof(T), U) ? ozaki2_gemm_nn<T>(ctx, m, k, k, 1.0, U, m, M, k, 0.0, U, m)
+                                                                           : ozaki_gemm_nn<T>(ctx, m, k, k, 1.0, U, m, M, k, 0.0, U, m);
         ctx->i8_digits = old;
         RLB_CHECK(rc_u);
     } else RLB_CHECK(gemm_nn_inplace<T>(ctx, m, k, k, 1.0, U, m, M, k));
