@@ -32,6 +32,28 @@ OZ_TRAFFIC_SOURCE = ("traffic: every kernel of one step, ncu launch list of this
                      "traffic_dominant_launches_only: ncu --set full captures of oz2_kernel (profiles/ncu_oz2_nn_r2.txt, ncu_oz2_tn_r2.txt), DRAM bytes per row "
                      "of A x rows x launches; algorithmic bytes per row and pass: 8 n (A, read once as fp64) + 8 k (Y written) for A*Omega, "
                      "8 n + S k (digits of Y) for A^T*Y")
+# The contract is ONE JSON line on stdout.  Libraries loaded below may print there too (NCCL's version banner when a communicator is
+# created): the process's stdout is pointed at stderr for the whole run and the JSON line is written to the saved descriptor.
+_REAL_STDOUT = None
+
+
+def _capture_stdout():
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(obj):
+    line = (json.dumps(obj) + "\n").encode()
+    sys.stdout.flush()
+    if _REAL_STDOUT is None:
+        os.write(1, line)
+    else:
+        os.write(_REAL_STDOUT, line)
+
+
 METRIC = "rsvd_gflops"
 UNIT = "Gflop/s"
 
@@ -436,7 +458,7 @@ def run_secondary(args):
     out.update({"n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": args.dtype, "data": "synthetic", "clocks": clocks, "gpu_launches": ctx.launch_count(), "cpu_baseline": cpu, "e2e": None})
     out["config"]["l2"] = "inputs exceed the 126 MB L2 by >100x; no flush needed"
-    print(json.dumps(out))
+    emit(out)
     return 0
 
 
@@ -471,6 +493,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
+    _capture_stdout()
     if args.workload != "rsvd":
         if args.dtype is None:
             args.dtype = "f64" if args.workload == "bqrrp" else "f32"
@@ -499,12 +522,12 @@ def main():
             return 0
         gf, t, kind, cores = cpu_sample(n, k, p, q, args.m_cpu, max(1, args.steps), max(0, min(args.warmup, 1)))
         sample = f"{args.m_cpu} x {n} fp64 rows of the same workload (k={k}, p={p}), {cores} threads"
-        print(json.dumps({"impl": "reference", "metric": METRIC, "value": gf, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        emit({"impl": "reference", "metric": METRIC, "value": gf, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
                           "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": scaling,
                           "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
                           "cpu_baseline": {"value": gf, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
                           "e2e": {"value": gf, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-                          "gpu_launches": 0}))
+                          "gpu_launches": 0})
         return 0
 
     import torch
@@ -725,7 +748,7 @@ def main():
            "flops_executed_per_step": sum(class_flops(m_global, n, k, p, q).values()),
            "note": "value = nominal algorithm flops F(m,n,k,p) (DESIGN.md, same F as the reference arm) / time; CholQR's m x k "
                    "triangular solves are folded into the next product and not executed (flops_executed_per_step)"}
-    print(json.dumps(out))
+    emit(out)
     if dist is not None:
         dist.destroy_process_group()
     return 0
