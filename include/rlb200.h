@@ -72,6 +72,15 @@ typedef struct rlb200_stack_opts {
     int32_t reserved;          /* bit 0: 1 = do NOT fold CholQR's triangular solve into the next product (default 0 = fold; same outputs) */
 } rlb200_stack_opts;
 
+/* The algorithm objects of test/drivers/test_revd2.cc:78-101, flattened (SYPS(p, q), SYRF(syps, orth), REVD2(syrf, error_est_p)). */
+enum { RLB200_UPLO_UPPER = 0, RLB200_UPLO_LOWER = 1 };
+typedef struct rlb200_revd2_opts {
+    int64_t syps_passes;           /* SYPS::passes_over_data (rl_syps.hh:27) */
+    int64_t syps_passes_per_stab;  /* SYPS::passes_per_stab  (rl_syps.hh:28) */
+    int32_t orth;                  /* SYRF's orthogonaliser, RLB200_STAB_* (the reference's tests use HQRQ) */
+    int32_t error_est_p;           /* REVD2::error_est_p     (rl_revd2.hh:81) */
+} rlb200_revd2_opts;
+
 /* Sum-allreduce hook for row-sharded operation (net-new; the reference is single-address-space).
  * Called on `count` elements of `elem_size` bytes at DEVICE pointer `buf`, stream-ordered on
  * `stream` (a cudaStream_t).  Return 0 on success.  NULL hook = single shard. */
@@ -324,6 +333,35 @@ RLB200_API int rlb200_col_swap_f32_dev(rlb200_ctx* ctx, int64_t m, int64_t n, fl
  * values (descending), W_dev (k x k, ld k) by the RIGHT singular vectors as columns (so B_in = B_out diag(S) W^T). */
 RLB200_API int rlb200_svd_tall_f64_dev(rlb200_ctx* ctx, int64_t n, int64_t k, double* B_dev, double* S_dev, double* W_dev);
 RLB200_API int rlb200_svd_tall_f32_dev(rlb200_ctx* ctx, int64_t n, int64_t k, float* B_dev, float* S_dev, float* W_dev);
+
+/* ---- f3: SYPS / SYRF / REVD2 on an explicit symmetric matrix (RandLAPACK/comps/rl_syps.hh:21-143, comps/rl_syrf.hh:21-118,
+ *      drivers/rl_revd2.hh:75-246).  A_dev: m x m column-major, lda >= m; only the `uplo` triangle is read (ExplicitSymLinOp,
+ *      linops/rl_sym_linops.hh; the other triangle may hold anything, NaN included).  Replicas only (not row-shardable).
+ * SYPS::call(uplo, m, A, lda, k, state, skop_buff, work_buff): skop_dev (m x k) <- the power-sketched operator, work_dev: m x k scratch;
+ *   state <- the state after the DenseDist(m, k) sample.  The stabiliser is Householder QR (geqrf + ungqr), k <= 256.
+ * SYRF::call(uplo, m, A, k, Q, state, work_buff): Q_dev (m x k) <- orth(A * syps(A)); work_dev: m x k scratch.  Returns 0, or 2 when the
+ *   orthogonaliser fails (the reference throws).
+ * REVD2::call(uplo, m, A, k, tol, V, eigvals, state): V_dev (m x k_cap), eigvals_dev (k_cap); *k in/out: the rank estimate doubles (capped at m)
+ *   until the error estimate <= 5 max(tol, nu) (:225-231).  Returns 0; 1 = Cholesky of the regularised core failed, 2 = orthogonaliser
+ *   failed (both std::runtime_error in the reference); 3 = the next k would exceed k_cap (outputs hold the last iterate; the reference
+ *   would have grown its std::vectors).  err_est (optional) <- the last error estimate. */
+RLB200_API int rlb200_syps_f64_dev(rlb200_ctx* ctx, int uplo, int64_t m, const double* A_dev, int64_t lda, int64_t k, int64_t passes,
+                        int64_t passes_per_stab, double* skop_dev, double* work_dev, uint32_t state[6]);
+RLB200_API int rlb200_syps_f32_dev(rlb200_ctx* ctx, int uplo, int64_t m, const float* A_dev, int64_t lda, int64_t k, int64_t passes,
+                        int64_t passes_per_stab, float* skop_dev, float* work_dev, uint32_t state[6]);
+RLB200_API int rlb200_syrf_f64_dev(rlb200_ctx* ctx, int uplo, int64_t m, const double* A_dev, int64_t lda, int64_t k, double* Q_dev,
+                        double* work_dev, uint32_t state[6], const rlb200_revd2_opts* opts);
+RLB200_API int rlb200_syrf_f32_dev(rlb200_ctx* ctx, int uplo, int64_t m, const float* A_dev, int64_t lda, int64_t k, float* Q_dev,
+                        float* work_dev, uint32_t state[6], const rlb200_revd2_opts* opts);
+RLB200_API int rlb200_revd2_f64_dev(rlb200_ctx* ctx, int uplo, int64_t m, const double* A_dev, int64_t lda, int64_t* k, int64_t k_cap, double tol,
+                         double* V_dev, double* eigvals_dev, uint32_t state[6], const rlb200_revd2_opts* opts, double* err_est);
+RLB200_API int rlb200_revd2_f32_dev(rlb200_ctx* ctx, int uplo, int64_t m, const float* A_dev, int64_t lda, int64_t* k, int64_t k_cap, float tol,
+                         float* V_dev, float* eigvals_dev, uint32_t state[6], const rlb200_revd2_opts* opts, float* err_est);
+/* Host-pointer form (the reference's calling convention): A, V (m x k_cap), eigvals (k_cap) are HOST buffers. */
+RLB200_API int rlb200_revd2_f64_host(rlb200_ctx* ctx, int uplo, int64_t m, const double* A, int64_t lda, int64_t* k, int64_t k_cap, double tol,
+                          double* V, double* eigvals, uint32_t state[6], const rlb200_revd2_opts* opts, double* err_est);
+RLB200_API int rlb200_revd2_f32_host(rlb200_ctx* ctx, int uplo, int64_t m, const float* A, int64_t lda, int64_t* k, int64_t k_cap, float tol,
+                          float* V, float* eigvals, uint32_t state[6], const rlb200_revd2_opts* opts, float* err_est);
 
 #ifdef __cplusplus
 }

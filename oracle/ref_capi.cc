@@ -20,6 +20,9 @@
 #include "RandLAPACK/drivers/rl_cqrrpt.hh"
 #include "RandLAPACK/drivers/rl_cqrrt.hh"
 #include "RandLAPACK/drivers/rl_bqrrp.hh"
+#include "RandLAPACK/comps/rl_syps.hh"
+#include "RandLAPACK/comps/rl_syrf.hh"
+#include "RandLAPACK/drivers/rl_revd2.hh"
 #include "RandLAPACK/testing/rl_gen.hh"
 
 #include <cstring>
@@ -259,6 +262,54 @@ static int bqrrp_impl(int64_t m, int64_t n, T* A, int64_t lda, T d_factor, int64
     RL_CATCH
 }
 
+// SYPS / SYRF / REVD2 (RandLAPACK/comps/rl_syps.hh:21-143, comps/rl_syrf.hh:21-118, drivers/rl_revd2.hh:75-246); the algorithm objects
+// of test/drivers/test_revd2.cc:78-101.  uplo: 0 upper, 1 lower.
+template <typename T>
+static int syps_impl(int uplo, int64_t m, const T* A, int64_t lda, int64_t k, int64_t p, int64_t q, T* skop, uint32_t state[6]) {
+    RL_TRY
+    RandLAPACK::SYPS<T, RNG> syps(p, q, false, false);
+    State st = load_state(state);
+    T* sk = skop;
+    std::vector<T> work(m * k, 0.0);
+    int rc = syps.call(uplo ? blas::Uplo::Lower : blas::Uplo::Upper, m, A, lda, k, st, sk, work.data());
+    store_state(st, state);
+    return rc;
+    RL_CATCH
+}
+template <typename T>
+static int syrf_impl(int uplo, int64_t m, const T* A, int64_t k, int64_t p, int64_t q, int orth, T* Q, uint32_t state[6]) {
+    RL_TRY
+    RandLAPACK::SYPS<T, RNG> syps(p, q, false, false);
+    auto o = make_stab<T>(orth, false);
+    RandLAPACK::SYRF<RandLAPACK::SYPS<T, RNG>, RandLAPACK::Stabilization<T>> syrf(syps, *o, false, false);
+    State st = load_state(state);
+    std::vector<T> Qv;
+    int rc = syrf.call(uplo ? blas::Uplo::Lower : blas::Uplo::Upper, m, A, k, Qv, st, nullptr);
+    std::memcpy(Q, Qv.data(), sizeof(T) * m * k);
+    store_state(st, state);
+    return rc;
+    RL_CATCH
+}
+template <typename T>
+static int revd2_impl(int uplo, int64_t m, const T* A, int64_t* k, int64_t k_cap, T tol, int64_t p, int64_t q, int orth, int error_est_p,
+                      T* V, T* eigvals, uint32_t state[6]) {
+    RL_TRY
+    RandLAPACK::SYPS<T, RNG> syps(p, q, false, false);
+    auto o = make_stab<T>(orth, false);
+    using SYRF_t = RandLAPACK::SYRF<RandLAPACK::SYPS<T, RNG>, RandLAPACK::Stabilization<T>>;
+    SYRF_t syrf(syps, *o, false, false);
+    RandLAPACK::REVD2<SYRF_t> revd2(syrf, error_est_p, false);
+    State st = load_state(state);
+    std::vector<T> Vv, ev;
+    int rc = revd2.call(uplo ? blas::Uplo::Lower : blas::Uplo::Upper, m, A, *k, tol, Vv, ev, st);
+    if (*k > k_cap) throw std::runtime_error("revd2: k grew beyond the caller's capacity");
+    std::memcpy(V, Vv.data(), sizeof(T) * m * (*k));
+    std::memcpy(eigvals, ev.data(), sizeof(T) * (*k));
+    store_state(st, state);
+    return rc;
+    RL_CATCH
+}
+
 extern "C" {
 
 const char* rlref_last_error(void) { return g_err; }
@@ -371,6 +422,16 @@ int rlref_mat_gen_f32(int type, int64_t m, int64_t n, int64_t rank, float cond, 
     int rlref_cqrrt_##SUF(int64_t m, int64_t n, T* A, int64_t lda, T* R, int64_t ldr, T d_factor, T eps, int64_t nnz, int orthogonalization,     \
                           int compute_Q, uint32_t state[6]) {                                                                              \
         return cqrrt_impl<T>(m, n, A, lda, R, ldr, d_factor, eps, nnz, orthogonalization, compute_Q, state);                               \
+    }                                                                                                                                     \
+    int rlref_syps_##SUF(int uplo, int64_t m, const T* A, int64_t lda, int64_t k, int64_t p, int64_t q, T* skop, uint32_t state[6]) {      \
+        return syps_impl<T>(uplo, m, A, lda, k, p, q, skop, state);                                                                        \
+    }                                                                                                                                     \
+    int rlref_syrf_##SUF(int uplo, int64_t m, const T* A, int64_t k, int64_t p, int64_t q, int orth, T* Q, uint32_t state[6]) {            \
+        return syrf_impl<T>(uplo, m, A, k, p, q, orth, Q, state);                                                                          \
+    }                                                                                                                                     \
+    int rlref_revd2_##SUF(int uplo, int64_t m, const T* A, int64_t* k, int64_t k_cap, T tol, int64_t p, int64_t q, int orth,               \
+                          int error_est_p, T* V, T* eigvals, uint32_t state[6]) {                                                          \
+        return revd2_impl<T>(uplo, m, A, k, k_cap, tol, p, q, orth, error_est_p, V, eigvals, state);                                       \
     }                                                                                                                                     \
     int rlref_bqrrp_##SUF(int64_t m, int64_t n, T* A, int64_t lda, T d_factor, int64_t b_sz, int qrcp_wide, int qr_tall, T* tau,           \
                           int64_t* J, int64_t* rank, uint32_t state[6]) {                                                                  \

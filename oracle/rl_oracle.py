@@ -18,6 +18,7 @@ import os
 from dataclasses import dataclass
 
 import numpy as np
+import scipy.linalg
 from scipy.linalg import get_blas_funcs, get_lapack_funcs
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
@@ -588,6 +589,127 @@ class CQRRT:
         if not self.orthogonalization:
             R[:, :] = np.triu(R) @ np.triu(A_hat[:n, :n]) + np.tril(R, -1)          # trmm :249
         return 0, A, R, state
+
+
+# --------------------------------------------------------------------------------------------
+# SYPS / SYRF / REVD2 (RandLAPACK/comps/rl_syps.hh, comps/rl_syrf.hh, drivers/rl_revd2.hh)
+# --------------------------------------------------------------------------------------------
+def _symm(uplo, A, B):
+    """ExplicitSymLinOp::operator() (linops/rl_sym_linops.hh:76-99): blas::symm(Left, uplo) - only the `uplo` triangle of A is read."""
+    (symm,) = get_blas_funcs(("symm",), (A, B))
+    return _F(symm(1.0, A, B, side=0, lower=int(uplo in ("L", "l", 1))))
+
+
+class SYPS:
+    """rl_syps.hh:21-143 - skop = fill_dense(DenseDist(m, k)); p passes of skop <- A skop with geqrf + ungqr every q passes."""
+
+    def __init__(self, p, q, verbose=False, cond_check=False):
+        self.passes_over_data, self.passes_per_stab = p, q
+
+    def call(self, uplo, A, k, state: RNGState):
+        """-> (0, skop m x k, next state)."""
+        m = A.shape[0]
+        p, q = self.passes_over_data, self.passes_per_stab
+        mat, state = fill_dense(m, k, state, dtype=A.dtype)                          # :74-75
+        skop = _F(mat)                          # m >= k: the natural layout of DenseDist(m, k) is column-major (dense_skops.hh:184-196)
+        work = np.zeros((m, k), dtype=A.dtype, order="F")                            # :80
+        geqrf, orgqr = get_lapack_funcs(("geqrf", "orgqr"), (A,))
+        bufs = {"skop": skop, "work": work}
+        out, inn = "work", "skop"
+        p_done = 0
+        while p - p_done > 0:
+            bufs[out] = _symm(uplo, A, bufs[inn])                                    # :86
+            p_done += 1
+            if p_done % q == 0:                                                      # :88-93
+                qr, tau, _, info = geqrf(bufs[out])
+                if info:
+                    raise RuntimeError("GEQRF failed.")
+                bufs[out] = _F(orgqr(qr, tau)[0])
+            out, inn = ("skop", "work") if p_done % 2 == 1 else ("work", "skop")     # :95-96
+        if p % 2 == 1:
+            bufs["skop"] = bufs["work"].copy(order="F")                              # :99-100
+        return 0, bufs["skop"], state
+
+
+class SYRF:
+    """rl_syrf.hh:21-118 - Q = orth(A * syps(A)); a failing orthogonaliser raises as the reference throws."""
+
+    def __init__(self, syps, orth, verbose=False, cond_check=False):
+        self.syps, self.orth = syps, orth
+
+    def call(self, uplo, A, k, state: RNGState):
+        _, omega, state = self.syps.call(uplo, A, k, state)                          # :83
+        Q = _symm(uplo, A, omega)                                                    # :86
+        rc, Q = self.orth.call(Q)                                                    # :94
+        if rc:
+            raise RuntimeError("Orthogonalization failed.")
+        return 0, Q, state
+
+
+def power_error_est(uplo, A, k, p, g, V, eigvals):
+    """rl_revd2.hh:20-71 (g: the m-vector the reference keeps in the first column of vector_buf)."""
+    err = A.dtype.type(0)
+    g = g.copy()
+    for _ in range(p):
+        g = g / np.linalg.norm(g)                                                    # :34-36
+        t1 = V.T @ g                                                                 # :40
+        Mat = V * eigvals[None, :k]                                                  # :44-48
+        t2 = Mat @ t1                                                                # :52
+        t3 = _symm(uplo, A, _F(g.reshape(-1, 1))).ravel()                            # :55
+        w = t3 - t2                                                                  # :60
+        err = g @ w                                                                  # :62
+        g = w                                                                        # :64
+    return err
+
+
+class REVD2:
+    """rl_revd2.hh:75-246."""
+
+    def __init__(self, syrf, error_est_power_iters, verbose=False):
+        self.syrf, self.error_est_p, self.err, self.k_history = syrf, error_est_power_iters, None, []
+
+    def call(self, uplo, A, k, tol, state: RNGState):
+        """-> (0, k, V m x k, eigvals k, next state)."""
+        if not (k > 0 and tol >= 0):
+            raise ValueError("randlapack_require failed")                            # :131-134
+        A = _F(A)
+        m = A.shape[0]
+        dt = A.dtype
+        est_state = RNGState(key=_key_incr(state.key, 1), counter=state.counter)     # :152-153
+        (trsm,) = get_blas_funcs(("trsm",), (A,))
+        (potrf,) = get_lapack_funcs(("potrf",), (A,))
+        self.k_history = []
+        while True:
+            self.k_history.append(k)
+            _, Omega, state = self.syrf.call(uplo, A, k, state)                      # :166
+            Y = _symm(uplo, A, Omega)                                                # :169
+            nu = dt.type(np.finfo(dt).eps) * dt.type(np.linalg.norm(Y, "fro"))       # :171
+            R = nu * (Omega.T @ Omega)                                               # syrk + mirror (:177-179)
+            R = _F(Omega.T @ Y + R)                                                  # :181
+            c, info = potrf(R, lower=0, clean=1)                                     # :185-187 (get_U)
+            if info:
+                raise RuntimeError("Cholesky decomposition failed.")
+            B = trsm(1.0, _F(c), Y, side=1, lower=0, trans_a=0, diag=0)              # :190
+            V, S, _ = scipy.linalg.svd(B, full_matrices=False, lapack_driver="gesdd")   # :195
+            V = _F(V)
+            eig = (S * S).astype(dt)                                                 # :198-207
+            r = int(np.sum(eig > nu))
+            for i in range(r):                                                       # :211-212
+                if not (eig[i] - nu < 0):
+                    eig[i] -= nu
+            V[:, r:] = 0                                                             # :214
+            g, est_state = fill_dense(m, 1, est_state, dtype=dt)                     # :219-221
+            err = power_error_est(uplo, A, k, self.error_est_p, np.asarray(g).ravel(order="A"), V, eig)   # :223
+            self.err = err
+            if err <= 5 * max(tol, nu) or k == m:                                    # :225-231
+                break
+            k = m if 2 * k > m else 2 * k
+        return 0, k, V, eig, state
+
+
+def _key_incr(key, n):
+    v = (key[0] | (key[1] << 32)) + n
+    return (v & 0xFFFFFFFF, (v >> 32) & 0xFFFFFFFF)
 
 
 # --------------------------------------------------------------------------------------------

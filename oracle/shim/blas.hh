@@ -65,6 +65,8 @@ void RLB_F(dgemm)(const char*, const char*, const int*, const int*, const int*, 
 void RLB_F(sgemm)(const char*, const char*, const int*, const int*, const int*, const float*, const float*, const int*, const float*, const int*, const float*, float*, const int*, size_t, size_t);
 void RLB_F(dsyrk)(const char*, const char*, const int*, const int*, const double*, const double*, const int*, const double*, double*, const int*, size_t, size_t);
 void RLB_F(ssyrk)(const char*, const char*, const int*, const int*, const float*, const float*, const int*, const float*, float*, const int*, size_t, size_t);
+void RLB_F(dsymm)(const char*, const char*, const int*, const int*, const double*, const double*, const int*, const double*, const int*, const double*, double*, const int*, size_t, size_t);
+void RLB_F(ssymm)(const char*, const char*, const int*, const int*, const float*, const float*, const int*, const float*, const int*, const float*, float*, const int*, size_t, size_t);
 void RLB_F(dtrsm)(const char*, const char*, const char*, const char*, const int*, const int*, const double*, const double*, const int*, double*, const int*, size_t, size_t, size_t, size_t);
 void RLB_F(strsm)(const char*, const char*, const char*, const char*, const int*, const int*, const float*, const float*, const int*, float*, const int*, size_t, size_t, size_t, size_t);
 void RLB_F(dtrmm)(const char*, const char*, const char*, const char*, const int*, const int*, const double*, const double*, const int*, double*, const int*, size_t, size_t, size_t, size_t);
@@ -120,6 +122,21 @@ inline void syrk(Layout layout, Uplo uplo, Op trans, int64_t n, int64_t k, T alp
 }
 RLB_SYRK(double, dsyrk)
 RLB_SYRK(float, ssyrk)
+
+#define RLB_SYMM(T, f)                                                                                   \
+inline void symm(Layout layout, Side side, Uplo uplo, int64_t m, int64_t n, T alpha, const T* A,        \
+                 int64_t lda, const T* B, int64_t ldb, T beta, T* C, int64_t ldc) {                      \
+    int m_ = RLB_BI(m), n_ = RLB_BI(n), lda_ = RLB_BI(lda), ldb_ = RLB_BI(ldb), ldc_ = RLB_BI(ldc);      \
+    if (layout == Layout::RowMajor) {                                                                    \
+        side = (side == Side::Left ? Side::Right : Side::Left);                                          \
+        uplo = (uplo == Uplo::Lower ? Uplo::Upper : Uplo::Lower);                                        \
+        std::swap(m_, n_);                                                                               \
+    }                                                                                                    \
+    char sd = to_char(side), ul = to_char(uplo);                                                         \
+    RLB_F(f)(&sd, &ul, &m_, &n_, &alpha, A, &lda_, B, &ldb_, &beta, C, &ldc_, 1, 1);                     \
+}
+RLB_SYMM(double, dsymm)
+RLB_SYMM(float, ssymm)
 
 #define RLB_TRXM(name, T, f)                                                                             \
 inline void name(Layout layout, Side side, Uplo uplo, Op trans, Diag diag, int64_t m, int64_t n,        \

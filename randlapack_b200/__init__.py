@@ -652,6 +652,86 @@ class CQRRT:
         return rc, R
 
 
+class SYPS:
+    """RandLAPACK::SYPS(p, q, verbose, cond_check) (rl_syps.hh:21-143): power sketch of a symmetric operator, Householder-QR stabilised."""
+
+    def __init__(self, passes_over_data, passes_per_stab, verbose=False, cond_check=False):
+        self.passes_over_data, self.passes_per_stab = passes_over_data, passes_per_stab
+
+    def call(self, ctx: Context, uplo, A, k, state: RNGState):
+        """A: m x m device column-major (only the `uplo` triangle is read) -> (0, skop m x k)."""
+        assert _is_f(A) and A.shape[0] == A.shape[1]
+        m = A.shape[0]
+        skop, work = empty_f(m, k, A.dtype, A.device), empty_f(m, k, A.dtype, A.device)
+        w = state.words()
+        fn = getattr(ctx._lib, f"rlb200_syps_{_suffix(A.dtype)}_dev")
+        rc = ctx.check(fn(ctx._h, _uplo(uplo), m, A.data_ptr(), _ld(A), k, self.passes_over_data, self.passes_per_stab, skop.data_ptr(),
+                          work.data_ptr(), w))
+        state.assign(w)
+        return rc, skop
+
+
+class SYRF:
+    """RandLAPACK::SYRF(syps, orth) (rl_syrf.hh:21-118): Q = orth(A * syps(A))."""
+
+    def __init__(self, syps: SYPS, orth: _Stab, verbose=False, cond_check=False):
+        self.syps, self.orth = syps, orth
+
+    def _opts(self, error_est_p=0):
+        return _capi.Revd2Opts(self.syps.passes_over_data, self.syps.passes_per_stab, self.orth.kind, error_est_p)
+
+    def call(self, ctx: Context, uplo, A, k, state: RNGState):
+        assert _is_f(A) and A.shape[0] == A.shape[1]
+        m = A.shape[0]
+        Q, work = empty_f(m, k, A.dtype, A.device), empty_f(m, k, A.dtype, A.device)
+        w = state.words()
+        o = self._opts()
+        fn = getattr(ctx._lib, f"rlb200_syrf_{_suffix(A.dtype)}_dev")
+        rc = ctx.check(fn(ctx._h, _uplo(uplo), m, A.data_ptr(), _ld(A), k, Q.data_ptr(), work.data_ptr(), w, ctypes.byref(o)))
+        state.assign(w)
+        return rc, Q
+
+
+class REVD2:
+    """RandLAPACK::REVD2(syrf, error_est_power_iters) (rl_revd2.hh:75-246): rank-revealing randomized eigendecomposition of a PSD matrix.
+    call -> (rc, k, V m x k, eigvals k); rc 1 / 2 are the reference's std::runtime_error cases, 3 = k_cap reached (include/rlb200.h)."""
+
+    def __init__(self, syrf: SYRF, error_est_power_iters, verbose=False):
+        self.syrf, self.error_est_p, self.err = syrf, error_est_power_iters, None
+
+    def _run(self, ctx, host, uplo, A, k, tol, state, k_cap):
+        torch = _torch()
+        assert _is_f(A) and A.shape[0] == A.shape[1] and A.is_cuda != host
+        m = A.shape[0]
+        k_cap = m if k_cap is None else k_cap
+        V = empty_f(m, k_cap, A.dtype, A.device)
+        ev = torch.zeros(k_cap, dtype=A.dtype, device=A.device)
+        kk = ctypes.c_int64(k)
+        err = (ctypes.c_double if A.dtype == torch.float64 else ctypes.c_float)(0)
+        o = self.syrf._opts(self.error_est_p)
+        w = state.words()
+        fn = getattr(ctx._lib, f"rlb200_revd2_{_suffix(A.dtype)}_{'host' if host else 'dev'}")
+        rc = ctx.check(fn(ctx._h, _uplo(uplo), m, A.data_ptr(), _ld(A), ctypes.byref(kk), k_cap, tol, V.data_ptr(), ev.data_ptr(), w,
+                          ctypes.byref(o), ctypes.byref(err)))
+        state.assign(w)
+        self.err = err.value
+        return rc, kk.value, V[:, :kk.value], ev[:kk.value]
+
+    def call(self, ctx: Context, uplo, A, k, tol, state: RNGState, k_cap=None):
+        return self._run(ctx, False, uplo, A, k, tol, state, k_cap)
+
+    def call_host(self, ctx: Context, uplo, A_host, k, tol, state: RNGState, k_cap=None):
+        return self._run(ctx, True, uplo, A_host, k, tol, state, k_cap)
+
+
+def _uplo(u):
+    if u in (_capi.UPLO_UPPER, "U", "u", "upper", "Upper"):
+        return _capi.UPLO_UPPER
+    if u in (_capi.UPLO_LOWER, "L", "l", "lower", "Lower"):
+        return _capi.UPLO_LOWER
+    raise Error(_capi.ERR_ARG, f"uplo {u!r}")
+
+
 class BQRRP:
     """RandLAPACK::BQRRP(time_subroutines, b_sz) (rl_bqrrp.hh:43-152); public fields block_size, qrcp_wide, qr_tall, rank.
     Defaults are the reference's (luqr + geqrf); BQRRP_GPU's configuration is qr_tall = QRTALL_CHOLQR."""

@@ -31,6 +31,13 @@ class StackOpts(ctypes.Structure):
                 ("orth_rf", c_i32), ("orth_qb", c_i32), ("cond_check", c_i32), ("orth_check", c_i32), ("reserved", c_i32)]
 
 
+class Revd2Opts(ctypes.Structure):
+    """rlb200_revd2_opts (include/rlb200.h) — SYPS(p, q) / SYRF(syps, orth) / REVD2(syrf, error_est_p), test/drivers/test_revd2.cc:78-101."""
+    _fields_ = [("syps_passes", c_i64), ("syps_passes_per_stab", c_i64), ("orth", c_i32), ("error_est_p", c_i32)]
+
+
+UPLO_UPPER, UPLO_LOWER = 0, 1
+
 ALLREDUCE_FN = ctypes.CFUNCTYPE(c_int, c_vp, c_vp, c_i64, c_i32, c_vp)
 
 # name -> (restype, argtypes); mirrors include/rlb200.h one to one (tests/test_abi.py checks the header against this table)
@@ -91,6 +98,11 @@ for _suf, _ft in (("f64", ctypes.c_double), ("f32", ctypes.c_float)):
     SIGNATURES[f"rlb200_bqrrp_{_suf}_host"] = (c_int, [c_vp, c_i64, c_i64, c_vp, c_i64, _ft, c_i64, c_int, c_int, c_vp, c_vp, P_i64, P_u32])
     SIGNATURES[f"rlb200_cqrrt_{_suf}_dev"] = (c_int, [c_vp, c_i64, c_i64, c_vp, c_i64, c_vp, c_i64, _ft, c_i64, c_int, c_int, P_u32])
     SIGNATURES[f"rlb200_cqrrt_{_suf}_host"] = (c_int, [c_vp, c_i64, c_i64, c_vp, c_i64, c_vp, c_i64, _ft, c_i64, c_int, c_int, P_u32])
+    SIGNATURES[f"rlb200_syps_{_suf}_dev"] = (c_int, [c_vp, c_int, c_i64, c_vp, c_i64, c_i64, c_i64, c_i64, c_vp, c_vp, P_u32])
+    SIGNATURES[f"rlb200_syrf_{_suf}_dev"] = (c_int, [c_vp, c_int, c_i64, c_vp, c_i64, c_i64, c_vp, c_vp, P_u32, ctypes.POINTER(Revd2Opts)])
+    SIGNATURES[f"rlb200_revd2_{_suf}_dev"] = (c_int, [c_vp, c_int, c_i64, c_vp, c_i64, P_i64, c_i64, _ft, c_vp, c_vp, P_u32,
+                                                       ctypes.POINTER(Revd2Opts), ctypes.POINTER(_ft)])
+    SIGNATURES[f"rlb200_revd2_{_suf}_host"] = SIGNATURES[f"rlb200_revd2_{_suf}_dev"]
     SIGNATURES[f"rlb200_bqrrp_{_suf}_dev_sk"] = (c_int, [c_vp, c_i64, c_i64, c_vp, c_i64, c_vp, c_i64, c_i64, c_int, c_vp, c_vp, P_i64])
     SIGNATURES[f"rlb200_rsvd_{_suf}_host"] = (c_int, [c_vp, c_i64, c_i64, c_vp, P_i64, _ft, c_vp, c_vp, c_vp, P_u32,
                                                       ctypes.POINTER(StackOpts), P_int])

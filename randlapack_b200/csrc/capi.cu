@@ -322,6 +322,37 @@ int rlb200_set_i8_digits(rlb200_ctx* ctx, int digits) {
         RLB_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));                                                                       \
         return rc;                                                                                                                  \
     }                                                                                                                               \
+    int rlb200_syps_##SUF##_dev(rlb200_ctx* ctx, int uplo, int64_t m, const T* A_dev, int64_t lda, int64_t k, int64_t passes,       \
+                                int64_t passes_per_stab, T* skop_dev, T* work_dev, uint32_t state[6]) {                             \
+        CTX_OK(ctx); RLB_CHECK(bind(ctx)); RLB_REQUIRE(ctx, state != nullptr);                                                      \
+        return syps_call<T>(ctx, uplo, m, A_dev, lda, k, passes, passes_per_stab, skop_dev, work_dev, state);                       \
+    }                                                                                                                               \
+    int rlb200_syrf_##SUF##_dev(rlb200_ctx* ctx, int uplo, int64_t m, const T* A_dev, int64_t lda, int64_t k, T* Q_dev, T* work_dev,\
+                                uint32_t state[6], const rlb200_revd2_opts* opts) {                                                 \
+        CTX_OK(ctx); RLB_CHECK(bind(ctx)); RLB_REQUIRE(ctx, opts && state);                                                         \
+        return syrf_call<T>(ctx, uplo, m, A_dev, lda, k, Q_dev, work_dev, state, *opts);                                            \
+    }                                                                                                                               \
+    int rlb200_revd2_##SUF##_dev(rlb200_ctx* ctx, int uplo, int64_t m, const T* A_dev, int64_t lda, int64_t* k, int64_t k_cap, T tol,\
+                                 T* V_dev, T* eigvals_dev, uint32_t state[6], const rlb200_revd2_opts* opts, T* err_est) {          \
+        CTX_OK(ctx); RLB_CHECK(bind(ctx)); RLB_REQUIRE(ctx, opts && state && k);                                                    \
+        return revd2_call<T>(ctx, uplo, m, A_dev, lda, k, k_cap, tol, V_dev, eigvals_dev, state, *opts, err_est);                   \
+    }                                                                                                                               \
+    int rlb200_revd2_##SUF##_host(rlb200_ctx* ctx, int uplo, int64_t m, const T* A, int64_t lda, int64_t* k, int64_t k_cap, T tol,  \
+                                  T* V, T* eigvals, uint32_t state[6], const rlb200_revd2_opts* opts, T* err_est) {                 \
+        CTX_OK(ctx); RLB_CHECK(bind(ctx)); RLB_REQUIRE(ctx, opts && state && k);                                                    \
+        RLB_REQUIRE(ctx, m > 0 && lda >= m && A && V && eigvals && k_cap >= *k && *k > 0);                                          \
+        ArenaScope as(ctx);                                                                                                         \
+        T* dA = as.take<T>((size_t)m * m); if (!dA) return RLB200_ERR_ALLOC;                                                        \
+        T* dV = as.take<T>((size_t)m * k_cap); if (!dV) return RLB200_ERR_ALLOC;                                                    \
+        T* dE = as.take<T>((size_t)k_cap); if (!dE) return RLB200_ERR_ALLOC;                                                        \
+        RLB_CUDA_OK(ctx, cudaMemcpy2DAsync(dA, m * sizeof(T), A, lda * sizeof(T), m * sizeof(T), m, cudaMemcpyHostToDevice, ctx->stream)); \
+        int rc = revd2_call<T>(ctx, uplo, m, dA, m, k, k_cap, tol, dV, dE, state, *opts, err_est);                                  \
+        if (rc < 0) return rc;                                                                                                      \
+        RLB_CUDA_OK(ctx, cudaMemcpyAsync(V, dV, sizeof(T) * m * (*k), cudaMemcpyDeviceToHost, ctx->stream));                        \
+        RLB_CUDA_OK(ctx, cudaMemcpyAsync(eigvals, dE, sizeof(T) * (*k), cudaMemcpyDeviceToHost, ctx->stream));                      \
+        RLB_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));                                                                       \
+        return rc;                                                                                                                  \
+    }                                                                                                                               \
     int rlb200_bqrrp_##SUF##_dev(rlb200_ctx* ctx, int64_t m, int64_t n, T* A_dev, int64_t lda, T d_factor, int64_t block_size,      \
                                  int qrcp_wide, int qr_tall, T* tau_dev, int64_t* J_dev, int64_t* rank, uint32_t state[6]) {        \
         CTX_OK(ctx); RLB_CHECK(bind(ctx)); RLB_REQUIRE(ctx, state && rank);                                                         \

@@ -841,6 +841,220 @@ int cqrrt_call(Ctx* ctx, int64_t m, int64_t n, T* A, int64_t lda, T* R, int64_t 
     return 0;
 }
 
+// ------------------------------------------------------------------------------------------------
+// SYPS / SYRF / REVD2  (rl_syps.hh:21-143, rl_syrf.hh:21-118, rl_revd2.hh:20-246)
+// ------------------------------------------------------------------------------------------------
+// ExplicitSymLinOp reads one triangle of A only (the reference's tests poison the other one with NaN, test_revd2.cc:120-137): the
+// triangle is mirrored once into a full m x m scratch matrix and every  A * X  below is an ordinary tall product over it.
+template <typename T>
+__global__ void __launch_bounds__(256) sym_fill_kernel(int upper, int64_t m, const T* __restrict__ A, int64_t lda, T* __restrict__ F) {
+    __shared__ T tile[32][33];
+    const int64_t bi = blockIdx.x, bj = blockIdx.y;
+    if (bi > bj) return;                       // block pairs (bi <= bj): writes F(bi, bj) and its mirror F(bj, bi)
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    // source block holding the valid triangle: (bi, bj) for upper, (bj, bi) for lower
+    const int64_t sr = (upper ? bi : bj) * 32, sc = (upper ? bj : bi) * 32;
+    for (int c = ty; c < 32; c += 8) {
+        const int64_t i = sr + tx, j = sc + c;
+        T v = (T)0;
+        if (i < m && j < m) {
+            const bool valid = upper ? (i <= j) : (i >= j);
+            v = valid ? A[i + j * lda] : A[j + i * lda];        // diagonal blocks: take the mirrored entry from the valid side
+        }
+        tile[c][tx] = v;                       // tile[c][r] = S(sr + r, sc + c)
+    }
+    __syncthreads();
+    for (int c = ty; c < 32; c += 8) {
+        const int64_t i = sr + tx, j = sc + c;
+        if (i < m && j < m) F[i + j * m] = tile[c][tx];
+        const int64_t i2 = sc + tx, j2 = sr + c;               // mirrored block: F(sc + r, sr + c) = S(sr + c, sc + r)
+        if (bi != bj && i2 < m && j2 < m) F[i2 + j2 * m] = tile[tx][c];
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) col_scale_kernel(int64_t m, int64_t k, const T* __restrict__ V, const T* __restrict__ e, T* __restrict__ out) {
+    const int64_t total = m * k;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) out[i] = V[i] * e[i / m];
+}
+// y <- a * x + b * y  (b == 0: y is not read)
+template <typename T>
+__global__ void __launch_bounds__(256) vec_axpby_kernel(int64_t n, T a, const T* __restrict__ x, T b, T* __restrict__ y) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) y[i] = (b == (T)0) ? a * x[i] : a * x[i] + b * y[i];
+}
+template <typename T>
+static int vec_axpby(Ctx* ctx, int64_t n, T a, const T* x, T b, T* y) {
+    if (n == 0) return 0;
+    LaunchScope ls(ctx, RLB200_TIMER_SMALL);
+    vec_axpby_kernel<T><<<(unsigned)std::min<int64_t>((n + 255) / 256, (int64_t)ctx->num_sms * 8), 256, 0, ctx->stream>>>(n, a, x, b, y);
+    RLB_CUDA_OK(ctx, cudaGetLastError());
+    return 0;
+}
+
+template <typename T>
+static int sym_full(Ctx* ctx, int uplo, int64_t m, const T* A, int64_t lda, T* F) {
+    const int64_t nb = (m + 31) / 32;
+    RLB_REQUIRE(ctx, nb < 65536);
+    LaunchScope ls(ctx, RLB200_TIMER_SMALL);
+    sym_fill_kernel<T><<<dim3((unsigned)nb, (unsigned)nb), 256, 0, ctx->stream>>>(uplo == RLB200_UPLO_UPPER ? 1 : 0, m, A, lda, F);
+    RLB_CUDA_OK(ctx, cudaGetLastError());
+    return 0;
+}
+
+// SYPS::call on the mirrored matrix F (rl_syps.hh:58-137).  skop (m x k): in/out as the reference's skop_buff, work (m x k): scratch.
+template <typename T>
+static int syps_full(Ctx* ctx, int64_t m, const T* F, int64_t k, int64_t p, int64_t q, T* skop, T* work, uint32_t state[6]) {
+    RLB_REQUIRE(ctx, p >= 0 && (p == 0 || q >= 1));
+    // skop <- fill_dense(DenseDist(m, k)) (:74-75): the natural-layout buffer, read as m x k column-major whatever its shape
+    RLB_CHECK(fill_dense_unpacked<T>(ctx, m, k, RLB200_FAMILY_GAUSSIAN, RLB200_AXIS_LONG, RLB200_LAYOUT_NATURAL, m, k, 0, 0, skop, state));
+    RLB_CUDA_OK(ctx, cudaMemsetAsync(work, 0, sizeof(T) * m * k, ctx->stream));                       // :80
+    T* out = work; T* in = skop;
+    for (int64_t p_done = 0; p_done < p;) {
+        RLB_CHECK(tall_nn<T>(ctx, m, k, m, 1.0, F, m, in, m, 0.0, out, m));                           // :86
+        ++p_done;
+        if (p_done % q == 0) RLB_CHECK(hqrq<T>(ctx, m, k, out));                                      // geqrf + ungqr (:88-93)
+        out = (p_done % 2 == 1) ? skop : work;                                                       // :95-96
+        in = (p_done % 2 == 1) ? work : skop;
+    }
+    if (p % 2 == 1) RLB_CUDA_OK(ctx, cudaMemcpyAsync(skop, work, sizeof(T) * m * k, cudaMemcpyDeviceToDevice, ctx->stream));   // :99-100
+    return 0;
+}
+
+// SYRF::call (rl_syrf.hh:67-112): Q = orth(A * syps(A)).  Returns 0, or 2 when the orthogonaliser fails (the reference throws).
+template <typename T>
+static int syrf_full(Ctx* ctx, int64_t m, const T* F, int64_t k, T* Q, T* work, uint32_t state[6], const rlb200_revd2_opts& o) {
+    RLB_CHECK(syps_full<T>(ctx, m, F, k, o.syps_passes, o.syps_passes_per_stab, work, Q, state));   // the sketch lands in `work`, Q is its scratch (:83)
+    RLB_CHECK(tall_nn<T>(ctx, m, k, m, 1.0, F, m, work, m, 0.0, Q, m));                               // :86
+    int rc = stab_call<T>(ctx, o.orth, m, k, Q, false, false, nullptr);                               // :94
+    if (rc < 0) return rc;
+    if (rc) { ctx->err = "SYRF: orthogonalization failed"; return 2; }
+    return 0;
+}
+
+template <typename T>
+int syps_call(Ctx* ctx, int uplo, int64_t m, const T* A, int64_t lda, int64_t k, int64_t passes, int64_t passes_per_stab, T* skop, T* work,
+              uint32_t state[6]) {
+    RLB_REQUIRE(ctx, m > 0 && k > 0 && lda >= m && A && skop && work && ctx->m_global < 0);
+    RLB_REQUIRE(ctx, uplo == RLB200_UPLO_UPPER || uplo == RLB200_UPLO_LOWER);
+    ArenaScope as(ctx);
+    T* F = as.take<T>((size_t)m * m); RLB_ALLOC(ctx, F);
+    RLB_CHECK(sym_full<T>(ctx, uplo, m, A, lda, F));
+    OzConstScope a_const(ctx, F);
+    return syps_full<T>(ctx, m, F, k, passes, passes_per_stab, skop, work, state);
+}
+
+template <typename T>
+int syrf_call(Ctx* ctx, int uplo, int64_t m, const T* A, int64_t lda, int64_t k, T* Q, T* work, uint32_t state[6], const rlb200_revd2_opts& o) {
+    RLB_REQUIRE(ctx, m > 0 && k > 0 && lda >= m && A && Q && work && ctx->m_global < 0);
+    RLB_REQUIRE(ctx, uplo == RLB200_UPLO_UPPER || uplo == RLB200_UPLO_LOWER);
+    ArenaScope as(ctx);
+    T* F = as.take<T>((size_t)m * m); RLB_ALLOC(ctx, F);
+    RLB_CHECK(sym_full<T>(ctx, uplo, m, A, lda, F));
+    OzConstScope a_const(ctx, F);
+    return syrf_full<T>(ctx, m, F, k, Q, work, state, o);
+}
+
+// power_error_est (rl_revd2.hh:20-71): p steps of the power method on  A - V diag(e) V^T  from the vector in vb[0:m]; vb: 4 m scratch
+// entries, Mat: m x k scratch.  The last Rayleigh quotient is returned.
+template <typename T>
+static int revd2_error_est(Ctx* ctx, int64_t m, const T* F, int64_t k, int p, T* vb, const T* V, T* Mat, const T* e_dev, T* err_out) {
+    T err = 0;
+    T* g = vb; T* t1 = vb + m; T* t2 = vb + 2 * m; T* t3 = vb + 3 * m;
+    ArenaScope as(ctx);
+    T* dotv = as.take<T>(1); RLB_ALLOC(ctx, dotv);
+    for (int i = 0; i < p; ++i) {
+        double gn = 0;
+        RLB_CHECK(fro_norm<T>(ctx, g, m, 1, m, false, &gn));
+        RLB_CHECK(vec_axpby<T>(ctx, m, (T)(1.0 / gn), g, (T)0, g));                                   // g / ||g||  (:36)
+        RLB_CHECK(gemm_tn<T>(ctx, m, k, 1, 1.0, V, m, g, m, 0.0, t1, m, 0));                           // V^T g  (:40)
+        {
+            LaunchScope ls(ctx, RLB200_TIMER_SMALL);
+            col_scale_kernel<T><<<(unsigned)std::min<int64_t>((m * k + 255) / 256, (int64_t)ctx->num_sms * 8), 256, 0, ctx->stream>>>(m, k, V, e_dev, Mat);   // :44-48
+            RLB_CUDA_OK(ctx, cudaGetLastError());
+        }
+        RLB_CHECK(gemm_nn<T>(ctx, m, 1, k, 1.0, Mat, m, t1, m, 0.0, t2, m));                           // V diag(e) V^T g  (:52)
+        RLB_CHECK(gemm_nn<T>(ctx, m, 1, m, 1.0, F, m, g, m, 0.0, t3, m));                              // A g  (:55)
+        RLB_CHECK(vec_axpby<T>(ctx, m, (T)-1, t2, (T)1, t3));                                          // w  (:60)
+        RLB_CHECK(gemm_tn<T>(ctx, m, 1, 1, 1.0, g, m, t3, m, 0.0, dotv, 1, 0));                        // g . w  (:62)
+        RLB_CHECK(read_scalar<T>(ctx, dotv, &err));
+        RLB_CUDA_OK(ctx, cudaMemcpyAsync(g, t3, sizeof(T) * m, cudaMemcpyDeviceToDevice, ctx->stream));   // :64
+    }
+    *err_out = err;
+    return 0;
+}
+
+// REVD2::call (rl_revd2.hh:120-246).  V (m x k_cap) and eigvals (k_cap) are the caller's device buffers; *k_io grows as in the reference
+// (k <- 2k, capped at m) until the error estimate passes.  Returns 0; 1 = the Cholesky factorization failed and 2 = the orthogonaliser
+// failed (the reference throws std::runtime_error for both); 3 = the next k would exceed k_cap (the outputs hold the last, unconverged
+// iterate and *k_io its size; the reference would have grown its vectors).  *err_out: the last error estimate.
+template <typename T>
+int revd2_call(Ctx* ctx, int uplo, int64_t m, const T* A, int64_t lda, int64_t* k_io, int64_t k_cap, T tol, T* V, T* eigvals, uint32_t state[6],
+               const rlb200_revd2_opts& o, T* err_out) {
+    RLB_REQUIRE(ctx, m >= 0 && k_io && *k_io > 0 && tol >= (T)0 && !(A == nullptr && m > 0));          // :131-134
+    RLB_REQUIRE(ctx, uplo == RLB200_UPLO_UPPER || uplo == RLB200_UPLO_LOWER);
+    RLB_REQUIRE(ctx, lda >= m && V && eigvals && k_cap >= *k_io && ctx->m_global < 0 && o.error_est_p >= 0);
+    RLB_REQUIRE(ctx, m > 0 && *k_io <= m);
+    int64_t k = *k_io;
+    uint32_t est_state[6];
+    std::memcpy(est_state, state, sizeof est_state);                                                   // :152-153: same counter, key + 1
+    if (++est_state[4] == 0) ++est_state[5];
+    ArenaScope as(ctx);
+    T* F = as.take<T>((size_t)m * m); RLB_ALLOC(ctx, F);
+    RLB_CHECK(sym_full<T>(ctx, uplo, m, A, lda, F));
+    OzConstScope a_const(ctx, F);
+    const T eps = std::numeric_limits<T>::epsilon();
+    T err = 0;
+    int code = 0;
+    while (true) {
+        ArenaScope it(ctx);
+        const int64_t ko = std::max<int64_t>(k, 4);
+        T* Omega = it.take<T>((size_t)m * ko); RLB_ALLOC(ctx, Omega);
+        T* Y = it.take<T>((size_t)m * k); RLB_ALLOC(ctx, Y);
+        T* work = it.take<T>((size_t)m * k); RLB_ALLOC(ctx, work);
+        T* R = it.take<T>((size_t)k * k); RLB_ALLOC(ctx, R);
+        T* S = it.take<T>((size_t)k); RLB_ALLOC(ctx, S);
+        T* W = it.take<T>((size_t)k * k); RLB_ALLOC(ctx, W);
+        int rc = syrf_full<T>(ctx, m, F, k, Omega, work, state, o);                                    // :166
+        if (rc) { code = rc; break; }
+        RLB_CHECK(gemm_nn<T>(ctx, m, k, m, 1.0, F, m, Omega, m, 0.0, Y, m));                           // Y = A Omega on the fp64 pipe (:169): nu below is eps-sized
+        double ynorm = 0;
+        RLB_CHECK(fro_norm<T>(ctx, Y, m, k, m, false, &ynorm));
+        const T nu = eps * (T)ynorm;                                                                   // :171
+        // R = chol(Omega^T Y + nu Omega^T Omega)  (:177-186)
+        RLB_CUDA_OK(ctx, cudaMemsetAsync(R, 0, sizeof(T) * k * k, ctx->stream));
+        RLB_CHECK(gemm_tn<T>(ctx, m, k, k, (double)nu, Omega, m, Omega, m, 0.0, R, k, 0));
+        RLB_CHECK(gemm_tn<T>(ctx, m, k, k, 1.0, Omega, m, Y, m, 1.0, R, k, 0));
+        int info = 0;
+        RLB_CHECK(potrf_blocked<T>(ctx, k, R, k, &info));
+        if (info != 0) { ctx->err = "REVD2: Cholesky decomposition failed"; code = 1; break; }
+        RLB_CHECK(trsm_right_upper<T>(ctx, m, k, R, k, Y, m));                                         // B = Y R^-1  (:190)
+        {   // [V, S, ~] = svd(B)  (:195)
+            void* ws = arena_push(ctx, svd_ws_bytes(m, k, sizeof(T))); RLB_ALLOC(ctx, ws);
+            RLB_CHECK(svd_tall<T>(ctx, m, k, Y, m, S, W, ws, nullptr));
+        }
+        RLB_CUDA_OK(ctx, cudaMemcpyAsync(V, Y, sizeof(T) * m * k, cudaMemcpyDeviceToDevice, ctx->stream));
+        std::vector<T> s(k), ev(k);
+        RLB_CUDA_OK(ctx, cudaMemcpyAsync(s.data(), S, sizeof(T) * k, cudaMemcpyDeviceToHost, ctx->stream));
+        RLB_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+        int64_t r = 0;
+        for (int64_t i = 0; i < k; ++i) { ev[i] = s[i] * s[i]; if (ev[i] > nu) ++r; }                  // :198-207
+        for (int64_t i = 0; i < r; ++i) if (!(ev[i] - nu < 0)) ev[i] -= nu;                            // :211-212
+        RLB_CUDA_OK(ctx, cudaMemcpyAsync(eigvals, ev.data(), sizeof(T) * k, cudaMemcpyHostToDevice, ctx->stream));
+        if (r < k) RLB_CUDA_OK(ctx, cudaMemsetAsync(V + m * r, 0, sizeof(T) * m * (k - r), ctx->stream));   // :214
+        // error estimate from a fresh Gaussian vector (:219-223)
+        RLB_CHECK(fill_dense_unpacked<T>(ctx, m, 1, RLB200_FAMILY_GAUSSIAN, RLB200_AXIS_LONG, RLB200_LAYOUT_NATURAL, m, 1, 0, 0, Omega, est_state));
+        RLB_CHECK(revd2_error_est<T>(ctx, m, F, k, o.error_est_p, Omega, V, Y, eigvals, &err));
+        RLB_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));                                          // ev is host memory of this iteration
+        if (err <= 5 * std::max(tol, nu) || k == m) break;                                             // :225-231
+        const int64_t k_next = (2 * k > m) ? m : 2 * k;
+        if (k_next > k_cap) { ctx->err = "REVD2: the next rank estimate exceeds the capacity of V / eigvals"; code = 3; break; }
+        k = k_next;
+    }
+    *k_io = k;
+    if (err_out) *err_out = err;
+    return code;
+}
+
 #define INST(T)                                                                                                             \
     template int cqrrt_call<T>(Ctx*, int64_t, int64_t, T*, int64_t, T*, int64_t, T, int64_t, int, int, uint32_t*);          \
     template int stab_call<T>(Ctx*, int, int64_t, int64_t, T*, bool, bool, int*);                                           \
@@ -848,7 +1062,10 @@ int cqrrt_call(Ctx* ctx, int64_t m, int64_t n, T* A, int64_t lda, T* R, int64_t 
     template int rf_call<T>(Ctx*, int64_t, int64_t, const T*, int64_t, T*, uint32_t*, const rlb200_stack_opts&);             \
     template int qb_call<T>(Ctx*, int64_t, int64_t, T*, int64_t*, int64_t, T, T*, T*, T*, uint32_t*, const rlb200_stack_opts&); \
     template int rsvd_call<T>(Ctx*, int64_t, int64_t, T*, int64_t*, T, T*, T*, T*, T*, uint32_t*, const rlb200_stack_opts&, int*); \
-    template int cqrrpt_call<T>(Ctx*, int64_t, int64_t, T*, int64_t, T*, int64_t, int64_t*, T, T, int64_t, int64_t*, uint32_t*);
+    template int cqrrpt_call<T>(Ctx*, int64_t, int64_t, T*, int64_t, T*, int64_t, int64_t*, T, T, int64_t, int64_t*, uint32_t*); \
+    template int syps_call<T>(Ctx*, int, int64_t, const T*, int64_t, int64_t, int64_t, int64_t, T*, T*, uint32_t*);          \
+    template int syrf_call<T>(Ctx*, int, int64_t, const T*, int64_t, int64_t, T*, T*, uint32_t*, const rlb200_revd2_opts&);  \
+    template int revd2_call<T>(Ctx*, int, int64_t, const T*, int64_t, int64_t*, int64_t, T, T*, T*, uint32_t*, const rlb200_revd2_opts&, T*);
 INST(double)
 INST(float)
 

@@ -152,6 +152,16 @@ template <typename T>
 int cqrrt_call(Ctx* ctx, int64_t m, int64_t n, T* A, int64_t lda, T* R, int64_t ldr, T d_factor, int64_t nnz, int orthogonalization, int compute_Q,
                uint32_t state[6]);
 
+// SYPS / SYRF / REVD2 (rl_syps.hh, rl_syrf.hh, rl_revd2.hh) on an explicit symmetric matrix of which the `uplo` triangle is read.
+template <typename T>
+int syps_call(Ctx* ctx, int uplo, int64_t m, const T* A, int64_t lda, int64_t k, int64_t passes, int64_t passes_per_stab, T* skop, T* work,
+              uint32_t state[6]);
+template <typename T>
+int syrf_call(Ctx* ctx, int uplo, int64_t m, const T* A, int64_t lda, int64_t k, T* Q, T* work, uint32_t state[6], const rlb200_revd2_opts& o);
+template <typename T>
+int revd2_call(Ctx* ctx, int uplo, int64_t m, const T* A, int64_t lda, int64_t* k_io, int64_t k_cap, T tol, T* V, T* eigvals, uint32_t state[6],
+               const rlb200_revd2_opts& o, T* err_out);
+
 // BQRRP::call (rl_bqrrp.hh:154-665).  qrcp_wide: 0 luqr (default), 1 geqp3; qr_tall: 0 geqrf (default), 1 cholqr (+orhr_col), 2 geqrt.
 // A_sk_ext != nullptr: BQRRP_GPU::call (rl_bqrrp_gpu.hh:152-942) - the d_ext x n sketch (leading dimension d_ext) is the caller's and is
 // overwritten; d_factor and state are not used.

@@ -168,6 +168,49 @@ def ref_cqrrt(lib, A, d_factor, seed6, nnz=2, orthogonalization=False, compute_Q
     return rc, Q, R, list(st)
 
 
+def ref_syps(lib, uplo, A, k, p, q, seed6):
+    """RandLAPACK::SYPS::call via the compiled reference -> (rc, skop m x k, state).  uplo: 0 upper / 1 lower."""
+    m = A.shape[0]
+    dt = A.dtype
+    F = np.asfortranarray(A)
+    sk = np.zeros((m, k), dtype=dt, order="F")
+    st = (u32 * 6)(*seed6)
+    f = getattr(lib, f"rlref_syps_{_suf(dt)}")
+    f.argtypes = [ctypes.c_int, i64, ctypes.c_void_p, i64, i64, i64, i64, ctypes.c_void_p, ctypes.POINTER(u32)]
+    rc = f(uplo, m, F.ctypes.data, m, k, p, q, sk.ctypes.data, st)
+    return rc, sk, list(st)
+
+
+def ref_syrf(lib, uplo, A, k, p, q, orth, seed6):
+    """RandLAPACK::SYRF::call via the compiled reference -> (rc, Q m x k, state)."""
+    m = A.shape[0]
+    dt = A.dtype
+    F = np.asfortranarray(A)
+    Q = np.zeros((m, k), dtype=dt, order="F")
+    st = (u32 * 6)(*seed6)
+    f = getattr(lib, f"rlref_syrf_{_suf(dt)}")
+    f.argtypes = [ctypes.c_int, i64, ctypes.c_void_p, i64, i64, i64, ctypes.c_int, ctypes.c_void_p, ctypes.POINTER(u32)]
+    rc = f(uplo, m, F.ctypes.data, k, p, q, orth, Q.ctypes.data, st)
+    return rc, Q, list(st)
+
+
+def ref_revd2(lib, uplo, A, k, tol, p, q, orth, error_est_p, seed6, k_cap=None):
+    """RandLAPACK::REVD2::call via the compiled reference -> (rc, k, V m x k, eigvals k, state)."""
+    m = A.shape[0]
+    dt = A.dtype
+    k_cap = m if k_cap is None else k_cap
+    F = np.asfortranarray(A)
+    V = np.zeros((m, k_cap), dtype=dt, order="F")
+    ev = np.zeros(k_cap, dtype=dt)
+    kk = i64(k)
+    st = (u32 * 6)(*seed6)
+    f = getattr(lib, f"rlref_revd2_{_suf(dt)}")
+    f.argtypes = [ctypes.c_int, i64, ctypes.c_void_p, ctypes.POINTER(i64), i64, _ft(dt), i64, i64, ctypes.c_int, ctypes.c_int,
+                  ctypes.c_void_p, ctypes.c_void_p, ctypes.POINTER(u32)]
+    rc = f(uplo, m, F.ctypes.data, ctypes.byref(kk), k_cap, tol, p, q, orth, error_est_p, V.ctypes.data, ev.ctypes.data, st)
+    return rc, kk.value, V[:, :kk.value].copy(order="F"), ev[:kk.value].copy(), list(st)
+
+
 def ref_bqrrp(lib, A, d_factor, b_sz, seed6, qrcp_wide=0, qr_tall=0):
     """RandLAPACK::BQRRP::call via the compiled reference -> (rc, rank, A_out [GEQP3 format], tau, J, state)."""
     m, n = A.shape
