@@ -14,6 +14,8 @@
 //   RandLAPACK::CQRRTalg / CQRRT      drivers/rl_cqrrt.hh:20-297           rlb200::CQRRT<T>
 //   RandLAPACK::BQRRPalg / BQRRP      drivers/rl_bqrrp.hh:19-665           rlb200::BQRRP<T>
 //   RandLAPACK::BQRRP_GPU_alg / BQRRP_GPU  drivers/rl_bqrrp_gpu.hh:27-942   rlb200::BQRRP_GPU<T>   (device pointers, sketch as input)
+//   RandLAPACK::linops::DenseLinOp / ExplicitSymLinOp  linops/rl_dense_linop.hh:36, linops/rl_sym_linops.hh   rlb200::DenseLinOp / ExplicitSymLinOp<T>  (matrix resident on the device)
+//   RandLAPACK::SYPS / SYRF / REVD2   comps/rl_syps.hh, comps/rl_syrf.hh, drivers/rl_revd2.hh   rlb200::SYPS / SYRF / REVD2<T>  (explicit symmetric A)
 //
 // Two modes:
 //  * default: self-contained (no reference headers needed); `rlb200::RNGState` stands in for RandBLAS::RNGState.
@@ -25,6 +27,7 @@
 // QB and RSVD).  A B200 RS/RF/QB needs B200 stabilisers (it asks them for their kind); mixing in a CPU stabiliser is
 // rejected with std::invalid_argument rather than silently falling back to the CPU.
 #pragma once
+#include <cmath>
 #include <cstdint>
 #include <cstdlib>
 #include <cstring>
@@ -109,12 +112,16 @@ template <> struct abi<double> {
     static constexpr auto qb = rlb200_qb_f64_dev; static constexpr auto rsvd_host = rlb200_rsvd_f64_host;
     static constexpr auto cqrrpt_host = rlb200_cqrrpt_f64_host; static constexpr auto bqrrp_host = rlb200_bqrrp_f64_host;
     static constexpr auto bqrrp_dev_sk = rlb200_bqrrp_f64_dev_sk; static constexpr auto cqrrt_host = rlb200_cqrrt_f64_host;
+    static constexpr auto syps = rlb200_syps_f64_dev; static constexpr auto syrf = rlb200_syrf_f64_dev; static constexpr auto revd2_host = rlb200_revd2_f64_host;
+    static constexpr auto gemm = rlb200_gemm_f64_dev;
 };
 template <> struct abi<float> {
     static constexpr auto stab = rlb200_stab_f32_dev; static constexpr auto rs = rlb200_rs_f32_dev; static constexpr auto rf = rlb200_rf_f32_dev;
     static constexpr auto qb = rlb200_qb_f32_dev; static constexpr auto rsvd_host = rlb200_rsvd_f32_host;
     static constexpr auto cqrrpt_host = rlb200_cqrrpt_f32_host; static constexpr auto bqrrp_host = rlb200_bqrrp_f32_host;
     static constexpr auto bqrrp_dev_sk = rlb200_bqrrp_f32_dev_sk; static constexpr auto cqrrt_host = rlb200_cqrrt_f32_host;
+    static constexpr auto syps = rlb200_syps_f32_dev; static constexpr auto syrf = rlb200_syrf_f32_dev; static constexpr auto revd2_host = rlb200_revd2_f32_host;
+    static constexpr auto gemm = rlb200_gemm_f32_dev;
 };
 
 // device buffer staged from / to a host pointer
@@ -474,6 +481,195 @@ public:
     GPUSubroutine::QRTall qr_tall;
 private:
     Context* ctx_;
+};
+
+// ---------------------------------------------------------------------------------------------------------------------
+// SYPS / SYRF / REVD2 (rl_syps.hh:21-143, rl_syrf.hh:21-118, rl_revd2.hh:75-246) for an explicit symmetric matrix: the reference's
+// constructors, public fields and the `call(uplo, m, A, ...)` overloads with HOST pointers (the SymmetricLinearOperator overloads are
+// not offered: the device path needs the matrix itself).  Failures the reference reports by throwing std::runtime_error throw here too.
+// ---------------------------------------------------------------------------------------------------------------------
+#ifndef RLB200_WITH_RANDLAPACK
+enum class Uplo : char { Upper = 'U', Lower = 'L' };
+using uplo_t = Uplo;
+inline int uplo_code(Uplo u) { return u == Uplo::Upper ? RLB200_UPLO_UPPER : RLB200_UPLO_LOWER; }
+#else
+using uplo_t = blas::Uplo;
+inline int uplo_code(blas::Uplo u) { return u == blas::Uplo::Upper ? RLB200_UPLO_UPPER : RLB200_UPLO_LOWER; }
+#endif
+
+template <typename T>
+class SYPS {
+public:
+    using scalar_t = T;
+    SYPS(int64_t p, int64_t q, bool verb, bool cond) : SYPS(default_context(), p, q, verb, cond) {}
+    SYPS(Context& c, int64_t p, int64_t q, bool verb, bool cond) : passes_over_data(p), passes_per_stab(q), verbose(verb), cond_check(cond), ctx_(&c) {}
+    // skop_buff (m x k; allocated with new[] when null, as the reference does) <- the power sketch; work_buff is not needed (rl_syps.hh:47-57)
+    int call(uplo_t uplo, int64_t m, const T* A, int64_t lda, int64_t k, state_t& state, T*& skop_buff, T* /*work_buff*/) {
+        if (!skop_buff) skop_buff = new T[m * k];
+        std::vector<T> Ac((size_t)m * m);
+        for (int64_t j = 0; j < m; ++j) std::memcpy(Ac.data() + j * m, A + j * lda, sizeof(T) * m);
+        detail::DevBuf<T> dA(*ctx_, m * m, Ac.data()), dS(*ctx_, m * k), dW(*ctx_, m * k);
+        uint32_t w[6]; state_to_words(state, w);
+        int rc = ctx_->check(detail::abi<T>::syps(ctx_->get(), uplo_code(uplo), m, dA.ptr(), m, k, passes_over_data, passes_per_stab, dS.ptr(), dW.ptr(), w));
+        words_to_state(w, state);
+        dS.to_host(skop_buff, m * k);
+        return rc;
+    }
+    Context& context() const { return *ctx_; }
+    int64_t passes_over_data, passes_per_stab;
+    bool verbose, cond_check;
+    std::vector<T> cond_nums;
+private:
+    Context* ctx_;
+};
+
+template <typename T>
+class SYRF {
+public:
+    SYRF(SYPS<T>& syps_obj, StabBase<T>& orth_obj, bool verb = false, bool cond = false) : syps(syps_obj), orth(orth_obj), verbose(verb), cond_check(cond) {}
+    // Q (resized to m x k) <- orth(A * syps(A))  (rl_syrf.hh:43-56)
+    int call(uplo_t uplo, int64_t m, const T* A, int64_t k, std::vector<T>& Q, state_t& state, T* /*work_buff*/) {
+        Context& c = syps.context();
+        rlb200_revd2_opts o = opts(0);
+        if ((int64_t)Q.size() < m * k) Q.resize(m * k);
+        detail::DevBuf<T> dA(c, m * m, A), dQ(c, m * k), dW(c, m * k);
+        uint32_t w[6]; state_to_words(state, w);
+        int rc = c.check(detail::abi<T>::syrf(c.get(), uplo_code(uplo), m, dA.ptr(), m, k, dQ.ptr(), dW.ptr(), w, &o));
+        words_to_state(w, state);
+        if (rc == 2) throw std::runtime_error("Orthogonalization failed.");
+        dQ.to_host(Q.data(), m * k);
+        return rc;
+    }
+    rlb200_revd2_opts opts(int error_est_p) const {
+        rlb200_revd2_opts o;
+        o.syps_passes = syps.passes_over_data; o.syps_passes_per_stab = syps.passes_per_stab;
+        o.orth = require_device_stab<T>(orth, "rlb200::SYRF").kind(); o.error_est_p = error_est_p;
+        return o;
+    }
+    SYPS<T>& syps;
+    StabBase<T>& orth;
+    bool verbose, cond_check;
+    std::vector<T> cond_nums;
+};
+
+template <typename T>
+class REVD2 {
+public:
+    REVD2(SYRF<T>& syrf_obj, int error_est_power_iters, bool verb = false) : syrf(syrf_obj), error_est_p(error_est_power_iters), verbose(verb) {}
+    // V (resized to m x k) and eigvals (k) for the final k (rl_revd2.hh:120-139)
+    int call(uplo_t uplo, int64_t m, const T* A, int64_t& k, T tol, std::vector<T>& V, std::vector<T>& eigvals, state_t& state) {
+        Context& c = syrf.syps.context();
+        rlb200_revd2_opts o = syrf.opts(error_est_p);
+        if (m > 0) { V.resize((size_t)m * m); eigvals.resize((size_t)m); }       // k may grow up to m
+        uint32_t w[6]; state_to_words(state, w);
+        T err = 0;
+        int rc = c.check(detail::abi<T>::revd2_host(c.get(), uplo_code(uplo), m, A, m, &k, m, tol, V.data(), eigvals.data(), w, &o, &err));
+        words_to_state(w, state);
+        if (rc == 1) throw std::runtime_error("Cholesky decomposition failed.");
+        if (rc == 2) throw std::runtime_error("Orthogonalization failed.");
+        V.resize((size_t)m * k); eigvals.resize((size_t)k);
+        last_error_estimate = err;
+        return rc;
+    }
+    SYRF<T>& syrf;
+    int error_est_p;
+    bool verbose;
+    T last_error_estimate = 0;
+};
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Linear operators with the matrix RESIDENT ON THE DEVICE.  They satisfy the reference's LinearOperator /
+// SymmetricLinearOperator concepts (linops/rl_concepts.hh:30-57: n_rows / n_cols / dim members and the GEMM- / SYMM-like call with HOST
+// B and C), so the reference's operator-templated algorithms (SYPS / SYRF / REVD2 `call(SLO&, ...)`, rl_revd2.hh:142-150) run their
+// products on the B200 while the matrix crosses PCIe once, at construction.  ColMajor only; op(A), op(B) not both transposed.
+// ---------------------------------------------------------------------------------------------------------------------
+#ifndef RLB200_WITH_RANDLAPACK
+enum class Layout : char { ColMajor = 'C', RowMajor = 'R' };
+enum class Op : char { NoTrans = 'N', Trans = 'T' };
+using layout_t = Layout; using op_t = Op;
+inline bool is_colmajor(Layout l) { return l == Layout::ColMajor; }
+inline int op_code(Op o) { return o == Op::NoTrans ? 0 : 1; }
+#else
+using layout_t = blas::Layout; using op_t = blas::Op;
+inline bool is_colmajor(blas::Layout l) { return l == blas::Layout::ColMajor; }
+inline int op_code(blas::Op o) { return o == blas::Op::NoTrans ? 0 : 1; }
+#endif
+
+template <typename T>
+struct DenseLinOp {
+    using scalar_t = T;
+    const int64_t n_rows;
+    const int64_t n_cols;
+    // A_host: n_rows x n_cols column-major (lda >= n_rows, rl_dense_linop.hh:52-58); copied to the device here
+    DenseLinOp(int64_t rows, int64_t cols, const T* A_host, int64_t lda) : DenseLinOp(default_context(), rows, cols, A_host, lda) {}
+    DenseLinOp(Context& c, int64_t rows, int64_t cols, const T* A_host, int64_t lda) : n_rows(rows), n_cols(cols), ctx_(&c) {
+        if (lda < rows) throw Error(RLB200_ERR_ARG, "DenseLinOp: lda must be >= n_rows under ColMajor");
+        std::vector<T> packed;
+        const T* src = A_host;
+        double ss = 0;
+        if (lda != rows) {
+            packed.resize((size_t)rows * cols);
+            for (int64_t j = 0; j < cols; ++j) std::memcpy(packed.data() + j * rows, A_host + j * lda, sizeof(T) * rows);
+            src = packed.data();
+        }
+        for (int64_t i = 0; i < rows * cols; ++i) ss += (double)src[i] * (double)src[i];
+        fro_ = (T)std::sqrt(ss);
+        dA_ = std::make_shared<detail::DevBuf<T>>(c, rows * cols, src);
+    }
+    T fro_nrm() { return fro_; }
+    // C := alpha * op(A) * op(B) + beta * C with HOST B and C (rl_dense_linop.hh:70-84)
+    void operator()(layout_t layout, op_t trans_A, op_t trans_B, int64_t m, int64_t n, int64_t k, T alpha, const T* B, int64_t ldb, T beta, T* C,
+                    int64_t ldc) {
+        if (!is_colmajor(layout)) throw Error(RLB200_ERR_UNSUPPORTED, "rlb200::DenseLinOp: ColMajor only");
+        const int ta = op_code(trans_A), tb = op_code(trans_B);
+        const int64_t rows_A = ta ? k : m, cols_A = ta ? m : k, rows_B = tb ? n : k, cols_B = tb ? k : n;
+        if (rows_A != n_rows || cols_A != n_cols) throw Error(RLB200_ERR_ARG, "DenseLinOp: (m, k, trans_A) do not match the operator");   // :103-106
+        if (ldb < rows_B || ldc < m) throw Error(RLB200_ERR_ARG, "DenseLinOp: ldb / ldc too small");                                        // :109-111
+        std::vector<T> Bp((size_t)rows_B * cols_B), Cp((size_t)m * n);
+        for (int64_t j = 0; j < cols_B; ++j) std::memcpy(Bp.data() + j * rows_B, B + j * ldb, sizeof(T) * rows_B);
+        if (beta != (T)0) for (int64_t j = 0; j < n; ++j) std::memcpy(Cp.data() + j * m, C + j * ldc, sizeof(T) * m);
+        detail::DevBuf<T> dB(*ctx_, rows_B * cols_B, Bp.data()), dC(*ctx_, m * n, beta != (T)0 ? Cp.data() : nullptr);
+        ctx_->check(detail::abi<T>::gemm(ctx_->get(), ta, tb, m, n, k, alpha, dA_->ptr(), n_rows, dB.ptr(), rows_B, beta, dC.ptr(), m));
+        dC.to_host(Cp.data(), m * n);
+        for (int64_t j = 0; j < n; ++j) std::memcpy(C + j * ldc, Cp.data() + j * m, sizeof(T) * m);
+    }
+    T* device_ptr() { return dA_->ptr(); }
+private:
+    Context* ctx_;
+    std::shared_ptr<detail::DevBuf<T>> dA_;
+    T fro_ = 0;
+};
+
+// ExplicitSymLinOp (linops/rl_sym_linops.hh:40-99): only the `uplo` triangle of A_host is read; the mirrored matrix lives on the device
+template <typename T>
+struct ExplicitSymLinOp {
+    using scalar_t = T;
+    const int64_t dim;
+    const int64_t n_rows;
+    const int64_t n_cols;
+    ExplicitSymLinOp(int64_t d, uplo_t uplo, const T* A_host, int64_t lda) : ExplicitSymLinOp(default_context(), d, uplo, A_host, lda) {}
+    ExplicitSymLinOp(Context& c, int64_t d, uplo_t uplo, const T* A_host, int64_t lda) : dim(d), n_rows(d), n_cols(d), op_(c, d, d, mirror(d, uplo, A_host, lda).data(), d) {}
+    // C := alpha * A * B + beta * C, B and C with n columns (rl_sym_linops.hh:76-99)
+    void operator()(layout_t layout, int64_t n, T alpha, const T* B, int64_t ldb, T beta, T* C, int64_t ldc) {
+#ifndef RLB200_WITH_RANDLAPACK
+        op_(layout, Op::NoTrans, Op::NoTrans, dim, n, dim, alpha, B, ldb, beta, C, ldc);
+#else
+        op_(layout, blas::Op::NoTrans, blas::Op::NoTrans, dim, n, dim, alpha, B, ldb, beta, C, ldc);
+#endif
+    }
+private:
+    static std::vector<T> mirror(int64_t d, uplo_t uplo, const T* A, int64_t lda) {
+        if (lda < d) throw Error(RLB200_ERR_ARG, "ExplicitSymLinOp: lda must be >= dim");
+        const bool upper = uplo_code(uplo) == RLB200_UPLO_UPPER;
+        std::vector<T> F((size_t)d * d);
+        for (int64_t j = 0; j < d; ++j)
+            for (int64_t i = 0; i < d; ++i) {
+                const bool valid = upper ? (i <= j) : (i >= j);
+                F[i + j * d] = valid ? A[i + j * lda] : A[j + i * lda];
+            }
+        return F;
+    }
+    DenseLinOp<T> op_;
 };
 
 }  // namespace rlb200

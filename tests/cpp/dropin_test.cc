@@ -18,6 +18,7 @@
 #include "RandLAPACK/drivers/rl_cqrrpt.hh"
 #include "RandLAPACK/drivers/rl_cqrrt.hh"
 #include "RandLAPACK/drivers/rl_bqrrp.hh"
+#include "RandLAPACK/drivers/rl_revd2.hh"
 #include "RandLAPACK/testing/rl_gen.hh"
 #define RLB200_WITH_RANDLAPACK
 #endif
@@ -105,6 +106,66 @@ int main() {
         int rcb = bq.call(m, n, Ab.data(), m, 1.0, tauq.data(), Jq.data(), st2);
         std::printf("standalone BQRRP: rc=%d rank=%lld\n", rcb, (long long)bq.rank);
         fails += !(rcb == 0 && bq.rank > 0 && bq.rank <= n);
+    }
+    {
+        // REVD2 on a planted PSD matrix of rank 12, only the lower triangle valid (test/drivers/test_revd2.cc: Uplo)
+        const int64_t me = 200, re = 12;
+        std::vector<double> G(me * re), Se(me * me, 0.0);
+        for (auto& v : G) v = nd(gen);
+        for (int64_t j = 0; j < me; ++j)
+            for (int64_t i = 0; i < me; ++i) {
+                double acc = 0;
+                for (int64_t l = 0; l < re; ++l) acc += G[i + l * me] * G[j + l * me] / ((1.0 + l) * (1.0 + l));
+                Se[i + j * me] = acc;
+            }
+        std::vector<double> Al = Se;
+        for (int64_t j = 0; j < me; ++j)
+            for (int64_t i = 0; i < j; ++i) Al[i + j * me] = std::nan("");
+        rlb200::SYPS<double> syps(3, 1, false, false);
+        rlb200::HQRQ<double> orth(false, false);
+        rlb200::SYRF<double> syrf(syps, orth, false, false);
+        rlb200::REVD2<double> revd2(syrf, 10, false);
+        rlb200::RNGState st(0);
+        std::vector<double> Ve, ee;
+        int64_t ke = 2;
+        int rce = revd2.call(rlb200::Uplo::Lower, me, Al.data(), ke, 1e-12, Ve, ee, st);
+        double num = 0;
+        for (int64_t j = 0; j < me; ++j)
+            for (int64_t i = 0; i < me; ++i) {
+                double d = Se[i + j * me];
+                for (int64_t l = 0; l < ke; ++l) d -= Ve[i + l * me] * ee[l] * Ve[j + l * me];
+                num += d * d;
+            }
+        std::printf("standalone REVD2: rc=%d k=%lld  ||A - V E V'||/||A|| = %.2e  err_est=%.2e\n", rce, (long long)ke, std::sqrt(num) / fro(Se),
+                    revd2.last_error_estimate);
+        fails += !(rce == 0 && ke == 16 && std::sqrt(num) / fro(Se) <= 1e-12 && (int64_t)Ve.size() == me * ke && (int64_t)ee.size() == ke);
+        // device-resident linear operators: C = 2 A^T B - C on the planted m x n matrix; symmetric operator from the NaN-poisoned triangle
+        rlb200::DenseLinOp<double> Aop(m, n, A.data(), m);
+        const int64_t nb = 7;
+        std::vector<double> Bm(m * nb), Cm(n * nb, 1.0), Cref(n * nb);
+        for (auto& v : Bm) v = nd(gen);
+        for (int64_t j = 0; j < nb; ++j)
+            for (int64_t i = 0; i < n; ++i) {
+                double acc = 0;
+                for (int64_t l = 0; l < m; ++l) acc += A[l + i * m] * Bm[l + j * m];
+                Cref[i + j * n] = 2.0 * acc - 1.0;
+            }
+        Aop(rlb200::Layout::ColMajor, rlb200::Op::Trans, rlb200::Op::NoTrans, n, nb, m, 2.0, Bm.data(), m, -1.0, Cm.data(), n);
+        double dl = 0, nl = 0;
+        for (int64_t i = 0; i < n * nb; ++i) { dl = std::max(dl, std::abs(Cm[i] - Cref[i])); nl = std::max(nl, std::abs(Cref[i])); }
+        rlb200::ExplicitSymLinOp<double> Sop(me, rlb200::Uplo::Lower, Al.data(), me);
+        std::vector<double> Xs(me * 3), Ys(me * 3, 0.0);
+        for (auto& v : Xs) v = nd(gen);
+        Sop(rlb200::Layout::ColMajor, 3, 1.0, Xs.data(), me, 0.0, Ys.data(), me);
+        double ds = 0, ns = 0;
+        for (int64_t j = 0; j < 3; ++j)
+            for (int64_t i = 0; i < me; ++i) {
+                double acc = 0;
+                for (int64_t l = 0; l < me; ++l) acc += Se[i + l * me] * Xs[l + j * me];
+                ds = std::max(ds, std::abs(acc - Ys[i + j * me])); ns = std::max(ns, std::abs(acc));
+            }
+        std::printf("standalone linops: DenseLinOp %.2e  ExplicitSymLinOp %.2e  fro %.6e / %.6e\n", dl / nl, ds / ns, (double)Aop.fro_nrm(), fro(A));
+        fails += !(dl <= 1e-12 * nl && ds <= 1e-12 * ns && std::abs(Aop.fro_nrm() - fro(A)) <= 1e-12 * fro(A));
     }
 #else
     using RNG = r123::Philox4x32;
@@ -199,6 +260,49 @@ int main() {
         std::printf("with-ref BQRRP: rank %lld / %lld  J equal %d  max|dA| %.2e  max|dtau| %.2e  state %d / %d\n", (long long)bq_ref.rank,
                     (long long)bq_dev.rank, (int)(J0 == J1), dA, dt, s0, s1);
         fails += !(bq_ref.rank == bq_dev.rank && J0 == J1 && dA <= 1e-9 && dt <= 1e-9 && s0 == s1);
+    }
+    {
+        // the reference's REVD2 on its own SYRF / SYPS / HQRQ objects vs rlb200::REVD2, same matrix (test_revd2.cc recipe), same state
+        int64_t me = 300, re = 60;
+        std::vector<double> B(me * me), Sm(me * me, 0.0);
+        auto st0 = RandBLAS::RNGState<RNG>();
+        RandLAPACK::gen::mat_gen_info<double> info(me, me, RandLAPACK::gen::polynomial);
+        info.cond_num = 1e4; info.rank = re; info.exponent = 2.0;
+        RandLAPACK::gen::mat_gen(info, B.data(), st0);
+        blas::syrk(blas::Layout::ColMajor, blas::Uplo::Lower, blas::Op::Trans, me, me, 1.0, B.data(), me, 0.0, Sm.data(), me);
+        for (int64_t j = 0; j < me; ++j)
+            for (int64_t i = 0; i < j; ++i) Sm[i + j * me] = Sm[j + i * me];
+        using SYPS_t = RandLAPACK::SYPS<double, RNG>;
+        using SYRF_t = RandLAPACK::SYRF<SYPS_t, RandLAPACK::HQRQ<double>>;
+        SYPS_t syps_r(3, 1, false, false);
+        RandLAPACK::HQRQ<double> orth_r(false, false);
+        SYRF_t syrf_r(syps_r, orth_r, false, false);
+        RandLAPACK::REVD2<SYRF_t> revd2_r(syrf_r, 10, false);
+        rlb200::SYPS<double> syps_d(3, 1, false, false);
+        rlb200::HQRQ<double> orth_d(false, false);
+        rlb200::SYRF<double> syrf_d(syps_d, orth_d, false, false);
+        rlb200::REVD2<double> revd2_d(syrf_d, 10, false);
+        std::vector<double> V0, e0, V1, e1;
+        int64_t k0 = 4, k1 = 4;
+        auto sa = RandBLAS::RNGState<RNG>(5), sb = RandBLAS::RNGState<RNG>(5);
+        revd2_r.call(blas::Uplo::Upper, me, Sm.data(), k0, 1e-13, V0, e0, sa);
+        revd2_d.call(blas::Uplo::Upper, me, Sm.data(), k1, 1e-13, V1, e1, sb);
+        double de = 0;
+        for (int64_t i = 0; i < std::min(k0, k1); ++i) de = std::max(de, std::abs(e0[i] - e1[i]));
+        std::printf("with-ref REVD2: k %lld / %lld  max|d eig| %.2e  state %u / %u\n", (long long)k0, (long long)k1, de, sa.counter.v[0], sb.counter.v[0]);
+        fails += !(k0 == k1 && de <= 1e-10 * e0[0] && sa.counter.v[0] == sb.counter.v[0]);
+        // the REFERENCE's REVD2 (operator overload, rl_revd2.hh:142-150) on a device-resident symmetric operator
+        static_assert(RandLAPACK::linops::SymmetricLinearOperator<rlb200::ExplicitSymLinOp<double>>);
+        static_assert(RandLAPACK::linops::LinearOperator<rlb200::DenseLinOp<double>>);
+        rlb200::ExplicitSymLinOp<double> Sop(me, blas::Uplo::Upper, Sm.data(), me);
+        std::vector<double> V2, e2;
+        int64_t k2 = 4;
+        auto sc = RandBLAS::RNGState<RNG>(5);
+        revd2_r.call(Sop, k2, 1e-13, V2, e2, sc);
+        double de2 = 0;
+        for (int64_t i = 0; i < std::min(k0, k2); ++i) de2 = std::max(de2, std::abs(e0[i] - e2[i]));
+        std::printf("with-ref REVD2 on rlb200::ExplicitSymLinOp: k %lld / %lld  max|d eig| %.2e\n", (long long)k0, (long long)k2, de2);
+        fails += !(k0 == k2 && de2 <= 1e-10 * e0[0] && sa.counter.v[0] == sc.counter.v[0]);
     }
 #endif
     std::printf(fails ? "DROPIN_FAIL\n" : "DROPIN_OK\n");
