@@ -632,8 +632,10 @@ struct DenseLinOp {
         ctx_->check(detail::abi<T>::gemm(ctx_->get(), ta, tb, m, n, k, alpha, dA_->ptr(), n_rows, dB.ptr(), rows_B, beta, dC.ptr(), m));
         dC.to_host(Cp.data(), m * n);
         for (int64_t j = 0; j < n; ++j) std::memcpy(C + j * ldc, Cp.data() + j * m, sizeof(T) * m);
+        ++n_products;
     }
     T* device_ptr() { return dA_->ptr(); }
+    int64_t n_products = 0;      // products executed on the device so far
 private:
     Context* ctx_;
     std::shared_ptr<detail::DevBuf<T>> dA_;
@@ -657,6 +659,7 @@ struct ExplicitSymLinOp {
         op_(layout, blas::Op::NoTrans, blas::Op::NoTrans, dim, n, dim, alpha, B, ldb, beta, C, ldc);
 #endif
     }
+    int64_t n_products() const { return op_.n_products; }
 private:
     static std::vector<T> mirror(int64_t d, uplo_t uplo, const T* A, int64_t lda) {
         if (lda < d) throw Error(RLB200_ERR_ARG, "ExplicitSymLinOp: lda must be >= dim");

@@ -301,8 +301,9 @@ int main() {
         revd2_r.call(Sop, k2, 1e-13, V2, e2, sc);
         double de2 = 0;
         for (int64_t i = 0; i < std::min(k0, k2); ++i) de2 = std::max(de2, std::abs(e0[i] - e2[i]));
-        std::printf("with-ref REVD2 on rlb200::ExplicitSymLinOp: k %lld / %lld  max|d eig| %.2e\n", (long long)k0, (long long)k2, de2);
-        fails += !(k0 == k2 && de2 <= 1e-10 * e0[0] && sa.counter.v[0] == sc.counter.v[0]);
+        std::printf("with-ref REVD2 on rlb200::ExplicitSymLinOp: k %lld / %lld  max|d eig| %.2e  device products %lld  e[3] %.17g / %.17g\n", (long long)k0,
+                    (long long)k2, de2, (long long)Sop.n_products(), e0[3], e2[3]);
+        fails += !(k0 == k2 && de2 <= 1e-10 * e0[0] && sa.counter.v[0] == sc.counter.v[0] && Sop.n_products() > 0);
     }
 #endif
     std::printf(fails ? "DROPIN_FAIL\n" : "DROPIN_OK\n");

@@ -20,10 +20,11 @@ def _run(path):
 
 def test_standalone_objects():
     exe = os.path.join(ROOT, "tests", "cpp", "dropin_standalone")
-    if not os.path.exists(exe):
-        subprocess.check_call(["g++", "-O2", "-std=c++17", "-I" + os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "cpp", "dropin_test.cc"),
+    deps = [os.path.join(ROOT, "tests", "cpp", "dropin_test.cc"), os.path.join(ROOT, "include", "RandLAPACK_B200.hh"), os.path.join(ROOT, "include", "rlb200.h")]
+    if not os.path.exists(exe) or os.path.getmtime(exe) < max(os.path.getmtime(d) for d in deps):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-I" + os.path.join(ROOT, "include"), deps[0],
                                "-o", exe, "-L" + os.path.join(ROOT, "randlapack_b200"), "-lrlb200",
-                               "-Wl,-rpath," + os.path.join(ROOT, "randlapack_b200")])
+                               "-Wl,-rpath,$ORIGIN/../../randlapack_b200"])
     r = _run(exe)
     assert r.returncode == 0 and "DROPIN_OK" in r.stdout
 
