@@ -424,6 +424,7 @@ public:
         uint32_t w[6]; state_to_words(state, w);
         int64_t r = 0;
         if (timing) ctx_->phase_timing(true);
+        ctx_->check(rlb200_set_bqrrp_tol(ctx_->get(), (double)tol));
         int rc = ctx_->check(detail::abi<T>::bqrrp_host(ctx_->get(), m, n, A, lda, d_factor, block_size, (int)qrcp_wide, (int)qr_tall, tau, J, &r, w));
         if (timing) { times = ctx_->phase_times(); ctx_->phase_timing(false); }
         words_to_state(w, state);
@@ -468,6 +469,7 @@ public:
     {
         int64_t r = 0;
         if (timing) ctx_->phase_timing(true);
+        ctx_->check(rlb200_set_bqrrp_tol(ctx_->get(), (double)tol));
         int rc = ctx_->check(detail::abi<T>::bqrrp_dev_sk(ctx_->get(), m, n, A, lda, A_sk, d, block_size, (int)qr_tall, tau, J, &r));
         if (timing) { times = ctx_->phase_times(); ctx_->phase_timing(false); }
         rank = r;

@@ -118,6 +118,10 @@ RLB200_API int rlb200_timer_read(rlb200_ctx* ctx, int which, double* ms, int64_t
  * CQRRPT 8 entries rl_cqrrpt.hh:371-384, CQRRT 10 entries rl_cqrrt.hh:279-282, BQRRP 10 entries rl_bqrrp.hh:582-584).  Recorded only while
  * enabled (every phase boundary then synchronises the stream).  rlb200_get_phase_times returns the number of entries of the last call. */
 RLB200_API int rlb200_set_phase_timing(rlb200_ctx* ctx, int on);
+/* BQRRP's public `tol` field (rl_bqrrp.hh:141, used at :422 to cut the block rank where |R_sk(i,i)| / |R_sk(0,0)| < tol); 0 = the
+ * constructor default (machine epsilon of the working type).  Applies to the following rlb200_bqrrp_* calls on this context.  The fields
+ * `internal_nb` and `apply_trans_q` (:138, :149) select LAPACK blockings of the same factorization and have no counterpart here. */
+RLB200_API int rlb200_set_bqrrp_tol(rlb200_ctx* ctx, double tol);
 RLB200_API int rlb200_get_phase_times(rlb200_ctx* ctx, long long* out_us, int cap);
 
 /* ---- device memory helpers for host-pointer callers (the C++ adapters in RandLAPACK_B200.hh stage through these so that

@@ -248,9 +248,10 @@ static int cqrrt_impl(int64_t m, int64_t n, T* A, int64_t lda, T* R, int64_t ldr
 // BQRRP (RandLAPACK/drivers/rl_bqrrp.hh:154-665). qrcp_wide: 0 luqr (default), 1 geqp3; qr_tall: 0 geqrf (default), 1 cholqr, 2 geqrt
 template <typename T>
 static int bqrrp_impl(int64_t m, int64_t n, T* A, int64_t lda, T d_factor, int64_t b_sz, int qrcp_wide, int qr_tall, T* tau, int64_t* J,
-                      int64_t* rank, uint32_t state[6]) {
+                      int64_t* rank, uint32_t state[6], T tol = 0) {
     RL_TRY
     RandLAPACK::BQRRP<T, RNG> alg(false, b_sz);
+    if (tol > 0) alg.tol = tol;
     alg.qrcp_wide = qrcp_wide == 1 ? RandLAPACK::BQRRPSubroutines::QRCPWide::geqp3 : RandLAPACK::BQRRPSubroutines::QRCPWide::luqr;
     alg.qr_tall = qr_tall == 1 ? RandLAPACK::BQRRPSubroutines::QRTall::cholqr
                 : qr_tall == 2 ? RandLAPACK::BQRRPSubroutines::QRTall::geqrt : RandLAPACK::BQRRPSubroutines::QRTall::geqrf;
@@ -436,6 +437,10 @@ int rlref_mat_gen_f32(int type, int64_t m, int64_t n, int64_t rank, float cond, 
     int rlref_bqrrp_##SUF(int64_t m, int64_t n, T* A, int64_t lda, T d_factor, int64_t b_sz, int qrcp_wide, int qr_tall, T* tau,           \
                           int64_t* J, int64_t* rank, uint32_t state[6]) {                                                                  \
         return bqrrp_impl<T>(m, n, A, lda, d_factor, b_sz, qrcp_wide, qr_tall, tau, J, rank, state);                                       \
+    }                                                                                                                                     \
+    int rlref_bqrrp_tol_##SUF(int64_t m, int64_t n, T* A, int64_t lda, T d_factor, int64_t b_sz, int qrcp_wide, int qr_tall, T tol, T* tau, \
+                              int64_t* J, int64_t* rank, uint32_t state[6]) {                                                              \
+        return bqrrp_impl<T>(m, n, A, lda, d_factor, b_sz, qrcp_wide, qr_tall, tau, J, rank, state, tol);                                  \
     }
 RLREF_TYPED(double, f64)
 RLREF_TYPED(float, f32)

@@ -745,7 +745,7 @@ class BQRRP:
     apply_trans_q = ormqr (applied here through the compact-WY form, which is what ormqr computes)."""
 
     def __init__(self, b_sz, qrcp_wide="luqr", qr_tall="geqrf"):
-        self.block_size, self.qrcp_wide, self.qr_tall, self.rank = b_sz, qrcp_wide, qr_tall, None
+        self.block_size, self.qrcp_wide, self.qr_tall, self.rank, self.tol = b_sz, qrcp_wide, qr_tall, None, None
 
     def call(self, A, d_factor, state: RNGState):
         """-> (rc, A_out [GEQP3 format], tau, J (1-based), next state)."""
@@ -753,7 +753,7 @@ class BQRRP:
         m, n = A.shape
         dt = A.dtype
         eps = np.finfo(dt).eps
-        tol = eps
+        tol = eps if self.tol is None else dt.type(self.tol)                          # this->tol (:141), ctor default eps (:71)
         tau = np.zeros(n, dtype=dt)
         J = np.zeros(n, dtype=np.int64)
         rows, cols, curr, b_sz = m, n, 0, self.block_size

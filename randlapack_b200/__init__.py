@@ -741,6 +741,10 @@ class BQRRP:
             raise Error(_capi.ERR_ARG, "randlapack_require(b_sz > 0)")
         self.timing, self.block_size, self.rank = time_subroutines, b_sz, None
         self.qrcp_wide, self.qr_tall = _capi.QRCP_LUQR, _capi.QRTALL_GEQRF
+        self.tol = None      # BQRRP::tol (rl_bqrrp.hh:141); None = the constructor default (machine epsilon of the working type)
+
+    def _set_tol(self, ctx):
+        ctx.check(ctx._lib.rlb200_set_bqrrp_tol(ctx._h, 0.0 if self.tol is None else float(self.tol)))
 
     def call(self, ctx: Context, A, d_factor, state: RNGState, tau=None, J=None):
         """A (m x n device, column-major) is overwritten GEQP3-style -> (rc, tau (n), J int64 1-based)."""
@@ -752,6 +756,7 @@ class BQRRP:
         rank = ctypes.c_int64(0)
         w = state.words()
         fn = getattr(ctx._lib, f"rlb200_bqrrp_{_suffix(A.dtype)}_dev")
+        self._set_tol(ctx)
         rc = ctx.check(fn(ctx._h, m, n, A.data_ptr(), _ld(A), d_factor, self.block_size, self.qrcp_wide, self.qr_tall, tau.data_ptr(),
                           J.data_ptr(), ctypes.byref(rank), w))
         state.assign(w)
@@ -770,6 +775,7 @@ class BQRRP:
         J = torch.zeros(n, dtype=torch.int64, device=A.device) if J is None else J
         rank = ctypes.c_int64(0)
         fn = getattr(ctx._lib, f"rlb200_bqrrp_{_suffix(A.dtype)}_dev_sk")
+        self._set_tol(ctx)
         rc = ctx.check(fn(ctx._h, m, n, A.data_ptr(), _ld(A), A_sk.data_ptr(), d, self.block_size, self.qr_tall, tau.data_ptr(), J.data_ptr(),
                           ctypes.byref(rank)))
         self.rank = rank.value
@@ -784,6 +790,7 @@ class BQRRP:
         rank = ctypes.c_int64(0)
         w = state.words()
         fn = getattr(ctx._lib, f"rlb200_bqrrp_{_suffix(A_host.dtype)}_host")
+        self._set_tol(ctx)
         rc = ctx.check(fn(ctx._h, m, n, A_host.data_ptr(), _ld(A_host), d_factor, self.block_size, self.qrcp_wide, self.qr_tall,
                           tau.data_ptr(), J.data_ptr(), ctypes.byref(rank), w))
         state.assign(w)

@@ -311,7 +311,7 @@ int bqrrp_call(Ctx* ctx, int64_t m, int64_t n, T* A, int64_t lda, T d_factor, in
     *rank_out = 0;
     if (m == 0 || n == 0) return 0;
     const T eps = std::numeric_limits<T>::epsilon();
-    const T tol = eps;                                                                  // ctor default :69
+    const T tol = ctx->bqrrp_tol > 0.0 ? (T)ctx->bqrrp_tol : eps;                       // this->tol (:141, :422); ctor default eps (:71)
     int64_t rows = m, cols = n, curr_sz = 0, b_sz = block_size;
     const int64_t maxiter = (int64_t)std::ceil((T)std::min(m, n) / (T)b_sz);            // :201
     const int64_t b_const = b_sz;

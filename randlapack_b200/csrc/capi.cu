@@ -191,6 +191,12 @@ int rlb200_set_fp64_engine(rlb200_ctx* ctx, int engine) {
     ctx->fp64_engine = engine;
     return 0;
 }
+int rlb200_set_bqrrp_tol(rlb200_ctx* ctx, double tol) {
+    CTX_OK(ctx);
+    RLB_REQUIRE(ctx, tol >= 0.0);
+    ctx->bqrrp_tol = tol;
+    return 0;
+}
 int rlb200_set_phase_timing(rlb200_ctx* ctx, int on) { CTX_OK(ctx); ctx->phase_timing = on != 0; ctx->phase_us.clear(); return 0; }
 int rlb200_get_phase_times(rlb200_ctx* ctx, long long* out_us, int cap) {
     CTX_OK(ctx);

@@ -10,6 +10,7 @@
 //                      also the norm machinery of rl_hqrrp.hh:336-461
 //   geqrf_unblocked    lapack::geqrf of the small d x n sketch            rl_bqrrp.hh:356
 #include "drivers.cuh"
+#include <cooperative_groups.h>
 #include <algorithm>
 #include <cmath>
 #include <limits>
@@ -345,6 +346,267 @@ __global__ void iota_i64_kernel(int64_t n, int64_t* p, int64_t base) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] = base + i;
 }
 
+// ------------------------------------------------------------------------------------------------
+// The same factorisation in ONE cooperative launch (one grid-wide barrier per column instead of two kernel launches).
+//   * columns are never swapped physically: a column keeps its storage and carries a logical position (col2pos); idamax ties are broken by
+//     position, which reproduces LAPACK's order after its swaps; the columns are gathered into pivot order once at the end;
+//   * nothing is serial: every CTA reduces the per-CTA pivot candidates of the previous step, reads alpha and the exact sum of squares of
+//     the pivot column below the diagonal (accumulated for every column for free while it was last updated) and derives dlarfg's
+//     (beta, tau, scale) redundantly; the scaled reflector is staged in shared memory; a warp owns a column: dot, update, sum of squares
+//     of the updated column, dlaqp2 norm downdate and the next pivot candidate in one pass pair;
+//   * the pivot column itself is scaled / gets beta one step later by its owner (other CTAs still read its raw entries during the step).
+// ------------------------------------------------------------------------------------------------
+struct QrCand { double v; long long pos; long long col; long long pad; };
+
+__device__ __forceinline__ bool qr_better(double v, long long pos, double bv, long long bp) { return v > bv || (v == bv && pos < bp); }
+
+// A column is owned by a group of GS threads: one warp for short columns (d <= 1024), four warps beyond.
+constexpr int kQrEpt = 32;            // column entries a thread keeps in registers: one pass over memory for up to GS * 32 live rows
+
+template <int GS>
+__device__ __forceinline__ void qr_gbar(int grp) {
+    if constexpr (GS == 32) __syncwarp();
+    else asm volatile("bar.sync %0, 128;" ::"r"(grp + 1) : "memory");
+}
+// sum over the warps of a group; every thread of the group gets the total.  `slot` alternates so that consecutive reductions do not collide.
+template <int GS>
+__device__ __forceinline__ double qr_group_sum(double v, double* red /* [2][4] of this group */, int slot, int grp, int wig, int lane) {
+    v = warp_sum(v);
+    if constexpr (GS == 32) return v;
+    if (lane == 0) red[slot * 4 + wig] = v;
+    qr_gbar<GS>(grp);
+    return (red[slot * 4 + 0] + red[slot * 4 + 1]) + (red[slot * 4 + 2] + red[slot * 4 + 3]);
+}
+
+template <typename T, bool PIVOT, int GS>
+__global__ void __launch_bounds__(512) qr_coop_kernel(int64_t d, int64_t n, int64_t kmin, T* __restrict__ A, int64_t lda, double* __restrict__ vn1,
+                                                      double* __restrict__ vn2, double* __restrict__ ss2, long long* __restrict__ col2pos,
+                                                      QrCand* __restrict__ cand, T* __restrict__ tau_out, double safmin, double tol3z) {
+    namespace cg = cooperative_groups;
+    cg::grid_group grid = cg::this_grid();
+    extern __shared__ double sv[];                        // scaled reflector, rows j+1 .. d-1
+    constexpr int kQrGroups = 512 / GS;
+    __shared__ double s_bv[kQrGroups];
+    __shared__ long long s_bp[kQrGroups], s_bc[kQrGroups];
+    __shared__ double s_red[kQrGroups][12];
+    __shared__ double s_sc[4];                            // scal, tau, beta
+    __shared__ long long s_piv[2];                        // pivot column, its position
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int grp = tid / GS, wig = (tid % GS) >> 5, gt = tid % GS;     // group, warp in group, thread in group
+    const int64_t G = gridDim.x, cta = blockIdx.x;
+    const int64_t gg = cta * kQrGroups + grp, ng = G * kQrGroups;      // columns c == gg (mod ng) belong to this group
+    double* red = s_red[grp];
+
+    auto publish = [&](double bv, long long bp, long long bc, int64_t slot) {
+        if (gt == 0) { s_bv[grp] = bv; s_bp[grp] = bp; s_bc[grp] = bc; }
+        __syncthreads();
+        if (tid == 0) {
+            for (int w = 1; w < kQrGroups; ++w) if (s_bc[w] >= 0 && (bc < 0 || qr_better(s_bv[w], s_bp[w], bv, bp))) { bv = s_bv[w]; bp = s_bp[w]; bc = s_bc[w]; }
+            QrCand c; c.v = bv; c.pos = bp; c.col = bc; c.pad = 0;
+            cand[slot * G + cta] = c;
+        }
+    };
+
+    // prologue: column norms, sum of squares below row 0, logical positions, first candidates
+    {
+        double bv = -1.0; long long bp = n, bc = -1;
+        for (int64_t c = gg; c < n; c += ng) {
+            const T* a = A + c * lda;
+            double s = 0.0;
+            for (int64_t i = 1 + gt; i < d; i += GS) { const double x = (double)a[i]; s = fma(x, x, s); }
+            s = qr_group_sum<GS>(s, red, 0, grp, wig, lane);
+            const double a0 = (double)a[0];
+            const double nv = sqrt(fma(a0, a0, s));
+            if (gt == 0) { ss2[c] = s; col2pos[c] = c; if (PIVOT) { vn1[c] = nv; vn2[c] = nv; } }
+            if (PIVOT) { const double key = (nv == nv) ? nv : -0.5; if (bc < 0 || qr_better(key, c, bv, bp)) { bv = key; bp = c; bc = c; } }
+            qr_gbar<GS>(grp);      // red[] is free again
+        }
+        if (PIVOT) publish(bv, bp, bc, 0);
+    }
+    grid.sync();
+
+    long long prev_pc = -1;
+    double prev_scal = 1.0, prev_beta = 0.0;
+    bool prev_scaled = false;
+    for (int64_t j = 0; j < kmin; ++j) {
+        // ---- pivot (every CTA, redundantly)
+        if (warp == 0) {
+            long long pc = j, pp = j;
+            if (PIVOT) {
+                double bv = -2.0; long long bp = n; pc = -1;
+                for (int64_t g = lane; g < G; g += 32) {
+                    const QrCand* q = cand + (j & 1) * G + g;
+                    const double v = __ldcg(&q->v); const long long ps = __ldcg(&q->pos), cl = __ldcg(&q->col);
+                    if (cl >= 0 && (pc < 0 || qr_better(v, ps, bv, bp))) { bv = v; bp = ps; pc = cl; }
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
+                    const long long op = __shfl_xor_sync(0xffffffffu, bp, o), oc = __shfl_xor_sync(0xffffffffu, pc, o);
+                    if (oc >= 0 && (pc < 0 || qr_better(ov, op, bv, bp))) { bv = ov; bp = op; pc = oc; }
+                }
+                pp = bp;
+            }
+            if (lane == 0) {
+                s_piv[0] = pc; s_piv[1] = pp;
+                // dlarfg(d - j, x[j], x[j+1:]) from alpha and the exact sum of squares below the diagonal
+                const double alpha = (double)__ldcg(A + j + pc * lda);
+                const double xnorm = (j + 1 < d) ? sqrt(__ldcg(ss2 + pc)) : 0.0;
+                double tau = 0.0, scal = 1.0, beta = alpha;
+                if (xnorm != 0.0 && j + 1 < d) {
+                    beta = -copysign(hypot(alpha, xnorm), alpha);
+                    if (fabs(beta) < safmin) {
+                        const double rs = 1.0 / safmin;
+                        const double a2 = alpha * rs, x2 = xnorm * rs;
+                        const double b2 = -copysign(hypot(a2, x2), a2);
+                        tau = (b2 - a2) / b2;
+                        scal = rs / (a2 - b2);
+                        beta = b2 * safmin;
+                    } else {
+                        tau = (beta - alpha) / beta;
+                        scal = 1.0 / (alpha - beta);
+                    }
+                }
+                s_sc[0] = scal; s_sc[1] = tau; s_sc[2] = beta;
+                if (cta == 0) tau_out[j] = (T)tau;
+            }
+        }
+        __syncthreads();
+        const long long pc = s_piv[0], pp = s_piv[1];
+        const double scal = s_sc[0], tau_full = s_sc[1], beta = s_sc[2];
+        const double tau = (double)(T)tau_full;
+        if (tau_full != 0.0) {
+            const T* x = A + pc * lda;
+            for (int64_t i = j + 1 + tid; i < d; i += blockDim.x) sv[i] = (double)(T)((double)__ldcg(x + i) * scal);
+        }
+        __syncthreads();
+        // ---- apply H_j to the owned live columns: a group of 4 warps per column, the column's live rows in registers
+        const int64_t len = d - (j + 1);
+        const bool one_pass = len <= (int64_t)GS * kQrEpt;
+        double bv = -1.0; long long bp = n, bc = -1;
+        for (int64_t c = gg; c < n; c += ng) {
+            T* a = A + c * lda;
+            long long pos = col2pos[c];
+            if (c == pc) { qr_gbar<GS>(grp); if (gt == 0) col2pos[c] = j; continue; }
+            if (pos < j) {
+                if (c == prev_pc) {                       // last step's pivot column: nobody reads it any more
+                    if (prev_scaled) for (int64_t i = j + gt; i < d; i += GS) a[i] = (T)((double)a[i] * prev_scal);
+                    if (gt == 0) a[j - 1] = (T)prev_beta;
+                }
+                continue;
+            }
+            qr_gbar<GS>(grp);      // everyone has read col2pos[c] before it may change
+            if (pos == j) { pos = pp; if (gt == 0) col2pos[c] = pp; }          // the displaced column takes the pivot's old position
+            double ajc = (double)a[j];
+            double s = 0.0, a_next = 0.0;
+            T ar[kQrEpt];
+            if (one_pass) {
+#pragma unroll
+                for (int e = 0; e < kQrEpt; ++e) { const int64_t i = j + 1 + gt + GS * e; ar[e] = (i < d) ? a[i] : (T)0; }
+            }
+            if (tau_full != 0.0) {
+                double w = 0.0;
+                if (one_pass) {
+#pragma unroll
+                    for (int e = 0; e < kQrEpt; ++e) { const int64_t i = j + 1 + gt + GS * e; if (i < d) w = fma(sv[i], (double)ar[e], w); }
+                } else {
+                    for (int64_t i = j + 1 + gt; i < d; i += GS) w = fma(sv[i], (double)a[i], w);
+                }
+                w = qr_group_sum<GS>(w, red, 0, grp, wig, lane) + ajc;
+                const double tw = tau * w;
+                if (one_pass) {
+#pragma unroll
+                    for (int e = 0; e < kQrEpt; ++e) {
+                        const int64_t i = j + 1 + gt + GS * e;
+                        if (i < d) {
+                            const T nvT = (T)((double)ar[e] - tw * sv[i]);
+                            a[i] = nvT;
+                            const double xn = (double)nvT;
+                            if (i == j + 1) a_next = xn; else s = fma(xn, xn, s);
+                        }
+                    }
+                } else {
+                    for (int64_t i = j + 1 + gt; i < d; i += GS) {
+                        const T nvT = (T)((double)a[i] - tw * sv[i]);
+                        a[i] = nvT;
+                        const double xn = (double)nvT;
+                        if (i == j + 1) a_next = xn; else s = fma(xn, xn, s);
+                    }
+                }
+                ajc = (double)(T)(ajc - tw);
+                if (gt == 0) a[j] = (T)ajc;
+            } else {
+                if (one_pass) {
+#pragma unroll
+                    for (int e = 0; e < kQrEpt; ++e) {
+                        const int64_t i = j + 1 + gt + GS * e;
+                        if (i < d) { const double xn = (double)ar[e]; if (i == j + 1) a_next = xn; else s = fma(xn, xn, s); }
+                    }
+                } else {
+                    for (int64_t i = j + 1 + gt; i < d; i += GS) { const double xn = (double)a[i]; if (i == j + 1) a_next = xn; else s = fma(xn, xn, s); }
+                }
+            }
+            if constexpr (GS == 32) {
+                a_next = __shfl_sync(0xffffffffu, a_next, 0);     // row j + 1 is held by thread 0 of the group
+                s = warp_sum(s);
+            } else {
+                if (gt == 0) red[8] = a_next;
+                s = qr_group_sum<GS>(s, red, 1, grp, wig, lane);
+                a_next = red[8];
+            }
+            if (gt == 0) ss2[c] = s;                      // rows >= j + 2: what dlarfg needs if this column is the next pivot
+            if (PIVOT) {
+                double n1 = vn1[c];
+                if (n1 != 0.0) {                          // LAPACK dlaqp2 partial-norm downdate
+                    double temp = fabs(ajc) / n1;
+                    temp = fmax(0.0, (1.0 + temp) * (1.0 - temp));
+                    const double r = n1 / vn2[c];
+                    const double temp2 = temp * r * r;
+                    if (temp2 <= tol3z) {
+                        n1 = (j + 1 < d) ? sqrt(fma(a_next, a_next, s)) : 0.0;
+                        qr_gbar<GS>(grp);  // all threads of the group have read vn1 / vn2
+                        if (gt == 0) { vn1[c] = n1; vn2[c] = n1; }
+                    } else {
+                        n1 = n1 * sqrt(temp);
+                        qr_gbar<GS>(grp);
+                        if (gt == 0) vn1[c] = n1;
+                    }
+                }
+                const double key = (n1 == n1) ? n1 : -0.5;
+                if (bc < 0 || qr_better(key, pos, bv, bp)) { bv = key; bp = pos; bc = c; }
+            }
+        }
+        prev_pc = pc; prev_scal = scal; prev_beta = beta; prev_scaled = tau_full != 0.0;
+        if (PIVOT) publish(bv, bp, bc, (j + 1) & 1);
+        grid.sync();
+    }
+    // the last pivot column
+    for (int64_t c = gg; c < n; c += ng) {
+        if (c != prev_pc) continue;
+        T* a = A + c * lda;
+        if (prev_scaled) for (int64_t i = kmin + gt; i < d; i += GS) a[i] = (T)((double)a[i] * prev_scal);
+        if (gt == 0) a[kmin - 1] = (T)prev_beta;
+    }
+}
+
+// pivots and the gather into pivot order: position q receives the column stored at pos2col[q]
+__global__ void qr_pos2col_kernel(int64_t n, const long long* __restrict__ col2pos, long long* __restrict__ pos2col, int64_t* __restrict__ jpvt) {
+    for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < n; c += (int64_t)gridDim.x * blockDim.x) {
+        const long long q = col2pos[c];
+        pos2col[q] = c;
+        jpvt[q] = c + 1;
+    }
+}
+template <typename T>
+__global__ void __launch_bounds__(256) qr_gather_kernel(int64_t d, int64_t n, const T* __restrict__ src, T* __restrict__ A, int64_t lda,
+                                                        const long long* __restrict__ pos2col) {
+    for (int64_t q = blockIdx.x; q < n; q += gridDim.x) {
+        const T* s = src + (int64_t)pos2col[q] * d;
+        T* a = A + q * lda;
+        for (int64_t i = threadIdx.x; i < d; i += blockDim.x) a[i] = s[i];
+    }
+}
+
 size_t qrcp_ws_bytes(int64_t n) { return ws_round(sizeof(double) * n) * 2 + ws_round(sizeof(QrcpStep)); }
 
 // geqp3 (pivot = true; jpvt_dev receives 1-based GEQP3-style pivots, all columns free) or geqrf (pivot = false; jpvt_dev unused)
@@ -364,6 +626,41 @@ int qr_small(Ctx* ctx, bool pivot, int64_t d, int64_t n, T* A, int64_t lda, int6
     const double eps = sizeof(T) == 8 ? 1.1102230246251565e-16 : 5.9604644775390625e-08;       // lamch('Epsilon')
     const double safmin = (sizeof(T) == 8 ? 2.2250738585072014e-308 : 1.1754943508222875e-38) / eps;
     const double tol3z = std::sqrt(eps);
+    // one cooperative launch (qr_coop_kernel) whenever the reflector fits shared memory and the grid can be co-resident
+    // (measured, tools/bench_qrcp.py: 4096 x 2048: 91.7 -> 41.2 ms; with more than ~8 columns per group and step the two-launch form, whose apply
+    //  kernel spreads the columns over 8 CTAs per SM, is faster: 256 x 65536: 19.8 vs 35.9 ms)
+    const bool wide_groups = d > 1024;
+    const int groups_per_cta = wide_groups ? 4 : 16;
+    if (d <= 16384 && n <= (int64_t)8 * groups_per_cta * ctx->num_sms && getenv("RLB200_QR_NOCOOP") == nullptr) {
+        const size_t smem = sizeof(double) * (size_t)d;
+        void* kern = wide_groups ? (pivot ? (void*)qr_coop_kernel<T, true, 128> : (void*)qr_coop_kernel<T, false, 128>)
+                                 : (pivot ? (void*)qr_coop_kernel<T, true, 32> : (void*)qr_coop_kernel<T, false, 32>);
+        RLB_CUDA_OK(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int occ = 0;
+        RLB_CUDA_OK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 512, smem));
+        if (occ > 0) {
+            ArenaScope as(ctx);
+            const int64_t G = std::max<int64_t>(1, std::min<int64_t>((int64_t)ctx->num_sms, (n + groups_per_cta - 1) / groups_per_cta));
+            double* ss2 = as.take<double>((size_t)n); if (!ss2) return RLB200_ERR_ALLOC;
+            long long* col2pos = as.take<long long>((size_t)n); if (!col2pos) return RLB200_ERR_ALLOC;
+            long long* pos2col = as.take<long long>((size_t)n); if (!pos2col) return RLB200_ERR_ALLOC;
+            QrCand* cand = as.take<QrCand>((size_t)2 * G); if (!cand) return RLB200_ERR_ALLOC;
+            T* tmp = nullptr;
+            if (pivot) { tmp = as.take<T>((size_t)d * n); if (!tmp) return RLB200_ERR_ALLOC; }
+            LaunchScope ls(ctx, RLB200_TIMER_FACTOR, pivot ? 3 : 1);
+            int64_t d_ = d, n_ = n, k_ = kmin, lda_ = lda;
+            double safmin_ = safmin, tol3z_ = tol3z;
+            void* args[] = {&d_, &n_, &k_, &A, &lda_, &vn1, &vn2, &ss2, &col2pos, &cand, &tau_dev, &safmin_, &tol3z_};
+            RLB_CUDA_OK(ctx, cudaLaunchCooperativeKernel(kern, dim3((unsigned)G), dim3(512), args, smem, ctx->stream));
+            if (pivot) {
+                RLB_CUDA_OK(ctx, cudaMemcpy2DAsync(tmp, d * sizeof(T), A, lda * sizeof(T), d * sizeof(T), n, cudaMemcpyDeviceToDevice, ctx->stream));
+                qr_pos2col_kernel<<<(unsigned)std::min<int64_t>((n + 255) / 256, 1024), 256, 0, ctx->stream>>>(n, col2pos, pos2col, jpvt_dev);
+                qr_gather_kernel<T><<<(unsigned)std::min<int64_t>(n, (int64_t)ctx->num_sms * 8), 256, 0, ctx->stream>>>(d, n, tmp, A, lda, pos2col);
+            }
+            RLB_CUDA_OK(ctx, cudaGetLastError());
+            return 0;      // (the scratch is reused in stream order)
+        }
+    }
     LaunchScope ls(ctx, RLB200_TIMER_FACTOR, (int)(2 * kmin + 2));
     if (pivot) {
         iota_i64_kernel<T><<<(unsigned)std::min<int64_t>((n + 255) / 256, 1024), 256, 0, ctx->stream>>>(n, jpvt_dev, 1);

@@ -211,8 +211,8 @@ def ref_revd2(lib, uplo, A, k, tol, p, q, orth, error_est_p, seed6, k_cap=None):
     return rc, kk.value, V[:, :kk.value].copy(order="F"), ev[:kk.value].copy(), list(st)
 
 
-def ref_bqrrp(lib, A, d_factor, b_sz, seed6, qrcp_wide=0, qr_tall=0):
-    """RandLAPACK::BQRRP::call via the compiled reference -> (rc, rank, A_out [GEQP3 format], tau, J, state)."""
+def ref_bqrrp(lib, A, d_factor, b_sz, seed6, qrcp_wide=0, qr_tall=0, tol=None):
+    """RandLAPACK::BQRRP::call via the compiled reference -> (rc, rank, A_out [GEQP3 format], tau, J, state).  tol: the object's public field."""
     m, n = A.shape
     dt = A.dtype
     F = np.asfortranarray(A.copy())
@@ -220,6 +220,12 @@ def ref_bqrrp(lib, A, d_factor, b_sz, seed6, qrcp_wide=0, qr_tall=0):
     J = np.zeros(n, dtype=np.int64)
     rank = i64(0)
     st = (u32 * 6)(*seed6)
+    if tol is not None:
+        f = getattr(lib, f"rlref_bqrrp_tol_{_suf(dt)}")
+        f.argtypes = [i64, i64, ctypes.c_void_p, i64, _ft(dt), i64, ctypes.c_int, ctypes.c_int, _ft(dt), ctypes.c_void_p, ctypes.c_void_p,
+                      ctypes.POINTER(i64), ctypes.POINTER(u32)]
+        rc = f(m, n, F.ctypes.data, m, d_factor, b_sz, qrcp_wide, qr_tall, tol, tau.ctypes.data, J.ctypes.data, ctypes.byref(rank), st)
+        return rc, rank.value, F, tau, J, list(st)
     f = getattr(lib, f"rlref_bqrrp_{_suf(dt)}")
     f.argtypes = [i64, i64, ctypes.c_void_p, i64, _ft(dt), i64, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p,
                   ctypes.POINTER(i64), ctypes.POINTER(u32)]

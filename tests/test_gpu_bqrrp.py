@@ -186,3 +186,27 @@ def test_bqrrp_gpu_interface_same_sketch_as_cpu(ctx, shape, b, d_factor, qr_tall
     assert np.linalg.norm(np.triu(F[:kn, :nc]) - np.triu(F2[:kn, :nc])) <= eps ** 0.60 * sc
     e = geqp3_format_invariants(A, F, tau, J, alg.rank if kn == o.rank else kn)
     assert e[2] <= eps ** 0.75 and (kn < o.rank or max(e) <= eps ** 0.75), e
+
+
+def test_bqrrp_tol_field_vs_oracle(ctx):
+    """BQRRP's public `tol` (rl_bqrrp.hh:141, rank cut at :422): a rank-70 matrix plus 1e-7 noise factors to full rank with the default
+    tol = eps and is cut at 96 columns with tol = 1e-3 - the same rank, pivots and R as the oracle (itself pinned to the compiled
+    reference in tests/test_oracle_qr.py::test_bqrrp_tol_field)."""
+    rng = np.random.default_rng(3)
+    A = np.asfortranarray(rng.standard_normal((600, 70)) @ rng.standard_normal((70, 200)) + 1e-7 * rng.standard_normal((600, 200)))
+    for tol, want in ((1e-3, 96), (None, 200)):
+        alg = rl.BQRRP(False, 32)
+        alg.tol = tol
+        Ad = dev(A)
+        s = rl.RNGState(4)
+        rc, tau, J = alg.call(ctx, Ad, 1.0, s)
+        o = O.BQRRP(32)
+        o.tol = tol
+        rc2, F2, tau2, J2, st2 = o.call(A, 1.0, O.RNGState(4))
+        assert (rc, alg.rank) == (rc2, o.rank) and alg.rank == want
+        assert list(s.words()) == list(st2.words())
+        r = min(alg.rank, 70)      # beyond the numerical rank the pivots order noise
+        assert np.array_equal(J.cpu().numpy()[:r], J2[:r])
+        F = host(Ad)
+        assert np.abs(np.triu(F)[:r, :] - np.triu(F2)[:r, :]).max() <= 1e-9 * np.abs(np.diag(F2)).max()
+    ctx.check(ctx._lib.rlb200_set_bqrrp_tol(ctx._h, 0.0))

@@ -90,3 +90,21 @@ def test_cqrrt_zero_column_returns_1():
     A[:, 7] = 0
     rc, *_ = O.CQRRT(None, 2).call(A, 2.0, st)
     assert rc == 1
+
+
+@pytest.mark.skipif(_ref.ref_lib() is None, reason="compiled reference not present")
+def test_bqrrp_tol_field():
+    """The oracle's `tol` (rl_bqrrp.hh:141, :422) against the compiled reference with the same public field set."""
+    L = _ref.ref_lib()
+    rng = np.random.default_rng(3)
+    A = np.asfortranarray(rng.standard_normal((600, 70)) @ rng.standard_normal((70, 200)) + 1e-7 * rng.standard_normal((600, 200)))
+    for tol, want in ((1e-3, 96), (None, 200)):
+        st = O.RNGState(4)
+        rc, rank, F, tau, J, st2 = _ref.ref_bqrrp(L, A, 1.0, 32, list(st.words()), tol=tol)
+        alg = O.BQRRP(32)
+        alg.tol = tol
+        rc2, F2, tau2, J2, st3 = alg.call(A, 1.0, st)
+        assert (rc, rank) == (rc2, alg.rank) and rank == want and list(st3.words()) == st2
+        r = min(rank, 70)
+        assert np.array_equal(J[:r], J2[:r])
+        assert np.abs(np.triu(F)[:r] - np.triu(F2)[:r]).max() <= 1e-10 * np.abs(np.diag(F)).max()
