@@ -170,7 +170,8 @@ template int fill_sparse_unpacked<float>(Ctx*, int64_t, int64_t, int64_t, int, i
 __global__ void __launch_bounds__(256) saso_plan_kernel(Ctr128 seed, uint32_t k0, uint32_t k1, int64_t col0, int64_t m_sub, int64_t d_full,
                                                         int64_t ro, int d_sub, int nnz, int R, int E2, int d_pad,
                                                         uint16_t* __restrict__ ent, uint16_t* __restrict__ off,
-                                                        uint32_t* __restrict__ key_out = nullptr, int rows_per_group = 0, int ngroups = 0) {
+                                                        uint32_t* __restrict__ key_out = nullptr, int rows_per_group = 0, int ngroups = 0,
+                                                        int sub = 0) {
     extern __shared__ uint32_t keys[];
     const int q = blockIdx.x;
     const int E = R * nnz;
@@ -183,7 +184,17 @@ __global__ void __launch_bounds__(256) saso_plan_kernel(Ctr128 seed, uint32_t k0
             uint32_t key = 0xFFFFFFFFu;
             if (j < m_sub) {
                 const int64_t r = (int64_t)rows[t] - ro;
-                if (r >= 0 && r < d_sub) key = ((uint32_t)r << 12) | ((uint32_t)jl << 1) | neg[t];
+                if (r >= 0 && r < d_sub) {
+                    uint32_t rr = (uint32_t)r;
+                    if (sub > 0) {
+                        // strip kernel: the `sub` lane groups of a warp share a range of sub * rows_per_group sketch rows and split it by
+                        // row mod sub, so that their accumulator accesses fall into disjoint shared-memory banks; the key carries the
+                        // row's index in that regrouped order (group = rr / rows_per_group)
+                        const uint32_t span = (uint32_t)sub * (uint32_t)rows_per_group, w0 = rr / span, in = rr - w0 * span;
+                        rr = w0 * span + (in % (uint32_t)sub) * (uint32_t)rows_per_group + in / (uint32_t)sub;
+                    }
+                    key = (rr << 12) | ((uint32_t)jl << 1) | neg[t];
+                }
             }
             keys[jl * nnz + t] = key;
         }
@@ -208,8 +219,8 @@ __global__ void __launch_bounds__(256) saso_plan_kernel(Ctr128 seed, uint32_t k0
         // rows_per_group sketch rows (ngroups + 1 values, padded to a multiple of 8)
         for (int i = threadIdx.x; i < E; i += blockDim.x) key_out[(int64_t)q * E + i] = keys[i];
         for (int gq = threadIdx.x; gq <= ngroups; gq += blockDim.x) {
-            const int64_t r = (int64_t)gq * rows_per_group;
-            const uint32_t bound = (r >= d_sub) ? 0xFFFFFFFFu : ((uint32_t)r << 12);
+            const int64_t r = (int64_t)gq * rows_per_group;      // (regrouped row indices run up to ngroups * rows_per_group)
+            const uint32_t bound = (gq >= ngroups) ? 0xFFFFFFFFu : ((uint32_t)r << 12);
             int lo = 0, hi = E2;
             while (lo < hi) { const int mid = (lo + hi) >> 1; if (keys[mid] < bound) lo = mid + 1; else hi = mid; }
             off[(int64_t)q * (ngroups + 8) + gq] = (uint16_t)lo;
@@ -363,6 +374,11 @@ __device__ __forceinline__ void ss_bulk(uint32_t dst, const void* src, uint32_t 
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
+// +-v by flipping the sign bit with bit 0 of the key
+__device__ __forceinline__ float saso_signed(float v, uint32_t k) { return __uint_as_float(__float_as_uint(v) ^ (k << 31)); }
+__device__ __forceinline__ double saso_signed(double v, uint32_t k) {
+    return __hiloint2double(__double2hiint(v) ^ (int)(k << 31), __double2loint(v));
+}
 constexpr int kStripThreads = 512;      // consumer threads (16 warps); one more warp produces
 constexpr int kStripBufs = 2;           // chunk buffers (measured: 4 buffers of half the size are not faster - the loop is bound by the
                                         // shared-memory pipe, ~4 accesses per entry and lane group, not by load latency)
@@ -413,7 +429,12 @@ saso_strip_kernel(const T* __restrict__ A, int64_t lda, int n, int d_sub, int d_
         }
     } else {
         // ---- consumers
-        const int col = lane % CPS, grp = warp * (32 / CPS) + lane / CPS;
+        constexpr int SUB = 32 / CPS;
+        const int col = lane % CPS, sub = lane / CPS, grp = warp * SUB + sub;
+        // keys carry the row's index in the regrouped order (saso_plan_kernel): key row rr of group grp is sketch row
+        // warp * SUB * rpg + sub + SUB * (rr - grp * rpg); the accumulator of (row, col) lives at acc[row * CPS + col]
+        const int rpg = d_pad / NG;
+        T* ac = acc + (warp * SUB * rpg + sub - SUB * grp * rpg) * CPS + col;
         for (int q = q0; q < q1; ++q) {
             const int i = q - q0, b = i % NB;
             ss_wait(ss_smem(&bar_full[b]), (uint32_t)((i / NB) & 1));
@@ -422,28 +443,30 @@ saso_strip_kernel(const T* __restrict__ A, int64_t lda, int n, int d_sub, int d_
             const int e1 = s_off[(size_t)b * OP + grp + 1];
             int e = s_off[(size_t)b * OP + grp];
             // four entries per step: their key / tile / accumulator loads are independent and in flight together; equal sketch rows are
-            // adjacent in the sorted list, so a repeated accumulator address only needs the previous entry's updated value
+            // adjacent in the sorted list, so a repeated accumulator index only needs the previous entry's updated value.  All indices are
+            // 32-bit offsets into shared memory and the sign is applied by flipping the sign bit (ncu of the first version: issue-bound,
+            // 65 % issue-active with the math pipe throttled by 64-bit address arithmetic).
             for (; e + 4 <= e1; e += 4) {
-                uint32_t k[4]; T v[4]; T* a[4]; T x[4];
+                uint32_t k[4]; T v[4]; int ai[4]; T x[4];
 #pragma unroll
                 for (int u = 0; u < 4; ++u) k[u] = kp[e + u];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) { v[u] = t[(k[u] >> 1) & 0x7FFu]; a[u] = acc + (size_t)(k[u] >> 12) * CPS + col; }
+                for (int u = 0; u < 4; ++u) { v[u] = t[(k[u] >> 1) & 0x7FFu]; ai[u] = (int)(k[u] >> 12) * (SUB * CPS); }
 #pragma unroll
-                for (int u = 0; u < 4; ++u) x[u] = *a[u];
+                for (int u = 0; u < 4; ++u) x[u] = ac[ai[u]];
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
-                    if (u > 0 && a[u] == a[u - 1]) x[u] = x[u - 1];
-                    x[u] += (k[u] & 1u) ? -v[u] : v[u];
+                    if (u > 0 && ai[u] == ai[u - 1]) x[u] = x[u - 1];
+                    x[u] += saso_signed(v[u], k[u]);
                 }
 #pragma unroll
-                for (int u = 0; u < 4; ++u) *a[u] = x[u];
+                for (int u = 0; u < 4; ++u) ac[ai[u]] = x[u];
             }
             for (; e < e1; ++e) {
                 const uint32_t k = kp[e];
                 const T v = t[(k >> 1) & 0x7FFu];
-                T* a = acc + (size_t)(k >> 12) * CPS + col;
-                *a += (k & 1u) ? -v : v;
+                const int ai = (int)(k >> 12) * (SUB * CPS);
+                ac[ai] += saso_signed(v, k);
             }
             // release the buffer: one arrive per warp (no CTA-wide barrier, warps may run a few chunks apart)
             __syncwarp();
@@ -512,7 +535,7 @@ static int saso_apply_strips(Ctx* ctx, Ctr128 seed, const uint32_t* state, int64
         RLB_CUDA_OK(ctx, cudaFuncSetAttribute(saso_plan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, E2 * 4));
         LaunchScope ls(ctx, RLB200_TIMER_SKETCH);
         saso_plan_kernel<<<nchunks, 256, E2 * 4, ctx->stream>>>(seed, state[4], state[5], col0, m_full, S_rows, ro, (int)d, (int)vec_nnz, R, E2, d_pad, nullptr,
-                                                                goff, keys, rpg, NG);
+                                                                goff, keys, rpg, NG, 32 / CPS);
         RLB_CUDA_OK(ctx, cudaGetLastError());
     }
     const int strips = (int)((n + CPS - 1) / CPS);
@@ -568,10 +591,10 @@ int sketch_sparse_left(Ctx* ctx, int64_t S_rows, int64_t S_cols, int64_t vec_nnz
             const int cps_sel = acc_cap >= 8 ? 8 : acc_cap >= 4 ? 4 : acc_cap >= 2 ? 2 : 0;
             int Rs = 1024;
             while (Rs > 64 && ((int64_t)Rs * vec_nnz > 3072 || (int64_t)kStripBufs * cps_sel * (Rs + EV) * (int64_t)sizeof(T) > 68 * 1024)) Rs >>= 1;
-            // measured (profiles/sec_sketch_sparse_*): the strip kernel wins for vec_nnz <= 2 (count-sketch and the CQRRPT default), the generic
-            // one for denser columns; RLB200_SASO_STRIPS=1 / RLB200_SASO_GENERIC=1 force either for experiments
+            // measured (profiles/sec_sketch_sparse_*_r2b): the strip kernel wins for vec_nnz <= 4 (nnz 4: 68 vs 82 ms), the generic
+            // one is kept for denser columns; RLB200_SASO_STRIPS=1 / RLB200_SASO_GENERIC=1 force either for experiments
             const bool strips_ok = cps_sel > 0 && (reinterpret_cast<uintptr_t>(A) % 16 == 0) && (lda % EV == 0) && (int64_t)Rs * vec_nnz <= 3072 &&
-                                   m >= 4 * (int64_t)Rs && getenv("RLB200_SASO_GENERIC") == nullptr && (vec_nnz <= 2 || getenv("RLB200_SASO_STRIPS") != nullptr);
+                                   m >= 4 * (int64_t)Rs && getenv("RLB200_SASO_GENERIC") == nullptr && (vec_nnz <= 4 || getenv("RLB200_SASO_STRIPS") != nullptr);
             int rc = 0;
             if (strips_ok) {
                 const int64_t m_full = (m / Rs) * Rs, tail = m - m_full;
