@@ -93,23 +93,44 @@ __device__ __forceinline__ float oz2_ldg(const float* p) {
 // 0 .. SP-1-s of the N side (<= 4 digit tiles = 256 columns per instruction), accumulator of anti-diagonal d at TMEM column 64 d.
 // lo: shared-memory address of the stage's first byte >> 4; the high word of a descriptor (SBO, version) is a constant.
 template <int SD, int SP, bool TN>
-__device__ __forceinline__ void oz2_issue_step(uint32_t lo, uint32_t tmem, bool first) {
+__device__ __forceinline__ void oz2_issue_one(uint32_t lo, uint32_t tmem, int s, int t0, uint32_t acc) {
     constexpr uint32_t IDESC0 = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(OZ_BM >> 4) << 24) | (TN ? ((1u << 15) | (1u << 16)) : 0u);
     constexpr uint64_t HI = ((uint64_t)((TN ? 512 : 256) >> 4) | ((uint64_t)1 << 14)) << 32;
     constexpr uint32_t LBO = (uint32_t)(128 >> 4) << 16;
     // (the start-address field holds bits 4..17 of the shared-memory address: inside a cluster a CTA's window does not start at 0)
+    const uint64_t da = HI | (uint64_t)(((lo + (uint32_t)((s * OZ_TILE_A) >> 4)) & 0x3FFFu) | LBO);
+    const int nt = (SP - s - t0) < 4 ? (SP - s - t0) : 4;
+    const uint32_t idesc = IDESC0 | ((uint32_t)((nt * OZ_BN) >> 3) << 17);
+    const uint64_t db = HI | (uint64_t)(((lo + (uint32_t)((SD * OZ_TILE_A + t0 * OZ_TILE_B) >> 4)) & 0x3FFFu) | LBO);
+    oz_mma_i8(tmem + (uint32_t)((s + t0) * OZ_BN), da, db, idesc, acc);
+}
+// Order inside a K step.  The issuing warp pays a fixed cost between two steps (commit, barrier wait, proxy fence: ~150-250 cycles) during
+// which the tensor pipe only has what is already queued; the queue is shallow (measured: with the narrow instructions at the end of a step
+// the loop runs at MMA time + that cost, 930-1100 cycles per step instead of 790).  So every step but the first ends with its widest
+// instructions (N = 256: 128 cycles each): narrow remainders first, then the 4-tile instructions.  The first step of a tile keeps the
+// ascending-digit order because its s = 0 instructions initialise the accumulators (accumulate flag 0).
+template <int SD, int SP, bool TN>
+__device__ __forceinline__ void oz2_issue_step(uint32_t lo, uint32_t tmem, bool first, bool ascending = true) {
+    if (first || ascending) {      // (the wide-last sequence below is an experiment: RLB200_OZ2_DBG bit 1024)
 #pragma unroll
-    for (int s = 0; s < SP; ++s) {
-        const uint64_t da = HI | (uint64_t)(((lo + (uint32_t)((s * OZ_TILE_A) >> 4)) & 0x3FFFu) | LBO);
+        for (int s = 0; s < SP; ++s)
 #pragma unroll
-        for (int t0 = 0; t0 < SP - s; t0 += 4) {
-            constexpr int dummy = 0; (void)dummy;
-            const int nt = (SP - s - t0) < 4 ? (SP - s - t0) : 4;
-            const uint32_t idesc = IDESC0 | ((uint32_t)((nt * OZ_BN) >> 3) << 17);
-            const uint64_t db = HI | (uint64_t)(((lo + (uint32_t)((SD * OZ_TILE_A + t0 * OZ_TILE_B) >> 4)) & 0x3FFFu) | LBO);
-            oz_mma_i8(tmem + (uint32_t)((s + t0) * OZ_BN), da, db, idesc, (!first || s > 0) ? 1u : 0u);
-        }
+            for (int t0 = 0; t0 < SP - s; t0 += 4) oz2_issue_one<SD, SP, TN>(lo, tmem, s, t0, (!first || s > 0) ? 1u : 0u);
+        return;
     }
+    // remainders (fewer than 4 digit tiles), narrowest first
+#pragma unroll
+    for (int nt = 1; nt < 4; ++nt)
+#pragma unroll
+        for (int s = SP - 1; s >= 0; --s) {
+            const int rem = (SP - s) % 4, t0 = (SP - s) - rem;
+            if (rem == nt) oz2_issue_one<SD, SP, TN>(lo, tmem, s, t0, 1u);
+        }
+    // full 4-tile instructions last
+#pragma unroll
+    for (int s = SP - 1; s >= 0; --s)
+#pragma unroll
+        for (int t0 = 0; t0 + 4 <= SP - s; t0 += 4) oz2_issue_one<SD, SP, TN>(lo, tmem, s, t0, 1u);
 }
 
 // T: element type of the tall matrix X; TO: element type of `out` (Gram partials are always fp64)
@@ -326,6 +347,7 @@ __global__ void __launch_bounds__(Oz2Threads<NG>::N, 1) oz2_kernel(const Oz2Para
                         for (int t = 0; t < SD; ++t) pk[q][t] = (uint32_t)__double_as_longlong((double)raw[4 * q + (t & 3)]);
                 }
                 if (share == 1) {
+                    if (!(p.dbg_flags & 256))      // (256: timing experiment without the digit stores)
 #pragma unroll
                     for (int t = 0; t < SD; ++t)
                         if (t < sp) *reinterpret_cast<uint4*>(dst + t * OZ_TILE_B) = make_uint4(pk[0][t], pk[1][t], pk[2][t], pk[3][t]);
@@ -451,7 +473,7 @@ __global__ void __launch_bounds__(Oz2Threads<NG>::N, 1) oz2_kernel(const Oz2Para
             if (p.dbg) t0 = clock64();
             if (share == 1) {
                 oz_mbar_wait(oz_smem(&bar_full[slot]), (uint32_t)((kb / DST) & 1));
-                if (!gram) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // the converters' stores of this stage (see there)
+                if (!gram && !(p.dbg_flags & 512)) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // the converters' stores of this stage (see there)
             } else {
                 // the digits of this stage may come from a peer CTA: acquire at cluster scope, then order those generic-proxy stores before the
                 // tensor core's async-proxy reads on the consumer side as well
@@ -463,8 +485,8 @@ __global__ void __launch_bounds__(Oz2Threads<NG>::N, 1) oz2_kernel(const Oz2Para
             if (elected) {
                 const uint32_t lo = base_lo0 + (uint32_t)slot * (uint32_t)(Cfg::STAGE_BYTES >> 4);
                 if (p.dbg_flags & 32) {}      // timing experiment: no MMAs (stages are released at once)
-                else if (sp == SD) oz2_issue_step<SD, SD, TN>(lo, tmem, kb == 0);
-                else oz2_issue_step<SD, (SD > 2 ? SD - 1 : SD), TN>(lo, tmem, kb == 0);
+                else if (sp == SD) oz2_issue_step<SD, SD, TN>(lo, tmem, kb == 0, (p.dbg_flags & 1024) == 0);
+                else oz2_issue_step<SD, (SD > 2 ? SD - 1 : SD), TN>(lo, tmem, kb == 0, (p.dbg_flags & 1024) == 0);
                 if (share == 1)
                     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(oz_smem(&bar_empty[slot])) : "memory");
                 else
@@ -587,6 +609,7 @@ struct Oz3Params {
     const int* En;                                  // raw row exponents of A
     int nkb, nbm; int64_t ntiles;                   // K blocks per tile, column tiles, tiles in all (tile t: bx = t % nbm, by = t / nbm)
     void* out; int64_t ldo; double alpha, beta;
+    int order_asc;                                  // timing experiments (RLB200_OZ3_ONE_STAGE): one stage per issue round
 };
 
 template <int SD, typename T>
@@ -830,21 +853,33 @@ __global__ void __launch_bounds__(Oz2Threads<2>::N, 1) oz3_kernel(const Oz3Param
         const uint32_t base_lo0 = sbase >> 4;
         int64_t gb = 0;
         for (int64_t j = 0; j < ntl; ++j) {
-            for (int kb = 0; kb < nkb; ++kb, ++gb) {
+            for (int kb = 0; kb < nkb;) {
                 const int slot = (int)(gb % DST);
                 oz_mbar_wait(oz_smem(&bar_full[slot]), (uint32_t)((gb / DST) & 1));
                 // the previous tile's accumulators have been read
                 if (kb == 0 && j > 0) oz_mbar_wait(oz_smem(&bar_acc_empty), (uint32_t)((j - 1) & 1));
+                // If the next stage is full already, both are issued behind one barrier wait / proxy fence: between two issue rounds the
+                // tensor pipe only has what is queued (measured: ~135 cycles per round on top of the 790 of the MMAs of a K step)
+                const int slot2 = (int)((gb + 1) % DST);
+                bool two = (kb + 1 < nkb) && !p.order_asc && oz_mbar_test(oz_smem(&bar_full[slot2]), (uint32_t)(((gb + 1) / DST) & 1));
+                two = __all_sync(0xffffffffu, two);
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // the converters' generic-proxy stores of this stage
                 asm volatile("tcgen05.fence::after_thread_sync;");
                 if (elected) {
                     const uint32_t lo = base_lo0 + (uint32_t)slot * (uint32_t)(Cfg::STAGE_BYTES >> 4);
-                    oz2_issue_step<SD, SD, false>(lo, tmem, kb == 0);
+                    oz2_issue_step<SD, SD, false>(lo, tmem, kb == 0, true);
                     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(oz_smem(&bar_empty[slot])) : "memory");
-                    if (kb == nkb - 1)
+                    if (two) {
+                        const uint32_t lo2 = base_lo0 + (uint32_t)slot2 * (uint32_t)(Cfg::STAGE_BYTES >> 4);
+                        oz2_issue_step<SD, SD, false>(lo2, tmem, false, true);
+                        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(oz_smem(&bar_empty[slot2])) : "memory");
+                    }
+                    if (kb + (two ? 1 : 0) == nkb - 1)
                         asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(oz_smem(&bar_acc_full)) : "memory");
                 }
                 __syncwarp();
+                kb += two ? 2 : 1;
+                gb += two ? 2 : 1;
             }
         }
     }
@@ -1020,6 +1055,8 @@ static int oz2_nn(Ctx* ctx, int64_t m, int64_t N, int64_t K, double alpha, const
         q.X = A; q.ldx = lda; q.rows_n = m; q.kdim = K; q.En = Ea;
         q.nkb = nkb; q.nbm = nbm; q.ntiles = nbn * nbm;
         q.out = C; q.ldo = ldc; q.alpha = alpha; q.beta = beta;
+        static const int order_asc = getenv("RLB200_OZ3_ONE_STAGE") ? 1 : 0;
+        q.order_asc = order_asc;
         LaunchScope ls(ctx, RLB200_TIMER_I8_MMA_NN);
         const unsigned grid = (unsigned)std::min<int64_t>(q.ntiles, (int64_t)ctx->num_sms);
         oz3_kernel<SD, T><<<grid, Oz2Threads<2>::N, Oz3Cfg<SD, T>::SMEM_BYTES, st>>>(q);
