@@ -25,10 +25,11 @@ sys.path.insert(0, ROOT)
 # profiles/ncu_oz2_tn_r2.txt: 4.485 GB + 0.078 GB per 27 x 16384 rows).  Algorithmic bytes per row: 8 n = 8192 (A read once per pass).
 OZ2_TRAFFIC_NN_PER_ROW = (8.597615e9 + 2.091834e9) / float(1 << 20)
 OZ2_TRAFFIC_TN_PER_ROW = (4.485259e9 + 0.077737e9) / (27.0 * 16384.0)
-# whole step, ALL kernels (profiles/launches_dram_r2.csv, 218 launches of one step at m = 2^20: 61.205 GB read + 6.595 GB written) plus the
-# digits of Y that ncu's serialised replay flushes between launches and so attributes to no kernel (2 passes x 7 k bytes per row, model)
-STEP_TRAFFIC_PER_ROW = (61.20515712e9 + 6.594783232e9) / float(1 << 20) + 2 * 7 * 256
-OZ_TRAFFIC_SOURCE = ("traffic: every kernel of one step, ncu launch list of this command at m = 2^20 (profiles/launches_dram_r2.csv) scaled by m; "
+# whole step, ALL kernels (profiles/launches_dram_r2b.csv: the ncu launch list of `bench.py --steps 1 --warmup 1 --m 1048576`, 3 steps executed:
+# 242.18 GB read + written by this library's kernels = 80.73 GB per step of 2^20 rows; the persistent A*Omega kernel reads 1.47x the bytes of A
+# from DRAM - L2 misses on re-referenced lines)
+STEP_TRAFFIC_PER_ROW = 80.72608972799999e9 / float(1 << 20)
+OZ_TRAFFIC_SOURCE = ("traffic: every kernel of one step, ncu launch list of this command at m = 2^20 (profiles/launches_dram_r2b.csv) scaled by m; "
                      "traffic_dominant_launches_only: ncu --set full captures of oz2_kernel (profiles/ncu_oz2_nn_r2.txt, ncu_oz2_tn_r2.txt), DRAM bytes per row "
                      "of A x rows x launches; algorithmic bytes per row and pass: 8 n (A, read once as fp64) + 8 k (Y written) for A*Omega, "
                      "8 n + S k (digits of Y) for A^T*Y")

@@ -630,7 +630,11 @@ __global__ void __launch_bounds__(Oz2Threads<2>::N, 1) oz3_kernel(const Oz3Param
     constexpr int W_PROD = 4 * NG, W_ISSUE = 4 * NG + 1;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int nkb = p.nkb;
-    const int64_t ntl = p.ntiles > (int64_t)blockIdx.x ? (p.ntiles - 1 - blockIdx.x) / gridDim.x + 1 : 0;      // tiles of this CTA
+    // Tiles of this CTA: ALL column tiles of its row blocks, back to back (row block blockIdx.x + r * gridDim.x, r = 0, 1, ...): the second
+    // column tile re-reads the rows of A a few microseconds after the first and finds them in L2.  (With the tiles dealt out one by one
+    // the two readers of a row block were different CTAs that drift apart: ncu showed 1.47x the bytes of A read from DRAM.)
+    const int64_t nrbt = p.ntiles / p.nbm;
+    const int64_t ntl = nrbt > (int64_t)blockIdx.x ? ((nrbt - 1 - blockIdx.x) / gridDim.x + 1) * p.nbm : 0;
 
     extern __shared__ __align__(1024) unsigned char oz3_smem_raw[];
     __shared__ __align__(8) uint64_t bar_full[DST], bar_empty[DST], bar_acc_full, bar_acc_empty;
@@ -738,9 +742,8 @@ __global__ void __launch_bounds__(Oz2Threads<2>::N, 1) oz3_kernel(const Oz3Param
         const int pre = nkb < DST ? nkb : DST;      // blocks of the next tile converted before the previous tile's epilogue
 #pragma unroll 1
         for (int64_t j = 0; j < ntl; ++j) {
-            const int64_t t = (int64_t)blockIdx.x + j * gridDim.x;
-            const int bx = (int)(t % p.nbm);
-            const int64_t by = t / p.nbm;
+            const int bx = (int)(j % p.nbm);
+            const int64_t by = (int64_t)blockIdx.x + (j / p.nbm) * gridDim.x;
             const int par = (int)(j & 1);
             // exponents of the tile (out-of-range rows mirror an in-range one so that they do not widen the range)
             if (warp == 0) {
@@ -835,8 +838,7 @@ __global__ void __launch_bounds__(Oz2Threads<2>::N, 1) oz3_kernel(const Oz3Param
         // ================= M-side bulk copies =================
         int64_t gb = 0;
         for (int64_t j = 0; j < ntl; ++j) {
-            const int64_t t = (int64_t)blockIdx.x + j * gridDim.x;
-            const int bx = (int)(t % p.nbm);
+            const int bx = (int)(j % p.nbm);
             const int8_t* gm = p.m_tiles + (int64_t)bx * p.nkb_stride * (SD * OZ_TILE_A);
             for (int kb = 0; kb < nkb; ++kb, ++gb) {
                 const int slot = (int)(gb % DST);
@@ -1058,7 +1060,7 @@ static int oz2_nn(Ctx* ctx, int64_t m, int64_t N, int64_t K, double alpha, const
         static const int order_asc = getenv("RLB200_OZ3_ONE_STAGE") ? 1 : 0;
         q.order_asc = order_asc;
         LaunchScope ls(ctx, RLB200_TIMER_I8_MMA_NN);
-        const unsigned grid = (unsigned)std::min<int64_t>(q.ntiles, (int64_t)ctx->num_sms);
+        const unsigned grid = (unsigned)std::min<int64_t>(nbn, (int64_t)ctx->num_sms);
         oz3_kernel<SD, T><<<grid, Oz2Threads<2>::N, Oz3Cfg<SD, T>::SMEM_BYTES, st>>>(q);
         RLB_CUDA_OK(ctx, cudaGetLastError());
         return 0;
