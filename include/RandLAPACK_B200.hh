@@ -333,6 +333,9 @@ public:
 // ---------------------------------------------------------------------------------------------------------------------
 // CQRRPT (rl_cqrrpt.hh:20-391): same constructor (time_subroutines, eps), public fields and call signature (HOST pointers).
 // ---------------------------------------------------------------------------------------------------------------------
+struct CQRRPTSubroutines {
+    enum QRCP { geqp3 = RLB200_CQRRPT_QRCP_GEQP3, bqrrp = RLB200_CQRRPT_QRCP_BQRRP };     // rl_cqrrpt.hh:39-43 (hqrrp is not offered)
+};
 template <typename T>
 class CQRRPT
 #ifdef RLB200_WITH_RANDLAPACK
@@ -340,14 +343,16 @@ class CQRRPT
 #endif
 {
 public:
-    CQRRPT(bool time_subroutines, T ep) : timing(time_subroutines), eps(ep), rank(0), nnz(2), ctx_(&default_context()) {}
-    CQRRPT(Context& c, bool time_subroutines, T ep) : timing(time_subroutines), eps(ep), rank(0), nnz(2), ctx_(&c) {}
+    using Subroutines = CQRRPTSubroutines;
+    CQRRPT(bool time_subroutines, T ep) : timing(time_subroutines), eps(ep), rank(0), nnz(2), qrcp(Subroutines::geqp3), ctx_(&default_context()) {}
+    CQRRPT(Context& c, bool time_subroutines, T ep) : timing(time_subroutines), eps(ep), rank(0), nnz(2), qrcp(Subroutines::geqp3), ctx_(&c) {}
     virtual ~CQRRPT() {}
     // A (m x n, lda) <- Q; R (ldr >= n): rank x n; J: n 1-based pivots (rl_cqrrpt.hh:146-156)
     int call(int64_t m, int64_t n, T* A, int64_t lda, T* R, int64_t ldr, int64_t* J, T d_factor, state_t& state) RLB200_OVERRIDE {
         uint32_t w[6]; state_to_words(state, w);
         int64_t r = 0;
         if (timing) ctx_->phase_timing(true);
+        ctx_->check(rlb200_set_cqrrpt_qrcp(ctx_->get(), (int)qrcp));
         int rc = ctx_->check(detail::abi<T>::cqrrpt_host(ctx_->get(), m, n, A, lda, R, ldr, J, d_factor, eps, nnz, &r, w));
         if (timing) { times = ctx_->phase_times(); ctx_->phase_timing(false); }
         words_to_state(w, state);
@@ -359,6 +364,7 @@ public:
     int64_t rank;
     std::vector<long> times;   // 8 entries when `timing` (rl_cqrrpt.hh:371-384)
     int64_t nnz;
+    Subroutines::QRCP qrcp;    // QRCP of the sketch: geqp3 (default) or bqrrp (rl_cqrrpt.hh:230-247)
 private:
     Context* ctx_;
 };

@@ -122,6 +122,11 @@ RLB200_API int rlb200_set_phase_timing(rlb200_ctx* ctx, int on);
  * constructor default (machine epsilon of the working type).  Applies to the following rlb200_bqrrp_* calls on this context.  The fields
  * `internal_nb` and `apply_trans_q` (:138, :149) select LAPACK blockings of the same factorization and have no counterpart here. */
 RLB200_API int rlb200_set_bqrrp_tol(rlb200_ctx* ctx, double tol);
+/* CQRRPT's public `qrcp` field (rl_cqrrpt.hh:41, used at :230-247): the QRCP of the sketch by lapack::geqp3 (default) or by BQRRP with the
+ * reference's block ratio (n <= 2000: 1, n <= 8000: 1/2, else 1/32; BQRRP(false, n * ratio).call(d, n, A_hat, d, 1.0, tau, J, state) - the RNG
+ * state advances through BQRRP's own sketch).  hqrrp is not offered (RLB200_ERR_UNSUPPORTED).  Applies to the following rlb200_cqrrpt_* calls. */
+enum { RLB200_CQRRPT_QRCP_GEQP3 = 0, RLB200_CQRRPT_QRCP_BQRRP = 1 };
+RLB200_API int rlb200_set_cqrrpt_qrcp(rlb200_ctx* ctx, int qrcp);
 RLB200_API int rlb200_get_phase_times(rlb200_ctx* ctx, long long* out_us, int cap);
 
 /* ---- device memory helpers for host-pointer callers (the C++ adapters in RandLAPACK_B200.hh stage through these so that

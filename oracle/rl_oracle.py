@@ -503,10 +503,10 @@ def col_swap(A, idx):
 
 
 class CQRRPT:
-    """RandLAPACK::CQRRPT(timing, eps); fields nnz (=2), rank.  qrcp = geqp3."""
+    """RandLAPACK::CQRRPT(timing, eps); fields nnz (=2), rank, qrcp ('geqp3' default | 'bqrrp', rl_cqrrpt.hh:230-244)."""
 
     def __init__(self, eps, nnz=2):
-        self.eps, self.nnz, self.rank = eps, nnz, None
+        self.eps, self.nnz, self.rank, self.qrcp = eps, nnz, None, "geqp3"
 
     def call(self, A, d_factor, state: RNGState, R=None):
         """-> (rc, Q (m x n, first rank columns meaningful), R (n x n), J (1-based), next state)."""
@@ -522,7 +522,12 @@ class CQRRPT:
         A_hat, state = sketch_sparse_left(d, m, self.nnz, d, A, state)              # :214-221
         geqp3, trsm_, potrf = get_lapack_funcs(("geqp3",), (A_hat,))[0], get_blas_funcs(("trsm",), (A,))[0], \
             get_lapack_funcs(("potrf",), (A,))[0]
-        A_hat, jpvt, tau, _, info = geqp3(A_hat)                                    # :247
+        if self.qrcp == "bqrrp":                                                    # :232-244
+            ratio = 1.0 if n <= 2000 else (0.5 if n <= 8000 else 1.0 / 32.0)
+            bq = BQRRP(int(dt.type(n) * dt.type(ratio)))
+            _, A_hat, tau, jpvt, state = bq.call(A_hat, 1.0, state)
+        else:
+            A_hat, jpvt, tau, _, info = geqp3(A_hat)                                # :247
         J[:] = jpvt
         if not A_hat[0, 0]:                                                         # :256
             return 0, A, R, J, state

@@ -575,10 +575,16 @@ class RSVD:
 
 class CQRRPT:
     """RandLAPACK::CQRRPT(time_subroutines, eps) (rl_cqrrpt.hh:45-146); public fields nnz (SASO non-zeros per column, default 2), rank.
-    qrcp is fixed to the reference's default (geqp3)."""
+    qrcp: "geqp3" (the reference's default) or "bqrrp" (rl_cqrrpt.hh:41, 230-244); hqrrp is not offered."""
 
     def __init__(self, time_subroutines=False, eps=None):
-        self.timing, self.eps, self.nnz, self.rank = time_subroutines, eps, 2, None
+        self.timing, self.eps, self.nnz, self.rank, self.qrcp = time_subroutines, eps, 2, None, "geqp3"
+
+    def _set_qrcp(self, ctx):
+        kinds = {"geqp3": _capi.CQRRPT_QRCP_GEQP3, "bqrrp": _capi.CQRRPT_QRCP_BQRRP}
+        if self.qrcp not in kinds:
+            raise Error(_capi.ERR_UNSUPPORTED, f"CQRRPT qrcp {self.qrcp!r}: geqp3 and bqrrp are offered")
+        ctx.check(ctx._lib.rlb200_set_cqrrpt_qrcp(ctx._h, kinds[self.qrcp]))
 
     def _eps(self, dtype):
         torch = _torch()
@@ -596,6 +602,7 @@ class CQRRPT:
         rank = ctypes.c_int64(0)
         w = state.words()
         fn = getattr(ctx._lib, f"rlb200_cqrrpt_{_suffix(A.dtype)}_dev")
+        self._set_qrcp(ctx)
         rc = ctx.check(fn(ctx._h, m, n, A.data_ptr(), _ld(A), R.data_ptr(), _ld(R), J.data_ptr(), d_factor, self._eps(A.dtype), self.nnz,
                           ctypes.byref(rank), w))
         state.assign(w)
@@ -612,6 +619,7 @@ class CQRRPT:
         rank = ctypes.c_int64(0)
         w = state.words()
         fn = getattr(ctx._lib, f"rlb200_cqrrpt_{_suffix(A_host.dtype)}_host")
+        self._set_qrcp(ctx)
         rc = ctx.check(fn(ctx._h, m, n, A_host.data_ptr(), _ld(A_host), R.data_ptr(), _ld(R), J.data_ptr(), d_factor,
                           self._eps(A_host.dtype), self.nnz, ctypes.byref(rank), w))
         state.assign(w)

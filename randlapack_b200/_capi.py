@@ -37,6 +37,7 @@ class Revd2Opts(ctypes.Structure):
 
 
 UPLO_UPPER, UPLO_LOWER = 0, 1
+CQRRPT_QRCP_GEQP3, CQRRPT_QRCP_BQRRP = 0, 1
 
 ALLREDUCE_FN = ctypes.CFUNCTYPE(c_int, c_vp, c_vp, c_i64, c_i32, c_vp)
 
@@ -83,6 +84,7 @@ SIGNATURES = {
     "rlb200_set_shard_rank": (c_int, [c_vp, c_int, c_int]),
     "rlb200_set_phase_timing": (c_int, [c_vp, c_int]),
     "rlb200_set_bqrrp_tol": (c_int, [c_vp, ctypes.c_double]),
+    "rlb200_set_cqrrpt_qrcp": (c_int, [c_vp, c_int]),
     "rlb200_get_phase_times": (c_int, [c_vp, c_vp, c_int]),
     "rlb200_comm_unique_id": (c_int, [c_vp]),
     "rlb200_comm_init": (c_int, [c_vp, c_int, c_int, c_vp]),

@@ -191,6 +191,15 @@ int rlb200_set_fp64_engine(rlb200_ctx* ctx, int engine) {
     ctx->fp64_engine = engine;
     return 0;
 }
+int rlb200_set_cqrrpt_qrcp(rlb200_ctx* ctx, int qrcp) {
+    CTX_OK(ctx);
+    if (qrcp != RLB200_CQRRPT_QRCP_GEQP3 && qrcp != RLB200_CQRRPT_QRCP_BQRRP) {
+        ctx->err = "CQRRPT qrcp: geqp3 and bqrrp are offered (hqrrp is not)";
+        return RLB200_ERR_UNSUPPORTED;
+    }
+    ctx->cqrrpt_qrcp = qrcp;
+    return 0;
+}
 int rlb200_set_bqrrp_tol(rlb200_ctx* ctx, double tol) {
     CTX_OK(ctx);
     RLB_REQUIRE(ctx, tol >= 0.0);

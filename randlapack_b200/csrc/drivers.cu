@@ -699,8 +699,18 @@ int cqrrpt_call(Ctx* ctx, int64_t m, int64_t n, T* A, int64_t lda, T* R, int64_t
     // SASO (:214-221); state <- S.next_state
     RLB_CHECK(sketch_sparse_left<T>(ctx, d, mg, nnz, d, n, m, (T)1, 0, 0, A, lda, (T)0, A_hat, d, state));
     t_saso = pt.lap();
-    // QRCP of the sketch (:247)
-    {
+    // QRCP of the sketch: geqp3 (:247) or BQRRP with the reference's block ratio (:232-244)
+    if (ctx->cqrrpt_qrcp == RLB200_CQRRPT_QRCP_BQRRP) {
+        if (sharded) { ctx->err = "CQRRPT with qrcp = bqrrp is not offered on a row-sharded context"; return RLB200_ERR_UNSUPPORTED; }
+        const T ratio = n <= 2000 ? (T)1 : (n <= 8000 ? (T)0.5 : (T)1 / (T)32);
+        const int64_t bsz = (int64_t)((T)n * ratio);
+        int64_t rank_b = 0;
+        const double tol_saved = ctx->bqrrp_tol;
+        ctx->bqrrp_tol = 0.0;                                                                  // a fresh BQRRP object: tol = eps
+        const int rcb = bqrrp_call<T>(ctx, d, n, A_hat, d, (T)1, bsz, RLB200_QRCP_LUQR, RLB200_QRTALL_GEQRF, tau, J_dev, &rank_b, state);
+        ctx->bqrrp_tol = tol_saved;
+        if (rcb < 0) return rcb;
+    } else {
         ArenaScope as2(ctx);
         void* ws = arena_push(ctx, qrcp_ws_bytes(n)); RLB_ALLOC(ctx, ws);
         RLB_CHECK(qr_small<T>(ctx, true, d, n, A_hat, d, J_dev, tau, ws));

@@ -276,3 +276,32 @@ def test_phase_times_vectors(ctx):
         assert len(t) == 10 and t[-1] > 0 and sum(t[:-1]) == t[-1]
     finally:
         ctx.phase_timing(False)
+
+
+@pytest.mark.parametrize("shape", [(3000, 200, 1e3, 1.5), (20000, 300, 1e6, 2.0)])
+def test_cqrrpt_qrcp_bqrrp_vs_oracle(ctx, shape):
+    """CQRRPT's `qrcp` field = bqrrp (rl_cqrrpt.hh:41, 232-244: the QRCP of the sketch by BQRRP(false, n * ratio), which draws its own sketch from
+    the state): rank, pivots and the advanced state exact, R 1e-9, the reference's eps^0.75 measures - against the oracle, itself pinned to
+    the compiled reference (tests/test_oracle_qr.py::test_cqrrpt_qrcp_bqrrp)."""
+    m, n, cond, df = shape
+    A, st = O.gen_poly_mat(m, n, n, cond, 2.0, O.RNGState(0))
+    alg = rl.CQRRPT(False, None)
+    alg.qrcp = "bqrrp"
+    Ad = dev(A)
+    s = rl.RNGState(st.key, st.counter)
+    rc, R, J = alg.call(ctx, Ad, df, s)
+    o = O.CQRRPT(float(np.finfo(np.float64).eps) ** 0.85, 2)
+    o.qrcp = "bqrrp"
+    rc2, Q2, R2, J2, st2 = o.call(A, df, O.RNGState(st.key, st.counter))
+    assert (rc, alg.rank) == (rc2, o.rank)
+    assert list(s.words()) == list(st2.words())
+    J, R, Q = J.cpu().numpy(), host(R), host(Ad)
+    assert np.array_equal(J, J2)
+    k = alg.rank
+    assert np.abs(np.triu(R[:k]) - np.triu(R2[:k])).max() <= 1e-9 * np.abs(R2).max()
+    e = qr_invariants(A, Q, R, J, k)
+    assert max(e) <= np.finfo(np.float64).eps ** 0.75, e
+    alg.qrcp = "hqrrp"
+    with pytest.raises(rl.Error):
+        alg.call(ctx, dev(A), df, rl.RNGState(0))
+    ctx.check(ctx._lib.rlb200_set_cqrrpt_qrcp(ctx._h, 0))

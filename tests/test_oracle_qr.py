@@ -108,3 +108,18 @@ def test_bqrrp_tol_field():
         r = min(rank, 70)
         assert np.array_equal(J[:r], J2[:r])
         assert np.abs(np.triu(F)[:r] - np.triu(F2)[:r]).max() <= 1e-10 * np.abs(np.diag(F)).max()
+
+
+@pytest.mark.skipif(_ref.ref_lib() is None, reason="compiled reference not present")
+@pytest.mark.parametrize("shape", [(3000, 200, 1e3, 1.5), (2000, 120, 10.0, 1.25)])
+def test_cqrrpt_qrcp_bqrrp(shape):
+    """CQRRPT with qrcp = bqrrp (rl_cqrrpt.hh:41, 232-244): the oracle against the compiled reference with the same field set."""
+    L = _ref.ref_lib()
+    m, n, cond, df = shape
+    A, st = O.gen_poly_mat(m, n, n, cond, 2.0, O.RNGState(0))
+    rc, rank, Q, Rm, J, st2 = _ref.ref_cqrrpt(L, A, df, list(st.words()), None, 2, qrcp=1)
+    alg = O.CQRRPT(float(np.finfo(np.float64).eps) ** 0.85, 2)
+    alg.qrcp = "bqrrp"
+    rc2, Q2, R2, J2, st3 = alg.call(A, df, st)
+    assert (rc, rank) == (rc2, alg.rank) and list(st3.words()) == st2 and np.array_equal(J, J2)
+    assert np.abs(np.triu(Rm) - np.triu(R2)).max() <= 1e-12 * np.abs(Rm).max()
