@@ -344,8 +344,8 @@ class CQRRPT
 {
 public:
     using Subroutines = CQRRPTSubroutines;
-    CQRRPT(bool time_subroutines, T ep) : timing(time_subroutines), eps(ep), rank(0), nnz(2), qrcp(Subroutines::geqp3), ctx_(&default_context()) {}
-    CQRRPT(Context& c, bool time_subroutines, T ep) : timing(time_subroutines), eps(ep), rank(0), nnz(2), qrcp(Subroutines::geqp3), ctx_(&c) {}
+    CQRRPT(bool time_subroutines, T ep) : timing(time_subroutines), eps(ep), rank(0), nnz(2), qrcp(Subroutines::geqp3), orthogonalization(false), ctx_(&default_context()) {}
+    CQRRPT(Context& c, bool time_subroutines, T ep) : timing(time_subroutines), eps(ep), rank(0), nnz(2), qrcp(Subroutines::geqp3), orthogonalization(false), ctx_(&c) {}
     virtual ~CQRRPT() {}
     // A (m x n, lda) <- Q; R (ldr >= n): rank x n; J: n 1-based pivots (rl_cqrrpt.hh:146-156)
     int call(int64_t m, int64_t n, T* A, int64_t lda, T* R, int64_t ldr, int64_t* J, T d_factor, state_t& state) RLB200_OVERRIDE {
@@ -353,6 +353,7 @@ public:
         int64_t r = 0;
         if (timing) ctx_->phase_timing(true);
         ctx_->check(rlb200_set_cqrrpt_qrcp(ctx_->get(), (int)qrcp));
+        ctx_->check(rlb200_set_cqrrpt_orthogonalization(ctx_->get(), orthogonalization ? 1 : 0));
         int rc = ctx_->check(detail::abi<T>::cqrrpt_host(ctx_->get(), m, n, A, lda, R, ldr, J, d_factor, eps, nnz, &r, w));
         if (timing) { times = ctx_->phase_times(); ctx_->phase_timing(false); }
         words_to_state(w, state);
@@ -365,6 +366,7 @@ public:
     std::vector<long> times;   // 8 entries when `timing` (rl_cqrrpt.hh:371-384)
     int64_t nnz;
     Subroutines::QRCP qrcp;    // QRCP of the sketch: geqp3 (default) or bqrrp (rl_cqrrpt.hh:230-247)
+    bool orthogonalization;    // rl_cqrrpt.hh:139-142
 private:
     Context* ctx_;
 };

@@ -127,6 +127,11 @@ RLB200_API int rlb200_set_bqrrp_tol(rlb200_ctx* ctx, double tol);
  * state advances through BQRRP's own sketch).  hqrrp is not offered (RLB200_ERR_UNSUPPORTED).  Applies to the following rlb200_cqrrpt_* calls. */
 enum { RLB200_CQRRPT_QRCP_GEQP3 = 0, RLB200_CQRRPT_QRCP_BQRRP = 1 };
 RLB200_API int rlb200_set_cqrrpt_qrcp(rlb200_ctx* ctx, int qrcp);
+/* CQRRPT's public `orthogonalization` field (rl_cqrrpt.hh:139-142, 343-368): R keeps the Cholesky factor (the preconditioning is not undone)
+ * and, when rank < n, the trailing n - rank columns of A are completed to an orthonormal set: Gaussian columns (DenseDist(m, n - rank) drawn
+ * at the current state, which - as in the reference - does not advance), projected against Q and orthogonalized by Householder QR.
+ * n - rank <= 256, single shard. */
+RLB200_API int rlb200_set_cqrrpt_orthogonalization(rlb200_ctx* ctx, int on);
 RLB200_API int rlb200_get_phase_times(rlb200_ctx* ctx, long long* out_us, int cap);
 
 /* ---- device memory helpers for host-pointer callers (the C++ adapters in RandLAPACK_B200.hh stage through these so that

@@ -215,10 +215,11 @@ static int sketch_dense_impl(bool left, int64_t S_rows, int64_t S_cols, int fami
 // CQRRPT (RandLAPACK/drivers/rl_cqrrpt.hh:146-391) with the default subroutines (geqp3) unless qrcp says otherwise
 template <typename T>
 static int cqrrpt_impl(int64_t m, int64_t n, T* A, int64_t lda, T* R, int64_t ldr, int64_t* J, T d_factor, T eps, int64_t nnz, int qrcp,
-                       int64_t* rank, uint32_t state[6]) {
+                       int64_t* rank, uint32_t state[6], int orthogonalization = 0) {
     RL_TRY
     RandLAPACK::CQRRPT<T, RNG> alg(false, eps);
     alg.nnz = nnz;
+    alg.orthogonalization = orthogonalization != 0;
     alg.qrcp = qrcp == 1 ? RandLAPACK::CQRRPTSubroutines::QRCP::bqrrp
              : qrcp == 2 ? RandLAPACK::CQRRPTSubroutines::QRCP::hqrrp : RandLAPACK::CQRRPTSubroutines::QRCP::geqp3;
     State st = load_state(state);
@@ -419,6 +420,10 @@ int rlref_mat_gen_f32(int type, int64_t m, int64_t n, int64_t rank, float cond, 
     int rlref_cqrrpt_##SUF(int64_t m, int64_t n, T* A, int64_t lda, T* R, int64_t ldr, int64_t* J, T d_factor, T eps, int64_t nnz,         \
                            int qrcp, int64_t* rank, uint32_t state[6]) {                                                                   \
         return cqrrpt_impl<T>(m, n, A, lda, R, ldr, J, d_factor, eps, nnz, qrcp, rank, state);                                             \
+    }                                                                                                                                     \
+    int rlref_cqrrpt_orth_##SUF(int64_t m, int64_t n, T* A, int64_t lda, T* R, int64_t ldr, int64_t* J, T d_factor, T eps, int64_t nnz,    \
+                                int qrcp, int64_t* rank, uint32_t state[6]) {                                                              \
+        return cqrrpt_impl<T>(m, n, A, lda, R, ldr, J, d_factor, eps, nnz, qrcp, rank, state, 1);                                          \
     }                                                                                                                                     \
     int rlref_cqrrt_##SUF(int64_t m, int64_t n, T* A, int64_t lda, T* R, int64_t ldr, T d_factor, T eps, int64_t nnz, int orthogonalization,     \
                           int compute_Q, uint32_t state[6]) {                                                                              \

@@ -506,7 +506,7 @@ class CQRRPT:
     """RandLAPACK::CQRRPT(timing, eps); fields nnz (=2), rank, qrcp ('geqp3' default | 'bqrrp', rl_cqrrpt.hh:230-244)."""
 
     def __init__(self, eps, nnz=2):
-        self.eps, self.nnz, self.rank, self.qrcp = eps, nnz, None, "geqp3"
+        self.eps, self.nnz, self.rank, self.qrcp, self.orthogonalization = eps, nnz, None, "geqp3", False
 
     def call(self, A, d_factor, state: RNGState, R=None):
         """-> (rc, Q (m x n, first rank columns meaningful), R (n x n), J (1-based), next state)."""
@@ -558,7 +558,18 @@ class CQRRPT:
                     break
         self.rank = new_rank                                                        # :339
         A[:, :new_rank] = trsm_(1.0, _F(R[:new_rank, :new_rank]), _F(A[:, :new_rank]), side=1, lower=0)   # :342
-        R[:new_rank, :] = R[:new_rank, :] @ np.triu(A_hat[:n, :n])                  # trmm :349
+        if not self.orthogonalization:
+            R[:new_rank, :] = R[:new_rank, :] @ np.triu(A_hat[:n, :n])              # trmm :345
+        elif new_rank != n:                                                         # complete the orthonormal set (:347-368)
+            cols = n - new_rank
+            G, _ = fill_dense(m, cols, state, dtype=dt)          # (:351 discards fill_dense's return value: the state does not advance)
+            G = _F(G)
+            Qr = _F(A[:, :new_rank])
+            temp = _gemm(Qr, G, ta=True)
+            G = _F(G - Qr @ temp)
+            geqrf, orgqr = get_lapack_funcs(("geqrf", "orgqr"), (G,))
+            qr, tau_o, _, _ = geqrf(G)
+            A[:, new_rank:] = orgqr(qr, tau_o)[0]
         return 0, A, R, J, state
 
 

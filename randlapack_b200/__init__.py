@@ -579,12 +579,14 @@ class CQRRPT:
 
     def __init__(self, time_subroutines=False, eps=None):
         self.timing, self.eps, self.nnz, self.rank, self.qrcp = time_subroutines, eps, 2, None, "geqp3"
+        self.orthogonalization = False      # rl_cqrrpt.hh:139-142: R keeps the Cholesky factor, Q is completed to n orthonormal columns
 
     def _set_qrcp(self, ctx):
         kinds = {"geqp3": _capi.CQRRPT_QRCP_GEQP3, "bqrrp": _capi.CQRRPT_QRCP_BQRRP}
         if self.qrcp not in kinds:
             raise Error(_capi.ERR_UNSUPPORTED, f"CQRRPT qrcp {self.qrcp!r}: geqp3 and bqrrp are offered")
         ctx.check(ctx._lib.rlb200_set_cqrrpt_qrcp(ctx._h, kinds[self.qrcp]))
+        ctx.check(ctx._lib.rlb200_set_cqrrpt_orthogonalization(ctx._h, int(bool(self.orthogonalization))))
 
     def _eps(self, dtype):
         torch = _torch()

@@ -85,6 +85,7 @@ SIGNATURES = {
     "rlb200_set_phase_timing": (c_int, [c_vp, c_int]),
     "rlb200_set_bqrrp_tol": (c_int, [c_vp, ctypes.c_double]),
     "rlb200_set_cqrrpt_qrcp": (c_int, [c_vp, c_int]),
+    "rlb200_set_cqrrpt_orthogonalization": (c_int, [c_vp, c_int]),
     "rlb200_get_phase_times": (c_int, [c_vp, c_vp, c_int]),
     "rlb200_comm_unique_id": (c_int, [c_vp]),
     "rlb200_comm_init": (c_int, [c_vp, c_int, c_int, c_vp]),

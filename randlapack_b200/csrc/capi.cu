@@ -191,6 +191,7 @@ int rlb200_set_fp64_engine(rlb200_ctx* ctx, int engine) {
     ctx->fp64_engine = engine;
     return 0;
 }
+int rlb200_set_cqrrpt_orthogonalization(rlb200_ctx* ctx, int on) { CTX_OK(ctx); ctx->cqrrpt_orth = on != 0; return 0; }
 int rlb200_set_cqrrpt_qrcp(rlb200_ctx* ctx, int qrcp) {
     CTX_OK(ctx);
     if (qrcp != RLB200_CQRRPT_QRCP_GEQP3 && qrcp != RLB200_CQRRPT_QRCP_BQRRP) {

@@ -78,6 +78,7 @@ struct Ctx {
     // rl_bqrrp.hh:582-584), microseconds, recorded only when phase_timing is set (each lap synchronises the stream, like the reference's
     // steady_clock around synchronous BLAS calls)
     bool phase_timing = false;
+    bool cqrrpt_orth = false;    // CQRRPT::orthogonalization (rl_cqrrpt.hh:139-142)
     int cqrrpt_qrcp = 0;         // CQRRPT::qrcp (rl_cqrrpt.hh:41): 0 = geqp3 (default), 1 = bqrrp
     double bqrrp_tol = 0.0;      // BQRRP::tol (rl_bqrrp.hh:141): 0 = the constructor default, eps of the working type
     std::vector<long long> phase_us;

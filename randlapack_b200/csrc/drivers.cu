@@ -760,6 +760,26 @@ int cqrrpt_call(Ctx* ctx, int64_t m, int64_t n, T* A, int64_t lda, T* R, int64_t
     }
     *rank_out = new_rank;                                                                     // :339
     RLB_CHECK(tall_right_solve<T>(ctx, m, new_rank, R, ldr, A, lda));                         // :342
+    if (ctx->cqrrpt_orth) {
+        // orthogonalization mode (:343-368): R stays the Cholesky factor; the trailing columns complete the orthonormal set
+        const int64_t cols = n - new_rank;
+        if (cols > 0) {
+            if (sharded) { ctx->err = "CQRRPT orthogonalization mode with rank < n is not offered on a row-sharded context"; return RLB200_ERR_UNSUPPORTED; }
+            RLB_REQUIRE(ctx, cols <= 256 && m > cols);
+            T* Gc = as.take<T>((size_t)m * cols); RLB_ALLOC(ctx, Gc);
+            T* tmp = as.take<T>((size_t)std::max<int64_t>(new_rank, 1) * cols); RLB_ALLOC(ctx, tmp);
+            uint32_t st_tmp[6];
+            std::memcpy(st_tmp, state, sizeof st_tmp);                                          // :351: fill_dense's next state is discarded
+            RLB_CHECK(fill_dense_unpacked<T>(ctx, m, cols, RLB200_FAMILY_GAUSSIAN, RLB200_AXIS_LONG, RLB200_LAYOUT_NATURAL, m, cols, 0, 0, Gc, st_tmp));
+            if (new_rank > 0) {
+                RLB_CUDA_OK(ctx, cudaMemsetAsync(tmp, 0, sizeof(T) * new_rank * cols, ctx->stream));
+                RLB_CHECK(gemm_tn<T>(ctx, m, new_rank, cols, 1.0, A, lda, Gc, m, 0.0, tmp, new_rank, 0));             // Q^T G  (:357)
+                RLB_CHECK(gemm_nn<T>(ctx, m, cols, new_rank, -1.0, A, lda, tmp, new_rank, 1.0, Gc, m));               // G - Q Q^T G  (:359)
+            }
+            RLB_CHECK(hqrq<T>(ctx, m, cols, Gc));                                                                     // geqrf + orgqr  (:364-365)
+            RLB_CUDA_OK(ctx, cudaMemcpy2DAsync(A + new_rank * lda, lda * sizeof(T), Gc, m * sizeof(T), m * sizeof(T), cols, cudaMemcpyDeviceToDevice, ctx->stream));
+        }
+    } else
     // R <- R[0:new_rank, 0:n] * triu(A_hat[0:n, 0:n])  (trmm :349)
     if (new_rank > 0) {
         T* U = as.take<T>((size_t)n * n); RLB_ALLOC(ctx, U);

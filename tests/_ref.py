@@ -136,7 +136,7 @@ def ref_sketch_dense(lib, left, S_rows, S_cols, d, A, seed6, family=0, axis=0, a
     return rc, B, list(st)
 
 
-def ref_cqrrpt(lib, A, d_factor, seed6, eps=None, nnz=2, qrcp=0):
+def ref_cqrrpt(lib, A, d_factor, seed6, eps=None, nnz=2, qrcp=0, orthogonalization=False):
     """RandLAPACK::CQRRPT::call via the compiled reference -> (rc, rank, Q m x n [first rank cols valid], R n x n, J, state)."""
     m, n = A.shape
     dt = A.dtype
@@ -147,7 +147,7 @@ def ref_cqrrpt(lib, A, d_factor, seed6, eps=None, nnz=2, qrcp=0):
     st = (u32 * 6)(*seed6)
     ft = _ft(dt)
     eps = float(np.finfo(dt).eps) ** 0.85 if eps is None else eps
-    f = getattr(lib, f"rlref_cqrrpt_{_suf(dt)}")
+    f = getattr(lib, f"rlref_cqrrpt_{'orth_' if orthogonalization else ''}{_suf(dt)}")
     f.argtypes = [i64, i64, ctypes.c_void_p, i64, ctypes.c_void_p, i64, ctypes.c_void_p, ft, ft, i64, ctypes.c_int, ctypes.POINTER(i64),
                   ctypes.POINTER(u32)]
     rc = f(m, n, Q.ctypes.data, m, R.ctypes.data, n, J.ctypes.data, d_factor, eps, nnz, qrcp, ctypes.byref(rank), st)

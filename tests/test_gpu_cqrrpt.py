@@ -305,3 +305,32 @@ def test_cqrrpt_qrcp_bqrrp_vs_oracle(ctx, shape):
     with pytest.raises(rl.Error):
         alg.call(ctx, dev(A), df, rl.RNGState(0))
     ctx.check(ctx._lib.rlb200_set_cqrrpt_qrcp(ctx._h, 0))
+
+
+@pytest.mark.parametrize("shape", [(3000, 200, 120, 1e3, 1.5), (2000, 120, 120, 10.0, 1.25), (20000, 150, 60, 1e2, 2.0)])
+def test_cqrrpt_orthogonalization_mode_vs_oracle(ctx, shape):
+    """CQRRPT's `orthogonalization` field (rl_cqrrpt.hh:139-142, 343-368) against the oracle (pinned to the compiled reference in
+    tests/test_oracle_qr.py): rank, leading pivots and state exact; R (the Cholesky factor, preconditioning not undone) 1e-9; all n columns
+    of Q orthonormal, the first `rank` ones equal to the oracle's up to sign and the completed ones orthogonal to them."""
+    m, n, rk, cond, df = shape
+    A, st = O.gen_poly_mat(m, n, rk, cond, 2.0, O.RNGState(0))
+    alg = rl.CQRRPT(False, None)
+    alg.orthogonalization = True
+    Ad = dev(A)
+    s = rl.RNGState(st.key, st.counter)
+    rc, R, J = alg.call(ctx, Ad, df, s)
+    o = O.CQRRPT(float(np.finfo(np.float64).eps) ** 0.85, 2)
+    o.orthogonalization = True
+    rc2, Q2, R2, J2, st2 = o.call(A, df, O.RNGState(st.key, st.counter))
+    k = o.rank
+    assert (rc, alg.rank) == (rc2, k) and list(s.words()) == list(st2.words())
+    J, R, Q = J.cpu().numpy(), host(R), host(Ad)
+    assert np.array_equal(J[:k], J2[:k])
+    assert np.abs(np.triu(R[:k, :k]) - np.triu(R2[:k, :k])).max() <= 1e-9 * np.abs(R2).max()
+    assert np.linalg.norm(Q.T @ Q - np.eye(n)) <= 1e-11
+    assert np.abs(np.abs(Q[:, :k]) - np.abs(Q2[:, :k])).max() <= 1e-8
+    if k < n:      # same Gaussian block, same projection: the completed columns span the oracle's completion
+        P1, P2 = Q[:, k:] @ Q[:, k:].T, Q2[:, k:] @ Q2[:, k:].T
+        v = np.random.default_rng(0).standard_normal((m, 3))
+        assert np.abs(P1 @ v - P2 @ v).max() <= 1e-9 * np.linalg.norm(v)      # (the leading Q itself agrees to ~1e-9: CholQR of a sketch-preconditioned matrix)
+    ctx.check(ctx._lib.rlb200_set_cqrrpt_orthogonalization(ctx._h, 0))

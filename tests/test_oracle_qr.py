@@ -123,3 +123,21 @@ def test_cqrrpt_qrcp_bqrrp(shape):
     rc2, Q2, R2, J2, st3 = alg.call(A, df, st)
     assert (rc, rank) == (rc2, alg.rank) and list(st3.words()) == st2 and np.array_equal(J, J2)
     assert np.abs(np.triu(Rm) - np.triu(R2)).max() <= 1e-12 * np.abs(Rm).max()
+
+
+@pytest.mark.skipif(_ref.ref_lib() is None, reason="compiled reference not present")
+@pytest.mark.parametrize("shape", [(3000, 200, 120, 1e3, 1.5), (2000, 120, 120, 10.0, 1.25), (4000, 150, 60, 1e2, 2.0)])
+def test_cqrrpt_orthogonalization_mode(shape):
+    """CQRRPT::orthogonalization (rl_cqrrpt.hh:139-142, 343-368): R keeps the Cholesky factor, rank-deficient inputs get their Q completed to n
+    orthonormal columns from a Gaussian block drawn at the (not advanced) state.  Oracle vs the compiled reference."""
+    L = _ref.ref_lib()
+    m, n, rk, cond, df = shape
+    A, st = O.gen_poly_mat(m, n, rk, cond, 2.0, O.RNGState(0))
+    rc, rank, Q, Rm, J, st2 = _ref.ref_cqrrpt(L, A, df, list(st.words()), None, 2, qrcp=0, orthogonalization=True)
+    alg = O.CQRRPT(float(np.finfo(np.float64).eps) ** 0.85, 2)
+    alg.orthogonalization = True
+    rc2, Q2, R2, J2, st3 = alg.call(A, df, st)
+    assert (rc, rank) == (rc2, alg.rank) and list(st3.words()) == st2 and np.array_equal(J[:rank], J2[:rank])
+    assert np.abs(np.triu(Rm[:rank, :rank]) - np.triu(R2[:rank, :rank])).max() <= 1e-11 * np.abs(Rm).max()
+    assert np.abs(np.abs(Q) - np.abs(Q2)).max() <= 1e-10
+    assert np.linalg.norm(Q2.T @ Q2 - np.eye(n)) <= 1e-12
