@@ -382,6 +382,12 @@ __device__ __forceinline__ bool oz_mbar_test(uint32_t bar, uint32_t parity) {
                  : "=r"(done) : "r"(bar), "r"(parity) : "memory");
     return done != 0;
 }
+__device__ __forceinline__ bool oz_mbar_test_cluster(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                 : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    return done != 0;
+}
 // acquire at cluster scope: the data guarded by the barrier may have been written by a peer CTA (distributed shared memory)
 __device__ __forceinline__ void oz_mbar_wait_cluster(uint32_t bar, uint32_t parity) {
     uint32_t done = 0;

@@ -467,33 +467,46 @@ __global__ void __launch_bounds__(Oz2Threads<NG>::N, 1) oz2_kernel(const Oz2Para
         asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}\n" : "=r"(elected));
         long long c_iwait = 0;
         const uint32_t base_lo0 = sbase >> 4;
-        for (int kb = 0; kb < nkb; ++kb) {
-            const int slot = kb % DST;
+        const bool one_stage = (p.dbg_flags & 2048) != 0;      // timing experiments: one stage per issue round
+        for (int kb = 0; kb < nkb;) {
+            const int slot = kb % DST, slot2 = (kb + 1) % DST;
             long long t0 = 0;
             if (p.dbg) t0 = clock64();
+            // up to two stages per issue round (the second only if it is full already): the barrier wait and the proxy fence between two
+            // rounds are serial time in which the tensor pipe only has what is queued
+            bool two = false;
             if (share == 1) {
                 oz_mbar_wait(oz_smem(&bar_full[slot]), (uint32_t)((kb / DST) & 1));
+                if (kb > 0 && kb + 1 < nkb && !one_stage) two = oz_mbar_test(oz_smem(&bar_full[slot2]), (uint32_t)(((kb + 1) / DST) & 1));
+                two = __all_sync(0xffffffffu, two);
                 if (!gram && !(p.dbg_flags & 512)) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // the converters' stores of this stage (see there)
             } else {
                 // the digits of this stage may come from a peer CTA: acquire at cluster scope, then order those generic-proxy stores before the
                 // tensor core's async-proxy reads on the consumer side as well
                 oz_mbar_wait_cluster(oz_smem(&bar_full[slot]), (uint32_t)((kb / DST) & 1));
+                if (kb > 0 && kb + 1 < nkb && !one_stage) two = oz_mbar_test_cluster(oz_smem(&bar_full[slot2]), (uint32_t)(((kb + 1) / DST) & 1));
+                two = __all_sync(0xffffffffu, two);
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             }
             if (p.dbg) c_iwait += clock64() - t0;
             asm volatile("tcgen05.fence::after_thread_sync;");
             if (elected) {
-                const uint32_t lo = base_lo0 + (uint32_t)slot * (uint32_t)(Cfg::STAGE_BYTES >> 4);
-                if (p.dbg_flags & 32) {}      // timing experiment: no MMAs (stages are released at once)
-                else if (sp == SD) oz2_issue_step<SD, SD, TN>(lo, tmem, kb == 0, (p.dbg_flags & 1024) == 0);
-                else oz2_issue_step<SD, (SD > 2 ? SD - 1 : SD), TN>(lo, tmem, kb == 0, (p.dbg_flags & 1024) == 0);
-                if (share == 1)
-                    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(oz_smem(&bar_empty[slot])) : "memory");
-                else
-                    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-                                 ::"r"(oz_smem(&bar_empty[slot])), "h"(cmask) : "memory");
+#pragma unroll 1
+                for (int r = 0; r < (two ? 2 : 1); ++r) {
+                    const int sl = r ? slot2 : slot;
+                    const uint32_t lo = base_lo0 + (uint32_t)sl * (uint32_t)(Cfg::STAGE_BYTES >> 4);
+                    if (p.dbg_flags & 32) {}      // timing experiment: no MMAs (stages are released at once)
+                    else if (sp == SD) oz2_issue_step<SD, SD, TN>(lo, tmem, kb + r == 0, (p.dbg_flags & 1024) == 0);
+                    else oz2_issue_step<SD, (SD > 2 ? SD - 1 : SD), TN>(lo, tmem, kb + r == 0, (p.dbg_flags & 1024) == 0);
+                    if (share == 1)
+                        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(oz_smem(&bar_empty[sl])) : "memory");
+                    else
+                        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                                     ::"r"(oz_smem(&bar_empty[sl])), "h"(cmask) : "memory");
+                }
             }
             __syncwarp();
+            kb += two ? 2 : 1;
         }
         if (elected) asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(oz_smem(&bar_acc)) : "memory");
         if (p.dbg && lane == 0) p.dbg[((int64_t)blockIdx.z * gridDim.x + blockIdx.x) * 8 + 4] = c_iwait;
