@@ -687,10 +687,15 @@ int sketch_dense_left(Ctx* ctx, int64_t S_rows, int64_t S_cols, int family, int 
         pc = std::min<int64_t>((pc / 64) * 64, std::max<int64_t>(m, 1));
         // tcgen05 int8 digit-slice engine for the long contraction: panels of four 16384-row accumulation chunks keep every SM busy
         const bool i8 = ctx->fp64_engine == RLB200_FP64_I8SLICES && m >= 16384 && d >= 64 && n >= 64;
-        if (i8) pc = std::min<int64_t>(std::max<int64_t>(pc, 65536), ((m + 63) / 64) * 64);
+        // (measured at d = 256, 2^22 x 2048 fp64: 65536-row panels 71.2 ms, 131072 67.5, 262144 63.2, 2^20 62.5 - the per-panel launches
+        //  (fill, digit slicing, reduction) amortise; the two panel buffers are kept within 1 GiB)
+        static const int64_t panel_rows_env = getenv("RLB200_DENSE_PANEL_ROWS") ? atoll(getenv("RLB200_DENSE_PANEL_ROWS")) : 0;
+        int64_t panel_rows = panel_rows_env > 0 ? panel_rows_env : 262144;
+        while (panel_rows_env <= 0 && panel_rows > 65536 && 2 * panel_rows * d * (int64_t)sizeof(T) > (1ll << 30)) panel_rows >>= 1;
+        if (i8) pc = std::min<int64_t>(std::max<int64_t>(pc, panel_rows), ((m + 63) / 64) * 64);
         // Fused engine: the DATA matrix is the tall operand that is sliced inside the tensor-core kernel (read once, as fp64 / fp32), the
         // regenerated panels of S^T are the small operand; the kernel then produces (S A)^T, accumulated over the panels in scratch and
-        // transposed into B at the end.  Panels of 65536 rows x d values stay a fraction of L2 for d <= 128 and are 134 MB at d = 256.
+        // transposed into B at the end.
         const bool fused = i8 && ozaki2_tn_ok(ctx, std::min<int64_t>(pc, m), n, d, A, lda * (int64_t)sizeof(T));
         ArenaScope as(ctx);
         T* panel = as.take<T>((size_t)2 * d * pc); if (!panel) return RLB200_ERR_ALLOC;
