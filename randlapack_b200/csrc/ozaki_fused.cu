@@ -945,7 +945,16 @@ static int oz2_cache_reserve(Ctx* ctx, OzCacheEntry& e, size_t n_e, size_t n_s) 
 static void oz2_cache_set(OzCacheEntry& e, const void* ptr, int64_t m, int64_t n, int64_t ld, int64_t L, int elem) {
     e.ptr = ptr; e.m = m; e.n = n; e.ld = ld; e.L = L; e.P = OZ_RAW_P; e.elem = elem; e.valid = true;
 }
-static int64_t oz2_chunk_rows(int64_t m) { return std::min<int64_t>(OZ_CHUNK, ((m + OZ_KB - 1) / OZ_KB) * OZ_KB); }
+// Rows per accumulation chunk of the long-contraction (A^T Y) launches = rows per exponent group of the N side: a CTA runs one chunk of
+// one tile.  OZ_CHUNK = 16384 is the exactness bound of the int32 accumulators: an anti-diagonal sums up to 7 digit pairs x L rows of
+// products <= 2^14, and 7 * 2^14 * 2^14 < 2^31.  Longer chunks are faster on random data (m = 2^21, n = 1024, k = 256: 13.5 ms at 16384 rows,
+// 12.3-12.8 ms at 32768: fewer epilogues and partial sums) but can overflow on adversarial digits, so they stay an experiment
+// (RLB200_OZ2_CHUNK) and are never the default.
+static int64_t oz2_chunk_rows(int64_t m) {
+    static const int64_t chunk_env = getenv("RLB200_OZ2_CHUNK") ? atoll(getenv("RLB200_OZ2_CHUNK")) : 0;
+    const int64_t chunk = chunk_env > 0 ? chunk_env : OZ_CHUNK;
+    return std::min<int64_t>(chunk, ((m + OZ_KB - 1) / OZ_KB) * OZ_KB);
+}
 
 // Raw row exponents, raw column-group exponents and the sums of squares of the constant data matrix of a driver scope, in one sweep
 // (both caches are independent of the digit count: the kernels apply the floor P - 1023 themselves).
