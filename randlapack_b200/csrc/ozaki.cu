@@ -154,31 +154,40 @@ ozaki_mma_kernel(const int8_t* __restrict__ a_tiles, int64_t a_group_stride, con
         asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}\n" : "=r"(elected));
         const uint32_t base_lo0 = sbase >> 4;
         constexpr uint32_t LBO = (uint32_t)(128 >> 4) << 16;      // (start-address field = bits 4..17 of the address: a CTA's window inside a cluster does not start at 0)
-        for (int kb = 0; kb < nkb; ++kb) {
-            const int slot = kb % STAGES;
+        for (int kb = 0; kb < nkb;) {
+            const int slot = kb % STAGES, slot2 = (kb + 1) % STAGES;
             oz_mbar_wait(oz_smem(&bar_full[slot]), (uint32_t)((kb / STAGES) & 1));
+            // up to two stages per issue round (the second only if it has landed already): the barrier wait between two rounds is serial time in
+            // which the tensor pipe only has what is queued
+            bool two = kb > 0 && kb + 1 < nkb && oz_mbar_test(oz_smem(&bar_full[slot2]), (uint32_t)(((kb + 1) / STAGES) & 1));
+            two = __all_sync(0xffffffffu, two);
             if (dbg && kb == 0 && elected) dbg[((int64_t)(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 8 + 2] = clock64();
             asm volatile("tcgen05.fence::after_thread_sync;");
             if (elected) {
-                const uint32_t lo = base_lo0 + (uint32_t)slot * (uint32_t)(Cfg::STAGE_BYTES >> 4);
+#pragma unroll 1
+                for (int r = 0; r < (two ? 2 : 1); ++r) {
+                    const int sl = r ? slot2 : slot;
+                    const uint32_t lo = base_lo0 + (uint32_t)sl * (uint32_t)(Cfg::STAGE_BYTES >> 4);
 #pragma unroll
-                for (int s = 0; s < S; ++s) {
-                    const uint64_t da = HI | (uint64_t)(((lo + (uint32_t)((s * OZ_TILE_A) >> 4)) & 0x3FFFu) | LBO);
+                    for (int s = 0; s < S; ++s) {
+                        const uint64_t da = HI | (uint64_t)(((lo + (uint32_t)((s * OZ_TILE_A) >> 4)) & 0x3FFFu) | LBO);
 #pragma unroll
-                    for (int t0 = 0; t0 < S - s; t0 += 4) {
-                        const int nt = (S - s - t0) < 4 ? (S - s - t0) : 4;      // digit tiles of the second operand in this instruction
-                        const uint32_t idesc = IDESC0 | ((uint32_t)((nt * OZ_BN) >> 3) << 17);
-                        const uint64_t db = HI | (uint64_t)(((lo + (uint32_t)((S * OZ_TILE_A + t0 * OZ_TILE_B) >> 4)) & 0x3FFFu) | LBO);
-                        oz_mma_i8(tmem + (uint32_t)((s + t0) * OZ_BN), da, db, idesc, (kb > 0 || s > 0) ? 1u : 0u);
+                        for (int t0 = 0; t0 < S - s; t0 += 4) {
+                            const int nt = (S - s - t0) < 4 ? (S - s - t0) : 4;      // digit tiles of the second operand in this instruction
+                            const uint32_t idesc = IDESC0 | ((uint32_t)((nt * OZ_BN) >> 3) << 17);
+                            const uint64_t db = HI | (uint64_t)(((lo + (uint32_t)((S * OZ_TILE_A + t0 * OZ_TILE_B) >> 4)) & 0x3FFFu) | LBO);
+                            oz_mma_i8(tmem + (uint32_t)((s + t0) * OZ_BN), da, db, idesc, (kb + r > 0 || s > 0) ? 1u : 0u);
+                        }
                     }
+                    if (cs == 1)
+                        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(oz_smem(&bar_empty[sl])) : "memory");
+                    else
+                        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                                     ::"r"(oz_smem(&bar_empty[sl])), "h"(cmask) : "memory");
                 }
-                if (cs == 1)
-                    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(oz_smem(&bar_empty[slot])) : "memory");
-                else
-                    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-                                 ::"r"(oz_smem(&bar_empty[slot])), "h"(cmask) : "memory");
             }
             __syncwarp();
+            kb += two ? 2 : 1;
         }
         if (elected) asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(oz_smem(&bar_acc)) : "memory");
     }
