@@ -27,6 +27,7 @@
 // QB and RSVD).  A B200 RS/RF/QB needs B200 stabilisers (it asks them for their kind); mixing in a CPU stabiliser is
 // rejected with std::invalid_argument rather than silently falling back to the CPU.
 #pragma once
+#include <algorithm>
 #include <cmath>
 #include <cstdint>
 #include <cstdlib>
@@ -570,10 +571,22 @@ public:
     int call(uplo_t uplo, int64_t m, const T* A, int64_t& k, T tol, std::vector<T>& V, std::vector<T>& eigvals, state_t& state) {
         Context& c = syrf.syps.context();
         rlb200_revd2_opts o = syrf.opts(error_est_p);
-        if (m > 0) { V.resize((size_t)m * m); eigvals.resize((size_t)m); }       // k may grow up to m
-        uint32_t w[6]; state_to_words(state, w);
+        // k doubles until the error estimate passes (up to m): the outputs are sized for 8 k and, if the rank estimate outgrows that
+        // (code 3), the call is repeated from the caller's state with four times the room - the algorithm is deterministic, so the
+        // repeated prefix reproduces itself and V never needs m x m entries up front
+        const int64_t k_in = k;
+        int64_t k_cap = std::min<int64_t>(m, std::max<int64_t>(8 * k_in, 64));
+        uint32_t w[6];
         T err = 0;
-        int rc = c.check(detail::abi<T>::revd2_host(c.get(), uplo_code(uplo), m, A, m, &k, m, tol, V.data(), eigvals.data(), w, &o, &err));
+        int rc = 0;
+        while (true) {
+            state_to_words(state, w);
+            k = k_in;
+            V.resize((size_t)m * k_cap); eigvals.resize((size_t)k_cap);
+            rc = c.check(detail::abi<T>::revd2_host(c.get(), uplo_code(uplo), m, A, m, &k, k_cap, tol, V.data(), eigvals.data(), w, &o, &err));
+            if (rc != 3 || k_cap >= m) break;
+            k_cap = std::min<int64_t>(m, 4 * k_cap);
+        }
         words_to_state(w, state);
         if (rc == 1) throw std::runtime_error("Cholesky decomposition failed.");
         if (rc == 2) throw std::runtime_error("Orthogonalization failed.");

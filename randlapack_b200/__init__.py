@@ -713,16 +713,22 @@ class REVD2:
         torch = _torch()
         assert _is_f(A) and A.shape[0] == A.shape[1] and A.is_cuda != host
         m = A.shape[0]
-        k_cap = m if k_cap is None else k_cap
-        V = empty_f(m, k_cap, A.dtype, A.device)
-        ev = torch.zeros(k_cap, dtype=A.dtype, device=A.device)
-        kk = ctypes.c_int64(k)
+        # without an explicit capacity the outputs are sized for 8 k; if the rank estimate outgrows that (code 3) the call is repeated from
+        # the caller's state with four times the room (deterministic: the repeated prefix reproduces itself)
+        auto, k_cap = k_cap is None, (min(m, max(8 * k, 64)) if k_cap is None else k_cap)
         err = (ctypes.c_double if A.dtype == torch.float64 else ctypes.c_float)(0)
         o = self.syrf._opts(self.error_est_p)
-        w = state.words()
         fn = getattr(ctx._lib, f"rlb200_revd2_{_suffix(A.dtype)}_{'host' if host else 'dev'}")
-        rc = ctx.check(fn(ctx._h, _uplo(uplo), m, A.data_ptr(), _ld(A), ctypes.byref(kk), k_cap, tol, V.data_ptr(), ev.data_ptr(), w,
-                          ctypes.byref(o), ctypes.byref(err)))
+        while True:
+            V = empty_f(m, k_cap, A.dtype, A.device)
+            ev = torch.zeros(k_cap, dtype=A.dtype, device=A.device)
+            kk = ctypes.c_int64(k)
+            w = state.words()
+            rc = ctx.check(fn(ctx._h, _uplo(uplo), m, A.data_ptr(), _ld(A), ctypes.byref(kk), k_cap, tol, V.data_ptr(), ev.data_ptr(), w,
+                              ctypes.byref(o), ctypes.byref(err)))
+            if rc != 3 or not auto or k_cap >= m:
+                break
+            k_cap = min(m, 4 * k_cap)
         state.assign(w)
         self.err = err.value
         return rc, kk.value, V[:, :kk.value], ev[:kk.value]
