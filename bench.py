@@ -667,6 +667,8 @@ def main():
                     "whole_step_frac": i8_ops / (ms_step * 1e-3) / 1e12 / peak,
                     "fp64_equivalent_tflops": ((p + 2) * 2.0 * m_local * n * k + 2.0 * m_local * k * k * (1 + (tn_fold + 1) * gram_frac))
                     / (mma_ms * 1e-3) / 1e12 if mma_ms > 0 else None,
+                    "binding_resource": "L1 data pipe of the SM (tensor-core operand reads 46 % + shared-memory / global LSU traffic 34 % of its peak in "
+                                        "the A*Omega launch: ncu --set full, profiles/ncu_oz3_nn_r2i.txt; DESIGN.md 3b) - not HBM (37 %) and not the tensor pipe",
                     "digits": {"a_omega": S_dig, "u_and_at_y_in_power_iteration_and_gram": S_tn},
                     "digit_pairs": {"a_omega_and_last_at_y": pairs, "u_and_at_y_in_power_iteration_and_gram": pairs_full},
                     "int8_ops_per_step": i8_ops,
