@@ -375,6 +375,15 @@ __device__ __forceinline__ void oz_mbar_wait(uint32_t bar, uint32_t parity) {
                      : "=r"(done) : "r"(bar), "r"(parity) : "memory");
     }
 }
+// the same with a suspend-time hint (ns): the thread is woken when the phase completes, the hint only bounds how long the hardware may keep
+// it suspended before the instruction returns false - fewer re-polls of the barrier word through the shared-memory pipe
+__device__ __forceinline__ void oz_mbar_wait_hint(uint32_t bar, uint32_t parity, uint32_t ns) {
+    uint32_t done = 0;
+    while (!done) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                     : "=r"(done) : "r"(bar), "r"(parity), "r"(ns) : "memory");
+    }
+}
 // non-blocking: has the phase completed?
 __device__ __forceinline__ bool oz_mbar_test(uint32_t bar, uint32_t parity) {
     uint32_t done;
@@ -394,6 +403,13 @@ __device__ __forceinline__ void oz_mbar_wait_cluster(uint32_t bar, uint32_t pari
     while (!done) {
         asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
                      : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    }
+}
+__device__ __forceinline__ void oz_mbar_wait_cluster_hint(uint32_t bar, uint32_t parity, uint32_t ns) {
+    uint32_t done = 0;
+    while (!done) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                     : "=r"(done) : "r"(bar), "r"(parity), "r"(ns) : "memory");
     }
 }
 // long waits (the epilogue warps wait for a whole tile's main loop): back off so that the spinning warps do not take issue slots from

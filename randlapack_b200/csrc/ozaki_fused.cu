@@ -288,6 +288,7 @@ __global__ void __launch_bounds__(Oz2Threads<NG>::N, 1) oz2_kernel(const Oz2Para
             const bool dbg_on = p.dbg != nullptr && tid == 0;
             long long c_wait = 0, c_conv = 0, c_fence = 0, c_load = 0;
             const bool skip_fence = (p.dbg_flags & 4) != 0, skip_math = (p.dbg_flags & 8) != 0;
+            const bool nohint = (p.dbg_flags & 4096) != 0;      // timing experiments: barrier waits without the suspend-time hint
             // L2 prefetch of the tile of K block kb (one 128-byte line per thread: the tile is 64 x 32 elements = 16 KB in fp64): issued
             // several blocks before the register loads, which then find their lines in L2 (~700 cycles) instead of DRAM (> 2000 under load) -
             // the register double buffer alone covers only about one block time (~1200 cycles).  Costs one instruction and no registers.
@@ -319,8 +320,12 @@ __global__ void __launch_bounds__(Oz2Threads<NG>::N, 1) oz2_kernel(const Oz2Para
                 if (dbg_on) t1 = clock64();
                 const int slot = kb % DST;
                 if (kb >= DST) {
-                    if (share == 1) oz_mbar_wait(oz_smem(&bar_empty[slot]), (uint32_t)(((kb / DST) - 1) & 1));
-                    else while (s_free_upto <= kb) {}
+                    if (share == 1) {
+                        if (nohint) oz_mbar_wait(oz_smem(&bar_empty[slot]), (uint32_t)(((kb / DST) - 1) & 1));
+                        else oz_mbar_wait_hint(oz_smem(&bar_empty[slot]), (uint32_t)(((kb / DST) - 1) & 1), 20000u);
+                    } else {
+                        while (s_free_upto <= kb) { if (!nohint) __nanosleep(20); }       // (every poll is a shared-memory access of 8 warps)
+                    }
                 }
                 if (dbg_on) t2 = clock64();
                 unsigned char* dst = oz2_smem_raw + slot * Cfg::STAGE_BYTES + SD * OZ_TILE_A + off;
@@ -438,7 +443,8 @@ __global__ void __launch_bounds__(Oz2Threads<NG>::N, 1) oz2_kernel(const Oz2Para
         for (int kb = 0; kb < nkb; ++kb) {
             const int slot = kb % DST;
             if (kb >= DST) {
-                oz_mbar_wait(oz_smem(&bar_empty[slot]), (uint32_t)(((kb / DST) - 1) & 1));
+                if (p.dbg_flags & 4096) oz_mbar_wait(oz_smem(&bar_empty[slot]), (uint32_t)(((kb / DST) - 1) & 1));
+                else oz_mbar_wait_hint(oz_smem(&bar_empty[slot]), (uint32_t)(((kb / DST) - 1) & 1), 20000u);
                 if (share > 1) s_free_upto = kb + 1;      // every sharing CTA's MMAs have consumed block kb - DST: its stage is free in all of them
             }
             const uint32_t bar = oz_smem(&bar_full[slot]);
@@ -476,14 +482,16 @@ __global__ void __launch_bounds__(Oz2Threads<NG>::N, 1) oz2_kernel(const Oz2Para
             // rounds are serial time in which the tensor pipe only has what is queued
             bool two = false;
             if (share == 1) {
-                oz_mbar_wait(oz_smem(&bar_full[slot]), (uint32_t)((kb / DST) & 1));
+                if (p.dbg_flags & 4096) oz_mbar_wait(oz_smem(&bar_full[slot]), (uint32_t)((kb / DST) & 1));
+                else oz_mbar_wait_hint(oz_smem(&bar_full[slot]), (uint32_t)((kb / DST) & 1), 20000u);
                 if (kb > 0 && kb + 1 < nkb && !one_stage) two = oz_mbar_test(oz_smem(&bar_full[slot2]), (uint32_t)(((kb + 1) / DST) & 1));
                 two = __all_sync(0xffffffffu, two);
                 if (!gram && !(p.dbg_flags & 512)) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // the converters' stores of this stage (see there)
             } else {
                 // the digits of this stage may come from a peer CTA: acquire at cluster scope, then order those generic-proxy stores before the
                 // tensor core's async-proxy reads on the consumer side as well
-                oz_mbar_wait_cluster(oz_smem(&bar_full[slot]), (uint32_t)((kb / DST) & 1));
+                if (p.dbg_flags & 4096) oz_mbar_wait_cluster(oz_smem(&bar_full[slot]), (uint32_t)((kb / DST) & 1));
+                else oz_mbar_wait_cluster_hint(oz_smem(&bar_full[slot]), (uint32_t)((kb / DST) & 1), 20000u);
                 if (kb > 0 && kb + 1 < nkb && !one_stage) two = oz_mbar_test_cluster(oz_smem(&bar_full[slot2]), (uint32_t)(((kb + 1) / DST) & 1));
                 two = __all_sync(0xffffffffu, two);
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -622,7 +630,7 @@ struct Oz3Params {
     const int* En;                                  // raw row exponents of A
     int nkb, nbm; int64_t ntiles;                   // K blocks per tile, column tiles, tiles in all (tile t: bx = t % nbm, by = t / nbm)
     void* out; int64_t ldo; double alpha, beta;
-    int order_asc;                                  // timing experiments (RLB200_OZ3_ONE_STAGE): one stage per issue round
+    int order_asc;                                  // timing experiments: bit 0 (RLB200_OZ3_ONE_STAGE) one stage per issue round, bit 1 (RLB200_OZ3_NO_WAIT_HINT) plain try_wait
 };
 
 template <int SD, typename T>
@@ -802,7 +810,7 @@ __global__ void __launch_bounds__(Oz2Threads<2>::N, 1) oz3_kernel(const Oz3Param
             auto convert_block = [&](int kb, const T (&raw)[16]) {
                 const int64_t gb = gb0 + kb;
                 const int slot = (int)(gb % DST);
-                if (gb >= DST) oz_mbar_wait(oz_smem(&bar_empty[slot]), (uint32_t)(((gb / DST) - 1) & 1));
+                if (gb >= DST) { if (p.order_asc & 2) oz_mbar_wait(oz_smem(&bar_empty[slot]), (uint32_t)(((gb / DST) - 1) & 1)); else oz_mbar_wait_hint(oz_smem(&bar_empty[slot]), (uint32_t)(((gb / DST) - 1) & 1), 20000u); }
                 unsigned char* dst = oz3_smem_raw + slot * Cfg::STAGE_BYTES + SD * OZ_TILE_A + off;
                 uint32_t pk[4][SD];
 #pragma unroll
@@ -855,7 +863,7 @@ __global__ void __launch_bounds__(Oz2Threads<2>::N, 1) oz3_kernel(const Oz3Param
             const int8_t* gm = p.m_tiles + (int64_t)bx * p.nkb_stride * (SD * OZ_TILE_A);
             for (int kb = 0; kb < nkb; ++kb, ++gb) {
                 const int slot = (int)(gb % DST);
-                if (gb >= DST) oz_mbar_wait(oz_smem(&bar_empty[slot]), (uint32_t)(((gb / DST) - 1) & 1));
+                if (gb >= DST) { if (p.order_asc & 2) oz_mbar_wait(oz_smem(&bar_empty[slot]), (uint32_t)(((gb / DST) - 1) & 1)); else oz_mbar_wait_hint(oz_smem(&bar_empty[slot]), (uint32_t)(((gb / DST) - 1) & 1), 20000u); }
                 const uint32_t bar = oz_smem(&bar_full[slot]);
                 asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)(SD * OZ_TILE_A)) : "memory");
                 oz_bulk_load(sbase + slot * Cfg::STAGE_BYTES, gm + (int64_t)kb * (SD * OZ_TILE_A), (uint32_t)(SD * OZ_TILE_A), bar);
@@ -870,13 +878,13 @@ __global__ void __launch_bounds__(Oz2Threads<2>::N, 1) oz3_kernel(const Oz3Param
         for (int64_t j = 0; j < ntl; ++j) {
             for (int kb = 0; kb < nkb;) {
                 const int slot = (int)(gb % DST);
-                oz_mbar_wait(oz_smem(&bar_full[slot]), (uint32_t)((gb / DST) & 1));
+                if (p.order_asc & 2) oz_mbar_wait(oz_smem(&bar_full[slot]), (uint32_t)((gb / DST) & 1)); else oz_mbar_wait_hint(oz_smem(&bar_full[slot]), (uint32_t)((gb / DST) & 1), 20000u);
                 // the previous tile's accumulators have been read
                 if (kb == 0 && j > 0) oz_mbar_wait(oz_smem(&bar_acc_empty), (uint32_t)((j - 1) & 1));
                 // If the next stage is full already, both are issued behind one barrier wait / proxy fence: between two issue rounds the
                 // tensor pipe only has what is queued (measured: ~135 cycles per round on top of the 790 of the MMAs of a K step)
                 const int slot2 = (int)((gb + 1) % DST);
-                bool two = (kb + 1 < nkb) && !p.order_asc && oz_mbar_test(oz_smem(&bar_full[slot2]), (uint32_t)(((gb + 1) / DST) & 1));
+                bool two = (kb + 1 < nkb) && !(p.order_asc & 1) && oz_mbar_test(oz_smem(&bar_full[slot2]), (uint32_t)(((gb + 1) / DST) & 1));
                 two = __all_sync(0xffffffffu, two);
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // the converters' generic-proxy stores of this stage
                 asm volatile("tcgen05.fence::after_thread_sync;");
@@ -1079,7 +1087,7 @@ static int oz2_nn(Ctx* ctx, int64_t m, int64_t N, int64_t K, double alpha, const
         q.X = A; q.ldx = lda; q.rows_n = m; q.kdim = K; q.En = Ea;
         q.nkb = nkb; q.nbm = nbm; q.ntiles = nbn * nbm;
         q.out = C; q.ldo = ldc; q.alpha = alpha; q.beta = beta;
-        static const int order_asc = getenv("RLB200_OZ3_ONE_STAGE") ? 1 : 0;
+        static const int order_asc = (getenv("RLB200_OZ3_ONE_STAGE") ? 1 : 0) | (getenv("RLB200_OZ3_NO_WAIT_HINT") ? 2 : 0);
         q.order_asc = order_asc;
         LaunchScope ls(ctx, RLB200_TIMER_I8_MMA_NN);
         const unsigned grid = (unsigned)std::min<int64_t>(nbn, (int64_t)ctx->num_sms);
