@@ -790,6 +790,8 @@ __global__ void __launch_bounds__(Oz2Threads<2>::N, 1) oz3_kernel(const Oz3Param
                     if (row0 < p.rows_n) pf_src = X + row0 + (int64_t)(tt / LPC) * p.ldx;
                 }
             }
+            // (a bulk form - one cp.async.bulk.prefetch.L2 of 512 bytes per column, issued by one warp - keeps the 128 line requests per block
+            //  off the L1 data pipe but is far slower: A*Omega 14.8 ms against 10.8-11.3 ms on the same box)
             auto prefetch_block = [&](int kb) {
                 if (pf_src != nullptr && kb < kb_full) asm volatile("prefetch.global.L2 [%0];" ::"l"(pf_src + (int64_t)kb * OZ_KB * p.ldx));
             };
