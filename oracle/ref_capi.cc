@@ -264,6 +264,18 @@ static int bqrrp_impl(int64_t m, int64_t n, T* A, int64_t lda, T d_factor, int64
     RL_CATCH
 }
 
+// hqrrp (RandLAPACK/drivers/rl_hqrrp.hh:811-1196): Householder QR with randomized pivoting; J (1-based) and tau as geqp3 returns them
+template <typename T>
+static int hqrrp_impl(int64_t m, int64_t n, T* A, int64_t lda, int64_t* J, T* tau, int64_t nb_alg, int64_t pp, int64_t panel_pivoting,
+                      int64_t qr_type, uint32_t state[6]) {
+    RL_TRY
+    State st = load_state(state);
+    int rc = (int)RandLAPACK::hqrrp(m, n, A, lda, J, tau, nb_alg, pp, panel_pivoting, qr_type, st, (T**)nullptr);
+    store_state(st, state);
+    return rc;
+    RL_CATCH
+}
+
 // SYPS / SYRF / REVD2 (RandLAPACK/comps/rl_syps.hh:21-143, comps/rl_syrf.hh:21-118, drivers/rl_revd2.hh:75-246); the algorithm objects
 // of test/drivers/test_revd2.cc:78-101.  uplo: 0 upper, 1 lower.
 template <typename T>
@@ -438,6 +450,10 @@ int rlref_mat_gen_f32(int type, int64_t m, int64_t n, int64_t rank, float cond, 
     int rlref_revd2_##SUF(int uplo, int64_t m, const T* A, int64_t* k, int64_t k_cap, T tol, int64_t p, int64_t q, int orth,               \
                           int error_est_p, T* V, T* eigvals, uint32_t state[6]) {                                                          \
         return revd2_impl<T>(uplo, m, A, k, k_cap, tol, p, q, orth, error_est_p, V, eigvals, state);                                       \
+    }                                                                                                                                     \
+    int rlref_hqrrp_##SUF(int64_t m, int64_t n, T* A, int64_t lda, int64_t* J, T* tau, int64_t nb_alg, int64_t pp, int64_t panel_pivoting, \
+                          int64_t qr_type, uint32_t state[6]) {                                                                            \
+        return hqrrp_impl<T>(m, n, A, lda, J, tau, nb_alg, pp, panel_pivoting, qr_type, state);                                            \
     }                                                                                                                                     \
     int rlref_bqrrp_##SUF(int64_t m, int64_t n, T* A, int64_t lda, T d_factor, int64_t b_sz, int qrcp_wide, int qr_tall, T* tau,           \
                           int64_t* J, int64_t* rank, uint32_t state[6]) {                                                                  \

@@ -863,3 +863,140 @@ class BQRRP:
             cols -= b_sz
         self.rank = curr
         return 0, A, tau, J, state
+
+
+# --------------------------------------------------------------------------------------------
+# HQRRP (RandLAPACK/drivers/rl_hqrrp.hh): Householder QR with randomized pivoting
+# --------------------------------------------------------------------------------------------
+def _qrp_unb(A, p, t, num_stages, pivoting, B=None, C=None, build_T=False):
+    """NoFLA_QRPmod_WY_unb_var4's unblocked loop (rl_hqrrp.hh:556-775): Householder QR of A (in place, a Fortran-ordered view) with
+    optional column pivoting by downdated partial column norms; B and C (views with A's column count) are pivoted along; p / t are
+    views of the pivot and tau vectors.  Returns T (larft, Forward / Columnwise, num_stages x num_stages) when build_T."""
+    m, n = A.shape
+    dt = A.dtype
+    mn = min(m, n)
+    if num_stages < 0:
+        num_stages = mn
+    larfg, = get_lapack_funcs(("larfg",), (A,))
+    tol3z = np.sqrt(np.finfo(np.float64).eps / 2)                  # sqrt(dlamch('E')) for every T (:376-378)
+    if pivoting:
+        d = np.array([np.linalg.norm(A[:, j]) for j in range(n)], dtype=dt)    # NoFLA_QRP_compute_norms (:336-357)
+        e = d.copy()
+    for j in range(num_stages):
+        if pivoting:
+            jm = int(np.argmax(d[j:]))                             # blas::iamax: first maximum (:662)
+            if jm != 0:                                            # NoFLA_QRP_pivot_G_B_C (:414-461)
+                a, b = j, j + jm
+                A[:, [a, b]] = A[:, [b, a]]
+                if B is not None:
+                    B[:, [a, b]] = B[:, [b, a]]
+                if C is not None:
+                    C[:, [a, b]] = C[:, [b, a]]
+                p[a], p[b] = p[b], p[a]
+                d[b], e[b] = d[a], e[a]                            # norms of column 0 are COPIED to column j_max_col
+        # larfg on (alpha11, a21) (:683-688)
+        if m - j - 1 > 0:
+            alpha, x, tau_j = larfg(m - j, A[j, j], A[j + 1:, j].copy())
+            A[j, j], A[j + 1:, j], t[j] = alpha, x, tau_j
+        else:
+            t[j] = 0                                               # larfg with n = 1: tau = 0
+        # | a12t; A22 | = H | a12t; A22 | (:700-709)
+        if n - j - 1 > 0 and t[j] != 0:
+            v = np.concatenate(([dt.type(1)], A[j + 1:, j]))
+            blk = A[j:, j + 1:]
+            w = blk.T @ v
+            blk -= t[j] * np.outer(v, w)
+        if pivoting and n - j - 1 > 0:                             # NoFLA_QRP_downdate_partial_norms (:360-411)
+            for c in range(j + 1, n):
+                if d[c] != 0:
+                    temp = abs(A[j, c]) / d[c]
+                    temp = max(0.0, (1.0 + temp) * (1 - temp))
+                    temp5 = d[c] / e[c]
+                    temp2 = temp * temp5 * temp5
+                    if temp2 <= tol3z:
+                        d[c] = np.linalg.norm(A[j + 1:, c]) if m - j - 1 > 0 else 0
+                        e[c] = d[c]
+                    else:
+                        d[c] = d[c] * np.sqrt(temp)
+    if build_T:
+        return _larft(A, t, num_stages)
+    return None
+
+
+def _larft(V, tau, k):
+    """lapack::larft(Forward, Columnwise) on the unit-lower-trapezoidal reflectors stored below the diagonal of V (m x >= k)."""
+    dt = V.dtype
+    m = V.shape[0]
+    Vu = np.tril(V[:, :k], -1) + np.eye(m, k, dtype=dt)
+    T = np.zeros((k, k), dtype=dt, order="F")
+    for i in range(k):
+        T[i, i] = tau[i]
+        if i > 0 and tau[i] != 0:
+            T[:i, i] = -tau[i] * (T[:i, :i] @ (Vu[:, :i].T @ Vu[:, i]))
+    return T
+
+
+def hqrrp(A, nb_alg, pp, panel_pivoting, qr_type, state: RNGState):
+    """RandLAPACK::hqrrp(m, n, A, lda, jpvt, tau, nb_alg, pp, panel_pivoting, qr_type, state, timing) (rl_hqrrp.hh:811-1196).
+    -> (rc, A_out [GEQP3 format], tau (n entries, first min(m, n) meaningful), J (1-based), next state).
+    qr_type (the panel QR when panel_pivoting == 0): 0 unblocked Householder, 1 geqrf (:464-502), 2 CholQR + orhr_col (:505-553)."""
+    A = _F(np.array(A, copy=True))
+    m, n = A.shape
+    dt = A.dtype
+    mn = min(m, n)
+    tau = np.zeros(n, dtype=dt)
+    J = np.zeros(n, dtype=np.int64)
+    if mn == 0:                                                        # quick return (:886-888): J is not initialised
+        return 0, A, tau, J, state
+    m_Y = nb_alg + pp
+    J[:] = np.arange(1, n + 1)                                         # std::iota (:919)
+    # G = fill_dense(DenseDist(nb_alg + pp, m, Uniform)): the natural-layout buffer is read as ColMajor with ld = m_Y (:928-935)
+    Gm, state = fill_dense(m_Y, m, state, dt, family=FAMILY_UNIFORM)
+    G = _F(Gm.ravel(order="K").reshape((m_Y, m), order="F"))
+    Y = _F(G @ A)
+    geqrf, potrf = get_lapack_funcs(("geqrf", "potrf"), (A,))
+    (trsm_,) = get_blas_funcs(("trsm",), (A,))
+    for j in range(0, mn, nb_alg):
+        b = min(nb_alg, n - j, m - j)
+        last_iter = (j + nb_alg >= m) or (j + nb_alg >= n)
+        if not last_iter:                                              # QRP of a copy of YR; AR and YR pivoted along (:1019-1046)
+            V = _F(Y[:, j:].copy())
+            _qrp_unb(V, J[j:], tau[j:], b, True, B=A[:, j:], C=Y[:, j:])
+        AB1 = A[j:, j:j + b]
+        if panel_pivoting:                                             # :1075-1080 with pivoting = 1
+            Tm = _qrp_unb(AB1, J[j:j + b], tau[j:j + b], -1, True, B=A[:j, j:j + b], C=Y[:, j:j + b], build_T=True)
+        elif qr_type == 2:                                             # CHOLQR_mod_WY (:505-553)
+            R = np.triu(_gemm(_F(AB1), _F(AB1), ta=True))
+            c, info = potrf(_F(R), lower=0, clean=1)
+            if info:      # CHOLQR_mod_WY returns 1 and hqrrp, which does not look at it (:1075), goes on with an unfactored panel
+                raise NotImplementedError("hqrrp: Cholesky failure inside a panel (the reference's output is unspecified here)")
+            Q = trsm_(1.0, _F(c), _F(AB1), side=1, lower=0)
+            Vh, Tm, D = orhr_col(Q)
+            Rs = np.triu(c) * D[:, None]
+            AB1[:, :] = np.tril(Vh, -1)
+            AB1[:b, :b] += np.triu(Rs)
+            tau[j:j + b] = np.diag(Tm)
+        else:                                                          # geqrf (qr_type 1, :464-502) or the unblocked loop without pivoting (qr_type 0)
+            if qr_type == 1:
+                qr, tq, _, _ = geqrf(_F(AB1))
+                AB1[:, :] = qr
+                tau[j:j + len(tq)] = tq
+                Tm = _larft(AB1, tau[j:j + b], min(AB1.shape))
+            else:
+                Tm = _qrp_unb(AB1, J[j:j + b], tau[j:j + b], -1, False, build_T=True)
+        k = Tm.shape[0]
+        if j + b < n:                                                  # [A12; A22] <- Q^T [A12; A22] (:1091-1100), larfb Left / Trans
+            U = np.tril(AB1[:, :k], -1) + np.eye(m - j, k, dtype=dt)
+            C2 = A[j:, j + b:]
+            C2 -= U @ (Tm.T @ (U.T @ C2))
+        if not last_iter:                                              # NoFLA_Downdate_Y (:206-296)
+            U11 = np.tril(AB1[:b, :b], -1) + np.eye(b, dtype=dt)
+            U21 = AB1[b:, :b]
+            G1, G2 = G[:, j:j + b], G[:, j + b:]
+            Bm = ((G1 @ U11 + G2 @ U21) @ Tm) @ U11.T
+            Bm = G1 - Bm
+            Y[:, j + b:] -= Bm @ A[j:j + b, j + b:]
+            GR = G[:, j:]                                              # GR <- GR Q, larfb Right / NoTrans (:288-291)
+            Ufull = np.vstack((U11, U21))
+            GR -= ((GR @ Ufull) @ Tm) @ Ufull.T
+    return 0, A, tau, J, state

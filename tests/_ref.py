@@ -231,3 +231,17 @@ def ref_bqrrp(lib, A, d_factor, b_sz, seed6, qrcp_wide=0, qr_tall=0, tol=None):
                   ctypes.POINTER(i64), ctypes.POINTER(u32)]
     rc = f(m, n, F.ctypes.data, m, d_factor, b_sz, qrcp_wide, qr_tall, tau.ctypes.data, J.ctypes.data, ctypes.byref(rank), st)
     return rc, rank.value, F, tau, J, list(st)
+
+
+def ref_hqrrp(lib, A, nb_alg, pp, panel_pivoting, qr_type, seed6):
+    """RandLAPACK::hqrrp via the compiled reference -> (rc, A_out [GEQP3 format], tau, J, state)."""
+    m, n = A.shape
+    dt = A.dtype
+    F = np.asfortranarray(A.copy())
+    tau = np.zeros(n, dtype=dt)
+    J = np.zeros(n, dtype=np.int64)
+    st = (u32 * 6)(*seed6)
+    f = getattr(lib, f"rlref_hqrrp_{_suf(dt)}")
+    f.argtypes = [i64, i64, ctypes.c_void_p, i64, ctypes.c_void_p, ctypes.c_void_p, i64, i64, i64, i64, ctypes.POINTER(u32)]
+    rc = f(m, n, F.ctypes.data, max(m, 1), J.ctypes.data, tau.ctypes.data, nb_alg, pp, panel_pivoting, qr_type, st)
+    return rc, F, tau, J, list(st)
