@@ -13,6 +13,7 @@
 //   RandLAPACK::CQRRPTalg / CQRRPT    drivers/rl_cqrrpt.hh:20-391          rlb200::CQRRPT<T>
 //   RandLAPACK::CQRRTalg / CQRRT      drivers/rl_cqrrt.hh:20-297           rlb200::CQRRT<T>
 //   RandLAPACK::BQRRPalg / BQRRP      drivers/rl_bqrrp.hh:19-665           rlb200::BQRRP<T>
+//   RandLAPACK::hqrrp (free function) drivers/rl_hqrrp.hh:811-1196         rlb200::hqrrp<T>
 //   RandLAPACK::BQRRP_GPU_alg / BQRRP_GPU  drivers/rl_bqrrp_gpu.hh:27-942   rlb200::BQRRP_GPU<T>   (device pointers, sketch as input)
 //   RandLAPACK::linops::DenseLinOp / ExplicitSymLinOp  linops/rl_dense_linop.hh:36, linops/rl_sym_linops.hh   rlb200::DenseLinOp / ExplicitSymLinOp<T>  (matrix resident on the device)
 //   RandLAPACK::SYPS / SYRF / REVD2   comps/rl_syps.hh, comps/rl_syrf.hh, drivers/rl_revd2.hh   rlb200::SYPS / SYRF / REVD2<T>  (explicit symmetric A)
@@ -112,6 +113,7 @@ template <> struct abi<double> {
     static constexpr auto stab = rlb200_stab_f64_dev; static constexpr auto rs = rlb200_rs_f64_dev; static constexpr auto rf = rlb200_rf_f64_dev;
     static constexpr auto qb = rlb200_qb_f64_dev; static constexpr auto rsvd_host = rlb200_rsvd_f64_host;
     static constexpr auto cqrrpt_host = rlb200_cqrrpt_f64_host; static constexpr auto bqrrp_host = rlb200_bqrrp_f64_host;
+    static constexpr auto hqrrp_host = rlb200_hqrrp_f64_host;
     static constexpr auto bqrrp_dev_sk = rlb200_bqrrp_f64_dev_sk; static constexpr auto cqrrt_host = rlb200_cqrrt_f64_host;
     static constexpr auto syps = rlb200_syps_f64_dev; static constexpr auto syrf = rlb200_syrf_f64_dev; static constexpr auto revd2_host = rlb200_revd2_f64_host;
     static constexpr auto gemm = rlb200_gemm_f64_dev;
@@ -120,6 +122,7 @@ template <> struct abi<float> {
     static constexpr auto stab = rlb200_stab_f32_dev; static constexpr auto rs = rlb200_rs_f32_dev; static constexpr auto rf = rlb200_rf_f32_dev;
     static constexpr auto qb = rlb200_qb_f32_dev; static constexpr auto rsvd_host = rlb200_rsvd_f32_host;
     static constexpr auto cqrrpt_host = rlb200_cqrrpt_f32_host; static constexpr auto bqrrp_host = rlb200_bqrrp_f32_host;
+    static constexpr auto hqrrp_host = rlb200_hqrrp_f32_host;
     static constexpr auto bqrrp_dev_sk = rlb200_bqrrp_f32_dev_sk; static constexpr auto cqrrt_host = rlb200_cqrrt_f32_host;
     static constexpr auto syps = rlb200_syps_f32_dev; static constexpr auto syrf = rlb200_syrf_f32_dev; static constexpr auto revd2_host = rlb200_revd2_f32_host;
     static constexpr auto gemm = rlb200_gemm_f32_dev;
@@ -332,10 +335,37 @@ public:
 };
 
 // ---------------------------------------------------------------------------------------------------------------------
+// hqrrp (rl_hqrrp.hh:811-1196): the reference's free function, same argument list (HOST pointers).  `timing`: when non-null, *timing is
+// (re)allocated with realloc to 26 entries as the reference does (:1137) and the nine leading entries (:1140-1148) are filled, in
+// microseconds; the 2 x 9 per-routine entries of the unblocked QR loops, which have no counterpart here, are zero.
+// ---------------------------------------------------------------------------------------------------------------------
+template <typename T>
+int64_t hqrrp(Context& c, int64_t m_A, int64_t n_A, T* buff_A, int64_t ldim_A, int64_t* buff_jpvt, T* buff_tau, int64_t nb_alg, int64_t pp,
+              int64_t panel_pivoting, int64_t qr_type, state_t& state, T** timing) {
+    uint32_t w[6]; state_to_words(state, w);
+    if (timing) c.phase_timing(true);
+    int rc = c.check(detail::abi<T>::hqrrp_host(c.get(), m_A, n_A, buff_A, ldim_A, buff_jpvt, buff_tau, nb_alg, pp, (int)panel_pivoting,
+                                                (int)qr_type, w));
+    if (timing) {
+        std::vector<long> t = c.phase_times();
+        c.phase_timing(false);
+        T* out = static_cast<T*>(std::realloc(*timing, 26 * sizeof(T)));
+        if (out) { for (int i = 0; i < 26; ++i) out[i] = i < (int)t.size() ? (T)t[i] : (T)0; *timing = out; }
+    }
+    words_to_state(w, state);
+    return rc;
+}
+template <typename T>
+int64_t hqrrp(int64_t m_A, int64_t n_A, T* buff_A, int64_t ldim_A, int64_t* buff_jpvt, T* buff_tau, int64_t nb_alg, int64_t pp,
+              int64_t panel_pivoting, int64_t qr_type, state_t& state, T** timing) {
+    return hqrrp<T>(default_context(), m_A, n_A, buff_A, ldim_A, buff_jpvt, buff_tau, nb_alg, pp, panel_pivoting, qr_type, state, timing);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
 // CQRRPT (rl_cqrrpt.hh:20-391): same constructor (time_subroutines, eps), public fields and call signature (HOST pointers).
 // ---------------------------------------------------------------------------------------------------------------------
 struct CQRRPTSubroutines {
-    enum QRCP { geqp3 = RLB200_CQRRPT_QRCP_GEQP3, bqrrp = RLB200_CQRRPT_QRCP_BQRRP };     // rl_cqrrpt.hh:39-43 (hqrrp is not offered)
+    enum QRCP { geqp3 = RLB200_CQRRPT_QRCP_GEQP3, bqrrp = RLB200_CQRRPT_QRCP_BQRRP, hqrrp = RLB200_CQRRPT_QRCP_HQRRP };     // rl_cqrrpt.hh:39-43
 };
 template <typename T>
 class CQRRPT
@@ -345,8 +375,10 @@ class CQRRPT
 {
 public:
     using Subroutines = CQRRPTSubroutines;
-    CQRRPT(bool time_subroutines, T ep) : timing(time_subroutines), eps(ep), rank(0), nnz(2), qrcp(Subroutines::geqp3), orthogonalization(false), ctx_(&default_context()) {}
-    CQRRPT(Context& c, bool time_subroutines, T ep) : timing(time_subroutines), eps(ep), rank(0), nnz(2), qrcp(Subroutines::geqp3), orthogonalization(false), ctx_(&c) {}
+    CQRRPT(bool time_subroutines, T ep) : CQRRPT(default_context(), time_subroutines, ep) {}
+    CQRRPT(Context& c, bool time_subroutines, T ep)
+        : timing(time_subroutines), eps(ep), rank(0), nnz(2), qrcp(Subroutines::geqp3), orthogonalization(false), nb_alg(64), oversampling(10),
+          panel_pivoting(1), use_cholqr(0), ctx_(&c) {}                                      // HQRRP defaults: rl_cqrrpt.hh:60-63
     virtual ~CQRRPT() {}
     // A (m x n, lda) <- Q; R (ldr >= n): rank x n; J: n 1-based pivots (rl_cqrrpt.hh:146-156)
     int call(int64_t m, int64_t n, T* A, int64_t lda, T* R, int64_t ldr, int64_t* J, T d_factor, state_t& state) RLB200_OVERRIDE {
@@ -355,6 +387,7 @@ public:
         if (timing) ctx_->phase_timing(true);
         ctx_->check(rlb200_set_cqrrpt_qrcp(ctx_->get(), (int)qrcp));
         ctx_->check(rlb200_set_cqrrpt_orthogonalization(ctx_->get(), orthogonalization ? 1 : 0));
+        ctx_->check(rlb200_set_cqrrpt_hqrrp_opts(ctx_->get(), nb_alg, oversampling, (int)panel_pivoting, (int)use_cholqr));
         int rc = ctx_->check(detail::abi<T>::cqrrpt_host(ctx_->get(), m, n, A, lda, R, ldr, J, d_factor, eps, nnz, &r, w));
         if (timing) { times = ctx_->phase_times(); ctx_->phase_timing(false); }
         words_to_state(w, state);
@@ -366,8 +399,9 @@ public:
     int64_t rank;
     std::vector<long> times;   // 8 entries when `timing` (rl_cqrrpt.hh:371-384)
     int64_t nnz;
-    Subroutines::QRCP qrcp;    // QRCP of the sketch: geqp3 (default) or bqrrp (rl_cqrrpt.hh:230-247)
+    Subroutines::QRCP qrcp;    // QRCP of the sketch: geqp3 (default), bqrrp or hqrrp (rl_cqrrpt.hh:230-247)
     bool orthogonalization;    // rl_cqrrpt.hh:139-142
+    int64_t nb_alg, oversampling, panel_pivoting, use_cholqr;     // HQRRP-related (rl_cqrrpt.hh:134-137)
 private:
     Context* ctx_;
 };

@@ -124,9 +124,13 @@ RLB200_API int rlb200_set_phase_timing(rlb200_ctx* ctx, int on);
 RLB200_API int rlb200_set_bqrrp_tol(rlb200_ctx* ctx, double tol);
 /* CQRRPT's public `qrcp` field (rl_cqrrpt.hh:41, used at :230-247): the QRCP of the sketch by lapack::geqp3 (default) or by BQRRP with the
  * reference's block ratio (n <= 2000: 1, n <= 8000: 1/2, else 1/32; BQRRP(false, n * ratio).call(d, n, A_hat, d, 1.0, tau, J, state) - the RNG
- * state advances through BQRRP's own sketch).  hqrrp is not offered (RLB200_ERR_UNSUPPORTED).  Applies to the following rlb200_cqrrpt_* calls. */
-enum { RLB200_CQRRPT_QRCP_GEQP3 = 0, RLB200_CQRRPT_QRCP_BQRRP = 1 };
+ * state advances through BQRRP's own sketch), or by hqrrp(d, n, A_hat, d, J, tau, nb_alg, oversampling, panel_pivoting, use_cholqr, state)
+ * (:230-231; the state advances through hqrrp's uniform operator).  bqrrp and hqrrp: single shard.  Applies to the following rlb200_cqrrpt_* calls. */
+enum { RLB200_CQRRPT_QRCP_GEQP3 = 0, RLB200_CQRRPT_QRCP_BQRRP = 1, RLB200_CQRRPT_QRCP_HQRRP = 2 };
 RLB200_API int rlb200_set_cqrrpt_qrcp(rlb200_ctx* ctx, int qrcp);
+/* CQRRPT's public HQRRP fields nb_alg, oversampling, panel_pivoting, use_cholqr (rl_cqrrpt.hh:134-137; constructor defaults 64, 10, 1, 0 at
+ * :60-63), used when qrcp = hqrrp. */
+RLB200_API int rlb200_set_cqrrpt_hqrrp_opts(rlb200_ctx* ctx, int64_t nb_alg, int64_t oversampling, int panel_pivoting, int use_cholqr);
 /* CQRRPT's public `orthogonalization` field (rl_cqrrpt.hh:139-142, 343-368): R keeps the Cholesky factor (the preconditioning is not undone)
  * and, when rank < n, the trailing n - rank columns of A are completed to an orthonormal set: Gaussian columns (DenseDist(m, n - rank) drawn
  * at the current state, which - as in the reference - does not advance), projected against Q and orthogonalized by Householder QR.
@@ -330,6 +334,24 @@ RLB200_API int rlb200_bqrrp_f64_host(rlb200_ctx* ctx, int64_t m, int64_t n, doub
                           int qrcp_wide, int qr_tall, double* tau, int64_t* J, int64_t* rank, uint32_t state[6]);
 RLB200_API int rlb200_bqrrp_f32_host(rlb200_ctx* ctx, int64_t m, int64_t n, float* A, int64_t lda, float d_factor, int64_t block_size,
                           int qrcp_wide, int qr_tall, float* tau, int64_t* J, int64_t* rank, uint32_t state[6]);
+
+/* ---- f2: hqrrp(m, n, A, lda, jpvt, tau, nb_alg, pp, panel_pivoting, qr_type, state, timing) (RandLAPACK/drivers/rl_hqrrp.hh:811-1196):
+ *      Householder QR with randomized pivoting.  nb_alg = block size, pp = oversampling (the sketch has nb_alg + pp rows),
+ *      panel_pivoting != 0: every panel is factored by norm-downdating QRCP (:556-775); otherwise qr_type picks the panel QR: 0 the unblocked
+ *      Householder loop, 1 geqrf (:464-502), 2 CholQR + Householder reconstruction (:505-553; needs m - j >= nb_alg in every block).
+ * On exit A is GEQP3-formatted, tau holds min(m, n) scalars, J n 1-based pivots (J is NOT written when min(m, n) = 0, :886-888);
+ * state <- fill_dense(DenseDist(nb_alg + pp, m, Uniform)).next_state (:928-929).  Returns 0 (the reference's only return value), or 1 when a
+ * panel's Cholesky factorization fails under qr_type 2 (the reference continues with an unfactored panel there).  With
+ * rlb200_set_phase_timing the nine leading entries of the reference's timing vector (:1140-1148) are recorded.  Replicas only (not row-shardable). */
+RLB200_API int rlb200_hqrrp_f64_dev(rlb200_ctx* ctx, int64_t m, int64_t n, double* A_dev, int64_t lda, int64_t* J_dev, double* tau_dev,
+                         int64_t nb_alg, int64_t pp, int panel_pivoting, int qr_type, uint32_t state[6]);
+RLB200_API int rlb200_hqrrp_f32_dev(rlb200_ctx* ctx, int64_t m, int64_t n, float* A_dev, int64_t lda, int64_t* J_dev, float* tau_dev,
+                         int64_t nb_alg, int64_t pp, int panel_pivoting, int qr_type, uint32_t state[6]);
+/* Host-pointer form (the reference's calling convention): A, J, tau are HOST buffers. */
+RLB200_API int rlb200_hqrrp_f64_host(rlb200_ctx* ctx, int64_t m, int64_t n, double* A, int64_t lda, int64_t* J, double* tau,
+                          int64_t nb_alg, int64_t pp, int panel_pivoting, int qr_type, uint32_t state[6]);
+RLB200_API int rlb200_hqrrp_f32_host(rlb200_ctx* ctx, int64_t m, int64_t n, float* A, int64_t lda, int64_t* J, float* tau,
+                          int64_t nb_alg, int64_t pp, int panel_pivoting, int qr_type, uint32_t state[6]);
 
 /* ---- lapack::geqp3 / geqrf of a small (L2-resident) d x n matrix, as used on the sketch (rl_cqrrpt.hh:247, rl_bqrrp.hh:336,356).
  * pivot != 0: J_dev receives n 1-based pivots (all columns free on entry, i.e. LAPACK's jpvt = 0 convention of the call sites). */

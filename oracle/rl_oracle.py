@@ -503,10 +503,12 @@ def col_swap(A, idx):
 
 
 class CQRRPT:
-    """RandLAPACK::CQRRPT(timing, eps); fields nnz (=2), rank, qrcp ('geqp3' default | 'bqrrp', rl_cqrrpt.hh:230-244)."""
+    """RandLAPACK::CQRRPT(timing, eps); fields nnz (=2), rank, qrcp ('geqp3' default | 'bqrrp' | 'hqrrp', rl_cqrrpt.hh:230-247) and the
+    HQRRP fields nb_alg, oversampling, panel_pivoting, use_cholqr (:134-137, defaults :60-63)."""
 
     def __init__(self, eps, nnz=2):
         self.eps, self.nnz, self.rank, self.qrcp, self.orthogonalization = eps, nnz, None, "geqp3", False
+        self.nb_alg, self.oversampling, self.panel_pivoting, self.use_cholqr = 64, 10, 1, 0
 
     def call(self, A, d_factor, state: RNGState, R=None):
         """-> (rc, Q (m x n, first rank columns meaningful), R (n x n), J (1-based), next state)."""
@@ -526,6 +528,8 @@ class CQRRPT:
             ratio = 1.0 if n <= 2000 else (0.5 if n <= 8000 else 1.0 / 32.0)
             bq = BQRRP(int(dt.type(n) * dt.type(ratio)))
             _, A_hat, tau, jpvt, state = bq.call(A_hat, 1.0, state)
+        elif self.qrcp == "hqrrp":                                                  # :230-231
+            _, A_hat, tau, jpvt, state = hqrrp(A_hat, self.nb_alg, self.oversampling, self.panel_pivoting, self.use_cholqr, state)
         else:
             A_hat, jpvt, tau, _, info = geqp3(A_hat)                                # :247
         J[:] = jpvt

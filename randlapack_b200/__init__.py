@@ -21,7 +21,7 @@ from ._capi import (STAB_PLUL, STAB_CHOLQRQ, STAB_HQRQ, FAMILY_GAUSSIAN, FAMILY_
                     LAYOUT_NATURAL, LAYOUT_COLMAJOR, LAYOUT_ROWMAJOR, StackOpts, QRCP_LUQR, QRCP_GEQP3, QRTALL_GEQRF,
                     QRTALL_CHOLQR, QRTALL_GEQRT)
 
-__all__ = ["Context", "RNGState", "DenseDist", "fill_dense", "SparseDist", "fill_sparse", "sketch_general_left", "sketch_general_right", "CQRRPT", "BQRRP", "qr_small", "col_swap", "CholQRQ", "PLUL", "HQRQ", "RS", "RF", "QB", "RSVD", "empty_f",
+__all__ = ["Context", "RNGState", "DenseDist", "fill_dense", "SparseDist", "fill_sparse", "sketch_general_left", "sketch_general_right", "CQRRPT", "BQRRP", "hqrrp", "qr_small", "col_swap", "CholQRQ", "PLUL", "HQRQ", "RS", "RF", "QB", "RSVD", "empty_f",
            "to_f", "Error", "shard_rows"]
 
 
@@ -575,17 +575,21 @@ class RSVD:
 
 class CQRRPT:
     """RandLAPACK::CQRRPT(time_subroutines, eps) (rl_cqrrpt.hh:45-146); public fields nnz (SASO non-zeros per column, default 2), rank.
-    qrcp: "geqp3" (the reference's default) or "bqrrp" (rl_cqrrpt.hh:41, 230-244); hqrrp is not offered."""
+    qrcp: "geqp3" (the reference's default), "bqrrp" or "hqrrp" (rl_cqrrpt.hh:39-43, 230-247); nb_alg, oversampling, panel_pivoting,
+    use_cholqr are the HQRRP fields (:134-137, constructor defaults :60-63)."""
 
     def __init__(self, time_subroutines=False, eps=None):
         self.timing, self.eps, self.nnz, self.rank, self.qrcp = time_subroutines, eps, 2, None, "geqp3"
+        self.nb_alg, self.oversampling, self.panel_pivoting, self.use_cholqr = 64, 10, 1, 0
         self.orthogonalization = False      # rl_cqrrpt.hh:139-142: R keeps the Cholesky factor, Q is completed to n orthonormal columns
 
     def _set_qrcp(self, ctx):
-        kinds = {"geqp3": _capi.CQRRPT_QRCP_GEQP3, "bqrrp": _capi.CQRRPT_QRCP_BQRRP}
+        kinds = {"geqp3": _capi.CQRRPT_QRCP_GEQP3, "bqrrp": _capi.CQRRPT_QRCP_BQRRP, "hqrrp": _capi.CQRRPT_QRCP_HQRRP}
         if self.qrcp not in kinds:
-            raise Error(_capi.ERR_UNSUPPORTED, f"CQRRPT qrcp {self.qrcp!r}: geqp3 and bqrrp are offered")
+            raise Error(_capi.ERR_ARG, f"CQRRPT qrcp {self.qrcp!r}: geqp3, bqrrp and hqrrp are the reference's choices")
         ctx.check(ctx._lib.rlb200_set_cqrrpt_qrcp(ctx._h, kinds[self.qrcp]))
+        ctx.check(ctx._lib.rlb200_set_cqrrpt_hqrrp_opts(ctx._h, int(self.nb_alg), int(self.oversampling), int(self.panel_pivoting),
+                                                         int(self.use_cholqr)))
         ctx.check(ctx._lib.rlb200_set_cqrrpt_orthogonalization(ctx._h, int(bool(self.orthogonalization))))
 
     def _eps(self, dtype):
@@ -812,6 +816,22 @@ class BQRRP:
         state.assign(w)
         self.rank = rank.value
         return rc, tau, J
+
+
+def hqrrp(ctx: Context, A, nb_alg, pp, panel_pivoting, qr_type, state: RNGState, tau=None, J=None):
+    """RandLAPACK::hqrrp(m, n, A, lda, jpvt, tau, nb_alg, pp, panel_pivoting, qr_type, state, timing) (rl_hqrrp.hh:811-1196): Householder QR
+    with randomized pivoting.  A (m x n, column-major; device or host tensor) is overwritten GEQP3-style -> (rc, tau (n), J int64 1-based)."""
+    torch = _torch()
+    assert _is_f(A)
+    m, n = A.shape
+    tau = torch.zeros(n, dtype=A.dtype, device=A.device) if tau is None else tau
+    J = torch.zeros(n, dtype=torch.int64, device=A.device) if J is None else J
+    w = state.words()
+    fn = getattr(ctx._lib, f"rlb200_hqrrp_{_suffix(A.dtype)}_{'dev' if A.is_cuda else 'host'}")
+    rc = ctx.check(fn(ctx._h, m, n, A.data_ptr(), _ld(A), J.data_ptr(), tau.data_ptr(), int(nb_alg), int(pp), int(panel_pivoting),
+                      int(qr_type), w))
+    state.assign(w)
+    return rc, tau, J
 
 
 def qr_small(ctx: Context, A, pivot=True):

@@ -37,7 +37,7 @@ class Revd2Opts(ctypes.Structure):
 
 
 UPLO_UPPER, UPLO_LOWER = 0, 1
-CQRRPT_QRCP_GEQP3, CQRRPT_QRCP_BQRRP = 0, 1
+CQRRPT_QRCP_GEQP3, CQRRPT_QRCP_BQRRP, CQRRPT_QRCP_HQRRP = 0, 1, 2
 
 ALLREDUCE_FN = ctypes.CFUNCTYPE(c_int, c_vp, c_vp, c_i64, c_i32, c_vp)
 
@@ -86,6 +86,7 @@ SIGNATURES = {
     "rlb200_set_bqrrp_tol": (c_int, [c_vp, ctypes.c_double]),
     "rlb200_set_cqrrpt_qrcp": (c_int, [c_vp, c_int]),
     "rlb200_set_cqrrpt_orthogonalization": (c_int, [c_vp, c_int]),
+    "rlb200_set_cqrrpt_hqrrp_opts": (c_int, [c_vp, c_i64, c_i64, c_int, c_int]),
     "rlb200_get_phase_times": (c_int, [c_vp, c_vp, c_int]),
     "rlb200_comm_unique_id": (c_int, [c_vp]),
     "rlb200_comm_init": (c_int, [c_vp, c_int, c_int, c_vp]),
@@ -100,6 +101,8 @@ for _suf, _ft in (("f64", ctypes.c_double), ("f32", ctypes.c_float)):
         SIGNATURES[f"rlb200_{_name}_{_suf}_dev"] = _sig
     SIGNATURES[f"rlb200_cqrrpt_{_suf}_host"] = (c_int, [c_vp, c_i64, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, _ft, _ft, c_i64, P_i64, P_u32])
     SIGNATURES[f"rlb200_bqrrp_{_suf}_host"] = (c_int, [c_vp, c_i64, c_i64, c_vp, c_i64, _ft, c_i64, c_int, c_int, c_vp, c_vp, P_i64, P_u32])
+    SIGNATURES[f"rlb200_hqrrp_{_suf}_dev"] = (c_int, [c_vp, c_i64, c_i64, c_vp, c_i64, c_vp, c_vp, c_i64, c_i64, c_int, c_int, P_u32])
+    SIGNATURES[f"rlb200_hqrrp_{_suf}_host"] = SIGNATURES[f"rlb200_hqrrp_{_suf}_dev"]
     SIGNATURES[f"rlb200_cqrrt_{_suf}_dev"] = (c_int, [c_vp, c_i64, c_i64, c_vp, c_i64, c_vp, c_i64, _ft, c_i64, c_int, c_int, P_u32])
     SIGNATURES[f"rlb200_cqrrt_{_suf}_host"] = (c_int, [c_vp, c_i64, c_i64, c_vp, c_i64, c_vp, c_i64, _ft, c_i64, c_int, c_int, P_u32])
     SIGNATURES[f"rlb200_syps_{_suf}_dev"] = (c_int, [c_vp, c_int, c_i64, c_vp, c_i64, c_i64, c_i64, c_i64, c_vp, c_vp, P_u32])

@@ -511,11 +511,187 @@ int bqrrp_call(Ctx* ctx, int64_t m, int64_t n, T* A, int64_t lda, T d_factor, in
     return finish(curr_sz);
 }
 
+// ================================================================================================================================
+// hqrrp (RandLAPACK/drivers/rl_hqrrp.hh:811-1196): Householder QR with randomized pivoting (Martinsson, Quintana-Orti, Heavner, van de Geijn).
+// Per block of nb_alg columns the reference (i) runs b steps of norm-downdating QRCP on a COPY of the trailing sketch Y = G A to pick the
+// block's pivots, swapping the same columns of A (all m rows) and Y; (ii) factors the panel (unblocked QRCP | geqrf | CholQR + orhr_col)
+// and builds its T factor; (iii) applies Q^T to the trailing matrix (larfb); (iv) downdates Y and updates G <- G Q (:206-296).
+// Here: G ((nb_alg + pp) x m uniform operator, kept because step (iv) rewrites it) and Y live on the device; (i) is the stage-limited
+// cooperative QRCP kernel of factor.cu on a copy of Y plus one gather of A's and Y's trailing columns; (ii) the same kernel on the panel
+// (or the CholQR / Householder-reconstruction sequence of BQRRP above); (iii) compact WY on the tall GEMMs (apply_qt_wy); (iv) six
+// small GEMMs.  Only the pivot vector of a block (b integers) travels to the host.
+// ================================================================================================================================
+template <typename T>
+int hqrrp_call(Ctx* ctx, int64_t m, int64_t n, T* A, int64_t lda, int64_t* J_dev, T* tau, int64_t nb_alg, int64_t pp, int panel_pivoting,
+               int qr_type, uint32_t state[6]) {
+    RLB_REQUIRE(ctx, m >= 0 && n >= 0);                                                 // :873-879 (the reference only prints here)
+    RLB_REQUIRE(ctx, lda >= std::max<int64_t>(1, m));
+    RLB_REQUIRE(ctx, nb_alg > 0 && pp >= 0);
+    RLB_REQUIRE(ctx, qr_type >= 0 && qr_type <= 2);
+    RLB_REQUIRE(ctx, state != nullptr);
+    if (ctx->m_global >= 0) { ctx->err = "hqrrp is not row-shardable (column pivoting couples all rows): replicas only"; return RLB200_ERR_UNSUPPORTED; }
+    const int64_t mn = std::min(m, n);
+    if (mn == 0) return 0;                                                              // quick return (:886-888): J and tau untouched
+    RLB_REQUIRE(ctx, A != nullptr && J_dev != nullptr && tau != nullptr);
+    const int64_t mY = nb_alg + pp, nb = nb_alg;
+    // rl_hqrrp.hh:376-378: sqrt(dlamch('E')) whatever T is
+    const double tol3z = std::sqrt(1.1102230246251565e-16);
+
+    PhaseTimer pt(ctx);
+    long long t_pre = 0, t_sk = 0, t_qrcp = 0, t_qr = 0, t_updA = 0, t_updS = 0;
+    ArenaScope as(ctx);
+    T* G = as.take<T>((size_t)mY * m); RLB_ALLOC_(G);
+    T* Y = as.take<T>((size_t)mY * n); RLB_ALLOC_(Y);
+    T* V = as.take<T>((size_t)mY * n); RLB_ALLOC_(V);
+    T* T_dat = as.take<T>((size_t)nb * nb); RLB_ALLOC_(T_dat);
+    T* V1c = as.take<T>((size_t)nb * nb); RLB_ALLOC_(V1c);
+    T* Gs = as.take<T>((size_t)nb * nb); RLB_ALLOC_(Gs);
+    T* R_tall = as.take<T>((size_t)nb * nb); RLB_ALLOC_(R_tall);
+    T* Dv = as.take<T>((size_t)nb); RLB_ALLOC_(Dv);
+    T* tau_sk = as.take<T>((size_t)std::max<int64_t>(mY, nb)); RLB_ALLOC_(tau_sk);
+    T* Wa = as.take<T>((size_t)nb * n); RLB_ALLOC_(Wa);
+    T* Wb = as.take<T>((size_t)nb * n); RLB_ALLOC_(Wb);
+    T* Bm = as.take<T>((size_t)mY * nb); RLB_ALLOC_(Bm);
+    T* Bm2 = as.take<T>((size_t)mY * nb); RLB_ALLOC_(Bm2);
+    T* Bf = as.take<T>((size_t)mY * nb); RLB_ALLOC_(Bf);
+    int64_t* Jbuf_dev = as.take<int64_t>((size_t)n); RLB_ALLOC_(Jbuf_dev);
+    void* qr_ws = arena_push(ctx, qrcp_ws_bytes(std::max<int64_t>(n, nb))); RLB_ALLOC_(qr_ws);
+    std::vector<int64_t> J((size_t)n), Jb((size_t)n), p0((size_t)n), old;
+    std::iota(J.begin(), J.end(), (int64_t)1);                                          // :919
+    t_pre = pt.lap();
+
+    // G = fill_dense(DenseDist(nb_alg + pp, m, Uniform)): the natural-layout buffer, read as ColMajor with ld = mY (:928-935); Y = G A
+    RLB_CHECK(fill_dense_unpacked<T>(ctx, mY, m, RLB200_FAMILY_UNIFORM, RLB200_AXIS_LONG, RLB200_LAYOUT_NATURAL, mY, m, 0, 0, G, state));
+    RLB_CHECK(gemm_nn<T>(ctx, mY, n, m, 1.0, G, mY, A, lda, 0.0, Y, mY));
+    t_sk = pt.lap();
+
+    auto fetch_pivots = [&](int64_t count) -> int {
+        RLB_CUDA_OK(ctx, cudaMemcpyAsync(Jb.data(), Jbuf_dev, sizeof(int64_t) * count, cudaMemcpyDeviceToHost, ctx->stream));
+        RLB_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+        for (int64_t i = 0; i < count; ++i) { RLB_REQUIRE(ctx, Jb[i] >= 1 && Jb[i] <= count); p0[i] = Jb[i] - 1; }
+        return 0;
+    };
+    auto permute_J = [&](int64_t at, int64_t count) {
+        old.assign(J.begin() + at, J.begin() + at + count);
+        for (int64_t i = 0; i < count; ++i) J[at + i] = old[p0[i]];
+    };
+    int rc_out = 0;
+
+    for (int64_t j = 0; j < mn; j += nb) {
+        const int64_t b = std::min(nb, std::min(n - j, m - j));
+        const bool last_iter = (j + nb >= m) || (j + nb >= n);                          // :945
+        const int64_t rows = m - j, nR = n - j, nc = n - j - b;
+        T* AB1 = A + j + j * lda;
+        T* YR = Y + j * mY;
+        T* tau1 = tau + j;
+        if (!last_iter) {
+            // ---- b steps of QRCP on a copy of YR; the swaps go to AR (all m rows) and YR (:1019-1046)
+            RLB_CUDA_OK(ctx, cudaMemcpyAsync(V, YR, sizeof(T) * mY * nR, cudaMemcpyDeviceToDevice, ctx->stream));
+            RLB_CHECK(qr_small<T>(ctx, true, mY, nR, V, mY, Jbuf_dev, tau_sk, qr_ws, b, tol3z));
+            RLB_CHECK(fetch_pivots(nR));
+            RLB_CHECK(col_permute<T>(ctx, m, nR, A + j * lda, lda, p0.data()));
+            RLB_CHECK(col_permute<T>(ctx, mY, nR, YR, mY, p0.data()));
+            permute_J(j, nR);
+        }
+        t_qrcp += pt.lap();
+        // ---- panel factorization [A11; A21] and its T factor (:1075-1080)
+        bool t_ready = false;
+        if (panel_pivoting) {
+            RLB_CHECK(qr_small<T>(ctx, true, rows, b, AB1, lda, Jbuf_dev, tau1, qr_ws, -1, tol3z));
+            RLB_CHECK(fetch_pivots(b));
+            if (j > 0) RLB_CHECK(col_permute<T>(ctx, j, b, A + j * lda, lda, p0.data()));          // A01
+            RLB_CHECK(col_permute<T>(ctx, mY, b, YR, mY, p0.data()));                               // Y1
+            permute_J(j, b);
+        } else if (qr_type == 2) {
+            // CHOLQR_mod_WY (:505-553): R = chol(A^T A), Q = A R^-1, Householder reconstruction, signs into R
+            RLB_REQUIRE(ctx, rows >= b);
+            RLB_CUDA_OK(ctx, cudaMemsetAsync(Gs, 0, sizeof(T) * b * b, ctx->stream));
+            RLB_CHECK(gemm_tn<T>(ctx, rows, b, b, 1.0, AB1, lda, AB1, lda, 0.0, Gs, b, 1));
+            int info = 0;
+            RLB_CHECK(potrf_blocked<T>(ctx, b, Gs, b, &info));
+            if (info != 0) { rc_out = 1; break; }
+            RLB_CUDA_OK(ctx, cudaMemsetAsync(R_tall, 0, sizeof(T) * nb * nb, ctx->stream));
+            RLB_CHECK(tri_op<T>(ctx, 0, b, b, Gs, b, R_tall, b));
+            RLB_CHECK(trsm_right_upper<T>(ctx, rows, b, R_tall, b, AB1, lda));
+            {
+                LaunchScope ls(ctx, RLB200_TIMER_SMALL);
+                orhr_getrfnp_kernel<T><<<1, 1024, 0, ctx->stream>>>((int)b, AB1, lda, Dv);
+                RLB_CUDA_OK(ctx, cudaGetLastError());
+            }
+            if (rows > b) RLB_CHECK(trsm_right_upper<T>(ctx, rows - b, b, AB1, lda, AB1 + b, lda));
+            const unsigned nbk = (unsigned)std::min<int64_t>((b * b + 255) / 256, 1024);
+            {
+                LaunchScope ls(ctx, RLB200_TIMER_SMALL, 2);
+                unit_lower_kernel<T><<<nbk, 256, 0, ctx->stream>>>((int)b, AB1, lda, V1c, (int)b);
+                orhr_rhs_kernel<T><<<nbk, 256, 0, ctx->stream>>>((int)b, AB1, lda, Dv, T_dat, (int)b);
+                RLB_CUDA_OK(ctx, cudaGetLastError());
+            }
+            RLB_CHECK(transpose<T>(ctx, b, b, V1c, b, Gs, b));
+            RLB_CHECK(trsm_right_upper<T>(ctx, b, b, Gs, b, T_dat, b));
+            {
+                LaunchScope ls(ctx, RLB200_TIMER_SMALL, 2);
+                diag_copy_kernel<T><<<(unsigned)((b + 255) / 256), 256, 0, ctx->stream>>>((int)b, T_dat, (int)b, tau1);
+                scale_rows_upper_kernel<T><<<nbk, 256, 0, ctx->stream>>>((int)b, R_tall, (int)b, Dv);
+                RLB_CUDA_OK(ctx, cudaGetLastError());
+            }
+            RLB_CHECK(tri_op<T>(ctx, 0, b, b, R_tall, b, AB1, lda));                                // lacpy(Upper) (:542)
+            t_ready = true;
+        } else {
+            RLB_CHECK(qr_small<T>(ctx, false, rows, b, AB1, lda, nullptr, tau1, qr_ws));           // geqrf (:464-502) / the unblocked loop
+        }
+        const int64_t k = std::min(rows, b);                                            // reflectors of this panel (= b: b <= m - j)
+        if (!t_ready) {
+            // larft(Forward, Columnwise) from G = V^T V and tau (:770-775, :492-497)
+            {
+                LaunchScope ls(ctx, RLB200_TIMER_SMALL);
+                unit_lower_kernel<T><<<(unsigned)std::min<int64_t>((k * k + 255) / 256, 1024), 256, 0, ctx->stream>>>((int)k, AB1, lda, V1c, (int)k);
+                RLB_CUDA_OK(ctx, cudaGetLastError());
+            }
+            RLB_CHECK(gemm_tn<T>(ctx, k, k, k, 1.0, V1c, k, V1c, k, 0.0, Gs, k, 0));
+            if (rows > k) RLB_CHECK(gemm_tn<T>(ctx, rows - k, k, k, 1.0, AB1 + k, lda, AB1 + k, lda, 1.0, Gs, k, 0));
+            RLB_CUDA_OK(ctx, cudaMemsetAsync(T_dat, 0, sizeof(T) * nb * nb, ctx->stream));
+            LaunchScope ls(ctx, RLB200_TIMER_SMALL);
+            larft_gram_kernel<T><<<1, 1024, sizeof(double) * k, ctx->stream>>>((int)k, Gs, (int)k, tau1, T_dat, (int)k);
+            RLB_CUDA_OK(ctx, cudaGetLastError());
+        }
+        t_qr += pt.lap();
+        // ---- [A12; A22] <- Q^T [A12; A22] (:1091-1100)
+        if (nc > 0) RLB_CHECK(apply_qt_wy<T>(ctx, rows, k, nc, V1c, AB1 + k, lda, T_dat, k, A + j + (j + b) * lda, lda, Wa, Wb));
+        t_updA += pt.lap();
+        // ---- NoFLA_Downdate_Y (:206-296): Y2 -= (G1 - (G1 U11 + G2 U21) T U11^T) R12, then GR <- GR Q
+        if (!last_iter) {
+            T* G1 = G + j * mY;
+            T* G2 = G + (j + b) * mY;
+            const int64_t m21 = rows - b;
+            RLB_CHECK(gemm_nn<T>(ctx, mY, b, b, 1.0, G1, mY, V1c, b, 0.0, Bm, mY));                                   // G1 U11
+            if (m21 > 0) RLB_CHECK(gemm_nn<T>(ctx, mY, b, m21, 1.0, G2, mY, AB1 + b, lda, 1.0, Bm, mY));              //   + G2 U21
+            RLB_CHECK(gemm_nn<T>(ctx, mY, b, b, 1.0, Bm, mY, T_dat, k, 0.0, Bm2, mY));                                // ... T
+            RLB_CUDA_OK(ctx, cudaMemcpyAsync(Bf, G1, sizeof(T) * mY * b, cudaMemcpyDeviceToDevice, ctx->stream));
+            RLB_CHECK(gemm_nt<T>(ctx, mY, b, b, -1.0, Bm2, mY, V1c, b, 1.0, Bf, mY));                                 // G1 - ... U11^T
+            if (nc > 0) RLB_CHECK(gemm_nn<T>(ctx, mY, nc, b, -1.0, Bf, mY, A + j + (j + b) * lda, lda, 1.0, Y + (j + b) * mY, mY));
+            RLB_CHECK(gemm_nt<T>(ctx, mY, b, b, -1.0, Bm2, mY, V1c, b, 1.0, G1, mY));                                 // G1 <- G1 - (GR U) T U11^T
+            if (m21 > 0) RLB_CHECK(gemm_nt<T>(ctx, mY, m21, b, -1.0, Bm2, mY, AB1 + b, lda, 1.0, G2, mY));            // G2 <- G2 - (GR U) T U21^T
+        }
+        t_updS += pt.lap();
+    }
+    RLB_CUDA_OK(ctx, cudaMemcpyAsync(J_dev, J.data(), sizeof(int64_t) * n, cudaMemcpyHostToDevice, ctx->stream));
+    RLB_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+    if (pt.on) {
+        // the first nine entries of the reference's timing vector (:1140-1148): preallocation, sketching, downdating (a debug check there),
+        // qrcp, qr, updating A, updating the sketch, other, total
+        pt.lap();
+        const long long tot = pt.total();
+        ctx->phase_us = {t_pre, t_sk, 0, t_qrcp, t_qr, t_updA, t_updS, tot - (t_pre + t_sk + t_qrcp + t_qr + t_updA + t_updS), tot};
+    }
+    return rc_out;
+}
+
 #define INST(T)                                                                                                      \
     template int transpose<T>(Ctx*, int64_t, int64_t, const T*, int64_t, T*, int64_t);                               \
     template int make_unit_lower<T>(Ctx*, int64_t, const T*, int64_t, T*, int64_t);                                  \
     template int larft_from_gram<T>(Ctx*, int64_t, const T*, int64_t, const T*, T*, int64_t);                        \
     template int set_upper_diag<T>(Ctx*, int64_t, T*, int64_t, T, bool);                                             \
+    template int hqrrp_call<T>(Ctx*, int64_t, int64_t, T*, int64_t, int64_t*, T*, int64_t, int64_t, int, int, uint32_t*);                 \
     template int bqrrp_call<T>(Ctx*, int64_t, int64_t, T*, int64_t, T, int64_t, int, int, T*, int64_t*, int64_t*, uint32_t*, T*, int64_t);
 INST(double)
 INST(float)

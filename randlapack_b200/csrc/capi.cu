@@ -194,11 +194,15 @@ int rlb200_set_fp64_engine(rlb200_ctx* ctx, int engine) {
 int rlb200_set_cqrrpt_orthogonalization(rlb200_ctx* ctx, int on) { CTX_OK(ctx); ctx->cqrrpt_orth = on != 0; return 0; }
 int rlb200_set_cqrrpt_qrcp(rlb200_ctx* ctx, int qrcp) {
     CTX_OK(ctx);
-    if (qrcp != RLB200_CQRRPT_QRCP_GEQP3 && qrcp != RLB200_CQRRPT_QRCP_BQRRP) {
-        ctx->err = "CQRRPT qrcp: geqp3 and bqrrp are offered (hqrrp is not)";
-        return RLB200_ERR_UNSUPPORTED;
-    }
+    RLB_REQUIRE(ctx, qrcp == RLB200_CQRRPT_QRCP_GEQP3 || qrcp == RLB200_CQRRPT_QRCP_BQRRP || qrcp == RLB200_CQRRPT_QRCP_HQRRP);
     ctx->cqrrpt_qrcp = qrcp;
+    return 0;
+}
+int rlb200_set_cqrrpt_hqrrp_opts(rlb200_ctx* ctx, int64_t nb_alg, int64_t oversampling, int panel_pivoting, int use_cholqr) {
+    CTX_OK(ctx);
+    RLB_REQUIRE(ctx, nb_alg > 0 && oversampling >= 0 && use_cholqr >= 0 && use_cholqr <= 2);
+    ctx->cqrrpt_nb_alg = nb_alg; ctx->cqrrpt_oversampling = oversampling;
+    ctx->cqrrpt_panel_pivoting = panel_pivoting != 0; ctx->cqrrpt_use_cholqr = use_cholqr;
     return 0;
 }
 int rlb200_set_bqrrp_tol(rlb200_ctx* ctx, double tol) {
@@ -397,6 +401,31 @@ int rlb200_set_i8_digits(rlb200_ctx* ctx, int digits) {
         RLB_CUDA_OK(ctx, cudaMemcpy2DAsync(dA, m * sizeof(T), A, lda * sizeof(T), m * sizeof(T), n, cudaMemcpyHostToDevice, ctx->stream)); \
         RLB_CUDA_OK(ctx, cudaMemcpyAsync(dtau, tau, sizeof(T) * n, cudaMemcpyHostToDevice, ctx->stream));                           \
         int rc = bqrrp_call<T>(ctx, m, n, dA, m, d_factor, block_size, qrcp_wide, qr_tall, dtau, dJ, rank, state);                  \
+        if (rc < 0) return rc;                                                                                                      \
+        RLB_CUDA_OK(ctx, cudaMemcpy2DAsync(A, lda * sizeof(T), dA, m * sizeof(T), m * sizeof(T), n, cudaMemcpyDeviceToHost, ctx->stream)); \
+        RLB_CUDA_OK(ctx, cudaMemcpyAsync(tau, dtau, sizeof(T) * n, cudaMemcpyDeviceToHost, ctx->stream));                           \
+        RLB_CUDA_OK(ctx, cudaMemcpyAsync(J, dJ, sizeof(int64_t) * n, cudaMemcpyDeviceToHost, ctx->stream));                         \
+        RLB_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));                                                                       \
+        return rc;                                                                                                                  \
+    }                                                                                                                               \
+    int rlb200_hqrrp_##SUF##_dev(rlb200_ctx* ctx, int64_t m, int64_t n, T* A_dev, int64_t lda, int64_t* J_dev, T* tau_dev,          \
+                                 int64_t nb_alg, int64_t pp, int panel_pivoting, int qr_type, uint32_t state[6]) {                  \
+        CTX_OK(ctx); RLB_CHECK(bind(ctx)); RLB_REQUIRE(ctx, state != nullptr);                                                      \
+        return hqrrp_call<T>(ctx, m, n, A_dev, lda, J_dev, tau_dev, nb_alg, pp, panel_pivoting, qr_type, state);                    \
+    }                                                                                                                               \
+    int rlb200_hqrrp_##SUF##_host(rlb200_ctx* ctx, int64_t m, int64_t n, T* A, int64_t lda, int64_t* J, T* tau, int64_t nb_alg,     \
+                                  int64_t pp, int panel_pivoting, int qr_type, uint32_t state[6]) {                                 \
+        CTX_OK(ctx); RLB_CHECK(bind(ctx)); RLB_REQUIRE(ctx, state != nullptr);                                                      \
+        RLB_REQUIRE(ctx, m >= 0 && n >= 0 && lda >= (m > 1 ? m : 1));                                                               \
+        if (m == 0 || n == 0) return hqrrp_call<T>(ctx, m, n, A, lda, J, tau, nb_alg, pp, panel_pivoting, qr_type, state);          \
+        RLB_REQUIRE(ctx, A && tau && J);                                                                                            \
+        ArenaScope as(ctx);                                                                                                         \
+        T* dA = as.take<T>((size_t)m * n); if (!dA) return RLB200_ERR_ALLOC;                                                        \
+        T* dtau = as.take<T>((size_t)n); if (!dtau) return RLB200_ERR_ALLOC;                                                        \
+        int64_t* dJ = as.take<int64_t>((size_t)n); if (!dJ) return RLB200_ERR_ALLOC;                                                \
+        RLB_CUDA_OK(ctx, cudaMemcpy2DAsync(dA, m * sizeof(T), A, lda * sizeof(T), m * sizeof(T), n, cudaMemcpyHostToDevice, ctx->stream)); \
+        RLB_CUDA_OK(ctx, cudaMemcpyAsync(dtau, tau, sizeof(T) * n, cudaMemcpyHostToDevice, ctx->stream));                           \
+        int rc = hqrrp_call<T>(ctx, m, n, dA, m, dJ, dtau, nb_alg, pp, panel_pivoting, qr_type, state);                             \
         if (rc < 0) return rc;                                                                                                      \
         RLB_CUDA_OK(ctx, cudaMemcpy2DAsync(A, lda * sizeof(T), dA, m * sizeof(T), m * sizeof(T), n, cudaMemcpyDeviceToHost, ctx->stream)); \
         RLB_CUDA_OK(ctx, cudaMemcpyAsync(tau, dtau, sizeof(T) * n, cudaMemcpyDeviceToHost, ctx->stream));                           \

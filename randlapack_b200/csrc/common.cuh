@@ -79,7 +79,10 @@ struct Ctx {
     // steady_clock around synchronous BLAS calls)
     bool phase_timing = false;
     bool cqrrpt_orth = false;    // CQRRPT::orthogonalization (rl_cqrrpt.hh:139-142)
-    int cqrrpt_qrcp = 0;         // CQRRPT::qrcp (rl_cqrrpt.hh:41): 0 = geqp3 (default), 1 = bqrrp
+    int cqrrpt_qrcp = 0;         // CQRRPT::qrcp (rl_cqrrpt.hh:41): 0 = geqp3 (default), 1 = bqrrp, 2 = hqrrp
+    // CQRRPT's HQRRP fields (rl_cqrrpt.hh:134-137; constructor defaults :60-63)
+    int64_t cqrrpt_nb_alg = 64, cqrrpt_oversampling = 10;
+    int cqrrpt_panel_pivoting = 1, cqrrpt_use_cholqr = 0;
     double bqrrp_tol = 0.0;      // BQRRP::tol (rl_bqrrp.hh:141): 0 = the constructor default, eps of the working type
     std::vector<long long> phase_us;
     // stats

@@ -699,7 +699,7 @@ int cqrrpt_call(Ctx* ctx, int64_t m, int64_t n, T* A, int64_t lda, T* R, int64_t
     // SASO (:214-221); state <- S.next_state
     RLB_CHECK(sketch_sparse_left<T>(ctx, d, mg, nnz, d, n, m, (T)1, 0, 0, A, lda, (T)0, A_hat, d, state));
     t_saso = pt.lap();
-    // QRCP of the sketch: geqp3 (:247) or BQRRP with the reference's block ratio (:232-244)
+    // QRCP of the sketch: geqp3 (:247), BQRRP with the reference's block ratio (:232-244) or hqrrp (:230-231)
     if (ctx->cqrrpt_qrcp == RLB200_CQRRPT_QRCP_BQRRP) {
         if (sharded) { ctx->err = "CQRRPT with qrcp = bqrrp is not offered on a row-sharded context"; return RLB200_ERR_UNSUPPORTED; }
         const T ratio = n <= 2000 ? (T)1 : (n <= 8000 ? (T)0.5 : (T)1 / (T)32);
@@ -710,6 +710,12 @@ int cqrrpt_call(Ctx* ctx, int64_t m, int64_t n, T* A, int64_t lda, T* R, int64_t
         const int rcb = bqrrp_call<T>(ctx, d, n, A_hat, d, (T)1, bsz, RLB200_QRCP_LUQR, RLB200_QRTALL_GEQRF, tau, J_dev, &rank_b, state);
         ctx->bqrrp_tol = tol_saved;
         if (rcb < 0) return rcb;
+    } else if (ctx->cqrrpt_qrcp == RLB200_CQRRPT_QRCP_HQRRP) {
+        // hqrrp(d, n, A_hat, d, J, tau, nb_alg, oversampling, panel_pivoting, use_cholqr, state, nullptr) (:230-231)
+        if (sharded) { ctx->err = "CQRRPT with qrcp = hqrrp is not offered on a row-sharded context"; return RLB200_ERR_UNSUPPORTED; }
+        const int rch = hqrrp_call<T>(ctx, d, n, A_hat, d, J_dev, tau, ctx->cqrrpt_nb_alg, ctx->cqrrpt_oversampling, ctx->cqrrpt_panel_pivoting,
+                                      ctx->cqrrpt_use_cholqr, state);
+        if (rch < 0) return rch;
     } else {
         ArenaScope as2(ctx);
         void* ws = arena_push(ctx, qrcp_ws_bytes(n)); RLB_ALLOC(ctx, ws);

@@ -104,7 +104,8 @@ template <typename T>
 int trsm_right_upper(Ctx* ctx, int64_t m, int64_t k, const T* R, int64_t ldr, T* X, int64_t ldx);
 size_t qrcp_ws_bytes(int64_t n);
 template <typename T>
-int qr_small(Ctx* ctx, bool pivot, int64_t d, int64_t n, T* A, int64_t lda, int64_t* jpvt_dev, T* tau_dev, void* ws);
+int qr_small(Ctx* ctx, bool pivot, int64_t d, int64_t n, T* A, int64_t lda, int64_t* jpvt_dev, T* tau_dev, void* ws, int64_t stages = -1,
+             double tol3z_in = 0.0);
 
 template <typename T>
 int make_unit_lower(Ctx* ctx, int64_t n, const T* src, int64_t lds, T* dst, int64_t ldd);
@@ -168,5 +169,12 @@ int revd2_call(Ctx* ctx, int uplo, int64_t m, const T* A, int64_t lda, int64_t* 
 template <typename T>
 int bqrrp_call(Ctx* ctx, int64_t m, int64_t n, T* A, int64_t lda, T d_factor, int64_t block_size, int qrcp_wide, int qr_tall, T* tau,
                int64_t* J_dev, int64_t* rank_out, uint32_t state[6], T* A_sk_ext = nullptr, int64_t d_ext = 0);
+
+// hqrrp (rl_hqrrp.hh:811-1196): Householder QR with randomized pivoting, GEQP3 output format (A: R + reflectors, tau, J 1-based).
+// qr_type (panel QR when panel_pivoting == 0): 0 / 1 Householder, 2 CholQR + Householder reconstruction.  Returns 0; 1 when the Cholesky
+// factorization of a panel's Gram matrix fails (qr_type 2; the reference goes on with an unfactored panel there).
+template <typename T>
+int hqrrp_call(Ctx* ctx, int64_t m, int64_t n, T* A, int64_t lda, int64_t* J_dev, T* tau, int64_t nb_alg, int64_t pp, int panel_pivoting,
+               int qr_type, uint32_t state[6]);
 
 }  // namespace rlb

@@ -611,10 +611,13 @@ size_t qrcp_ws_bytes(int64_t n) { return ws_round(sizeof(double) * n) * 2 + ws_r
 
 // geqp3 (pivot = true; jpvt_dev receives 1-based GEQP3-style pivots, all columns free) or geqrf (pivot = false; jpvt_dev unused)
 // of the d x n matrix A (lda); tau_dev has min(d, n) entries.  R ends up in the upper triangle, reflectors below it.
+// stages >= 0: only the first min(stages, d, n) Householder steps are taken (the num_stages of NoFLA_QRPmod_WY_unb_var4, rl_hqrrp.hh:556-575:
+// jpvt then holds exactly the column swaps of those steps).  tol3z_in > 0 replaces sqrt(eps of T) in the norm-downdate recompute rule
+// (rl_hqrrp.hh:376-378 takes sqrt(dlamch('E')) for every T).
 template <typename T>
-int qr_small(Ctx* ctx, bool pivot, int64_t d, int64_t n, T* A, int64_t lda, int64_t* jpvt_dev, T* tau_dev, void* ws) {
+int qr_small(Ctx* ctx, bool pivot, int64_t d, int64_t n, T* A, int64_t lda, int64_t* jpvt_dev, T* tau_dev, void* ws, int64_t stages, double tol3z_in) {
     RLB_REQUIRE(ctx, d >= 0 && n >= 0 && lda >= std::max<int64_t>(d, 1));
-    const int64_t kmin = std::min(d, n);
+    const int64_t kmin = stages >= 0 ? std::min(stages, std::min(d, n)) : std::min(d, n);
     if (kmin == 0) {
         if (pivot && n > 0) { iota_i64_kernel<T><<<(unsigned)std::min<int64_t>((n + 255) / 256, 1024), 256, 0, ctx->stream>>>(n, jpvt_dev, 1); }
         return 0;
@@ -625,7 +628,7 @@ int qr_small(Ctx* ctx, bool pivot, int64_t d, int64_t n, T* A, int64_t lda, int6
     QrcpStep* step = cv.take<QrcpStep>(1);
     const double eps = sizeof(T) == 8 ? 1.1102230246251565e-16 : 5.9604644775390625e-08;       // lamch('Epsilon')
     const double safmin = (sizeof(T) == 8 ? 2.2250738585072014e-308 : 1.1754943508222875e-38) / eps;
-    const double tol3z = std::sqrt(eps);
+    const double tol3z = tol3z_in > 0.0 ? tol3z_in : std::sqrt(eps);
     // one cooperative launch (qr_coop_kernel) whenever the reflector fits shared memory and the grid can be co-resident
     // (measured, tools/bench_qrcp.py: 4096 x 2048: 91.7 -> 41.2 ms; with more than ~8 columns per group and step the two-launch form, whose apply
     //  kernel spreads the columns over 8 CTAs per SM, is faster: 256 x 65536: 19.8 vs 35.9 ms)
@@ -686,7 +689,7 @@ int qr_small(Ctx* ctx, bool pivot, int64_t d, int64_t n, T* A, int64_t lda, int6
     template int tri_op<T>(Ctx*, int, int64_t, int64_t, const T*, int64_t, T*, int64_t);                     \
     template int potrf_blocked<T>(Ctx*, int64_t, T*, int64_t, int*);                                         \
     template int trsm_right_upper<T>(Ctx*, int64_t, int64_t, const T*, int64_t, T*, int64_t);                \
-    template int qr_small<T>(Ctx*, bool, int64_t, int64_t, T*, int64_t, int64_t*, T*, void*);
+    template int qr_small<T>(Ctx*, bool, int64_t, int64_t, T*, int64_t, int64_t*, T*, void*, int64_t, double);
 INST(double)
 INST(float)
 

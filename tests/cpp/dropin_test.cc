@@ -106,6 +106,27 @@ int main() {
         int rcb = bq.call(m, n, Ab.data(), m, 1.0, tauq.data(), Jq.data(), st2);
         std::printf("standalone BQRRP: rc=%d rank=%lld\n", rcb, (long long)bq.rank);
         fails += !(rcb == 0 && bq.rank > 0 && bq.rank <= n);
+        // hqrrp with the reference's argument list and CQRRPT with qrcp = hqrrp (rl_cqrrpt.hh:230-231)
+        std::vector<double> Ah = A;
+        rlb200::RNGState st3(0);
+        int64_t rch = rlb200::hqrrp<double>(m, n, Ah.data(), m, Jq.data(), tauq.data(), 16, 4, 1, 0, st3, (double**)nullptr);
+        std::vector<int64_t> seen(n, 0);
+        for (int64_t i = 0; i < n; ++i) if (Jq[i] >= 1 && Jq[i] <= n) seen[Jq[i] - 1] += 1;
+        bool perm_ok = true, diag_ok = true;
+        for (int64_t i = 0; i < n; ++i) perm_ok = perm_ok && seen[i] == 1;
+        diag_ok = std::abs(Ah[k + k * m]) <= 1e-6 * std::abs(Ah[0]) && std::abs(Ah[(k - 1) + (k - 1) * m]) >= 1e-4 * std::abs(Ah[0]);
+        std::printf("standalone hqrrp: rc=%lld permutation %d  rank %lld revealed on R's diagonal %d\n", (long long)rch, (int)perm_ok, (long long)k, (int)diag_ok);
+        fails += !(rch == 0 && perm_ok && diag_ok);
+        std::vector<double> Aq2 = A;
+        std::fill(Rq.begin(), Rq.end(), 0.0);
+        rlb200::CQRRPT<double> cqh(false, std::pow(std::numeric_limits<double>::epsilon(), 0.85));
+        cqh.qrcp = rlb200::CQRRPTSubroutines::hqrrp;
+        cqh.nb_alg = 16; cqh.oversampling = 4;
+        rlb200::RNGState st4(0);
+        int rcq2 = cqh.call(m, n, Aq2.data(), m, Rq.data(), n, Jq.data(), 2.0, st4);
+        double eq2 = orth_err(m, cqh.rank, Aq2.data());
+        std::printf("standalone CQRRPT(qrcp = hqrrp): rc=%d rank=%lld ||Q'Q-I||=%.2e\n", rcq2, (long long)cqh.rank, eq2);
+        fails += !(rcq2 == 0 && cqh.rank >= k && cqh.rank <= n && eq2 <= 1e-9);
     }
     {
         // REVD2 on a planted PSD matrix of rank 12, only the lower triangle valid (test/drivers/test_revd2.cc: Uplo)
@@ -260,6 +281,21 @@ int main() {
         std::printf("with-ref BQRRP: rank %lld / %lld  J equal %d  max|dA| %.2e  max|dtau| %.2e  state %d / %d\n", (long long)bq_ref.rank,
                     (long long)bq_dev.rank, (int)(J0 == J1), dA, dt, s0, s1);
         fails += !(bq_ref.rank == bq_dev.rank && J0 == J1 && dA <= 1e-9 && dt <= 1e-9 && s0 == s1);
+
+        // hqrrp, the reference's free function (rl_hqrrp.hh:811) and rlb200::hqrrp with the same argument list
+        auto call_hq = [&](bool dev, std::vector<double>& A, std::vector<double>& tau, std::vector<int64_t>& J) {
+            auto st = RandBLAS::RNGState<RNG>();
+            gen(A, st);
+            if (dev) rlb200::hqrrp<double>(mq, nq, A.data(), mq, J.data(), tau.data(), 32, 8, 1, 0, st, (double**)nullptr);
+            else RandLAPACK::hqrrp(mq, nq, A.data(), mq, J.data(), tau.data(), (int64_t)32, (int64_t)8, (int64_t)1, (int64_t)0, st, (double**)nullptr);
+            return (int)st.counter.v[0];
+        };
+        s0 = call_hq(false, A0, t0, J0); s1 = call_hq(true, A1, t1, J1);
+        dA = 0; dt = 0;
+        for (int64_t i = 0; i < mq * nq; ++i) dA = std::max(dA, std::abs(A0[i] - A1[i]));
+        for (int64_t i = 0; i < nq; ++i) dt = std::max(dt, std::abs(t0[i] - t1[i]));
+        std::printf("with-ref hqrrp: J equal %d  max|dA| %.2e  max|dtau| %.2e  state %d / %d\n", (int)(J0 == J1), dA, dt, s0, s1);
+        fails += !(J0 == J1 && dA <= 1e-9 && dt <= 1e-9 && s0 == s1);
     }
     {
         // the reference's REVD2 on its own SYRF / SYPS / HQRQ objects vs rlb200::REVD2, same matrix (test_revd2.cc recipe), same state

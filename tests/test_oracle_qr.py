@@ -141,3 +141,52 @@ def test_cqrrpt_orthogonalization_mode(shape):
     assert np.abs(np.triu(Rm[:rank, :rank]) - np.triu(R2[:rank, :rank])).max() <= 1e-11 * np.abs(Rm).max()
     assert np.abs(np.abs(Q) - np.abs(Q2)).max() <= 1e-10
     assert np.linalg.norm(Q2.T @ Q2 - np.eye(n)) <= 1e-12
+
+
+from _qrcases import GH, check_hqrrp_against_golden, hq_input  # noqa: E402
+
+
+@pytest.mark.parametrize("i", range(int(GH["hq_count"])))
+def test_hqrrp_golden(i):
+    """The restatement of RandLAPACK::hqrrp (rl_hqrrp.hh:811-1196) against golden vectors of the compiled reference
+    (tests/golden/make_golden_hqrrp.py): code, RNG state and pivots exact, R / tau to round-off, test_hqrrp.cc's acceptance measures."""
+    A, st, c = hq_input(i)
+    rc, F, tau, J, st2 = O.hqrrp(A, c["nb_alg"], c["pp"], c["panel_pivoting"], c["qr_type"], st)
+    check_hqrrp_against_golden(i, c, A, rc, F, tau, J, st2.words())
+
+
+def test_hqrrp_quick_return_and_tall_operator():
+    """min(m, n) = 0 returns before the pivot vector is initialised (rl_hqrrp.hh:886-888); nb_alg + pp > m makes DenseDist(nb_alg + pp, m)
+    a TALL operator whose natural layout is column-major."""
+    rc, F, tau, J, st = O.hqrrp(np.zeros((0, 5)), 4, 2, 1, 0, O.RNGState(3))
+    assert rc == 0 and not J.any() and list(st.words()) == list(O.RNGState(3).words())
+    L = _ref.ref_lib()
+    if L is None:
+        return
+    A, s0 = _ref.ref_mat_gen(L, 0, 40, 30, 30, 10.0, 2.0, [0] * 6, np.float64)
+    rc, F, tau, J, s1 = _ref.ref_hqrrp(L, A, 64, 10, 1, 0, s0)
+    rc2, F2, tau2, J2, st2 = O.hqrrp(A, 64, 10, 1, 0, O.RNGState.from_words(s0))
+    assert rc == rc2 and np.array_equal(J, J2) and list(st2.words()) == s1
+    assert np.abs(np.triu(F[:30]) - np.triu(F2[:30])).max() <= 1e-12
+
+
+@pytest.mark.skipif(_ref.ref_lib() is None, reason="compiled reference not present")
+@pytest.mark.parametrize("shape", [(3000, 200, 1e3, 1.5, 64, 10), (2000, 120, 10.0, 1.25, 32, 8)])
+def test_cqrrpt_qrcp_hqrrp(shape):
+    """CQRRPT with qrcp = hqrrp (rl_cqrrpt.hh:41, 230-231): the oracle against the compiled reference with the same field set
+    (test/drivers/test_cqrrpt.cc:184-304 runs this option on 10000 x 200)."""
+    L = _ref.ref_lib()
+    m, n, cond, df, nb, ov = shape
+    A, st = O.gen_poly_mat(m, n, n, cond, 2.0, O.RNGState(0))
+    alg = O.CQRRPT(float(np.finfo(np.float64).eps) ** 0.85, 2)
+    alg.qrcp = "hqrrp"
+    if (nb, ov) == (64, 10):          # the compiled reference's constructor defaults
+        rc, rank, Q, Rm, J, st2 = _ref.ref_cqrrpt(L, A, df, list(st.words()), None, 2, qrcp=2)
+    else:
+        alg.nb_alg, alg.oversampling = nb, ov
+    rc2, Q2, R2, J2, st3 = alg.call(A, df, st)
+    if (nb, ov) == (64, 10):
+        assert (rc, rank) == (rc2, alg.rank) and list(st3.words()) == st2 and np.array_equal(J, J2)
+        assert np.abs(np.triu(Rm) - np.triu(R2)).max() <= 1e-12 * np.abs(Rm).max()
+    e = qr_invariants(A, Q2, R2, J2, alg.rank)
+    assert alg.rank == n and max(e) <= np.finfo(np.float64).eps ** 0.75
