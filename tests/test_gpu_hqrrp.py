@@ -79,7 +79,7 @@ def test_hqrrp_quick_return_host_call_and_timing(ctx):
     nt = ctx._lib.rlb200_get_phase_times(ctx._h, buf, 32)
     ctx.check(ctx._lib.rlb200_set_phase_timing(ctx._h, 0))
     assert rc2 == rc and np.array_equal(J2.numpy(), Jd) and list(s2.words()) == list(s1.words())
-    assert np.array_equal(np.asfortranarray(Ah.numpy()), F) and np.array_equal(tau2.numpy(), tau)
+    assert np.abs(np.asfortranarray(Ah.numpy()) - F).max() <= 1e-12 and np.abs(tau2.numpy() - tau).max() <= 1e-12
     t = list(buf)[:nt]
     assert nt == 9 and all(x >= 0 for x in t) and sum(t[:8]) == t[8] and t[8] > 0
 
