@@ -301,7 +301,7 @@ def test_cqrrpt_qrcp_bqrrp_vs_oracle(ctx, shape):
     assert np.abs(np.triu(R[:k]) - np.triu(R2[:k])).max() <= 1e-9 * np.abs(R2).max()
     e = qr_invariants(A, Q, R, J, k)
     assert max(e) <= np.finfo(np.float64).eps ** 0.75, e
-    alg.qrcp = "hqrrp"
+    alg.qrcp = "lu"                                   # not one of the reference's three choices (rl_cqrrpt.hh:39-43)
     with pytest.raises(rl.Error):
         alg.call(ctx, dev(A), df, rl.RNGState(0))
     ctx.check(ctx._lib.rlb200_set_cqrrpt_qrcp(ctx._h, 0))
