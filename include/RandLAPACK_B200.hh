@@ -117,6 +117,7 @@ template <> struct abi<double> {
     static constexpr auto bqrrp_dev_sk = rlb200_bqrrp_f64_dev_sk; static constexpr auto cqrrt_host = rlb200_cqrrt_f64_host;
     static constexpr auto syps = rlb200_syps_f64_dev; static constexpr auto syrf = rlb200_syrf_f64_dev; static constexpr auto revd2_host = rlb200_revd2_f64_host;
     static constexpr auto gemm = rlb200_gemm_f64_dev;
+    static constexpr auto sketch_sparse_left = rlb200_sketch_sparse_left_f64_dev; static constexpr auto sketch_dense_left = rlb200_sketch_dense_left_f64_dev;
 };
 template <> struct abi<float> {
     static constexpr auto stab = rlb200_stab_f32_dev; static constexpr auto rs = rlb200_rs_f32_dev; static constexpr auto rf = rlb200_rf_f32_dev;
@@ -126,6 +127,7 @@ template <> struct abi<float> {
     static constexpr auto bqrrp_dev_sk = rlb200_bqrrp_f32_dev_sk; static constexpr auto cqrrt_host = rlb200_cqrrt_f32_host;
     static constexpr auto syps = rlb200_syps_f32_dev; static constexpr auto syrf = rlb200_syrf_f32_dev; static constexpr auto revd2_host = rlb200_revd2_f32_host;
     static constexpr auto gemm = rlb200_gemm_f32_dev;
+    static constexpr auto sketch_sparse_left = rlb200_sketch_sparse_left_f32_dev; static constexpr auto sketch_dense_left = rlb200_sketch_dense_left_f32_dev;
 };
 
 // device buffer staged from / to a host pointer
@@ -643,13 +645,16 @@ public:
 #ifndef RLB200_WITH_RANDLAPACK
 enum class Layout : char { ColMajor = 'C', RowMajor = 'R' };
 enum class Op : char { NoTrans = 'N', Trans = 'T' };
-using layout_t = Layout; using op_t = Op;
+enum class Side : char { Left = 'L', Right = 'R' };
+using layout_t = Layout; using op_t = Op; using side_t = Side;
 inline bool is_colmajor(Layout l) { return l == Layout::ColMajor; }
 inline int op_code(Op o) { return o == Op::NoTrans ? 0 : 1; }
+inline bool is_left(Side s) { return s == Side::Left; }
 #else
-using layout_t = blas::Layout; using op_t = blas::Op;
+using layout_t = blas::Layout; using op_t = blas::Op; using side_t = blas::Side;
 inline bool is_colmajor(blas::Layout l) { return l == blas::Layout::ColMajor; }
 inline int op_code(blas::Op o) { return o == blas::Op::NoTrans ? 0 : 1; }
+inline bool is_left(blas::Side s) { return s == blas::Side::Left; }
 #endif
 
 template <typename T>
@@ -691,9 +696,70 @@ struct DenseLinOp {
         for (int64_t j = 0; j < n; ++j) std::memcpy(C + j * ldc, Cp.data() + j * m, sizeof(T) * m);
         ++n_products;
     }
+    // The overload with an explicit side (rl_dense_linop.hh:91-142): Side::Left as above; Side::Right: C := alpha * op(B) * op(A) + beta * C.
+    // This is the form CholQR_linops / sCholQR3_linops / CQRRT_linops call (rl_cholqr_linops.hh:169-171, rl_cqrrt_linops.hh:275-283).
+    void operator()(side_t side, layout_t layout, op_t trans_A, op_t trans_B, int64_t m, int64_t n, int64_t k, T alpha, const T* B, int64_t ldb,
+                    T beta, T* C, int64_t ldc) {
+        if (is_left(side)) { (*this)(layout, trans_A, trans_B, m, n, k, alpha, B, ldb, beta, C, ldc); return; }
+        if (!is_colmajor(layout)) throw Error(RLB200_ERR_UNSUPPORTED, "rlb200::DenseLinOp: ColMajor only");
+        const int ta = op_code(trans_A), tb = op_code(trans_B);
+        const int64_t rows_B = tb ? k : m, cols_B = tb ? m : k, rows_A = ta ? n : k, cols_A = ta ? k : n;
+        if (rows_A != n_rows || cols_A != n_cols) throw Error(RLB200_ERR_ARG, "DenseLinOp: (k, n, trans_A) do not match the operator");   // :131-132
+        if (ldb < rows_B || ldc < m) throw Error(RLB200_ERR_ARG, "DenseLinOp: ldb / ldc too small");                                        // :135-137
+        std::vector<T> Bp((size_t)rows_B * cols_B), Cp((size_t)m * n);
+        for (int64_t j = 0; j < cols_B; ++j) std::memcpy(Bp.data() + j * rows_B, B + j * ldb, sizeof(T) * rows_B);
+        if (beta != (T)0) for (int64_t j = 0; j < n; ++j) std::memcpy(Cp.data() + j * m, C + j * ldc, sizeof(T) * m);
+        detail::DevBuf<T> dB(*ctx_, rows_B * cols_B, Bp.data()), dC(*ctx_, m * n, beta != (T)0 ? Cp.data() : nullptr);
+        ctx_->check(detail::abi<T>::gemm(ctx_->get(), tb, ta, m, n, k, alpha, dB.ptr(), rows_B, dA_->ptr(), n_rows, beta, dC.ptr(), m));
+        dC.to_host(Cp.data(), m * n);
+        for (int64_t j = 0; j < n; ++j) std::memcpy(C + j * ldc, Cp.data() + j * m, sizeof(T) * m);
+        ++n_products;
+    }
+#ifdef RLB200_WITH_RANDLAPACK
+    // Sketching-operator overloads (rl_dense_linop.hh:236-300), Side::Right, ColMajor, NoTrans / NoTrans - the call CQRRT_linops makes
+    // (rl_cqrrt_linops.hh:204, 211): C (d x n, HOST) := alpha * S * A + beta * C.  The operator never crosses PCIe: the device regenerates it
+    // from S.dist and S.seed_state (bit-exact triplets / counter rule) and applies it to the resident matrix.
+    void operator()(side_t side, layout_t layout, op_t trans_A, op_t trans_S, int64_t d, int64_t n, int64_t m, T alpha,
+                    RandBLAS::SparseSkOp<T, r123::Philox4x32>& S, T beta, T* C, int64_t ldc) {
+        sk_check(side, layout, trans_A, trans_S, d, n, m, S.dist.n_rows, S.dist.n_cols, ldc);
+        if (S.dist.major_axis != RandBLAS::Axis::Short) throw Error(RLB200_ERR_UNSUPPORTED, "rlb200::DenseLinOp: short-axis (SASO) sparse operators only");
+        uint32_t w[6]; state_to_words(S.seed_state, w);
+        sk_apply(d, n, beta, C, ldc, [&](T* dC) {
+            return detail::abi<T>::sketch_sparse_left(ctx_->get(), S.dist.n_rows, S.dist.n_cols, S.dist.vec_nnz, d, n, m, alpha, 0, 0, dA_->ptr(), n_rows, beta, dC, d, w);
+        });
+    }
+    void operator()(side_t side, layout_t layout, op_t trans_A, op_t trans_S, int64_t d, int64_t n, int64_t m, T alpha,
+                    RandBLAS::DenseSkOp<T, r123::Philox4x32>& S, T beta, T* C, int64_t ldc) {
+        sk_check(side, layout, trans_A, trans_S, d, n, m, S.dist.n_rows, S.dist.n_cols, ldc);
+        uint32_t w[6]; state_to_words(S.seed_state, w);
+        const int fam = S.dist.family == RandBLAS::ScalarDist::Uniform ? RLB200_FAMILY_UNIFORM : RLB200_FAMILY_GAUSSIAN;
+        const int ax = S.dist.major_axis == RandBLAS::Axis::Short ? RLB200_AXIS_SHORT : RLB200_AXIS_LONG;
+        sk_apply(d, n, beta, C, ldc, [&](T* dC) {
+            return detail::abi<T>::sketch_dense_left(ctx_->get(), S.dist.n_rows, S.dist.n_cols, fam, ax, d, n, m, alpha, 0, 0, dA_->ptr(), n_rows, beta, dC, d, w);
+        });
+    }
+#endif
     T* device_ptr() { return dA_->ptr(); }
     int64_t n_products = 0;      // products executed on the device so far
 private:
+#ifdef RLB200_WITH_RANDLAPACK
+    void sk_check(side_t side, layout_t layout, op_t trans_A, op_t trans_S, int64_t d, int64_t n, int64_t m, int64_t S_rows, int64_t S_cols, int64_t ldc) {
+        if (is_left(side) || !is_colmajor(layout) || op_code(trans_A) || op_code(trans_S))
+            throw Error(RLB200_ERR_UNSUPPORTED, "rlb200::DenseLinOp with a sketching operator: Side::Right, ColMajor, NoTrans / NoTrans only");
+        if (m != n_rows || n != n_cols || S_rows != d || S_cols != m) throw Error(RLB200_ERR_ARG, "DenseLinOp: (d, n, m) do not match the operators");
+        if (ldc < d) throw Error(RLB200_ERR_ARG, "DenseLinOp: ldc too small");
+    }
+    template <typename F>
+    void sk_apply(int64_t d, int64_t n, T beta, T* C, int64_t ldc, F&& f) {
+        std::vector<T> Cp((size_t)d * n);
+        if (beta != (T)0) for (int64_t j = 0; j < n; ++j) std::memcpy(Cp.data() + j * d, C + j * ldc, sizeof(T) * d);
+        detail::DevBuf<T> dC(*ctx_, d * n, beta != (T)0 ? Cp.data() : nullptr);
+        ctx_->check(f(dC.ptr()));
+        dC.to_host(Cp.data(), d * n);
+        for (int64_t j = 0; j < n; ++j) std::memcpy(C + j * ldc, Cp.data() + j * d, sizeof(T) * d);
+        ++n_products;
+    }
+#endif
     Context* ctx_;
     std::shared_ptr<detail::DevBuf<T>> dA_;
     T fro_ = 0;

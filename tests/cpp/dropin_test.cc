@@ -19,6 +19,9 @@
 #include "RandLAPACK/drivers/rl_cqrrt.hh"
 #include "RandLAPACK/drivers/rl_bqrrp.hh"
 #include "RandLAPACK/drivers/rl_revd2.hh"
+#include "RandLAPACK/drivers/rl_cholqr_linops.hh"
+#include "RandLAPACK/drivers/rl_scholqr3_linops.hh"
+#include "RandLAPACK/drivers/rl_cqrrt_linops.hh"
 #include "RandLAPACK/testing/rl_gen.hh"
 #define RLB200_WITH_RANDLAPACK
 #endif
@@ -340,6 +343,52 @@ int main() {
         std::printf("with-ref REVD2 on rlb200::ExplicitSymLinOp: k %lld / %lld  max|d eig| %.2e  device products %lld  e[3] %.17g / %.17g\n", (long long)k0,
                     (long long)k2, de2, (long long)Sop.n_products(), e0[3], e2[3]);
         fails += !(k0 == k2 && de2 <= 1e-10 * e0[0] && sa.counter.v[0] == sc.counter.v[0] && Sop.n_products() > 0);
+    }
+    {
+        // The REFERENCE's operator-templated QR drivers - CholQR_linops (rl_cholqr_linops.hh:35), sCholQR3_linops (rl_scholqr3_linops.hh:50) and
+        // CQRRT_linops (rl_cqrrt_linops.hh:33; SASO and dense sketch) - on a device-resident rlb200::DenseLinOp: every operator product, and the
+        // sketch S A with S regenerated on the device from S.dist / S.seed_state, runs on the B200.  Same R as on the reference's own DenseLinOp.
+        const int64_t ml = 3000, nl = 64;
+        std::vector<double> Al(ml * nl, 0.0);
+        auto stl = RandBLAS::RNGState<RNG>();
+        RandLAPACK::gen::mat_gen_info<double> info((int64_t&)ml, (int64_t&)nl, RandLAPACK::gen::polynomial);
+        info.cond_num = 100; info.rank = nl; info.exponent = 2.0;
+        RandLAPACK::gen::mat_gen(info, Al.data(), stl);
+        RandLAPACK::linops::DenseLinOp<double> Ah(ml, nl, Al.data(), ml, blas::Layout::ColMajor);
+        rlb200::DenseLinOp<double> Ad(ml, nl, Al.data(), ml);
+        const double tol = std::pow(std::numeric_limits<double>::epsilon(), 0.85);
+        auto rdiff = [&](const std::vector<double>& R0, const std::vector<double>& R1) {
+            double d = 0, s = 0;
+            for (int64_t j = 0; j < nl; ++j)
+                for (int64_t i = 0; i <= j; ++i) { d = std::max(d, std::abs(R0[i + j * nl] - R1[i + j * nl])); s = std::max(s, std::abs(R0[i + j * nl])); }
+            return d / s;
+        };
+        std::vector<double> R0(nl * nl, 0.0), R1(nl * nl, 0.0);
+        RandLAPACK::CholQR_linops<double> c0(false, tol), c1(false, tol);
+        int rc0 = c0.call(Ah, R0.data(), nl), rc1 = c1.call(Ad, R1.data(), nl);
+        const double d_chol = rdiff(R0, R1);
+        std::fill(R0.begin(), R0.end(), 0.0); std::fill(R1.begin(), R1.end(), 0.0);
+        RandLAPACK::sCholQR3_linops<double> s0(false, tol), s1(false, tol);
+        int rs0 = s0.call(Ah, R0.data(), nl), rs1 = s1.call(Ad, R1.data(), nl);
+        const double d_s3 = rdiff(R0, R1);
+        double d_cq[2] = {0, 0};
+        int rq[2][2] = {{0, 0}, {0, 0}};
+        uint32_t sq[2][2] = {{0, 0}, {0, 0}};
+        for (int dense = 0; dense < 2; ++dense) {
+            std::fill(R0.begin(), R0.end(), 0.0); std::fill(R1.begin(), R1.end(), 0.0);
+            RandLAPACK::CQRRT_linops<double, RNG> q0(false, tol), q1(false, tol);
+            q0.use_dense_sketch = q1.use_dense_sketch = dense != 0;
+            q0.nnz = q1.nnz = 4;
+            auto sa = RandBLAS::RNGState<RNG>(11), sb = RandBLAS::RNGState<RNG>(11);
+            rq[dense][0] = q0.call(Ah, R0.data(), nl, 2.0, sa); rq[dense][1] = q1.call(Ad, R1.data(), nl, 2.0, sb);
+            sq[dense][0] = sa.counter.v[0]; sq[dense][1] = sb.counter.v[0];
+            d_cq[dense] = rdiff(R0, R1);
+        }
+        std::printf("with-ref linop drivers on rlb200::DenseLinOp: max|dR|/max|R|  CholQR_linops %.2e  sCholQR3_linops %.2e  CQRRT_linops saso %.2e dense %.2e"
+                    "  device products %lld\n", d_chol, d_s3, d_cq[0], d_cq[1], (long long)Ad.n_products);
+        // the dense sketch's Gaussians differ from the host libm's by a few float ulps (tests/test_gpu_fill.py): R of the preconditioned matrix moves by ~1e-7 relative
+        fails += !(rc0 == 0 && rc1 == 0 && rs0 == rs1 && rq[0][0] == rq[0][1] && rq[1][0] == rq[1][1] && sq[0][0] == sq[0][1] && sq[1][0] == sq[1][1] &&
+                   d_chol <= 1e-11 && d_s3 <= 1e-11 && d_cq[0] <= 1e-11 && d_cq[1] <= 1e-9 && Ad.n_products >= 8);
     }
 #endif
     std::printf(fails ? "DROPIN_FAIL\n" : "DROPIN_OK\n");
