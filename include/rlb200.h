@@ -203,6 +203,26 @@ RLB200_API int rlb200_sketch_dense_right_f32_dev(rlb200_ctx* ctx, int64_t S_rows
                                       int64_t d, int64_t n, float alpha, const float* A_dev, int64_t lda, int64_t ro_s, int64_t co_s,
                                       float beta, float* B_dev, int64_t ldb, uint32_t state[6]);
 
+/* sketch_general with every layout and transposition flag, dense operators (RandBLAS/RandBLAS/skge.hh:859-905 left -> lskge3 :100-203;
+ * :1031-1076 right -> rskge3 :253-356).  layout: RLB200_LAYOUT_COLMAJOR | RLB200_LAYOUT_ROWMAJOR; opS / opA: 0 NoTrans, 1 Trans.
+ *   left :  B(d x n) = alpha * op(submat(S))(d x m) * op(A)(m x n) + beta * B      submat(S) = the (d x m | m x d) block of S at (ro_s, co_s)
+ *   right:  B(m x d) = alpha * op(A)(m x n) * op(submat(S))(n x d) + beta * B
+ * lda / ldb follow `layout` as in the reference (:136-143, :289-296).  ColMajor with opA = NoTrans is the direct form; a data matrix that
+ * arrives transposed is transposed once into device scratch (m * n extra elements), a RowMajor result is formed in scratch and written
+ * through a transposing axpby.  state <- S.next_state.  Row-sharded contexts: the direct form only. */
+RLB200_API int rlb200_sketch_general_dense_left_f64_dev(rlb200_ctx* ctx, int layout, int opS, int opA, int64_t d, int64_t n, int64_t m, double alpha,
+                                             int64_t S_rows, int64_t S_cols, int family, int major_axis, int64_t ro_s, int64_t co_s,
+                                             const double* A_dev, int64_t lda, double beta, double* B_dev, int64_t ldb, uint32_t state[6]);
+RLB200_API int rlb200_sketch_general_dense_left_f32_dev(rlb200_ctx* ctx, int layout, int opS, int opA, int64_t d, int64_t n, int64_t m, float alpha,
+                                             int64_t S_rows, int64_t S_cols, int family, int major_axis, int64_t ro_s, int64_t co_s,
+                                             const float* A_dev, int64_t lda, float beta, float* B_dev, int64_t ldb, uint32_t state[6]);
+RLB200_API int rlb200_sketch_general_dense_right_f64_dev(rlb200_ctx* ctx, int layout, int opA, int opS, int64_t m, int64_t d, int64_t n, double alpha,
+                                              const double* A_dev, int64_t lda, int64_t S_rows, int64_t S_cols, int family, int major_axis,
+                                              int64_t ro_s, int64_t co_s, double beta, double* B_dev, int64_t ldb, uint32_t state[6]);
+RLB200_API int rlb200_sketch_general_dense_right_f32_dev(rlb200_ctx* ctx, int layout, int opA, int opS, int64_t m, int64_t d, int64_t n, float alpha,
+                                              const float* A_dev, int64_t lda, int64_t S_rows, int64_t S_cols, int family, int major_axis,
+                                              int64_t ro_s, int64_t co_s, float beta, float* B_dev, int64_t ldb, uint32_t state[6]);
+
 /* ---- blas::gemm as used on the path (ColMajor; rl_rs.hh:142,153,165; rl_rf.hh:123; rl_qb.hh:218;
  *      rl_rsvd.hh:148).  transa/transb: 0 = NoTrans, 1 = Trans.  Shapes the tall-skinny kernels cover:
  *      NN with the long dimension on m; TN with the long dimension on k (split-K, deterministic). */

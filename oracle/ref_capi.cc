@@ -212,6 +212,25 @@ static int sketch_dense_impl(bool left, int64_t S_rows, int64_t S_cols, int fami
     RL_CATCH
 }
 
+// sketch_general with every layout / transposition flag (RandBLAS/RandBLAS/skge.hh:859-905 left, :1031-1076 right); layout: 1 ColMajor, 2 RowMajor
+template <typename T>
+static int sketch_general_dense_impl(bool left, int layout, int opS, int opA, int64_t S_rows, int64_t S_cols, int family, int major_axis, int64_t d,
+                                     int64_t n, int64_t m, T alpha, int64_t ro, int64_t co, const T* A, int64_t lda, T beta, T* B, int64_t ldb,
+                                     uint32_t state[6]) {
+    RL_TRY
+    RandBLAS::DenseDist D(S_rows, S_cols, family == RL_FAMILY_UNIFORM ? RandBLAS::ScalarDist::Uniform : RandBLAS::ScalarDist::Gaussian,
+                          major_axis == RL_AXIS_SHORT ? RandBLAS::Axis::Short : RandBLAS::Axis::Long);
+    State st = load_state(state);
+    RandBLAS::DenseSkOp<T, RNG> S(D, st);
+    store_state(S.next_state, state);
+    const blas::Layout L = layout == 2 ? blas::Layout::RowMajor : blas::Layout::ColMajor;
+    const blas::Op oS = opS ? blas::Op::Trans : blas::Op::NoTrans, oA = opA ? blas::Op::Trans : blas::Op::NoTrans;
+    if (left) RandBLAS::sketch_general(L, oS, oA, d, n, m, alpha, S, ro, co, A, lda, beta, B, ldb);
+    else      RandBLAS::sketch_general(L, oA, oS, m, d, n, alpha, A, lda, S, ro, co, beta, B, ldb);
+    return 0;
+    RL_CATCH
+}
+
 // CQRRPT (RandLAPACK/drivers/rl_cqrrpt.hh:146-391) with the default subroutines (geqp3) unless qrcp says otherwise
 template <typename T>
 static int cqrrpt_impl(int64_t m, int64_t n, T* A, int64_t lda, T* R, int64_t ldr, int64_t* J, T d_factor, T eps, int64_t nnz, int qrcp,
@@ -428,6 +447,12 @@ int rlref_mat_gen_f32(int type, int64_t m, int64_t n, int64_t rank, float cond, 
                                        T alpha, const T* A, int64_t lda, int64_t ro, int64_t co, T beta, T* B, int64_t ldb,                \
                                        uint32_t state[6]) {                                                                                \
         return sketch_dense_impl<T>(false, S_rows, S_cols, family, major_axis, d, n, m, alpha, ro, co, A, lda, beta, B, ldb, state);       \
+    }                                                                                                                                     \
+    int rlref_sketch_general_dense_##SUF(int left, int layout, int opS, int opA, int64_t S_rows, int64_t S_cols, int family, int major_axis,    \
+                                         int64_t d, int64_t n, int64_t m, T alpha, int64_t ro, int64_t co, const T* A, int64_t lda, T beta,    \
+                                         T* B, int64_t ldb, uint32_t state[6]) {                                                              \
+        return sketch_general_dense_impl<T>(left != 0, layout, opS, opA, S_rows, S_cols, family, major_axis, d, n, m, alpha, ro, co, A, lda,   \
+                                            beta, B, ldb, state);                                                                             \
     }                                                                                                                                     \
     int rlref_cqrrpt_##SUF(int64_t m, int64_t n, T* A, int64_t lda, T* R, int64_t ldr, int64_t* J, T d_factor, T eps, int64_t nnz,         \
                            int qrcp, int64_t* rank, uint32_t state[6]) {                                                                   \

@@ -497,6 +497,36 @@ def sketch_dense_right(A, S_rows, S_cols, d, state: RNGState, family=FAMILY_GAUS
 # --------------------------------------------------------------------------------------------
 # CQRRPT (RandLAPACK/drivers/rl_cqrrpt.hh:146-391), default subroutines (SASO sketch, geqp3)
 # --------------------------------------------------------------------------------------------
+def _mat_view(flat, rows, cols, ld, layout):
+    """rows x cols view into a flat buffer stored in `layout` (LAYOUT_COLMAJOR | LAYOUT_ROWMAJOR) with leading dimension ld."""
+    if layout == LAYOUT_COLMAJOR:
+        return flat[:ld * cols].reshape((ld, cols), order="F")[:rows, :]
+    return flat[:rows * ld].reshape((rows, ld))[:, :cols]
+
+
+def sketch_general_dense(left, layout, opS, opA, d, n, m, alpha, S_rows, S_cols, ro, co, A_flat, lda, beta, B_flat, ldb, state: RNGState,
+                         family=FAMILY_GAUSSIAN, major_axis=AXIS_LONG):
+    """RandBLAS::sketch_general with a DenseSkOp and every layout / transposition flag (skge.hh:859-905 left -> lskge3 :100-203;
+    :1031-1076 right -> rskge3 :253-356), restated on the materialised operator.
+    left : B(d x n) = alpha * op(S[ro:, co:])(d x m) * op(A)(m x n) + beta * B;   right: B(m x d) = alpha * op(A)(m x n) * op(S[ro:, co:])(n x d) + beta * B.
+    A_flat / B_flat: flat buffers in `layout` order.  -> (B_flat (new), S.next_state)."""
+    dt = A_flat.dtype
+    S, nxt = fill_dense(S_rows, S_cols, state, dt, family, major_axis)
+    rs, cs = ((m, d) if opS else (d, m)) if left else ((d, n) if opS else (n, d))           # dims_before_op
+    if S_rows < rs + ro or S_cols < cs + co:
+        raise ValueError("sketch_general: submatrix of S out of range (randblas_require)")
+    Sub = np.asarray(S)[ro:ro + rs, co:co + cs]
+    opSm = Sub.T if opS else Sub
+    ra, ca = (n, m) if opA else (m, n)
+    A2 = _mat_view(A_flat, ra, ca, lda, layout)
+    opAm = A2.T if opA else A2
+    R = (opSm @ opAm) if left else (opAm @ opSm)
+    out = np.array(B_flat, copy=True)
+    Bv = _mat_view(out, *((d, n) if left else (m, d)), ldb, layout)
+    Bv[:, :] = dt.type(alpha) * R + (dt.type(beta) * Bv if beta != 0 else 0)
+    return out, nxt
+
+
 def col_swap(A, idx):
     """util::col_swap = lapack::lapmt(forward) (rl_util.hh:151-165): new column i = old column idx[i]-1."""
     return _F(A[:, np.asarray(idx, dtype=np.int64) - 1])

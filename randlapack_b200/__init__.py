@@ -21,7 +21,7 @@ from ._capi import (STAB_PLUL, STAB_CHOLQRQ, STAB_HQRQ, FAMILY_GAUSSIAN, FAMILY_
                     LAYOUT_NATURAL, LAYOUT_COLMAJOR, LAYOUT_ROWMAJOR, StackOpts, QRCP_LUQR, QRCP_GEQP3, QRTALL_GEQRF,
                     QRTALL_CHOLQR, QRTALL_GEQRT)
 
-__all__ = ["Context", "RNGState", "DenseDist", "fill_dense", "SparseDist", "fill_sparse", "sketch_general_left", "sketch_general_right", "CQRRPT", "BQRRP", "hqrrp", "qr_small", "col_swap", "CholQRQ", "PLUL", "HQRQ", "RS", "RF", "QB", "RSVD", "empty_f",
+__all__ = ["Context", "RNGState", "DenseDist", "fill_dense", "SparseDist", "fill_sparse", "sketch_general_left", "sketch_general_right", "sketch_general_dense_left", "sketch_general_dense_right", "CQRRPT", "BQRRP", "hqrrp", "qr_small", "col_swap", "CholQRQ", "PLUL", "HQRQ", "RS", "RF", "QB", "RSVD", "empty_f",
            "to_f", "Error", "shard_rows"]
 
 
@@ -376,6 +376,29 @@ def sketch_general_right(ctx: Context, A, D: DenseDist, state: RNGState, d=None,
     fn = getattr(ctx._lib, f"rlb200_sketch_dense_right_{_suffix(A.dtype)}_dev")
     ctx.check(fn(ctx._h, D.n_rows, D.n_cols, D.family, D.major_axis, m, d, n, alpha, A.data_ptr(), _ld(A), ro_s, co_s, beta,
                  B.data_ptr(), _ld(B), w))
+    state.assign(w)
+    return B
+
+
+def sketch_general_dense_left(ctx: Context, layout, opS, opA, d, n, m, alpha, D: DenseDist, ro_s, co_s, A, lda, beta, B, ldb, state: RNGState):
+    """RandBLAS::sketch_general(layout, opS, opA, d, n, m, alpha, S, ro_s, co_s, A, lda, beta, B, ldb) with a DenseSkOp S = D.sample(state)
+    (skge.hh:859-905): B(d x n) = alpha * op(submat(S)) * op(A) + beta * B for every layout (LAYOUT_COLMAJOR | LAYOUT_ROWMAJOR) and
+    transposition flag (False / True).  A and B are device buffers (any tensor; data_ptr, lda / ldb in elements).  `state` <- S.next_state."""
+    w = state.words()
+    fn = getattr(ctx._lib, f"rlb200_sketch_general_dense_left_{_suffix(A.dtype)}_dev")
+    ctx.check(fn(ctx._h, int(layout), int(bool(opS)), int(bool(opA)), d, n, m, alpha, D.n_rows, D.n_cols, D.family, D.major_axis, ro_s, co_s,
+                 A.data_ptr(), lda, beta, B.data_ptr(), ldb, w))
+    state.assign(w)
+    return B
+
+
+def sketch_general_dense_right(ctx: Context, layout, opA, opS, m, d, n, alpha, A, lda, D: DenseDist, ro_s, co_s, beta, B, ldb, state: RNGState):
+    """RandBLAS::sketch_general(layout, opA, opS, m, d, n, alpha, A, lda, S, ro_s, co_s, beta, B, ldb) (skge.hh:1031-1076):
+    B(m x d) = alpha * op(A) * op(submat(S)) + beta * B, every layout / transposition flag."""
+    w = state.words()
+    fn = getattr(ctx._lib, f"rlb200_sketch_general_dense_right_{_suffix(A.dtype)}_dev")
+    ctx.check(fn(ctx._h, int(layout), int(bool(opA)), int(bool(opS)), m, d, n, alpha, A.data_ptr(), lda, D.n_rows, D.n_cols, D.family,
+                 D.major_axis, ro_s, co_s, beta, B.data_ptr(), ldb, w))
     state.assign(w)
     return B
 

@@ -672,14 +672,28 @@ __global__ void __launch_bounds__(256) sk_transpose_axpby_kernel(const T* __rest
     }
 }
 
+// the w x d column-major panel (ld = w) that holds rows j0 .. j0 + w of op(S)^T, op(S) = the d x m operator block applied from the left:
+//   opS = NoTrans: the d x w block of S at (ro, co + j0), written ROW-major (= the natural, contiguous-write layout of a wide Long-axis operator);
+//   opS = Trans  : op(S) = (the m x d block of S at (ro, co))^T, so the panel is the w x d block of S at (ro + j0, co), written COLUMN-major.
+template <typename T>
+static int fill_left_panel(Ctx* ctx, int64_t S_rows, int64_t S_cols, int family, int major_axis, int opS, int64_t d, int64_t w, int64_t ro, int64_t co,
+                           int64_t j0, T* P, const uint32_t state[6]) {
+    uint32_t st[6];
+    std::memcpy(st, state, sizeof st);
+    if (opS == 0) return fill_dense_unpacked<T>(ctx, S_rows, S_cols, family, major_axis, RLB200_LAYOUT_ROWMAJOR, d, w, ro, co + j0, P, st);
+    return fill_dense_unpacked<T>(ctx, S_rows, S_cols, family, major_axis, RLB200_LAYOUT_COLMAJOR, w, d, ro + j0, co, P, st);
+}
+
 template <typename T>
 int sketch_dense_left(Ctx* ctx, int64_t S_rows, int64_t S_cols, int family, int major_axis, int64_t d, int64_t n, int64_t m, T alpha,
-                      int64_t ro, int64_t co, const T* A, int64_t lda, T beta, T* B, int64_t ldb, uint32_t state[6]) {
+                      int64_t ro, int64_t co, const T* A, int64_t lda, T beta, T* B, int64_t ldb, uint32_t state[6], int opS) {
     RLB_REQUIRE(ctx, S_rows > 0 && S_cols > 0 && d >= 0 && n >= 0 && m >= 0 && ro >= 0 && co >= 0);
+    RLB_REQUIRE(ctx, opS == 0 || opS == 1);
     const bool sharded = ctx->m_global >= 0;
     const int64_t shard_off = sharded ? ctx->row_offset : 0;
-    RLB_REQUIRE(ctx, S_rows >= d + ro);
-    RLB_REQUIRE(ctx, S_cols >= (sharded ? ctx->m_global : m) + co);
+    // dims_before_op(d, m, opS) (skge.hh:118, 133-134)
+    RLB_REQUIRE(ctx, (opS ? S_cols : S_rows) >= d + (opS ? co : ro));
+    RLB_REQUIRE(ctx, (opS ? S_rows : S_cols) >= (sharded ? ctx->m_global : m) + (opS ? ro : co));
     RLB_REQUIRE(ctx, lda >= m && ldb >= d);
     if (d > 0 && n > 0) {
         const T beta0 = (sharded && shard_off != 0) ? (T)0 : beta;
@@ -706,9 +720,7 @@ int sketch_dense_left(Ctx* ctx, int64_t S_rows, int64_t S_cols, int family, int 
         for (int64_t j0 = 0; fused && j0 < m; j0 += pc, buf ^= 1) {
             const int64_t w = std::min(pc, m - j0);
             T* P = panel + (size_t)buf * d * pc;
-            uint32_t st[6];
-            std::memcpy(st, state, sizeof st);
-            RLB_CHECK(fill_dense_unpacked<T>(ctx, S_rows, S_cols, family, major_axis, RLB200_LAYOUT_ROWMAJOR, d, w, ro, co + shard_off + j0, P, st));
+            RLB_CHECK(fill_left_panel<T>(ctx, S_rows, S_cols, family, major_axis, opS, d, w, ro, co, shard_off + j0, P, state));
             RLB_CHECK(ozaki2_gemm_tn<T>(ctx, w, n, d, 1.0, A + j0, lda, P, w, j0 == 0 ? 0.0 : 1.0, Zacc, n));
         }
         if (fused) {
@@ -721,12 +733,9 @@ int sketch_dense_left(Ctx* ctx, int64_t S_rows, int64_t S_cols, int family, int 
         for (int64_t j0 = 0; !fused && j0 < m; j0 += pc, buf ^= 1) {
             const int64_t w = std::min(pc, m - j0);
             T* P = panel + (size_t)buf * d * pc;
-            uint32_t st[6];
-            std::memcpy(st, state, sizeof st);
-            // the d x w block of S at (ro, co + shard_off + j0) in ROW-major order (= the natural, contiguous-write layout of a wide
-            // Long-axis operator), i.e. the w x d column-major matrix S_block^T with ld = w: the product is then the long-contraction
-            // (split-K, whole-machine) form  B += (S_block^T)^T A_block
-            RLB_CHECK(fill_dense_unpacked<T>(ctx, S_rows, S_cols, family, major_axis, RLB200_LAYOUT_ROWMAJOR, d, w, ro, co + shard_off + j0, P, st));
+            // the w x d column-major matrix op(S)_block^T with ld = w: the product is then the long-contraction
+            // (split-K, whole-machine) form  B += (op(S)_block^T)^T A_block
+            RLB_CHECK(fill_left_panel<T>(ctx, S_rows, S_cols, family, major_axis, opS, d, w, ro, co, shard_off + j0, P, state));
             if (i8) RLB_CHECK(ozaki_gemm_tn<T>(ctx, w, d, n, (double)alpha, P, w, A + j0, lda, j0 == 0 ? (double)beta0 : 1.0, B, ldb));
             else RLB_CHECK(gemm_tn<T>(ctx, w, d, n, (double)alpha, P, w, A + j0, lda, j0 == 0 ? (double)beta0 : 1.0, B, ldb, 0));
         }
@@ -743,10 +752,12 @@ int sketch_dense_left(Ctx* ctx, int64_t S_rows, int64_t S_cols, int family, int 
 
 template <typename T>
 int sketch_dense_right(Ctx* ctx, int64_t S_rows, int64_t S_cols, int family, int major_axis, int64_t m, int64_t d, int64_t n, T alpha,
-                       const T* A, int64_t lda, int64_t ro, int64_t co, T beta, T* B, int64_t ldb, uint32_t state[6]) {
+                       const T* A, int64_t lda, int64_t ro, int64_t co, T beta, T* B, int64_t ldb, uint32_t state[6], int opS) {
     RLB_REQUIRE(ctx, S_rows > 0 && S_cols > 0 && d >= 0 && n >= 0 && m >= 0 && ro >= 0 && co >= 0);
-    RLB_REQUIRE(ctx, S_rows >= n + ro);
-    RLB_REQUIRE(ctx, S_cols >= d + co);
+    RLB_REQUIRE(ctx, opS == 0 || opS == 1);
+    // dims_before_op(n, d, opS) (skge.hh:271, 286-287)
+    RLB_REQUIRE(ctx, (opS ? S_cols : S_rows) >= n + (opS ? co : ro));
+    RLB_REQUIRE(ctx, (opS ? S_rows : S_cols) >= d + (opS ? ro : co));
     RLB_REQUIRE(ctx, lda >= m && ldb >= m);
     if (m > 0 && d > 0) {
         int64_t pr = std::max<int64_t>(64, (int64_t)(kDensePanelBytes / sizeof(T)) / std::max<int64_t>(d, 1));
@@ -760,8 +771,10 @@ int sketch_dense_right(Ctx* ctx, int64_t S_rows, int64_t S_cols, int family, int
             T* P = panel + (size_t)buf * d * pr;
             uint32_t st[6];
             std::memcpy(st, state, sizeof st);
-            // the h x d block of S at (ro + i0, co), column-major with ld = h
-            RLB_CHECK(fill_dense_unpacked<T>(ctx, S_rows, S_cols, family, major_axis, RLB200_LAYOUT_COLMAJOR, h, d, ro + i0, co, P, st));
+            // rows i0 .. i0 + h of op(S) as an h x d column-major panel (ld = h): the h x d block of S at (ro + i0, co) written column-major,
+            // or, for opS = Trans, the d x h block of S at (ro, co + i0) written row-major
+            if (opS == 0) RLB_CHECK(fill_dense_unpacked<T>(ctx, S_rows, S_cols, family, major_axis, RLB200_LAYOUT_COLMAJOR, h, d, ro + i0, co, P, st));
+            else RLB_CHECK(fill_dense_unpacked<T>(ctx, S_rows, S_cols, family, major_axis, RLB200_LAYOUT_ROWMAJOR, d, h, ro, co + i0, P, st));
             RLB_CHECK(gemm_nn<T>(ctx, m, d, h, (double)alpha, A + i0 * lda, lda, P, h, i0 == 0 ? (double)beta : 1.0, B, ldb));
         }
     }
@@ -769,9 +782,96 @@ int sketch_dense_right(Ctx* ctx, int64_t S_rows, int64_t S_cols, int family, int
     return 0;
 }
 
+// ------------------------------------------------------------------------------------------------
+// sketch_general with every layout / transposition flag (RandBLAS/RandBLAS/skge.hh:859-905 left, :1031-1076 right; lskge3 :100-203,
+// rskge3 :253-356).  The tall-product engines want the data matrix as a column-major (long x short) array and write a column-major
+// result, so the other presentations are brought to that form:
+//   * op(S) only changes which sub-block of the operator a panel regenerates and in which order it is written (fill_left_panel);
+//   * a data matrix that arrives as the column-major (short x long) array - ColMajor + opA = Trans, or RowMajor + opA = NoTrans - is
+//     transposed once into scratch (one extra read and write of A: HBM-bound, 3x the traffic of the direct form);
+//   * a RowMajor result is the column-major transpose: computed in scratch, then written through the transposing axpby.
+// ------------------------------------------------------------------------------------------------
+// dst (cols x rows, ldd) = src (rows x cols, lds)^T, any size (the tile kernel's grid.y is bounded)
+template <typename T>
+static int transpose_big(Ctx* ctx, int64_t rows, int64_t cols, const T* src, int64_t lds, T* dst, int64_t ldd) {
+    const int64_t step = (int64_t)1 << 20;
+    for (int64_t c0 = 0; c0 < cols; c0 += step) {
+        const int64_t w = std::min(step, cols - c0);
+        RLB_CHECK(transpose<T>(ctx, rows, w, src + c0 * lds, lds, dst + c0, ldd));
+    }
+    return 0;
+}
+
+// op(A) (m x n) as a column-major m x n array: returns A itself or a transposed scratch copy
+template <typename T>
+static int data_as_colmajor(Ctx* ctx, ArenaScope& as, int layout, int opA, int64_t m, int64_t n, const T* A, int64_t lda, const T** out, int64_t* ld_out) {
+    const bool colmajor = layout == RLB200_LAYOUT_COLMAJOR;
+    // stored array, column-major view: ColMajor/NoTrans m x n; ColMajor/Trans n x m; RowMajor/NoTrans n x m; RowMajor/Trans m x n
+    const bool direct = colmajor == (opA == 0);
+    RLB_REQUIRE(ctx, lda >= std::max<int64_t>(1, direct ? m : n));          // skge.hh:136-143 / 289-296
+    if (direct || m == 0 || n == 0) { *out = A; *ld_out = direct ? lda : std::max<int64_t>(m, 1); return 0; }
+    T* At = as.take<T>((size_t)m * n); if (!At) return RLB200_ERR_ALLOC;
+    RLB_CHECK(transpose_big<T>(ctx, n, m, A, lda, At, m));
+    *out = At; *ld_out = m;
+    return 0;
+}
+
+// run `inner(Bc, ldc, beta_c)` on a column-major r x c result: B itself (ColMajor), or scratch that is then written into the RowMajor B
+template <typename T, typename F>
+static int result_as_colmajor(Ctx* ctx, ArenaScope& as, int layout, int64_t r, int64_t c, T alpha, T beta, T* B, int64_t ldb, F&& inner) {
+    if (layout == RLB200_LAYOUT_COLMAJOR) {
+        RLB_REQUIRE(ctx, ldb >= std::max<int64_t>(1, r));
+        return inner(B, ldb, alpha, beta);
+    }
+    RLB_REQUIRE(ctx, ldb >= std::max<int64_t>(1, c));                       // RowMajor r x c = column-major c x r with ld = ldb
+    if (r == 0 || c == 0) return inner(B, std::max<int64_t>(r, 1), alpha, beta);
+    T* Z = as.take<T>((size_t)r * c); if (!Z) return RLB200_ERR_ALLOC;
+    RLB_CHECK(inner(Z, r, (T)1, (T)0));                                     // Z (r x c) = op(S) op(A)  or  op(A) op(S)
+    LaunchScope ls(ctx, RLB200_TIMER_SKETCH);
+    // B^T (c x r, ldb) = alpha * Z (r x c, ld r)^T + beta * B^T
+    sk_transpose_axpby_kernel<T><<<dim3((unsigned)((r + 31) / 32), (unsigned)((c + 31) / 32)), 256, 0, ctx->stream>>>(Z, r, c, r, (double)alpha,
+                                                                                                                  (double)beta, B, ldb);
+    RLB_CUDA_OK(ctx, cudaGetLastError());
+    RLB_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));                   // Z is scratch of the caller's scope
+    return 0;
+}
+
+template <typename T>
+int sketch_general_dense_left(Ctx* ctx, int layout, int opS, int opA, int64_t d, int64_t n, int64_t m, T alpha, int64_t S_rows, int64_t S_cols,
+                              int family, int major_axis, int64_t ro, int64_t co, const T* A, int64_t lda, T beta, T* B, int64_t ldb, uint32_t state[6]) {
+    RLB_REQUIRE(ctx, layout == RLB200_LAYOUT_COLMAJOR || layout == RLB200_LAYOUT_ROWMAJOR);
+    RLB_REQUIRE(ctx, (opS == 0 || opS == 1) && (opA == 0 || opA == 1));
+    RLB_REQUIRE(ctx, d >= 0 && n >= 0 && m >= 0);
+    if (layout == RLB200_LAYOUT_COLMAJOR && opA == 0) return sketch_dense_left<T>(ctx, S_rows, S_cols, family, major_axis, d, n, m, alpha, ro, co, A, lda, beta, B, ldb, state, opS);
+    if (ctx->m_global >= 0) { ctx->err = "sketch_general on a row-sharded context: ColMajor with opA = NoTrans only"; return RLB200_ERR_UNSUPPORTED; }
+    ArenaScope as(ctx);
+    const T* Ac = nullptr; int64_t ldac = 0;
+    RLB_CHECK(data_as_colmajor<T>(ctx, as, layout, opA, m, n, A, lda, &Ac, &ldac));
+    return result_as_colmajor<T>(ctx, as, layout, d, n, alpha, beta, B, ldb, [&](T* Bc, int64_t ldc, T al, T be) {
+        return sketch_dense_left<T>(ctx, S_rows, S_cols, family, major_axis, d, n, m, al, ro, co, Ac, ldac, be, Bc, ldc, state, opS);
+    });
+}
+
+template <typename T>
+int sketch_general_dense_right(Ctx* ctx, int layout, int opA, int opS, int64_t m, int64_t d, int64_t n, T alpha, const T* A, int64_t lda,
+                               int64_t S_rows, int64_t S_cols, int family, int major_axis, int64_t ro, int64_t co, T beta, T* B, int64_t ldb, uint32_t state[6]) {
+    RLB_REQUIRE(ctx, layout == RLB200_LAYOUT_COLMAJOR || layout == RLB200_LAYOUT_ROWMAJOR);
+    RLB_REQUIRE(ctx, (opS == 0 || opS == 1) && (opA == 0 || opA == 1));
+    RLB_REQUIRE(ctx, d >= 0 && n >= 0 && m >= 0);
+    if (layout == RLB200_LAYOUT_COLMAJOR && opA == 0) return sketch_dense_right<T>(ctx, S_rows, S_cols, family, major_axis, m, d, n, alpha, A, lda, ro, co, beta, B, ldb, state, opS);
+    ArenaScope as(ctx);
+    const T* Ac = nullptr; int64_t ldac = 0;
+    RLB_CHECK(data_as_colmajor<T>(ctx, as, layout, opA, m, n, A, lda, &Ac, &ldac));
+    return result_as_colmajor<T>(ctx, as, layout, m, d, alpha, beta, B, ldb, [&](T* Bc, int64_t ldc, T al, T be) {
+        return sketch_dense_right<T>(ctx, S_rows, S_cols, family, major_axis, m, d, n, al, Ac, ldac, ro, co, be, Bc, ldc, state, opS);
+    });
+}
+
 #define INST(T)                                                                                                                                  \
-    template int sketch_dense_left<T>(Ctx*, int64_t, int64_t, int, int, int64_t, int64_t, int64_t, T, int64_t, int64_t, const T*, int64_t, T, T*, int64_t, uint32_t*); \
-    template int sketch_dense_right<T>(Ctx*, int64_t, int64_t, int, int, int64_t, int64_t, int64_t, T, const T*, int64_t, int64_t, int64_t, T, T*, int64_t, uint32_t*);
+    template int sketch_dense_left<T>(Ctx*, int64_t, int64_t, int, int, int64_t, int64_t, int64_t, T, int64_t, int64_t, const T*, int64_t, T, T*, int64_t, uint32_t*, int); \
+    template int sketch_dense_right<T>(Ctx*, int64_t, int64_t, int, int, int64_t, int64_t, int64_t, T, const T*, int64_t, int64_t, int64_t, T, T*, int64_t, uint32_t*, int); \
+    template int sketch_general_dense_left<T>(Ctx*, int, int, int, int64_t, int64_t, int64_t, T, int64_t, int64_t, int, int, int64_t, int64_t, const T*, int64_t, T, T*, int64_t, uint32_t*); \
+    template int sketch_general_dense_right<T>(Ctx*, int, int, int, int64_t, int64_t, int64_t, T, const T*, int64_t, int64_t, int64_t, int, int, int64_t, int64_t, T, T*, int64_t, uint32_t*);
 INST(double)
 INST(float)
 

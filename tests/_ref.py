@@ -245,3 +245,18 @@ def ref_hqrrp(lib, A, nb_alg, pp, panel_pivoting, qr_type, seed6):
     f.argtypes = [i64, i64, ctypes.c_void_p, i64, ctypes.c_void_p, ctypes.c_void_p, i64, i64, i64, i64, ctypes.POINTER(u32)]
     rc = f(m, n, F.ctypes.data, max(m, 1), J.ctypes.data, tau.ctypes.data, nb_alg, pp, panel_pivoting, qr_type, st)
     return rc, F, tau, J, list(st)
+
+
+def ref_sketch_general_dense(lib, left, layout, opS, opA, D, dims, A_flat, lda, B_flat, ldb, seed6, alpha=1.0, beta=0.0, ro=0, co=0):
+    """RandBLAS::sketch_general with every flag via the compiled reference.  D = (S_rows, S_cols, family, axis); dims = (d, n, m);
+    layout: 1 ColMajor, 2 RowMajor; A_flat / B_flat: 1-D buffers holding the matrices in `layout` order with lda / ldb -> (rc, B_flat, state)."""
+    dt = A_flat.dtype
+    B = B_flat.copy()
+    st = (u32 * 6)(*seed6)
+    ft = _ft(dt)
+    f = getattr(lib, f"rlref_sketch_general_dense_{_suf(dt)}")
+    f.argtypes = [ctypes.c_int] * 4 + [i64, i64, ctypes.c_int, ctypes.c_int, i64, i64, i64, ft, i64, i64, ctypes.c_void_p, i64, ft, ctypes.c_void_p, i64,
+                                       ctypes.POINTER(u32)]
+    d, n, m = dims
+    rc = f(int(left), layout, int(opS), int(opA), D[0], D[1], D[2], D[3], d, n, m, alpha, ro, co, A_flat.ctypes.data, lda, beta, B.ctypes.data, ldb, st)
+    return rc, B, list(st)

@@ -168,3 +168,59 @@ def test_dense_left_never_materialised_matches_materialised(ctx, dtype):
 def O_next(nr, nc, key):
     s = O.dense_next_state(nr, nc, O.AXIS_LONG, O.RNGState(key))
     return rl.RNGState(s.key, s.counter)
+
+
+# ---- sketch_general with every layout / transposition flag (skge.hh:859-905 left, 1031-1076 right) -----------------------------------------
+from _qrcases import GS, sg_input  # noqa: E402
+
+
+def _sg_run(ctx, c, A, B, alpha, beta, seed):
+    Ad, Bd = torch.from_numpy(A).cuda(), torch.from_numpy(B.copy()).cuda()
+    D = rl.DenseDist(c["S_rows"], c["S_cols"], c["family"], c["axis"])
+    s = _st(seed)
+    if c["left"]:
+        rl.sketch_general_dense_left(ctx, c["layout"], c["opS"], c["opA"], c["d"], c["n"], c["m"], alpha, D, c["ro"], c["co"], Ad, c["lda"], beta,
+                                     Bd, c["ldb"], s)
+    else:
+        rl.sketch_general_dense_right(ctx, c["layout"], c["opA"], c["opS"], c["m"], c["d"], c["n"], alpha, Ad, c["lda"], D, c["ro"], c["co"], beta,
+                                      Bd, c["ldb"], s)
+    return Bd.cpu().numpy(), s
+
+
+@pytest.mark.parametrize("i", range(int(GS["sg_count"])))
+def test_sketch_general_dense_all_flags_golden(ctx, i):
+    """Every layout / opS / opA combination, left and right, against golden outputs of the compiled reference (padded leading dimensions,
+    submatrix offsets, alpha = 0.75, beta = -0.5).  RNG state exact; the padding of B untouched (bit-exact); values 2e-6 (fp64) / 2e-5 (fp32)
+    relative to the largest entry (the device's Gaussians are within a few float ulps of the host libm's)."""
+    c = sg_input(i)
+    out, s = _sg_run(ctx, c, c["A"], c["B"], 0.75, -0.5, c["seed"])
+    ref = GS[f"sg{i}_Bout"]
+    assert list(s.words()) == list(GS[f"sg{i}_state_out"])
+    rb, cb = (c["d"], c["n"]) if c["left"] else (c["m"], c["d"])
+    mask = np.ones(ref.shape, dtype=bool)
+    O._mat_view(mask, rb, cb, c["ldb"], c["layout"])[:, :] = False          # True on the padding
+    assert np.array_equal(out[mask], c["B"][mask]), "padding of B was written"
+    tol = 2e-6 if c["dtype"] == np.float64 else 2e-5
+    assert np.abs(out - ref).max() <= tol * np.abs(ref).max()
+
+
+@pytest.mark.parametrize("flags", [(1, 2, 0, 0), (1, 1, 1, 1), (1, 2, 1, 1), (0, 2, 0, 0), (0, 1, 1, 1)])
+def test_sketch_general_dense_tall_vs_oracle(ctx, flags):
+    """The same at a size where the left sketch runs on the digit-slice engine (m = 20000 rows, d = 64, n = 96) and the data matrix has to be
+    transposed / the result written transposed; against the restatement on the same operator (2e-6 relative, Frobenius)."""
+    left, layout, opS, opA = flags
+    d, n, m = 64, 96, 20000
+    rs, cs = ((m, d) if opS else (d, m)) if left else ((d, n) if opS else (n, d))
+    ra, ca = (n, m) if opA else (m, n)
+    rb, cb = (d, n) if left else (m, d)
+    c = dict(left=left, layout=layout, opS=opS, opA=opA, d=d, n=n, m=m, ro=1, co=2, S_rows=rs + 1, S_cols=cs + 2, family=0, axis=0,
+             lda=(ra if layout == 1 else ca) + 1, ldb=(rb if layout == 1 else cb))
+    rng = np.random.RandomState(5)
+    A = rng.standard_normal(c["lda"] * (ca if layout == 1 else ra))
+    B = rng.standard_normal(c["ldb"] * (cb if layout == 1 else rb))
+    seed = [3, 0, 0, 0, 9, 0]
+    out, s = _sg_run(ctx, c, A, B, 1.0, 0.5, seed)
+    ref, nxt = O.sketch_general_dense(left, layout, opS, opA, d, n, m, 1.0, c["S_rows"], c["S_cols"], 1, 2, A, c["lda"], 0.5, B, c["ldb"],
+                                      O.RNGState.from_words(seed))
+    assert list(s.words()) == list(nxt.words())
+    assert np.linalg.norm(out - ref) <= 2e-6 * np.linalg.norm(ref)

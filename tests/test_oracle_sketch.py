@@ -79,3 +79,20 @@ def test_fill_sparse_vs_compiled_reference():
         k2, v2, r2, c2, st2 = O.fill_sparse(nr, nc, nnz, _state(seed), sub=sub)
         assert rc == 0 and k == k2 and np.array_equal(rows, r2) and np.array_equal(cols, c2) and np.array_equal(vals, v2)
         assert st == list(st2.words())
+
+
+from _qrcases import GS, sg_input  # noqa: E402
+
+
+@pytest.mark.parametrize("i", range(int(GS["sg_count"])))
+def test_sketch_general_dense_all_flags_golden(i):
+    """sketch_general with a DenseSkOp for every layout / opS / opA, left and right (skge.hh:859-905, 1031-1076): the restatement against
+    golden outputs of the compiled reference (padded leading dimensions, submatrix offsets, alpha = 0.75, beta = -0.5; the padding of B
+    must come back untouched).  fp64 1e-12, fp32 2e-5 (relative to the largest entry)."""
+    c = sg_input(i)
+    out, nxt = O.sketch_general_dense(c["left"], c["layout"], c["opS"], c["opA"], c["d"], c["n"], c["m"], 0.75, c["S_rows"], c["S_cols"], c["ro"],
+                                      c["co"], c["A"], c["lda"], -0.5, c["B"], c["ldb"], O.RNGState.from_words(c["seed"]), c["family"], c["axis"])
+    ref = GS[f"sg{i}_Bout"]
+    assert list(nxt.words()) == list(GS[f"sg{i}_state_out"])
+    tol = 1e-12 if c["dtype"] == np.float64 else 2e-5
+    assert np.abs(out - ref).max() <= tol * np.abs(ref).max()
