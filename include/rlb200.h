@@ -223,6 +223,23 @@ RLB200_API int rlb200_sketch_general_dense_right_f32_dev(rlb200_ctx* ctx, int la
                                               const float* A_dev, int64_t lda, int64_t S_rows, int64_t S_cols, int family, int major_axis,
                                               int64_t ro_s, int64_t co_s, float beta, float* B_dev, int64_t ldb, uint32_t state[6]);
 
+/* The same for short-axis SparseSkOps (skge.hh:907-960 left -> lskges :538-571; :1078-1131 right -> rskges :573-620): op(submat(S)) must be
+ * a WIDE operator, i.e. opS = NoTrans with a wide S or opS = Trans with a tall S (left), the reverse for the right sketch - the shapes a
+ * sketch has; the operator is regenerated on the device from the state (a tall short-axis operator is the transpose of the wide one with the
+ * same seed).  The right sketch runs as the left sketch of the transposed problem, as in the reference. */
+RLB200_API int rlb200_sketch_general_sparse_left_f64_dev(rlb200_ctx* ctx, int layout, int opS, int opA, int64_t d, int64_t n, int64_t m, double alpha,
+                                              int64_t S_rows, int64_t S_cols, int64_t vec_nnz, int64_t ro_s, int64_t co_s, const double* A_dev,
+                                              int64_t lda, double beta, double* B_dev, int64_t ldb, uint32_t state[6]);
+RLB200_API int rlb200_sketch_general_sparse_left_f32_dev(rlb200_ctx* ctx, int layout, int opS, int opA, int64_t d, int64_t n, int64_t m, float alpha,
+                                              int64_t S_rows, int64_t S_cols, int64_t vec_nnz, int64_t ro_s, int64_t co_s, const float* A_dev,
+                                              int64_t lda, float beta, float* B_dev, int64_t ldb, uint32_t state[6]);
+RLB200_API int rlb200_sketch_general_sparse_right_f64_dev(rlb200_ctx* ctx, int layout, int opA, int opS, int64_t m, int64_t d, int64_t n, double alpha,
+                                               const double* A_dev, int64_t lda, int64_t S_rows, int64_t S_cols, int64_t vec_nnz, int64_t ro_s,
+                                               int64_t co_s, double beta, double* B_dev, int64_t ldb, uint32_t state[6]);
+RLB200_API int rlb200_sketch_general_sparse_right_f32_dev(rlb200_ctx* ctx, int layout, int opA, int opS, int64_t m, int64_t d, int64_t n, float alpha,
+                                               const float* A_dev, int64_t lda, int64_t S_rows, int64_t S_cols, int64_t vec_nnz, int64_t ro_s,
+                                               int64_t co_s, float beta, float* B_dev, int64_t ldb, uint32_t state[6]);
+
 /* ---- blas::gemm as used on the path (ColMajor; rl_rs.hh:142,153,165; rl_rf.hh:123; rl_qb.hh:218;
  *      rl_rsvd.hh:148).  transa/transb: 0 = NoTrans, 1 = Trans.  Shapes the tall-skinny kernels cover:
  *      NN with the long dimension on m; TN with the long dimension on k (split-K, deterministic). */

@@ -231,6 +231,24 @@ static int sketch_general_dense_impl(bool left, int layout, int opS, int opA, in
     RL_CATCH
 }
 
+// the same with a short-axis SparseSkOp (skge.hh:907-960 left, :1078-1131 right)
+template <typename T>
+static int sketch_general_sparse_impl(bool left, int layout, int opS, int opA, int64_t S_rows, int64_t S_cols, int64_t vec_nnz, int64_t d, int64_t n,
+                                      int64_t m, T alpha, int64_t ro, int64_t co, const T* A, int64_t lda, T beta, T* B, int64_t ldb,
+                                      uint32_t state[6]) {
+    RL_TRY
+    RandBLAS::SparseDist DS(S_rows, S_cols, vec_nnz);
+    State st = load_state(state);
+    RandBLAS::SparseSkOp<T, RNG> S(DS, st);
+    store_state(S.next_state, state);
+    const blas::Layout L = layout == 2 ? blas::Layout::RowMajor : blas::Layout::ColMajor;
+    const blas::Op oS = opS ? blas::Op::Trans : blas::Op::NoTrans, oA = opA ? blas::Op::Trans : blas::Op::NoTrans;
+    if (left) RandBLAS::sketch_general(L, oS, oA, d, n, m, alpha, S, ro, co, A, lda, beta, B, ldb);
+    else      RandBLAS::sketch_general(L, oA, oS, m, d, n, alpha, A, lda, S, ro, co, beta, B, ldb);
+    return 0;
+    RL_CATCH
+}
+
 // CQRRPT (RandLAPACK/drivers/rl_cqrrpt.hh:146-391) with the default subroutines (geqp3) unless qrcp says otherwise
 template <typename T>
 static int cqrrpt_impl(int64_t m, int64_t n, T* A, int64_t lda, T* R, int64_t ldr, int64_t* J, T d_factor, T eps, int64_t nnz, int qrcp,
@@ -453,6 +471,12 @@ int rlref_mat_gen_f32(int type, int64_t m, int64_t n, int64_t rank, float cond, 
                                          T* B, int64_t ldb, uint32_t state[6]) {                                                              \
         return sketch_general_dense_impl<T>(left != 0, layout, opS, opA, S_rows, S_cols, family, major_axis, d, n, m, alpha, ro, co, A, lda,   \
                                             beta, B, ldb, state);                                                                             \
+    }                                                                                                                                     \
+    int rlref_sketch_general_sparse_##SUF(int left, int layout, int opS, int opA, int64_t S_rows, int64_t S_cols, int64_t vec_nnz, int64_t d,  \
+                                          int64_t n, int64_t m, T alpha, int64_t ro, int64_t co, const T* A, int64_t lda, T beta, T* B,        \
+                                          int64_t ldb, uint32_t state[6]) {                                                                    \
+        return sketch_general_sparse_impl<T>(left != 0, layout, opS, opA, S_rows, S_cols, vec_nnz, d, n, m, alpha, ro, co, A, lda, beta, B,    \
+                                             ldb, state);                                                                                     \
     }                                                                                                                                     \
     int rlref_cqrrpt_##SUF(int64_t m, int64_t n, T* A, int64_t lda, T* R, int64_t ldr, int64_t* J, T d_factor, T eps, int64_t nnz,         \
                            int qrcp, int64_t* rank, uint32_t state[6]) {                                                                   \

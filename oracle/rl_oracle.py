@@ -527,6 +527,34 @@ def sketch_general_dense(left, layout, opS, opA, d, n, m, alpha, S_rows, S_cols,
     return out, nxt
 
 
+def sketch_general_sparse(left, layout, opS, opA, d, n, m, alpha, S_rows, S_cols, vec_nnz, ro, co, A_flat, lda, beta, B_flat, ldb, state: RNGState):
+    """RandBLAS::sketch_general with a short-axis SparseSkOp and every layout / transposition flag (skge.hh:907-960 left, :1078-1131 right),
+    restated on the materialised operator.  A tall short-axis operator is generated as the transpose of the wide one with swapped dimensions
+    and the same seed (sparse_skops.hh:585-610: the index stream depends on (dim_major, dim_minor) only).  -> (B_flat (new), S.next_state)."""
+    dt = A_flat.dtype
+    tall = S_rows > S_cols
+    wr, wc = (S_cols, S_rows) if tall else (S_rows, S_cols)
+    k, vals, rows, cols, _ = fill_sparse(wr, wc, vec_nnz, state, dt)
+    S = np.zeros((wr, wc), dtype=dt)
+    np.add.at(S, (rows, cols), vals)
+    if tall:
+        S = S.T
+    nxt = saso_next_state(wr, wc, vec_nnz, state)
+    rs, cs = ((m, d) if opS else (d, m)) if left else ((d, n) if opS else (n, d))
+    if S_rows < rs + ro or S_cols < cs + co:
+        raise ValueError("sketch_general: submatrix of S out of range (randblas_require)")
+    Sub = S[ro:ro + rs, co:co + cs]
+    opSm = Sub.T if opS else Sub
+    ra, ca = (n, m) if opA else (m, n)
+    A2 = _mat_view(A_flat, ra, ca, lda, layout)
+    opAm = A2.T if opA else A2
+    R = (opSm @ opAm) if left else (opAm @ opSm)
+    out = np.array(B_flat, copy=True)
+    Bv = _mat_view(out, *((d, n) if left else (m, d)), ldb, layout)
+    Bv[:, :] = dt.type(alpha) * R + (dt.type(beta) * Bv if beta != 0 else 0)
+    return out, nxt
+
+
 def col_swap(A, idx):
     """util::col_swap = lapack::lapmt(forward) (rl_util.hh:151-165): new column i = old column idx[i]-1."""
     return _F(A[:, np.asarray(idx, dtype=np.int64) - 1])

@@ -21,7 +21,7 @@ from ._capi import (STAB_PLUL, STAB_CHOLQRQ, STAB_HQRQ, FAMILY_GAUSSIAN, FAMILY_
                     LAYOUT_NATURAL, LAYOUT_COLMAJOR, LAYOUT_ROWMAJOR, StackOpts, QRCP_LUQR, QRCP_GEQP3, QRTALL_GEQRF,
                     QRTALL_CHOLQR, QRTALL_GEQRT)
 
-__all__ = ["Context", "RNGState", "DenseDist", "fill_dense", "SparseDist", "fill_sparse", "sketch_general_left", "sketch_general_right", "sketch_general_dense_left", "sketch_general_dense_right", "CQRRPT", "BQRRP", "hqrrp", "qr_small", "col_swap", "CholQRQ", "PLUL", "HQRQ", "RS", "RF", "QB", "RSVD", "empty_f",
+__all__ = ["Context", "RNGState", "DenseDist", "fill_dense", "SparseDist", "fill_sparse", "sketch_general_left", "sketch_general_right", "sketch_general_dense_left", "sketch_general_dense_right", "sketch_general_sparse_left", "sketch_general_sparse_right", "CQRRPT", "BQRRP", "hqrrp", "qr_small", "col_swap", "CholQRQ", "PLUL", "HQRQ", "RS", "RF", "QB", "RSVD", "empty_f",
            "to_f", "Error", "shard_rows"]
 
 
@@ -399,6 +399,31 @@ def sketch_general_dense_right(ctx: Context, layout, opA, opS, m, d, n, alpha, A
     fn = getattr(ctx._lib, f"rlb200_sketch_general_dense_right_{_suffix(A.dtype)}_dev")
     ctx.check(fn(ctx._h, int(layout), int(bool(opA)), int(bool(opS)), m, d, n, alpha, A.data_ptr(), lda, D.n_rows, D.n_cols, D.family,
                  D.major_axis, ro_s, co_s, beta, B.data_ptr(), ldb, w))
+    state.assign(w)
+    return B
+
+
+def sketch_general_sparse_left(ctx: Context, layout, opS, opA, d, n, m, alpha, D: SparseDist, ro_s, co_s, A, lda, beta, B, ldb, state: RNGState):
+    """sketch_general(layout, opS, opA, d, n, m, alpha, S, ro_s, co_s, A, lda, beta, B, ldb) with a short-axis SparseSkOp S = D.sample(state)
+    (skge.hh:907-960), every layout / transposition flag; op(submat(S)) must be wide.  A, B: device buffers with lda / ldb in elements."""
+    if D.major_axis != AXIS_SHORT:
+        raise Error(_capi.ERR_UNSUPPORTED, "Axis::Long sparse operators are not offered on the device")
+    w = state.words()
+    fn = getattr(ctx._lib, f"rlb200_sketch_general_sparse_left_{_suffix(A.dtype)}_dev")
+    ctx.check(fn(ctx._h, int(layout), int(bool(opS)), int(bool(opA)), d, n, m, alpha, D.n_rows, D.n_cols, D.vec_nnz, ro_s, co_s, A.data_ptr(), lda,
+                 beta, B.data_ptr(), ldb, w))
+    state.assign(w)
+    return B
+
+
+def sketch_general_sparse_right(ctx: Context, layout, opA, opS, m, d, n, alpha, A, lda, D: SparseDist, ro_s, co_s, beta, B, ldb, state: RNGState):
+    """sketch_general(layout, opA, opS, m, d, n, alpha, A, lda, S, ro_s, co_s, beta, B, ldb) with a short-axis SparseSkOp (skge.hh:1078-1131)."""
+    if D.major_axis != AXIS_SHORT:
+        raise Error(_capi.ERR_UNSUPPORTED, "Axis::Long sparse operators are not offered on the device")
+    w = state.words()
+    fn = getattr(ctx._lib, f"rlb200_sketch_general_sparse_right_{_suffix(A.dtype)}_dev")
+    ctx.check(fn(ctx._h, int(layout), int(bool(opA)), int(bool(opS)), m, d, n, alpha, A.data_ptr(), lda, D.n_rows, D.n_cols, D.vec_nnz, ro_s, co_s,
+                 beta, B.data_ptr(), ldb, w))
     state.assign(w)
     return B
 

@@ -107,6 +107,10 @@ for _suf, _ft in (("f64", ctypes.c_double), ("f32", ctypes.c_float)):
                                                                          c_i64, c_i64, c_vp, c_i64, _ft, c_vp, c_i64, P_u32])
     SIGNATURES[f"rlb200_sketch_general_dense_right_{_suf}_dev"] = (c_int, [c_vp, c_int, c_int, c_int, c_i64, c_i64, c_i64, _ft, c_vp, c_i64, c_i64, c_i64,
                                                                           c_int, c_int, c_i64, c_i64, _ft, c_vp, c_i64, P_u32])
+    SIGNATURES[f"rlb200_sketch_general_sparse_left_{_suf}_dev"] = (c_int, [c_vp, c_int, c_int, c_int, c_i64, c_i64, c_i64, _ft, c_i64, c_i64, c_i64,
+                                                                          c_i64, c_i64, c_vp, c_i64, _ft, c_vp, c_i64, P_u32])
+    SIGNATURES[f"rlb200_sketch_general_sparse_right_{_suf}_dev"] = (c_int, [c_vp, c_int, c_int, c_int, c_i64, c_i64, c_i64, _ft, c_vp, c_i64, c_i64, c_i64,
+                                                                           c_i64, c_i64, c_i64, _ft, c_vp, c_i64, P_u32])
     SIGNATURES[f"rlb200_cqrrt_{_suf}_dev"] = (c_int, [c_vp, c_i64, c_i64, c_vp, c_i64, c_vp, c_i64, _ft, c_i64, c_int, c_int, P_u32])
     SIGNATURES[f"rlb200_cqrrt_{_suf}_host"] = (c_int, [c_vp, c_i64, c_i64, c_vp, c_i64, c_vp, c_i64, _ft, c_i64, c_int, c_int, P_u32])
     SIGNATURES[f"rlb200_syps_{_suf}_dev"] = (c_int, [c_vp, c_int, c_i64, c_vp, c_i64, c_i64, c_i64, c_i64, c_vp, c_vp, P_u32])

@@ -259,6 +259,20 @@ int rlb200_set_i8_digits(rlb200_ctx* ctx, int digits) {
         return sketch_dense_right<T>(ctx, S_rows, S_cols, family, major_axis, m, d, n, alpha, A_dev, lda, ro_s, co_s, beta, B_dev,  \
                                      ldb, state);                                                                                   \
     }                                                                                                                               \
+    int rlb200_sketch_general_sparse_left_##SUF##_dev(rlb200_ctx* ctx, int layout, int opS, int opA, int64_t d, int64_t n, int64_t m, T alpha, \
+                                                      int64_t S_rows, int64_t S_cols, int64_t vec_nnz, int64_t ro_s, int64_t co_s,  \
+                                                      const T* A_dev, int64_t lda, T beta, T* B_dev, int64_t ldb, uint32_t state[6]) { \
+        CTX_OK(ctx); RLB_CHECK(bind(ctx)); RLB_REQUIRE(ctx, state);                                                                 \
+        return sketch_general_sparse_left<T>(ctx, layout, opS, opA, d, n, m, alpha, S_rows, S_cols, vec_nnz, ro_s, co_s, A_dev, lda, beta, \
+                                             B_dev, ldb, state);                                                                    \
+    }                                                                                                                               \
+    int rlb200_sketch_general_sparse_right_##SUF##_dev(rlb200_ctx* ctx, int layout, int opA, int opS, int64_t m, int64_t d, int64_t n, T alpha, \
+                                                       const T* A_dev, int64_t lda, int64_t S_rows, int64_t S_cols, int64_t vec_nnz, \
+                                                       int64_t ro_s, int64_t co_s, T beta, T* B_dev, int64_t ldb, uint32_t state[6]) { \
+        CTX_OK(ctx); RLB_CHECK(bind(ctx)); RLB_REQUIRE(ctx, state);                                                                 \
+        return sketch_general_sparse_right<T>(ctx, layout, opA, opS, m, d, n, alpha, A_dev, lda, S_rows, S_cols, vec_nnz, ro_s, co_s, beta, \
+                                              B_dev, ldb, state);                                                                   \
+    }                                                                                                                               \
     int rlb200_sketch_general_dense_left_##SUF##_dev(rlb200_ctx* ctx, int layout, int opS, int opA, int64_t d, int64_t n, int64_t m, T alpha, \
                                                      int64_t S_rows, int64_t S_cols, int family, int major_axis, int64_t ro_s, int64_t co_s, \
                                                      const T* A_dev, int64_t lda, T beta, T* B_dev, int64_t ldb, uint32_t state[6]) {   \

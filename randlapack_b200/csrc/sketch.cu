@@ -867,9 +867,47 @@ int sketch_general_dense_right(Ctx* ctx, int layout, int opA, int opS, int64_t m
     });
 }
 
+// sketch_general with a SparseSkOp (short-axis / SASO) and every layout / transposition flag (skge.hh:907-960 left -> lskges :538-571;
+// :1078-1131 right -> rskges :573-620).  A tall short-axis operator is the transpose of the wide one with swapped dimensions and the same
+// seed (sparse_skops.hh:585-610: the index stream depends on (dim_major, dim_minor) only), so opS = Trans on a tall operator is the wide
+// kernel with (S_rows, S_cols) and (ro, co) swapped.  The right sketch is the left sketch of the transposed problem, as in the reference:
+// B = op(A) op(S)  <=>  B^T = op(S)^T op(A)^T, i.e. left(flipped layout, flipped opS, opA, d, m, n) on the same buffers.
+template <typename T>
+int sketch_general_sparse_left(Ctx* ctx, int layout, int opS, int opA, int64_t d, int64_t n, int64_t m, T alpha, int64_t S_rows, int64_t S_cols,
+                               int64_t vec_nnz, int64_t ro, int64_t co, const T* A, int64_t lda, T beta, T* B, int64_t ldb, uint32_t state[6]) {
+    RLB_REQUIRE(ctx, layout == RLB200_LAYOUT_COLMAJOR || layout == RLB200_LAYOUT_ROWMAJOR);
+    RLB_REQUIRE(ctx, (opS == 0 || opS == 1) && (opA == 0 || opA == 1));
+    RLB_REQUIRE(ctx, d >= 0 && n >= 0 && m >= 0);
+    if (opS) {
+        if (S_rows <= S_cols) { ctx->err = "sparse sketch_general: op(S) must be a wide short-axis operator (opS = Trans needs a tall S)"; return RLB200_ERR_UNSUPPORTED; }
+        std::swap(S_rows, S_cols);
+        std::swap(ro, co);
+    }
+    if (layout == RLB200_LAYOUT_COLMAJOR && opA == 0) return sketch_sparse_left<T>(ctx, S_rows, S_cols, vec_nnz, d, n, m, alpha, ro, co, A, lda, beta, B, ldb, state);
+    if (ctx->m_global >= 0) { ctx->err = "sketch_general on a row-sharded context: ColMajor with opA = NoTrans only"; return RLB200_ERR_UNSUPPORTED; }
+    ArenaScope as(ctx);
+    const T* Ac = nullptr; int64_t ldac = 0;
+    RLB_CHECK(data_as_colmajor<T>(ctx, as, layout, opA, m, n, A, lda, &Ac, &ldac));
+    return result_as_colmajor<T>(ctx, as, layout, d, n, alpha, beta, B, ldb, [&](T* Bc, int64_t ldc, T al, T be) {
+        return sketch_sparse_left<T>(ctx, S_rows, S_cols, vec_nnz, d, n, m, al, ro, co, Ac, ldac, be, Bc, ldc, state);
+    });
+}
+
+template <typename T>
+int sketch_general_sparse_right(Ctx* ctx, int layout, int opA, int opS, int64_t m, int64_t d, int64_t n, T alpha, const T* A, int64_t lda,
+                                int64_t S_rows, int64_t S_cols, int64_t vec_nnz, int64_t ro, int64_t co, T beta, T* B, int64_t ldb, uint32_t state[6]) {
+    RLB_REQUIRE(ctx, layout == RLB200_LAYOUT_COLMAJOR || layout == RLB200_LAYOUT_ROWMAJOR);
+    RLB_REQUIRE(ctx, (opS == 0 || opS == 1) && (opA == 0 || opA == 1));
+    if (ctx->m_global >= 0) { ctx->err = "right sparse sketch on a row-sharded context is not offered"; return RLB200_ERR_UNSUPPORTED; }
+    const int flipped = layout == RLB200_LAYOUT_COLMAJOR ? RLB200_LAYOUT_ROWMAJOR : RLB200_LAYOUT_COLMAJOR;
+    return sketch_general_sparse_left<T>(ctx, flipped, 1 - opS, opA, d, m, n, alpha, S_rows, S_cols, vec_nnz, ro, co, A, lda, beta, B, ldb, state);
+}
+
 #define INST(T)                                                                                                                                  \
     template int sketch_dense_left<T>(Ctx*, int64_t, int64_t, int, int, int64_t, int64_t, int64_t, T, int64_t, int64_t, const T*, int64_t, T, T*, int64_t, uint32_t*, int); \
     template int sketch_dense_right<T>(Ctx*, int64_t, int64_t, int, int, int64_t, int64_t, int64_t, T, const T*, int64_t, int64_t, int64_t, T, T*, int64_t, uint32_t*, int); \
+    template int sketch_general_sparse_left<T>(Ctx*, int, int, int, int64_t, int64_t, int64_t, T, int64_t, int64_t, int64_t, int64_t, int64_t, const T*, int64_t, T, T*, int64_t, uint32_t*); \
+    template int sketch_general_sparse_right<T>(Ctx*, int, int, int, int64_t, int64_t, int64_t, T, const T*, int64_t, int64_t, int64_t, int64_t, int64_t, int64_t, T, T*, int64_t, uint32_t*); \
     template int sketch_general_dense_left<T>(Ctx*, int, int, int, int64_t, int64_t, int64_t, T, int64_t, int64_t, int, int, int64_t, int64_t, const T*, int64_t, T, T*, int64_t, uint32_t*); \
     template int sketch_general_dense_right<T>(Ctx*, int, int, int, int64_t, int64_t, int64_t, T, const T*, int64_t, int64_t, int64_t, int, int, int64_t, int64_t, T, T*, int64_t, uint32_t*);
 INST(double)

@@ -260,3 +260,16 @@ def ref_sketch_general_dense(lib, left, layout, opS, opA, D, dims, A_flat, lda, 
     d, n, m = dims
     rc = f(int(left), layout, int(opS), int(opA), D[0], D[1], D[2], D[3], d, n, m, alpha, ro, co, A_flat.ctypes.data, lda, beta, B.ctypes.data, ldb, st)
     return rc, B, list(st)
+
+
+def ref_sketch_general_sparse(lib, left, layout, opS, opA, D, dims, A_flat, lda, B_flat, ldb, seed6, alpha=1.0, beta=0.0, ro=0, co=0):
+    """sketch_general with a short-axis SparseSkOp and every flag via the compiled reference.  D = (S_rows, S_cols, vec_nnz); dims = (d, n, m)."""
+    dt = A_flat.dtype
+    B = B_flat.copy()
+    st = (u32 * 6)(*seed6)
+    ft = _ft(dt)
+    f = getattr(lib, f"rlref_sketch_general_sparse_{_suf(dt)}")
+    f.argtypes = [ctypes.c_int] * 4 + [i64, i64, i64, i64, i64, i64, ft, i64, i64, ctypes.c_void_p, i64, ft, ctypes.c_void_p, i64, ctypes.POINTER(u32)]
+    d, n, m = dims
+    rc = f(int(left), layout, int(opS), int(opA), D[0], D[1], D[2], d, n, m, alpha, ro, co, A_flat.ctypes.data, lda, beta, B.ctypes.data, ldb, st)
+    return rc, B, list(st)

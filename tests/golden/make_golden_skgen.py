@@ -38,5 +38,31 @@ for left, layout, opS, opA in itertools.product((1, 0), (1, 2), (0, 1), (0, 1)):
         out[f"sg{i}_state_in"], out[f"sg{i}_state_out"] = np.array(seed, dtype=np.uint32), np.array(st, dtype=np.uint32)
         i += 1
 out["sg_count"] = np.array(i)
+# ---- the same with a short-axis SparseSkOp (skge.hh:907-960, 1078-1131): op(submat(S)) wide, i.e. S tall whenever its transpose is applied
+j = 0
+for left, layout, opS, opA in itertools.product((1, 0), (1, 2), (0, 1), (0, 1)):
+    for (d, n, m, ro, co, dt, nnz) in ((24, 37, 150, 3, 5, np.float64, 3), (8, 5, 33, 0, 2, np.float32, 1)):
+        if not left:
+            n = 60 if d == 24 else 21         # right sketch: contraction length n > d so that the n x d block is tall
+        rs, cs = ((m, d) if opS else (d, m)) if left else ((d, n) if opS else (n, d))
+        S_rows, S_cols = rs + ro + 2, cs + co + 1
+        assert (S_rows > S_cols) == (rs > cs)
+        ra, ca = (n, m) if opA else (m, n)
+        rb, cb = (d, n) if left else (m, d)
+        lda = (ra if layout == 1 else ca) + 3
+        ldb = (rb if layout == 1 else cb) + 2
+        rng = np.random.RandomState(2000 + j)
+        A = rng.standard_normal(lda * (ca if layout == 1 else ra)).astype(dt)
+        B = rng.standard_normal(ldb * (cb if layout == 1 else rb)).astype(dt)
+        seed = [5 + j, 0, 0, 0, 13, 0]
+        rc, Bo, st = _ref.ref_sketch_general_sparse(R, left, layout, opS, opA, (S_rows, S_cols, nnz), (d, n, m), A, lda, B, ldb, seed, alpha=0.75,
+                                                    beta=-0.5, ro=ro, co=co)
+        assert rc == 0
+        out[f"ss{j}_args"] = np.array([left, layout, opS, opA, d, n, m, ro, co, S_rows, S_cols, nnz, lda, ldb], dtype=np.int64)
+        out[f"ss{j}_Bout"] = Bo
+        out[f"ss{j}_dtype"] = np.array("f64" if dt == np.float64 else "f32")
+        out[f"ss{j}_state_in"], out[f"ss{j}_state_out"] = np.array(seed, dtype=np.uint32), np.array(st, dtype=np.uint32)
+        j += 1
+out["ss_count"] = np.array(j)
 np.savez_compressed(os.path.join(HERE, "skgen_vectors.npz"), **out)
-print("cases", i)
+print("cases", i, j)

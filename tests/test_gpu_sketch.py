@@ -224,3 +224,67 @@ def test_sketch_general_dense_tall_vs_oracle(ctx, flags):
                                       O.RNGState.from_words(seed))
     assert list(s.words()) == list(nxt.words())
     assert np.linalg.norm(out - ref) <= 2e-6 * np.linalg.norm(ref)
+
+
+from _qrcases import ss_input  # noqa: E402
+
+
+def _ss_run(ctx, c, A, B, alpha, beta, seed):
+    Ad, Bd = torch.from_numpy(A).cuda(), torch.from_numpy(B.copy()).cuda()
+    D = rl.SparseDist(c["S_rows"], c["S_cols"], c["vec_nnz"])
+    s = _st(seed)
+    if c["left"]:
+        rl.sketch_general_sparse_left(ctx, c["layout"], c["opS"], c["opA"], c["d"], c["n"], c["m"], alpha, D, c["ro"], c["co"], Ad, c["lda"], beta,
+                                      Bd, c["ldb"], s)
+    else:
+        rl.sketch_general_sparse_right(ctx, c["layout"], c["opA"], c["opS"], c["m"], c["d"], c["n"], alpha, Ad, c["lda"], D, c["ro"], c["co"], beta,
+                                       Bd, c["ldb"], s)
+    return Bd.cpu().numpy(), s
+
+
+@pytest.mark.parametrize("i", range(int(GS["ss_count"])))
+def test_sketch_general_sparse_all_flags_golden(ctx, i):
+    """Short-axis SparseSkOp, every layout / opS / opA, left (skge.hh:907-960) and right (:1078-1131; run as the left sketch of the transposed
+    problem), against golden outputs of the compiled reference.  RNG state exact, padding of B untouched, values 1e-12 (fp64) / 2e-5 (fp32)
+    relative to the largest entry (sums of at most a few dozen +-A entries in a different order)."""
+    c = ss_input(i)
+    out, s = _ss_run(ctx, c, c["A"], c["B"], 0.75, -0.5, c["seed"])
+    ref = GS[f"ss{i}_Bout"]
+    assert list(s.words()) == list(GS[f"ss{i}_state_out"])
+    rb, cb = (c["d"], c["n"]) if c["left"] else (c["m"], c["d"])
+    mask = np.ones(ref.shape, dtype=bool)
+    O._mat_view(mask, rb, cb, c["ldb"], c["layout"])[:, :] = False
+    assert np.array_equal(out[mask], c["B"][mask]), "padding of B was written"
+    tol = 1e-12 if c["dtype"] == np.float64 else 2e-5
+    assert np.abs(out - ref).max() <= tol * np.abs(ref).max()
+
+
+def test_sketch_general_sparse_rejects_tall_op(ctx):
+    """op(submat(S)) tall (a wide S transposed on the left) is not a sketch: RLB200_ERR_UNSUPPORTED, never a fallback."""
+    A = torch.zeros(40 * 8, dtype=torch.float64, device="cuda")
+    B = torch.zeros(40 * 8, dtype=torch.float64, device="cuda")
+    with pytest.raises(rl.Error):
+        rl.sketch_general_sparse_left(ctx, rl.LAYOUT_COLMAJOR, True, False, 20, 8, 10, 1.0, rl.SparseDist(10, 40, 2), 0, 0, A, 10, 0.0, B, 20,
+                                      rl.RNGState(0))
+
+
+@pytest.mark.parametrize("flags", [(1, 2, 0, 0), (1, 1, 1, 1), (0, 1, 0, 0), (0, 2, 1, 1)])
+def test_sketch_general_sparse_tall_vs_oracle(ctx, flags):
+    """The same at a size where the strip kernel runs (20000-row data matrix, d = 256, 128 columns, vec_nnz = 2) behind the transposition
+    wrappers, against the restatement on the same operator."""
+    left, layout, opS, opA = flags
+    d, n, m = (256, 128, 20000) if left else (64, 2000, 300)
+    rs, cs = ((m, d) if opS else (d, m)) if left else ((d, n) if opS else (n, d))
+    ra, ca = (n, m) if opA else (m, n)
+    rb, cb = (d, n) if left else (m, d)
+    c = dict(left=left, layout=layout, opS=opS, opA=opA, d=d, n=n, m=m, ro=1, co=2, S_rows=rs + 1, S_cols=cs + 2, vec_nnz=2,
+             lda=(ra if layout == 1 else ca), ldb=(rb if layout == 1 else cb) + 1)
+    rng = np.random.RandomState(6)
+    A = rng.standard_normal(c["lda"] * (ca if layout == 1 else ra))
+    B = rng.standard_normal(c["ldb"] * (cb if layout == 1 else rb))
+    seed = [4, 0, 0, 0, 21, 0]
+    out, s = _ss_run(ctx, c, A, B, 1.5, 0.5, seed)
+    ref, nxt = O.sketch_general_sparse(left, layout, opS, opA, d, n, m, 1.5, c["S_rows"], c["S_cols"], 2, 1, 2, A, c["lda"], 0.5, B, c["ldb"],
+                                       O.RNGState.from_words(seed))
+    assert list(s.words()) == list(nxt.words())
+    assert np.abs(out - ref).max() <= 1e-11 * np.abs(ref).max()

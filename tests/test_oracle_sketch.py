@@ -96,3 +96,19 @@ def test_sketch_general_dense_all_flags_golden(i):
     assert list(nxt.words()) == list(GS[f"sg{i}_state_out"])
     tol = 1e-12 if c["dtype"] == np.float64 else 2e-5
     assert np.abs(out - ref).max() <= tol * np.abs(ref).max()
+
+
+from _qrcases import ss_input  # noqa: E402
+
+
+@pytest.mark.parametrize("i", range(int(GS["ss_count"])))
+def test_sketch_general_sparse_all_flags_golden(i):
+    """The same with a short-axis SparseSkOp (skge.hh:907-960, 1078-1131): restatement vs golden outputs of the compiled reference.
+    This also pins the fact the device path relies on: a tall short-axis operator is the transpose of the wide one with the same seed."""
+    c = ss_input(i)
+    out, nxt = O.sketch_general_sparse(c["left"], c["layout"], c["opS"], c["opA"], c["d"], c["n"], c["m"], 0.75, c["S_rows"], c["S_cols"],
+                                       c["vec_nnz"], c["ro"], c["co"], c["A"], c["lda"], -0.5, c["B"], c["ldb"], O.RNGState.from_words(c["seed"]))
+    ref = GS[f"ss{i}_Bout"]
+    assert list(nxt.words()) == list(GS[f"ss{i}_state_out"])
+    tol = 1e-12 if c["dtype"] == np.float64 else 2e-5
+    assert np.abs(out - ref).max() <= tol * np.abs(ref).max()
