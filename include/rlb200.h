@@ -184,6 +184,17 @@ RLB200_API int rlb200_sketch_sparse_left_f32_dev(rlb200_ctx* ctx, int64_t S_rows
                                       int64_t m, float alpha, int64_t ro_s, int64_t co_s, const float* A_dev, int64_t lda, float beta,
                                       float* B_dev, int64_t ldb, uint32_t state[6]);
 
+/* The same call with a WIDE Axis::Long SparseSkOp (LASO, sparse_skops.hh:167-282, 669-684): every ROW of S holds vec_nnz iid uniform column
+ * indices drawn with replacement, duplicates merged into sqrt(count) * (first sign).  One CTA per sketch row regenerates the row and gathers
+ * the <= vec_nnz rows of A it touches.  state <- S.next_state.  rlb200_fill_sparse_*_dev exports the same operator (major_axis = RLB200_AXIS_LONG;
+ * its size query then returns the upper bound vec_nnz * #vectors, the call the exact count after merging).  Single shard. */
+RLB200_API int rlb200_sketch_sparse_left_laso_f64_dev(rlb200_ctx* ctx, int64_t S_rows, int64_t S_cols, int64_t vec_nnz, int64_t d, int64_t n,
+                                           int64_t m, double alpha, int64_t ro_s, int64_t co_s, const double* A_dev, int64_t lda, double beta,
+                                           double* B_dev, int64_t ldb, uint32_t state[6]);
+RLB200_API int rlb200_sketch_sparse_left_laso_f32_dev(rlb200_ctx* ctx, int64_t S_rows, int64_t S_cols, int64_t vec_nnz, int64_t d, int64_t n,
+                                           int64_t m, float alpha, int64_t ro_s, int64_t co_s, const float* A_dev, int64_t lda, float beta,
+                                           float* B_dev, int64_t ldb, uint32_t state[6]);
+
 /* ---- a5: sketch_general with a DenseSkOp, left (lskge3, skge.hh:155-203) and right (rskge3, skge.hh:308-356), ColMajor, NoTrans.
  * S = DenseSkOp(DenseDist(S_rows, S_cols, family, major_axis), state); it is never materialised as a whole: panels are regenerated
  * from the Philox state into an L2-resident ring buffer and consumed by the tensor-pipe GEMM.

@@ -235,9 +235,9 @@ static int sketch_general_dense_impl(bool left, int layout, int opS, int opA, in
 template <typename T>
 static int sketch_general_sparse_impl(bool left, int layout, int opS, int opA, int64_t S_rows, int64_t S_cols, int64_t vec_nnz, int64_t d, int64_t n,
                                       int64_t m, T alpha, int64_t ro, int64_t co, const T* A, int64_t lda, T beta, T* B, int64_t ldb,
-                                      uint32_t state[6]) {
+                                      uint32_t state[6], int major_axis = RL_AXIS_SHORT) {
     RL_TRY
-    RandBLAS::SparseDist DS(S_rows, S_cols, vec_nnz);
+    RandBLAS::SparseDist DS(S_rows, S_cols, vec_nnz, major_axis == RL_AXIS_SHORT ? RandBLAS::Axis::Short : RandBLAS::Axis::Long);
     State st = load_state(state);
     RandBLAS::SparseSkOp<T, RNG> S(DS, st);
     store_state(S.next_state, state);
@@ -477,6 +477,12 @@ int rlref_mat_gen_f32(int type, int64_t m, int64_t n, int64_t rank, float cond, 
                                           int64_t ldb, uint32_t state[6]) {                                                                    \
         return sketch_general_sparse_impl<T>(left != 0, layout, opS, opA, S_rows, S_cols, vec_nnz, d, n, m, alpha, ro, co, A, lda, beta, B,    \
                                              ldb, state);                                                                                     \
+    }                                                                                                                                     \
+    int rlref_sketch_general_sparse_axis_##SUF(int left, int layout, int opS, int opA, int64_t S_rows, int64_t S_cols, int64_t vec_nnz,       \
+                                               int major_axis, int64_t d, int64_t n, int64_t m, T alpha, int64_t ro, int64_t co, const T* A,   \
+                                               int64_t lda, T beta, T* B, int64_t ldb, uint32_t state[6]) {                                    \
+        return sketch_general_sparse_impl<T>(left != 0, layout, opS, opA, S_rows, S_cols, vec_nnz, d, n, m, alpha, ro, co, A, lda, beta, B,    \
+                                             ldb, state, major_axis);                                                                         \
     }                                                                                                                                     \
     int rlref_cqrrpt_##SUF(int64_t m, int64_t n, T* A, int64_t lda, T* R, int64_t ldr, int64_t* J, T d_factor, T eps, int64_t nnz,         \
                            int qrcp, int64_t* rank, uint32_t state[6]) {                                                                   \

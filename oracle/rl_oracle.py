@@ -446,6 +446,45 @@ def fill_sparse(n_rows, n_cols, vec_nnz, state: RNGState, dtype=np.float64, sub=
     return k, vals[:k].astype(dtype), rows[:k].copy(), cols[:k].copy(), RNGState.from_words(w)
 
 
+def fill_sparse_laso(n_rows, n_cols, vec_nnz, state: RNGState, dtype=np.float64, sub=None):
+    """RandBLAS::fill_sparse_unpacked for SparseDist(n_rows, n_cols, vec_nnz, Axis::Long) (sparse_skops.hh:585-610, 669-704): every long-axis
+    vector draws vec_nnz iid uniform indices (one Philox counter each: (rv0 + 2^32 rv1) mod dim_major, sign from rv2, util.hh:521-541),
+    duplicates are merged into sqrt(count) * first sign (:483-511), survivors sorted by index, then filtered to the sub-matrix window.
+    -> (nnz, vals, rows, cols, returned RNGState)."""
+    sr, sc, ro, co = sub if sub is not None else (n_rows, n_cols, 0, 0)
+    dt = np.dtype(dtype)
+    short_rows = n_rows <= n_cols
+    dim_major = max(n_rows, n_cols)
+    vec_off, vec_sub = (ro, sr) if short_rows else (co, sc)
+    lo, ls = (co, sc) if short_rows else (ro, sr)
+    ctr = ctr_incr(state.counter, vec_off * vec_nnz)
+    maj, mino, vals = [], [], []
+    for v in range(vec_sub):
+        first, count = {}, {}
+        for _ in range(vec_nnz):
+            rv = philox4x32_10(ctr, state.key)
+            ctr = ctr_incr(ctr, 1)
+            ell = (rv[0] + (rv[1] << 32)) % dim_major
+            if ell in count:
+                count[ell] += 1
+            else:
+                count[ell] = 1
+                first[ell] = 1.0 if rv[2] % 2 == 0 else -1.0
+        for ell in sorted(count):
+            if lo <= ell < lo + ls:
+                maj.append(ell - lo)
+                mino.append(v)
+                vals.append(np.sqrt(dt.type(count[ell])) * dt.type(first[ell]))
+    maj, mino = np.array(maj, dtype=np.int64), np.array(mino, dtype=np.int64)
+    rows, cols = (mino, maj) if short_rows else (maj, mino)
+    return len(vals), np.array(vals, dtype=dt), rows, cols, RNGState(state.key, ctr)
+
+
+def laso_next_state(n_rows, n_cols, vec_nnz, state: RNGState):
+    """compute_next_state for Axis::Long (sparse_skops.hh:302-312): min(n_rows, n_cols) vectors of vec_nnz draws."""
+    return RNGState(state.key, ctr_incr(state.counter, min(n_rows, n_cols) * vec_nnz))
+
+
 def saso_next_state(n_rows, n_cols, vec_nnz, state: RNGState):
     """SparseSkOp::next_state (sparse_skops.hh:302-312)."""
     w = state.words()
@@ -527,19 +566,26 @@ def sketch_general_dense(left, layout, opS, opA, d, n, m, alpha, S_rows, S_cols,
     return out, nxt
 
 
-def sketch_general_sparse(left, layout, opS, opA, d, n, m, alpha, S_rows, S_cols, vec_nnz, ro, co, A_flat, lda, beta, B_flat, ldb, state: RNGState):
+def sketch_general_sparse(left, layout, opS, opA, d, n, m, alpha, S_rows, S_cols, vec_nnz, ro, co, A_flat, lda, beta, B_flat, ldb, state: RNGState,
+                          major_axis=AXIS_SHORT):
     """RandBLAS::sketch_general with a short-axis SparseSkOp and every layout / transposition flag (skge.hh:907-960 left, :1078-1131 right),
     restated on the materialised operator.  A tall short-axis operator is generated as the transpose of the wide one with swapped dimensions
     and the same seed (sparse_skops.hh:585-610: the index stream depends on (dim_major, dim_minor) only).  -> (B_flat (new), S.next_state)."""
     dt = A_flat.dtype
-    tall = S_rows > S_cols
-    wr, wc = (S_cols, S_rows) if tall else (S_rows, S_cols)
-    k, vals, rows, cols, _ = fill_sparse(wr, wc, vec_nnz, state, dt)
-    S = np.zeros((wr, wc), dtype=dt)
-    np.add.at(S, (rows, cols), vals)
-    if tall:
-        S = S.T
-    nxt = saso_next_state(wr, wc, vec_nnz, state)
+    if major_axis == AXIS_LONG:
+        k, vals, rows, cols, _ = fill_sparse_laso(S_rows, S_cols, vec_nnz, state, dt)
+        S = np.zeros((S_rows, S_cols), dtype=dt)
+        np.add.at(S, (rows, cols), vals)
+        nxt = laso_next_state(S_rows, S_cols, vec_nnz, state)
+    else:
+        tall = S_rows > S_cols
+        wr, wc = (S_cols, S_rows) if tall else (S_rows, S_cols)
+        k, vals, rows, cols, _ = fill_sparse(wr, wc, vec_nnz, state, dt)
+        S = np.zeros((wr, wc), dtype=dt)
+        np.add.at(S, (rows, cols), vals)
+        if tall:
+            S = S.T
+        nxt = saso_next_state(wr, wc, vec_nnz, state)
     rs, cs = ((m, d) if opS else (d, m)) if left else ((d, n) if opS else (n, d))
     if S_rows < rs + ro or S_cols < cs + co:
         raise ValueError("sketch_general: submatrix of S out of range (randblas_require)")

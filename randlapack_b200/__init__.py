@@ -302,7 +302,8 @@ def fill_dense(ctx: Context, D: DenseDist, state: RNGState, dtype=None, layout=L
 
 @dataclass
 class SparseDist:
-    """RandBLAS::SparseDist (RandBLAS/RandBLAS/sparse_skops.hh:167-282); Axis::Short (SASO) is the default and the only axis on device."""
+    """RandBLAS::SparseDist (RandBLAS/RandBLAS/sparse_skops.hh:167-282); Axis::Short (SASO) is the default; Axis::Long (LASO) is offered for generation (fill_sparse) and
+    for the left sketch with a wide operator (sketch_general_left)."""
     n_rows: int
     n_cols: int
     vec_nnz: int = 4
@@ -352,9 +353,9 @@ def sketch_general_left(ctx: Context, D, state: RNGState, A, d=None, alpha=1.0, 
         beta = 0.0
     w = state.words()
     if isinstance(D, SparseDist):
-        if D.major_axis != AXIS_SHORT:
-            raise Error(_capi.ERR_UNSUPPORTED, "Axis::Long sparse operators are not offered on the device")
-        fn = getattr(ctx._lib, f"rlb200_sketch_sparse_left_{_suffix(A.dtype)}_dev")
+        # Axis::Long (LASO, sparse_skops.hh:669-684): rows of the wide operator drawn with replacement; Axis::Short: SASO
+        name = "sketch_sparse_left" if D.major_axis == AXIS_SHORT else "sketch_sparse_left_laso"
+        fn = getattr(ctx._lib, f"rlb200_{name}_{_suffix(A.dtype)}_dev")
         ctx.check(fn(ctx._h, D.n_rows, D.n_cols, D.vec_nnz, d, n, m, alpha, ro_s, co_s, A.data_ptr(), _ld(A), beta, B.data_ptr(), _ld(B), w))
     else:
         fn = getattr(ctx._lib, f"rlb200_sketch_dense_left_{_suffix(A.dtype)}_dev")

@@ -107,6 +107,7 @@ for _suf, _ft in (("f64", ctypes.c_double), ("f32", ctypes.c_float)):
                                                                          c_i64, c_i64, c_vp, c_i64, _ft, c_vp, c_i64, P_u32])
     SIGNATURES[f"rlb200_sketch_general_dense_right_{_suf}_dev"] = (c_int, [c_vp, c_int, c_int, c_int, c_i64, c_i64, c_i64, _ft, c_vp, c_i64, c_i64, c_i64,
                                                                           c_int, c_int, c_i64, c_i64, _ft, c_vp, c_i64, P_u32])
+    SIGNATURES[f"rlb200_sketch_sparse_left_laso_{_suf}_dev"] = _F(_ft)["sketch_sparse_left"]
     SIGNATURES[f"rlb200_sketch_general_sparse_left_{_suf}_dev"] = (c_int, [c_vp, c_int, c_int, c_int, c_i64, c_i64, c_i64, _ft, c_i64, c_i64, c_i64,
                                                                           c_i64, c_i64, c_vp, c_i64, _ft, c_vp, c_i64, P_u32])
     SIGNATURES[f"rlb200_sketch_general_sparse_right_{_suf}_dev"] = (c_int, [c_vp, c_int, c_int, c_int, c_i64, c_i64, c_i64, _ft, c_vp, c_i64, c_i64, c_i64,

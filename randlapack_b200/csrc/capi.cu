@@ -259,6 +259,12 @@ int rlb200_set_i8_digits(rlb200_ctx* ctx, int digits) {
         return sketch_dense_right<T>(ctx, S_rows, S_cols, family, major_axis, m, d, n, alpha, A_dev, lda, ro_s, co_s, beta, B_dev,  \
                                      ldb, state);                                                                                   \
     }                                                                                                                               \
+    int rlb200_sketch_sparse_left_laso_##SUF##_dev(rlb200_ctx* ctx, int64_t S_rows, int64_t S_cols, int64_t vec_nnz, int64_t d, int64_t n, \
+                                                   int64_t m, T alpha, int64_t ro_s, int64_t co_s, const T* A_dev, int64_t lda, T beta, \
+                                                   T* B_dev, int64_t ldb, uint32_t state[6]) {                                      \
+        CTX_OK(ctx); RLB_CHECK(bind(ctx)); RLB_REQUIRE(ctx, state);                                                                 \
+        return sketch_sparse_left_laso<T>(ctx, S_rows, S_cols, vec_nnz, d, n, m, alpha, ro_s, co_s, A_dev, lda, beta, B_dev, ldb, state); \
+    }                                                                                                                               \
     int rlb200_sketch_general_sparse_left_##SUF##_dev(rlb200_ctx* ctx, int layout, int opS, int opA, int64_t d, int64_t n, int64_t m, T alpha, \
                                                       int64_t S_rows, int64_t S_cols, int64_t vec_nnz, int64_t ro_s, int64_t co_s,  \
                                                       const T* A_dev, int64_t lda, T beta, T* B_dev, int64_t ldb, uint32_t state[6]) { \

@@ -100,6 +100,9 @@ template <typename T>
 int sketch_general_dense_right(Ctx* ctx, int layout, int opA, int opS, int64_t m, int64_t d, int64_t n, T alpha, const T* A, int64_t lda,
                                int64_t S_rows, int64_t S_cols, int family, int major_axis, int64_t ro, int64_t co, T beta, T* B, int64_t ldb, uint32_t state[6]);
 template <typename T>
+int sketch_sparse_left_laso(Ctx* ctx, int64_t S_rows, int64_t S_cols, int64_t vec_nnz, int64_t d, int64_t n, int64_t m, T alpha, int64_t ro,
+                            int64_t co, const T* A, int64_t lda, T beta, T* B, int64_t ldb, uint32_t state[6]);
+template <typename T>
 int sketch_general_sparse_left(Ctx* ctx, int layout, int opS, int opA, int64_t d, int64_t n, int64_t m, T alpha, int64_t S_rows, int64_t S_cols,
                                int64_t vec_nnz, int64_t ro, int64_t co, const T* A, int64_t lda, T beta, T* B, int64_t ldb, uint32_t state[6]);
 template <typename T>

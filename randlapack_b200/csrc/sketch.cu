@@ -107,14 +107,103 @@ __global__ void __launch_bounds__(256) saso_coo_kernel(Ctr128 seed, uint32_t k0,
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Axis::Long sparse operators (LASO, sparse_skops.hh:669-684): long-axis vector i draws vec_nnz iid uniform indices in [0, dim_major) - one Philox
+// counter each, index = (rv[0] + 2^32 rv[1]) mod dim_major, sign from rv[2] (util.hh:521-541) - duplicates are merged into
+// sqrt(count) * (sign of the first occurrence) (laso_merge_long_axis_vector_coo_data, :483-511) and the survivors sorted by index (:641-653).
+// Returns the number of distinct indices; idx ascending, cnt their multiplicities, neg the first-occurrence signs.
+// ------------------------------------------------------------------------------------------------
+__device__ int laso_vector(const Ctr128& seed, uint32_t k0, uint32_t k1, int64_t i, int nnz, int64_t dim_major, int64_t* idx, int* cnt, uint8_t* neg) {
+    int nd = 0;
+    for (int t = 0; t < nnz; ++t) {
+        uint32_t rv[4];
+        philox4x32_10(ctr_add(seed, (uint64_t)i * (uint64_t)nnz + (uint64_t)t), k0, k1, rv);
+        const uint64_t s = (uint64_t)rv[0] + ((uint64_t)rv[1] << 32);
+        const int64_t ell = (int64_t)(s % (uint64_t)dim_major);
+        int f = 0;
+        for (; f < nd && idx[f] != ell; ++f) {}
+        if (f < nd) cnt[f] += 1;
+        else { idx[nd] = ell; cnt[nd] = 1; neg[nd] = (rv[2] & 1u) ? 1 : 0; ++nd; }
+    }
+    for (int a = 1; a < nd; ++a) {
+        const int64_t key = idx[a]; const int c0 = cnt[a]; const uint8_t v = neg[a];
+        int c = a - 1;
+        for (; c >= 0 && idx[c] > key; --c) { idx[c + 1] = idx[c]; cnt[c + 1] = cnt[c]; neg[c + 1] = neg[c]; }
+        idx[c + 1] = key; cnt[c + 1] = c0; neg[c + 1] = v;
+    }
+    return nd;
+}
+template <typename T>
+__device__ __forceinline__ T laso_value(int count, uint8_t neg) {          // std::sqrt(c) * loc2scale[ell] in the working type (:506)
+    T r;
+    if constexpr (sizeof(T) == 8) r = sqrt((double)count); else r = sqrtf((float)count);
+    return neg ? -r : r;
+}
+// vector v (absolute index vec_off + v) keeps the entries whose long-axis index lies in [long_off, long_off + long_sub)
+__global__ void __launch_bounds__(128) laso_count_kernel(Ctr128 seed, uint32_t k0, uint32_t k1, int64_t vec_off, int64_t vec_sub, int nnz, int64_t dim_major,
+                                                         int64_t long_off, int64_t long_sub, int* __restrict__ out) {
+    for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < vec_sub; v += (int64_t)gridDim.x * blockDim.x) {
+        int64_t idx[kSasoMaxNnz]; int cnt[kSasoMaxNnz]; uint8_t neg[kSasoMaxNnz];
+        const int nd = laso_vector(seed, k0, k1, vec_off + v, nnz, dim_major, idx, cnt, neg);
+        int c = 0;
+        for (int t = 0; t < nd; ++t) c += (idx[t] >= long_off && idx[t] < long_off + long_sub);
+        out[v] = c;
+    }
+}
+template <typename T>
+__global__ void __launch_bounds__(128) laso_coo_kernel(Ctr128 seed, uint32_t k0, uint32_t k1, int64_t vec_off, int64_t vec_sub, int nnz, int64_t dim_major,
+                                                       int64_t long_off, int64_t long_sub, const int64_t* __restrict__ pos, T* __restrict__ vals,
+                                                       int64_t* __restrict__ idx_major, int64_t* __restrict__ idx_minor) {
+    for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < vec_sub; v += (int64_t)gridDim.x * blockDim.x) {
+        int64_t idx[kSasoMaxNnz]; int cnt[kSasoMaxNnz]; uint8_t neg[kSasoMaxNnz];
+        const int nd = laso_vector(seed, k0, k1, vec_off + v, nnz, dim_major, idx, cnt, neg);
+        int64_t o = pos[v];
+        for (int t = 0; t < nd; ++t) {
+            const int64_t r = idx[t] - long_off;
+            if (r >= 0 && r < long_sub) { idx_major[o] = r; idx_minor[o] = v; vals[o] = laso_value<T>(cnt[t], neg[t]); ++o; }
+        }
+    }
+}
+// B(d x n) = alpha * S[ro : ro + d, co : co + m] A + beta * B for a WIDE long-axis operator (its rows are the long-axis vectors): one CTA per
+// sketch row regenerates the row's <= vec_nnz entries and gathers those rows of A; d * vec_nnz * n elements are touched in all.
+template <typename T>
+__global__ void __launch_bounds__(256) laso_apply_kernel(Ctr128 seed, uint32_t k0, uint32_t k1, int64_t ro, int nnz, int64_t dim_major, int64_t co,
+                                                         int64_t m, int64_t n, const T* __restrict__ A, int64_t lda, double alpha, double beta,
+                                                         T* __restrict__ B, int64_t ldb) {
+    __shared__ int64_t s_idx[kSasoMaxNnz];
+    __shared__ double s_w[kSasoMaxNnz];
+    __shared__ int s_n;
+    const int64_t r = blockIdx.x;
+    if (threadIdx.x == 0) {
+        int64_t idx[kSasoMaxNnz]; int cnt[kSasoMaxNnz]; uint8_t neg[kSasoMaxNnz];
+        const int nd = laso_vector(seed, k0, k1, ro + r, nnz, dim_major, idx, cnt, neg);
+        int k = 0;
+        for (int t = 0; t < nd; ++t) {
+            const int64_t j = idx[t] - co;
+            if (j >= 0 && j < m) { s_idx[k] = j; s_w[k] = (double)laso_value<T>(cnt[t], neg[t]); ++k; }
+        }
+        s_n = k;
+    }
+    __syncthreads();
+    const int k = s_n;
+    for (int64_t c = threadIdx.x; c < n; c += blockDim.x) {
+        double acc = 0.0;
+        for (int t = 0; t < k; ++t) acc = fma(s_w[t], (double)A[s_idx[t] + c * lda], acc);
+        double v = alpha * acc;
+        if (beta != 0.0) v += beta * (double)B[r + c * ldb];
+        B[r + c * ldb] = (T)v;
+    }
+}
+
 static int saso_check(Ctx* ctx, int64_t n_rows, int64_t n_cols, int64_t vec_nnz, int major_axis) {
     RLB_REQUIRE(ctx, n_rows > 0);          // sparse_skops.hh:222-225
     RLB_REQUIRE(ctx, n_cols > 0);
     RLB_REQUIRE(ctx, vec_nnz > 0);
-    if (major_axis != RLB200_AXIS_SHORT) { ctx->err = "SparseDist with Axis::Long (LASO) is not offered on the device"; return RLB200_ERR_UNSUPPORTED; }
-    RLB_REQUIRE(ctx, vec_nnz <= std::min(n_rows, n_cols));
+    RLB_REQUIRE(ctx, major_axis == RLB200_AXIS_SHORT || major_axis == RLB200_AXIS_LONG);
+    // vec_nnz <= dim_major (sparse_skops.hh:241)
+    RLB_REQUIRE(ctx, vec_nnz <= (major_axis == RLB200_AXIS_SHORT ? std::min(n_rows, n_cols) : std::max(n_rows, n_cols)));
     if (vec_nnz > kSasoMaxNnz) { ctx->err = "vec_nnz > 64 is not offered on the device"; return RLB200_ERR_UNSUPPORTED; }
-    RLB_REQUIRE(ctx, std::min(n_rows, n_cols) < (1ll << 31));
+    if (major_axis == RLB200_AXIS_SHORT) RLB_REQUIRE(ctx, std::min(n_rows, n_cols) < (1ll << 31));
     return 0;
 }
 
@@ -133,6 +222,36 @@ int fill_sparse_unpacked(Ctx* ctx, int64_t n_rows, int64_t n_cols, int64_t vec_n
     RLB_REQUIRE(ctx, n_rows >= sub_rows + ro);      // sparse_skops.hh:575-576
     RLB_REQUIRE(ctx, n_cols >= sub_cols + co);
     RLB_REQUIRE(ctx, nnz_out != nullptr);
+    if (major_axis == RLB200_AXIS_LONG) {
+        // sparse_skops.hh:585-610, 669-704: the vectors run along the LONG axis and are indexed by the short one
+        const bool short_rows = n_rows <= n_cols;
+        const int64_t dim_major_l = std::max(n_rows, n_cols);
+        const int64_t vec_off = short_rows ? ro : co, vec_sub = short_rows ? sub_rows : sub_cols;
+        const int64_t lo = short_rows ? co : ro, ls = short_rows ? sub_cols : sub_rows;
+        if (!vals || !rows || !cols) { *nnz_out = vec_nnz * vec_sub; return 0; }       // size query (:603-606): an upper bound for LASO
+        Ctr128 seed_l;
+        for (int i = 0; i < 4; ++i) seed_l.v[i] = state[i];
+        *nnz_out = 0;
+        if (vec_sub > 0) {
+            ArenaScope as(ctx);
+            int* cnt = as.take<int>(vec_sub); if (!cnt) return RLB200_ERR_ALLOC;
+            int64_t* pos = as.take<int64_t>(vec_sub + 1); if (!pos) return RLB200_ERR_ALLOC;
+            const int nb = (int)std::min<int64_t>((vec_sub + 127) / 128, (int64_t)ctx->num_sms * 16);
+            LaunchScope ls_(ctx, RLB200_TIMER_FILL, 3);
+            laso_count_kernel<<<nb, 128, 0, ctx->stream>>>(seed_l, state[4], state[5], vec_off, vec_sub, (int)vec_nnz, dim_major_l, lo, ls, cnt);
+            scan_int_kernel<<<1, 1024, 0, ctx->stream>>>(cnt, vec_sub, pos);
+            // major (long-axis) index = column of a wide operator, row of a tall one
+            laso_coo_kernel<T><<<nb, 128, 0, ctx->stream>>>(seed_l, state[4], state[5], vec_off, vec_sub, (int)vec_nnz, dim_major_l, lo, ls, pos, vals,
+                                                            short_rows ? cols : rows, short_rows ? rows : cols);
+            RLB_CUDA_OK(ctx, cudaGetLastError());
+            RLB_CUDA_OK(ctx, cudaMemcpyAsync(ctx->hbox, pos + vec_sub, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+            RLB_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+            *nnz_out = *static_cast<int64_t*>(ctx->hbox);
+        }
+        Ctr128 nx = ctr_add(seed_l, (uint64_t)((vec_off + vec_sub) * vec_nnz));        // end_state after the last sampled vector
+        for (int i = 0; i < 4; ++i) state[i] = nx.v[i];
+        return 0;
+    }
     const bool short_is_rows = n_rows <= n_cols;
     const int64_t dim_major = std::min(n_rows, n_cols);
     const int64_t short_off = short_is_rows ? ro : co, short_sub = short_is_rows ? sub_rows : sub_cols;
@@ -684,6 +803,31 @@ static int fill_left_panel(Ctx* ctx, int64_t S_rows, int64_t S_cols, int family,
     return fill_dense_unpacked<T>(ctx, S_rows, S_cols, family, major_axis, RLB200_LAYOUT_COLMAJOR, w, d, ro + j0, co, P, st);
 }
 
+// sketch_general(ColMajor, NoTrans, NoTrans, d, n, m, alpha, S, ro, co, A, lda, beta, B, ldb) with a WIDE Axis::Long SparseSkOp
+// (sparse_skops.hh:167-282, 669-684): state <- S.next_state = seed + min(S_rows, S_cols) * vec_nnz (:302-312).
+template <typename T>
+int sketch_sparse_left_laso(Ctx* ctx, int64_t S_rows, int64_t S_cols, int64_t vec_nnz, int64_t d, int64_t n, int64_t m, T alpha, int64_t ro,
+                            int64_t co, const T* A, int64_t lda, T beta, T* B, int64_t ldb, uint32_t state[6]) {
+    RLB_CHECK(saso_check(ctx, S_rows, S_cols, vec_nnz, RLB200_AXIS_LONG));
+    RLB_REQUIRE(ctx, d >= 0 && n >= 0 && m >= 0 && ro >= 0 && co >= 0);
+    RLB_REQUIRE(ctx, S_rows >= d + ro && S_cols >= m + co);
+    RLB_REQUIRE(ctx, lda >= m && ldb >= d);
+    if (ctx->m_global >= 0) { ctx->err = "long-axis sparse operators are not offered on a row-sharded context"; return RLB200_ERR_UNSUPPORTED; }
+    if (S_rows > S_cols) { ctx->err = "left sparse sketch with a tall operator is not offered on the device"; return RLB200_ERR_UNSUPPORTED; }
+    RLB_REQUIRE(ctx, d < (1ll << 31));
+    Ctr128 seed;
+    for (int i = 0; i < 4; ++i) seed.v[i] = state[i];
+    if (d > 0 && n > 0) {
+        LaunchScope ls(ctx, RLB200_TIMER_SKETCH);
+        laso_apply_kernel<T><<<(unsigned)d, 256, 0, ctx->stream>>>(seed, state[4], state[5], ro, (int)vec_nnz, S_cols, co, m, n, A, lda, (double)alpha,
+                                                                  (double)beta, B, ldb);
+        RLB_CUDA_OK(ctx, cudaGetLastError());
+    }
+    Ctr128 nx = ctr_add(seed, (uint64_t)(std::min(S_rows, S_cols) * vec_nnz));
+    for (int i = 0; i < 4; ++i) state[i] = nx.v[i];
+    return 0;
+}
+
 template <typename T>
 int sketch_dense_left(Ctx* ctx, int64_t S_rows, int64_t S_cols, int family, int major_axis, int64_t d, int64_t n, int64_t m, T alpha,
                       int64_t ro, int64_t co, const T* A, int64_t lda, T beta, T* B, int64_t ldb, uint32_t state[6], int opS) {
@@ -906,6 +1050,7 @@ int sketch_general_sparse_right(Ctx* ctx, int layout, int opA, int opS, int64_t 
 #define INST(T)                                                                                                                                  \
     template int sketch_dense_left<T>(Ctx*, int64_t, int64_t, int, int, int64_t, int64_t, int64_t, T, int64_t, int64_t, const T*, int64_t, T, T*, int64_t, uint32_t*, int); \
     template int sketch_dense_right<T>(Ctx*, int64_t, int64_t, int, int, int64_t, int64_t, int64_t, T, const T*, int64_t, int64_t, int64_t, T, T*, int64_t, uint32_t*, int); \
+    template int sketch_sparse_left_laso<T>(Ctx*, int64_t, int64_t, int64_t, int64_t, int64_t, int64_t, T, int64_t, int64_t, const T*, int64_t, T, T*, int64_t, uint32_t*); \
     template int sketch_general_sparse_left<T>(Ctx*, int, int, int, int64_t, int64_t, int64_t, T, int64_t, int64_t, int64_t, int64_t, int64_t, const T*, int64_t, T, T*, int64_t, uint32_t*); \
     template int sketch_general_sparse_right<T>(Ctx*, int, int, int, int64_t, int64_t, int64_t, T, const T*, int64_t, int64_t, int64_t, int64_t, int64_t, int64_t, T, T*, int64_t, uint32_t*); \
     template int sketch_general_dense_left<T>(Ctx*, int, int, int, int64_t, int64_t, int64_t, T, int64_t, int64_t, int, int, int64_t, int64_t, const T*, int64_t, T, T*, int64_t, uint32_t*); \

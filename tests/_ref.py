@@ -268,8 +268,10 @@ def ref_sketch_general_sparse(lib, left, layout, opS, opA, D, dims, A_flat, lda,
     B = B_flat.copy()
     st = (u32 * 6)(*seed6)
     ft = _ft(dt)
-    f = getattr(lib, f"rlref_sketch_general_sparse_{_suf(dt)}")
-    f.argtypes = [ctypes.c_int] * 4 + [i64, i64, i64, i64, i64, i64, ft, i64, i64, ctypes.c_void_p, i64, ft, ctypes.c_void_p, i64, ctypes.POINTER(u32)]
+    f = getattr(lib, f"rlref_sketch_general_sparse_axis_{_suf(dt)}")
+    f.argtypes = [ctypes.c_int] * 4 + [i64, i64, i64, ctypes.c_int, i64, i64, i64, ft, i64, i64, ctypes.c_void_p, i64, ft, ctypes.c_void_p, i64,
+                                       ctypes.POINTER(u32)]
     d, n, m = dims
-    rc = f(int(left), layout, int(opS), int(opA), D[0], D[1], D[2], d, n, m, alpha, ro, co, A_flat.ctypes.data, lda, beta, B.ctypes.data, ldb, st)
+    axis = D[3] if len(D) > 3 else 1          # RL_AXIS_SHORT
+    rc = f(int(left), layout, int(opS), int(opA), D[0], D[1], D[2], axis, d, n, m, alpha, ro, co, A_flat.ctypes.data, lda, beta, B.ctypes.data, ldb, st)
     return rc, B, list(st)

@@ -64,5 +64,32 @@ for left, layout, opS, opA in itertools.product((1, 0), (1, 2), (0, 1), (0, 1)):
         out[f"ss{j}_state_in"], out[f"ss{j}_state_out"] = np.array(seed, dtype=np.uint32), np.array(st, dtype=np.uint32)
         j += 1
 out["ss_count"] = np.array(j)
+# ---- Axis::Long operators (LASO, sparse_skops.hh:669-704): COO export (wide / tall / square, sub-matrices, many duplicates, fp32) and the left sketch
+LA = [(20, 300, 5, np.float64, None), (300, 20, 4, np.float64, None), (16, 40, 30, np.float32, None), (20, 300, 6, np.float64, (7, 100, 3, 50)),
+      (50, 50, 8, np.float64, (20, 30, 5, 10)), (64, 5000, 64, np.float64, None)]
+for k, (r, c, nnz, dt, sub) in enumerate(LA):
+    seed = [3 + k, 0, 0, 0, 17, 0]
+    rc, nz, vals, rows, cols, st = _ref.ref_fill_sparse(R, r, c, nnz, seed, dt, axis=0, sub=sub)
+    assert rc == 0
+    out[f"la{k}_args"] = np.array([r, c, nnz] + list(sub if sub else (r, c, 0, 0)), dtype=np.int64)
+    out[f"la{k}_dtype"] = np.array("f64" if dt == np.float64 else "f32")
+    out[f"la{k}_vals"], out[f"la{k}_rows"], out[f"la{k}_cols"] = vals[:nz], rows[:nz], cols[:nz]
+    out[f"la{k}_state_in"], out[f"la{k}_state_out"] = np.array(seed, dtype=np.uint32), np.array(st, dtype=np.uint32)
+out["la_count"] = np.array(len(LA))
+LS = [(24, 37, 150, 3, 5, np.float64, 6), (8, 5, 33, 0, 2, np.float32, 20), (128, 64, 3000, 1, 7, np.float64, 8)]
+for k, (d, n, m, ro, co, dt, nnz) in enumerate(LS):
+    S_rows, S_cols = d + ro + 2, m + co + 1
+    lda, ldb = m + 3, d + 2
+    rng = np.random.RandomState(3000 + k)
+    A = rng.standard_normal(lda * n).astype(dt)
+    B = rng.standard_normal(ldb * n).astype(dt)
+    seed = [9 + k, 0, 0, 0, 23, 0]
+    rc, Bo, st = _ref.ref_sketch_general_sparse(R, 1, 1, 0, 0, (S_rows, S_cols, nnz, 0), (d, n, m), A, lda, B, ldb, seed, alpha=0.75, beta=-0.5, ro=ro, co=co)
+    assert rc == 0
+    out[f"ls{k}_args"] = np.array([d, n, m, ro, co, S_rows, S_cols, nnz, lda, ldb], dtype=np.int64)
+    out[f"ls{k}_dtype"] = np.array("f64" if dt == np.float64 else "f32")
+    out[f"ls{k}_Bout"] = Bo
+    out[f"ls{k}_state_in"], out[f"ls{k}_state_out"] = np.array(seed, dtype=np.uint32), np.array(st, dtype=np.uint32)
+out["ls_count"] = np.array(len(LS))
 np.savez_compressed(os.path.join(HERE, "skgen_vectors.npz"), **out)
 print("cases", i, j)

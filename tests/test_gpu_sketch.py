@@ -288,3 +288,58 @@ def test_sketch_general_sparse_tall_vs_oracle(ctx, flags):
                                        O.RNGState.from_words(seed))
     assert list(s.words()) == list(nxt.words())
     assert np.abs(out - ref).max() <= 1e-11 * np.abs(ref).max()
+
+
+# ---- Axis::Long sparse operators (LASO, sparse_skops.hh:167-282, 669-704) ---------------------------------------------------------------------
+from _qrcases import ls_input  # noqa: E402
+
+
+@pytest.mark.parametrize("k", range(int(GS["la_count"])))
+def test_fill_sparse_laso_golden(ctx, k):
+    """COO export of an Axis::Long operator: indices, merged sqrt(count) * sign values (in the working precision), their order and the returned
+    state are integer / correctly-rounded work: bit-exact against the golden triplets of the compiled reference."""
+    r, c, nnz, sr, sc, ro, co = [int(x) for x in GS[f"la{k}_args"]]
+    dt = torch.float64 if str(GS[f"la{k}_dtype"]) == "f64" else torch.float32
+    D = rl.SparseDist(r, c, nnz, rl.AXIS_LONG)
+    nz, vals, rows, cols, st = rl.fill_sparse(ctx, D, _st(GS[f"la{k}_state_in"]), dt, sub=(sr, sc, ro, co))
+    assert nz == len(GS[f"la{k}_vals"]) and list(st.words()) == list(GS[f"la{k}_state_out"])
+    assert np.array_equal(vals.cpu().numpy(), GS[f"la{k}_vals"])
+    assert np.array_equal(rows.cpu().numpy(), GS[f"la{k}_rows"]) and np.array_equal(cols.cpu().numpy(), GS[f"la{k}_cols"])
+
+
+@pytest.mark.parametrize("k", range(int(GS["ls_count"])))
+def test_sketch_sparse_left_laso_golden(ctx, k):
+    """Left sketch with a wide Axis::Long operator against golden outputs of the compiled reference (sub-matrix offsets, padded leading
+    dimensions, alpha = 0.75, beta = -0.5): state exact, padding untouched, values 1e-12 (fp64) / 2e-5 (fp32) relative to the largest entry."""
+    c = ls_input(k)
+    dt = torch.float64 if c["dtype"] == np.float64 else torch.float32
+    Ad = torch.from_numpy(c["A"]).cuda().view(c["n"], c["lda"]).t()[: c["m"], :]
+    Bfull = torch.from_numpy(c["B"].copy()).cuda()
+    Bd = Bfull.view(c["n"], c["ldb"]).t()[: c["d"], :]
+    assert rl._ld(Ad) == c["lda"] and rl._ld(Bd) == c["ldb"] and Ad.dtype == dt
+    s = _st(c["seed"])
+    rl.sketch_general_left(ctx, rl.SparseDist(c["S_rows"], c["S_cols"], c["vec_nnz"], rl.AXIS_LONG), s, Ad, d=c["d"], alpha=0.75, beta=-0.5, B=Bd,
+                           ro_s=c["ro"], co_s=c["co"])
+    out, ref = Bfull.cpu().numpy(), GS[f"ls{k}_Bout"]
+    assert list(s.words()) == list(GS[f"ls{k}_state_out"])
+    mask = np.ones(ref.shape, dtype=bool)
+    O._mat_view(mask, c["d"], c["n"], c["ldb"], O.LAYOUT_COLMAJOR)[:, :] = False
+    assert np.array_equal(out[mask], c["B"][mask]), "padding of B was written"
+    tol = 1e-12 if c["dtype"] == np.float64 else 2e-5
+    assert np.abs(out - ref).max() <= tol * np.abs(ref).max()
+
+
+def test_sketch_sparse_left_laso_vs_device_coo(ctx):
+    """A larger case (d = 512, 2^16 x 96 data, vec_nnz = 16): the applied sketch equals the product with the operator exported by fill_sparse
+    on the same state (1e-13 relative), and the state advances by min(S_rows, S_cols) * vec_nnz counters."""
+    d, m, n, nnz = 512, 1 << 16, 96, 16
+    D = rl.SparseDist(d, m, nnz, rl.AXIS_LONG)
+    g = torch.Generator(device="cuda").manual_seed(3)
+    A = rl.to_f(torch.randn((m, n), dtype=torch.float64, device="cuda", generator=g))
+    s = rl.RNGState(5)
+    B = rl.sketch_general_left(ctx, D, s, A)
+    nz, vals, rows, cols, _ = rl.fill_sparse(ctx, D, rl.RNGState(5))
+    S = torch.sparse_coo_tensor(torch.stack([rows, cols]), vals, (d, m)).coalesce()
+    Bref = torch.sparse.mm(S, A.contiguous())
+    assert (B - Bref).abs().max().item() <= 1e-13 * Bref.abs().max().item()
+    assert nz <= d * nnz and list(s.words())[:1] == [d * nnz]

@@ -112,3 +112,28 @@ def test_sketch_general_sparse_all_flags_golden(i):
     assert list(nxt.words()) == list(GS[f"ss{i}_state_out"])
     tol = 1e-12 if c["dtype"] == np.float64 else 2e-5
     assert np.abs(out - ref).max() <= tol * np.abs(ref).max()
+
+
+from _qrcases import ls_input  # noqa: E402
+
+
+@pytest.mark.parametrize("k", range(int(GS["la_count"])))
+def test_fill_sparse_laso_golden(k):
+    """Axis::Long operators (sparse_skops.hh:669-704): the COO triplets of the restatement are bit-exact with the compiled reference's
+    (indices, merged sqrt(count) values in the working precision, order, returned state)."""
+    r, c, nnz, sr, sc, ro, co = [int(x) for x in GS[f"la{k}_args"]]
+    dt = np.float64 if str(GS[f"la{k}_dtype"]) == "f64" else np.float32
+    nz, vals, rows, cols, st = O.fill_sparse_laso(r, c, nnz, O.RNGState.from_words([int(x) for x in GS[f"la{k}_state_in"]]), dt, sub=(sr, sc, ro, co))
+    assert nz == len(GS[f"la{k}_vals"]) and list(st.words()) == list(GS[f"la{k}_state_out"])
+    assert np.array_equal(vals, GS[f"la{k}_vals"]) and np.array_equal(rows, GS[f"la{k}_rows"]) and np.array_equal(cols, GS[f"la{k}_cols"])
+
+
+@pytest.mark.parametrize("k", range(int(GS["ls_count"])))
+def test_sketch_sparse_left_laso_golden(k):
+    c = ls_input(k)
+    out, nxt = O.sketch_general_sparse(1, O.LAYOUT_COLMAJOR, 0, 0, c["d"], c["n"], c["m"], 0.75, c["S_rows"], c["S_cols"], c["vec_nnz"], c["ro"], c["co"],
+                                       c["A"], c["lda"], -0.5, c["B"], c["ldb"], O.RNGState.from_words(c["seed"]), major_axis=O.AXIS_LONG)
+    ref = GS[f"ls{k}_Bout"]
+    assert list(nxt.words()) == list(GS[f"ls{k}_state_out"])
+    tol = 1e-12 if c["dtype"] == np.float64 else 2e-5
+    assert np.abs(out - ref).max() <= tol * np.abs(ref).max()
