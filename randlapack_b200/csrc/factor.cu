@@ -341,6 +341,63 @@ __global__ void __launch_bounds__(256) qr_apply_kernel(int64_t d, int64_t n, int
     }
 }
 
+// The same step for TALL panels (d - j in the tens of thousands): one CTA per trailing column instead of one warp, so that a column's d - j
+// entries are covered by 256 threads (a warp walking 32768 rows is 1024 dependent iterations: 150 us per step measured through BQRRP / hqrrp
+// at m = 32768).  The sum of squares of the updated column is accumulated in the same pass, so the norm recomputation costs nothing extra.
+template <typename T, bool PIVOT>
+__global__ void __launch_bounds__(256) qr_apply_block_kernel(int64_t d, int64_t n, int64_t j, T* __restrict__ A, int64_t lda, double* __restrict__ vn1,
+                                                             double* __restrict__ vn2, const QrcpStep* __restrict__ step, double tol3z) {
+    __shared__ double s_red[8];
+    __shared__ double s_bc;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const double tau = step->tau;
+    const T* v = A + j * lda;
+    auto block_sum = [&](double x) -> double {
+        x = warp_sum(x);
+        __syncthreads();                       // s_red / s_bc of the previous reduction have been read by everyone
+        if (lane == 0) s_red[wid] = x;
+        __syncthreads();
+        if (tid == 0) s_bc = ((s_red[0] + s_red[1]) + (s_red[2] + s_red[3])) + ((s_red[4] + s_red[5]) + (s_red[6] + s_red[7]));
+        __syncthreads();
+        return s_bc;
+    };
+    for (int64_t c = j + 1 + blockIdx.x; c < n; c += gridDim.x) {
+        T* a = A + c * lda;
+        double ajc = (double)a[j];
+        double ss = 0.0;
+        if (tau != 0.0) {
+            double w = 0.0;
+            for (int64_t i = j + 1 + tid; i < d; i += 256) w = fma((double)v[i], (double)a[i], w);
+            w = block_sum(w) + ajc;
+            const double tw = tau * w;
+            for (int64_t i = j + 1 + tid; i < d; i += 256) {
+                const T nv = (T)((double)a[i] - tw * (double)v[i]);
+                a[i] = nv;
+                ss = fma((double)nv, (double)nv, ss);
+            }
+            ajc = (double)(T)(ajc - tw);
+            if (tid == 0) a[j] = (T)ajc;
+        } else if (PIVOT) {
+            for (int64_t i = j + 1 + tid; i < d; i += 256) { const double x = (double)a[i]; ss = fma(x, x, ss); }
+        }
+        if (PIVOT) {
+            ss = block_sum(ss);
+            const double n1 = vn1[c];
+            if (n1 != 0.0) {                   // LAPACK dlaqp2 partial-norm downdate
+                double temp = fabs(ajc) / n1;
+                temp = fmax(0.0, (1.0 + temp) * (1.0 - temp));
+                const double r = n1 / vn2[c];
+                const double temp2 = temp * r * r;
+                __syncthreads();               // every thread has read vn1 / vn2 of this column
+                if (tid == 0) {
+                    if (temp2 <= tol3z) { const double nv = (j + 1 < d) ? sqrt(ss) : 0.0; vn1[c] = nv; vn2[c] = nv; }
+                    else vn1[c] = n1 * sqrt(temp);
+                }
+            }
+        }
+    }
+}
+
 template <typename T>
 __global__ void iota_i64_kernel(int64_t n, int64_t* p, int64_t base) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] = base + i;
@@ -670,11 +727,16 @@ int qr_small(Ctx* ctx, bool pivot, int64_t d, int64_t n, T* A, int64_t lda, int6
         colnorm_kernel<T><<<(unsigned)std::min<int64_t>((n + 7) / 8, (int64_t)ctx->num_sms * 8), 256, 0, ctx->stream>>>(d, n, A, lda, vn1, vn2);
     }
     const int head_threads = d >= 2048 ? 1024 : (d >= 512 ? 512 : 256);
+    static const bool warp_apply_env = getenv("RLB200_QR_WARP_APPLY") != nullptr;      // timing switch: the one-warp-per-column apply everywhere
     for (int64_t j = 0; j < kmin; ++j) {
         if (pivot) qr_head_kernel<T, true><<<1, head_threads, 0, ctx->stream>>>(d, n, j, A, lda, vn1, vn2, jpvt_dev, tau_dev, step, safmin);
         else       qr_head_kernel<T, false><<<1, head_threads, 0, ctx->stream>>>(d, n, j, A, lda, vn1, vn2, jpvt_dev, tau_dev, step, safmin);
         const int64_t rem = n - j - 1;
-        if (rem > 0) {
+        if (rem > 0 && d - j >= 4096 && !warp_apply_env) {
+            const unsigned nbk = (unsigned)std::min<int64_t>(rem, (int64_t)ctx->num_sms * 8);
+            if (pivot) qr_apply_block_kernel<T, true><<<nbk, 256, 0, ctx->stream>>>(d, n, j, A, lda, vn1, vn2, step, tol3z);
+            else       qr_apply_block_kernel<T, false><<<nbk, 256, 0, ctx->stream>>>(d, n, j, A, lda, vn1, vn2, step, tol3z);
+        } else if (rem > 0) {
             const unsigned nb = (unsigned)std::min<int64_t>((rem + 7) / 8, (int64_t)ctx->num_sms * 8);
             if (pivot) qr_apply_kernel<T, true><<<nb, 256, 0, ctx->stream>>>(d, n, j, A, lda, vn1, vn2, step, tol3z);
             else       qr_apply_kernel<T, false><<<nb, 256, 0, ctx->stream>>>(d, n, j, A, lda, vn1, vn2, step, tol3z);
