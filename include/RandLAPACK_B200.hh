@@ -798,4 +798,92 @@ private:
     DenseLinOp<T> op_;
 };
 
+#ifdef RLB200_WITH_RANDLAPACK
+// ---------------------------------------------------------------------------------------------------------------------
+// RandBLAS::sketch_general (RandBLAS/RandBLAS/skge.hh:859-960 left, :1031-1131 right) with the reference's argument lists: the sketching
+// operator object is only read for its distribution and seed state - the device regenerates it - so nothing but A and B crosses PCIe
+// (sketch_general: HOST pointers, copies inside, the drop-in form) or nothing at all (sketch_general_dev: DEVICE pointers).
+// Dense operators: every layout / transposition flag.  Sparse operators: short-axis with every flag (op(S) wide), long-axis wide operators
+// from the left with ColMajor / NoTrans / NoTrans.  S.next_state is what the reference computed at construction; it is not touched.
+// ---------------------------------------------------------------------------------------------------------------------
+namespace detail {
+inline int layout_code(blas::Layout l) { return l == blas::Layout::ColMajor ? RLB200_LAYOUT_COLMAJOR : RLB200_LAYOUT_ROWMAJOR; }
+inline int64_t buf_len(blas::Layout l, int64_t rows, int64_t cols, int64_t ld) { return l == blas::Layout::ColMajor ? ld * cols : rows * ld; }
+template <typename T> struct skabi;
+template <> struct skabi<double> {
+    static constexpr auto dl = rlb200_sketch_general_dense_left_f64_dev; static constexpr auto dr = rlb200_sketch_general_dense_right_f64_dev;
+    static constexpr auto sl = rlb200_sketch_general_sparse_left_f64_dev; static constexpr auto sr = rlb200_sketch_general_sparse_right_f64_dev;
+    static constexpr auto laso = rlb200_sketch_sparse_left_laso_f64_dev;
+};
+template <> struct skabi<float> {
+    static constexpr auto dl = rlb200_sketch_general_dense_left_f32_dev; static constexpr auto dr = rlb200_sketch_general_dense_right_f32_dev;
+    static constexpr auto sl = rlb200_sketch_general_sparse_left_f32_dev; static constexpr auto sr = rlb200_sketch_general_sparse_right_f32_dev;
+    static constexpr auto laso = rlb200_sketch_sparse_left_laso_f32_dev;
+};
+}  // namespace detail
+
+// B(d x n) = alpha * op(submat(S)) * op(A) + beta * B, DEVICE A and B
+template <typename T>
+void sketch_general_dev(Context& c, blas::Layout layout, blas::Op opS, blas::Op opA, int64_t d, int64_t n, int64_t m, T alpha,
+                        const RandBLAS::DenseSkOp<T, r123::Philox4x32>& S, int64_t ro_s, int64_t co_s, const T* A_dev, int64_t lda, T beta, T* B_dev, int64_t ldb) {
+    uint32_t w[6]; state_to_words(S.seed_state, w);
+    const int fam = S.dist.family == RandBLAS::ScalarDist::Uniform ? RLB200_FAMILY_UNIFORM : RLB200_FAMILY_GAUSSIAN;
+    const int ax = S.dist.major_axis == RandBLAS::Axis::Short ? RLB200_AXIS_SHORT : RLB200_AXIS_LONG;
+    c.check(detail::skabi<T>::dl(c.get(), detail::layout_code(layout), op_code(opS), op_code(opA), d, n, m, alpha, S.dist.n_rows, S.dist.n_cols, fam, ax,
+                                 ro_s, co_s, A_dev, lda, beta, B_dev, ldb, w));
+}
+template <typename T>
+void sketch_general_dev(Context& c, blas::Layout layout, blas::Op opS, blas::Op opA, int64_t d, int64_t n, int64_t m, T alpha,
+                        const RandBLAS::SparseSkOp<T, r123::Philox4x32>& S, int64_t ro_s, int64_t co_s, const T* A_dev, int64_t lda, T beta, T* B_dev, int64_t ldb) {
+    uint32_t w[6]; state_to_words(S.seed_state, w);
+    if (S.dist.major_axis == RandBLAS::Axis::Long) {
+        if (layout != blas::Layout::ColMajor || op_code(opS) || op_code(opA))
+            throw Error(RLB200_ERR_UNSUPPORTED, "rlb200::sketch_general: long-axis sparse operators with ColMajor / NoTrans / NoTrans only");
+        c.check(detail::skabi<T>::laso(c.get(), S.dist.n_rows, S.dist.n_cols, S.dist.vec_nnz, d, n, m, alpha, ro_s, co_s, A_dev, lda, beta, B_dev, ldb, w));
+        return;
+    }
+    c.check(detail::skabi<T>::sl(c.get(), detail::layout_code(layout), op_code(opS), op_code(opA), d, n, m, alpha, S.dist.n_rows, S.dist.n_cols,
+                                 S.dist.vec_nnz, ro_s, co_s, A_dev, lda, beta, B_dev, ldb, w));
+}
+// B(m x d) = alpha * op(A) * op(submat(S)) + beta * B, DEVICE A and B
+template <typename T>
+void sketch_general_dev(Context& c, blas::Layout layout, blas::Op opA, blas::Op opS, int64_t m, int64_t d, int64_t n, T alpha, const T* A_dev, int64_t lda,
+                        const RandBLAS::DenseSkOp<T, r123::Philox4x32>& S, int64_t ro_s, int64_t co_s, T beta, T* B_dev, int64_t ldb) {
+    uint32_t w[6]; state_to_words(S.seed_state, w);
+    const int fam = S.dist.family == RandBLAS::ScalarDist::Uniform ? RLB200_FAMILY_UNIFORM : RLB200_FAMILY_GAUSSIAN;
+    const int ax = S.dist.major_axis == RandBLAS::Axis::Short ? RLB200_AXIS_SHORT : RLB200_AXIS_LONG;
+    c.check(detail::skabi<T>::dr(c.get(), detail::layout_code(layout), op_code(opA), op_code(opS), m, d, n, alpha, A_dev, lda, S.dist.n_rows, S.dist.n_cols,
+                                 fam, ax, ro_s, co_s, beta, B_dev, ldb, w));
+}
+template <typename T>
+void sketch_general_dev(Context& c, blas::Layout layout, blas::Op opA, blas::Op opS, int64_t m, int64_t d, int64_t n, T alpha, const T* A_dev, int64_t lda,
+                        const RandBLAS::SparseSkOp<T, r123::Philox4x32>& S, int64_t ro_s, int64_t co_s, T beta, T* B_dev, int64_t ldb) {
+    if (S.dist.major_axis == RandBLAS::Axis::Long) throw Error(RLB200_ERR_UNSUPPORTED, "rlb200::sketch_general: long-axis sparse operators from the left only");
+    uint32_t w[6]; state_to_words(S.seed_state, w);
+    c.check(detail::skabi<T>::sr(c.get(), detail::layout_code(layout), op_code(opA), op_code(opS), m, d, n, alpha, A_dev, lda, S.dist.n_rows, S.dist.n_cols,
+                                 S.dist.vec_nnz, ro_s, co_s, beta, B_dev, ldb, w));
+}
+// HOST pointers: RandBLAS::sketch_general's own signatures (left: skge.hh:859-905 / 907-960; right: :1031-1076 / 1078-1131)
+template <typename T, typename SKOP>
+void sketch_general(blas::Layout layout, blas::Op opS, blas::Op opA, int64_t d, int64_t n, int64_t m, T alpha, const SKOP& S, int64_t ro_s, int64_t co_s,
+                    const T* A, int64_t lda, T beta, T* B, int64_t ldb) {
+    Context& c = default_context();
+    const int64_t ra = op_code(opA) ? n : m, ca = op_code(opA) ? m : n;
+    const int64_t la = detail::buf_len(layout, ra, ca, lda), lb = detail::buf_len(layout, d, n, ldb);
+    detail::DevBuf<T> dA(c, std::max<int64_t>(la, 1), la > 0 ? A : nullptr), dB(c, std::max<int64_t>(lb, 1), lb > 0 ? B : nullptr);
+    sketch_general_dev<T>(c, layout, opS, opA, d, n, m, alpha, S, ro_s, co_s, dA.ptr(), lda, beta, dB.ptr(), ldb);
+    if (lb > 0) dB.to_host(B, lb);
+}
+template <typename T, typename SKOP>
+void sketch_general(blas::Layout layout, blas::Op opA, blas::Op opS, int64_t m, int64_t d, int64_t n, T alpha, const T* A, int64_t lda, const SKOP& S,
+                    int64_t ro_s, int64_t co_s, T beta, T* B, int64_t ldb) {
+    Context& c = default_context();
+    const int64_t ra = op_code(opA) ? n : m, ca = op_code(opA) ? m : n;
+    const int64_t la = detail::buf_len(layout, ra, ca, lda), lb = detail::buf_len(layout, m, d, ldb);
+    detail::DevBuf<T> dA(c, std::max<int64_t>(la, 1), la > 0 ? A : nullptr), dB(c, std::max<int64_t>(lb, 1), lb > 0 ? B : nullptr);
+    sketch_general_dev<T>(c, layout, opA, opS, m, d, n, alpha, dA.ptr(), lda, S, ro_s, co_s, beta, dB.ptr(), ldb);
+    if (lb > 0) dB.to_host(B, lb);
+}
+#endif
+
 }  // namespace rlb200

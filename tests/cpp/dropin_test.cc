@@ -390,6 +390,74 @@ int main() {
         fails += !(rc0 == 0 && rc1 == 0 && rs0 == rs1 && rq[0][0] == rq[0][1] && rq[1][0] == rq[1][1] && sq[0][0] == sq[0][1] && sq[1][0] == sq[1][1] &&
                    d_chol <= 1e-11 && d_s3 <= 1e-11 && d_cq[0] <= 1e-11 && d_cq[1] <= 1e-9 && Ad.n_products >= 8);
     }
+    {
+        // RandBLAS::sketch_general and rlb200::sketch_general, same argument lists (host pointers): dense and sparse operators, left and right,
+        // a RowMajor / transposed combination each, and a long-axis (LASO) operator
+        const int64_t ms = 700, ns = 40, ds = 24;
+        std::vector<double> As(ms * ns), B0, B1;
+        std::mt19937_64 g2(11);
+        std::normal_distribution<double> nd2;
+        for (auto& v : As) v = nd2(g2);
+        auto maxdiff = [&](const std::vector<double>& X, const std::vector<double>& Y) {
+            double dmax = 0, smax = 0;
+            for (size_t i = 0; i < X.size(); ++i) { dmax = std::max(dmax, std::abs(X[i] - Y[i])); smax = std::max(smax, std::abs(X[i])); }
+            return dmax / smax;
+        };
+        double e[6];
+        {   // dense, left, ColMajor, NoTrans / NoTrans with offsets
+            RandBLAS::DenseDist D(ds + 2, ms + 3);
+            RandBLAS::DenseSkOp<double, RNG> S(D, RandBLAS::RNGState<RNG>(3));
+            B0.assign(ds * ns, 0.5); B1 = B0;
+            RandBLAS::sketch_general(blas::Layout::ColMajor, blas::Op::NoTrans, blas::Op::NoTrans, ds, ns, ms, 1.5, S, 1, 2, As.data(), ms, -0.5, B0.data(), ds);
+            rlb200::sketch_general(blas::Layout::ColMajor, blas::Op::NoTrans, blas::Op::NoTrans, ds, ns, ms, 1.5, S, 1, 2, As.data(), ms, -0.5, B1.data(), ds);
+            e[0] = maxdiff(B0, B1);
+        }
+        {   // dense, left, RowMajor, opS = Trans (S is (m x d)), A given as the RowMajor m x n array = the same buffer read as ColMajor n x m
+            RandBLAS::DenseDist D(ns + 1, ds + 1);      // here the data matrix is As read as RowMajor (ns x ms)... contraction over ns
+            RandBLAS::DenseSkOp<double, RNG> S(D, RandBLAS::RNGState<RNG>(4));
+            B0.assign(ds * ms, 0.25); B1 = B0;
+            // B (ds x ms, RowMajor) = S[0:ns, 0:ds]^T (ds x ns) * A (ns x ms, RowMajor)
+            RandBLAS::sketch_general(blas::Layout::RowMajor, blas::Op::Trans, blas::Op::NoTrans, ds, ms, ns, 1.0, S, 0, 0, As.data(), ms, 2.0, B0.data(), ms);
+            rlb200::sketch_general(blas::Layout::RowMajor, blas::Op::Trans, blas::Op::NoTrans, ds, ms, ns, 1.0, S, 0, 0, As.data(), ms, 2.0, B1.data(), ms);
+            e[1] = maxdiff(B0, B1);
+        }
+        {   // dense, right: B (ms x ds) = A (ms x ns) * S (ns x ds)
+            RandBLAS::DenseDist D(ns, ds);
+            RandBLAS::DenseSkOp<double, RNG> S(D, RandBLAS::RNGState<RNG>(5));
+            B0.assign(ms * ds, 0.0); B1 = B0;
+            RandBLAS::sketch_general(blas::Layout::ColMajor, blas::Op::NoTrans, blas::Op::NoTrans, ms, ds, ns, 1.0, As.data(), ms, S, 0, 0, 0.0, B0.data(), ms);
+            rlb200::sketch_general(blas::Layout::ColMajor, blas::Op::NoTrans, blas::Op::NoTrans, ms, ds, ns, 1.0, As.data(), ms, S, 0, 0, 0.0, B1.data(), ms);
+            e[2] = maxdiff(B0, B1);
+        }
+        {   // sparse (SASO), left, ColMajor
+            RandBLAS::SparseDist D(ds, ms, 3);
+            RandBLAS::SparseSkOp<double, RNG> S(D, RandBLAS::RNGState<RNG>(6));
+            B0.assign(ds * ns, 1.0); B1 = B0;
+            RandBLAS::sketch_general(blas::Layout::ColMajor, blas::Op::NoTrans, blas::Op::NoTrans, ds, ns, ms, 1.0, S, 0, 0, As.data(), ms, 1.0, B0.data(), ds);
+            rlb200::sketch_general(blas::Layout::ColMajor, blas::Op::NoTrans, blas::Op::NoTrans, ds, ns, ms, 1.0, S, 0, 0, As.data(), ms, 1.0, B1.data(), ds);
+            e[3] = maxdiff(B0, B1);
+        }
+        {   // sparse (SASO), right with a tall operator, RowMajor: B (ms x ds) = A (ms x ns) S (ns x ds), everything RowMajor
+            RandBLAS::SparseDist D(ns, ds, 2);
+            RandBLAS::SparseSkOp<double, RNG> S(D, RandBLAS::RNGState<RNG>(7));
+            B0.assign(ms * ds, 0.0); B1 = B0;
+            RandBLAS::sketch_general(blas::Layout::RowMajor, blas::Op::NoTrans, blas::Op::NoTrans, ms, ds, ns, 1.0, As.data(), ns, S, 0, 0, 0.0, B0.data(), ds);
+            rlb200::sketch_general(blas::Layout::RowMajor, blas::Op::NoTrans, blas::Op::NoTrans, ms, ds, ns, 1.0, As.data(), ns, S, 0, 0, 0.0, B1.data(), ds);
+            e[4] = maxdiff(B0, B1);
+        }
+        {   // sparse, long-axis (LASO), left
+            RandBLAS::SparseDist D(ds, ms, 8, RandBLAS::Axis::Long);
+            RandBLAS::SparseSkOp<double, RNG> S(D, RandBLAS::RNGState<RNG>(8));
+            B0.assign(ds * ns, 0.0); B1 = B0;
+            RandBLAS::sketch_general(blas::Layout::ColMajor, blas::Op::NoTrans, blas::Op::NoTrans, ds, ns, ms, 1.0, S, 0, 0, As.data(), ms, 0.0, B0.data(), ds);
+            rlb200::sketch_general(blas::Layout::ColMajor, blas::Op::NoTrans, blas::Op::NoTrans, ds, ns, ms, 1.0, S, 0, 0, As.data(), ms, 0.0, B1.data(), ds);
+            e[5] = maxdiff(B0, B1);
+        }
+        std::printf("with-ref sketch_general (RandBLAS vs rlb200, same arguments): dense left %.2e  dense RowMajor/opS=T %.2e  dense right %.2e  saso left %.2e"
+                    "  saso right RowMajor %.2e  laso left %.2e\n", e[0], e[1], e[2], e[3], e[4], e[5]);
+        // dense: the device's Gaussians are within a few float ulps of the host libm's (2e-6); sparse: +-1 / sqrt(count) entries, exact up to summation order
+        fails += !(e[0] <= 2e-6 && e[1] <= 2e-6 && e[2] <= 2e-6 && e[3] <= 1e-13 && e[4] <= 1e-13 && e[5] <= 1e-13);
+    }
 #endif
     std::printf(fails ? "DROPIN_FAIL\n" : "DROPIN_OK\n");
     return fails;
