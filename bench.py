@@ -405,11 +405,38 @@ def run_secondary(args):
                "roofline": roof,
                "config": {"workload": f"BQRRP of a {m} x {n} {args.dtype} Gaussian matrix, b={b}, d_factor={args.d_factor}, luqr + cholqr/orhr_col "
                                       "panels + compact-WY update (configs[3])"}}
+    elif wl == "hqrrp":
+        # RandLAPACK::hqrrp (rl_hqrrp.hh:811) on a tall Gaussian matrix: nb_alg = --block, pp = nb_alg / 8, CholQR + Householder-reconstruction
+        # panels (qr_type 2) unless --hqrrp-panel says otherwise.  SURVEY 8(f) row 2; not one of BASELINE.json's configs.
+        m = args.m if args.m != (1 << 24) else 32768
+        n = args.n if args.n != 1024 else 4096
+        dtype = torch.float32 if args.dtype == "f32" else torch.float64
+        nb, pp = args.block if args.block != 256 else 128, max(1, (args.block if args.block != 256 else 128) // 8)
+        piv, qt = {"cholqr": (0, 2), "geqrf": (0, 1), "pivoted": (1, 0)}[args.hqrrp_panel]
+        A = rl.empty_f(m, n, dtype, dev)
+        fn = fill32 if dtype == torch.float32 else fill64
+        tau = torch.zeros(n, dtype=dtype, device=dev)
+        J = torch.zeros(n, dtype=torch.int64, device=dev)
+
+        def prep():
+            ctx.check(fn(ctx._h, max(m, n), min(m, n), rl.FAMILY_GAUSSIAN, rl.AXIS_LONG, rl.LAYOUT_COLMAJOR if m >= n else rl.LAYOUT_ROWMAJOR,
+                         max(m, n), min(m, n), 0, 0, A.data_ptr(), rl.RNGState(0xA5).words()))
+
+        def step():
+            rc, _, _ = rl.hqrrp(ctx, A, nb, pp, piv, qt, rl.RNGState(0), tau=tau, J=J)
+            assert rc == 0, rc
+        ms = timed(step, prep, args.steps, args.warmup)
+        fl = 2.0 * m * n * n - 2.0 / 3.0 * n ** 3 + 2.0 * (nb + pp) * m * n
+        peak, src, _ = measured_fp64_peak()
+        roof = {"bound": "tensor", "achieved": fl / ms / 1e9, "peak": peak, "unit": "TFLOP/s", "frac": fl / ms / 1e9 / peak, "traffic": None,
+                "peak_source": src, "note": "whole step against the fp64 pipe; the trailing updates of blocks with >= 8192 rows below them run on the int8 engine"}
+        out = {"metric": "hqrrp_gflops", "value": fl / ms / 1e6, "unit": "Gflop/s", "ms_per_step": ms, "roofline": roof,
+               "config": {"workload": f"hqrrp of a {m} x {n} {args.dtype} Gaussian matrix, nb_alg={nb}, pp={pp}, panels: {args.hqrrp_panel} (SURVEY 8f row 2)"}}
     else:
         raise SystemExit(f"unknown workload {wl}")
     clocks = sampler.stop()
     # per-class CUDA-event times of one extra, untimed step
-    if wl in ("cqrrpt", "bqrrp"):
+    if wl in ("cqrrpt", "bqrrp", "hqrrp"):
         names = ["gemm_nn", "gemm_tn", "rightmul", "small", "fill", "sketch", "factor", "i8_mma_nn", "i8_mma_tn", "i8_slice"]
         ctx.timers_enable(True)
         for w in range(len(names)):
@@ -422,7 +449,7 @@ def run_secondary(args):
         out["class_ms_per_step"] = {k_: round(v[0], 3) for k_, v in tm.items() if v[1]}
         out["class_launches_per_step"] = {k_: v[1] for k_, v in tm.items() if v[1]}
     cpu = None
-    if wl in ("cqrrpt", "bqrrp") and not args.no_cpu:
+    if wl in ("cqrrpt", "bqrrp", "hqrrp") and not args.no_cpu:
         # the reference's own CPU driver (oracle/_ref/librl_ref.so = its unmodified headers over OpenBLAS) on a bounded sample of the same
         # workload, all host threads; rates are size-normalised with the same flop formula
         try:
@@ -444,6 +471,15 @@ def run_secondary(args):
                 dc = int(d_factor * nc)
                 flc = 3.0 * mc * nc * nc + mc * nc * nnz + (2.0 * dc * nc * nc - 2.0 / 3.0 * nc ** 3)
                 sample = f"{mc} x {nc} {args.dtype} rows of the same workload, RandLAPACK::CQRRPT (geqp3), {cores} threads, one run"
+            elif wl == "hqrrp":
+                mc, nc = 8192, 2048
+                Ac, _ = O.fill_dense(mc, nc, O.RNGState(0xA5), dtype=npdt)
+                Ac = np.asfortranarray(Ac)
+                t0 = time.perf_counter()
+                _ref.ref_hqrrp(Rl, Ac, nb, pp, piv, qt, [0] * 6)
+                tc = time.perf_counter() - t0
+                flc = 2.0 * mc * nc * nc - 2.0 / 3.0 * nc ** 3 + 2.0 * (nb + pp) * mc * nc
+                sample = f"{mc} x {nc} {args.dtype}, RandLAPACK::hqrrp (nb_alg={nb}, pp={pp}, panels: {args.hqrrp_panel}), {cores} threads, one run"
             else:
                 nc = 8192
                 Ac, _ = O.fill_dense(nc, nc, O.RNGState(0xA4), dtype=npdt)
@@ -476,7 +512,8 @@ def main():
     ap.add_argument("--q", type=int, default=1, help="RS passes_per_stab")
     ap.add_argument("--m-cpu", type=int, default=1 << 17, help="rows of the bounded CPU-baseline sample")
     ap.add_argument("--m-e2e", type=int, default=1 << 20, help="rows of the host-buffer (e2e) measurement")
-    ap.add_argument("--workload", default="rsvd", choices=["rsvd", "cqrrpt", "bqrrp", "sketch_sparse", "sketch_dense"])
+    ap.add_argument("--workload", default="rsvd", choices=["rsvd", "cqrrpt", "bqrrp", "hqrrp", "sketch_sparse", "sketch_dense"])
+    ap.add_argument("--hqrrp-panel", default="cholqr", choices=["cholqr", "geqrf", "pivoted"], help="hqrrp workload: the panel QR")
     ap.add_argument("--dtype", default=None, help="secondary workloads: f32 | f64")
     ap.add_argument("--d", type=int, default=4096, help="sketch rows (sketch workloads)")
     ap.add_argument("--nnz", type=int, default=1, help="SASO non-zeros per column")
@@ -497,7 +534,7 @@ def main():
     _capture_stdout()
     if args.workload != "rsvd":
         if args.dtype is None:
-            args.dtype = "f64" if args.workload == "bqrrp" else "f32"
+            args.dtype = "f64" if args.workload in ("bqrrp", "hqrrp") else "f32"
         if args.d_factor is None:
             args.d_factor = 1.0 if args.workload == "bqrrp" else 2.0
         return run_secondary(args)
