@@ -12,6 +12,7 @@
 //   RandLAPACK::RSVDalg / RSVD        drivers/rl_rsvd.hh:15-154            rlb200::RSVD<T>
 //   RandLAPACK::CQRRPTalg / CQRRPT    drivers/rl_cqrrpt.hh:20-391          rlb200::CQRRPT<T>
 //   RandLAPACK::CQRRTalg / CQRRT      drivers/rl_cqrrt.hh:20-297           rlb200::CQRRT<T>
+//   RandLAPACK::CQRRPT_GPU_alg / CQRRPT_GPU  drivers/rl_cqrrpt_gpu.hh:15-387  rlb200::CQRRPT_GPU<T>  (host pointers, as in the reference)
 //   RandLAPACK::BQRRPalg / BQRRP      drivers/rl_bqrrp.hh:19-665           rlb200::BQRRP<T>
 //   RandLAPACK::hqrrp (free function) drivers/rl_hqrrp.hh:811-1196         rlb200::hqrrp<T>
 //   RandLAPACK::BQRRP_GPU_alg / BQRRP_GPU  drivers/rl_bqrrp_gpu.hh:27-942   rlb200::BQRRP_GPU<T>   (device pointers, sketch as input)
@@ -482,6 +483,52 @@ public:
     std::vector<long> times;
     Subroutines::QRCPWide qrcp_wide;
     Subroutines::QRTall qr_tall;
+private:
+    Context* ctx_;
+};
+
+// CQRRPT_GPU (rl_cqrrpt_gpu.hh:15-387): the reference's hybrid driver - HOST pointers in and out, the O(m n^2) part on the GPU.  Same
+// constructor (verb, time_subroutines, eps), public fields and call signature; here every phase runs on the device (rlb200_cqrrpt_*_host).
+// QRCP of the sketch: geqp3 when `no_hqrrp` (the constructor default, :62), else hqrrp with nb_alg / oversampling / panel_pivoting / use_cholqr
+// (:222-226).  Define RLB200_WITH_RANDLAPACK_GPU after including the reference's header to derive from RandLAPACK::CQRRPT_GPU_alg.
+template <typename T>
+class CQRRPT_GPU
+#if defined(RLB200_WITH_RANDLAPACK) && defined(RLB200_WITH_RANDLAPACK_GPU)
+    : public RandLAPACK::CQRRPT_GPU_alg<T, r123::Philox4x32>
+#endif
+{
+public:
+    CQRRPT_GPU(bool verb, bool time_subroutines, T ep) : CQRRPT_GPU(default_context(), verb, time_subroutines, ep) {}
+    CQRRPT_GPU(Context& c, bool verb, bool time_subroutines, T ep)
+        : verbosity(verb), timing(time_subroutines), eps(ep), rank(0), num_threads(0), nnz(2), no_hqrrp(1), nb_alg(64), oversampling(10),
+          panel_pivoting(1), use_cholqr(0), ctx_(&c) {}
+    virtual ~CQRRPT_GPU() {}
+    int call(int64_t m, int64_t n, T* A, int64_t lda, T* R, int64_t ldr, int64_t* J, T d_factor, state_t& state)
+#if defined(RLB200_WITH_RANDLAPACK) && defined(RLB200_WITH_RANDLAPACK_GPU)
+        override
+#endif
+    {
+        uint32_t w[6]; state_to_words(state, w);
+        int64_t r = 0;
+        if (timing) ctx_->phase_timing(true);
+        ctx_->check(rlb200_set_cqrrpt_qrcp(ctx_->get(), no_hqrrp ? RLB200_CQRRPT_QRCP_GEQP3 : RLB200_CQRRPT_QRCP_HQRRP));
+        ctx_->check(rlb200_set_cqrrpt_orthogonalization(ctx_->get(), 0));
+        ctx_->check(rlb200_set_cqrrpt_hqrrp_opts(ctx_->get(), nb_alg, oversampling, (int)panel_pivoting, (int)use_cholqr));
+        int rc = ctx_->check(detail::abi<T>::cqrrpt_host(ctx_->get(), m, n, A, lda, R, ldr, J, d_factor, eps, nnz, &r, w));
+        if (timing) { times = ctx_->phase_times(); ctx_->phase_timing(false); }
+        words_to_state(w, state);
+        rank = r;
+        return rc;
+    }
+    bool verbosity;
+    bool timing;
+    T eps;
+    int64_t rank;
+    std::vector<long> times;   // 8 entries when `timing` (rl_cqrrpt_gpu.hh:133-134)
+    int num_threads;           // SASO tuning knob of the CPU sketch (:137); unused here
+    int64_t nnz;
+    int no_hqrrp;              // :141
+    int64_t nb_alg, oversampling, panel_pivoting, use_cholqr;
 private:
     Context* ctx_;
 };

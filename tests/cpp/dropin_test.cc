@@ -130,6 +130,18 @@ int main() {
         double eq2 = orth_err(m, cqh.rank, Aq2.data());
         std::printf("standalone CQRRPT(qrcp = hqrrp): rc=%d rank=%lld ||Q'Q-I||=%.2e\n", rcq2, (long long)cqh.rank, eq2);
         fails += !(rcq2 == 0 && cqh.rank >= k && cqh.rank <= n && eq2 <= 1e-9);
+        // CQRRPT_GPU's interface (rl_cqrrpt_gpu.hh:43-149): (verb, time_subroutines, eps), no_hqrrp switches geqp3 / hqrrp; same results as CQRRPT
+        std::vector<double> Aq3 = A, Rq3(n * n, 0.0);
+        std::vector<int64_t> Jq3(n);
+        rlb200::CQRRPT_GPU<double> cqg(false, true, std::pow(std::numeric_limits<double>::epsilon(), 0.85));
+        cqg.no_hqrrp = 0; cqg.nb_alg = 16; cqg.oversampling = 4;
+        rlb200::RNGState st5(0);
+        int rcq3 = cqg.call(m, n, Aq3.data(), m, Rq3.data(), n, Jq3.data(), 2.0, st5);
+        double dq = 0;
+        for (int64_t i = 0; i < m * n; ++i) dq = std::max(dq, std::abs(Aq3[i] - Aq2[i]));
+        std::printf("standalone CQRRPT_GPU(no_hqrrp = 0): rc=%d rank=%lld  max|Q - Q(CQRRPT, qrcp = hqrrp)| %.2e  J equal %d  times %zu\n", rcq3,
+                    (long long)cqg.rank, dq, (int)(Jq3 == Jq), cqg.times.size());
+        fails += !(rcq3 == 0 && cqg.rank == cqh.rank && dq <= 1e-12 && Jq3 == Jq && cqg.times.size() == 8 && st5.counter[0] == st4.counter[0]);
     }
     {
         // REVD2 on a planted PSD matrix of rank 12, only the lower triangle valid (test/drivers/test_revd2.cc: Uplo)
