@@ -164,7 +164,10 @@ RLB200_API int rlb200_fill_dense_f32_dev(rlb200_ctx* ctx, int64_t n_rows, int64_
  * SparseDist(n_rows, n_cols, vec_nnz, major_axis) defined by `state`, in the reference's order (one long-axis vector after the
  * other, short-axis indices ascending within a vector).  *nnz_out (HOST) receives the number of triplets; with NULL output
  * arrays only the size bound vec_nnz * (#long-axis vectors) is returned and `state` is untouched (the reference's size query).
- * state <- the reference's returned state (counter after the last sampled vector).  Axis::Short only (SASO; the default). */
+ * state <- the reference's returned state (counter after the last sampled vector).  major_axis = RLB200_AXIS_SHORT (SASO, the default:
+ * vec_nnz distinct short-axis indices per long-axis position, values +-1) or RLB200_AXIS_LONG (LASO, :669-704: each of the min(n_rows, n_cols)
+ * long-axis vectors draws vec_nnz indices with replacement, duplicates merged into sqrt(count) * first sign, long-axis indices ascending
+ * within a vector; the triplet count after merging is only known after the call). */
 RLB200_API int rlb200_fill_sparse_f64_dev(rlb200_ctx* ctx, int64_t n_rows, int64_t n_cols, int64_t vec_nnz, int major_axis,
                                int64_t sub_rows, int64_t sub_cols, int64_t ro, int64_t co, int64_t* nnz_out, double* vals_dev,
                                int64_t* rows_dev, int64_t* cols_dev, uint32_t state[6]);
