@@ -190,3 +190,23 @@ def test_cqrrpt_qrcp_hqrrp(shape):
         assert np.abs(np.triu(Rm) - np.triu(R2)).max() <= 1e-12 * np.abs(Rm).max()
     e = qr_invariants(A, Q2, R2, J2, alg.rank)
     assert alg.rank == n and max(e) <= np.finfo(np.float64).eps ** 0.75
+
+
+@pytest.mark.skipif(_ref.ref_lib() is None, reason="compiled reference not present")
+def test_cqrrpt_qrcp_hqrrp_reference_test_shape():
+    """The reference's own CQRRPT-with-HQRRP case (test/drivers/test_cqrrpt.cc:184-304: 10000 x 200, rank 100, d_factor 2): the restatement
+    against the compiled reference.  Rank and RNG state exact; the pivots are defined up to the last complete HQRRP block below the rank
+    (nb_alg = 64: past it the sketch's columns are round-off), R's leading block to 1e-10."""
+    L = _ref.ref_lib()
+    m, n, rk = 10000, 200, 100
+    A, st = O.gen_poly_mat(m, n, rk, 2.0, 2.0, O.RNGState(0))
+    eps = float(np.finfo(np.float64).eps) ** 0.85
+    rc, rank, Q, Rm, J, st2 = _ref.ref_cqrrpt(L, A, 2.0, list(st.words()), eps, 2, qrcp=2)
+    alg = O.CQRRPT(eps, 2)
+    alg.qrcp = "hqrrp"
+    rc2, Q2, R2, J2, st3 = alg.call(A, 2.0, st)
+    assert (rc, rank) == (rc2, alg.rank) == (0, rk) and list(st3.words()) == st2
+    assert np.array_equal(J[:64], J2[:64])
+    assert np.abs(np.triu(Rm[:64, :64]) - np.triu(R2[:64, :64])).max() <= 1e-10 * np.abs(Rm).max()
+    e = qr_invariants(A, Q2, R2, J2, alg.rank)
+    assert max(e) <= np.finfo(np.float64).eps ** 0.75, e
